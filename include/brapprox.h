@@ -1,0 +1,172 @@
+/* libbrapprox -- C ABI of the B200-native sketch-then-factor path.
+ *
+ * This header is the drop-in boundary for LowRankApprox.jl's hot path
+ * (reference citations are into /root/reference/).  The reference has no
+ * plugin interface; its only FFI is the Fortran-style `ccall` into LAPACK
+ * (src/lapack.jl:117-139).  The seams replaced here are the Julia-level
+ * internal functions
+ *     sketch_*(side, trans, A, order, opts) -> B      src/sketch.jl:114,298,530,659
+ *     geqp3_adap!(B, opts) -> (p, tau, k)             src/pqr.jl:348
+ *     pqrback_postproc(B, p, tau, k, opts)            src/pqr.jl:420
+ *     sketchfact(side, trans, A, opts)                src/sketch.jl:52
+ *     idfact / pqrfact / psvdfact                     src/id.jl:434, src/pqr.jl:290, src/psvd.jl:238
+ *
+ * Conventions (same as the reference's LAPACK calls): FP64 real, column-major,
+ * explicit leading dimensions, int64 dimensions, 1-based index outputs
+ * (Julia `Vector{Int}`).  Every pointer argument may be a HOST or a DEVICE
+ * pointer (detected with cudaPointerGetAttributes); device-resident inputs are
+ * the benchmarked mode.  Every function returns an int status: 0 ok, <0 the
+ * number of the invalid argument (LAPACK `info` style), >0 a BRA_ERR_* code;
+ * nothing throws or aborts.  There is NO CPU fallback: without a usable B200
+ * the calls fail with BRA_ERR_CUDA.
+ *
+ * A context owns one device, one stream and all workspaces; it is not
+ * thread-safe, distinct contexts are independent.
+ */
+#ifndef BRAPPROX_H
+#define BRAPPROX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BRA_OK 0
+#define BRA_ERR_CUDA 1          /* CUDA runtime/driver failure; see bra_last_error */
+#define BRA_ERR_UNSUPPORTED 2   /* option combination not built (caller may route to the reference) */
+#define BRA_ERR_ROUNDS 3        /* adaptive loop needed more rounds than random inputs supplied */
+#define BRA_ERR_INTERNAL 4      /* kernel-side failure (exchange timeout etc.) */
+#define BRA_ERR_NOTREADY 5      /* bra_fetch of a factor the last call did not produce */
+
+#define BRA_MAX_ROUNDS 24
+
+/* opts.sketch (src/LowRankApprox.jl:137-138) */
+#define BRA_SKETCH_NONE 0
+#define BRA_SKETCH_RANDN 1
+#define BRA_SKETCH_SPRN 2
+#define BRA_SKETCH_SRFT 3
+#define BRA_SKETCH_SUB 4
+
+/* opts.retval_mask: the q/r/t substring tests of pqrfact_retval (src/pqr.jl:423-425) */
+#define BRA_RET_Q 1
+#define BRA_RET_R 2
+#define BRA_RET_T 4
+
+/* bra_fetch selectors */
+#define BRA_F_P 1        /* int64[n]   pivot permutation p, 1-based (sk = p[0:k], rd = p[k:n]) */
+#define BRA_F_T 2        /* double k x (n-k)   interpolation matrix, ld = k */
+#define BRA_F_Q 3        /* double m x k       pqrfact Q, ld = m */
+#define BRA_F_R 4        /* double k x n       pqrfact R = [R1 | R1 T], ld = k */
+#define BRA_F_U 5        /* double m x ksvd    psvdfact U, ld = m */
+#define BRA_F_S 6        /* double[ksvd]       psvdfact singular values */
+#define BRA_F_VT 7       /* double ksvd x n    psvdfact Vt, ld = ksvd */
+#define BRA_F_TAU 8      /* double[k]          Householder scalars of the last QRCP */
+#define BRA_F_BSKETCH 9  /* double l x n       last sketch after QRCP, LAPACK layout, ld = l */
+
+typedef struct bra_ctx bra_ctx;
+
+/* POD mirror of LRAOptions' hot-path fields (src/LowRankApprox.jl:77-119).  The
+ * three *_samp closures cannot cross a C ABI: the shim evaluates them into the
+ * affine pair (samp_a, samp_b), order = samp_a*n + samp_b, or passes explicit
+ * per-round orders in bra_rand.orders. */
+typedef struct bra_opts {
+  double atol;               /* >= 0 */
+  double rtol;               /* >= 0; default 5*eps */
+  int64_t rank;              /* < 0: unbounded */
+  int64_t nb;                /* QRCP block size and first adaptive rank guess; default 32 */
+  int32_t sketch;            /* BRA_SKETCH_* */
+  int32_t sketch_randn_niter;/* must be 0 in this build */
+  int32_t sketchfact_adap;   /* default 1 */
+  int32_t retval_mask;       /* BRA_RET_* */
+  double maxdet_tol;         /* must be < 0 in this build */
+  int64_t maxdet_niter;
+  int64_t samp_a, samp_b;    /* 0,0 = the reference default for opts.sketch */
+  uint64_t seed;             /* fast mode: Philox key */
+  int32_t verb;
+  int32_t reserved;
+} bra_opts;
+
+/* Per-round random inputs in the order the reference draws them (SURVEY.md
+ * Appendix D).  n_rounds == 0 selects the fast mode (device Philox keyed by
+ * opts.seed and the round).  Round t uses:
+ *   randn: omega[t]  order_t x mA  col-major (ld = order_t)     src/util.jl:4
+ *   srft:  d[t] (+-1, length mA), idx[t] (int64, 1-based, length order_t)   src/sketch.jl:339-361
+ *   sprn:  perm[t] (int64, 1-based randperm(mA)), s[t] (length mA)          src/sketch.jl:575-579
+ *   sub:   r[t] (int64, 1-based, length order_t)                            src/sketch.jl:252
+ * where mA is the contracted dimension of op(A). */
+typedef struct bra_rand {
+  int32_t n_rounds;
+  int32_t reserved;
+  const double* const* omega;
+  const double* const* d;
+  const int64_t* const* idx;
+  const int64_t* const* perm;
+  const double* const* s;
+  const int64_t* const* r;
+} bra_rand;
+
+typedef struct bra_info {
+  int64_t m, n;              /* dims of op(A) */
+  int64_t k;                 /* ID rank */
+  int64_t ksvd;              /* psvd rank (0 unless psvdfact) */
+  int32_t rounds;
+  int32_t reserved;
+  int64_t orders[BRA_MAX_ROUNDS];
+  int64_t ks[BRA_MAX_ROUNDS];
+  int64_t steps[BRA_MAX_ROUNDS];   /* pivot steps executed per round (>= ks: blocks run to their end) */
+} bra_info;
+
+/* ---- context ----------------------------------------------------------- */
+int bra_version(void);
+int bra_create(bra_ctx** ctx, int device);
+int bra_destroy(bra_ctx* ctx);
+const char* bra_last_error(bra_ctx* ctx);
+void bra_opts_default(bra_opts* opts);           /* LRAOptions(Float64), src/LowRankApprox.jl:96-119 */
+int bra_chkopts(bra_ctx* ctx, const bra_opts* o); /* chkopts!, src/LowRankApprox.jl:133-141 */
+uint64_t bra_launch_count(bra_ctx* ctx);         /* kernels launched so far by this ctx */
+int bra_sync(bra_ctx* ctx);
+void* bra_stream(bra_ctx* ctx);                  /* the ctx's cudaStream_t */
+
+/* ---- stage-wise entry points (parity tests feed each the oracle's input) -- */
+
+/* sketch_randn(:left, trans, A, order) = Omega * op(A)   (src/sketch.jl:129-151)
+ * trans = 'n': A is m x n, Omega order x m, B order x n.
+ * trans = 'c': B = Omega * A', Omega order x n, B order x m. */
+int bra_sketch_randn_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A, int64_t lda,
+                         int64_t order, const double* Omega, int64_t ldo, double* B, int64_t ldb);
+
+/* geqp3_adap!(B, opts) (src/pqr.jl:348-418) on an l x n matrix B, in place:
+ * on return B holds R in its upper triangle and the reflectors below (LAPACK
+ * layout, columns permuted), jpvt (1-based) the permutation, tau[0:kcap] the
+ * scalars, *k the detected rank, *nsteps the pivot steps executed (blocks run
+ * to their end, src/pqr.jl:397-414).  kb_trace (optional, host or device,
+ * capacity kb_cap) receives the block lengths laqps would have returned. */
+int bra_geqp3_adap_f64(bra_ctx* ctx, int64_t l, int64_t n, double* B, int64_t ldb, const bra_opts* opts,
+                       int64_t* jpvt, double* tau, int64_t* k, int64_t* nsteps,
+                       int32_t* kb_trace, int64_t kb_cap, int64_t* n_blocks);
+
+/* maxdet_t (src/pqr.jl:438-442): T = R[:,0:k]^{-1} R[:,k:n], R is k x n upper trapezoidal. */
+int bra_trsolve_T_f64(bra_ctx* ctx, int64_t k, int64_t n, const double* R, int64_t ldr, double* T, int64_t ldt);
+
+/* ---- fused entry points -------------------------------------------------- */
+
+/* idfact(trans, A, opts) (src/id.jl:434-447): results stay in ctx-owned device
+ * buffers; read sizes with bra_get_info and copy out with bra_fetch. */
+int bra_idfact_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A, int64_t lda,
+                   const bra_opts* opts, const bra_rand* rnd);
+
+int bra_get_info(bra_ctx* ctx, bra_info* info);
+int bra_fetch(bra_ctx* ctx, int which, void* dst, int64_t ld);
+
+/* ---- diagnostics ---------------------------------------------------------- */
+/* FP64 peak probes used as roofline denominators (bench.py): a register-resident
+ * DMMA loop and a DFMA loop; returns TFLOP/s in out[0], out[1]. */
+int bra_probe_fp64_peak(bra_ctx* ctx, double* out);
+/* Average latency (microseconds) of one LL all-gather exchange across `ctas` CTAs. */
+int bra_probe_exchange_latency(bra_ctx* ctx, int ctas, int iters, double* usec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRAPPROX_H */

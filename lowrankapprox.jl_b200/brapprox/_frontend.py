@@ -1,0 +1,182 @@
+"""Front-ends with the reference's names and argument meaning, over the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _binding as B
+from ._binding import BraError, Context, DeviceMatrix, IDPackedV, LRAOptions, lib, mat_arg
+
+_default_ctx: Dict[int, Context] = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+def _trans(trans: str) -> bytes:
+    t = str(trans).lstrip(":").lower()
+    if t not in ("n", "c"):
+        raise ValueError("trans")                      # chktrans (src/LowRankApprox.jl:150)
+    return t.encode()
+
+
+def _opts(opts: Optional[LRAOptions], kw) -> LRAOptions:
+    o = (opts or LRAOptions()).copy(**kw)              # copy(opts; args...) -- kwargs win
+    o.chk()
+    return o
+
+
+class _RandPack:
+    """Marshals per-round random inputs into a bra_rand (keeps the arrays alive)."""
+
+    def __init__(self, rounds: Optional[Sequence[dict]]):
+        self.keep = []
+        self.c = B.bra_rand()
+        self.c.n_rounds = 0
+        if not rounds:
+            return
+        n = len(rounds)
+        self.c.n_rounds = n
+
+        def column(key, dtype):
+            arr = (C.c_void_p * n)()
+            any_ = False
+            for t, r in enumerate(rounds):
+                v = r.get(key)
+                if v is None:
+                    arr[t] = None
+                    continue
+                any_ = True
+                if isinstance(v, DeviceMatrix):
+                    self.keep.append(v)
+                    arr[t] = v.ptr
+                else:
+                    a = np.asfortranarray(v, dtype=dtype)
+                    self.keep.append(a)
+                    arr[t] = a.ctypes.data
+            self.keep.append(arr)
+            return C.cast(arr, B._pp_d) if any_ else None
+
+        self.c.omega = column("Omega", np.float64)
+        self.c.d = column("d", np.float64)
+        self.c.idx = column("idx", np.int64)
+        self.c.perm = column("perm", np.int64)
+        self.c.s = column("s", np.float64)
+        self.c.r = column("r", np.int64)
+
+
+def sketch(A, order: int, opts: Optional[LRAOptions] = None, side: str = "left", trans: str = "n",
+           rand: Optional[dict] = None, ctx: Optional[Context] = None, **kw) -> np.ndarray:
+    """sketch(side, trans, A, order, opts; kw...) (src/sketch.jl:35-50).  `rand` carries the random
+    inputs the reference would draw (Omega for :randn)."""
+    if str(side).lstrip(":") not in ("left", "right"):
+        raise ValueError("side")                       # sketchfact_chkargs (src/sketch.jl:80-84)
+    tr = _trans(trans)
+    if order < 0:
+        raise ValueError("order")
+    o = _opts(opts, kw)
+    if str(side).lstrip(":") == "right":
+        raise BraError(2, "side = :right is not built (SURVEY 8f-3)")
+    ctx = ctx or default_context()
+    pA, m, n, lda, keepA = mat_arg(A)
+    mA, nA = (m, n) if tr == b"n" else (n, m)
+    out = np.zeros((order, nA), order="F")
+    if o.sketch == "randn" or o.sketch == "none":
+        if rand is None or "Omega" not in rand:
+            raise ValueError("stage-wise sketch needs rand['Omega'] (order x contracted-dim)")
+        pO, lo, mo, ldo, keepO = mat_arg(rand["Omega"])
+        if (lo, mo) != (order, mA):
+            raise ValueError("DimensionMismatch: Omega")
+        ctx.check(lib.bra_sketch_randn_f64(ctx.handle, tr, m, n, pA, lda, order, pO, ldo,
+                                           C.c_void_p(out.ctypes.data), max(order, 1)))
+        return out
+    raise BraError(2, f"sketch = :{o.sketch} is not built in this revision")
+
+
+def geqp3_adap(Bm: np.ndarray, opts: Optional[LRAOptions] = None, ctx: Optional[Context] = None, **kw):
+    """geqp3_adap!(B, opts) (src/pqr.jl:348-359): returns (B_out, jpvt 1-based, tau, k, trace) where
+    B_out is the in-place result in LAPACK layout and trace = {"kb": [...], "steps": n}."""
+    o = _opts(opts, kw)
+    ctx = ctx or default_context()
+    Bw = np.array(Bm, dtype=np.float64, order="F", copy=True)
+    l, n = Bw.shape
+    lmin = min(l, n)
+    kcap = lmin if (o.rank < 0 or o.rank > lmin) else o.rank
+    jpvt = np.zeros(n, dtype=np.int64)
+    tau = np.zeros(max(kcap, 1))
+    kb = np.zeros(max(kcap + 1, 1), dtype=np.int32)
+    k, ns, nbk = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    co = o.to_c()
+    ctx.check(lib.bra_geqp3_adap_f64(ctx.handle, l, n, C.c_void_p(Bw.ctypes.data), max(l, 1), C.byref(co),
+                                     C.c_void_p(jpvt.ctypes.data), C.c_void_p(tau.ctypes.data), C.byref(k),
+                                     C.byref(ns), C.c_void_p(kb.ctypes.data), kb.size, C.byref(nbk)))
+    return Bw, jpvt, tau[:ns.value], int(k.value), {"kb": kb[:nbk.value].tolist(), "steps": int(ns.value)}
+
+
+def trsolve_T(R: np.ndarray, ctx: Optional[Context] = None) -> np.ndarray:
+    """maxdet_t(R) = R[:, :k] \\ R[:, k:] (src/pqr.jl:438-442)."""
+    ctx = ctx or default_context()
+    Rf = np.asfortranarray(R, dtype=np.float64)
+    k, n = Rf.shape
+    T = np.zeros((k, n - k), order="F")
+    ctx.check(lib.bra_trsolve_T_f64(ctx.handle, k, n, C.c_void_p(Rf.ctypes.data), max(k, 1),
+                                    C.c_void_p(T.ctypes.data), max(k, 1)))
+    return T
+
+
+def _rounds(ctx: Context):
+    inf = ctx.info()
+    r = [(int(inf.orders[t]), int(inf.ks[t])) for t in range(inf.rounds)]
+    s = [int(inf.steps[t]) for t in range(inf.rounds)]
+    return inf, r, s
+
+
+def idfact_device(A, opts: Optional[LRAOptions] = None, trans: str = "n", rand=None,
+                  ctx: Optional[Context] = None, **kw):
+    """Runs idfact and leaves every result on the device; returns the bra_info (k, rounds...)."""
+    o = _opts(opts, kw)
+    o.pqrfact_retval = "t"                              # src/id.jl:438
+    ctx = ctx or default_context()
+    pA, m, n, lda, keepA = mat_arg(A)
+    rp = _RandPack(rand)
+    co = o.to_c()
+    ctx.check(lib.bra_idfact_f64(ctx.handle, _trans(trans), m, n, pA, lda, C.byref(co), C.byref(rp.c)))
+    return ctx.info()
+
+
+def idfact(A, opts: Optional[LRAOptions] = None, trans: str = "n", rand=None,
+           ctx: Optional[Context] = None, **kw) -> IDPackedV:
+    """idfact(trans, A, opts; kw...) -> IDPackedV(sk, rd, T) (src/id.jl:434-447)."""
+    ctx = ctx or default_context()
+    idfact_device(A, opts, trans, rand, ctx, **kw)
+    inf, rounds, steps = _rounds(ctx)
+    k, n = int(inf.k), int(inf.n)
+    p = ctx.fetch(B.F_P, (n,), np.int64)
+    T = ctx.fetch(B.F_T, (k, n - k))
+    return IDPackedV(p[:k].copy(), p[k:].copy(), T, rounds, steps)
+
+
+def id(A, *args, **kw):
+    """id(...) -> (sk, rd, T) (src/id.jl:452-456)."""
+    V = idfact(A, *args, **kw)
+    return V.sk, V.rd, V.T
+
+
+def probe_fp64_peak(ctx: Optional[Context] = None) -> dict:
+    ctx = ctx or default_context()
+    out = (C.c_double * 8)()
+    ctx.check(lib.bra_probe_fp64_peak(ctx.handle, out))
+    return {"dmma_m8n8k4": out[0], "dfma": out[1], "dmma_m16n8k4": out[2], "dmma_m16n8k8": out[3],
+            "dmma_m16n8k16": out[4]}
+
+
+def probe_exchange_latency(ctas: int = 148, iters: int = 2000, ctx: Optional[Context] = None) -> float:
+    ctx = ctx or default_context()
+    us = C.c_double(0)
+    ctx.check(lib.bra_probe_exchange_latency(ctx.handle, ctas, iters, C.byref(us)))
+    return us.value

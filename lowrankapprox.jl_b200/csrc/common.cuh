@@ -1,0 +1,127 @@
+// Shared declarations for libbrapprox (B200 / sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/brapprox.h"
+
+#define BRA_CUDA(expr)                                                            \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      ctx->set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+      return BRA_ERR_CUDA;                                                        \
+    }                                                                             \
+  } while (0)
+
+#define BRA_CHECK_ARG(cond, argno, msg)                                           \
+  do {                                                                            \
+    if (!(cond)) {                                                                \
+      ctx->set_error(std::string("invalid argument ") + #argno + ": " + msg);     \
+      return -(argno);                                                            \
+    }                                                                             \
+  } while (0)
+
+// A growable device buffer owned by the context (never freed behind the caller's back).
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+// Result of the last fused factorization, resident on the device (two-phase protocol).
+struct FactResult {
+  int64_t m = 0, n = 0;        // dims of op(A)
+  int64_t k = 0;               // ID rank
+  int64_t ksvd = 0;            // psvd rank after truncation
+  int rounds = 0;
+  int64_t orders[BRA_MAX_ROUNDS];
+  int64_t ks[BRA_MAX_ROUNDS];
+  int64_t steps[BRA_MAX_ROUNDS];
+  bool have_T = false, have_Q = false, have_R = false, have_svd = false;
+};
+
+struct bra_ctx {
+  int device = 0;
+  int num_sms = 0;
+  int smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;       // kernels launched by this ctx (bench's gpu_launches)
+
+  // workspaces
+  DevBuf A_stage;              // staging for host-resident A
+  DevBuf omega_t;              // Omega^T, K-major  [order][m]
+  DevBuf omega_in;             // staging for a host-resident Omega
+  DevBuf B;                    // sketch, l x n (col-major, ld = l)
+  DevBuf B2;                   // permuted copy / scratch
+  DevBuf partial;              // split-K partial sums
+  DevBuf vn1, vn2, lpos;       // QRCP per-column state
+  DevBuf rec;                  // LL exchange records
+  DevBuf jpvt, tau, rdiag, info, kbtrace;
+  DevBuf R11, T;               // k x k, k x (n-k)
+  DevBuf C, Q, R1, Rfull;      // pqr tail
+  DevBuf W, G, U, S, Vt, Z;    // psvd tail
+  DevBuf scratch, scratch2, scratch3;
+  DevBuf aux_in1, aux_in2;     // staged random inputs (d, idx, perm, s, r)
+  uint32_t rec_epoch = 1;
+  size_t rec_zeroed = 0;
+  int32_t* h_info = nullptr;   // pinned, 16 ints
+
+  FactResult res;
+
+  void set_error(const std::string& s) { err = s; }
+};
+
+static inline bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// ---- kernels' host launchers (defined in the .cu files) -------------------
+
+// qrcp.cu
+struct QrcpOut {
+  int k, nsteps, nblocks, status;
+};
+int bra_qrcp_run(bra_ctx* ctx, double* B, int64_t ldb, int l, int64_t n, int kcap, int nb,
+                 double atol, double rtol, QrcpOut* out);
+int bra_permute_cols(bra_ctx* ctx, const double* src, int64_t lds, double* dst, int64_t ldd,
+                     int64_t rows, int64_t n, const int64_t* jpvt1);
+int bra_gather_R(bra_ctx* ctx, const double* B, int64_t ldb, int64_t n, int k,
+                 const int64_t* jpvt1, double* R11, double* R12);
+
+// sketch_randn.cu
+int bra_transpose_omega(bra_ctx* ctx, const double* Om, int64_t ldo, int64_t l, int64_t m, double* Omt);
+int bra_fill_randn(bra_ctx* ctx, double* dst, int64_t count, uint64_t seed, uint64_t stream_id);
+int bra_gemm_sketch(bra_ctx* ctx, const double* Omt, int64_t l, int64_t m, const double* A, int64_t lda,
+                    int64_t n, double* B, int64_t ldb);
+bool bra_gemm_tma_ok(const double* A, int64_t lda, int64_t m, int64_t n);
+int bra_gemm_generic(bra_ctx* ctx, const double* Om, int64_t osi, int64_t osk, const double* A, int64_t sk,
+                     int64_t sj, int64_t l, int64_t n, int64_t K, double* C, int64_t ldc);
+
+// trsolve.cu
+int bra_trsolve_upper(bra_ctx* ctx, int k, int64_t nrhs, const double* R11, int64_t ldr, double* X, int64_t ldx);

@@ -1,0 +1,89 @@
+"""End-to-end GPU parity of idfact against the oracle on identical random inputs (same Omega):
+k equal, p equal, C*T within 1e-10*||A|| entrywise (the attainable end-to-end factor check,
+SURVEY.md section 7 hard part 3), spectral error within 2x of the oracle's."""
+import numpy as np
+import pytest
+
+import lra_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_pair(ctx, A, kw, seed=0, trans="n"):
+    import brapprox
+    rin = o.RandomInputs(seed)
+    Vo = o.idfact(A, o.LRAOptions(**kw), rin, trans)
+    Vg = brapprox.idfact(A, brapprox.LRAOptions(**kw), trans=trans, rand=rin.drawn, ctx=ctx)
+    return Vo, Vg
+
+
+def _check_pair(A, Vo, Vg, trans="n"):
+    Aop = A if trans == "n" else A.T
+    assert Vg.rounds == Vo.rounds
+    assert Vg.k == Vo.k
+    np.testing.assert_array_equal(Vg.p, Vo.p)
+    C = Aop[:, Vo.sk - 1]
+    nrm = np.linalg.norm(Aop, 2)
+    assert np.max(np.abs(C @ Vg.T - C @ Vo.T)) <= 1e-10 * nrm
+    eo = o.id_error(A, Vo, trans)
+    eg = o.id_error(A, Vg, trans)
+    assert eg <= 2 * eo + 1e-15
+
+
+def test_idfact_hilbert_1024(ctx):
+    """BASELINE config 1 (README.md:107,122 known answers)."""
+    A = o.matrixlib_hilb(1024)
+    Vo, Vg = _run_pair(ctx, A, dict(rtol=1e-12))
+    assert Vo.k == 22
+    _check_pair(A, Vo, Vg)
+    # rtol = 1e-15 terminates inside rounding noise: k within 1, pivots equal on the above-noise prefix
+    Vo, Vg = _run_pair(ctx, A, dict(rtol=1e-15))
+    assert abs(Vg.k - Vo.k) <= 1 and Vg.k in (26, 27, 28)
+    assert o.id_error(A, Vg) <= 2 * o.id_error(A, Vo) + 1e-15
+
+
+@pytest.mark.parametrize("m,n,r,rtol", [(1024, 1024, 120, 1e-12), (2048, 1536, 300, 1e-10), (700, 900, 64, 1e-8)])
+def test_idfact_decaying(ctx, m, n, r, rtol):
+    A = o.decaying_matrix(m, n, r, 14.0, r, seed=m + n)
+    Vo, Vg = _run_pair(ctx, A, dict(rtol=rtol))
+    _check_pair(A, Vo, Vg)
+
+
+def test_idfact_trans_c(ctx):
+    A = o.decaying_matrix(600, 400, 80, 13.0, 80, seed=4)
+    Vo, Vg = _run_pair(ctx, A, dict(rtol=1e-11), trans="c")
+    _check_pair(A, Vo, Vg, trans="c")
+
+
+def test_idfact_rank_and_nonadaptive(ctx):
+    A = o.decaying_matrix(800, 800, 200, 10.0, 200, seed=8)
+    for kw in (dict(rank=40), dict(rank=40, sketchfact_adap=False), dict(rank=0), dict(nb=16, rtol=1e-9)):
+        Vo, Vg = _run_pair(ctx, A, kw)
+        assert Vg.rounds == Vo.rounds and Vg.k == Vo.k
+        np.testing.assert_array_equal(Vg.p, Vo.p)
+
+
+def test_idfact_fast_mode_device_rng(ctx):
+    """Fast mode (device Philox Omega): no oracle twin, so check the reference's own inequality
+    (test/id.jl:27-32 style) and determinism."""
+    import brapprox
+    A = o.decaying_matrix(1500, 1200, 150, 14.0, 150, seed=2)
+    V1 = brapprox.idfact(A, rtol=1e-12, seed=5, ctx=ctx)
+    V2 = brapprox.idfact(A, rtol=1e-12, seed=5, ctx=ctx)
+    np.testing.assert_array_equal(V1.p, V2.p)
+    np.testing.assert_array_equal(V1.T, V2.T)
+    err = np.linalg.norm(A - A[:, V1.sk - 1] @ V1.matrix()) / np.linalg.norm(A)
+    assert err < 100 * 1e-12
+
+
+def test_errors_mirror_reference(ctx):
+    import brapprox
+    A = np.zeros((8, 8))
+    with pytest.raises(ValueError):
+        brapprox.idfact(A, rtol=-1.0, ctx=ctx)          # ArgumentError("rtol")
+    with pytest.raises(ValueError):
+        brapprox.idfact(A, sketch="bogus", ctx=ctx)     # ArgumentError("sketch")
+    with pytest.raises(ValueError):
+        brapprox.idfact(A, trans="x", ctx=ctx)          # ArgumentError("trans")
+    with pytest.raises(brapprox.BraError):
+        brapprox.idfact(A, maxdet_tol=0.0, ctx=ctx)     # unsupported -> loud, never a CPU fallback
