@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the sketch-then-factor path (BASELINE.json config 2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 8192] [--what idfact|psvdfact]
+
+A "step" is ONE factorization (idfact, or psvdfact once requested) of an n x n FP64 matrix
+A = U diag(sigma) V^T, sigma_j = 10^(-12 j / 500), rank-640 factors from thin QRs of seeded Gaussians
+(SURVEY.md section 8d, C2), rtol = 1e-12, sketch = :randn, adaptive rounds, device Philox Omega.
+
+Our arm prints ONE JSON line:
+  value         factorizations/s, A resident in HBM, results left on the device, only k read back
+  e2e           the same through the C ABI with a HOST (pinned) A: H2D of A and D2H of (p, T[, U, S, Vt])
+                inside the timed region every step
+  roofline      FP64-tensor bound: algorithmic flops of the sketch GEMM launches / their CUDA-event time
+                (events recorded on the library's own stream), against the FP64 peak measured in this run
+  cpu_baseline  the oracle (real LAPACK/BLAS through scipy's OpenBLAS) on the box's host cores, bounded sample
+
+`--impl reference` times the oracle only (rank 0), same metric/config.  N > 1: one process per GPU, each
+factorizing its own replica (the single-matrix configs do not shard: SURVEY.md section 8e, "replicas only").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "lowrankapprox.jl_b200"))
+
+RTOL = 1e-12
+RANK_GEN = 640
+DECADES, JDIV = 12.0, 500.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=8192)
+    ap.add_argument("--what", default="auto", choices=["auto", "idfact", "psvdfact"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def algorithmic_flops(m, n, rounds, steps, k):
+    """F_sk = 2 m n sum(l_t); F_qr = sum 4[l n k - (l+n)k^2/2 + k^3/3]; F_T = k^2 (n-k)."""
+    f_sk = 2.0 * m * n * sum(l for l, _ in rounds)
+    f_qr = sum(4.0 * (l * n * s - (l + n) * s * s / 2.0 + s ** 3 / 3.0) for (l, _), s in zip(rounds, steps))
+    f_t = float(k) * k * (n - k)
+    return f_sk, f_qr, f_t
+
+
+def psvd_extra_flops(m, n, k):
+    return (2.0 * m * k * k - 2.0 / 3.0 * k ** 3) + float(k) * k * (n - k) + 4.0 * n * k * k + 12.0 * k ** 3 + 2.0 * m * k * k
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample(n: int, what: str, max_seconds: float = 25.0, threads: int = 0):
+    """Times the oracle on the host cores: factorizations/s on a bounded sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import lra_oracle as o
+    cores = threads or os.cpu_count() or 1
+    o.set_blas_threads(cores)
+    A = o.decaying_matrix(n, n, RANK_GEN, DECADES, JDIV, seed=1)
+    opts = o.LRAOptions(rtol=RTOL)
+    fn = o.psvdfact if what == "psvdfact" else o.idfact
+    times, ks = [], []
+    t_start = time.perf_counter()
+    rep = 0
+    while True:
+        t0 = time.perf_counter()
+        F = fn(A, opts, o.RandomInputs(rep))
+        times.append(time.perf_counter() - t0)
+        ks.append(len(F.S) if what == "psvdfact" else F.k)
+        rep += 1
+        if rep >= 2 and (time.perf_counter() - t_start > max_seconds or rep >= 12):
+            break
+    best = sorted(times)[len(times) // 2]
+    return {"value": 1.0 / best, "unit": "factorizations/s", "cores": cores, "kind": "port",
+            "sample": f"{rep} x {what} of the same {n}x{n} workload on the host (median; includes drawing Omega "
+                      f"with numpy), OpenBLAS threads={o.get_blas_threads()}, k={ks[-1]}"}, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    what = "idfact" if args.what == "auto" else args.what
+    base, times = cpu_sample(args.n, what, max_seconds=60.0)
+    # honour --steps/--warmup within a bounded budget: the sample above already ran >= 2 factorizations
+    v = base["value"]
+    line = {"impl": "reference", "metric": f"{what}_factorizations_per_sec", "value": v, "unit": "factorizations/s",
+            "n_gpus": args.gpus, "steps": len(times), "warmup": 0, "ms_per_step": 1e3 / v, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C2: {what} of {args.n}x{args.n} FP64, sigma_j=10^(-12j/500), rtol=1e-12, "
+                                   "sketch=randn (oracle = reference's LAPACK/BLAS CPU path restated)"},
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": "factorizations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import brapprox
+    from brapprox import _binding as B
+    from brapprox._binding import DeviceMatrix
+    from brapprox._frontend import idfact_device
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ctx = brapprox.Context(local)
+    has_psvd = hasattr(brapprox, "psvdfact_device")
+    what = args.what if args.what != "auto" else ("psvdfact" if has_psvd else "idfact")
+
+    n = args.n
+    g = torch.Generator(device=dev)
+    g.manual_seed(1 + rank)
+    U, _ = torch.linalg.qr(torch.randn(n, RANK_GEN, dtype=torch.float64, device=dev, generator=g))
+    V, _ = torch.linalg.qr(torch.randn(n, RANK_GEN, dtype=torch.float64, device=dev, generator=g))
+    sig = 10.0 ** (-DECADES * torch.arange(RANK_GEN, dtype=torch.float64, device=dev) / JDIV)
+    At = ((V * sig) @ U.T).contiguous()         # row-major (n x n)  ==  column-major A = U diag(sig) V^T
+    A = DeviceMatrix(At.data_ptr(), n, n, n, keep=At)
+    del U, V
+    torch.cuda.synchronize()
+
+    if what == "psvdfact":
+        from brapprox._frontend import psvdfact_device as fact_device
+    else:
+        fact_device = idfact_device
+
+    def step(seed):
+        return fact_device(A, rtol=RTOL, seed=seed, ctx=ctx)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- FP64 peak measured in this run (MEASURED_PEAKS.json carries no FP64 figure) ----
+    peaks = brapprox.probe_fp64_peak(ctx)
+    x = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+    y = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+    for _ in range(2):
+        torch.matmul(x, y)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 1e9
+    for _ in range(3):
+        e0.record()
+        torch.matmul(x, y)
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    cublas_tf = 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+    del x, y
+    fp64_peak = max(cublas_tf, max(peaks.values()))
+
+    # ---- warm-up, then the timed region (A = 537 MB > 126 MB L2: inputs larger than L2) ----
+    for w in range(max(args.warmup, 3)):
+        inf = step(100 + w)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ctx.profile_enable(True)
+    launches0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    # the library launches on its own stream: record the CUDA events THERE (torch's current stream sees nothing)
+    ext = torch.cuda.ExternalStream(int(B.lib.bra_stream(ctx.handle)), device=dev)
+    t0 = time.perf_counter()
+    ev0.record(ext)
+    for s in range(args.steps):
+        inf = step(s)
+    ev1.record(ext)
+    ev1.synchronize()
+    barrier()
+    wall_host = time.perf_counter() - t0
+    wall = ev0.elapsed_time(ev1) * 1e-3
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    tmax = wall
+    if world > 1:
+        t = torch.tensor([wall], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tmax = float(t.item())
+    value = world * args.steps / tmax
+
+    rounds = [(int(inf.orders[t]), int(inf.ks[t])) for t in range(inf.rounds)]
+    steps = [int(inf.steps[t]) for t in range(inf.rounds)]
+    k = int(inf.k)
+    f_sk, f_qr, f_t = algorithmic_flops(n, n, rounds, steps, k)
+    f_total = f_sk + f_qr + f_t + (psvd_extra_flops(n, n, k) if what == "psvdfact" else 0.0)
+    gemm_ms, gemm_calls = prof["gemm"]
+    gemm_tf = f_sk * args.steps / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+
+    # ---- e2e: host-resident A through the C ABI, result fetched to the host, every step ----
+    e2e = None
+    if rank == 0 or world > 1:
+        Ah = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
+        Ah.copy_(At)
+        Ahn = Ah.numpy().T            # column-major view of the pinned buffer (F-contiguous)
+        from brapprox._frontend import idfact, _rounds
+        e2e_steps = max(3, min(args.steps, 10))
+
+        def e2e_step(seed):
+            if what == "psvdfact":
+                F = brapprox.psvdfact(Ahn, rtol=RTOL, seed=seed, ctx=ctx)
+                return F.U.nbytes + F.S.nbytes + F.Vt.nbytes
+            Vv = idfact(Ahn, rtol=RTOL, seed=seed, ctx=ctx)
+            return Vv.sk.nbytes + Vv.rd.nbytes + Vv.T.nbytes
+
+        e2e_step(7)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(e2e_steps):
+            d2h = e2e_step(s)
+        barrier()
+        te = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([te], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            te = float(t.item())
+        e2e = {"value": world * e2e_steps / te, "unit": "factorizations/s", "h2d_bytes_per_step": int(n * n * 8),
+               "d2h_bytes_per_step": int(d2h), "steps": e2e_steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu, _ = cpu_sample(n, what)
+
+    line = {
+        "metric": f"{what}_factorizations_per_sec", "value": value, "unit": "factorizations/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * tmax / args.steps,
+        "host_wall_ms_per_step": 1e3 * wall_host / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C2: {what} of {n}x{n} FP64, A=U diag(10^(-12j/500)) V^T (rank-640 factors), "
+                               "rtol=1e-12, sketch=randn, adaptive, device Philox Omega, A resident in HBM",
+                   "rounds_order_k": rounds, "pivot_steps": steps, "k": k,
+                   "l2": "inputs (537 MB) larger than L2 (126 MB); no flush needed",
+                   "parallelism": "replicas only" if world > 1 else "single GPU"},
+        "whole_factorization": {"algorithmic_gflop": f_total / 1e9,
+                                "achieved_tflops": f_total * world * args.steps / tmax / 1e12 / world,
+                                "frac_of_fp64_peak": f_total * args.steps / tmax / 1e12 / fp64_peak},
+        "roofline": {"bound": "tensor", "kernel": "gemm_sketch_kernel (TMA + DMMA m8n8k4 FP64)",
+                     "achieved": gemm_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": (gemm_tf / fp64_peak) if gemm_tf else None, "traffic": None,
+                     "peak_source": f"measured in this run: cuBLAS DGEMM 8192^3 = {cublas_tf:.1f} TF, "
+                                    f"DMMA issue probes = {max(peaks.values()):.1f} TF "
+                                    "(MEASURED_PEAKS.json has no FP64 figure)",
+                     "algorithmic_flops_per_step": f_sk, "gemm_launches": gemm_calls, "gemm_ms_total": gemm_ms},
+        "stage_ms_per_step": {k2: v[0] / args.steps for k2, v in prof.items()},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "fp64_peak_probes_tflops": peaks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -159,12 +159,33 @@ int bra_idfact_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double*
 int bra_get_info(bra_ctx* ctx, bra_info* info);
 int bra_fetch(bra_ctx* ctx, int which, void* dst, int64_t ld);
 
+/* ---- per-stage device timing (CUDA events recorded on the ctx stream around each stage) ---- */
+#define BRA_PROF_OMEGA 0     /* Omega generation / transpose */
+#define BRA_PROF_GEMM 1      /* sketch GEMM kernel (TMA + DMMA) */
+#define BRA_PROF_SPLITK 2    /* deterministic split-K reduction */
+#define BRA_PROF_QRCP 3      /* persistent QRCP kernel */
+#define BRA_PROF_GATHER 4    /* R gather / permutations */
+#define BRA_PROF_TRSOLVE 5   /* T = R11^-1 R12 */
+#define BRA_PROF_TAIL 6      /* pqr / psvd tail kernels */
+#define BRA_PROF_SKETCH_OTHER 7 /* srft / sprn / sub sketch kernels */
+#define BRA_PROF_NTAGS 8
+int bra_profile_enable(bra_ctx* ctx, int on);            /* also clears the accumulators */
+/* accumulated milliseconds and span counts per tag since the last enable; syncs the stream */
+int bra_profile_read(bra_ctx* ctx, double* ms, int64_t* calls);
+
 /* ---- diagnostics ---------------------------------------------------------- */
 /* FP64 peak probes used as roofline denominators (bench.py): a register-resident
- * DMMA loop and a DFMA loop; returns TFLOP/s in out[0], out[1]. */
+ * DMMA loop and a DFMA loop; returns TFLOP/s in out[0..4]:
+ * m8n8k4, DFMA, m16n8k4, m16n8k8, m16n8k16 (all lower to DMMA.8x8x4 on sm_100a). */
 int bra_probe_fp64_peak(bra_ctx* ctx, double* out);
 /* Average latency (microseconds) of one LL all-gather exchange across `ctas` CTAs. */
 int bra_probe_exchange_latency(bra_ctx* ctx, int ctas, int iters, double* usec);
+
+/* Kilo-cycles CTA 0 spent per phase of the last QRCP launch: local scan, publish, header gather,
+ * Householder, update (clock64 deltas; diagnostic only). */
+int bra_debug_qrcp_phases(bra_ctx* ctx, int32_t* out5);
+/* Same, for every CTA of the last QRCP launch: out[cta*8 + phase], ctas <= 160. */
+int bra_debug_qrcp_phases_all(bra_ctx* ctx, int32_t* out, int ctas);
 
 #ifdef __cplusplus
 }

@@ -81,6 +81,10 @@ lib.bra_trsolve_T_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, _vp, _i64]
 lib.bra_idfact_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand)]
 lib.bra_get_info.argtypes = [_vp, C.POINTER(bra_info)]
 lib.bra_fetch.argtypes = [_vp, C.c_int, _vp, _i64]
+lib.bra_profile_enable.argtypes = [_vp, C.c_int]
+lib.bra_profile_read.argtypes = [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+PROF_TAGS = ["omega", "gemm", "splitk", "qrcp", "gather", "trsolve", "tail", "sketch_other"]
+lib.bra_debug_qrcp_phases.argtypes = [_vp, C.POINTER(C.c_int32)]
 lib.bra_probe_fp64_peak.argtypes = [_vp, C.POINTER(C.c_double)]
 lib.bra_probe_exchange_latency.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(C.c_double)]
 
@@ -233,6 +237,21 @@ class Context:
 
     def launch_count(self) -> int:
         return int(lib.bra_launch_count(self._h))
+
+    def profile_enable(self, on: bool = True):
+        self.check(lib.bra_profile_enable(self._h, int(on)))
+
+    def profile_read(self) -> dict:
+        """{tag: (milliseconds, spans)} accumulated since profile_enable (CUDA events on the ctx stream)."""
+        ms = (C.c_double * len(PROF_TAGS))()
+        calls = (C.c_int64 * len(PROF_TAGS))()
+        self.check(lib.bra_profile_read(self._h, ms, calls))
+        return {t: (ms[i], int(calls[i])) for i, t in enumerate(PROF_TAGS)}
+
+    def qrcp_phases(self):
+        out = (C.c_int32 * 5)()
+        lib.bra_debug_qrcp_phases(self._h, out)
+        return dict(zip(["scan", "publish", "gather", "householder", "update"], [int(x) for x in out]))
 
     def sync(self):
         self.check(lib.bra_sync(self._h))

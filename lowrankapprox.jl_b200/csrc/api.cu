@@ -57,8 +57,10 @@ int prepare_omega_t(bra_ctx* ctx, const bra_opts* o, const bra_rand* rnd, int ro
     int64_t ldo;
     int rc = to_device(ctx, ctx->omega_in, rnd->omega[round], order, order, mA, &dOm, &ldo);
     if (rc) return rc;
+    ProfScope ps(ctx, BRA_PROF_OMEGA);
     return bra_transpose_omega(ctx, dOm, ldo, order, mA, ctx->omega_t.as<double>());
   }
+  ProfScope ps(ctx, BRA_PROF_OMEGA);
   return bra_fill_randn(ctx, ctx->omega_t.as<double>(), order * ldt, o->seed, (uint64_t)round);
 }
 
@@ -76,6 +78,7 @@ int sketch_randn_round(bra_ctx* ctx, char trans, int64_t m, int64_t n, const dou
 }
 
 int run_round_qrcp(bra_ctx* ctx, const bra_opts* o, int64_t order, int64_t nA, QrcpOut* q) {
+  ProfScope ps(ctx, BRA_PROF_QRCP);
   const int64_t lmin = order < nA ? order : nA;
   const int64_t kcap = (o->rank < 0 || o->rank > lmin) ? lmin : o->rank;       // src/pqr.jl:350-352
   return bra_qrcp_run(ctx, ctx->B.as<double>(), order, (int)order, nA, (int)kcap, (int)o->nb, o->atol, o->rtol, q);
@@ -150,6 +153,56 @@ void* bra_stream(bra_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int bra_sync(bra_ctx* ctx) {
   if (!ctx) return -1;
   BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BRA_OK;
+}
+
+int bra_profile_enable(bra_ctx* ctx, int on) {
+  if (!ctx) return -1;
+  BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (auto& sp : ctx->prof_spans) {
+    ctx->prof_pool.push_back(sp.e0);
+    ctx->prof_pool.push_back(sp.e1);
+  }
+  ctx->prof_spans.clear();
+  for (int t = 0; t < BRA_PROF_NTAGS; ++t) {
+    ctx->prof_ms[t] = 0;
+    ctx->prof_calls[t] = 0;
+  }
+  ctx->prof_on = on != 0;
+  return BRA_OK;
+}
+
+int bra_profile_read(bra_ctx* ctx, double* ms, int64_t* calls) {
+  if (!ctx) return -1;
+  BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (auto& sp : ctx->prof_spans) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, sp.e0, sp.e1) == cudaSuccess) {
+      ctx->prof_ms[sp.tag] += t;
+      ctx->prof_calls[sp.tag] += 1;
+    } else {
+      cudaGetLastError();
+    }
+    ctx->prof_pool.push_back(sp.e0);
+    ctx->prof_pool.push_back(sp.e1);
+  }
+  ctx->prof_spans.clear();
+  for (int t = 0; t < BRA_PROF_NTAGS; ++t) {
+    if (ms) ms[t] = ctx->prof_ms[t];
+    if (calls) calls[t] = ctx->prof_calls[t];
+  }
+  return BRA_OK;
+}
+
+int bra_debug_qrcp_phases(bra_ctx* ctx, int32_t* out5) {
+  if (!ctx || !out5) return -1;
+  for (int i = 0; i < 5; ++i) out5[i] = ctx->h_info[4 + i];
+  return BRA_OK;
+}
+
+int bra_debug_qrcp_phases_all(bra_ctx* ctx, int32_t* out, int ctas) {
+  if (!ctx || !out) return -1;
+  BRA_CUDA(cudaMemcpy(out, ctx->scratch3.p, (size_t)ctas * 8 * 4, cudaMemcpyDeviceToHost));
   return BRA_OK;
 }
 
@@ -325,10 +378,17 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
   if (k > 0) {
     BRA_CUDA(ctx->R11.reserve((size_t)k * k * 8));
     BRA_CUDA(ctx->T.reserve((size_t)k * (nA - k > 0 ? nA - k : 1) * 8));
-    int rc = bra_gather_R(ctx, ctx->B.as<double>(), order, nA, (int)k, ctx->jpvt.as<int64_t>(), ctx->R11.as<double>(),
-                          ctx->T.as<double>());
+    int rc;
+    {
+      ProfScope ps(ctx, BRA_PROF_GATHER);
+      rc = bra_gather_R(ctx, ctx->B.as<double>(), order, nA, (int)k, ctx->jpvt.as<int64_t>(), ctx->R11.as<double>(),
+                        ctx->T.as<double>());
+    }
     if (rc) return rc;
-    rc = bra_trsolve_upper(ctx, (int)k, nA - k, ctx->R11.as<double>(), k, ctx->T.as<double>(), k);
+    {
+      ProfScope ps(ctx, BRA_PROF_TRSOLVE);
+      rc = bra_trsolve_upper(ctx, (int)k, nA - k, ctx->R11.as<double>(), k, ctx->T.as<double>(), k);
+    }
     if (rc) return rc;
   }
   res.have_T = true;

@@ -89,7 +89,36 @@ struct bra_ctx {
 
   FactResult res;
 
+  // optional per-stage device timing (CUDA events on the launching stream); see bra_profile_*
+  bool prof_on = false;
+  struct ProfSpan { int tag; cudaEvent_t e0, e1; };
+  std::vector<ProfSpan> prof_spans;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[BRA_PROF_NTAGS] = {0};
+  int64_t prof_calls[BRA_PROF_NTAGS] = {0};
+  cudaEvent_t prof_event() {
+    if (!prof_pool.empty()) { cudaEvent_t e = prof_pool.back(); prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  void prof_begin(int tag) {
+    if (!prof_on) return;
+    ProfSpan sp{tag, prof_event(), prof_event()};
+    cudaEventRecord(sp.e0, stream);
+    prof_spans.push_back(sp);
+  }
+  void prof_end() {
+    if (!prof_on || prof_spans.empty()) return;
+    // close the most recent open span
+    cudaEventRecord(prof_spans.back().e1, stream);
+  }
+
   void set_error(const std::string& s) { err = s; }
+};
+
+struct ProfScope {
+  bra_ctx* c;
+  ProfScope(bra_ctx* ctx, int tag) : c(ctx) { c->prof_begin(tag); }
+  ~ProfScope() { c->prof_end(); }
 };
 
 static inline bool is_device_ptr(const void* p) {

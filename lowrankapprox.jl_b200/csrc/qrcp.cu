@@ -15,22 +15,27 @@
 //    as bookkeeping only, because it is observable: a flagged column ends the
 //    block, the rank test runs at block ends only, pivoting continues to the block
 //    end (src/pqr.jl:397-414).
-//  * ONE grid-wide exchange per pivot step: every CTA publishes its best
-//    candidate (downdated norm, logical position) TOGETHER with that candidate's
-//    current column, as self-validating 8-byte words (payload + step stamp, the
-//    "LL" idea of NCCL) so no fence or atomic is on the critical path.  Every CTA
-//    then reads the 148 headers, picks the winner with warp-shuffle reductions and
-//    computes the Householder vector redundantly (bitwise identical everywhere).
+//  * ONE grid-wide exchange per pivot step, push style: every CTA writes its
+//    candidate header (downdated norm, logical position, and the alpha / tail
+//    norm^2 dlarfg needs) into EVERY CTA's private inbox and its candidate's
+//    current column into its own record, all as self-validating 8-byte words
+//    (payload + step stamp, the "LL" idea of NCCL): no fence, no atomic and no
+//    shared polling hot-spot on the critical path.  Every CTA then reads its own
+//    inbox, picks the winner with warp-shuffle reductions and forms the
+//    Householder vector redundantly (bitwise identical everywhere).
+//  * Norm downdate + local argmax are fused into the update sweep; the scalar
+//    LAWN-176 arithmetic is vectorised across lanes (lane j <-> j-th column of the warp).
 //  * The rank/rtol termination test stays on the device.
 #include "common.cuh"
-#include <cooperative_groups.h>
+#include <type_traits>
 
 namespace {
 
 constexpr int QR_THREADS = 512;
 constexpr int QR_WARPS = QR_THREADS / 32;
-constexpr int HDR16 = 4;                       // header size in 16-byte units
-constexpr uint32_t SPIN_LIMIT = 1u << 24;      // exchange timeout (never hang the box)
+constexpr int HW = 5;                          // header words pushed per (src, dst)
+constexpr int MAXG = 160;                      // >= number of SMs
+constexpr uint32_t SPIN_LIMIT = 1u << 22;      // exchange timeout (never hang the box)
 
 struct __align__(16) LL16 {
   uint32_t lo, s0, hi, s1;
@@ -50,35 +55,39 @@ struct QrcpParams {
   double* vn1g;
   double* vn2g;
   int* lposg;
-  LL16* rec;        // [2][G][HDR16 + l]
+  LL16* rec;        // [2][G][l]        candidate columns
+  LL16* inbox;      // [2][G dst][HW][G src] headers
   uint32_t epoch;
   int64_t* jpvt;    // n, 1-based, LAPACK layout
   double* tau;      // kcap
   double* rdiag;    // kcap
-  int* info;        // k, nsteps, nblocks, status
+  int* info;        // k, nsteps, nblocks, status, phase kilo-cycles...
   int* kbtrace;
   int kbcap;
+  int* dbg;         // [G][8] per-CTA phase kilo-cycles (diagnostic)
 };
 
 __device__ __forceinline__ void ll_store(LL16* p, uint32_t lo, uint32_t hi, uint32_t stamp) {
-  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(lo), "r"(stamp), "r"(hi),
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(lo), "r"(stamp), "r"(hi),
                "r"(stamp)
                : "memory");
 }
+__device__ __forceinline__ void ll_store_d(LL16* p, double x, uint32_t stamp) {
+  ll_store(p, (uint32_t)__double2loint(x), (uint32_t)__double2hiint(x), stamp);
+}
+__device__ __forceinline__ void ll_ld(const LL16* p, uint32_t& lo, uint32_t& s0, uint32_t& hi, uint32_t& s1) {
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(lo), "=r"(s0), "=r"(hi), "=r"(s1)
+               : "l"(p)
+               : "memory");
+}
 __device__ __forceinline__ bool ll_load(const LL16* p, uint32_t stamp, uint32_t& lo, uint32_t& hi) {
-  uint32_t s0, s1;
-  uint32_t spins = 0;
+  uint32_t s0, s1, spins = 0;
   do {
-    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(lo), "=r"(s0), "=r"(hi), "=r"(s1)
-                 : "l"(p)
-                 : "memory");
+    ll_ld(p, lo, s0, hi, s1);
     if (s0 == stamp && s1 == stamp) return true;
   } while (++spins < SPIN_LIMIT);
   return false;
-}
-__device__ __forceinline__ void ll_store_d(LL16* p, double x, uint32_t stamp) {
-  ll_store(p, (uint32_t)__double2loint(x), (uint32_t)__double2hiint(x), stamp);
 }
 
 __device__ __forceinline__ double warp_sum(double x) {
@@ -94,40 +103,32 @@ __device__ __forceinline__ bool cand_better(double v, int lp, double bv, int blp
 }
 
 struct Cand {
-  double v;
-  int lp;     // logical position
-  int id;     // physical column (local scan) or CTA index (gather)
-  int ps;     // physical column currently at logical position s (or -1)
-  int flag;
+  double v;       // downdated norm vn1 (-1: none)
+  double ssx;     // sum of squares of the candidate column below its pivot row
+  double alpha;   // candidate column at its pivot row
+  int lp;         // logical position
+  int id;         // local column index
+  int ps;         // physical column at the next logical pivot position (or -1)
+  int flag;       // any column flagged during the step
 };
 
-__device__ __forceinline__ Cand cand_merge(Cand a, const Cand& b) {
-  if (cand_better(b.v, b.lp, a.v, a.lp)) {
-    a.v = b.v;
-    a.lp = b.lp;
-    a.id = b.id;
-  }
-  a.ps = max(a.ps, b.ps);
-  a.flag |= b.flag;
-  return a;
-}
-__device__ __forceinline__ Cand cand_warp_reduce(Cand c) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    Cand d;
-    d.v = __shfl_xor_sync(0xffffffffu, c.v, o);
-    d.lp = __shfl_xor_sync(0xffffffffu, c.lp, o);
-    d.id = __shfl_xor_sync(0xffffffffu, c.id, o);
-    d.ps = __shfl_xor_sync(0xffffffffu, c.ps, o);
-    d.flag = __shfl_xor_sync(0xffffffffu, c.flag, o);
-    c = cand_merge(c, d);
-  }
-  return c;
+// argmax of (v, lp) over the warp; returns the winning lane
+// Non-negative doubles order like their bit patterns, so the argmax runs on the integer pipe with
+// four warp collectives (redux.sync) instead of 5 x 3 shuffles + FP64 compares.  v < 0 means "none".
+__device__ __forceinline__ int warp_argmax(double v, int lp) {
+  const int hi = (v >= 0.0) ? __double2hiint(v) : (int)0x80000000;
+  const unsigned lo = (v >= 0.0) ? (unsigned)__double2loint(v) : 0u;
+  const int mh = __reduce_max_sync(0xffffffffu, hi);
+  const bool c1 = (hi == mh);
+  const unsigned ml = __reduce_max_sync(0xffffffffu, c1 ? lo : 0u);
+  const bool c2 = c1 && (lo == ml);
+  const int mlp = __reduce_min_sync(0xffffffffu, c2 ? lp : 0x7fffffff);
+  return __ffs(__ballot_sync(0xffffffffu, c2 && lp == mlp)) - 1;
 }
 
 constexpr double TOL3Z = 1.0536712127723509e-08;   // sqrt(2^-53) = sqrt(DLAMCH('Epsilon'))
 
-// NR = number of row-registers per lane (rows s + lane + 32*i); NR == 0: generic two-pass loop.
+// NR = row registers per lane (rows s + lane + 32*i); NR == 0: generic two-pass loop.
 template <int NR>
 __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_kernel(QrcpParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -137,13 +138,20 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_kernel(QrcpParams p) {
   const int64_t col0 = (int64_t)cta * p.cpc;
   const int ncols = (int)max((int64_t)0, min((int64_t)p.cpc, p.n - col0));
   const int csm = min(p.csm, ncols);
+  constexpr int CB = (NR == 0 || NR > 9) ? 1 : (NR > 5 ? 2 : 4);     // columns in flight per warp
 
   // ---- shared memory carve-up ----
   double* vbuf = reinterpret_cast<double*>(smem_raw);             // l
   double* rdblk = vbuf + l;                                       // nb
-  double* red = rdblk + p.nb;                                     // 64 doubles scratch
-  Cand* credc = reinterpret_cast<Cand*>(red + 64);                // QR_WARPS candidates
-  double* cache = reinterpret_cast<double*>(credc + QR_WARPS + 1);// csm * l
+  double* hv = rdblk + p.nb;                                      // MAXG  header payloads of the gather
+  double* hssx = hv + MAXG;
+  double* halpha = hssx + MAXG;
+  int* hlp = reinterpret_cast<int*>(halpha + MAXG);               // MAXG each
+  int* hphys = hlp + MAXG;
+  int* hps = hphys + MAXG;
+  int* hflag = hps + MAXG;
+  Cand* credc = reinterpret_cast<Cand*>(hflag + MAXG);            // [2][QR_WARPS]
+  double* cache = reinterpret_cast<double*>(credc + 2 * QR_WARPS);// csm * l
   double* vn1 = p.meta_smem ? cache + (size_t)p.csm * l : p.vn1g + col0;
   double* vn2 = p.meta_smem ? vn1 + p.cpc : p.vn2g + col0;
   int* lpos = p.meta_smem ? reinterpret_cast<int*>(vn2 + p.cpc) : p.lposg + col0;
@@ -185,7 +193,59 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_kernel(QrcpParams p) {
       lpos[lc] = (int)(col0 + lc);
     }
   }
-  __syncthreads();
+  __syncwarp();
+
+  // Per-warp candidate for pivot step `snext` over the warp's columns (lc = warp + 16*j), with the
+  // alpha / tail sum of squares dlarfg will need; result goes to credc[snext & 1][warp].
+  auto warp_candidate = [&](int snext, int wflag) {
+    double bv = -1.0;
+    int blp = 0x7fffffff, bid = -1, bps = -1;
+    for (int j0 = 0; warp + QR_WARPS * j0 < ncols; j0 += 32) {
+      const int lc = warp + QR_WARPS * (j0 + lane);
+      double v = -1.0;
+      int lp = 0x7fffffff;
+      if (lc < ncols) {
+        const int q = lpos[lc];
+        if (q >= snext) {
+          v = vn1[lc];
+          lp = q;
+          if (q == snext) bps = (int)(col0 + lc);
+        }
+      }
+      const int wl = warp_argmax(v, lp);
+      v = __shfl_sync(0xffffffffu, v, wl);
+      lp = __shfl_sync(0xffffffffu, lp, wl);
+      const int wlc = warp + QR_WARPS * (j0 + wl);
+      if (cand_better(v, lp, bv, blp)) {
+        bv = v;
+        blp = lp;
+        bid = (v >= 0.0) ? wlc : -1;
+      }
+    }
+    bps = __reduce_max_sync(0xffffffffu, bps);
+    double alpha = 0.0, ssx = 0.0;
+    if (bid >= 0) {
+      const double* a = colptr(bid);
+      for (int r = snext + lane; r < l; r += 32) {
+        const double x = a[r];
+        if (r == snext) alpha = x;
+        else ssx = fma(x, x, ssx);
+      }
+      ssx = warp_sum(ssx);
+      alpha = __shfl_sync(0xffffffffu, alpha, 0);
+    }
+    if (lane == 0) {
+      Cand c;
+      c.v = bv;
+      c.ssx = ssx;
+      c.alpha = alpha;
+      c.lp = blp;
+      c.id = bid;
+      c.ps = bps;
+      c.flag = wflag;
+      credc[(snext & 1) * QR_WARPS + warp] = c;
+    }
+  };
 
   const int lastrk = (int)min((int64_t)l, p.n);
   int s = 0;            // current pivot step
@@ -195,102 +255,126 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_kernel(QrcpParams p) {
   int nblocks = 0;
   int kres = -1;
   double ptol = 0.0;
-  int myflag = 0;       // any local column flagged during the previous step
   bool failed = false;
+  __shared__ long long s_tph[6];            // per-phase cycle totals (thread 0 of CTA 0 reports them)
+  if (tid == 0) {
+    for (int i = 0; i < 5; ++i) s_tph[i] = 0;
+    s_tph[5] = clock64();
+  }
+#define QR_TICK(i) if (tid == 0) { long long _t = clock64(); s_tph[i] += _t - s_tph[5]; s_tph[5] = _t; }
+
+  warp_candidate(0, 0);
+  __syncthreads();
 
   while (true) {
-    // ---- local scan: best candidate, holder of logical position s, flags ----
+    // ---- merge the warp candidates -> this CTA's candidate for step s ----
+    // (every warp does it redundantly: lane w < QR_WARPS holds warp w's candidate)
     Cand c;
-    c.v = -1.0;
-    c.lp = 0x7fffffff;
-    c.id = -1;
-    c.ps = -1;
-    c.flag = myflag;
-    for (int lc = tid; lc < ncols; lc += QR_THREADS) {
-      int lp = lpos[lc];
-      if (lp >= s) {
-        double v = vn1[lc];
-        if (cand_better(v, lp, c.v, c.lp)) {
-          c.v = v;
-          c.lp = lp;
-          c.id = lc;
-        }
-        if (lp == s) c.ps = (int)(col0 + lc);
+    {
+      const Cand* cw = credc + (s & 1) * QR_WARPS;
+      double v = -1.0;
+      int lp = 0x7fffffff, psx = -1, fl = 0;
+      if (lane < QR_WARPS) {
+        v = cw[lane].v;
+        lp = cw[lane].lp;
+        psx = cw[lane].ps;
+        fl = cw[lane].flag;
       }
+      const int wl = warp_argmax(v, lp);
+      c = cw[wl];
+      c.ps = __reduce_max_sync(0xffffffffu, psx);
+      c.flag = (int)__reduce_or_sync(0xffffffffu, (unsigned)fl);
     }
-    c = cand_warp_reduce(c);
-    if (lane == 0) credc[warp] = c;
-    __syncthreads();
-    c = credc[0];
-#pragma unroll
-    for (int w = 1; w < QR_WARPS; ++w) c = cand_merge(c, credc[w]);
-    __syncthreads();     // credc reused below
+    QR_TICK(0)
 
-    // ---- publish: header + the candidate's current column ----
+    // ---- publish: header pushed to every inbox + the candidate's current column ----
     const uint32_t stamp = p.epoch + (uint32_t)s;
-    LL16* myrec = p.rec + ((size_t)(s & 1) * G + cta) * (HDR16 + l);
+    const int par = s & 1;
+    // inbox layout [par][dst][src][HW]: the HW words of one (src, dst) pair are contiguous, so a warp's
+    // stores/loads coalesce into few L2 requests (the exchange is L2-request-bound, not byte-bound).
+    for (int e = tid; e < G * HW; e += QR_THREADS) {
+      const int dst = e / HW, w = e - dst * HW;
+      uint32_t lo, hi;
+      if (w == 0) {
+        lo = (uint32_t)__double2loint(c.v);
+        hi = (uint32_t)__double2hiint(c.v);
+      } else if (w == 1) {
+        lo = (uint32_t)__double2loint(c.ssx);
+        hi = (uint32_t)__double2hiint(c.ssx);
+      } else if (w == 2) {
+        lo = (uint32_t)__double2loint(c.alpha);
+        hi = (uint32_t)__double2hiint(c.alpha);
+      } else if (w == 3) {
+        lo = (uint32_t)c.lp;
+        hi = (uint32_t)(c.id >= 0 ? (int)(col0 + c.id) : -1);
+      } else {
+        lo = (uint32_t)c.ps;
+        hi = (uint32_t)c.flag;
+      }
+      ll_store(p.inbox + (((size_t)par * G + dst) * G + cta) * HW + w, lo, hi, stamp);
+    }
+    LL16* myrec = p.rec + ((size_t)par * G + cta) * l;
     if (c.id >= 0) {
       const double* a = colptr(c.id);
-      for (int r = s + tid; r < l; r += QR_THREADS) ll_store_d(myrec + HDR16 + r, a[r], stamp);
+      for (int r = s + 1 + tid; r < l; r += QR_THREADS) ll_store_d(myrec + r, a[r], stamp);
     }
-    if (tid == 0) {
-      ll_store_d(myrec + 0, c.v, stamp);
-      ll_store(myrec + 1, (uint32_t)c.lp, (uint32_t)(c.id >= 0 ? (int)(col0 + c.id) : -1), stamp);
-      ll_store(myrec + 2, (uint32_t)c.ps, (uint32_t)c.flag, stamp);
-    }
+    QR_TICK(1)
 
-    // ---- gather the G headers, pick the winner ----
-    Cand w;
-    w.v = -2.0;
-    w.lp = 0x7fffffff;
-    w.id = -1;
-    w.ps = -1;
-    w.flag = 0;
-    int wphys = -1;
-    const int gw = (G + 31) / 32;   // warps that hold headers
-    if (tid < G) {
-      const LL16* r = p.rec + ((size_t)(s & 1) * G + tid) * (HDR16 + l);
-      uint32_t a0, a1, b0, b1, c0, c1;
-      bool ok = ll_load(r + 0, stamp, a0, a1);
-      ok = ok && ll_load(r + 1, stamp, b0, b1);
-      ok = ok && ll_load(r + 2, stamp, c0, c1);
-      if (!ok) s_fail = 1;
-      w.v = __hiloint2double((int)a1, (int)a0);
-      w.lp = (int)b0;
-      wphys = (int)b1;
-      w.id = tid;
-      w.ps = (int)c0;
-      w.flag = (int)c1;
-    }
-    if (warp < gw) {
-      // carry the winner's physical column through the reduction in `id` afterwards
-      Cand wr = cand_warp_reduce(w);
-      int src = __ffs(__ballot_sync(0xffffffffu, w.id == wr.id && w.id >= 0)) - 1;
-      int wp = __shfl_sync(0xffffffffu, wphys, max(src, 0));
-      if (lane == 0) {
-        credc[warp] = wr;
-        red[warp] = (double)wp;
+    // ---- gather my inbox (G*HW contiguous words, all threads poll), pick the winner ----
+    for (int e = tid; e < G * HW; e += QR_THREADS) {
+      const LL16* src = p.inbox + ((size_t)par * G + cta) * G * HW + e;
+      uint32_t lo, hi;
+      if (!ll_load(src, stamp, lo, hi)) s_fail = 1;
+      const int t = e / HW, w = e - t * HW;
+      if (w == 0) hv[t] = __hiloint2double((int)hi, (int)lo);
+      else if (w == 1) hssx[t] = __hiloint2double((int)hi, (int)lo);
+      else if (w == 2) halpha[t] = __hiloint2double((int)hi, (int)lo);
+      else if (w == 3) {
+        hlp[t] = (int)lo;
+        hphys[t] = (int)hi;
+      } else {
+        hps[t] = (int)lo;
+        hflag[t] = (int)hi;
       }
     }
     __syncthreads();
-    w = credc[0];
-    wphys = (int)red[0];
-    for (int q = 1; q < gw; ++q) {
-      Cand o = credc[q];
-      if (cand_better(o.v, o.lp, w.v, w.lp)) wphys = (int)red[q];
-      w = cand_merge(w, o);
-    }
     if (s_fail) {
       failed = true;
       break;
     }
-    const int wcta = w.id;           // CTA that owns the winner
-    const int lw = w.lp;             // winner's logical position
-    const int pw = wphys;            // winner's physical column
-    const int ps = w.ps;             // physical column at logical position s
+    // every warp reduces the G headers redundantly (no second barrier)
+    int wcta;
+    {
+      // lane-local best over its <= ceil(G/32) headers first, then one warp argmax
+      double bv = -1.0;
+      int blp = 0x7fffffff, bsrc = -1, aps = -1, aflag = 0;
+      for (int t = lane; t < G; t += 32) {
+        const double v = hv[t];
+        const int lp = hlp[t];
+        aps = max(aps, hps[t]);
+        aflag |= hflag[t];
+        if (cand_better(v, lp, bv, blp)) {
+          bv = v;
+          blp = lp;
+          bsrc = t;
+        }
+      }
+      const int wl = warp_argmax(bv, blp);
+      wcta = __shfl_sync(0xffffffffu, bsrc, wl);
+      c.v = __shfl_sync(0xffffffffu, bv, wl);       // reuse c as the gathered result
+      c.lp = __shfl_sync(0xffffffffu, blp, wl);
+      c.ps = __reduce_max_sync(0xffffffffu, aps);
+      c.flag = (int)__reduce_or_sync(0xffffffffu, (unsigned)aflag);
+    }
+    const int lw = c.lp;               // winner's logical position
+    const int pw = hphys[wcta];        // winner's physical column
+    const int ps = c.ps;               // physical column at logical position s
+    const double alpha = halpha[wcta];
+    const double ssq = hssx[wcta];
+    QR_TICK(2)
 
     // ---- block bookkeeping for the previous step (needs the gathered flags) ----
-    if (cnt > 0 && w.flag) {
+    if (cnt > 0 && c.flag) {
       // a column was flagged during step s-1: dlaqps ended its block there
       if (cta == 0 && tid == 0 && nblocks < p.kbcap) p.kbtrace[nblocks] = cnt;
       ++nblocks;
@@ -308,37 +392,14 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_kernel(QrcpParams p) {
       jb = min(p.nb, p.kcap - jblk);
       // jblk < kcap here: a block that reaches kcap always ends by count
     }
-    if (s == 0) ptol = fmax(p.atol, p.rtol * w.v);       // src/pqr.jl:386-389
-    __syncthreads();   // rdblk / credc consumers done
+    if (s == 0) ptol = fmax(p.atol, p.rtol * c.v);       // src/pqr.jl:386-389
 
     // ---- Householder vector of the winner column (dlarfg), redundantly per CTA ----
-    const LL16* wrec = p.rec + ((size_t)(s & 1) * G + wcta) * (HDR16 + l) + HDR16;
-    constexpr int XS = 3;                         // covers l - s <= 3 * QR_THREADS rows in registers
-    double xs[XS];
-    double ss = 0.0;
-    {
-      int q = 0;
-      for (int r = s + tid; r < l; r += QR_THREADS, ++q) {
-        uint32_t lo, hi;
-        if (!ll_load(wrec + r, stamp, lo, hi)) s_fail = 1;
-        double x = __hiloint2double((int)hi, (int)lo);
-        if (q < XS) xs[q] = x;
-        else vbuf[r - s] = x;                           // l > 1056+: spill through smem
-        if (r > s) ss = fma(x, x, ss);
-      }
-    }
-    ss = warp_sum(ss);
-    if (lane == 0) red[32 + warp] = ss;
-    if (tid == 0) red[63] = xs[0];                        // alpha (row s is always thread 0's first)
-    __syncthreads();
-    if (s_fail) {
-      failed = true;
-      break;
-    }
-    double ssq = 0.0;
-#pragma unroll
-    for (int q = 0; q < QR_WARPS; ++q) ssq += red[32 + q];
-    const double alpha = red[63];
+    // (the winner column's loads are issued first so that their L2 round trip overlaps the sqrt/div)
+    const LL16* wrec = p.rec + ((size_t)par * G + wcta) * l;
+    const int r0 = s + 1 + tid;
+    uint32_t x0lo = 0, x0hi = 0, x0s0 = stamp, x0s1 = stamp;
+    if (r0 < l) ll_ld(wrec + r0, x0lo, x0s0, x0hi, x0s1);
     double beta, tau, scale;
     if (s >= l - 1 || ssq == 0.0) {
       beta = alpha;
@@ -349,16 +410,21 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_kernel(QrcpParams p) {
       tau = (beta - alpha) / beta;
       scale = 1.0 / (alpha - beta);
     }
-    {
-      int q = 0;
-      for (int r = s + tid; r < l; r += QR_THREADS, ++q) {
-        double x = (q < XS) ? xs[q] : vbuf[r - s];
-        vbuf[r - s] = (r == s) ? 1.0 : x * scale;
+    if (tid == 0) vbuf[0] = 1.0;
+    if (r0 < l) {
+      if (x0s0 != stamp || x0s1 != stamp) {
+        if (!ll_load(wrec + r0, stamp, x0lo, x0hi)) s_fail = 1;
       }
+      vbuf[r0 - s] = __hiloint2double((int)x0hi, (int)x0lo) * scale;
     }
-    if (tid == 0) rdblk[cnt] = beta;
-    // ---- ownership updates ----
+    for (int r = r0 + QR_THREADS; r < l; r += QR_THREADS) {
+      uint32_t lo, hi;
+      if (!ll_load(wrec + r, stamp, lo, hi)) s_fail = 1;
+      vbuf[r - s] = __hiloint2double((int)hi, (int)lo) * scale;
+    }
     if (tid == 0) {
+      rdblk[cnt] = beta;
+      // ---- ownership updates ----
       if (ps >= col0 && ps < col0 + ncols && ps != pw) lpos[ps - col0] = lw;   // column K moves to pvt
       if (wcta == cta) {
         lpos[pw - col0] = s;
@@ -368,111 +434,156 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_kernel(QrcpParams p) {
       }
     }
     __syncthreads();
+    if (s_fail) {
+      failed = true;
+      break;
+    }
+    QR_TICK(3)
     if (wcta == cta) {
       // store R[s,s] and the reflector into the winner column (LAPACK layout)
       double* a = colptr((int)(pw - col0));
       for (int r = s + tid; r < l; r += QR_THREADS) a[r] = (r == s) ? beta : vbuf[r - s];
     }
 
-    // ---- apply H to the local unpivoted columns, downdate their norms ----
-    myflag = 0;
+    // ---- apply H to the warp's unpivoted columns; downdate their norms (vectorised across lanes) ----
     const bool downdate = (s < lastrk - 1);
+    int wflag = 0;
+    double vr[NR > 0 ? NR : 1];
     if (NR > 0) {
-      double vr[NR > 0 ? NR : 1];
 #pragma unroll
       for (int i = 0; i < NR; ++i) {
-        int r = s + lane + 32 * i;
+        const int r = s + lane + 32 * i;
         vr[i] = (r < l) ? vbuf[r - s] : 0.0;
       }
-      for (int lc = warp; lc < ncols; lc += QR_WARPS) {
-        if (lpos[lc] <= s) continue;
-        double* a = colptr(lc);
-        double ar[NR > 0 ? NR : 1];
-        double dot = 0.0;
+    }
+    for (int j0 = 0; warp + QR_WARPS * j0 < ncols; j0 += 32) {
+      double myrs = 0.0;      // lane j: R[s, column j of this chunk]
+      bool myact = false;
+      const int jend = min(32, (ncols - warp + QR_WARPS - 1) / QR_WARPS - j0);
+      for (int jj = 0; jj < jend; jj += CB) {
+        bool act[CB];
+        int lcs[CB];
+        bool all_sm = true;
 #pragma unroll
-        for (int i = 0; i < NR; ++i) {
-          int r = s + lane + 32 * i;
-          ar[i] = (r < l) ? a[r] : 0.0;
-          dot = fma(ar[i], vr[i], dot);
+        for (int cc = 0; cc < CB; ++cc) {
+          lcs[cc] = warp + QR_WARPS * (j0 + jj + cc);
+          act[cc] = (jj + cc < jend) && (lpos[lcs[cc]] > s);
+          all_sm = all_sm && (!act[cc] || lcs[cc] < csm);
         }
-        dot = warp_sum(dot);
-        const double f = tau * dot;
-        double ss2 = 0.0;
+        // SM = true: every live column of the batch sits in the shared-memory cache, and the pointers are
+        // formed from `cache` alone so that ptxas emits LDS/STS instead of generic LD/ST.
+        auto batch = [&](auto sm_tag) {
+          constexpr bool SM = decltype(sm_tag)::value;
+          double* a[CB];
 #pragma unroll
-        for (int i = 0; i < NR; ++i) {
-          int r = s + lane + 32 * i;
-          ar[i] = fma(-f, vr[i], ar[i]);
-          if (r < l) a[r] = ar[i];
-          if (r > s) ss2 = fma(ar[i], ar[i], ss2);      // rows beyond l hold zeros
-        }
-        if (downdate) {
-          const double rsj = __shfl_sync(0xffffffffu, ar[0], 0);
-          const double v1 = vn1[lc];
-          if (v1 != 0.0) {
-            double t = fabs(rsj) / v1;
-            t = fmax(0.0, (1.0 + t) * (1.0 - t));
-            const double q = v1 / vn2[lc];
-            const double t2 = t * (q * q);
-            if (t2 <= TOL3Z) {
-              // flagged: dlaqps ends the block and recomputes the norm from rows s+1..l-1
-              ss2 = warp_sum(ss2);
-              const double nn = sqrt(ss2);
-              if (lane == 0) {
-                vn1[lc] = nn;
-                vn2[lc] = nn;
+          for (int cc = 0; cc < CB; ++cc) {
+            if (SM) a[cc] = cache + (size_t)(act[cc] ? lcs[cc] : 0) * l;
+            else a[cc] = act[cc] ? colptr(lcs[cc]) : vbuf;
+          }
+          if (NR > 0) {
+            double ar[CB][NR > 0 ? NR : 1];
+            double dot[CB];
+#pragma unroll
+            for (int cc = 0; cc < CB; ++cc) {
+              double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+              for (int i = 0; i < NR; ++i) {
+                const int r = s + lane + 32 * i;
+                ar[cc][i] = (act[cc] && r < l) ? a[cc][r] : 0.0;
+                if (i & 1) d1 = fma(ar[cc][i], vr[i], d1);
+                else d0 = fma(ar[cc][i], vr[i], d0);
               }
-              myflag = 1;
-            } else if (lane == 0) {
-              vn1[lc] = v1 * sqrt(t);
+              dot[cc] = d0 + d1;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+              for (int cc = 0; cc < CB; ++cc) dot[cc] += __shfl_xor_sync(0xffffffffu, dot[cc], o);
+            }
+#pragma unroll
+            for (int cc = 0; cc < CB; ++cc) {
+              const double f = tau * dot[cc];
+#pragma unroll
+              for (int i = 0; i < NR; ++i) {
+                const int r = s + lane + 32 * i;
+                ar[cc][i] = fma(-f, vr[i], ar[cc][i]);
+                if (act[cc] && r < l) a[cc][r] = ar[cc][i];
+              }
+              const double rs = __shfl_sync(0xffffffffu, ar[cc][0], 0);
+              if (lane == jj + cc) {
+                myrs = rs;
+                myact = act[cc];
+              }
+            }
+          } else {
+#pragma unroll
+            for (int cc = 0; cc < CB; ++cc) {
+              if (!act[cc]) {
+                if (lane == jj + cc) myact = false;
+                continue;
+              }
+              double dot = 0.0;
+              for (int r = s + lane; r < l; r += 32) dot = fma(a[cc][r], vbuf[r - s], dot);
+              dot = warp_sum(dot);
+              const double f = tau * dot;
+              double rs = 0.0;
+              for (int r = s + lane; r < l; r += 32) {
+                const double x = fma(-f, vbuf[r - s], a[cc][r]);
+                a[cc][r] = x;
+                if (r == s) rs = x;
+              }
+              rs = __shfl_sync(0xffffffffu, rs, 0);
+              if (lane == jj + cc) {
+                myrs = rs;
+                myact = true;
+              }
             }
           }
+        };
+        if (all_sm) batch(std::true_type{});
+        else batch(std::false_type{});
+      }
+      // LAWN-176 downdate, one column per lane (dlaqps step 8)
+      bool flagged = false;
+      const int mylc = warp + QR_WARPS * (j0 + lane);
+      if (downdate && myact) {
+        const double v1 = vn1[mylc];
+        if (v1 != 0.0) {
+          double t = fabs(myrs) / v1;
+          t = fmax(0.0, (1.0 + t) * (1.0 - t));
+          const double q = v1 / vn2[mylc];
+          const double t2 = t * (q * q);
+          if (t2 <= TOL3Z) flagged = true;
+          else vn1[mylc] = v1 * sqrt(t);
         }
       }
-    } else {
-      for (int lc = warp; lc < ncols; lc += QR_WARPS) {
-        if (lpos[lc] <= s) continue;
-        double* a = colptr(lc);
-        double dot = 0.0;
-        for (int r = s + lane; r < l; r += 32) dot = fma(a[r], vbuf[r - s], dot);
-        dot = warp_sum(dot);
-        const double f = tau * dot;
-        double ss2 = 0.0, rsj = 0.0;
-        for (int r = s + lane; r < l; r += 32) {
-          double x = fma(-f, vbuf[r - s], a[r]);
-          a[r] = x;
-          if (r > s) ss2 = fma(x, x, ss2);
-          else rsj = x;
-        }
-        if (downdate) {
-          rsj = __shfl_sync(0xffffffffu, rsj, 0);
-          const double v1 = vn1[lc];
-          if (v1 != 0.0) {
-            double t = fabs(rsj) / v1;
-            t = fmax(0.0, (1.0 + t) * (1.0 - t));
-            const double q = v1 / vn2[lc];
-            const double t2 = t * (q * q);
-            if (t2 <= TOL3Z) {
-              ss2 = warp_sum(ss2);
-              const double nn = sqrt(ss2);
-              if (lane == 0) {
-                vn1[lc] = nn;
-                vn2[lc] = nn;
-              }
-              myflag = 1;
-            } else if (lane == 0) {
-              vn1[lc] = v1 * sqrt(t);
-            }
-          }
+      unsigned fm = __ballot_sync(0xffffffffu, flagged);
+      if (fm) wflag = 1;
+      while (fm) {
+        // flagged: dlaqps ends the block and recomputes the norm from rows s+1..l-1 of the updated column
+        const int fl = __ffs(fm) - 1;
+        fm &= fm - 1;
+        const int lc = warp + QR_WARPS * (j0 + fl);
+        const double* a = colptr(lc);
+        double ss2 = 0.0;
+        for (int r = s + 1 + lane; r < l; r += 32) ss2 = fma(a[r], a[r], ss2);
+        ss2 = warp_sum(ss2);
+        if (lane == 0) {
+          const double nn = sqrt(ss2);
+          vn1[lc] = nn;
+          vn2[lc] = nn;
         }
       }
     }
-    myflag = __syncthreads_or(myflag);
+    __syncwarp();
+    QR_TICK(4)
 
     // ---- end of step ----
     ++cnt;
     ++s;
-    if (cnt == jb) {
-      // block ends by count; flags raised in this step are irrelevant (cnt is reset)
+    bool block_end = (cnt == jb);
+    if (block_end) {
+      // block ends by count; flags raised in this step are irrelevant
       if (cta == 0 && tid == 0 && nblocks < p.kbcap) p.kbtrace[nblocks] = cnt;
       ++nblocks;
       const int jn = jblk + cnt;
@@ -491,8 +602,9 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_kernel(QrcpParams p) {
         break;
       }
       jb = min(p.nb, p.kcap - jblk);
-      myflag = 0;
     }
+    warp_candidate(s, block_end ? 0 : wflag);
+    __syncthreads();
   }
 
   // ---- epilogue: write the cached slab back, finish jpvt, report ----
@@ -512,7 +624,10 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_kernel(QrcpParams p) {
     p.info[1] = nsteps;
     p.info[2] = nblocks;
     p.info[3] = failed ? 1 : 0;
+    for (int i = 0; i < 5; ++i) p.info[4 + i] = (int)(s_tph[i] >> 10);   // kilo-cycles per phase
   }
+  if (tid == 0 && p.dbg)
+    for (int i = 0; i < 5; ++i) p.dbg[cta * 8 + i] = (int)(s_tph[i] >> 10);
 }
 
 __global__ void permute_cols_kernel(const double* __restrict__ src, int64_t lds, double* __restrict__ dst,
@@ -561,13 +676,13 @@ int bra_qrcp_run(bra_ctx* ctx, double* B, int64_t ldb, int l, int64_t n, int kca
   const int nbe = nb < kcap ? nb : kcap;
 
   // grid: one CTA per SM, but keep >= 8 columns per CTA
-  int G = ctx->num_sms;
+  int G = ctx->num_sms < MAXG ? ctx->num_sms : MAXG;
   int64_t maxG = (n + 7) / 8;
   if (maxG < G) G = (int)(maxG < 1 ? 1 : maxG);
   const int cpc = (int)((n + G - 1) / G);
 
   // shared-memory budget
-  const size_t fixed = ((size_t)l + nbe + 64) * 8 + (QR_WARPS + 2) * sizeof(Cand) + 64;
+  const size_t fixed = ((size_t)l + nbe + 3 * MAXG) * 8 + 4 * MAXG * 4 + 2 * QR_WARPS * sizeof(Cand) + 64;
   const size_t budget = (size_t)ctx->smem_optin - 1024;
   const size_t meta = (size_t)cpc * 20 + 16;
   int meta_smem = (fixed + meta <= budget / 2) ? 1 : 0;
@@ -579,8 +694,12 @@ int bra_qrcp_run(bra_ctx* ctx, double* B, int64_t ldb, int l, int64_t n, int kca
   BRA_CUDA(ctx->vn1.reserve((size_t)n * 8));
   BRA_CUDA(ctx->vn2.reserve((size_t)n * 8));
   BRA_CUDA(ctx->lpos.reserve((size_t)n * 4));
-  const size_t rec_bytes = (size_t)2 * G * (HDR16 + l) * sizeof(LL16);
-  if (ctx->rec.cap < rec_bytes || ctx->rec_zeroed < rec_bytes || ctx->rec_epoch > 0xF0000000u) {
+  // LL exchange buffers: [candidate columns | header inboxes]; zeroed when (re)allocated or when the
+  // 32-bit stamp epoch is about to wrap, otherwise reused across launches with a fresh epoch.
+  const size_t col_bytes = (size_t)2 * G * l * sizeof(LL16);
+  const size_t inbox_bytes = (size_t)2 * G * HW * G * sizeof(LL16);
+  const size_t rec_bytes = col_bytes + inbox_bytes;
+  if (ctx->rec.cap < rec_bytes || ctx->rec_zeroed < ctx->rec.cap || ctx->rec_epoch > 0xF0000000u) {
     BRA_CUDA(ctx->rec.reserve(rec_bytes));
     BRA_CUDA(cudaMemsetAsync(ctx->rec.p, 0, ctx->rec.cap, ctx->stream));
     ctx->rec_zeroed = ctx->rec.cap;
@@ -608,6 +727,7 @@ int bra_qrcp_run(bra_ctx* ctx, double* B, int64_t ldb, int l, int64_t n, int kca
   p.vn2g = ctx->vn2.as<double>();
   p.lposg = ctx->lpos.as<int>();
   p.rec = ctx->rec.as<LL16>();
+  p.inbox = reinterpret_cast<LL16*>(reinterpret_cast<unsigned char*>(ctx->rec.p) + col_bytes);
   p.epoch = ctx->rec_epoch;
   p.jpvt = ctx->jpvt.as<int64_t>();
   p.tau = ctx->tau.as<double>();
@@ -615,6 +735,8 @@ int bra_qrcp_run(bra_ctx* ctx, double* B, int64_t ldb, int l, int64_t n, int kca
   p.info = ctx->info.as<int>();
   p.kbtrace = ctx->kbtrace.as<int>();
   p.kbcap = kcap + 1;
+  BRA_CUDA(ctx->scratch3.reserve((size_t)MAXG * 8 * 4));
+  p.dbg = ctx->scratch3.as<int>();
   ctx->rec_epoch += (uint32_t)l + 8;
 
   cudaError_t e;
@@ -626,7 +748,7 @@ int bra_qrcp_run(bra_ctx* ctx, double* B, int64_t ldb, int l, int64_t n, int kca
   else e = launch_qrcp<0>(p, G, smem, ctx->stream);
   BRA_CUDA(e);
   ctx->launches++;
-  BRA_CUDA(cudaMemcpyAsync(ctx->h_info, ctx->info.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  BRA_CUDA(cudaMemcpyAsync(ctx->h_info, ctx->info.p, 48, cudaMemcpyDeviceToHost, ctx->stream));
   BRA_CUDA(cudaStreamSynchronize(ctx->stream));      // the only host sync: read back k
   out->k = ctx->h_info[0];
   out->nsteps = ctx->h_info[1];

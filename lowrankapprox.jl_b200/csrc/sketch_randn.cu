@@ -344,10 +344,14 @@ int launch_gemm(bra_ctx* ctx, const CUtensorMap& mapA, const double* Omt, int64_
   }
   BRA_CUDA(cudaFuncSetAttribute(gemm_sketch_kernel<WA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
   dim3 grid(jt, itl, splits);
-  gemm_sketch_kernel<WA><<<grid, (GW + 1) * 32, Cfg::SMEM, ctx->stream>>>(mapA, mapO, m, n, l, kper, out, ldo, sstride);
+  {
+    ProfScope ps(ctx, BRA_PROF_GEMM);
+    gemm_sketch_kernel<WA><<<grid, (GW + 1) * 32, Cfg::SMEM, ctx->stream>>>(mapA, mapO, m, n, l, kper, out, ldo, sstride);
+  }
   ctx->launches++;
   BRA_CUDA(cudaGetLastError());
   if (splits > 1) {
+    ProfScope ps(ctx, BRA_PROF_SPLITK);
     int64_t total = l * n;
     int blocks = (int)((total + 255) / 256 < (int64_t)ctx->num_sms * 16 ? (total + 255) / 256 : (int64_t)ctx->num_sms * 16);
     splitk_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(out, sstride, splits, l, n, B, ldb);
@@ -416,6 +420,7 @@ int bra_gemm_generic(bra_ctx* ctx, const double* Om, int64_t osi, int64_t osk, c
                      int64_t sj, int64_t l, int64_t n, int64_t K, double* C, int64_t ldc) {
   if (l <= 0 || n <= 0) return BRA_OK;
   dim3 grid((unsigned)((n + 63) / 64), (unsigned)((l + 63) / 64));
+  ProfScope ps(ctx, BRA_PROF_GEMM);
   gemm_generic_kernel<<<grid, 256, 0, ctx->stream>>>(Om, osi, osk, A, sk, sj, l, n, K, C, ldc);
   ctx->launches++;
   BRA_CUDA(cudaGetLastError());

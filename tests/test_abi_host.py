@@ -1,0 +1,131 @@
+"""CPU tests of the boundary and the host logic (no compute calls: there is no GPU here).
+
+* the C-ABI library loads and exports EVERY function include/brapprox.h declares;
+* the POD structs of the ctypes binding match the header's layout (sizes);
+* LRAOptions mirrors the reference's defaults, copy semantics and validation
+  (src/LowRankApprox.jl:96-148);
+* without a usable B200 the product path fails LOUDLY (no CPU fallback, nothing routes through oracle/).
+"""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "brapprox.h")
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bra_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import brapprox
+    names = _declared_functions()
+    assert len(names) >= 15
+    for nm in names:
+        assert hasattr(brapprox.lib, nm), f"libbrapprox.so does not export {nm}"
+    assert brapprox.lib.bra_version() >= 100
+
+
+def test_struct_layouts_match_header():
+    """Compile a tiny C program against the header and compare sizeof with the ctypes mirrors."""
+    from brapprox import _binding as B
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "sz.c")
+        open(c, "w").write('#include <stdio.h>\n#include "brapprox.h"\nint main(){printf("%zu %zu %zu\\n",'
+                           "sizeof(bra_opts),sizeof(bra_rand),sizeof(bra_info));return 0;}\n")
+        exe = os.path.join(d, "sz")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        so, sr, si = (int(x) for x in subprocess.check_output([exe]).split())
+    assert ctypes.sizeof(B.bra_opts) == so
+    assert ctypes.sizeof(B.bra_rand) == sr
+    assert ctypes.sizeof(B.bra_info) == si
+
+
+def test_opts_defaults_match_reference():
+    import brapprox
+    from brapprox import _binding as B
+    o = brapprox.LRAOptions()
+    eps = np.finfo(np.float64).eps
+    assert (o.atol, o.rtol, o.rank, o.nb, o.sketch) == (0.0, 5 * eps, -1, 32, "randn")
+    assert (o.sketch_randn_niter, o.sketchfact_adap, o.maxdet_tol, o.maxdet_niter) == (0, True, -1.0, -1)
+    assert (o.pqrfact_retval, o.snorm_niter, o.verb) == ("qr", 32, True)
+    assert [o.sketchfact_randn_samp(32), o.sketchfact_srft_samp(32), o.sketchfact_sub_samp(32)] == [40, 40, 136]
+    c = B.bra_opts()
+    B.lib.bra_opts_default(ctypes.byref(c))
+    assert (c.atol, c.rtol, c.rank, c.nb, c.sketch, c.sketchfact_adap) == (0.0, 5 * eps, -1, 32, 1, 1)
+    assert c.maxdet_tol < 0 and c.retval_mask == 3
+
+
+def test_opts_copy_and_validation():
+    import brapprox
+    o = brapprox.LRAOptions(rtol=1e-8)
+    o2 = o.copy(rank=5, sketch="srft")
+    assert (o.rank, o.sketch) == (-1, "randn") and (o2.rank, o2.sketch, o2.rtol) == (5, "srft", 1e-8)
+    with pytest.raises(TypeError):
+        o.copy(not_a_field=1)
+    for bad in (dict(atol=-1.0), dict(nb=0), dict(rtol=-1e-3), dict(sketch="fft")):
+        with pytest.raises(ValueError):
+            brapprox.LRAOptions(**bad).chk()
+    o3 = brapprox.LRAOptions(pqrfact_retval="QRT")
+    o3.chk()
+    assert o3.pqrfact_retval == "qrt"
+    assert o3.to_c().retval_mask == 7
+
+
+def test_samp_closures_cross_as_affine():
+    import brapprox
+    o = brapprox.LRAOptions(sketchfact_randn_samp=lambda n: 2 * n + 4)
+    c = o.to_c()
+    assert (c.samp_a, c.samp_b) == (2, 4)
+    with pytest.raises(ValueError):
+        brapprox.LRAOptions(sketchfact_randn_samp=lambda n: n * n).to_c()
+    o = brapprox.LRAOptions(sketch="sub")
+    c = o.to_c()
+    assert (c.samp_a, c.samp_b) == (4, 8)
+
+
+def test_result_type_accessors():
+    import brapprox
+    V = brapprox.IDPackedV(np.array([2, 1]), np.array([3]), np.array([[0.5], [0.25]]))
+    assert V["k"] == 2 and V.shape == (2, 3)
+    np.testing.assert_array_equal(V["p"], [2, 1, 3])
+    M = V.matrix()
+    np.testing.assert_allclose(M[:, [1, 0, 2]], np.hstack([np.eye(2), V.T]))
+    with pytest.raises(KeyError):
+        V["nope"]
+
+
+def test_no_cpu_fallback():
+    """On a box without a B200 the context cannot be created and says why."""
+    import brapprox
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present; the loud-failure path is exercised on CPU boxes")
+    except ImportError:
+        pass
+    with pytest.raises(brapprox.BraError) as e:
+        brapprox.Context(0)
+    assert e.value.code != 0
+    with pytest.raises(brapprox.BraError):
+        brapprox.idfact(np.eye(8))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "lowrankapprox.jl_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".jl")):
+                txt = open(os.path.join(dp, f)).read()
+                bad = re.findall(r"^\s*(?:import|from)\s+(?:lra_oracle|oracle)\b|#include\s+[\"<][^\">]*oracle",
+                                 txt, flags=re.M)
+                assert not bad, (f, bad)

@@ -76,6 +76,40 @@ def test_idfact_fast_mode_device_rng(ctx):
     assert err < 100 * 1e-12
 
 
+def _golden(pattern):
+    import glob
+    import os
+    return sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", pattern)))
+
+
+@pytest.mark.parametrize("path", _golden("id_*.npz"))
+def test_idfact_golden(ctx, path):
+    """The committed fixtures (oracle outputs from the real LAPACK) replayed through the CUDA path."""
+    import brapprox
+    z = np.load(path, allow_pickle=True)
+    kw = dict(z["opts"].tolist())
+    rand = [{k[len(f"rand{t}_"):]: z[k] for k in z.files if k.startswith(f"rand{t}_")} for t in range(int(z["n_rand"]))]
+    trans = str(z["trans"])
+    V = brapprox.idfact(z["A"], brapprox.LRAOptions(**kw), trans=trans, rand=rand, ctx=ctx)
+    np.testing.assert_array_equal(V.sk, z["sk"])
+    np.testing.assert_array_equal(V.rd, z["rd"])
+    Aop = z["A"] if trans == "n" else z["A"].T
+    C = Aop[:, V.sk - 1]
+    assert np.max(np.abs(C @ V.T - C @ z["T"])) <= 1e-10 * np.linalg.norm(Aop, 2)
+
+
+@pytest.mark.parametrize("path", _golden("qrcp_*.npz"))
+def test_qrcp_golden(ctx, path):
+    import brapprox
+    z = np.load(path, allow_pickle=True)
+    kw = dict(z["opts"].tolist())
+    Bg, pg, taug, kg, trg = brapprox.geqp3_adap(z["B0"], brapprox.LRAOptions(**kw), ctx=ctx)
+    assert kg == int(z["k"]) and trg["kb"] == z["kb"].tolist()
+    np.testing.assert_array_equal(pg, z["p"])
+    ns = int(z["steps"])
+    assert np.max(np.abs(np.triu(Bg[:ns]) - z["R"])) <= 1e-13 * abs(z["R"][0, 0])
+
+
 def test_errors_mirror_reference(ctx):
     import brapprox
     A = np.zeros((8, 8))

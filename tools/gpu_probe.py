@@ -29,11 +29,14 @@ for n in (int(a) for a in (sys.argv[1:] or ["2048", "8192"])):
     torch.cuda.synchronize()
     from brapprox._frontend import idfact_device
     for rep in range(3):
+        ctx.profile_enable(rep == 2)
         t0 = time.perf_counter()
         inf = idfact_device(A, rtol=1e-12, seed=1, ctx=ctx)
         dt = time.perf_counter() - t0
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
     rounds = [(int(inf.orders[t]), int(inf.ks[t]), int(inf.steps[t])) for t in range(inf.rounds)]
-    out[f"idfact_n{n}"] = {"wall_ms": dt * 1e3, "k": int(inf.k), "rounds": rounds}
+    out[f"idfact_n{n}"] = {"wall_ms": dt * 1e3, "k": int(inf.k), "rounds": rounds, "prof_ms": prof}
     print(json.dumps(out[f"idfact_n{n}"]), flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "probe.json"), "w"), indent=1)
