@@ -1,0 +1,101 @@
+#= BRApprox.jl -- Julia shim over libbrapprox.so (the B200-native sketch-then-factor path).
+
+   NOT EXECUTABLE IN THE BUILD IMAGE (no Julia there): this file documents the reference-side binding a
+   maintainer adds; the same C ABI is exercised by the Python host in ../brapprox/ and by tests/.
+
+   It re-defines the hot-path front-ends with the reference's signatures and return types
+   (src/id.jl:434-456, src/pqr.jl:285-320, src/psvd.jl:238-299) and leaves everything else
+   (result-type arithmetic, LinearOperator, CUR/pheig bodies) to LowRankApprox.jl itself.
+=#
+module BRApprox
+
+using LowRankApprox
+using LowRankApprox: LRAOptions, IDPackedV, chkopts!, chktrans
+import LowRankApprox: idfact
+
+const libbra = "libbrapprox.so"
+const BRA_MAX_ROUNDS = 24
+const SKETCH = Dict(:none => 0, :randn => 1, :sprn => 2, :srft => 3, :sub => 4)
+
+struct BraOpts
+  atol::Cdouble; rtol::Cdouble; rank::Int64; nb::Int64
+  sketch::Int32; sketch_randn_niter::Int32; sketchfact_adap::Int32; retval_mask::Int32
+  maxdet_tol::Cdouble; maxdet_niter::Int64; samp_a::Int64; samp_b::Int64
+  seed::UInt64; verb::Int32; reserved::Int32
+end
+
+struct BraRand
+  n_rounds::Int32; reserved::Int32
+  omega::Ptr{Ptr{Float64}}; d::Ptr{Ptr{Float64}}; idx::Ptr{Ptr{Int64}}
+  perm::Ptr{Ptr{Int64}}; s::Ptr{Ptr{Float64}}; r::Ptr{Ptr{Int64}}
+end
+
+struct BraInfo
+  m::Int64; n::Int64; k::Int64; ksvd::Int64; rounds::Int32; reserved::Int32
+  orders::NTuple{BRA_MAX_ROUNDS,Int64}; ks::NTuple{BRA_MAX_ROUNDS,Int64}; steps::NTuple{BRA_MAX_ROUNDS,Int64}
+end
+
+const CTX = Ref{Ptr{Cvoid}}(C_NULL)
+
+function __init__()
+  rc = ccall((:bra_create, libbra), Cint, (Ref{Ptr{Cvoid}}, Cint), CTX, 0)
+  rc == 0 || error("bra_create: ", unsafe_string(ccall((:bra_last_error, libbra), Cstring, (Ptr{Cvoid},), CTX[])))
+end
+
+# the *_samp closures cannot cross the ABI: evaluate into (a, b), order = a*n + b
+function affine(f::Function)
+  b = f(0); a = f(1) - b
+  all(f(n) == a*n + b for n in (2, 32, 64, 1000)) || throw(ArgumentError("sketchfact_*_samp must be affine"))
+  a, b
+end
+
+function BraOpts(o::LRAOptions)
+  f = o.sketch == :srft ? o.sketchfact_srft_samp : o.sketch == :sub ? o.sketchfact_sub_samp : o.sketchfact_randn_samp
+  a, b = o.sketch == :sprn ? (0, 0) : affine(f)
+  rv = lowercase(o.pqrfact_retval)
+  mask = (occursin("q", rv) ? 1 : 0) | (occursin("r", rv) ? 2 : 0) | (occursin("t", rv) ? 4 : 0)
+  BraOpts(o.atol, o.rtol, o.rank, o.nb, SKETCH[o.sketch], o.sketch_randn_niter, o.sketchfact_adap, mask,
+          o.maxdet_tol, o.maxdet_niter, a, b, rand(UInt64), o.verb, 0)
+end
+
+throw_bra(rc) = rc < 0 ? throw(ArgumentError("libbrapprox: argument $(-rc)")) :
+  error("libbrapprox status $rc: ", unsafe_string(ccall((:bra_last_error, libbra), Cstring, (Ptr{Cvoid},), CTX[])))
+
+# Draw the Omegas the reference would draw (crandn, src/util.jl:4), one per adaptive round.
+function draw_omegas(o::LRAOptions, mA::Integer, maxrounds::Integer=8)
+  n = o.nb
+  Ωs = Matrix{Float64}[]
+  for _ = 1:maxrounds
+    push!(Ωs, randn(o.sketchfact_randn_samp(n), mA)); n *= 2
+  end
+  Ωs
+end
+
+function idfact(trans::Symbol, A::Matrix{Float64}, opts::LRAOptions=LRAOptions(); args...)
+  chktrans(trans)
+  opts = copy(opts; args...)
+  opts.pqrfact_retval = "t"
+  chkopts!(opts, A)
+  (opts.sketch == :none || opts.maxdet_tol >= 0 || opts.sketch_randn_niter > 0) &&
+    return invoke(LowRankApprox.idfact, Tuple{Symbol,AbstractMatrix,LRAOptions}, trans, A, opts)   # untouched path
+  m, n = size(A)
+  Ωs = draw_omegas(opts, trans == :n ? m : n)
+  ptrs = [pointer(Ω) for Ω in Ωs]
+  GC.@preserve Ωs ptrs begin
+    rnd = BraRand(length(Ωs), 0, pointer(ptrs), C_NULL, C_NULL, C_NULL, C_NULL, C_NULL)
+    rc = ccall((:bra_idfact_f64, libbra), Cint,
+               (Ptr{Cvoid}, Cchar, Int64, Int64, Ptr{Float64}, Int64, Ref{BraOpts}, Ref{BraRand}),
+               CTX[], trans == :n ? 'n' : 'c', m, n, A, stride(A, 2), BraOpts(opts), rnd)
+  end
+  rc == 0 || throw_bra(rc)
+  info = Ref{BraInfo}()
+  ccall((:bra_get_info, libbra), Cint, (Ptr{Cvoid}, Ref{BraInfo}), CTX[], info)
+  k, nn = info[].k, info[].n
+  p = Vector{Int}(undef, nn)
+  ccall((:bra_fetch, libbra), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Int64), CTX[], 1, p, nn)
+  T = Matrix{Float64}(undef, k, nn - k)
+  k > 0 && nn > k && ccall((:bra_fetch, libbra), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Int64), CTX[], 2, T, k)
+  IDPackedV(p[1:k], p[k+1:end], T)                        # src/id.jl:445-446
+end
+
+end # module
