@@ -156,6 +156,18 @@ int bra_trsolve_T_f64(bra_ctx* ctx, int64_t k, int64_t n, const double* R, int64
 int bra_idfact_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A, int64_t lda,
                    const bra_opts* opts, const bra_rand* rnd);
 
+/* pqrfact(trans, A, opts) (src/pqr.jl:290-307), sketched path: idfact, then QR of the skeleton columns
+ * (randomised-preconditioned CholeskyQR2) and R = [R1 | R1*T].  Fetch BRA_F_Q (m_op x k), BRA_F_R (k x n_op),
+ * BRA_F_P, BRA_F_T.  Q and R equal the reference's Householder factors up to the sign of each column of Q /
+ * row of R (Cholesky-QR makes diag(R) > 0; LAPACK's sign is -sign(alpha)). */
+int bra_pqrfact_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A, int64_t lda,
+                    const bra_opts* opts, const bra_rand* rnd);
+
+/* psvdfact(A, opts) (src/psvd.jl:238-272): picks trans = 'n' if m >= n else 'c' like the reference, truncates
+ * with psvdrank (src/psvd.jl:301-308).  Fetch BRA_F_U (m x ksvd), BRA_F_S (ksvd), BRA_F_VT (ksvd x n). */
+int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* opts,
+                     const bra_rand* rnd);
+
 int bra_get_info(bra_ctx* ctx, bra_info* info);
 int bra_fetch(bra_ctx* ctx, int which, void* dst, int64_t ld);
 
@@ -180,6 +192,9 @@ int bra_profile_read(bra_ctx* ctx, double* ms, int64_t* calls);
 int bra_probe_fp64_peak(bra_ctx* ctx, double* out);
 /* Average latency (microseconds) of one LL all-gather exchange across `ctas` CTAs. */
 int bra_probe_exchange_latency(bra_ctx* ctx, int ctas, int iters, double* usec);
+
+/* Exchange design probe: mode 0 = push `hw` words to every inbox, mode 1 = two hops through `leaders`. */
+int bra_probe_exchange2(bra_ctx* ctx, int ctas, int hw, int mode, int leaders, int iters, double* usec);
 
 /* Kilo-cycles CTA 0 spent per phase of the last QRCP launch: local scan, publish, header gather,
  * Householder, update (clock64 deltas; diagnostic only). */

@@ -30,6 +30,14 @@ from ._frontend import (  # noqa: F401
     geqp3_adap,
     id,
     idfact,
+    idfact_device,
+    pqr,
+    pqrfact,
+    pqrfact_device,
+    psvd,
+    psvdfact,
+    psvdfact_device,
+    psvdvals,
     probe_exchange_latency,
     probe_fp64_peak,
     sketch,

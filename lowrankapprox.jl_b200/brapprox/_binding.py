@@ -79,6 +79,8 @@ lib.bra_geqp3_adap_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, C.POINTER(bra_opt
                                    C.POINTER(_i64), C.POINTER(_i64), _vp, _i64, C.POINTER(_i64)]
 lib.bra_trsolve_T_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, _vp, _i64]
 lib.bra_idfact_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand)]
+lib.bra_pqrfact_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand)]
+lib.bra_psvdfact_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand)]
 lib.bra_get_info.argtypes = [_vp, C.POINTER(bra_info)]
 lib.bra_fetch.argtypes = [_vp, C.c_int, _vp, _i64]
 lib.bra_profile_enable.argtypes = [_vp, C.c_int]
@@ -320,6 +322,7 @@ class PartialQR:
     R: np.ndarray
     p: np.ndarray
     rounds: List[Tuple[int, int]] = field(default_factory=list)
+    T: Optional[np.ndarray] = None
 
     @property
     def k(self) -> int:

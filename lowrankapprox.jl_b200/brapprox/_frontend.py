@@ -167,6 +167,78 @@ def id(A, *args, **kw):
     return V.sk, V.rd, V.T
 
 
+def pqrfact_device(A, opts: Optional[LRAOptions] = None, trans: str = "n", rand=None,
+                   ctx: Optional[Context] = None, **kw):
+    o = _opts(opts, kw)
+    ctx = ctx or default_context()
+    pA, m, n, lda, keepA = mat_arg(A)
+    rp = _RandPack(rand)
+    co = o.to_c()
+    ctx.check(lib.bra_pqrfact_f64(ctx.handle, _trans(trans), m, n, pA, lda, C.byref(co), C.byref(rp.c)))
+    return ctx.info()
+
+
+def pqrfact(A, opts: Optional[LRAOptions] = None, trans: str = "n", rand=None,
+            ctx: Optional[Context] = None, **kw):
+    """pqrfact(trans, A, opts; kw...) (src/pqr.jl:290-307), sketched path.  Returns PartialQR(Q, R, p) when
+    pqrfact_retval has q and r and not t (the default "qr"), like the reference (src/pqr.jl:305)."""
+    ctx = ctx or default_context()
+    o = _opts(opts, kw)
+    pqrfact_device(A, o, trans, rand, ctx)
+    inf, rounds, steps = _rounds(ctx)
+    k, n, m = int(inf.k), int(inf.n), int(inf.m)
+    p = ctx.fetch(B.F_P, (n,), np.int64)
+    Q = ctx.fetch(B.F_Q, (m, k)) if k > 0 else np.zeros((m, 0), order="F")
+    R = ctx.fetch(B.F_R, (k, n)) if k > 0 else np.zeros((0, n), order="F")
+    F = B.PartialQR(Q, R, p, rounds)
+    if "t" in o.pqrfact_retval:
+        F.T = ctx.fetch(B.F_T, (k, n - k))
+    return F
+
+
+def pqr(A, *args, **kw):
+    """pqr(...) -> (Q, R, p) (src/pqr.jl:312-318)."""
+    kw.setdefault("pqrfact_retval", "qr")
+    F = pqrfact(A, *args, **kw)
+    return F.Q, F.R, F.p
+
+
+def psvdfact_device(A, opts: Optional[LRAOptions] = None, rand=None, ctx: Optional[Context] = None, **kw):
+    o = _opts(opts, kw)
+    ctx = ctx or default_context()
+    pA, m, n, lda, keepA = mat_arg(A)
+    rp = _RandPack(rand)
+    co = o.to_c()
+    ctx.check(lib.bra_psvdfact_f64(ctx.handle, m, n, pA, lda, C.byref(co), C.byref(rp.c)))
+    return ctx.info()
+
+
+def psvdfact(A, opts: Optional[LRAOptions] = None, rand=None, ctx: Optional[Context] = None, **kw):
+    """psvdfact(A, opts; kw...) -> PartialSVD(U, S, Vt) (src/psvd.jl:238-272)."""
+    ctx = ctx or default_context()
+    pA, m, n, lda, keepA = mat_arg(A)
+    psvdfact_device(A, opts, rand, ctx, **kw)
+    inf, rounds, steps = _rounds(ctx)
+    ks = int(inf.ksvd)
+    if ks == 0:
+        return B.PartialSVD(np.zeros((m, 0)), np.zeros(0), np.zeros((0, n)), int(inf.k), rounds)
+    U = ctx.fetch(B.F_U, (m, ks))
+    S = ctx.fetch(B.F_S, (ks,))
+    Vt = ctx.fetch(B.F_VT, (ks, n))
+    return B.PartialSVD(U, S, Vt, int(inf.k), rounds)
+
+
+def psvd(A, *args, **kw):
+    """psvd(A, ...) -> (U, S, V) with V = Vt' (src/psvd.jl:296-299)."""
+    F = psvdfact(A, *args, **kw)
+    return F.U, F.S, F.Vt.T
+
+
+def psvdvals(A, *args, **kw):
+    """psvdvals(A, ...) (src/psvd.jl:274-290)."""
+    return psvdfact(A, *args, **kw).S
+
+
 def probe_fp64_peak(ctx: Optional[Context] = None) -> dict:
     ctx = ctx or default_context()
     out = (C.c_double * 8)()

@@ -484,7 +484,7 @@ int bra_fetch(bra_ctx* ctx, int which, void* dst, int64_t ld) {
     case BRA_F_Q:
       if (!r.have_Q) return BRA_ERR_NOTREADY;
       BRA_CHECK_ARG(ld >= (m > 1 ? m : 1), 4, "ld");
-      BRA_CUDA(copy2d(ctx, dst, ld, ctx->Q.p, m, m, k));
+      BRA_CUDA(copy2d(ctx, dst, ld, ctx->Q.p, (m + 1) & ~int64_t(1), m, k));
       break;
     case BRA_F_R:
       if (!r.have_R) return BRA_ERR_NOTREADY;
@@ -493,8 +493,8 @@ int bra_fetch(bra_ctx* ctx, int which, void* dst, int64_t ld) {
       break;
     case BRA_F_U:
       if (!r.have_svd) return BRA_ERR_NOTREADY;
-      BRA_CHECK_ARG(ld >= (m > 1 ? m : 1), 4, "ld");
-      BRA_CUDA(copy2d(ctx, dst, ld, ctx->U.p, m, m, r.ksvd));
+      BRA_CHECK_ARG(ld >= (r.svd_m > 1 ? r.svd_m : 1), 4, "ld");
+      BRA_CUDA(copy2d(ctx, dst, ld, ctx->U.p, r.svd_m, r.svd_m, r.ksvd));
       break;
     case BRA_F_S:
       if (!r.have_svd) return BRA_ERR_NOTREADY;
@@ -503,7 +503,7 @@ int bra_fetch(bra_ctx* ctx, int which, void* dst, int64_t ld) {
     case BRA_F_VT:
       if (!r.have_svd) return BRA_ERR_NOTREADY;
       BRA_CHECK_ARG(ld >= (r.ksvd > 1 ? r.ksvd : 1), 4, "ld");
-      BRA_CUDA(copy2d(ctx, dst, ld, ctx->Vt.p, k, r.ksvd, n));
+      BRA_CUDA(copy2d(ctx, dst, ld, ctx->Vt.p, r.ksvd, r.ksvd, r.svd_n));
       break;
     default:
       BRA_CHECK_ARG(false, 2, "which");

@@ -1,0 +1,211 @@
+// Fused pqrfact / psvdfact drivers over the idfact core (reference: src/pqr.jl:290-307, src/psvd.jl:238-272).
+#include "common.cuh"
+#include <vector>
+
+int bra_set_identity(bra_ctx* ctx, int k, double* J, int64_t ldj);
+int bra_fix_signs(bra_ctx* ctx, int64_t rows, int k, double* Q, int64_t ldq, double* R, int64_t ldr);
+int bra_gather_scale_cols(bra_ctx* ctx, const double* X, int64_t ldx, int64_t rows, int kk, const int* order_dev,
+                          const double* scale_dev, double* out, int64_t ldo);
+int bra_scatter_cols(bra_ctx* ctx, const double* src, int64_t lds, int64_t rows, int64_t n, const int64_t* jpvt1,
+                     double* dst, int64_t ldd);
+
+namespace {
+
+inline int64_t even(int64_t x) { return (x + 1) & ~int64_t(1); }
+
+// QR of the skeleton columns: ctx->Q (mA x k, ld = even(mA)) and ctx->R1 (k x k).
+int skeleton_qr(bra_ctx* ctx, char trans, const double* dA, int64_t lda, int64_t mA, int64_t k) {
+  const int64_t ldq = even(mA);
+  BRA_CUDA(ctx->Q.reserve((size_t)ldq * k * 8));
+  BRA_CUDA(ctx->R1.reserve((size_t)k * k * 8));
+  int rc = bra_gather_cols(ctx, trans, dA, lda, mA, k, ctx->jpvt.as<int64_t>(), ctx->Q.as<double>(), ldq);   // getcols
+  if (rc) return rc;
+  // Y = C R11^{-1}: R11 is the triangular factor of the SKETCH of these very columns (Omega*C = Q_B*R11)
+  rc = bra_trsolve_right_upper(ctx, mA, (int)k, ctx->R11.as<double>(), k, ctx->Q.as<double>(), ldq);
+  if (rc) return rc;
+  rc = bra_cholqr2(ctx, mA, (int)k, ctx->Q.as<double>(), ldq, ctx->R11.as<double>(), ctx->R1.as<double>());
+  if (rc) return rc;
+  // R1 = R_y2 R_y1 R11 inherits the signs of diag(R11) (Householder: -sign(alpha)); normalise to diag(R1) >= 0
+  return bra_fix_signs(ctx, mA, (int)k, ctx->Q.as<double>(), ldq, ctx->R1.as<double>(), k);
+}
+
+}  // namespace
+
+extern "C" {
+
+int bra_pqrfact_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A, int64_t lda,
+                    const bra_opts* opts, const bra_rand* rnd) {
+  if (!ctx) return -1;
+  int rc = bra_check_fact_args(ctx, trans, m, n, A, lda, opts);
+  if (rc) return rc;
+  BRA_CUDA(cudaSetDevice(ctx->device));
+  const double* dA;
+  int64_t dlda;
+  {
+    // stage a host-resident A once (same helper as idfact: is_device_ptr + copy)
+    if (is_device_ptr(A)) {
+      dA = A;
+      dlda = lda;
+    } else {
+      dlda = even(m);
+      BRA_CUDA(ctx->A_stage.reserve((size_t)dlda * (n > 0 ? n : 1) * 8));
+      if (m > 0 && n > 0)
+        BRA_CUDA(cudaMemcpy2DAsync(ctx->A_stage.p, (size_t)dlda * 8, A, (size_t)lda * 8, (size_t)m * 8, (size_t)n,
+                                   cudaMemcpyDefault, ctx->stream));
+      dA = ctx->A_stage.as<double>();
+    }
+  }
+  rc = bra_sketchfact_core(ctx, trans, m, n, dA, dlda, opts, rnd);      // V = idfact(trans, A, opts)
+  if (rc) return rc;
+  FactResult& res = ctx->res;
+  const int64_t k = res.k, mA = res.m, nA = res.n;
+  if (k > 0) {
+    rc = skeleton_qr(ctx, trans, dA, dlda, mA, k);                      // F = qr!(getcols(trans, A, V[:sk]))
+    if (rc) return rc;
+    // R = pqrr(F.R, V[:T]) = [R1 | R1*T]   (src/pqr.jl:330-340)
+    BRA_CUDA(ctx->Rfull.reserve((size_t)k * nA * 8));
+    BRA_CUDA(cudaMemcpyAsync(ctx->Rfull.p, ctx->R1.p, (size_t)k * k * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (nA > k) {
+      BRA_CUDA(ctx->scratch2.reserve((size_t)even(k) * k * 8));
+      rc = bra_transpose(ctx, ctx->R1.as<double>(), k, k, k, ctx->scratch2.as<double>(), even(k));   // R1^T, K-major
+      if (rc) return rc;
+      rc = bra_gemm_tn(ctx, ctx->scratch2.as<double>(), even(k), k, k, ctx->T.as<double>(), k, nA - k,
+                       ctx->Rfull.as<double>() + (size_t)k * k, k);
+      if (rc) return rc;
+    }
+  }
+  res.have_Q = true;
+  res.have_R = true;
+  BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BRA_OK;
+}
+
+int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* opts,
+                     const bra_rand* rnd) {
+  if (!ctx) return -1;
+  const char trans = (m >= n) ? 'n' : 'c';                              // src/psvd.jl:242,256
+  int rc = bra_check_fact_args(ctx, trans, m, n, A, lda, opts);
+  if (rc) return rc;
+  BRA_CUDA(cudaSetDevice(ctx->device));
+  const double* dA;
+  int64_t dlda;
+  if (is_device_ptr(A)) {
+    dA = A;
+    dlda = lda;
+  } else {
+    dlda = even(m);
+    BRA_CUDA(ctx->A_stage.reserve((size_t)dlda * (n > 0 ? n : 1) * 8));
+    if (m > 0 && n > 0)
+      BRA_CUDA(cudaMemcpy2DAsync(ctx->A_stage.p, (size_t)dlda * 8, A, (size_t)lda * 8, (size_t)m * 8, (size_t)n,
+                                 cudaMemcpyDefault, ctx->stream));
+    dA = ctx->A_stage.as<double>();
+  }
+  rc = bra_sketchfact_core(ctx, trans, m, n, dA, dlda, opts, rnd);      // V = idfact(trans, A, opts)
+  if (rc) return rc;
+  FactResult& res = ctx->res;
+  const int64_t k = res.k, mA = res.m, nA = res.n;
+  res.ksvd = 0;
+  res.svd_m = m;
+  res.svd_n = n;
+  if (k == 0) {
+    res.have_svd = true;
+    return BRA_OK;
+  }
+  rc = skeleton_qr(ctx, trans, dA, dlda, mA, k);                        // Q, R = qr!(getcols(...))
+  if (rc) return rc;
+
+  // Z = [I; T'] (nA x k): Q_z R_z by CholeskyQR2  (W = R1 [I T] P' = (R1 R_z') Q_z' P')
+  const int64_t ldz = even(nA);
+  BRA_CUDA(ctx->Z.reserve((size_t)ldz * k * 8));
+  double* Z = ctx->Z.as<double>();
+  rc = bra_set_identity(ctx, (int)k, Z, ldz);
+  if (rc) return rc;
+  if (nA > k) {
+    rc = bra_transpose(ctx, ctx->T.as<double>(), k, k, nA - k, Z + k, ldz);
+    if (rc) return rc;
+  }
+  BRA_CUDA(ctx->W.reserve((size_t)4 * k * k * 8));
+  double* Rz = ctx->W.as<double>();
+  double* X = Rz + (size_t)k * k;           // Jacobi matrix: X = M' = R_z R1'
+  double* J = X + (size_t)k * k;
+  double* Ysel = J + (size_t)k * k;
+  rc = bra_cholqr2(ctx, nA, (int)k, Z, ldz, nullptr, Rz);
+  if (rc) return rc;
+  // X[i,j] = sum_t Rz[i,t] R1[j,t]
+  rc = bra_gemm_generic(ctx, Rz, 1, k, ctx->R1.as<double>(), k, 1, k, k, k, X, k);
+  if (rc) return rc;
+  std::vector<double> sig((size_t)k);
+  std::vector<int> order((size_t)k);
+  BRA_CUDA(ctx->S.reserve((size_t)2 * k * 8));     // [0:k] column norms (unsorted), [k:2k] sorted values
+  rc = bra_jacobi_svd(ctx, (int)k, X, k, J, k, sig.data(), order.data());   // M' J = Y Sigma  =>  M = J Sigma Y'
+  if (rc) return rc;
+  // psvdrank (src/psvd.jl:301-308) on the sorted singular values
+  std::vector<double> ssort((size_t)k);
+  for (int64_t i = 0; i < k; ++i) ssort[(size_t)i] = sig[(size_t)order[(size_t)i]];
+  int64_t kk = k;
+  const double ptol = std::max(opts->atol, opts->rtol * ssort[0]);
+  for (int64_t i = 1; i < k; ++i)
+    if (ssort[(size_t)i] <= ptol) {
+      kk = i;
+      break;
+    }
+  res.ksvd = kk;
+  BRA_CUDA(ctx->aux_in1.reserve((size_t)k * 4));
+  BRA_CUDA(cudaMemcpyAsync(ctx->aux_in1.p, order.data(), (size_t)k * 4, cudaMemcpyHostToDevice, ctx->stream));
+  BRA_CUDA(ctx->S.reserve((size_t)2 * k * 8));
+  double* Ssorted = ctx->S.as<double>() + k;       // ctx->S[0:k] holds the unsorted norms (bra_jacobi_svd)
+  BRA_CUDA(cudaMemcpyAsync(Ssorted, ssort.data(), (size_t)k * 8, cudaMemcpyHostToDevice, ctx->stream));
+
+  // Ut (kk x mA) = Jsel' Q'   and   Vp (kk x nA) = Ysel' Qz'   -- both on the TMA + DMMA kernel (TN form)
+  const int64_t ldk = even(k);
+  BRA_CUDA(ctx->scratch2.reserve((size_t)ldk * std::max(mA, nA) * 8));
+  BRA_CUDA(ctx->scratch3.reserve((size_t)even(kk) * std::max(mA, nA) * 8 + 64));
+  BRA_CUDA(ctx->U.reserve((size_t)std::max(m, n) * kk * 8 + 64));
+  BRA_CUDA(ctx->Vt.reserve((size_t)std::max(m, n) * kk * 8 + 64));
+  double* Qt = ctx->scratch2.as<double>();
+  double* Out = ctx->scratch3.as<double>();
+  // left factor of op(A):  Uop = Q * J[:, order[:kk]]   (mA x kk)
+  rc = bra_gather_scale_cols(ctx, J, k, k, (int)kk, ctx->aux_in1.as<int>(), nullptr, Ysel, k);
+  if (rc) return rc;
+  rc = bra_transpose(ctx, ctx->Q.as<double>(), even(mA), mA, k, Qt, ldk);          // Q' (k x mA)
+  if (rc) return rc;
+  rc = bra_gemm_tn(ctx, Ysel, k, kk, k, Qt, ldk, mA, Out, even(kk));                 // (kk x mA) = Jsel' Q'
+  if (rc) return rc;
+  double* Uop_t = Out;          // kk x mA, ld even(kk)
+  if (trans == 'n') {
+    rc = bra_transpose(ctx, Uop_t, even(kk), kk, mA, ctx->U.as<double>(), mA);      // U (m x kk)
+  } else {
+    // op(A) = A': A ~ Vop S Uop'  =>  Vt = Uop' (kk x n), ld = kk
+    BRA_CUDA(cudaMemcpy2DAsync(ctx->Vt.p, (size_t)kk * 8, Uop_t, (size_t)even(kk) * 8, (size_t)kk * 8, (size_t)mA,
+                               cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  if (rc) return rc;
+  // right factor of op(A):  Vop' = Ysel' Qz' P'   with Ysel = X[:, order] / sigma
+  rc = bra_gather_scale_cols(ctx, X, k, k, (int)kk, ctx->aux_in1.as<int>(), ctx->S.as<double>(), Ysel, k);
+  if (rc) return rc;
+  rc = bra_transpose(ctx, Z, ldz, nA, k, Qt, ldk);                                   // Qz' (k x nA)
+  if (rc) return rc;
+  BRA_CUDA(ctx->B2.reserve((size_t)even(kk) * nA * 8));
+  rc = bra_gemm_tn(ctx, Ysel, k, kk, k, Qt, ldk, nA, ctx->B2.as<double>(), even(kk));
+  if (rc) return rc;
+  // undo the pivoting: columns j -> p[j]
+  rc = bra_scatter_cols(ctx, ctx->B2.as<double>(), even(kk), kk, nA, ctx->jpvt.as<int64_t>(), Out, even(kk));
+  if (rc) return rc;
+  if (trans == 'n') {
+    BRA_CUDA(cudaMemcpy2DAsync(ctx->Vt.p, (size_t)kk * 8, Out, (size_t)even(kk) * 8, (size_t)kk * 8, (size_t)nA,
+                               cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    rc = bra_transpose(ctx, Out, even(kk), kk, nA, ctx->U.as<double>(), nA);        // U = Vop (m x kk), m == nA
+    if (rc) return rc;
+  }
+  // singular values, sorted
+  BRA_CUDA(cudaMemcpyAsync(ctx->S.p, Ssorted, (size_t)kk * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  res.have_svd = true;
+  // bra_fetch reports U as m x ksvd and Vt as ksvd x n of the ORIGINAL A
+  res.svd_m = m;
+  res.svd_n = n;
+  BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BRA_OK;
+}
+
+}  // extern "C"

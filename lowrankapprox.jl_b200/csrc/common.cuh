@@ -57,6 +57,7 @@ struct FactResult {
   int64_t orders[BRA_MAX_ROUNDS];
   int64_t ks[BRA_MAX_ROUNDS];
   int64_t steps[BRA_MAX_ROUNDS];
+  int64_t svd_m = 0, svd_n = 0;  // dims of the ORIGINAL A for psvdfact's U (svd_m x ksvd) and Vt (ksvd x svd_n)
   bool have_T = false, have_Q = false, have_R = false, have_svd = false;
 };
 
@@ -148,7 +149,25 @@ int bra_transpose_omega(bra_ctx* ctx, const double* Om, int64_t ldo, int64_t l, 
 int bra_fill_randn(bra_ctx* ctx, double* dst, int64_t count, uint64_t seed, uint64_t stream_id);
 int bra_gemm_sketch(bra_ctx* ctx, const double* Omt, int64_t l, int64_t m, const double* A, int64_t lda,
                     int64_t n, double* B, int64_t ldb);
+int bra_gemm_tn(bra_ctx* ctx, const double* X, int64_t ldx, int64_t l, int64_t m, const double* Y, int64_t ldy,
+                int64_t n, double* C, int64_t ldc);
 bool bra_gemm_tma_ok(const double* A, int64_t lda, int64_t m, int64_t n);
+
+// tail.cu (pqrfact / psvdfact tails)
+int bra_gather_cols(bra_ctx* ctx, char trans, const double* A, int64_t lda, int64_t mC, int64_t k,
+                    const int64_t* idx1, double* C, int64_t ldc);
+int bra_transpose(bra_ctx* ctx, const double* src, int64_t lds, int64_t rows, int64_t cols, double* dst, int64_t ldd);
+int bra_trsolve_right_upper(bra_ctx* ctx, int64_t rows, int k, const double* R, int64_t ldr, double* Y, int64_t ldy);
+int bra_cholesky_upper(bra_ctx* ctx, int k, double* G, int64_t ldg, double* Rout, int64_t ldr);
+int bra_cholqr2(bra_ctx* ctx, int64_t rows, int k, double* Y, int64_t ldy, const double* Rpre, double* Rout);
+int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64_t ldj, double* sigma_host,
+                   int* order_host);
+extern "C" {
+int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* dA, int64_t lda,
+                        const bra_opts* o, const bra_rand* rnd);
+int bra_check_fact_args(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A, int64_t lda,
+                        const bra_opts* opts);
+}
 int bra_gemm_generic(bra_ctx* ctx, const double* Om, int64_t osi, int64_t osk, const double* A, int64_t sk,
                      int64_t sj, int64_t l, int64_t n, int64_t K, double* C, int64_t ldc);
 

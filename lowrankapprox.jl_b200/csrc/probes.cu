@@ -129,9 +129,101 @@ __global__ void __launch_bounds__(512, 1) exchange_kernel(PLL16* rec, int iters,
   if (tid == 0 && s_bad) *fail = 1;
 }
 
+__device__ __forceinline__ void pst(PLL16* p, uint32_t a, uint32_t b, uint32_t stamp) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(stamp), "r"(b), "r"(stamp)
+               : "memory");
+}
+__device__ __forceinline__ bool pld(const PLL16* p, uint32_t stamp) {
+  uint32_t lo, s0, hi, s1, spins = 0;
+  do {
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(lo), "=r"(s0), "=r"(hi), "=r"(s1)
+                 : "l"(p)
+                 : "memory");
+  } while ((s0 != stamp || s1 != stamp) && ++spins < (1u << 22));
+  return s0 == stamp && s1 == stamp;
+}
+
+// mode 0: push `hw` contiguous words into every CTA's inbox, each CTA polls its own inbox.
+// mode 1: two hops through `leaders` leader CTAs (slot -> group result -> everyone).
+__global__ void __launch_bounds__(512, 1) exchange2_kernel(PLL16* buf, int iters, uint32_t epoch, int hw, int mode,
+                                                           int leaders, int* fail) {
+  const int G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x;
+  __shared__ int s_bad;
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+  PLL16* inbox = buf;                                  // [2][G][G][hw]
+  PLL16* slot = buf;                                   // mode 1: [2][G][hw]
+  PLL16* gslot = buf + (size_t)2 * G * hw;             // mode 1: [2][leaders][hw]
+  for (int s = 0; s < iters; ++s) {
+    const uint32_t stamp = epoch + s;
+    const int par = s & 1;
+    if (mode == 0) {
+      for (int e = tid; e < G * hw; e += 512) {
+        const int dst = e / hw, w = e - dst * hw;
+        pst(inbox + (((size_t)par * G + dst) * G + cta) * hw + w, (uint32_t)s, (uint32_t)w, stamp);
+      }
+      for (int e = tid; e < G * hw; e += 512)
+        if (!pld(inbox + ((size_t)par * G + cta) * G * hw + e, stamp)) s_bad = 1;
+    } else {
+      if (tid < hw) pst(slot + ((size_t)par * G + cta) * hw + tid, (uint32_t)s, (uint32_t)tid, stamp);
+      if (cta < leaders) {
+        // group of leader c: CTAs c, c + leaders, c + 2*leaders, ...
+        const int members = (G - cta + leaders - 1) / leaders;
+        for (int e = tid; e < members * hw; e += 512) {
+          const int mbr = cta + (e / hw) * leaders, w = e % hw;
+          if (!pld(slot + ((size_t)par * G + mbr) * hw + w, stamp)) s_bad = 1;
+        }
+        __syncthreads();
+        if (tid < hw) pst(gslot + ((size_t)par * leaders + cta) * hw + tid, (uint32_t)s, (uint32_t)tid, stamp);
+      }
+      for (int e = tid; e < leaders * hw; e += 512)
+        if (!pld(gslot + (size_t)par * leaders * hw + e, stamp)) s_bad = 1;
+    }
+    __syncthreads();
+    if (s_bad) break;
+  }
+  if (tid == 0 && s_bad) *fail = 1;
+}
+
 }  // namespace
 
 extern "C" {
+
+int bra_probe_exchange2(bra_ctx* ctx, int ctas, int hw, int mode, int leaders, int iters, double* usec) {
+  if (!ctx) return -1;
+  BRA_CHECK_ARG(ctas >= 1 && ctas <= ctx->num_sms, 2, "ctas");
+  BRA_CHECK_ARG(hw >= 1 && hw <= 8, 3, "hw");
+  BRA_CHECK_ARG(leaders >= 1 && leaders <= ctas, 5, "leaders");
+  BRA_CUDA(cudaSetDevice(ctx->device));
+  const size_t words = (size_t)2 * ctas * ctas * hw + 64;
+  BRA_CUDA(ctx->scratch3.reserve(words * 16 + 16));
+  BRA_CUDA(cudaMemsetAsync(ctx->scratch3.p, 0, words * 16 + 16, ctx->stream));
+  PLL16* buf = ctx->scratch3.as<PLL16>();
+  int* fail = reinterpret_cast<int*>(buf + words);
+  uint32_t epoch = 1;
+  cudaEvent_t e0, e1;
+  BRA_CUDA(cudaEventCreate(&e0));
+  BRA_CUDA(cudaEventCreate(&e1));
+  void* args[] = {(void*)&buf, (void*)&iters, (void*)&epoch, (void*)&hw, (void*)&mode, (void*)&leaders, (void*)&fail};
+  BRA_CUDA(cudaEventRecord(e0, ctx->stream));
+  BRA_CUDA(cudaLaunchCooperativeKernel((void*)exchange2_kernel, dim3(ctas), dim3(512), args, 0, ctx->stream));
+  BRA_CUDA(cudaEventRecord(e1, ctx->stream));
+  BRA_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  BRA_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  ctx->launches++;
+  int hfail = 0;
+  BRA_CUDA(cudaMemcpy(&hfail, fail, 4, cudaMemcpyDeviceToHost));
+  if (hfail) {
+    ctx->set_error("exchange2 probe timed out");
+    return BRA_ERR_INTERNAL;
+  }
+  *usec = (double)ms * 1e3 / iters;
+  return BRA_OK;
+}
 
 int bra_probe_fp64_peak(bra_ctx* ctx, double* out) {
   if (!ctx) return -1;

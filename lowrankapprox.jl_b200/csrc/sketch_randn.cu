@@ -390,9 +390,15 @@ bool bra_gemm_tma_ok(const double* A, int64_t lda, int64_t m, int64_t n) {
 // B (l x n) = Omega (l x m) * A (m x n); Omt is the K-major copy of Omega, ldt = roundup(m, 2)
 int bra_gemm_sketch(bra_ctx* ctx, const double* Omt, int64_t l, int64_t m, const double* A, int64_t lda, int64_t n,
                     double* B, int64_t ldb) {
+  return bra_gemm_tn(ctx, Omt, (m + 1) & ~int64_t(1), l, m, A, lda, n, B, ldb);
+}
+
+// General "TN" product on the same TMA + DMMA kernel: C (l x n) = X^T Y with X (m x l, ldx) and Y (m x n, ldy)
+// both column-major, i.e. both contiguous along the contraction index.
+int bra_gemm_tn(bra_ctx* ctx, const double* Omt, int64_t ldt, int64_t l, int64_t m, const double* A, int64_t lda,
+                int64_t n, double* B, int64_t ldb) {
   if (l <= 0 || n <= 0) return BRA_OK;
-  const int64_t ldt = (m + 1) & ~int64_t(1);
-  if (!bra_gemm_tma_ok(A, lda, m, n))
+  if (!bra_gemm_tma_ok(A, lda, m, n) || !bra_gemm_tma_ok(Omt, ldt, m, l))
     return bra_gemm_generic(ctx, Omt, ldt, 1, A, 1, lda, l, n, m, B, ldb);
   CUtensorMap mapA;
   if (!make_map(&mapA, A, m, n, lda, TJ)) {

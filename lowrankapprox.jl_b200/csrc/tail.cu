@@ -1,0 +1,495 @@
+// pqrfact / psvdfact tails (reference: src/pqr.jl:297-305,330-340; src/psvd.jl:243-269,301-308;
+// R*V at src/id.jl:153-158,354-360).
+//
+// B200 design (not the reference's geqrt + gesdd):
+//  * QR of the skeleton columns C = A[:,sk] is a RANDOMISED-PRECONDITIONED CholeskyQR2: the sketch already
+//    produced R11 with Omega*C = Q_B*R11, so Y = C*R11^{-1} is well conditioned (kappa = O(10..100)) even
+//    though kappa(C) ~ 1/rtol; two Cholesky-QR passes on Y give Q orthonormal to machine precision and
+//    R1 = R_y2 * R_y1 * R11.  All O(m k^2) work is GEMM-shaped and runs on the TMA + DMMA kernel.
+//  * psvd: W = R1 [I T] P' is never formed.  Z = [I; T'] (n x k) is well conditioned, Z = Q_z R_z by
+//    CholeskyQR2, so W = (R1 R_z') Q_z' P' and the ill-conditioning lives in the k x k core M = R1 R_z'
+//    only, whose SVD is a one-sided Jacobi (Hestenes) on the graded matrix M' (accurate for small sigma).
+#include "common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+namespace {
+
+constexpr int TB = 32;
+
+// C[:, i] = A[:, idx[i]-1]  (trans 'n', C is m x k)   or   C[:, i] = A[idx[i]-1, :]'  (trans 'c', C is n x k)
+__global__ void gather_cols_kernel(char trans, const double* __restrict__ A, int64_t lda, int64_t mC, int64_t k,
+                                   const int64_t* __restrict__ idx1, double* __restrict__ C, int64_t ldc) {
+  for (int64_t i = blockIdx.x; i < k; i += gridDim.x) {
+    const int64_t s = idx1[i] - 1;
+    double* d = C + i * ldc;
+    if (trans == 'n') {
+      const double* a = A + s * lda;
+      for (int64_t r = threadIdx.x; r < mC; r += blockDim.x) d[r] = a[r];
+    } else {
+      for (int64_t r = threadIdx.x; r < mC; r += blockDim.x) d[r] = A[s + r * lda];
+    }
+  }
+}
+
+__global__ void transpose2_kernel(const double* __restrict__ src, int64_t lds, int64_t rows, int64_t cols,
+                                  double* __restrict__ dst, int64_t ldd) {
+  __shared__ double t[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+  for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+    int64_t r = r0 + threadIdx.x, c = c0 + y;
+    t[y][threadIdx.x] = (r < rows && c < cols) ? src[r + c * lds] : 0.0;
+  }
+  __syncthreads();
+  for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+    int64_t c = c0 + threadIdx.x, r = r0 + y;
+    if (r < rows && c < cols) dst[c + r * ldd] = t[threadIdx.x][y];
+  }
+}
+
+// Y <- Y R^{-1}, R upper triangular k x k.  CTA = 64 rows; column blocks left to right.
+__global__ void __launch_bounds__(256) trsolve_right_upper_kernel(int64_t rows, int k, const double* __restrict__ R,
+                                                                  int64_t ldr, double* __restrict__ Y, int64_t ldy) {
+  __shared__ double Ys[64][TB + 1];    // Ys[r][c] = Y[row0 + r, ib*32 + c]
+  __shared__ double Rs[TB][TB + 1];    // Rs[r][c] = R[ib*32 + r, jb*32 + c]
+  const int tid = threadIdx.x;
+  const int tx = tid & 63;             // row within the panel
+  const int ty = tid >> 6;             // 4 column groups of 8
+  const int64_t row0 = (int64_t)blockIdx.x * 64;
+  const int nblk = (k + TB - 1) / TB;
+  for (int jb = 0; jb < nblk; ++jb) {
+    const int c0 = jb * TB;
+    double acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = c0 + ty * 8 + u;
+      acc[u] = (row0 + tx < rows && c < k) ? Y[row0 + tx + (int64_t)c * ldy] : 0.0;
+    }
+    for (int ib = 0; ib < jb; ++ib) {
+      __syncthreads();
+      for (int e = tid; e < 64 * TB; e += 256) {
+        const int rr = e & 63, cc = e >> 6;
+        const int c = ib * TB + cc;
+        Ys[rr][cc] = (row0 + rr < rows && c < k) ? Y[row0 + rr + (int64_t)c * ldy] : 0.0;
+      }
+      for (int e = tid; e < TB * TB; e += 256) {
+        const int rr = e & 31, cc = e >> 5;
+        const int r = ib * TB + rr, c = c0 + cc;
+        Rs[rr][cc] = (r < k && c < k) ? R[r + (int64_t)c * ldr] : 0.0;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int kk = 0; kk < TB; ++kk) {
+        const double y = Ys[tx][kk];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = fma(-y, Rs[kk][ty * 8 + u], acc[u]);
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < TB * TB; e += 256) {
+      const int rr = e & 31, cc = e >> 5;
+      const int r = c0 + rr, c = c0 + cc;
+      Rs[rr][cc] = (r < k && c < k) ? R[r + (int64_t)c * ldr] : (rr == cc ? 1.0 : 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) Ys[tx][ty * 8 + u] = acc[u];
+    __syncthreads();
+    if (ty == 0) {
+      // forward substitution along the 32 columns of this block, one row per thread
+      double y[TB];
+#pragma unroll
+      for (int c = 0; c < TB; ++c) y[c] = Ys[tx][c];
+#pragma unroll
+      for (int c = 0; c < TB; ++c) {
+        y[c] = y[c] / Rs[c][c];
+#pragma unroll
+        for (int cc = c + 1; cc < TB; ++cc) y[cc] = fma(-y[c], Rs[c][cc], y[cc]);
+      }
+      if (row0 + tx < rows) {
+#pragma unroll
+        for (int c = 0; c < TB; ++c)
+          if (c0 + c < k) Y[row0 + tx + (int64_t)(c0 + c) * ldy] = y[c];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- blocked Cholesky G = L L^T (lower, in place), k x k ----
+// panel: every CTA factors the 32x32 diagonal block redundantly in smem, then solves its own 32-row block.
+__global__ void __launch_bounds__(256) chol_panel_kernel(int k, int j0, double* __restrict__ G, int64_t ldg, int* info) {
+  __shared__ double D[TB][TB + 1];
+  __shared__ double P[TB][TB + 1];
+  const int tid = threadIdx.x;
+  const int jbsz = min(TB, k - j0);
+  for (int e = tid; e < TB * TB; e += 256) {
+    const int rr = e & 31, cc = e >> 5;
+    D[rr][cc] = (rr < jbsz && cc < jbsz) ? G[(j0 + rr) + (int64_t)(j0 + cc) * ldg] : (rr == cc ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  if (tid < 32) {
+    // unblocked Cholesky of D by one warp: lane = row
+    const int r = tid;
+    for (int c = 0; c < TB; ++c) {
+      double d = D[c][c];
+      if (!(d > 0.0)) {
+        if (r == 0 && c < jbsz) atomicExch(info, j0 + c + 1);
+        d = 1.0;
+      }
+      const double piv = sqrt(d);
+      __syncwarp();
+      if (r == c) D[c][c] = piv;
+      if (r > c) D[r][c] = D[r][c] / piv;
+      __syncwarp();
+      if (r > c)
+        for (int cc = c + 1; cc <= r; ++cc) D[r][cc] = fma(-D[r][c], D[cc][c], D[r][cc]);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  const int rb = blockIdx.x;        // 0: the diagonal block itself; b > 0: row block j0 + 32*b
+  if (rb == 0) {
+    for (int e = tid; e < TB * TB; e += 256) {
+      const int rr = e & 31, cc = e >> 5;
+      if (rr < jbsz && cc < jbsz) G[(j0 + rr) + (int64_t)(j0 + cc) * ldg] = (rr >= cc) ? D[rr][cc] : 0.0;
+    }
+    return;
+  }
+  const int r0 = j0 + rb * TB;
+  for (int e = tid; e < TB * TB; e += 256) {
+    const int rr = e & 31, cc = e >> 5;
+    P[rr][cc] = (r0 + rr < k && cc < jbsz) ? G[(r0 + rr) + (int64_t)(j0 + cc) * ldg] : 0.0;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    // X L_jj^T = P: forward substitution along columns, one row per lane
+    const int r = tid;
+    for (int c = 0; c < TB; ++c) {
+      double x = P[r][c];
+      for (int cc = 0; cc < c; ++cc) x = fma(-P[r][cc], D[c][cc], x);
+      P[r][c] = x / D[c][c];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < TB * TB; e += 256) {
+    const int rr = e & 31, cc = e >> 5;
+    if (r0 + rr < k && cc < jbsz) G[(r0 + rr) + (int64_t)(j0 + cc) * ldg] = P[rr][cc];
+  }
+}
+
+// trailing update: G[I,J] -= L[I,j] L[J,j]^T for 32x32 tiles I >= J > j
+__global__ void __launch_bounds__(256) chol_update_kernel(int k, int j0, double* __restrict__ G, int64_t ldg) {
+  __shared__ double Li[TB][TB + 1];
+  __shared__ double Lj[TB][TB + 1];
+  const int tid = threadIdx.x;
+  const int nb = (k - j0 - 1) / TB;          // trailing blocks (those after block j)
+  // linear index -> (I, J), I >= J
+  int t = blockIdx.x, I = 0;
+  while (t > I) {
+    t -= I + 1;
+    ++I;
+  }
+  const int J = t;
+  if (I >= nb) return;
+  const int ri = j0 + (I + 1) * TB, rj = j0 + (J + 1) * TB;
+  for (int e = tid; e < TB * TB; e += 256) {
+    const int rr = e & 31, cc = e >> 5;
+    Li[rr][cc] = (ri + rr < k && j0 + cc < k && cc < TB) ? G[(ri + rr) + (int64_t)(j0 + cc) * ldg] : 0.0;
+    Lj[rr][cc] = (rj + rr < k && j0 + cc < k && cc < TB) ? G[(rj + rr) + (int64_t)(j0 + cc) * ldg] : 0.0;
+  }
+  __syncthreads();
+  const int tx = tid & 31, ty = tid >> 5;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int c = ty * 4 + u;
+    double acc = 0.0;
+#pragma unroll 8
+    for (int kk = 0; kk < TB; ++kk) acc = fma(Li[tx][kk], Lj[c][kk], acc);
+    if (ri + tx < k && rj + c < k) G[(ri + tx) + (int64_t)(rj + c) * ldg] -= acc;
+  }
+}
+
+// Rout (upper) = L^T, zeros below the diagonal
+__global__ void tri_transpose_kernel(int k, const double* __restrict__ L, int64_t ldl, double* __restrict__ R,
+                                     int64_t ldr) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)k * k; e += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e % k), j = (int)(e / k);
+    R[i + (int64_t)j * ldr] = (i <= j) ? L[j + (int64_t)i * ldl] : 0.0;
+  }
+}
+
+__global__ void add_identity_kernel(int k, double* __restrict__ G, int64_t ldg) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) G[i + (int64_t)i * ldg] += 1.0;
+}
+
+// ---- one-sided Jacobi (Hestenes) on the columns of X (k x k), rotations accumulated into J ----
+__global__ void __launch_bounds__(128) jacobi_stage_kernel(int k, int np, int stage, double* __restrict__ X, int64_t ldx,
+                                                           double* __restrict__ Jm, int64_t ldj, double tol, int* flag) {
+  // round-robin (chess tournament) ordering over np = even number of players
+  const int i = blockIdx.x;
+  int p, q;
+  if (i == 0) {
+    p = np - 1;
+    q = stage % (np - 1);
+  } else {
+    p = (stage + i) % (np - 1);
+    q = (stage + np - 1 - i) % (np - 1);
+  }
+  if (p > q) {
+    const int t = p;
+    p = q;
+    q = t;
+  }
+  if (q >= k) return;        // padding player
+  double* xp = X + (int64_t)p * ldx;
+  double* xq = X + (int64_t)q * ldx;
+  double a = 0.0, b = 0.0, c = 0.0;
+  for (int r = threadIdx.x; r < k; r += 128) {
+    const double u = xp[r], v = xq[r];
+    a = fma(u, u, a);
+    b = fma(v, v, b);
+    c = fma(u, v, c);
+  }
+  __shared__ double red[3][4];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = a;
+    red[1][threadIdx.x >> 5] = b;
+    red[2][threadIdx.x >> 5] = c;
+  }
+  __syncthreads();
+  a = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+  b = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+  c = red[2][0] + red[2][1] + red[2][2] + red[2][3];
+  if (fabs(c) <= tol * sqrt(a) * sqrt(b) || c == 0.0) return;
+  if (threadIdx.x == 0) *flag = 1;
+  // rotation that orthogonalises the pair, keeping the larger column first (de Rijk)
+  const double zeta = (b - a) / (2.0 * c);
+  const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+  const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+  for (int r = threadIdx.x; r < k; r += 128) {
+    const double u = xp[r], v = xq[r];
+    xp[r] = cs * u - sn * v;
+    xq[r] = sn * u + cs * v;
+    const double ju = Jm[r + (int64_t)p * ldj], jv = Jm[r + (int64_t)q * ldj];
+    Jm[r + (int64_t)p * ldj] = cs * ju - sn * jv;
+    Jm[r + (int64_t)q * ldj] = sn * ju + cs * jv;
+  }
+}
+
+__global__ void set_identity_kernel(int k, double* __restrict__ J, int64_t ldj) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)k * k; e += (int64_t)gridDim.x * blockDim.x)
+    J[(e % k) + (e / k) * ldj] = ((e % k) == (e / k)) ? 1.0 : 0.0;
+}
+
+__global__ void col_norms_kernel(int k, const double* __restrict__ X, int64_t ldx, double* __restrict__ nrm) {
+  const int j = blockIdx.x;
+  double a = 0.0;
+  for (int r = threadIdx.x; r < k; r += 128) a = fma(X[r + (int64_t)j * ldx], X[r + (int64_t)j * ldx], a);
+  __shared__ double red[4];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) nrm[j] = sqrt(red[0] + red[1] + red[2] + red[3]);
+}
+
+}  // namespace
+
+int bra_gather_cols(bra_ctx* ctx, char trans, const double* A, int64_t lda, int64_t mC, int64_t k, const int64_t* idx1,
+                    double* C, int64_t ldc) {
+  if (k <= 0 || mC <= 0) return BRA_OK;
+  ProfScope ps(ctx, BRA_PROF_TAIL);
+  gather_cols_kernel<<<(unsigned)std::min<int64_t>(k, 148 * 8), 256, 0, ctx->stream>>>(trans, A, lda, mC, k, idx1, C, ldc);
+  ctx->launches++;
+  BRA_CUDA(cudaGetLastError());
+  return BRA_OK;
+}
+
+int bra_transpose(bra_ctx* ctx, const double* src, int64_t lds, int64_t rows, int64_t cols, double* dst, int64_t ldd) {
+  if (rows <= 0 || cols <= 0) return BRA_OK;
+  ProfScope ps(ctx, BRA_PROF_TAIL);
+  dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
+  transpose2_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(src, lds, rows, cols, dst, ldd);
+  ctx->launches++;
+  BRA_CUDA(cudaGetLastError());
+  return BRA_OK;
+}
+
+int bra_trsolve_right_upper(bra_ctx* ctx, int64_t rows, int k, const double* R, int64_t ldr, double* Y, int64_t ldy) {
+  if (rows <= 0 || k <= 0) return BRA_OK;
+  ProfScope ps(ctx, BRA_PROF_TAIL);
+  trsolve_right_upper_kernel<<<(unsigned)((rows + 63) / 64), 256, 0, ctx->stream>>>(rows, k, R, ldr, Y, ldy);
+  ctx->launches++;
+  BRA_CUDA(cudaGetLastError());
+  return BRA_OK;
+}
+
+// G (k x k, symmetric positive definite, destroyed) -> Rout upper triangular with G = Rout^T Rout
+int bra_cholesky_upper(bra_ctx* ctx, int k, double* G, int64_t ldg, double* Rout, int64_t ldr) {
+  if (k <= 0) return BRA_OK;
+  ProfScope ps(ctx, BRA_PROF_TAIL);
+  int* info = ctx->info.as<int>() + 12;
+  BRA_CUDA(cudaMemsetAsync(info, 0, 4, ctx->stream));
+  const int nblk = (k + TB - 1) / TB;
+  for (int jb = 0; jb < nblk; ++jb) {
+    const int j0 = jb * TB;
+    const int rowblocks = nblk - jb;
+    chol_panel_kernel<<<rowblocks, 256, 0, ctx->stream>>>(k, j0, G, ldg, info);
+    const int nb = nblk - jb - 1;
+    if (nb > 0) chol_update_kernel<<<nb * (nb + 1) / 2, 256, 0, ctx->stream>>>(k, j0, G, ldg);
+    ctx->launches += 2;
+  }
+  tri_transpose_kernel<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(k, G, ldg, Rout, ldr);
+  ctx->launches++;
+  BRA_CUDA(cudaGetLastError());
+  return BRA_OK;
+}
+
+// Two Cholesky-QR passes on Y (rows x k, well conditioned): on return Y holds Q (orthonormal columns) and
+// Rout (k x k, ld k) = R_y2 * R_y1 * Rpre (Rpre = the preconditioner already divided out of Y, or null).
+int bra_cholqr2(bra_ctx* ctx, int64_t rows, int k, double* Y, int64_t ldy, const double* Rpre, double* Rout) {
+  if (k <= 0) return BRA_OK;
+  BRA_CUDA(ctx->G.reserve((size_t)k * k * 8));
+  BRA_CUDA(ctx->scratch.reserve((size_t)3 * k * k * 8));
+  double* G = ctx->G.as<double>();
+  double* Ry = ctx->scratch.as<double>();          // current pass factor
+  double* Racc = Ry + (size_t)k * k;                // accumulated product
+  double* Rtmp = Racc + (size_t)k * k;
+  int rc;
+  for (int pass = 0; pass < 2; ++pass) {
+    if ((rc = bra_gemm_tn(ctx, Y, ldy, k, rows, Y, ldy, k, G, k))) return rc;          // G = Y^T Y
+    if ((rc = bra_cholesky_upper(ctx, k, G, k, Ry, k))) return rc;
+    if ((rc = bra_trsolve_right_upper(ctx, rows, k, Ry, k, Y, ldy))) return rc;         // Y <- Y Ry^{-1}
+    // Racc <- Ry * (pass == 0 ? Rpre : Racc)     (k x k upper-triangular products)
+    const double* prev = (pass == 0) ? Rpre : Racc;
+    if (prev) {
+      // C = Ry * prev : generic strided GEMM, Om(i,kk) = Ry[i + kk*k], Aop(kk,j) = prev[kk + j*k]
+      if ((rc = bra_gemm_generic(ctx, Ry, 1, k, prev, 1, k, k, k, k, Rtmp, k))) return rc;
+      BRA_CUDA(cudaMemcpyAsync(Racc, Rtmp, (size_t)k * k * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+      BRA_CUDA(cudaMemcpyAsync(Racc, Ry, (size_t)k * k * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  }
+  BRA_CUDA(cudaMemcpyAsync(Rout, Racc, (size_t)k * k * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  int hinfo = 0;
+  BRA_CUDA(cudaMemcpyAsync(&hinfo, ctx->info.as<int>() + 12, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (hinfo != 0) {
+    ctx->set_error("CholeskyQR2: Gram matrix not positive definite at pivot " + std::to_string(hinfo));
+    return BRA_ERR_INTERNAL;
+  }
+  return BRA_OK;
+}
+
+// One-sided Jacobi on the columns of X (k x k): X J = U diag(sigma).  On return X holds U diag(sigma) (columns
+// unsorted), J the accumulated rotations, sigma_host the column norms, order_host the descending order.
+int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64_t ldj, double* sigma_host,
+                   int* order_host) {
+  if (k <= 0) return BRA_OK;
+  ProfScope ps(ctx, BRA_PROF_TAIL);
+  set_identity_kernel<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(k, J, ldj);
+  ctx->launches++;
+  const int np = (k + 1) & ~1;
+  int* flag = ctx->info.as<int>() + 13;
+  const double tol = 1e-15;
+  bool converged = (k == 1);
+  for (int sweep = 0; sweep < 40 && !converged; ++sweep) {
+    BRA_CUDA(cudaMemsetAsync(flag, 0, 4, ctx->stream));
+    for (int st = 0; st < np - 1; ++st)
+      jacobi_stage_kernel<<<np / 2, 128, 0, ctx->stream>>>(k, np, st, X, ldx, J, ldj, tol, flag);
+    ctx->launches += np - 1;
+    int h = 0;
+    BRA_CUDA(cudaMemcpyAsync(&h, flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+    converged = (h == 0);
+  }
+  BRA_CUDA(ctx->S.reserve((size_t)k * 8));
+  col_norms_kernel<<<k, 128, 0, ctx->stream>>>(k, X, ldx, ctx->S.as<double>());
+  ctx->launches++;
+  BRA_CUDA(cudaMemcpyAsync(sigma_host, ctx->S.p, (size_t)k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::iota(order_host, order_host + k, 0);
+  std::stable_sort(order_host, order_host + k, [&](int a, int b) { return sigma_host[a] > sigma_host[b]; });
+  if (!converged) {
+    ctx->set_error("Jacobi SVD did not converge in 40 sweeps");
+    return BRA_ERR_INTERNAL;
+  }
+  return BRA_OK;
+}
+
+namespace {
+// out[:, j] = X[:, order[j]] * (scale ? 1/scale[order[j]] : 1)
+__global__ void gather_scale_cols_kernel(const double* __restrict__ X, int64_t ldx, int64_t rows, int kk,
+                                         const int* __restrict__ order, const double* __restrict__ scale,
+                                         double* __restrict__ out, int64_t ldo) {
+  for (int j = blockIdx.x; j < kk; j += gridDim.x) {
+    const int s = order[j];
+    const double f = scale ? (scale[s] != 0.0 ? 1.0 / scale[s] : 0.0) : 1.0;
+    for (int64_t r = threadIdx.x; r < rows; r += blockDim.x) out[r + (int64_t)j * ldo] = X[r + (int64_t)s * ldx] * f;
+  }
+}
+// dst[:, jpvt[j]-1] = src[:, j]
+__global__ void scatter_cols_kernel(const double* __restrict__ src, int64_t lds, int64_t rows, int64_t n,
+                                    const int64_t* __restrict__ jpvt1, double* __restrict__ dst, int64_t ldd) {
+  for (int64_t j = blockIdx.x; j < n; j += gridDim.x) {
+    const double* s = src + j * lds;
+    double* d = dst + (jpvt1[j] - 1) * ldd;
+    for (int64_t r = threadIdx.x; r < rows; r += blockDim.x) d[r] = s[r];
+  }
+}
+}  // namespace
+
+namespace {
+// make diag(R) >= 0: row i of R and column i of Q are flipped together (Q R unchanged)
+__global__ void fix_signs_kernel(int64_t rows, int k, double* __restrict__ Q, int64_t ldq, double* __restrict__ R,
+                                 int64_t ldr) {
+  for (int i = blockIdx.x; i < k; i += gridDim.x) {
+    if (!(R[i + (int64_t)i * ldr] < 0.0)) continue;      // uniform per block: every thread reads the same entry
+    __syncthreads();
+    for (int64_t r = threadIdx.x; r < rows; r += blockDim.x) Q[r + (int64_t)i * ldq] = -Q[r + (int64_t)i * ldq];
+    for (int j = i + threadIdx.x; j < k; j += blockDim.x) R[i + (int64_t)j * ldr] = -R[i + (int64_t)j * ldr];
+    __syncthreads();
+  }
+}
+}  // namespace
+
+int bra_fix_signs(bra_ctx* ctx, int64_t rows, int k, double* Q, int64_t ldq, double* R, int64_t ldr) {
+  if (k <= 0) return BRA_OK;
+  fix_signs_kernel<<<std::min(k, 148 * 4), 256, 0, ctx->stream>>>(rows, k, Q, ldq, R, ldr);
+  ctx->launches++;
+  BRA_CUDA(cudaGetLastError());
+  return BRA_OK;
+}
+
+int bra_set_identity(bra_ctx* ctx, int k, double* J, int64_t ldj) {
+  if (k <= 0) return BRA_OK;
+  set_identity_kernel<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(k, J, ldj);
+  ctx->launches++;
+  BRA_CUDA(cudaGetLastError());
+  return BRA_OK;
+}
+
+int bra_gather_scale_cols(bra_ctx* ctx, const double* X, int64_t ldx, int64_t rows, int kk, const int* order_dev,
+                          const double* scale_dev, double* out, int64_t ldo) {
+  if (kk <= 0 || rows <= 0) return BRA_OK;
+  gather_scale_cols_kernel<<<std::min(kk, 148 * 8), 128, 0, ctx->stream>>>(X, ldx, rows, kk, order_dev, scale_dev, out, ldo);
+  ctx->launches++;
+  BRA_CUDA(cudaGetLastError());
+  return BRA_OK;
+}
+
+int bra_scatter_cols(bra_ctx* ctx, const double* src, int64_t lds, int64_t rows, int64_t n, const int64_t* jpvt1,
+                     double* dst, int64_t ldd) {
+  if (n <= 0 || rows <= 0) return BRA_OK;
+  scatter_cols_kernel<<<(unsigned)std::min<int64_t>(n, 148 * 8), 128, 0, ctx->stream>>>(src, lds, rows, n, jpvt1, dst, ldd);
+  ctx->launches++;
+  BRA_CUDA(cudaGetLastError());
+  return BRA_OK;
+}

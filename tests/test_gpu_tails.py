@@ -1,0 +1,103 @@
+"""GPU parity of the pqrfact / psvdfact tails against the oracle on identical Omega.
+
+Criteria (hard part 5):
+  pqrfact : k, p identical; ||Q'Q - I|| <= 1e-13; Q, R equal to the oracle's Householder factors AFTER normalising
+            the per-column sign (Cholesky-QR gives diag(R) > 0, LAPACK's is -sign(alpha)), weighted like tau in the
+            stage-wise tests (column i of Q is determined to eps*|R11|/|R_ii|); ||A - QRP'|| within 2x of the oracle's.
+  psvdfact: rank after psvdrank identical; |dsigma| <= 1e-10*sigma_1; U diag(S)/sigma_1 and diag(S) Vt/sigma_1
+            entrywise within 1e-10 after sign-fixing; reconstruction error within 2x of the oracle's.
+"""
+import numpy as np
+import pytest
+
+import lra_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(fn_o, fn_g, A, kw, seed=0, **extra):
+    rin = o.RandomInputs(seed)
+    Fo = fn_o(A, o.LRAOptions(**kw), rin, **extra)
+    return Fo, rin
+
+
+@pytest.mark.parametrize("m,n,r,rtol,trans", [(1024, 768, 100, 1e-11, "n"), (600, 900, 64, 1e-9, "n"),
+                                               (512, 400, 80, 1e-10, "c")])
+def test_pqrfact_matches_oracle(ctx, m, n, r, rtol, trans):
+    import brapprox
+    A = o.decaying_matrix(m, n, r, 13.0, r, seed=m + n)
+    rin = o.RandomInputs(1)
+    Fo = o.pqrfact(A, o.LRAOptions(rtol=rtol), rin, trans)
+    Fg = brapprox.pqrfact(A, brapprox.LRAOptions(rtol=rtol), trans=trans, rand=rin.drawn, ctx=ctx)
+    assert Fg.k == Fo.k
+    np.testing.assert_array_equal(Fg.p, Fo.p)
+    k = Fo.k
+    assert np.linalg.norm(Fg.Q.T @ Fg.Q - np.eye(k)) <= 1e-13 * np.sqrt(k)
+    Aop = A if trans == "n" else A.T
+    nrm = np.linalg.norm(Aop)
+    eo = np.linalg.norm(Aop - Fo.matrix()) / nrm
+    eg = np.linalg.norm(Aop - Fg.matrix()) / nrm
+    assert eg <= 2 * eo + 1e-15
+    # factor parity modulo the Householder sign convention
+    d = np.sign(np.diag(Fo.R[:, :k]))
+    Qo, Ro = Fo.Q * d, Fo.R * d[:, None]
+    r11 = abs(Ro[0, 0])
+    w = np.abs(np.diag(Ro)) / r11
+    assert np.max(np.abs(Fg.R - Ro)) <= 1e-10 * r11
+    assert np.max(np.abs(Fg.Q - Qo) * w[None, :]) <= 1e-10
+
+
+def _signfix(U, Vt, Uref):
+    s = np.sign(np.sum(U * Uref, axis=0))
+    s[s == 0] = 1.0
+    return U * s, Vt * s[:, None]
+
+
+@pytest.mark.parametrize("m,n,r,rtol", [(1024, 768, 100, 1e-11), (700, 500, 64, 1e-8), (400, 640, 80, 1e-10)])
+def test_psvdfact_matches_oracle(ctx, m, n, r, rtol):
+    import brapprox
+    A = o.decaying_matrix(m, n, r, 13.0, r, seed=3 * m + n)
+    rin = o.RandomInputs(2)
+    So = o.psvdfact(A, o.LRAOptions(rtol=rtol), rin)
+    Sg = brapprox.psvdfact(A, brapprox.LRAOptions(rtol=rtol), rand=rin.drawn, ctx=ctx)
+    assert Sg.k_id == So.k_id
+    assert len(Sg.S) == len(So.S)
+    s1 = So.S[0]
+    assert np.max(np.abs(Sg.S - So.S)) <= 1e-10 * s1
+    assert np.all(np.diff(Sg.S) <= 0)
+    kk = len(So.S)
+    assert np.linalg.norm(Sg.U.T @ Sg.U - np.eye(kk)) <= 1e-12 * np.sqrt(kk)
+    assert np.linalg.norm(Sg.Vt @ Sg.Vt.T - np.eye(kk)) <= 1e-9      # rows for tiny sigma are noise-limited
+    Ug, Vtg = _signfix(Sg.U, Sg.Vt, So.U)
+    assert np.max(np.abs(Ug * Sg.S - So.U * So.S)) <= 1e-10 * s1
+    assert np.max(np.abs(Vtg * Sg.S[:, None] - So.Vt * So.S[:, None])) <= 1e-10 * s1
+    nrm = np.linalg.norm(A, 2)
+    eo = np.linalg.norm(A - So.matrix(), 2) / nrm
+    eg = np.linalg.norm(A - Sg.matrix(), 2) / nrm
+    assert eg <= 2 * eo + 1e-15
+
+
+def test_psvdfact_reference_inequality(ctx):
+    """test/psvd.jl:28-32 on the 128 x 64 Fourier (real part) matrix, fast mode (device Omega)."""
+    import brapprox
+    rng = np.random.default_rng(0)
+    A = np.asfortranarray(o.matrixlib_fourier(rng.random(128), rng.random(64)).real)
+    rtol = 5 * o.EPS
+    F = brapprox.psvdfact(A, rtol=rtol, seed=3, ctx=ctx)
+    assert np.linalg.norm(A - F.matrix()) < 100 * rtol * np.linalg.norm(A)
+    s = brapprox.psvdvals(A, rank=len(F.S), rtol=0.0, seed=4, ctx=ctx)
+    assert np.linalg.norm(s[:len(F.S)] - F.S) < 100 * rtol * np.linalg.norm(F.S)
+    G = brapprox.pqrfact(A, rtol=rtol, seed=5, ctx=ctx)
+    assert np.linalg.norm(A - G.matrix()) < 100 * rtol * np.linalg.norm(A)
+
+
+def test_tail_kernels_standalone(ctx):
+    """The building blocks through their effect: Hilbert-256 pqrfact (kappa(C) ~ 1e12) keeps Q orthonormal."""
+    import brapprox
+    A = o.matrixlib_hilb(256)
+    F = brapprox.pqrfact(A, rtol=1e-12, seed=1, ctx=ctx)
+    k = F.k
+    assert 15 <= k <= 25
+    assert np.linalg.norm(F.Q.T @ F.Q - np.eye(k)) <= 1e-13 * np.sqrt(k)
+    assert np.all(np.diag(F.R[:, :k]) > 0)
+    assert np.linalg.norm(A - F.matrix(), 2) <= 1e-10 * np.linalg.norm(A, 2)
