@@ -180,7 +180,10 @@ int bra_fetch(bra_ctx* ctx, int which, void* dst, int64_t ld);
 #define BRA_PROF_TRSOLVE 5   /* T = R11^-1 R12 */
 #define BRA_PROF_TAIL 6      /* pqr / psvd tail kernels */
 #define BRA_PROF_SKETCH_OTHER 7 /* srft / sprn / sub sketch kernels */
-#define BRA_PROF_NTAGS 8
+#define BRA_PROF_SVD 8       /* psvd core: k x k Jacobi SVD */
+#define BRA_PROF_QR 9        /* skeleton / Z CholeskyQR2 (Gram GEMMs, Cholesky, triangular solves) */
+#define BRA_PROF_TAILGEMM 10 /* GEMMs of the pqr / psvd tails (same TMA + DMMA kernel) */
+#define BRA_PROF_NTAGS 11
 int bra_profile_enable(bra_ctx* ctx, int on);            /* also clears the accumulators */
 /* accumulated milliseconds and span counts per tag since the last enable; syncs the stream */
 int bra_profile_read(bra_ctx* ctx, double* ms, int64_t* calls);
@@ -199,6 +202,11 @@ int bra_probe_exchange2(bra_ctx* ctx, int ctas, int hw, int mode, int leaders, i
 /* Kilo-cycles CTA 0 spent per phase of the last QRCP launch: local scan, publish, header gather,
  * Householder, update (clock64 deltas; diagnostic only). */
 int bra_debug_qrcp_phases(bra_ctx* ctx, int32_t* out5);
+/* Sweeps the last psvd core (k x k Jacobi SVD) needed. */
+int bra_debug_jacobi_sweeps(bra_ctx* ctx);
+/* Kilo-cycles thread 0 spent in the last Jacobi launch: panel load, round sync, panel store, grid barrier,
+ * dot products, shuffles, rotation scalars, rotation apply (out8[0..7]). */
+int bra_debug_jacobi_phases(bra_ctx* ctx, int32_t* out8);
 /* Same, for every CTA of the last QRCP launch: out[cta*8 + phase], ctas <= 160. */
 int bra_debug_qrcp_phases_all(bra_ctx* ctx, int32_t* out, int ctas);
 

@@ -85,7 +85,7 @@ lib.bra_get_info.argtypes = [_vp, C.POINTER(bra_info)]
 lib.bra_fetch.argtypes = [_vp, C.c_int, _vp, _i64]
 lib.bra_profile_enable.argtypes = [_vp, C.c_int]
 lib.bra_profile_read.argtypes = [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
-PROF_TAGS = ["omega", "gemm", "splitk", "qrcp", "gather", "trsolve", "tail", "sketch_other"]
+PROF_TAGS = ["omega", "gemm", "splitk", "qrcp", "gather", "trsolve", "tail", "sketch_other", "svd", "qr", "tail_gemm"]
 lib.bra_debug_qrcp_phases.argtypes = [_vp, C.POINTER(C.c_int32)]
 lib.bra_probe_fp64_peak.argtypes = [_vp, C.POINTER(C.c_double)]
 lib.bra_probe_exchange_latency.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(C.c_double)]

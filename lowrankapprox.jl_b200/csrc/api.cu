@@ -138,7 +138,7 @@ int bra_destroy(bra_ctx* ctx) {
                     &ctx->vn2, &ctx->lpos, &ctx->rec, &ctx->jpvt, &ctx->tau, &ctx->rdiag, &ctx->info,
                     &ctx->kbtrace, &ctx->R11, &ctx->T, &ctx->C, &ctx->Q, &ctx->R1, &ctx->Rfull, &ctx->W, &ctx->G,
                     &ctx->U, &ctx->S, &ctx->Vt, &ctx->Z, &ctx->scratch, &ctx->scratch2, &ctx->scratch3,
-                    &ctx->aux_in1, &ctx->aux_in2};
+                    &ctx->aux_in1, &ctx->aux_in2, &ctx->jwork};
   for (DevBuf* b : bufs) b->release();
   if (ctx->h_info) cudaFreeHost(ctx->h_info);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -197,6 +197,13 @@ int bra_profile_read(bra_ctx* ctx, double* ms, int64_t* calls) {
 int bra_debug_qrcp_phases(bra_ctx* ctx, int32_t* out5) {
   if (!ctx || !out5) return -1;
   for (int i = 0; i < 5; ++i) out5[i] = ctx->h_info[4 + i];
+  return BRA_OK;
+}
+
+int bra_debug_jacobi_sweeps(bra_ctx* ctx) { return ctx ? ctx->last_jacobi_sweeps : -1; }
+int bra_debug_jacobi_phases(bra_ctx* ctx, int32_t* out4) {
+  if (!ctx || !out4) return -1;
+  for (int i = 0; i < 8; ++i) out4[i] = ctx->jacobi_kcycles[i];
   return BRA_OK;
 }
 

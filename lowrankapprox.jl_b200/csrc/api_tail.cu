@@ -11,6 +11,12 @@ int bra_scatter_cols(bra_ctx* ctx, const double* src, int64_t lds, int64_t rows,
 
 namespace {
 
+struct GemmTagGuard {
+  bra_ctx* c;
+  explicit GemmTagGuard(bra_ctx* ctx) : c(ctx) { c->gemm_tag = BRA_PROF_TAILGEMM; }
+  ~GemmTagGuard() { c->gemm_tag = BRA_PROF_GEMM; }
+};
+
 inline int64_t even(int64_t x) { return (x + 1) & ~int64_t(1); }
 
 // QR of the skeleton columns: ctx->Q (mA x k, ld = even(mA)) and ctx->R1 (k x k).
@@ -59,6 +65,7 @@ int bra_pqrfact_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double
   if (rc) return rc;
   FactResult& res = ctx->res;
   const int64_t k = res.k, mA = res.m, nA = res.n;
+  GemmTagGuard gtag(ctx);
   if (k > 0) {
     rc = skeleton_qr(ctx, trans, dA, dlda, mA, k);                      // F = qr!(getcols(trans, A, V[:sk]))
     if (rc) return rc;
@@ -104,6 +111,7 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
   if (rc) return rc;
   FactResult& res = ctx->res;
   const int64_t k = res.k, mA = res.m, nA = res.n;
+  GemmTagGuard gtag(ctx);
   res.ksvd = 0;
   res.svd_m = m;
   res.svd_n = n;
@@ -124,20 +132,21 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
     rc = bra_transpose(ctx, ctx->T.as<double>(), k, k, nA - k, Z + k, ldz);
     if (rc) return rc;
   }
-  BRA_CUDA(ctx->W.reserve((size_t)4 * k * k * 8));
+  const int64_t ldj = even(k);                // even leading dimension: 16-byte aligned columns for the Jacobi panels
+  BRA_CUDA(ctx->W.reserve((size_t)4 * ldj * k * 8 + 64));
   double* Rz = ctx->W.as<double>();
-  double* X = Rz + (size_t)k * k;           // Jacobi matrix: X = M' = R_z R1'
-  double* J = X + (size_t)k * k;
-  double* Ysel = J + (size_t)k * k;
+  double* X = Rz + (size_t)ldj * k;         // Jacobi matrix: X = M' = R_z R1'
+  double* J = X + (size_t)ldj * k;
+  double* Ysel = J + (size_t)ldj * k;
   rc = bra_cholqr2(ctx, nA, (int)k, Z, ldz, nullptr, Rz);
   if (rc) return rc;
   // X[i,j] = sum_t Rz[i,t] R1[j,t]
-  rc = bra_gemm_generic(ctx, Rz, 1, k, ctx->R1.as<double>(), k, 1, k, k, k, X, k);
+  rc = bra_gemm_generic(ctx, Rz, 1, k, ctx->R1.as<double>(), k, 1, k, k, k, X, ldj);
   if (rc) return rc;
   std::vector<double> sig((size_t)k);
   std::vector<int> order((size_t)k);
   BRA_CUDA(ctx->S.reserve((size_t)2 * k * 8));     // [0:k] column norms (unsorted), [k:2k] sorted values
-  rc = bra_jacobi_svd(ctx, (int)k, X, k, J, k, sig.data(), order.data());   // M' J = Y Sigma  =>  M = J Sigma Y'
+  rc = bra_jacobi_svd(ctx, (int)k, X, ldj, J, ldj, sig.data(), order.data());   // M' J = Y Sigma  =>  M = J Sigma Y'
   if (rc) return rc;
   // psvdrank (src/psvd.jl:301-308) on the sorted singular values
   std::vector<double> ssort((size_t)k);
@@ -165,7 +174,7 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
   double* Qt = ctx->scratch2.as<double>();
   double* Out = ctx->scratch3.as<double>();
   // left factor of op(A):  Uop = Q * J[:, order[:kk]]   (mA x kk)
-  rc = bra_gather_scale_cols(ctx, J, k, k, (int)kk, ctx->aux_in1.as<int>(), nullptr, Ysel, k);
+  rc = bra_gather_scale_cols(ctx, J, ldj, k, (int)kk, ctx->aux_in1.as<int>(), nullptr, Ysel, k);
   if (rc) return rc;
   rc = bra_transpose(ctx, ctx->Q.as<double>(), even(mA), mA, k, Qt, ldk);          // Q' (k x mA)
   if (rc) return rc;
@@ -181,7 +190,7 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
   }
   if (rc) return rc;
   // right factor of op(A):  Vop' = Ysel' Qz' P'   with Ysel = X[:, order] / sigma
-  rc = bra_gather_scale_cols(ctx, X, k, k, (int)kk, ctx->aux_in1.as<int>(), ctx->S.as<double>(), Ysel, k);
+  rc = bra_gather_scale_cols(ctx, X, ldj, k, (int)kk, ctx->aux_in1.as<int>(), ctx->S.as<double>(), Ysel, k);
   if (rc) return rc;
   rc = bra_transpose(ctx, Z, ldz, nA, k, Qt, ldk);                                   // Qz' (k x nA)
   if (rc) return rc;

@@ -84,6 +84,10 @@ struct bra_ctx {
   DevBuf W, G, U, S, Vt, Z;    // psvd tail
   DevBuf scratch, scratch2, scratch3;
   DevBuf aux_in1, aux_in2;     // staged random inputs (d, idx, perm, s, r)
+  DevBuf jwork;                // Jacobi SVD: grid barrier, per-sweep flags
+  int last_jacobi_sweeps = 0;
+  int jacobi_kcycles[8] = {0};
+  int gemm_tag = BRA_PROF_GEMM; // profiling tag the GEMM launchers record under (tails switch it)
   uint32_t rec_epoch = 1;
   size_t rec_zeroed = 0;
   int32_t* h_info = nullptr;   // pinned, 16 ints

@@ -345,7 +345,7 @@ int launch_gemm(bra_ctx* ctx, const CUtensorMap& mapA, const double* Omt, int64_
   BRA_CUDA(cudaFuncSetAttribute(gemm_sketch_kernel<WA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
   dim3 grid(jt, itl, splits);
   {
-    ProfScope ps(ctx, BRA_PROF_GEMM);
+    ProfScope ps(ctx, ctx->gemm_tag);
     gemm_sketch_kernel<WA><<<grid, (GW + 1) * 32, Cfg::SMEM, ctx->stream>>>(mapA, mapO, m, n, l, kper, out, ldo, sstride);
   }
   ctx->launches++;
@@ -426,7 +426,7 @@ int bra_gemm_generic(bra_ctx* ctx, const double* Om, int64_t osi, int64_t osk, c
                      int64_t sj, int64_t l, int64_t n, int64_t K, double* C, int64_t ldc) {
   if (l <= 0 || n <= 0) return BRA_OK;
   dim3 grid((unsigned)((n + 63) / 64), (unsigned)((l + 63) / 64));
-  ProfScope ps(ctx, BRA_PROF_GEMM);
+  ProfScope ps(ctx, ctx->gemm_tag);
   gemm_generic_kernel<<<grid, 256, 0, ctx->stream>>>(Om, osi, osk, A, sk, sj, l, n, K, C, ldc);
   ctx->launches++;
   BRA_CUDA(cudaGetLastError());

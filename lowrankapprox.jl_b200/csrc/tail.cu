@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <numeric>
 
 namespace {
@@ -224,11 +225,46 @@ __global__ void add_identity_kernel(int k, double* __restrict__ G, int64_t ldg) 
 }
 
 // ---- one-sided Jacobi (Hestenes) on the columns of X (k x k), rotations accumulated into J ----
-__global__ void __launch_bounds__(128) jacobi_stage_kernel(int k, int np, int stage, double* __restrict__ X, int64_t ldx,
-                                                           double* __restrict__ Jm, int64_t ldj, double tol, int* flag) {
-  // round-robin (chess tournament) ordering over np = even number of players
-  const int i = blockIdx.x;
-  int p, q;
+// Block-cyclic and persistent: the k columns form nblk blocks of BC columns; in every outer step each CTA owns one
+// block PAIR (chess-tournament schedule over the blocks), stages its 2*BC columns of X and of J in shared memory and
+// runs one full round-robin sweep of plane rotations among them there (a team of 64 threads per column pair).  One
+// grid barrier per outer step (nblk-1 per sweep) instead of one launch per rotation round (k-1 per sweep).
+// The rotations themselves are the classical ones: computed from freshly accumulated a = |x_p|^2, b = |x_q|^2,
+// c = x_p.x_q of the CURRENT columns (no Gram-matrix shortcut), so small singular values keep their accuracy.
+struct JacobiParams {
+  int k, nblk;
+  double* X;
+  int64_t ldx;
+  double* J;
+  int64_t ldj;
+  double tol;
+  int max_sweeps;
+  unsigned* bar;       // grid barrier counter (zeroed before launch)
+  int* rotated;        // [max_sweeps] "a rotation happened in this sweep"
+  int* out;            // [0] sweeps done, [1] converged
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+
+__device__ __forceinline__ void rr_pair(int np, int stage, int i, int& p, int& q) {
+  // round-robin (chess tournament) over np = even number of players: np-1 stages of np/2 disjoint pairs
   if (i == 0) {
     p = np - 1;
     q = stage % (np - 1);
@@ -241,46 +277,161 @@ __global__ void __launch_bounds__(128) jacobi_stage_kernel(int k, int np, int st
     p = q;
     q = t;
   }
-  if (q >= k) return;        // padding player
-  double* xp = X + (int64_t)p * ldx;
-  double* xq = X + (int64_t)q * ldx;
-  double a = 0.0, b = 0.0, c = 0.0;
-  for (int r = threadIdx.x; r < k; r += 128) {
-    const double u = xp[r], v = xq[r];
-    a = fma(u, u, a);
-    b = fma(v, v, b);
-    c = fma(u, v, c);
-  }
-  __shared__ double red[3][4];
+}
+
+template <int BC>
+__global__ void __launch_bounds__(32 * BC, 1) jacobi_block_kernel(JacobiParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NT = 32 * BC;                      // one warp per column pair
+  constexpr int NC = 2 * BC;                       // columns in a panel
+  const int k = P.k, tid = threadIdx.x;
+  const int kp = (k + 1) & ~1;                     // padded column length (16-byte aligned columns)
+  double* Xs = reinterpret_cast<double*>(smem_raw);             // [NC][kp]
+  double* Js = Xs + (size_t)NC * kp;                             // [NC][kp]
+  __shared__ int s_rot;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int npairs = P.nblk / 2;
+  const double tol2 = P.tol * P.tol;
+  unsigned epoch = 0;
+  int sweep = 0, converged = 0;
+  long long tph[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+#define JTICK(i) if (tid == 0) { long long _t = clock64(); tph[i] += _t - tlast; tlast = _t; }
+  for (; sweep < P.max_sweeps; ++sweep) {
+    if (tid == 0) s_rot = 0;
+    for (int st = 0; st < P.nblk - 1; ++st) {
+      for (int pi = blockIdx.x; pi < npairs; pi += gridDim.x) {
+        int bI, bJ;
+        rr_pair(P.nblk, st, pi, bI, bJ);
+        // ---- stage the panel (L2 -> smem with cp.async.cg: no L1, other CTAs wrote these columns earlier) ----
+        __syncthreads();
+        for (int lc = warp; lc < NC; lc += BC) {
+          const int gc = (lc < BC ? bI * BC + lc : bJ * BC + (lc - BC));
+          double* xs = Xs + (size_t)lc * kp;
+          double* js = Js + (size_t)lc * kp;
+          if (gc < k) {
+            const double* gx = P.X + (int64_t)gc * P.ldx;
+            const double* gj = P.J + (int64_t)gc * P.ldj;
+            for (int r = 2 * lane; r < kp; r += 64) {
+              cp_async16(xs + r, gx + r);
+              cp_async16(js + r, gj + r);
+            }
+          } else {
+            for (int r = lane; r < kp; r += 32) {
+              xs[r] = 0.0;
+              js[r] = 0.0;
+            }
+          }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+        JTICK(0)
+        // ---- one round-robin sweep among the NC panel columns, one warp per pair ----
+        bool rot_any = false;
+        for (int rd = 0; rd < NC - 1; ++rd) {
+          int p, q;
+          rr_pair(NC, rd, warp, p, q);
+          double* xp = Xs + (size_t)p * kp;
+          double* xq = Xs + (size_t)q * kp;
+          double a0 = 0.0, b0 = 0.0, c0 = 0.0, a1 = 0.0, b1 = 0.0, c1 = 0.0;
+          int r = lane;
+          for (; r + 32 < k; r += 64) {
+            const double u0 = xp[r], v0 = xq[r], u1 = xp[r + 32], v1 = xq[r + 32];
+            a0 = fma(u0, u0, a0);
+            b0 = fma(v0, v0, b0);
+            c0 = fma(u0, v0, c0);
+            a1 = fma(u1, u1, a1);
+            b1 = fma(v1, v1, b1);
+            c1 = fma(u1, v1, c1);
+          }
+          if (r < k) {
+            const double u0 = xp[r], v0 = xq[r];
+            a0 = fma(u0, u0, a0);
+            b0 = fma(v0, v0, b0);
+            c0 = fma(u0, v0, c0);
+          }
+          double a = a0 + a1, b = b0 + b1, c = c0 + c1;
+          JTICK(4)
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, o);
-    b += __shfl_xor_sync(0xffffffffu, b, o);
-    c += __shfl_xor_sync(0xffffffffu, c, o);
+          for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+          }
+          JTICK(5)
+          // converged pair: |c| <= tol * sqrt(a b)
+          if (c * c > tol2 * a * b) {
+            rot_any = true;
+            // t = tan(theta) = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (b - a) / (2c), written with one
+            // square root, one division and one reciprocal square root
+            const double d = b - a, c2 = 2.0 * c;
+            const double h = sqrt(fma(d, d, c2 * c2));
+            const double t = ((d >= 0.0) ? c2 : -c2) / (fabs(d) + h);
+            const double cs = rsqrt(fma(t, t, 1.0)), sn = cs * t;
+            if (tid == 0 && cs == 123.0) tph[8]++;
+            JTICK(6)
+            double* jp = Js + (size_t)p * kp;
+            double* jq = Js + (size_t)q * kp;
+#pragma unroll 4
+            for (int rr = lane; rr < k; rr += 32) {
+              const double u = xp[rr], v = xq[rr];
+              xp[rr] = fma(cs, u, -sn * v);
+              xq[rr] = fma(sn, u, cs * v);
+              const double ju = jp[rr], jv = jq[rr];
+              jp[rr] = fma(cs, ju, -sn * jv);
+              jq[rr] = fma(sn, ju, cs * jv);
+            }
+            JTICK(7)
+          }
+          __syncthreads();
+          JTICK(1)
+        }
+        if (rot_any && lane == 0) s_rot = 1;
+        // ---- write the panel back ----
+        for (int lc = warp; lc < NC; lc += BC) {
+          const int gc = (lc < BC ? bI * BC + lc : bJ * BC + (lc - BC));
+          if (gc < k) {
+            const double2* xs = reinterpret_cast<const double2*>(Xs + (size_t)lc * kp);
+            const double2* js = reinterpret_cast<const double2*>(Js + (size_t)lc * kp);
+            double2* gx = reinterpret_cast<double2*>(P.X + (int64_t)gc * P.ldx);
+            double2* gj = reinterpret_cast<double2*>(P.J + (int64_t)gc * P.ldj);
+            for (int r = lane; r < kp / 2; r += 32) {
+              __stcg(gx + r, xs[r]);
+              __stcg(gj + r, js[r]);
+            }
+          }
+        }
+        JTICK(2)
+      }
+      if (st == P.nblk - 2) {
+        __syncthreads();
+        if (tid == 0 && s_rot) atomicExch(P.rotated + sweep, 1);
+      }
+      ++epoch;
+      grid_barrier(P.bar, epoch * gridDim.x);
+      JTICK(3)
+    }
+    int any;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(any) : "l"(P.rotated + sweep) : "memory");
+    if (!any) {
+      converged = 1;
+      ++sweep;
+      break;
+    }
   }
-  if ((threadIdx.x & 31) == 0) {
-    red[0][threadIdx.x >> 5] = a;
-    red[1][threadIdx.x >> 5] = b;
-    red[2][threadIdx.x >> 5] = c;
+  if (blockIdx.x == 0 && tid == 0) {
+    P.out[0] = sweep;
+    P.out[1] = converged;
+    for (int i = 0; i < 8; ++i) P.out[2 + i] = (int)(tph[i] >> 10);     // kilo-cycles: load, sync, store, barrier, dot, shuffle, math, apply
   }
-  __syncthreads();
-  a = red[0][0] + red[0][1] + red[0][2] + red[0][3];
-  b = red[1][0] + red[1][1] + red[1][2] + red[1][3];
-  c = red[2][0] + red[2][1] + red[2][2] + red[2][3];
-  if (fabs(c) <= tol * sqrt(a) * sqrt(b) || c == 0.0) return;
-  if (threadIdx.x == 0) *flag = 1;
-  // rotation that orthogonalises the pair, keeping the larger column first (de Rijk)
-  const double zeta = (b - a) / (2.0 * c);
-  const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-  const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
-  for (int r = threadIdx.x; r < k; r += 128) {
-    const double u = xp[r], v = xq[r];
-    xp[r] = cs * u - sn * v;
-    xq[r] = sn * u + cs * v;
-    const double ju = Jm[r + (int64_t)p * ldj], jv = Jm[r + (int64_t)q * ldj];
-    Jm[r + (int64_t)p * ldj] = cs * ju - sn * jv;
-    Jm[r + (int64_t)q * ldj] = sn * ju + cs * jv;
-  }
+#undef JTICK
+}
+
+template <int BC>
+cudaError_t launch_jacobi(const JacobiParams& P, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(jacobi_block_kernel<BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  void* args[] = {(void*)&P};
+  return cudaLaunchCooperativeKernel((void*)jacobi_block_kernel<BC>, dim3(grid), dim3(32 * BC), args, smem, st);
 }
 
 __global__ void set_identity_kernel(int k, double* __restrict__ J, int64_t ldj) {
@@ -324,7 +475,7 @@ int bra_transpose(bra_ctx* ctx, const double* src, int64_t lds, int64_t rows, in
 
 int bra_trsolve_right_upper(bra_ctx* ctx, int64_t rows, int k, const double* R, int64_t ldr, double* Y, int64_t ldy) {
   if (rows <= 0 || k <= 0) return BRA_OK;
-  ProfScope ps(ctx, BRA_PROF_TAIL);
+  ProfScope ps(ctx, BRA_PROF_QR);
   trsolve_right_upper_kernel<<<(unsigned)((rows + 63) / 64), 256, 0, ctx->stream>>>(rows, k, R, ldr, Y, ldy);
   ctx->launches++;
   BRA_CUDA(cudaGetLastError());
@@ -334,7 +485,7 @@ int bra_trsolve_right_upper(bra_ctx* ctx, int64_t rows, int k, const double* R, 
 // G (k x k, symmetric positive definite, destroyed) -> Rout upper triangular with G = Rout^T Rout
 int bra_cholesky_upper(bra_ctx* ctx, int k, double* G, int64_t ldg, double* Rout, int64_t ldr) {
   if (k <= 0) return BRA_OK;
-  ProfScope ps(ctx, BRA_PROF_TAIL);
+  ProfScope ps(ctx, BRA_PROF_QR);
   int* info = ctx->info.as<int>() + 12;
   BRA_CUDA(cudaMemsetAsync(info, 0, 4, ctx->stream));
   const int nblk = (k + TB - 1) / TB;
@@ -393,23 +544,64 @@ int bra_cholqr2(bra_ctx* ctx, int64_t rows, int k, double* Y, int64_t ldy, const
 int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64_t ldj, double* sigma_host,
                    int* order_host) {
   if (k <= 0) return BRA_OK;
-  ProfScope ps(ctx, BRA_PROF_TAIL);
+  ProfScope ps(ctx, BRA_PROF_SVD);
   set_identity_kernel<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(k, J, ldj);
   ctx->launches++;
-  const int np = (k + 1) & ~1;
-  int* flag = ctx->info.as<int>() + 13;
-  const double tol = 1e-15;
-  bool converged = (k == 1);
-  for (int sweep = 0; sweep < 40 && !converged; ++sweep) {
-    BRA_CUDA(cudaMemsetAsync(flag, 0, 4, ctx->stream));
-    for (int st = 0; st < np - 1; ++st)
-      jacobi_stage_kernel<<<np / 2, 128, 0, ctx->stream>>>(k, np, st, X, ldx, J, ldj, tol, flag);
-    ctx->launches += np - 1;
-    int h = 0;
-    BRA_CUDA(cudaMemcpyAsync(&h, flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    BRA_CUDA(cudaStreamSynchronize(ctx->stream));
-    converged = (h == 0);
+  constexpr int MAX_SWEEPS = 48;
+  int sweeps = 0, converged = 1;
+  if ((ldx & 1) || (ldj & 1) || (reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(J) & 15)) {
+    ctx->set_error("Jacobi SVD: X and J need even leading dimensions and 16-byte aligned bases");
+    return -4;
   }
+  if (k > 1) {
+    // widest block whose panel (2*BC columns of X and of J) fits in shared memory
+    const size_t budget = (size_t)ctx->smem_optin - 2048;
+    int bc = 8;
+    const size_t kp = (size_t)((k + 1) & ~1);
+    while (bc > 1 && (size_t)32 * bc * kp > budget) bc >>= 1;
+    if ((size_t)32 * bc * kp > budget) {
+      ctx->set_error("Jacobi SVD: k too large for the shared-memory panel");
+      return BRA_ERR_UNSUPPORTED;
+    }
+    // A round is shared-memory-bandwidth bound (every rotation streams its columns of X and J) while every outer
+    // step costs a grid barrier: measured on B200 at k = 500, blocks of 4 columns (64 CTAs) balance the two.
+    if (bc > 4) bc = 4;
+    if (const char* ev = getenv("BRA_JACOBI_BC")) bc = atoi(ev) > 0 ? atoi(ev) : bc;
+    while (bc > 1 && k <= bc) bc >>= 1;              // tiny cores: keep at least two blocks of real columns
+    const int nblk = 2 * ((k + 2 * bc - 1) / (2 * bc));
+    const int grid = std::min(nblk / 2, ctx->num_sms);
+    const size_t smem = (size_t)32 * bc * kp;
+    BRA_CUDA(ctx->jwork.reserve(256 + MAX_SWEEPS * 4));
+    BRA_CUDA(cudaMemsetAsync(ctx->jwork.p, 0, 256 + MAX_SWEEPS * 4, ctx->stream));
+    JacobiParams P;
+    P.k = k;
+    P.nblk = nblk;
+    P.X = X;
+    P.ldx = ldx;
+    P.J = J;
+    P.ldj = ldj;
+    P.tol = std::sqrt((double)k) * 1.1102230246251565e-16;      // sqrt(k) * eps, dgesvj's criterion
+    P.max_sweeps = MAX_SWEEPS;
+    P.bar = ctx->jwork.as<unsigned>();
+    P.out = ctx->jwork.as<int>() + 16;
+    P.rotated = ctx->jwork.as<int>() + 64;
+    cudaError_t e;
+    switch (bc) {
+      case 8: e = launch_jacobi<8>(P, grid, smem, ctx->stream); break;
+      case 4: e = launch_jacobi<4>(P, grid, smem, ctx->stream); break;
+      case 2: e = launch_jacobi<2>(P, grid, smem, ctx->stream); break;
+      default: e = launch_jacobi<1>(P, grid, smem, ctx->stream); break;
+    }
+    BRA_CUDA(e);
+    ctx->launches++;
+    int h[10] = {0};
+    BRA_CUDA(cudaMemcpyAsync(h, P.out, 40, cudaMemcpyDeviceToHost, ctx->stream));
+    BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+    sweeps = h[0];
+    converged = h[1];
+    for (int i = 0; i < 8; ++i) ctx->jacobi_kcycles[i] = h[2 + i];
+  }
+  ctx->last_jacobi_sweeps = sweeps;
   BRA_CUDA(ctx->S.reserve((size_t)k * 8));
   col_norms_kernel<<<k, 128, 0, ctx->stream>>>(k, X, ldx, ctx->S.as<double>());
   ctx->launches++;
@@ -418,7 +610,7 @@ int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64
   std::iota(order_host, order_host + k, 0);
   std::stable_sort(order_host, order_host + k, [&](int a, int b) { return sigma_host[a] > sigma_host[b]; });
   if (!converged) {
-    ctx->set_error("Jacobi SVD did not converge in 40 sweeps");
+    ctx->set_error("Jacobi SVD did not converge in 48 sweeps");
     return BRA_ERR_INTERNAL;
   }
   return BRA_OK;
