@@ -136,6 +136,20 @@ void* bra_stream(bra_ctx* ctx);                  /* the ctx's cudaStream_t */
 int bra_sketch_randn_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A, int64_t lda,
                          int64_t order, const double* Omega, int64_t ldo, double* B, int64_t ldb);
 
+/* The structured sketches, same shapes as bra_sketch_randn_f64, with the random inputs the reference draws
+ * (SURVEY.md Appendix D), host or device pointers, indices 1-based int64:
+ *   sub  (src/sketch.jl:248-279):  B[i,:] = op(A)[r_i,:],                     r[order]
+ *   sprn (src/sketch.jl:571-653):  B[i,:] = sum_t s[off_i+t] op(A)[perm[off_i+t],:],  perm[mA] = randperm, s[mA]
+ *   srft (src/sketch.jl:338-522):  sign flip d[mA] (+-1), l x m' reshape, length-l DFT, sampled frequencies
+ *                                  idx[order] with (Re, Im) filling row pairs (every other idx entry is unused)
+ * mA = size(op(A), 1) is the contracted dimension. */
+int bra_sketch_sub_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A, int64_t lda, int64_t order,
+                       const int64_t* r, double* B, int64_t ldb);
+int bra_sketch_sprn_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A, int64_t lda, int64_t order,
+                        const int64_t* perm, const double* s, double* B, int64_t ldb);
+int bra_sketch_srft_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A, int64_t lda, int64_t order,
+                        const double* d, const int64_t* idx, double* B, int64_t ldb);
+
 /* geqp3_adap!(B, opts) (src/pqr.jl:348-418) on an l x n matrix B, in place:
  * on return B holds R in its upper triangle and the reflectors below (LAPACK
  * layout, columns permuted), jpvt (1-based) the permutation, tau[0:kcap] the

@@ -75,6 +75,9 @@ lib.bra_sync.argtypes = [_vp]
 lib.bra_stream.argtypes = [_vp]
 lib.bra_stream.restype = _vp
 lib.bra_sketch_randn_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _i64]
+lib.bra_sketch_sub_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64]
+lib.bra_sketch_sprn_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _i64]
+lib.bra_sketch_srft_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _i64]
 lib.bra_geqp3_adap_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, C.POINTER(bra_opts), _vp, _vp,
                                    C.POINTER(_i64), C.POINTER(_i64), _vp, _i64, C.POINTER(_i64)]
 lib.bra_trsolve_T_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, _vp, _i64]

@@ -95,7 +95,31 @@ def sketch(A, order: int, opts: Optional[LRAOptions] = None, side: str = "left",
         ctx.check(lib.bra_sketch_randn_f64(ctx.handle, tr, m, n, pA, lda, order, pO, ldo,
                                            C.c_void_p(out.ctypes.data), max(order, 1)))
         return out
-    raise BraError(2, f"sketch = :{o.sketch} is not built in this revision")
+    outp, ldo = C.c_void_p(out.ctypes.data), max(order, 1)
+
+    def vec(key, dtype, length):
+        if rand is None or key not in rand:
+            raise ValueError(f"stage-wise sketch = :{o.sketch} needs rand[{key!r}]")
+        a = np.ascontiguousarray(rand[key], dtype=dtype)
+        if a.shape != (length,):
+            raise ValueError(f"DimensionMismatch: {key}")
+        return a
+
+    if o.sketch == "sub":
+        r = vec("r", np.int64, order)
+        ctx.check(lib.bra_sketch_sub_f64(ctx.handle, tr, m, n, pA, lda, order, C.c_void_p(r.ctypes.data), outp, ldo))
+        return out
+    if o.sketch == "sprn":
+        perm, sv = vec("perm", np.int64, mA), vec("s", np.float64, mA)
+        ctx.check(lib.bra_sketch_sprn_f64(ctx.handle, tr, m, n, pA, lda, order, C.c_void_p(perm.ctypes.data),
+                                          C.c_void_p(sv.ctypes.data), outp, ldo))
+        return out
+    if o.sketch == "srft":
+        d, idx = vec("d", np.float64, mA), vec("idx", np.int64, order)
+        ctx.check(lib.bra_sketch_srft_f64(ctx.handle, tr, m, n, pA, lda, order, C.c_void_p(d.ctypes.data),
+                                          C.c_void_p(idx.ctypes.data), outp, ldo))
+        return out
+    raise ValueError("sketch")                          # chkopts! already rejects unknown kinds
 
 
 def geqp3_adap(Bm: np.ndarray, opts: Optional[LRAOptions] = None, ctx: Optional[Context] = None, **kw):

@@ -77,6 +77,100 @@ int sketch_randn_round(bra_ctx* ctx, char trans, int64_t m, int64_t n, const dou
   return bra_gemm_generic(ctx, ctx->omega_t.as<double>(), ldt, 1, dA, lda, 1, order, nA, mA, ctx->B.as<double>(), order);
 }
 
+// a per-round random input array: device pointer to it (staging host data into `buf`)
+int stage_vec(bra_ctx* ctx, DevBuf& buf, const void* src, int64_t count, const void** out) {
+  if (is_device_ptr(src)) {
+    *out = src;
+    return BRA_OK;
+  }
+  BRA_CUDA(buf.reserve((size_t)(count > 0 ? count : 1) * 8));
+  BRA_CUDA(cudaMemcpyAsync(buf.p, src, (size_t)count * 8, cudaMemcpyHostToDevice, ctx->stream));
+  *out = buf.p;
+  return BRA_OK;
+}
+
+int need_input(bra_ctx* ctx, const bra_rand* rnd, int round, const void* const* col, const char* what) {
+  if (round >= rnd->n_rounds || !col || !col[round]) {
+    ctx->set_error(std::string("adaptive loop needs more rounds than random inputs supplied (") + what + ")");
+    return BRA_ERR_ROUNDS;
+  }
+  return BRA_OK;
+}
+
+// B (order x nA) = S * op(A) into ctx->B (ld = order) for any sketch kind (src/sketch.jl:35-50 dispatch)
+int sketch_round(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* dA, int64_t lda, const bra_opts* o,
+                 const bra_rand* rnd, int round, int64_t order) {
+  if (o->sketch == BRA_SKETCH_RANDN) return sketch_randn_round(ctx, trans, m, n, dA, lda, o, rnd, round, order);
+  const int64_t mA = (trans == 'n') ? m : n;
+  const int64_t nA = (trans == 'n') ? n : m;
+  const bool given = rnd && rnd->n_rounds > 0;
+  BRA_CUDA(ctx->B.reserve((size_t)(order > 0 ? order : 1) * nA * 8));
+  int rc;
+  if (o->sketch == BRA_SKETCH_SUB) {
+    const void* r = nullptr;
+    if (given) {
+      if ((rc = need_input(ctx, rnd, round, (const void* const*)rnd->r, "r"))) return rc;
+      if ((rc = stage_vec(ctx, ctx->aux_in1, rnd->r[round], order, &r))) return rc;
+    } else {
+      BRA_CUDA(ctx->aux_in1.reserve((size_t)order * 8));
+      if ((rc = bra_fill_meta(ctx, 1, ctx->aux_in1.p, order, mA, o->seed, (uint64_t)round))) return rc;
+      r = ctx->aux_in1.p;
+    }
+    return bra_sketch_sub(ctx, trans, dA, lda, mA, nA, order, (const int64_t*)r, ctx->B.as<double>(), order);
+  }
+  if (o->sketch == BRA_SKETCH_SPRN) {
+    const void *perm = nullptr, *sv = nullptr;
+    if (given) {
+      if ((rc = need_input(ctx, rnd, round, (const void* const*)rnd->perm, "perm"))) return rc;
+      if ((rc = need_input(ctx, rnd, round, (const void* const*)rnd->s, "s"))) return rc;
+      if ((rc = stage_vec(ctx, ctx->aux_in1, rnd->perm[round], mA, &perm))) return rc;
+      if ((rc = stage_vec(ctx, ctx->aux_in2, rnd->s[round], mA, &sv))) return rc;
+    } else {
+      BRA_CUDA(ctx->aux_in1.reserve((size_t)mA * 8));
+      BRA_CUDA(ctx->aux_in2.reserve((size_t)(mA + 1) * 8));
+      if ((rc = bra_fill_meta(ctx, 2, ctx->aux_in1.p, mA, mA, o->seed, (uint64_t)round))) return rc;
+      if ((rc = bra_fill_randn(ctx, ctx->aux_in2.as<double>(), mA, o->seed, (uint64_t)round))) return rc;
+      perm = ctx->aux_in1.p;
+      sv = ctx->aux_in2.p;
+    }
+    return bra_sketch_sprn(ctx, trans, dA, lda, mA, nA, order, (const int64_t*)perm, (const double*)sv,
+                           ctx->B.as<double>(), order);
+  }
+  if (o->sketch == BRA_SKETCH_SRFT) {
+    const void *d = nullptr, *idx = nullptr;
+    if (given) {
+      if ((rc = need_input(ctx, rnd, round, (const void* const*)rnd->d, "d"))) return rc;
+      if ((rc = need_input(ctx, rnd, round, (const void* const*)rnd->idx, "idx"))) return rc;
+      if ((rc = stage_vec(ctx, ctx->aux_in2, rnd->d[round], mA, &d))) return rc;
+      if ((rc = stage_vec(ctx, ctx->aux_in1, rnd->idx[round], order, &idx))) return rc;
+    } else {
+      BRA_CUDA(ctx->aux_in1.reserve((size_t)order * 8));
+      BRA_CUDA(ctx->aux_in2.reserve((size_t)mA * 8));
+      if ((rc = bra_fill_meta(ctx, 0, ctx->aux_in2.p, mA, 0, o->seed, (uint64_t)round))) return rc;
+      if ((rc = bra_fill_meta(ctx, 1, ctx->aux_in1.p, order, mA, o->seed, (uint64_t)round))) return rc;
+      d = ctx->aux_in2.p;
+      idx = ctx->aux_in1.p;
+    }
+    const double* Aop = dA;
+    int64_t ldop = lda;
+    if (trans == 'c') {
+      // sequences are the rows of A: work on a transposed copy (made once per factorization, see At_valid)
+      const int64_t ldat = (n + 1) & ~int64_t(1);
+      if (!ctx->At_valid) {
+        BRA_CUDA(ctx->At.reserve((size_t)ldat * m * 8));
+        if ((rc = bra_transpose(ctx, dA, lda, m, n, ctx->At.as<double>(), ldat))) return rc;
+        ctx->At_valid = true;
+      }
+      Aop = ctx->At.as<double>();
+      ldop = ldat;
+    }
+    return bra_sketch_srft(ctx, Aop, ldop, mA, nA, order, (const double*)d, (const int64_t*)idx, ctx->B.as<double>(),
+                           order);
+  }
+  ctx->set_error("sketch kind not built");
+  return BRA_ERR_UNSUPPORTED;
+}
+
 int run_round_qrcp(bra_ctx* ctx, const bra_opts* o, int64_t order, int64_t nA, QrcpOut* q) {
   ProfScope ps(ctx, BRA_PROF_QRCP);
   const int64_t lmin = order < nA ? order : nA;
@@ -138,7 +232,7 @@ int bra_destroy(bra_ctx* ctx) {
                     &ctx->vn2, &ctx->lpos, &ctx->rec, &ctx->jpvt, &ctx->tau, &ctx->rdiag, &ctx->info,
                     &ctx->kbtrace, &ctx->R11, &ctx->T, &ctx->C, &ctx->Q, &ctx->R1, &ctx->Rfull, &ctx->W, &ctx->G,
                     &ctx->U, &ctx->S, &ctx->Vt, &ctx->Z, &ctx->scratch, &ctx->scratch2, &ctx->scratch3,
-                    &ctx->aux_in1, &ctx->aux_in2, &ctx->jwork};
+                    &ctx->aux_in1, &ctx->aux_in2, &ctx->jwork, &ctx->At};
   for (DevBuf* b : bufs) b->release();
   if (ctx->h_info) cudaFreeHost(ctx->h_info);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -264,6 +358,75 @@ int bra_sketch_randn_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const d
   return BRA_OK;
 }
 
+// Stage-wise sketch for the three structured kinds: `kind` is BRA_SKETCH_{SPRN,SRFT,SUB}; v1/v2 are the random
+// inputs in reference order (sub: r, -; sprn: perm, s; srft: d, idx).
+static int sketch_structured(bra_ctx* ctx, int kind, char trans, int64_t m, int64_t n, const double* A, int64_t lda,
+                             int64_t order, const void* v1, const void* v2, double* B, int64_t ldb) {
+  BRA_CHECK_ARG(trans == 'n' || trans == 'c', 2, "trans");
+  BRA_CHECK_ARG(m >= 0, 3, "m");
+  BRA_CHECK_ARG(n >= 0, 4, "n");
+  BRA_CHECK_ARG(A != nullptr || m * n == 0, 5, "A");
+  BRA_CHECK_ARG(lda >= (m > 1 ? m : 1), 6, "lda");
+  BRA_CHECK_ARG(order >= 0, 7, "order");
+  const int64_t nA = (trans == 'n') ? n : m, mA = (trans == 'n') ? m : n;
+  BRA_CHECK_ARG(v1 != nullptr || order * mA == 0, 8, "random input 1");
+  BRA_CHECK_ARG(kind == BRA_SKETCH_SUB || v2 != nullptr || order * mA == 0, 9, "random input 2");
+  BRA_CHECK_ARG(B != nullptr || order * nA == 0, 10, "B");
+  BRA_CHECK_ARG(ldb >= (order > 1 ? order : 1), 11, "ldb");
+  if (order == 0 || nA == 0) return BRA_OK;
+  if (mA == 0) {
+    BRA_CUDA(cudaMemset2DAsync(B, (size_t)ldb * 8, 0, (size_t)order * 8, (size_t)nA, ctx->stream));
+    BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BRA_OK;
+  }
+  BRA_CUDA(cudaSetDevice(ctx->device));
+  const double* dA;
+  int64_t dlda;
+  int rc = to_device(ctx, ctx->A_stage, A, lda, m, n, &dA, &dlda);
+  if (rc) return rc;
+  bra_opts o;
+  bra_opts_default(&o);
+  o.sketch = kind;
+  const void* a1[1] = {v1};
+  const void* a2[1] = {v2};
+  bra_rand rnd;
+  std::memset(&rnd, 0, sizeof(rnd));
+  rnd.n_rounds = 1;
+  if (kind == BRA_SKETCH_SUB) {
+    rnd.r = (const int64_t* const*)a1;
+  } else if (kind == BRA_SKETCH_SPRN) {
+    rnd.perm = (const int64_t* const*)a1;
+    rnd.s = (const double* const*)a2;
+  } else {
+    rnd.d = (const double* const*)a1;
+    rnd.idx = (const int64_t* const*)a2;
+  }
+  ctx->At_valid = false;
+  rc = sketch_round(ctx, trans, m, n, dA, dlda, &o, &rnd, 0, order);
+  if (rc) return rc;
+  BRA_CUDA(copy2d(ctx, B, ldb, ctx->B.p, order, order, nA));
+  BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BRA_OK;
+}
+
+int bra_sketch_sub_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A, int64_t lda, int64_t order,
+                       const int64_t* r, double* B, int64_t ldb) {
+  if (!ctx) return -1;
+  return sketch_structured(ctx, BRA_SKETCH_SUB, trans, m, n, A, lda, order, r, nullptr, B, ldb);
+}
+
+int bra_sketch_sprn_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A, int64_t lda, int64_t order,
+                        const int64_t* perm, const double* s, double* B, int64_t ldb) {
+  if (!ctx) return -1;
+  return sketch_structured(ctx, BRA_SKETCH_SPRN, trans, m, n, A, lda, order, perm, s, B, ldb);
+}
+
+int bra_sketch_srft_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A, int64_t lda, int64_t order,
+                        const double* d, const int64_t* idx, double* B, int64_t ldb) {
+  if (!ctx) return -1;
+  return sketch_structured(ctx, BRA_SKETCH_SRFT, trans, m, n, A, lda, order, d, idx, B, ldb);
+}
+
 int bra_geqp3_adap_f64(bra_ctx* ctx, int64_t l, int64_t n, double* B, int64_t ldb, const bra_opts* opts,
                        int64_t* jpvt, double* tau, int64_t* k, int64_t* nsteps, int32_t* kb_trace, int64_t kb_cap,
                        int64_t* n_blocks) {
@@ -335,10 +498,7 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
   res = FactResult();
   res.m = (trans == 'n') ? m : n;
   res.n = nA;
-  if (o->sketch != BRA_SKETCH_RANDN) {
-    ctx->set_error("sketch kind not built in this revision");
-    return BRA_ERR_UNSUPPORTED;
-  }
+  ctx->At_valid = false;
   QrcpOut q = {0, 0, 0, 0};
   int64_t order = 0;
   if (o->sketchfact_adap || o->rank < 0) {
@@ -349,7 +509,7 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
         return BRA_ERR_ROUNDS;
       }
       order = default_order(o, nn);
-      int rc = sketch_randn_round(ctx, trans, m, n, dA, lda, o, rnd, round, order);
+      int rc = sketch_round(ctx, trans, m, n, dA, lda, o, rnd, round, order);
       if (rc) return rc;
       rc = run_round_qrcp(ctx, o, order, nA, &q);
       if (rc) return rc;
@@ -362,7 +522,7 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
     }
   } else {
     order = (o->sketch == BRA_SKETCH_SPRN) ? o->rank : default_order(o, o->rank);   // src/sketch.jl:236,686
-    int rc = sketch_randn_round(ctx, trans, m, n, dA, lda, o, rnd, 0, order);
+    int rc = sketch_round(ctx, trans, m, n, dA, lda, o, rnd, 0, order);
     if (rc) return rc;
     rc = run_round_qrcp(ctx, o, order, nA, &q);
     if (rc) return rc;

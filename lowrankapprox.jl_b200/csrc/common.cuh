@@ -87,6 +87,9 @@ struct bra_ctx {
   DevBuf jwork;                // Jacobi SVD: grid barrier, per-sweep flags
   int last_jacobi_sweeps = 0;
   int jacobi_kcycles[8] = {0};
+  std::vector<unsigned char> h_meta;  // host scratch for fast-mode index/sign generation
+  DevBuf At;                   // transposed copy of A for the (:left,:c) SRFT
+  bool At_valid = false;
   int gemm_tag = BRA_PROF_GEMM; // profiling tag the GEMM launchers record under (tails switch it)
   uint32_t rec_epoch = 1;
   size_t rec_zeroed = 0;
@@ -156,6 +159,17 @@ int bra_gemm_sketch(bra_ctx* ctx, const double* Omt, int64_t l, int64_t m, const
 int bra_gemm_tn(bra_ctx* ctx, const double* X, int64_t ldx, int64_t l, int64_t m, const double* Y, int64_t ldy,
                 int64_t n, double* C, int64_t ldc);
 bool bra_gemm_tma_ok(const double* A, int64_t lda, int64_t m, int64_t n);
+
+// sketch_other.cu
+int bra_sketch_sub(bra_ctx* ctx, char trans, const double* A, int64_t lda, int64_t mA, int64_t nA, int64_t order,
+                   const int64_t* r1_dev, double* B, int64_t ldb);
+int bra_sketch_sprn(bra_ctx* ctx, char trans, const double* A, int64_t lda, int64_t mA, int64_t nA, int64_t order,
+                    const int64_t* perm1_dev, const double* s_dev, double* B, int64_t ldb);
+int bra_sketch_srft(bra_ctx* ctx, const double* A, int64_t lda, int64_t mA, int64_t nA, int64_t order,
+                    const double* d_dev, const int64_t* idx1_dev, double* B, int64_t ldb);
+int bra_fill_meta(bra_ctx* ctx, int kind, void* dst_dev, int64_t count, int64_t range, uint64_t seed, uint64_t stream_id);
+int bra_splitk_reduce(bra_ctx* ctx, const double* part, int64_t split_stride, int splits, int64_t l, int64_t n,
+                      double* out, int64_t ldo);
 
 // tail.cu (pqrfact / psvdfact tails)
 int bra_gather_cols(bra_ctx* ctx, char trans, const double* A, int64_t lda, int64_t mC, int64_t k,

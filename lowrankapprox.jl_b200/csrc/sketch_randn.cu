@@ -363,6 +363,18 @@ int launch_gemm(bra_ctx* ctx, const CUtensorMap& mapA, const double* Omt, int64_
 
 }  // namespace
 
+int bra_splitk_reduce(bra_ctx* ctx, const double* part, int64_t split_stride, int splits, int64_t l, int64_t n,
+                      double* out, int64_t ldo) {
+  ProfScope ps(ctx, BRA_PROF_SPLITK);
+  const int64_t total = l * n;
+  if (total <= 0) return BRA_OK;
+  int blocks = (int)((total + 255) / 256 < (int64_t)ctx->num_sms * 16 ? (total + 255) / 256 : (int64_t)ctx->num_sms * 16);
+  splitk_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(part, split_stride, splits, l, n, out, ldo);
+  ctx->launches++;
+  BRA_CUDA(cudaGetLastError());
+  return BRA_OK;
+}
+
 int bra_transpose_omega(bra_ctx* ctx, const double* Om, int64_t ldo, int64_t l, int64_t m, double* Omt) {
   // Om is l x m (col-major); Omt[k + i*ldt], ldt = m rounded up to even
   const int64_t ldt = (m + 1) & ~int64_t(1);
