@@ -213,9 +213,10 @@ int bra_probe_exchange_latency(bra_ctx* ctx, int ctas, int iters, double* usec);
 /* Exchange design probe: mode 0 = push `hw` words to every inbox, mode 1 = two hops through `leaders`. */
 int bra_probe_exchange2(bra_ctx* ctx, int ctas, int hw, int mode, int leaders, int iters, double* usec);
 
-/* Kilo-cycles CTA 0 spent per phase of the last QRCP launch: local scan, publish, header gather,
- * Householder, update (clock64 deltas; diagnostic only). */
-int bra_debug_qrcp_phases(bra_ctx* ctx, int32_t* out5);
+/* Kilo-cycles CTA 0 spent per phase of the last QRCP launch: candidate merge + header push, dlarfg on its own
+ * candidate + record push, header gather, winner-vector fetch, rank-1 update + norm downdate, (unused)
+ * (clock64 deltas; diagnostic only). */
+int bra_debug_qrcp_phases(bra_ctx* ctx, int32_t* out6);
 /* Sweeps the last psvd core (k x k Jacobi SVD) needed. */
 int bra_debug_jacobi_sweeps(bra_ctx* ctx);
 /* Kilo-cycles thread 0 spent in the last Jacobi launch: panel load, round sync, panel store, grid barrier,

@@ -254,9 +254,10 @@ class Context:
         return {t: (ms[i], int(calls[i])) for i, t in enumerate(PROF_TAGS)}
 
     def qrcp_phases(self):
-        out = (C.c_int32 * 5)()
+        out = (C.c_int32 * 6)()
         lib.bra_debug_qrcp_phases(self._h, out)
-        return dict(zip(["scan", "publish", "gather", "householder", "update"], [int(x) for x in out]))
+        return dict(zip(["merge_hdr", "dlarfg_rec", "gather", "fetch", "update", "unused"],
+                        [int(x) for x in out]))
 
     def sync(self):
         self.check(lib.bra_sync(self._h))

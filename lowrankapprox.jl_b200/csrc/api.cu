@@ -229,7 +229,7 @@ int bra_destroy(bra_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->A_stage, &ctx->omega_t, &ctx->omega_in, &ctx->B, &ctx->B2, &ctx->partial, &ctx->vn1,
-                    &ctx->vn2, &ctx->lpos, &ctx->rec, &ctx->jpvt, &ctx->tau, &ctx->rdiag, &ctx->info,
+                    &ctx->vn2, &ctx->lpos, &ctx->fpend, &ctx->rec, &ctx->jpvt, &ctx->tau, &ctx->rdiag, &ctx->info,
                     &ctx->kbtrace, &ctx->R11, &ctx->T, &ctx->C, &ctx->Q, &ctx->R1, &ctx->Rfull, &ctx->W, &ctx->G,
                     &ctx->U, &ctx->S, &ctx->Vt, &ctx->Z, &ctx->scratch, &ctx->scratch2, &ctx->scratch3,
                     &ctx->aux_in1, &ctx->aux_in2, &ctx->jwork, &ctx->At};
@@ -288,9 +288,9 @@ int bra_profile_read(bra_ctx* ctx, double* ms, int64_t* calls) {
   return BRA_OK;
 }
 
-int bra_debug_qrcp_phases(bra_ctx* ctx, int32_t* out5) {
-  if (!ctx || !out5) return -1;
-  for (int i = 0; i < 5; ++i) out5[i] = ctx->h_info[4 + i];
+int bra_debug_qrcp_phases(bra_ctx* ctx, int32_t* out6) {
+  if (!ctx || !out6) return -1;
+  for (int i = 0; i < 6; ++i) out6[i] = ctx->h_info[4 + i];
   return BRA_OK;
 }
 

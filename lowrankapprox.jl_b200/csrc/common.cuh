@@ -76,7 +76,7 @@ struct bra_ctx {
   DevBuf B;                    // sketch, l x n (col-major, ld = l)
   DevBuf B2;                   // permuted copy / scratch
   DevBuf partial;              // split-K partial sums
-  DevBuf vn1, vn2, lpos;       // QRCP per-column state
+  DevBuf vn1, vn2, lpos, fpend; // QRCP per-column state
   DevBuf rec;                  // LL exchange records
   DevBuf jpvt, tau, rdiag, info, kbtrace;
   DevBuf R11, T;               // k x k, k x (n-k)

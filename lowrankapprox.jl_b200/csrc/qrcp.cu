@@ -15,14 +15,17 @@
 //    as bookkeeping only, because it is observable: a flagged column ends the
 //    block, the rank test runs at block ends only, pivoting continues to the block
 //    end (src/pqr.jl:397-414).
-//  * ONE grid-wide exchange per pivot step, push style: every CTA writes its
-//    candidate header (downdated norm, logical position, and the alpha / tail
-//    norm^2 dlarfg needs) into EVERY CTA's private inbox and its candidate's
-//    current column into its own record, all as self-validating 8-byte words
-//    (payload + step stamp, the "LL" idea of NCCL): no fence, no atomic and no
-//    shared polling hot-spot on the critical path.  Every CTA then reads its own
-//    inbox, picks the winner with warp-shuffle reductions and forms the
-//    Householder vector redundantly (bitwise identical everywhere).
+//  * ONE grid-wide exchange per pivot step, push style: as soon as a CTA knows
+//    its best downdated norm it pushes ONE 32-byte word (norm, logical position,
+//    flag; a single 256-bit store, 4-byte payload + 4-byte step stamp per 8 bytes,
+//    the "LL" idea of NCCL) into EVERY CTA's private inbox: no fence, no atomic,
+//    no shared polling hot-spot, one L2 request per (source, destination) pair.
+//    While those words are in flight the CTA runs dlarfg on its own candidate
+//    (block-wide sum of squares, beta, tau) and publishes the finished Householder
+//    vector in its record (speculatively: only the winner's record is read).  Every
+//    CTA then reads its inbox, picks the winner with redux.sync-based argmax and
+//    copies the winner's vector -- the sqrt/div latency of dlarfg and the column
+//    transfer hide behind the header exchange.
 //  * Norm downdate + local argmax are fused into the update sweep; the scalar
 //    LAWN-176 arithmetic is vectorised across lanes (lane j <-> j-th column of the warp).
 //  * The rank/rtol termination test stays on the device.
@@ -33,12 +36,16 @@ namespace {
 
 constexpr int QR_THREADS = 512;
 constexpr int QR_WARPS = QR_THREADS / 32;
-constexpr int HW = 5;                          // header words pushed per (src, dst)
+constexpr int RECH = 4;                        // record header words: tau, beta, physical column, (pad)
 constexpr int MAXG = 160;                      // >= number of SMs
 constexpr uint32_t SPIN_LIMIT = 1u << 22;      // exchange timeout (never hang the box)
 
 struct __align__(16) LL16 {
   uint32_t lo, s0, hi, s1;
+};
+
+struct __align__(32) LL32 {
+  uint32_t w[8];
 };
 
 struct QrcpParams {
@@ -56,7 +63,7 @@ struct QrcpParams {
   double* vn2g;
   int* lposg;
   LL16* rec;        // [2][G][l]        candidate columns
-  LL16* inbox;      // [2][G dst][HW][G src] headers
+  LL32* inbox;      // [2][G dst][G src] headers
   uint32_t epoch;
   int64_t* jpvt;    // n, 1-based, LAPACK layout
   double* tau;      // kcap
@@ -90,6 +97,36 @@ __device__ __forceinline__ bool ll_load(const LL16* p, uint32_t stamp, uint32_t&
   return false;
 }
 
+// header word: (v.lo, v.hi, lp, flag) as four 4-byte payloads, each followed by the step stamp
+__device__ __forceinline__ void ll32_store(LL32* p, double v, int lp, int flag, uint32_t stamp) {
+  asm volatile("st.relaxed.gpu.global.v8.b32 [%0], {%1,%2,%3,%2,%4,%2,%5,%2};" ::"l"(p),
+               "r"((uint32_t)__double2loint(v)), "r"(stamp), "r"((uint32_t)__double2hiint(v)), "r"((uint32_t)lp),
+               "r"((uint32_t)flag)
+               : "memory");
+}
+__device__ __forceinline__ void ll32_ld(const LL32* p, uint32_t (&q)[8]) {
+  asm volatile("ld.relaxed.gpu.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])
+               : "l"(p)
+               : "memory");
+}
+__device__ __forceinline__ bool ll32_load(const LL32* p, uint32_t stamp, double& v, int& lp, int& flag) {
+  uint32_t a, s0, b, s1, c, s2, d, s3, spins = 0;
+  do {
+    asm volatile("ld.relaxed.gpu.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a), "=r"(s0), "=r"(b), "=r"(s1), "=r"(c), "=r"(s2), "=r"(d), "=r"(s3)
+                 : "l"(p)
+                 : "memory");
+    if (s0 == stamp && s1 == stamp && s2 == stamp && s3 == stamp) {
+      v = __hiloint2double((int)b, (int)a);
+      lp = (int)c;
+      flag = (int)d;
+      return true;
+    }
+  } while (++spins < SPIN_LIMIT);
+  return false;
+}
+
 __device__ __forceinline__ double warp_sum(double x) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
@@ -104,8 +141,6 @@ __device__ __forceinline__ bool cand_better(double v, int lp, double bv, int blp
 
 struct Cand {
   double v;       // downdated norm vn1 (-1: none)
-  double ssx;     // sum of squares of the candidate column below its pivot row
-  double alpha;   // candidate column at its pivot row
   int lp;         // logical position
   int id;         // local column index
   int ps;         // physical column at the next logical pivot position (or -1)
@@ -144,12 +179,9 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_kernel(QrcpParams p) {
   double* vbuf = reinterpret_cast<double*>(smem_raw);             // l
   double* rdblk = vbuf + l;                                       // nb
   double* hv = rdblk + p.nb;                                      // MAXG  header payloads of the gather
-  double* hssx = hv + MAXG;
-  double* halpha = hssx + MAXG;
-  int* hlp = reinterpret_cast<int*>(halpha + MAXG);               // MAXG each
-  int* hphys = hlp + MAXG;
-  int* hps = hphys + MAXG;
-  int* hflag = hps + MAXG;
+  double* sred = hv + MAXG;                                       // QR_WARPS partial sums of squares
+  int* hlp = reinterpret_cast<int*>(sred + QR_WARPS);             // MAXG each
+  int* hflag = hlp + MAXG;
   Cand* credc = reinterpret_cast<Cand*>(hflag + MAXG);            // [2][QR_WARPS]
   double* cache = reinterpret_cast<double*>(credc + 2 * QR_WARPS);// csm * l
   double* vn1 = p.meta_smem ? cache + (size_t)p.csm * l : p.vn1g + col0;
@@ -196,7 +228,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_kernel(QrcpParams p) {
   __syncwarp();
 
   // Per-warp candidate for pivot step `snext` over the warp's columns (lc = warp + 16*j), with the
-  // alpha / tail sum of squares dlarfg will need; result goes to credc[snext & 1][warp].
+  // result goes to credc[snext & 1][warp].
   auto warp_candidate = [&](int snext, int wflag) {
     double bv = -1.0;
     int blp = 0x7fffffff, bid = -1, bps = -1;
@@ -223,22 +255,9 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_kernel(QrcpParams p) {
       }
     }
     bps = __reduce_max_sync(0xffffffffu, bps);
-    double alpha = 0.0, ssx = 0.0;
-    if (bid >= 0) {
-      const double* a = colptr(bid);
-      for (int r = snext + lane; r < l; r += 32) {
-        const double x = a[r];
-        if (r == snext) alpha = x;
-        else ssx = fma(x, x, ssx);
-      }
-      ssx = warp_sum(ssx);
-      alpha = __shfl_sync(0xffffffffu, alpha, 0);
-    }
     if (lane == 0) {
       Cand c;
       c.v = bv;
-      c.ssx = ssx;
-      c.alpha = alpha;
       c.lp = blp;
       c.id = bid;
       c.ps = bps;
@@ -287,55 +306,65 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_kernel(QrcpParams p) {
     }
     QR_TICK(0)
 
-    // ---- publish: header pushed to every inbox + the candidate's current column ----
+    // ---- publish 1: one 32-byte header word into every CTA's inbox ----
     const uint32_t stamp = p.epoch + (uint32_t)s;
     const int par = s & 1;
-    // inbox layout [par][dst][src][HW]: the HW words of one (src, dst) pair are contiguous, so a warp's
-    // stores/loads coalesce into few L2 requests (the exchange is L2-request-bound, not byte-bound).
-    for (int e = tid; e < G * HW; e += QR_THREADS) {
-      const int dst = e / HW, w = e - dst * HW;
-      uint32_t lo, hi;
-      if (w == 0) {
-        lo = (uint32_t)__double2loint(c.v);
-        hi = (uint32_t)__double2hiint(c.v);
-      } else if (w == 1) {
-        lo = (uint32_t)__double2loint(c.ssx);
-        hi = (uint32_t)__double2hiint(c.ssx);
-      } else if (w == 2) {
-        lo = (uint32_t)__double2loint(c.alpha);
-        hi = (uint32_t)__double2hiint(c.alpha);
-      } else if (w == 3) {
-        lo = (uint32_t)c.lp;
-        hi = (uint32_t)(c.id >= 0 ? (int)(col0 + c.id) : -1);
-      } else {
-        lo = (uint32_t)c.ps;
-        hi = (uint32_t)c.flag;
+    const int my_ps = c.ps;              // physical column sitting at logical position s, if this CTA owns it
+    const int cand_lc = c.id;
+    if (tid < G) ll32_store(p.inbox + ((size_t)par * G + tid) * G + cta, c.v, c.lp, c.flag, stamp);
+
+    // ---- publish 2 (while the headers fly): dlarfg on my candidate, finished vector into my record ----
+    LL16* myrec = p.rec + ((size_t)par * G + cta) * (l + RECH);
+    {
+      const double* a = (cand_lc >= 0) ? colptr(cand_lc) : vbuf;
+      double ss = 0.0;
+      double xr[2] = {0.0, 0.0};          // my rows s+1+tid, s+1+tid+512 of the candidate
+      if (cand_lc >= 0) {
+        const int r0 = s + 1 + tid, r1 = r0 + QR_THREADS;
+        if (r0 < l) xr[0] = a[r0];
+        if (r1 < l) xr[1] = a[r1];
+        ss = fma(xr[0], xr[0], xr[1] * xr[1]);
+        for (int r = r1 + QR_THREADS; r < l; r += QR_THREADS) ss = fma(a[r], a[r], ss);
       }
-      ll_store(p.inbox + (((size_t)par * G + dst) * G + cta) * HW + w, lo, hi, stamp);
-    }
-    LL16* myrec = p.rec + ((size_t)par * G + cta) * l;
-    if (c.id >= 0) {
-      const double* a = colptr(c.id);
-      for (int r = s + 1 + tid; r < l; r += QR_THREADS) ll_store_d(myrec + r, a[r], stamp);
+      ss = warp_sum(ss);
+      if (lane == 0) sred[warp] = ss;
+      __syncthreads();
+      if (cand_lc >= 0) {
+        double ssq = 0.0;
+#pragma unroll
+        for (int w = 0; w < QR_WARPS; ++w) ssq += sred[w];
+        const double alpha = a[s];
+        double beta, tau, scale;
+        if (s >= l - 1 || ssq == 0.0) {
+          beta = alpha;
+          tau = 0.0;
+          scale = 0.0;        // v = e_1
+        } else {
+          beta = -copysign(sqrt(fma(alpha, alpha, ssq)), alpha);
+          tau = (beta - alpha) / beta;
+          scale = 1.0 / (alpha - beta);
+        }
+        const int r0 = s + 1 + tid, r1 = r0 + QR_THREADS;
+        if (r0 < l) ll_store_d(myrec + RECH + r0, xr[0] * scale, stamp);
+        if (r1 < l) ll_store_d(myrec + RECH + r1, xr[1] * scale, stamp);
+        for (int r = r1 + QR_THREADS; r < l; r += QR_THREADS) ll_store_d(myrec + RECH + r, a[r] * scale, stamp);
+        if (tid == 0) {
+          ll_store_d(myrec + 0, tau, stamp);
+          ll_store_d(myrec + 1, beta, stamp);
+          ll_store(myrec + 2, (uint32_t)(col0 + cand_lc), 0u, stamp);
+        }
+      }
     }
     QR_TICK(1)
 
-    // ---- gather my inbox (G*HW contiguous words, all threads poll), pick the winner ----
-    for (int e = tid; e < G * HW; e += QR_THREADS) {
-      const LL16* src = p.inbox + ((size_t)par * G + cta) * G * HW + e;
-      uint32_t lo, hi;
-      if (!ll_load(src, stamp, lo, hi)) s_fail = 1;
-      const int t = e / HW, w = e - t * HW;
-      if (w == 0) hv[t] = __hiloint2double((int)hi, (int)lo);
-      else if (w == 1) hssx[t] = __hiloint2double((int)hi, (int)lo);
-      else if (w == 2) halpha[t] = __hiloint2double((int)hi, (int)lo);
-      else if (w == 3) {
-        hlp[t] = (int)lo;
-        hphys[t] = (int)hi;
-      } else {
-        hps[t] = (int)lo;
-        hflag[t] = (int)hi;
-      }
+    // ---- gather my inbox (G contiguous 32-byte words), pick the winner ----
+    if (tid < G) {
+      double v;
+      int lp, fl;
+      if (!ll32_load(p.inbox + ((size_t)par * G + cta) * G + tid, stamp, v, lp, fl)) s_fail = 1;
+      hv[tid] = v;
+      hlp[tid] = lp;
+      hflag[tid] = fl;
     }
     __syncthreads();
     if (s_fail) {
@@ -347,11 +376,10 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_kernel(QrcpParams p) {
     {
       // lane-local best over its <= ceil(G/32) headers first, then one warp argmax
       double bv = -1.0;
-      int blp = 0x7fffffff, bsrc = -1, aps = -1, aflag = 0;
+      int blp = 0x7fffffff, bsrc = -1, aflag = 0;
       for (int t = lane; t < G; t += 32) {
         const double v = hv[t];
         const int lp = hlp[t];
-        aps = max(aps, hps[t]);
         aflag |= hflag[t];
         if (cand_better(v, lp, bv, blp)) {
           bv = v;
@@ -363,14 +391,9 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_kernel(QrcpParams p) {
       wcta = __shfl_sync(0xffffffffu, bsrc, wl);
       c.v = __shfl_sync(0xffffffffu, bv, wl);       // reuse c as the gathered result
       c.lp = __shfl_sync(0xffffffffu, blp, wl);
-      c.ps = __reduce_max_sync(0xffffffffu, aps);
       c.flag = (int)__reduce_or_sync(0xffffffffu, (unsigned)aflag);
     }
     const int lw = c.lp;               // winner's logical position
-    const int pw = hphys[wcta];        // winner's physical column
-    const int ps = c.ps;               // physical column at logical position s
-    const double alpha = halpha[wcta];
-    const double ssq = hssx[wcta];
     QR_TICK(2)
 
     // ---- block bookkeeping for the previous step (needs the gathered flags) ----
@@ -394,38 +417,43 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_kernel(QrcpParams p) {
     }
     if (s == 0) ptol = fmax(p.atol, p.rtol * c.v);       // src/pqr.jl:386-389
 
-    // ---- Householder vector of the winner column (dlarfg), redundantly per CTA ----
-    // (the winner column's loads are issued first so that their L2 round trip overlaps the sqrt/div)
-    const LL16* wrec = p.rec + ((size_t)par * G + wcta) * l;
-    const int r0 = s + 1 + tid;
-    uint32_t x0lo = 0, x0hi = 0, x0s0 = stamp, x0s1 = stamp;
-    if (r0 < l) ll_ld(wrec + r0, x0lo, x0s0, x0hi, x0s1);
-    double beta, tau, scale;
-    if (s >= l - 1 || ssq == 0.0) {
-      beta = alpha;
-      tau = 0.0;
-      scale = 0.0;        // v = e_1
-    } else {
-      beta = -copysign(sqrt(fma(alpha, alpha, ssq)), alpha);
-      tau = (beta - alpha) / beta;
-      scale = 1.0 / (alpha - beta);
-    }
-    if (tid == 0) vbuf[0] = 1.0;
-    if (r0 < l) {
-      if (x0s0 != stamp || x0s1 != stamp) {
-        if (!ll_load(wrec + r0, stamp, x0lo, x0hi)) s_fail = 1;
+    // ---- the winner's Householder vector (already scaled by its owner), tau, beta, physical column ----
+    const LL16* wrec = p.rec + ((size_t)par * G + wcta) * (l + RECH);
+    double tau, beta;
+    int pw;
+    {
+      // all loads of this thread are issued before the first stamp check: one L2 round trip, not five
+      const int r0 = s + 1 + tid, r1 = r0 + QR_THREADS;
+      uint32_t q[5][4];
+      ll_ld(wrec + 0, q[0][0], q[0][1], q[0][2], q[0][3]);
+      ll_ld(wrec + 1, q[1][0], q[1][1], q[1][2], q[1][3]);
+      ll_ld(wrec + 2, q[2][0], q[2][1], q[2][2], q[2][3]);
+      if (r0 < l) ll_ld(wrec + RECH + r0, q[3][0], q[3][1], q[3][2], q[3][3]);
+      if (r1 < l) ll_ld(wrec + RECH + r1, q[4][0], q[4][1], q[4][2], q[4][3]);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const bool need = (i < 3) || (i == 3 && r0 < l) || (i == 4 && r1 < l);
+        if (need && (q[i][1] != stamp || q[i][3] != stamp)) {
+          const LL16* src = (i < 3) ? wrec + i : wrec + RECH + (i == 3 ? r0 : r1);
+          if (!ll_load(src, stamp, q[i][0], q[i][2])) s_fail = 1;
+        }
       }
-      vbuf[r0 - s] = __hiloint2double((int)x0hi, (int)x0lo) * scale;
-    }
-    for (int r = r0 + QR_THREADS; r < l; r += QR_THREADS) {
-      uint32_t lo, hi;
-      if (!ll_load(wrec + r, stamp, lo, hi)) s_fail = 1;
-      vbuf[r - s] = __hiloint2double((int)hi, (int)lo) * scale;
+      tau = __hiloint2double((int)q[0][2], (int)q[0][0]);
+      beta = __hiloint2double((int)q[1][2], (int)q[1][0]);
+      pw = (int)q[2][0];
+      if (tid == 0) vbuf[0] = 1.0;
+      if (r0 < l) vbuf[r0 - s] = __hiloint2double((int)q[3][2], (int)q[3][0]);
+      if (r1 < l) vbuf[r1 - s] = __hiloint2double((int)q[4][2], (int)q[4][0]);
+      for (int r = r1 + QR_THREADS; r < l; r += QR_THREADS) {
+        uint32_t lo, hi;
+        if (!ll_load(wrec + RECH + r, stamp, lo, hi)) s_fail = 1;
+        vbuf[r - s] = __hiloint2double((int)hi, (int)lo);
+      }
     }
     if (tid == 0) {
       rdblk[cnt] = beta;
       // ---- ownership updates ----
-      if (ps >= col0 && ps < col0 + ncols && ps != pw) lpos[ps - col0] = lw;   // column K moves to pvt
+      if (my_ps >= 0 && my_ps != pw) lpos[my_ps - col0] = lw;   // column K moves to pvt
       if (wcta == cta) {
         lpos[pw - col0] = s;
         p.jpvt[s] = (int64_t)pw + 1;
@@ -682,7 +710,7 @@ int bra_qrcp_run(bra_ctx* ctx, double* B, int64_t ldb, int l, int64_t n, int kca
   const int cpc = (int)((n + G - 1) / G);
 
   // shared-memory budget
-  const size_t fixed = ((size_t)l + nbe + 3 * MAXG) * 8 + 4 * MAXG * 4 + 2 * QR_WARPS * sizeof(Cand) + 64;
+  const size_t fixed = ((size_t)l + nbe + MAXG + QR_WARPS) * 8 + 2 * MAXG * 4 + 2 * QR_WARPS * sizeof(Cand) + 64;
   const size_t budget = (size_t)ctx->smem_optin - 1024;
   const size_t meta = (size_t)cpc * 20 + 16;
   int meta_smem = (fixed + meta <= budget / 2) ? 1 : 0;
@@ -696,8 +724,8 @@ int bra_qrcp_run(bra_ctx* ctx, double* B, int64_t ldb, int l, int64_t n, int kca
   BRA_CUDA(ctx->lpos.reserve((size_t)n * 4));
   // LL exchange buffers: [candidate columns | header inboxes]; zeroed when (re)allocated or when the
   // 32-bit stamp epoch is about to wrap, otherwise reused across launches with a fresh epoch.
-  const size_t col_bytes = (size_t)2 * G * l * sizeof(LL16);
-  const size_t inbox_bytes = (size_t)2 * G * HW * G * sizeof(LL16);
+  const size_t col_bytes = (((size_t)2 * G * (l + RECH) * sizeof(LL16)) + 31) & ~size_t(31);
+  const size_t inbox_bytes = (size_t)2 * G * G * sizeof(LL32);
   const size_t rec_bytes = col_bytes + inbox_bytes;
   if (ctx->rec.cap < rec_bytes || ctx->rec_zeroed < ctx->rec.cap || ctx->rec_epoch > 0xF0000000u) {
     BRA_CUDA(ctx->rec.reserve(rec_bytes));
@@ -727,7 +755,7 @@ int bra_qrcp_run(bra_ctx* ctx, double* B, int64_t ldb, int l, int64_t n, int kca
   p.vn2g = ctx->vn2.as<double>();
   p.lposg = ctx->lpos.as<int>();
   p.rec = ctx->rec.as<LL16>();
-  p.inbox = reinterpret_cast<LL16*>(reinterpret_cast<unsigned char*>(ctx->rec.p) + col_bytes);
+  p.inbox = reinterpret_cast<LL32*>(reinterpret_cast<unsigned char*>(ctx->rec.p) + col_bytes);
   p.epoch = ctx->rec_epoch;
   p.jpvt = ctx->jpvt.as<int64_t>();
   p.tau = ctx->tau.as<double>();
