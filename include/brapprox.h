@@ -38,6 +38,7 @@ extern "C" {
 #define BRA_ERR_ROUNDS 3        /* adaptive loop needed more rounds than random inputs supplied */
 #define BRA_ERR_INTERNAL 4      /* kernel-side failure (exchange timeout etc.) */
 #define BRA_ERR_NOTREADY 5      /* bra_fetch of a factor the last call did not produce */
+#define BRA_ERR_COMM 6          /* NCCL failure or libnccl.so.2 not loadable */
 
 #define BRA_MAX_ROUNDS 24
 
@@ -182,6 +183,20 @@ int bra_pqrfact_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double
 int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* opts,
                      const bra_rand* rnd);
 
+/* ---- multi-GPU: row-sharded tall matrices (BASELINE config 4) ----------------------
+ * One process per GPU, one ctx per process.  Rank 0 calls bra_comm_unique_id and ships the 128 bytes to the other
+ * ranks by any means (the Python host uses torch.distributed); every rank then calls bra_comm_init, which builds
+ * an NCCL communicator bound to the ctx.  After bra_set_row_shard(row0, m_global) the fused entry points
+ * (bra_idfact_f64 / bra_pqrfact_f64 / bra_psvdfact_f64 with trans = 'n', sketch = randn) take the LOCAL row block
+ * (m_local x n): the sketch is all-reduced once per adaptive round, the CholeskyQR2 Gram matrices once per pass;
+ * p, k, T, R, S, Vt come out replicated, Q / U hold the local rows.  Fast-mode Omega is keyed by the GLOBAL row
+ * index, so the factorization does not depend on the number of ranks beyond summation order. */
+int bra_comm_unique_id(void* id128);
+int bra_comm_init(bra_ctx* ctx, const void* id128, int rank, int world);
+int bra_comm_destroy(bra_ctx* ctx);
+int bra_set_row_shard(bra_ctx* ctx, int64_t row0, int64_t m_global);
+uint64_t bra_collective_count(bra_ctx* ctx);
+
 int bra_get_info(bra_ctx* ctx, bra_info* info);
 int bra_fetch(bra_ctx* ctx, int which, void* dst, int64_t ld);
 
@@ -197,7 +212,8 @@ int bra_fetch(bra_ctx* ctx, int which, void* dst, int64_t ld);
 #define BRA_PROF_SVD 8       /* psvd core: k x k Jacobi SVD */
 #define BRA_PROF_QR 9        /* skeleton / Z CholeskyQR2 (Gram GEMMs, Cholesky, triangular solves) */
 #define BRA_PROF_TAILGEMM 10 /* GEMMs of the pqr / psvd tails (same TMA + DMMA kernel) */
-#define BRA_PROF_NTAGS 11
+#define BRA_PROF_COMM 11     /* NCCL all-reduces (row-sharded sketch, Gram matrices) */
+#define BRA_PROF_NTAGS 12
 int bra_profile_enable(bra_ctx* ctx, int on);            /* also clears the accumulators */
 /* accumulated milliseconds and span counts per tag since the last enable; syncs the stream */
 int bra_profile_read(bra_ctx* ctx, double* ms, int64_t* calls);

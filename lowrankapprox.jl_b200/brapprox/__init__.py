@@ -25,6 +25,7 @@ from ._binding import (  # noqa: F401
     lib,
     lib_path,
 )
+from ._dist import block_shard, broadcast_bytes, init_comm, row_shard  # noqa: F401
 from ._frontend import (  # noqa: F401
     default_context,
     geqp3_adap,

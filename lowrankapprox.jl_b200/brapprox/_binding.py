@@ -78,6 +78,12 @@ lib.bra_sketch_randn_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, _i64,
 lib.bra_sketch_sub_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64]
 lib.bra_sketch_sprn_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _i64]
 lib.bra_sketch_srft_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _i64]
+lib.bra_comm_unique_id.argtypes = [_vp]
+lib.bra_comm_init.argtypes = [_vp, _vp, C.c_int, C.c_int]
+lib.bra_comm_destroy.argtypes = [_vp]
+lib.bra_set_row_shard.argtypes = [_vp, _i64, _i64]
+lib.bra_collective_count.argtypes = [_vp]
+lib.bra_collective_count.restype = C.c_uint64
 lib.bra_geqp3_adap_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, C.POINTER(bra_opts), _vp, _vp,
                                    C.POINTER(_i64), C.POINTER(_i64), _vp, _i64, C.POINTER(_i64)]
 lib.bra_trsolve_T_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, _vp, _i64]
@@ -88,7 +94,7 @@ lib.bra_get_info.argtypes = [_vp, C.POINTER(bra_info)]
 lib.bra_fetch.argtypes = [_vp, C.c_int, _vp, _i64]
 lib.bra_profile_enable.argtypes = [_vp, C.c_int]
 lib.bra_profile_read.argtypes = [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
-PROF_TAGS = ["omega", "gemm", "splitk", "qrcp", "gather", "trsolve", "tail", "sketch_other", "svd", "qr", "tail_gemm"]
+PROF_TAGS = ["omega", "gemm", "splitk", "qrcp", "gather", "trsolve", "tail", "sketch_other", "svd", "qr", "tail_gemm", "comm"]
 lib.bra_debug_qrcp_phases.argtypes = [_vp, C.POINTER(C.c_int32)]
 lib.bra_probe_fp64_peak.argtypes = [_vp, C.POINTER(C.c_double)]
 lib.bra_probe_exchange_latency.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(C.c_double)]
@@ -242,6 +248,13 @@ class Context:
 
     def launch_count(self) -> int:
         return int(lib.bra_launch_count(self._h))
+
+    def collective_count(self) -> int:
+        return int(lib.bra_collective_count(self._h))
+
+    def set_row_shard(self, row0: int, m_global: int):
+        """This ctx holds rows [row0, row0 + m_local) of an m_global-row matrix (0, 0 = not sharded)."""
+        self.check(lib.bra_set_row_shard(self._h, row0, m_global))
 
     def profile_enable(self, on: bool = True):
         self.check(lib.bra_profile_enable(self._h, int(on)))

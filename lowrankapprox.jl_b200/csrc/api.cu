@@ -61,6 +61,9 @@ int prepare_omega_t(bra_ctx* ctx, const bra_opts* o, const bra_rand* rnd, int ro
     return bra_transpose_omega(ctx, dOm, ldo, order, mA, ctx->omega_t.as<double>());
   }
   ProfScope ps(ctx, BRA_PROF_OMEGA);
+  if (ctx->shard_m_global > 0)      // row shard: key the stream by the global row index
+    return bra_fill_randn_rows(ctx, ctx->omega_t.as<double>(), ldt, order, ctx->shard_row0,
+                               (ctx->shard_m_global + 1) & ~int64_t(1), o->seed, (uint64_t)round);
   return bra_fill_randn(ctx, ctx->omega_t.as<double>(), order * ldt, o->seed, (uint64_t)round);
 }
 
@@ -73,8 +76,11 @@ int sketch_randn_round(bra_ctx* ctx, char trans, int64_t m, int64_t n, const dou
   if (rc) return rc;
   BRA_CUDA(ctx->B.reserve((size_t)order * nA * 8));
   const int64_t ldt = (mA + 1) & ~int64_t(1);
-  if (trans == 'n') return bra_gemm_sketch(ctx, ctx->omega_t.as<double>(), order, mA, dA, lda, nA, ctx->B.as<double>(), order);
-  return bra_gemm_generic(ctx, ctx->omega_t.as<double>(), ldt, 1, dA, lda, 1, order, nA, mA, ctx->B.as<double>(), order);
+  if (trans == 'n') rc = bra_gemm_sketch(ctx, ctx->omega_t.as<double>(), order, mA, dA, lda, nA, ctx->B.as<double>(), order);
+  else rc = bra_gemm_generic(ctx, ctx->omega_t.as<double>(), ldt, 1, dA, lda, 1, order, nA, mA, ctx->B.as<double>(), order);
+  if (rc) return rc;
+  // row-sharded A: B = sum over ranks of Omega_g * A_g  (one all-reduce of the l x n sketch per round)
+  return bra_allreduce_sum_f64(ctx, ctx->B.as<double>(), order * nA);
 }
 
 // a per-round random input array: device pointer to it (staging host data into `buf`)
@@ -234,6 +240,7 @@ int bra_destroy(bra_ctx* ctx) {
                     &ctx->U, &ctx->S, &ctx->Vt, &ctx->Z, &ctx->scratch, &ctx->scratch2, &ctx->scratch3,
                     &ctx->aux_in1, &ctx->aux_in2, &ctx->jwork, &ctx->At};
   for (DevBuf* b : bufs) b->release();
+  bra_comm_destroy(ctx);
   if (ctx->h_info) cudaFreeHost(ctx->h_info);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -580,6 +587,11 @@ int bra_check_fact_args(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
   }
   if (opts->sketch == BRA_SKETCH_NONE) {
     ctx->set_error("sketch = :none is not built (SURVEY 8f-3)");
+    return BRA_ERR_UNSUPPORTED;
+  }
+  if (ctx->world > 1 && (opts->sketch != BRA_SKETCH_RANDN || trans != 'n')) {
+    ctx->set_error("row-sharded factorizations need sketch = :randn and trans = 'n' (the sharded dimension must be "
+                   "the contracted one)");
     return BRA_ERR_UNSUPPORTED;
   }
   return BRA_OK;

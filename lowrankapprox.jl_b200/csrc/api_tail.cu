@@ -29,7 +29,7 @@ int skeleton_qr(bra_ctx* ctx, char trans, const double* dA, int64_t lda, int64_t
   // Y = C R11^{-1}: R11 is the triangular factor of the SKETCH of these very columns (Omega*C = Q_B*R11)
   rc = bra_trsolve_right_upper(ctx, mA, (int)k, ctx->R11.as<double>(), k, ctx->Q.as<double>(), ldq);
   if (rc) return rc;
-  rc = bra_cholqr2(ctx, mA, (int)k, ctx->Q.as<double>(), ldq, ctx->R11.as<double>(), ctx->R1.as<double>());
+  rc = bra_cholqr2(ctx, mA, (int)k, ctx->Q.as<double>(), ldq, ctx->R11.as<double>(), ctx->R1.as<double>(), true);
   if (rc) return rc;
   // R1 = R_y2 R_y1 R11 inherits the signs of diag(R11) (Householder: -sign(alpha)); normalise to diag(R1) >= 0
   return bra_fix_signs(ctx, mA, (int)k, ctx->Q.as<double>(), ldq, ctx->R1.as<double>(), k);

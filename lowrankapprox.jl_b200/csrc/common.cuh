@@ -90,6 +90,11 @@ struct bra_ctx {
   std::vector<unsigned char> h_meta;  // host scratch for fast-mode index/sign generation
   DevBuf At;                   // transposed copy of A for the (:left,:c) SRFT
   bool At_valid = false;
+  // multi-GPU (comm.cu): NCCL communicator over the ranks that hold the row blocks of one tall matrix
+  void* nccl_comm = nullptr;
+  int rank = 0, world = 1;
+  int64_t shard_row0 = 0, shard_m_global = 0;   // this rank's first global row / total rows (0: not sharded)
+  uint64_t collectives = 0;
   int gemm_tag = BRA_PROF_GEMM; // profiling tag the GEMM launchers record under (tails switch it)
   uint32_t rec_epoch = 1;
   size_t rec_zeroed = 0;
@@ -154,11 +159,16 @@ int bra_gather_R(bra_ctx* ctx, const double* B, int64_t ldb, int64_t n, int k,
 // sketch_randn.cu
 int bra_transpose_omega(bra_ctx* ctx, const double* Om, int64_t ldo, int64_t l, int64_t m, double* Omt);
 int bra_fill_randn(bra_ctx* ctx, double* dst, int64_t count, uint64_t seed, uint64_t stream_id);
+int bra_fill_randn_rows(bra_ctx* ctx, double* dst, int64_t ldt, int64_t order, int64_t row0, int64_t ldg, uint64_t seed,
+                        uint64_t stream_id);
 int bra_gemm_sketch(bra_ctx* ctx, const double* Omt, int64_t l, int64_t m, const double* A, int64_t lda,
                     int64_t n, double* B, int64_t ldb);
 int bra_gemm_tn(bra_ctx* ctx, const double* X, int64_t ldx, int64_t l, int64_t m, const double* Y, int64_t ldy,
                 int64_t n, double* C, int64_t ldc);
 bool bra_gemm_tma_ok(const double* A, int64_t lda, int64_t m, int64_t n);
+
+// comm.cu
+int bra_allreduce_sum_f64(bra_ctx* ctx, double* buf, int64_t count);
 
 // sketch_other.cu
 int bra_sketch_sub(bra_ctx* ctx, char trans, const double* A, int64_t lda, int64_t mA, int64_t nA, int64_t order,
@@ -177,7 +187,8 @@ int bra_gather_cols(bra_ctx* ctx, char trans, const double* A, int64_t lda, int6
 int bra_transpose(bra_ctx* ctx, const double* src, int64_t lds, int64_t rows, int64_t cols, double* dst, int64_t ldd);
 int bra_trsolve_right_upper(bra_ctx* ctx, int64_t rows, int k, const double* R, int64_t ldr, double* Y, int64_t ldy);
 int bra_cholesky_upper(bra_ctx* ctx, int k, double* G, int64_t ldg, double* Rout, int64_t ldr);
-int bra_cholqr2(bra_ctx* ctx, int64_t rows, int k, double* Y, int64_t ldy, const double* Rpre, double* Rout);
+int bra_cholqr2(bra_ctx* ctx, int64_t rows, int k, double* Y, int64_t ldy, const double* Rpre, double* Rout,
+                bool rows_sharded = false);
 int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64_t ldj, double* sigma_host,
                    int* order_host);
 extern "C" {

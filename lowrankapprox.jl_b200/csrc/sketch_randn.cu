@@ -284,6 +284,47 @@ __global__ void fill_randn_kernel(double* __restrict__ dst, int64_t count, uint6
   }
 }
 
+// Same stream, addressed by GLOBAL position: local element (i, k) of the K-major Omega^T block of a row shard is
+// element e = i*ldg + row0 + k of the (seed, stream_id) sequence, ldg = roundup(m_global, 2).  With row0 = 0 and
+// ldg = ldt this reproduces fill_randn_kernel exactly.
+__device__ __forceinline__ void philox_normal_pair(uint64_t pidx, uint64_t seed, uint64_t stream_id, double& z0, double& z1) {
+  uint32_t c[4] = {(uint32_t)pidx, (uint32_t)(pidx >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32)};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  const double u1 = ((double)(((uint64_t)c[0] << 21) ^ (c[1] >> 11)) + 1.0) * (1.0 / 9007199254740992.0);
+  const double u2 = ((double)(((uint64_t)c[2] << 21) ^ (c[3] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+  const double rad = sqrt(-2.0 * log(u1));
+  double sn, cs;
+  sincospi(2.0 * u2, &sn, &cs);
+  z0 = rad * cs;
+  z1 = rad * sn;
+}
+__global__ void fill_randn_rows_kernel(double* __restrict__ dst, int64_t ldt, int64_t order, int64_t row0, int64_t ldg,
+                                       uint64_t seed, uint64_t stream_id) {
+  const int64_t hp = ldt / 2, pairs = order * hp;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < pairs; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / hp, k = 2 * (t - i * hp);
+    const uint64_t e0 = (uint64_t)(i * ldg + row0 + k);
+    double a, b, z0, z1;
+    philox_normal_pair(e0 >> 1, seed, stream_id, z0, z1);
+    if ((e0 & 1) == 0) {
+      a = z0;
+      b = z1;
+    } else {
+      a = z1;
+      philox_normal_pair((e0 + 1) >> 1, seed, stream_id, z0, z1);
+      b = z0;
+    }
+    dst[k + i * ldt] = a;
+    dst[k + 1 + i * ldt] = b;
+  }
+}
+
 // ------------------------------------------------------------------ tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -388,6 +429,15 @@ int bra_transpose_omega(bra_ctx* ctx, const double* Om, int64_t ldo, int64_t l, 
 int bra_fill_randn(bra_ctx* ctx, double* dst, int64_t count, uint64_t seed, uint64_t stream_id) {
   if (count <= 0) return BRA_OK;
   fill_randn_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(dst, count, seed, stream_id);
+  ctx->launches++;
+  BRA_CUDA(cudaGetLastError());
+  return BRA_OK;
+}
+
+int bra_fill_randn_rows(bra_ctx* ctx, double* dst, int64_t ldt, int64_t order, int64_t row0, int64_t ldg, uint64_t seed,
+                        uint64_t stream_id) {
+  if (order <= 0 || ldt <= 0) return BRA_OK;
+  fill_randn_rows_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(dst, ldt, order, row0, ldg, seed, stream_id);
   ctx->launches++;
   BRA_CUDA(cudaGetLastError());
   return BRA_OK;
