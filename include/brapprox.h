@@ -39,6 +39,7 @@ extern "C" {
 #define BRA_ERR_INTERNAL 4      /* kernel-side failure (exchange timeout etc.) */
 #define BRA_ERR_NOTREADY 5      /* bra_fetch of a factor the last call did not produce */
 #define BRA_ERR_COMM 6          /* NCCL failure or libnccl.so.2 not loadable */
+#define BRA_ERR_TSLOT 7         /* batched idfact: some block has k > ldT (k_out is valid; enlarge the T slots) */
 
 #define BRA_MAX_ROUNDS 24
 
@@ -183,6 +184,21 @@ int bra_pqrfact_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double
 int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* opts,
                      const bra_rand* rnd);
 
+/* ---- batched idfact of independent blocks (BASELINE config 5; additive: the reference loops idfact) --------
+ * nblocks column-major m x n blocks, block b at A + b*strideA (leading dimension lda), all DEVICE resident.
+ * opts as for idfact with sketch = :sprn.  Random inputs in reference order per block (src/sketch.jl:575-579):
+ * perm (1-based randperm(m)) and s (m weights), block b at perm + b*perm_stride / s + b*s_stride (stride 0 shares
+ * one draw); perm = s = NULL selects the fast mode (one library-drawn (perm, s) per call, shared by the batch).
+ * Outputs (device): k_out[b]; p_out[b*n .. b*n+n) 1-based pivots (sk = first k_b, rd = rest); T_b (k_b x (n-k_b))
+ * at T_out + b*strideT with leading dimension ldT.  One fused kernel (sketch -> QRCP -> T, one CTA per block) runs
+ * the first adaptive round; blocks with k_b >= nb continue through the general path (bra_batched_unfinished tells
+ * how many).  Returns BRA_ERR_TSLOT if some k_b > ldT (k_out and p_out are valid, that block's T is not stored). */
+int bra_idfact_batched_f64(bra_ctx* ctx, int64_t nblocks, int64_t m, int64_t n, const double* A, int64_t lda,
+                           int64_t strideA, const bra_opts* opts, const int64_t* perm, int64_t perm_stride,
+                           const double* s, int64_t s_stride, int64_t* k_out, int64_t* p_out, double* T_out,
+                           int64_t ldT, int64_t strideT);
+int64_t bra_batched_unfinished(bra_ctx* ctx);
+
 /* ---- multi-GPU: row-sharded tall matrices (BASELINE config 4) ----------------------
  * One process per GPU, one ctx per process.  Rank 0 calls bra_comm_unique_id and ships the 128 bytes to the other
  * ranks by any means (the Python host uses torch.distributed); every rank then calls bra_comm_init, which builds
@@ -213,7 +229,8 @@ int bra_fetch(bra_ctx* ctx, int which, void* dst, int64_t ld);
 #define BRA_PROF_QR 9        /* skeleton / Z CholeskyQR2 (Gram GEMMs, Cholesky, triangular solves) */
 #define BRA_PROF_TAILGEMM 10 /* GEMMs of the pqr / psvd tails (same TMA + DMMA kernel) */
 #define BRA_PROF_COMM 11     /* NCCL all-reduces (row-sharded sketch, Gram matrices) */
-#define BRA_PROF_NTAGS 12
+#define BRA_PROF_BATCHED 12  /* fused one-CTA-per-block batched idfact kernel */
+#define BRA_PROF_NTAGS 13
 int bra_profile_enable(bra_ctx* ctx, int on);            /* also clears the accumulators */
 /* accumulated milliseconds and span counts per tag since the last enable; syncs the stream */
 int bra_profile_read(bra_ctx* ctx, double* ms, int64_t* calls);

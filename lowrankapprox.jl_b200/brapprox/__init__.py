@@ -31,6 +31,8 @@ from ._frontend import (  # noqa: F401
     geqp3_adap,
     id,
     idfact,
+    idfact_batched,
+    idfact_batched_device,
     idfact_device,
     pqr,
     pqrfact,

@@ -78,6 +78,10 @@ lib.bra_sketch_randn_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, _i64,
 lib.bra_sketch_sub_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64]
 lib.bra_sketch_sprn_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _i64]
 lib.bra_sketch_srft_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _i64]
+lib.bra_idfact_batched_f64.argtypes = [_vp, _i64, _i64, _i64, _vp, _i64, _i64, C.POINTER(bra_opts), _vp, _i64, _vp, _i64,
+                                       _vp, _vp, _vp, _i64, _i64]
+lib.bra_batched_unfinished.argtypes = [_vp]
+lib.bra_batched_unfinished.restype = C.c_int64
 lib.bra_comm_unique_id.argtypes = [_vp]
 lib.bra_comm_init.argtypes = [_vp, _vp, C.c_int, C.c_int]
 lib.bra_comm_destroy.argtypes = [_vp]
@@ -94,7 +98,7 @@ lib.bra_get_info.argtypes = [_vp, C.POINTER(bra_info)]
 lib.bra_fetch.argtypes = [_vp, C.c_int, _vp, _i64]
 lib.bra_profile_enable.argtypes = [_vp, C.c_int]
 lib.bra_profile_read.argtypes = [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
-PROF_TAGS = ["omega", "gemm", "splitk", "qrcp", "gather", "trsolve", "tail", "sketch_other", "svd", "qr", "tail_gemm", "comm"]
+PROF_TAGS = ["omega", "gemm", "splitk", "qrcp", "gather", "trsolve", "tail", "sketch_other", "svd", "qr", "tail_gemm", "comm", "batched"]
 lib.bra_debug_qrcp_phases.argtypes = [_vp, C.POINTER(C.c_int32)]
 lib.bra_probe_fp64_peak.argtypes = [_vp, C.POINTER(C.c_double)]
 lib.bra_probe_exchange_latency.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(C.c_double)]

@@ -185,6 +185,59 @@ def idfact(A, opts: Optional[LRAOptions] = None, trans: str = "n", rand=None,
     return IDPackedV(p[:k].copy(), p[k:].copy(), T, rounds, steps)
 
 
+def idfact_batched_device(a_ptr: int, nblocks: int, m: int, n: int, lda: int, stride_a: int, k_ptr: int, p_ptr: int,
+                          t_ptr: int, ld_t: int, stride_t: int, opts: Optional[LRAOptions] = None,
+                          perm_ptr: int = 0, perm_stride: int = 0, s_ptr: int = 0, s_stride: int = 0,
+                          ctx: Optional[Context] = None, **kw) -> int:
+    """Batched idfact of `nblocks` independent device-resident m x n blocks (the reference would loop idfact,
+    src/id.jl:434-447): raw device pointers in, results left on the device.  Returns the number of blocks that
+    needed adaptive rounds beyond the fused first one."""
+    o = _opts(opts, kw)
+    o.pqrfact_retval = "t"
+    ctx = ctx or default_context()
+    co = o.to_c()
+    ctx.check(lib.bra_idfact_batched_f64(ctx.handle, nblocks, m, n, C.c_void_p(a_ptr), lda, stride_a, C.byref(co),
+                                         C.c_void_p(perm_ptr or None), perm_stride, C.c_void_p(s_ptr or None), s_stride,
+                                         C.c_void_p(k_ptr), C.c_void_p(p_ptr), C.c_void_p(t_ptr), ld_t, stride_t))
+    return int(lib.bra_batched_unfinished(ctx.handle))
+
+
+def idfact_batched(blocks, opts: Optional[LRAOptions] = None, rand: Optional[Sequence[dict]] = None,
+                   ctx: Optional[Context] = None, device: int = 0, ld_t: Optional[int] = None, **kw) -> List[IDPackedV]:
+    """[idfact(A_b, opts) for A_b in blocks] through the fused batched kernel.  `blocks` is an array of shape
+    (nblocks, m, n); `rand[b]` = {"perm": ..., "s": ...} carries block b's reference-order random inputs (omit for
+    the fast mode).  torch is used here only to hold the device buffers."""
+    import torch
+    o = _opts(opts, kw)
+    ctx = ctx or default_context(device)
+    dev = torch.device("cuda", device)
+    blk = np.asarray(blocks, dtype=np.float64)
+    nb, m, n = blk.shape
+    At = torch.from_numpy(np.ascontiguousarray(blk.transpose(0, 2, 1))).to(dev)       # block b column-major, lda = m
+    ld_t = int(ld_t or min(o.nb, m, n))
+    kd = torch.zeros(nb, dtype=torch.int64, device=dev)
+    pd = torch.zeros((nb, n), dtype=torch.int64, device=dev)
+    Td = torch.zeros((nb, n, ld_t), dtype=torch.float64, device=dev)
+    perm_ptr = s_ptr = 0
+    keep = None
+    if rand is not None:
+        permd = torch.from_numpy(np.stack([np.asarray(r["perm"], dtype=np.int64) for r in rand])).to(dev)
+        sd = torch.from_numpy(np.stack([np.asarray(r["s"], dtype=np.float64) for r in rand])).to(dev)
+        keep = (permd, sd)
+        perm_ptr, s_ptr = permd.data_ptr(), sd.data_ptr()
+    torch.cuda.synchronize(dev)
+    idfact_batched_device(At.data_ptr(), nb, m, n, m, m * n, kd.data_ptr(), pd.data_ptr(), Td.data_ptr(), ld_t,
+                          ld_t * n, o, perm_ptr, m if rand is not None else 0, s_ptr, m if rand is not None else 0, ctx)
+    ks, ps, Ts = kd.cpu().numpy(), pd.cpu().numpy(), Td.cpu().numpy()
+    del keep
+    out = []
+    for b in range(nb):
+        k = int(ks[b])
+        T = np.asfortranarray(Ts[b, : n - k, :k].T)
+        out.append(IDPackedV(ps[b, :k].copy(), ps[b, k:].copy(), T))
+    return out
+
+
 def id(A, *args, **kw):
     """id(...) -> (sk, rd, T) (src/id.jl:452-456)."""
     V = idfact(A, *args, **kw)

@@ -509,8 +509,8 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
   QrcpOut q = {0, 0, 0, 0};
   int64_t order = 0;
   if (o->sketchfact_adap || o->rank < 0) {
-    int64_t nn = o->nb;                                              // src/sketch.jl:226
-    for (int round = 0;; ++round) {
+    int64_t nn = o->nb << ctx->start_round;                          // src/sketch.jl:226 (n doubles every round)
+    for (int round = ctx->start_round;; ++round) {
       if (round >= BRA_MAX_ROUNDS) {
         ctx->set_error("adaptive loop exceeded BRA_MAX_ROUNDS");
         return BRA_ERR_ROUNDS;

@@ -1,0 +1,430 @@
+// Batched idfact of many independent small blocks (BASELINE config 5: 16384 HODLR-style 512 x 512 off-diagonal
+// blocks, sketch = :sprn).  The reference has no batched API: this is the loop
+//     for b in blocks: idfact(A_b; sketch=:sprn, ...)          src/id.jl:434-447 -> src/sketch.jl:674-690
+// fused into ONE kernel, one CTA per block at a time:
+//   sparse-Gaussian sketch (src/sketch.jl:571-589)  ->  early-terminating QRCP with dlaqps semantics
+//   (src/pqr.jl:361-418)  ->  T = R11^{-1} R12 (src/pqr.jl:438-442),
+// with the l x n sketch living entirely on chip: shared memory while it is being formed (each entry of A_b is
+// read from HBM exactly once, coalesced, through a per-warp column stage), then one COLUMN PER THREAD in
+// registers for the factorization, so that the Householder dot products and rank-1 updates need no cross-lane
+// traffic at all; only the pivot search (redux.sync argmax + 16-entry merge) and the pivot column broadcast go
+// through shared memory.  HBM-bound by design: 8 m n bytes per block in, p, k and the k x (n-k) T out.
+//
+// This kernel covers the first adaptive round (order = nb <= 32, n <= 512, m*8*16 <= 64 KB of column stages);
+// blocks that do not terminate in it (k >= nb) and other shapes go through the general single-matrix path.
+#include "common.cuh"
+#include "qrcp_common.cuh"
+#include <algorithm>
+#include <vector>
+
+namespace {
+
+constexpr int BT = 512;            // threads = columns per block
+constexpr int BW = BT / 32;        // warps
+constexpr int BL = 32;             // sketch rows held in registers per thread
+
+struct BatchParams {
+  const double* A;
+  int64_t lda, strideA;
+  int m, n, l, kcap, nb;
+  double atol, rtol;
+  const int64_t* perm;     // 1-based randperm(m); block b at perm + b*perm_stride (0 = shared by all blocks)
+  int64_t perm_stride;
+  const double* s;         // weights, same layout
+  int64_t s_stride;
+  const int32_t* blocks;   // optional list of block ids to process (nullptr: 0..nblocks-1)
+  int nblocks;
+  int64_t* kout;           // [block id]
+  int64_t* pout;           // [block id][n], 1-based
+  double* Tout;            // block b: k_b x (n - k_b) at Tout + b*strideT, leading dimension ldT
+  int64_t ldT, strideT;
+  int32_t* status;         // [block id]: 0 ok, 1 T slot too small (k_b > ldT)
+};
+
+__global__ void __launch_bounds__(BT, 1) idfact_batched_kernel(BatchParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m = P.m, n = P.n, l = P.l;
+  const int mpad = (m + 1) & ~1;
+  constexpr int BSTR = BT + 1;                                   // padded row stride of the staged sketch
+  double* Bs = reinterpret_cast<double*>(smem_raw);             // [BL][BSTR]
+  double* colbuf = Bs + (size_t)BL * BSTR;                      // [BW][mpad]  (later: R11, [BL][BL+1])
+  double* sv = colbuf + (size_t)BW * mpad;                      // [mpad]
+  double* vv = sv + mpad;                                       // [BL] Householder vector
+  double* rdblk = vv + BL;                                      // [BL] diagonal of R within the current block
+  double* cv = rdblk + BL;                                      // [BW] warp candidates: norm
+  double* hh = cv + BW;                                         // tau, beta
+  int* clp = reinterpret_cast<int*>(hh + 2);                    // [BW] logical position
+  int* ctd = clp + BW;                                          // [BW] owning thread
+  int* permv = ctd + BW;                                        // [mpad] 0-based
+  double* mycol = colbuf + (size_t)warp * mpad;
+
+  const int lmin = min(l, n);
+  const int64_t q = m / l, rem = m % l;                          // p_i = q + (i < rem), off_i = i*q + min(i, rem)
+  bool tables_loaded = false;
+
+  for (int it = blockIdx.x; it < P.nblocks; it += gridDim.x) {
+    const int b = P.blocks ? P.blocks[it] : it;
+    const double* Ab = P.A + (int64_t)b * P.strideA;
+    __syncthreads();
+    if (!tables_loaded || P.perm_stride != 0 || P.s_stride != 0) {
+      const int64_t* pb = P.perm + (int64_t)b * P.perm_stride;
+      const double* sb = P.s + (int64_t)b * P.s_stride;
+      for (int r = tid; r < m; r += BT) {
+        permv[r] = (int)(pb[r] - 1);
+        sv[r] = sb[r];
+      }
+      tables_loaded = true;
+      __syncthreads();
+    }
+
+    // ---- sparse-Gaussian sketch: warp w stages column j (coalesced), lane i forms B[i, j] ----
+    for (int j = warp; j < n; j += BW) {
+      const double* a = Ab + (int64_t)j * P.lda;
+#pragma unroll 8
+      for (int r = lane; r < m; r += 32) mycol[r] = a[r];
+      __syncwarp();
+      if (lane < l) {
+        const int64_t pi = q + (lane < rem ? 1 : 0);
+        const int64_t off = (int64_t)lane * q + (lane < rem ? lane : rem);
+        double acc = 0.0;
+        for (int64_t t = 0; t < pi; ++t) acc += sv[off + t] * mycol[permv[off + t]];
+        Bs[lane * BSTR + j] = acc;
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- one column per thread, in registers ----
+    const bool live = tid < n;
+    double a[BL];
+#pragma unroll
+    for (int i = 0; i < BL; ++i) a[i] = (live && i < l) ? Bs[i * BSTR + tid] : 0.0;
+    double vn1, vn2;
+    {
+      // initial norm (src/pqr.jl:376-385), power-of-two scaled like the grid-wide kernel
+      double amax = 0.0;
+#pragma unroll
+      for (int i = 0; i < BL; ++i) amax = fmax(amax, fabs(a[i]));
+      double nrm = 0.0;
+      if (amax > 0.0) {
+        const int e = ilogb(amax);
+        const double sc = scalbn(1.0, -e);
+        double ss = 0.0;
+#pragma unroll
+        for (int i = 0; i < BL; ++i) {
+          const double x = a[i] * sc;
+          ss = fma(x, x, ss);
+        }
+        nrm = scalbn(sqrt(ss), e);
+      }
+      vn1 = vn2 = nrm;
+    }
+    int lpos = live ? tid : 0x7fffffff;
+
+    int s = 0, jblk = 0, cnt = 0, jb = min(P.nb, P.kcap), kres = (P.kcap == 0) ? 0 : -1;
+    double ptol = 0.0;
+    int pend_flag = 0;          // a column was flagged in the previous step
+    while (kres < 0) {
+      // ---- pivot search: first maximum of the downdated norms (idamax) ----
+      {
+        const double v = (live && lpos >= s) ? vn1 : -1.0;
+        const int wl = warp_argmax(v, lpos);
+        if (lane == wl) {
+          cv[warp] = v;
+          clp[warp] = lpos;
+          ctd[warp] = tid;
+        }
+      }
+      __syncthreads();
+      double wv;
+      int wlp, wt;
+      {
+        const double v = (lane < BW) ? cv[lane] : -1.0;
+        const int lp = (lane < BW) ? clp[lane] : 0x7fffffff;
+        const int wl = warp_argmax(v, lp);
+        wv = __shfl_sync(0xffffffffu, v, wl);
+        wlp = __shfl_sync(0xffffffffu, lp, wl);
+        wt = ctd[wl];
+      }
+      // ---- block bookkeeping for the previous step (a flagged column ends dlaqps' block) ----
+      if (cnt > 0 && pend_flag) {
+        if (fabs(rdblk[cnt - 1]) <= ptol) {
+          for (int i = 0; i < cnt; ++i)
+            if (fabs(rdblk[i]) <= ptol) {
+              kres = jblk + i;
+              break;
+            }
+        }
+        if (kres >= 0) break;
+        jblk += cnt;
+        cnt = 0;
+        jb = min(P.nb, P.kcap - jblk);
+      }
+      if (s == 0) ptol = fmax(P.atol, P.rtol * wv);                  // src/pqr.jl:386-389
+
+      // ---- pivot column -> shared memory; warp 0 runs dlarfg on it ----
+      if (tid == wt) {
+#pragma unroll
+        for (int i = 0; i < BL; ++i) vv[i] = a[i];
+      }
+      __syncthreads();
+      if (warp == 0) {
+        const double x = (lane > s && lane < l) ? vv[lane] : 0.0;
+        const double ssq = warp_sum(x * x);
+        const double alpha = vv[s];
+        double beta, tau, scale;
+        if (s >= l - 1 || ssq == 0.0) {
+          beta = alpha;
+          tau = 0.0;
+          scale = 0.0;
+        } else {
+          beta = -copysign(sqrt(fma(alpha, alpha, ssq)), alpha);
+          tau = (beta - alpha) / beta;
+          scale = 1.0 / (alpha - beta);
+        }
+        __syncwarp();
+        vv[lane] = (lane == s) ? 1.0 : x * scale;                   // v: 1 at row s, zeros above, scaled tail below
+        if (lane == 0) {
+          hh[0] = tau;
+          hh[1] = beta;
+          rdblk[cnt] = beta;
+        }
+      }
+      __syncthreads();
+      const double tau = hh[0], beta = hh[1];
+      // ---- ownership (no physical swaps: logical positions move instead) ----
+      if (live && lpos == s && tid != wt) lpos = wlp;                // column K takes the pivot's old position
+      if (tid == wt) {
+        lpos = s;
+#pragma unroll
+        for (int i = 0; i < BL; ++i)
+          if (i == s) a[i] = beta;                                   // R[s, s]
+      }
+      // ---- apply H to my column, downdate its norm (dlaqps steps 5-8 fused) ----
+      int flagged = 0;
+      if (live && lpos > s) {
+        double dot = 0.0;
+#pragma unroll
+        for (int i = 0; i < BL; ++i)
+          if (i >= s) dot = fma(a[i], vv[i], dot);
+        const double f = tau * dot;
+        double rs = 0.0;
+#pragma unroll
+        for (int i = 0; i < BL; ++i)
+          if (i >= s) {
+            a[i] = fma(-f, vv[i], a[i]);
+            if (i == s) rs = a[i];
+          }
+        if (s < lmin - 1 && vn1 != 0.0) {
+          double t = fabs(rs) / vn1;
+          t = fmax(0.0, (1.0 + t) * (1.0 - t));
+          const double r2 = vn1 / vn2;
+          const double t2 = t * (r2 * r2);
+          if (t2 <= TOL3Z) {
+            // flagged: norm recomputed from rows s+1.. of the updated column
+            double ss = 0.0;
+#pragma unroll
+            for (int i = 0; i < BL; ++i)
+              if (i > s) ss = fma(a[i], a[i], ss);
+            vn1 = vn2 = sqrt(ss);
+            flagged = 1;
+          } else {
+            vn1 *= sqrt(t);
+          }
+        }
+      }
+      pend_flag = __syncthreads_or(flagged);
+      // ---- end of step ----
+      ++cnt;
+      ++s;
+      if (cnt == jb) {
+        // block ends by count; flags raised in this step are irrelevant
+        pend_flag = 0;
+        if (fabs(rdblk[cnt - 1]) <= ptol) {
+          for (int i = 0; i < cnt; ++i)
+            if (fabs(rdblk[i]) <= ptol) {
+              kres = jblk + i;
+              break;
+            }
+        }
+        if (kres >= 0) break;
+        jblk += cnt;
+        cnt = 0;
+        if (jblk >= P.kcap) {
+          kres = P.kcap;
+          break;
+        }
+        jb = min(P.nb, P.kcap - jblk);
+      }
+    }
+    const int k = kres;
+
+    // ---- outputs: p, k, T = R11^{-1} R12 ----
+    if (live) P.pout[(int64_t)b * n + lpos] = (int64_t)tid + 1;
+    if (tid == 0) {
+      P.kout[b] = k;
+      P.status[b] = (k > P.ldT) ? 1 : 0;
+    }
+    __syncthreads();
+    double* R11 = colbuf;                                            // [BL][BL+1], row-major with padding
+    if (live && lpos < k) {
+#pragma unroll
+      for (int i = 0; i < BL; ++i)
+        if (i < k) R11[i * (BL + 1) + lpos] = (i <= lpos) ? a[i] : 0.0;
+    }
+    __syncthreads();
+    if (live && lpos >= k && k <= P.ldT) {
+      // back substitution on my column of R12 (dtrsm L,U,N,N), entirely in registers
+#pragma unroll
+      for (int i = BL - 1; i >= 0; --i) {
+        if (i < k) {
+          double x = a[i];
+#pragma unroll
+          for (int j = i + 1; j < BL; ++j)
+            if (j < k) x = fma(-R11[i * (BL + 1) + j], a[j], x);
+          a[i] = x / R11[i * (BL + 1) + i];
+        }
+      }
+      double* t = P.Tout + (int64_t)b * P.strideT + (int64_t)(lpos - k) * P.ldT;
+#pragma unroll
+      for (int i = 0; i < BL; ++i)
+        if (i < k) t[i] = a[i];
+    }
+  }
+}
+
+}  // namespace
+
+int bra_fill_meta(bra_ctx* ctx, int kind, void* dst_dev, int64_t count, int64_t range, uint64_t seed, uint64_t stream_id);
+
+extern "C" {
+
+int bra_idfact_batched_f64(bra_ctx* ctx, int64_t nblocks, int64_t m, int64_t n, const double* A, int64_t lda,
+                           int64_t strideA, const bra_opts* opts, const int64_t* perm, int64_t perm_stride,
+                           const double* s, int64_t s_stride, int64_t* k_out, int64_t* p_out, double* T_out,
+                           int64_t ldT, int64_t strideT) {
+  if (!ctx) return -1;
+  BRA_CHECK_ARG(nblocks >= 0, 2, "nblocks");
+  BRA_CHECK_ARG(m >= 1, 3, "m");
+  BRA_CHECK_ARG(n >= 1, 4, "n");
+  BRA_CHECK_ARG(A != nullptr || nblocks == 0, 5, "A");
+  BRA_CHECK_ARG(lda >= m, 6, "lda");
+  BRA_CHECK_ARG(strideA >= lda * (n - 1) + m || nblocks <= 1, 7, "strideA");
+  if (bra_chkopts(ctx, opts)) return -8;
+  BRA_CHECK_ARG((perm == nullptr) == (s == nullptr), 9, "perm and s must be given together");
+  BRA_CHECK_ARG(k_out != nullptr && p_out != nullptr && T_out != nullptr, 13, "outputs");
+  BRA_CHECK_ARG(ldT >= 1 && strideT >= ldT * n, 16, "ldT/strideT");
+  if (nblocks == 0) return BRA_OK;
+  BRA_CUDA(cudaSetDevice(ctx->device));
+  if (!is_device_ptr(A) || !is_device_ptr(k_out) || !is_device_ptr(p_out) || !is_device_ptr(T_out) ||
+      (perm && (!is_device_ptr(perm) || !is_device_ptr(s)))) {
+    ctx->set_error("bra_idfact_batched_f64 takes device-resident blocks, random inputs and outputs");
+    return BRA_ERR_UNSUPPORTED;
+  }
+  if (opts->sketch != BRA_SKETCH_SPRN || opts->maxdet_tol >= 0 || opts->sketch_randn_niter > 0) {
+    ctx->set_error("the batched kernel is built for sketch = :sprn (BASELINE config 5)");
+    return BRA_ERR_UNSUPPORTED;
+  }
+  // first adaptive round: order = nb (src/sketch.jl:677-680); non-adaptive: order = rank (:686)
+  const bool adaptive = opts->sketchfact_adap || opts->rank < 0;
+  const int64_t order = adaptive ? opts->nb : opts->rank;
+  const int64_t mpad = (m + 1) & ~int64_t(1);
+  const size_t smem = ((size_t)BL * (BT + 1) + (size_t)BW * mpad + mpad + 2 * BL + BW + 2) * 8 + (2 * BW + mpad) * 4 + 64;
+  if (order < 1 || order > BL || n > BT || order > m || smem > (size_t)ctx->smem_optin ||
+      (size_t)BW * mpad < (size_t)BL * (BL + 1)) {
+    ctx->set_error("batched idfact: shape outside the fused kernel (needs order = nb <= 32, n <= 512, "
+                   "32 <= m <= ~1000); factor such blocks one by one with bra_idfact_f64");
+    return BRA_ERR_UNSUPPORTED;
+  }
+  const int64_t lmin = order < n ? order : n;
+  const int64_t kcap = (opts->rank < 0 || opts->rank > lmin) ? lmin : opts->rank;
+
+  BatchParams P;
+  P.A = A;
+  P.lda = lda;
+  P.strideA = strideA;
+  P.m = (int)m;
+  P.n = (int)n;
+  P.l = (int)order;
+  P.kcap = (int)kcap;
+  P.nb = (int)(opts->nb < kcap ? opts->nb : (kcap > 0 ? kcap : 1));
+  P.atol = opts->atol;
+  P.rtol = opts->rtol;
+  if (perm) {
+    P.perm = perm;
+    P.perm_stride = perm_stride;
+    P.s = s;
+    P.s_stride = s_stride;
+  } else {
+    // fast mode: ONE (perm, s) draw per call, shared by all blocks of the batch (device Philox weights)
+    BRA_CUDA(ctx->aux_in1.reserve((size_t)m * 8));
+    BRA_CUDA(ctx->aux_in2.reserve((size_t)(m + 1) * 8));
+    int rc = bra_fill_meta(ctx, 2, ctx->aux_in1.p, m, m, opts->seed, 0);
+    if (rc) return rc;
+    rc = bra_fill_randn(ctx, ctx->aux_in2.as<double>(), m, opts->seed, 0);
+    if (rc) return rc;
+    P.perm = ctx->aux_in1.as<int64_t>();
+    P.perm_stride = 0;
+    P.s = ctx->aux_in2.as<double>();
+    P.s_stride = 0;
+  }
+  P.blocks = nullptr;
+  P.nblocks = (int)nblocks;
+  P.kout = k_out;
+  P.pout = p_out;
+  P.Tout = T_out;
+  P.ldT = ldT;
+  P.strideT = strideT;
+  BRA_CUDA(ctx->scratch.reserve((size_t)nblocks * 4));
+  P.status = ctx->scratch.as<int32_t>();
+  BRA_CUDA(cudaFuncSetAttribute(idfact_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)std::min<int64_t>(nblocks, ctx->num_sms);
+  {
+    ProfScope ps(ctx, BRA_PROF_BATCHED);
+    idfact_batched_kernel<<<grid, BT, smem, ctx->stream>>>(P);
+  }
+  ctx->launches++;
+  BRA_CUDA(cudaGetLastError());
+  // k is data dependent: read it back (the only host sync), report blocks the fused round could not finish
+  std::vector<int64_t> hk((size_t)nblocks);
+  std::vector<int32_t> hs((size_t)nblocks);
+  BRA_CUDA(cudaMemcpyAsync(hk.data(), k_out, (size_t)nblocks * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  BRA_CUDA(cudaMemcpyAsync(hs.data(), P.status, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+  int64_t unfinished = 0, tslot = 0;
+  for (int64_t b = 0; b < nblocks; ++b) {
+    if (hs[(size_t)b]) ++tslot;
+    // the adaptive loop continues while k >= n_t (src/sketch.jl:681-682): such blocks go through the general
+    // single-matrix path from the next round on (fresh library-drawn random inputs keyed by seed, round, block)
+    if (adaptive && hk[(size_t)b] >= order) {
+      ++unfinished;
+      bra_opts ob = *opts;
+      ob.seed = opts->seed + 0x9E3779B97F4A7C15ull * (uint64_t)(b + 1);
+      ctx->start_round = 1;
+      int rc = bra_sketchfact_core(ctx, 'n', m, n, A + b * strideA, lda, &ob, nullptr);
+      ctx->start_round = 0;
+      if (rc) return rc;
+      const int64_t kb = ctx->res.k;
+      BRA_CUDA(cudaMemcpyAsync(k_out + b, &kb, 8, cudaMemcpyHostToDevice, ctx->stream));
+      BRA_CUDA(cudaMemcpyAsync(p_out + b * n, ctx->jpvt.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+      if (kb > ldT) {
+        ++tslot;
+      } else if (kb > 0 && n > kb) {
+        BRA_CUDA(cudaMemcpy2DAsync(T_out + b * strideT, (size_t)ldT * 8, ctx->T.p, (size_t)kb * 8, (size_t)kb * 8,
+                                   (size_t)(n - kb), cudaMemcpyDeviceToDevice, ctx->stream));
+      }
+      BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  ctx->batched_unfinished = unfinished;
+  if (tslot) {
+    ctx->set_error("batched idfact: " + std::to_string(tslot) + " blocks have k > ldT; enlarge the T slots");
+    return BRA_ERR_TSLOT;
+  }
+  return BRA_OK;
+}
+
+int64_t bra_batched_unfinished(bra_ctx* ctx) { return ctx ? ctx->batched_unfinished : -1; }
+
+}  // extern "C"

@@ -95,6 +95,8 @@ struct bra_ctx {
   int rank = 0, world = 1;
   int64_t shard_row0 = 0, shard_m_global = 0;   // this rank's first global row / total rows (0: not sharded)
   uint64_t collectives = 0;
+  int64_t batched_unfinished = 0;   // blocks of the last batched call that needed rounds beyond the fused one
+  int start_round = 0;              // adaptive loop resumes at this round (batched fallback)
   int gemm_tag = BRA_PROF_GEMM; // profiling tag the GEMM launchers record under (tails switch it)
   uint32_t rec_epoch = 1;
   size_t rec_zeroed = 0;

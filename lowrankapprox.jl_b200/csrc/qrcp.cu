@@ -31,6 +31,7 @@
 //  * The rank/rtol termination test stays on the device.
 #include "common.cuh"
 #include <type_traits>
+#include "qrcp_common.cuh"
 
 namespace {
 
@@ -127,18 +128,6 @@ __device__ __forceinline__ bool ll32_load(const LL32* p, uint32_t stamp, double&
   return false;
 }
 
-__device__ __forceinline__ double warp_sum(double x) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-  return x;
-}
-
-// candidate ordering: larger norm wins; ties go to the smaller logical position
-// (idamax returns the FIRST maximum).
-__device__ __forceinline__ bool cand_better(double v, int lp, double bv, int blp) {
-  return (v > bv) || (v == bv && lp < blp);
-}
-
 struct Cand {
   double v;       // downdated norm vn1 (-1: none)
   int lp;         // logical position
@@ -146,22 +135,6 @@ struct Cand {
   int ps;         // physical column at the next logical pivot position (or -1)
   int flag;       // any column flagged during the step
 };
-
-// argmax of (v, lp) over the warp; returns the winning lane
-// Non-negative doubles order like their bit patterns, so the argmax runs on the integer pipe with
-// four warp collectives (redux.sync) instead of 5 x 3 shuffles + FP64 compares.  v < 0 means "none".
-__device__ __forceinline__ int warp_argmax(double v, int lp) {
-  const int hi = (v >= 0.0) ? __double2hiint(v) : (int)0x80000000;
-  const unsigned lo = (v >= 0.0) ? (unsigned)__double2loint(v) : 0u;
-  const int mh = __reduce_max_sync(0xffffffffu, hi);
-  const bool c1 = (hi == mh);
-  const unsigned ml = __reduce_max_sync(0xffffffffu, c1 ? lo : 0u);
-  const bool c2 = c1 && (lo == ml);
-  const int mlp = __reduce_min_sync(0xffffffffu, c2 ? lp : 0x7fffffff);
-  return __ffs(__ballot_sync(0xffffffffu, c2 && lp == mlp)) - 1;
-}
-
-constexpr double TOL3Z = 1.0536712127723509e-08;   // sqrt(2^-53) = sqrt(DLAMCH('Epsilon'))
 
 // NR = row registers per lane (rows s + lane + 32*i); NR == 0: generic two-pass loop.
 template <int NR>
