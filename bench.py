@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--n", type=int, default=8192)
     ap.add_argument("--what", default="auto", choices=["auto", "idfact", "psvdfact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C3/C4/C5 side measurements")
+    ap.add_argument("--c5-blocks", type=int, default=16384)
+    ap.add_argument("--c4-rows", type=int, default=1048576)
     return ap.parse_args()
 
 
@@ -153,6 +156,142 @@ def run_reference(args):
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "factorizations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def hbm_peak():
+    """HBM roofline denominator: the driver's measured copy bandwidth if present, else the guide's fallback."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback; MEASURED_PEAKS.json absent)"
+
+
+def _timed(ext, fn, steps, warmup):
+    """CUDA events on the library's own stream around `steps` calls of fn (after `warmup` untimed calls)."""
+    import torch
+    for w in range(warmup):
+        fn(1000 + w)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(ext)
+    out = None
+    for s_ in range(steps):
+        out = fn(s_)
+    e1.record(ext)
+    e1.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / steps, out
+
+
+def run_c3(ctx, ext, dev, steps=5, n=16384):
+    """BASELINE config 3: idfact, sketch=:srft, 16384^2 FP64, geometric spectrum, rtol=1e-12.  HBM-bound sketch."""
+    import torch
+    from brapprox._binding import DeviceMatrix
+    from brapprox._frontend import idfact_device
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    U, _ = torch.linalg.qr(torch.randn(n, RANK_GEN, dtype=torch.float64, device=dev, generator=g))
+    V, _ = torch.linalg.qr(torch.randn(n, RANK_GEN, dtype=torch.float64, device=dev, generator=g))
+    sig = 10.0 ** (-DECADES * torch.arange(RANK_GEN, dtype=torch.float64, device=dev) / JDIV)
+    At = ((V * sig) @ U.T).contiguous()
+    del U, V
+    A = DeviceMatrix(At.data_ptr(), n, n, n, keep=At)
+    ctx.profile_enable(True)
+    t, inf = _timed(ext, lambda sd: idfact_device(A, rtol=RTOL, sketch="srft", seed=sd, ctx=ctx), steps, 2)
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    rounds = [(int(inf.orders[i]), int(inf.ks[i])) for i in range(inf.rounds)]
+    nrun = steps + 2
+    sk_ms = prof["sketch_other"][0] / nrun
+    bytes_sk = sum(8.0 * n * n + 8.0 * l * n for l, _ in rounds)
+    peak, src = hbm_peak()
+    return {"workload": f"C3: idfact sketch=srft {n}x{n} FP64 rtol=1e-12, A resident", "ms_per_factorization": t * 1e3,
+            "factorizations_per_sec": 1.0 / t, "rounds_order_k": rounds, "k": int(inf.k),
+            "stage_ms": {k2: v[0] / nrun for k2, v in prof.items() if v[0] > 0},
+            "roofline": {"bound": "hbm", "kernel": "srft_kernel (smem radix-4/2 FFT + pruned twiddle stage)",
+                         "achieved": bytes_sk / (sk_ms * 1e-3) / 1e9 if sk_ms > 0 else None, "peak": peak, "unit": "GB/s",
+                         "frac": bytes_sk / (sk_ms * 1e-3) / 1e9 / peak if sk_ms > 0 else None,
+                         "algorithmic_bytes": bytes_sk, "peak_source": src}}
+
+
+def run_c5(ctx, ext, dev, rank, world, nblocks_total=16384, steps=3, m=512):
+    """BASELINE config 5: batched idfact of independent 512x512 Cauchy blocks, sketch=:sprn, rtol=1e-12; blocks are
+    dealt out in contiguous groups, one group per GPU, no collective (strong scaling: total block count fixed)."""
+    import torch
+    import brapprox
+    from brapprox._frontend import idfact_batched_device
+    b0, nb = brapprox.block_shard(nblocks_total, rank, world)
+    n = m
+    At = torch.empty((nb, n, m), dtype=torch.float64, device=dev)      # block b column-major, lda = m
+    g = torch.Generator(device=dev)
+    g.manual_seed(50 + rank)
+    for c0 in range(0, nb, 1024):
+        c1 = min(nb, c0 + 1024)
+        x = torch.sort(torch.rand((c1 - c0, m), dtype=torch.float64, device=dev, generator=g), dim=1).values
+        y = torch.sort(torch.rand((c1 - c0, n), dtype=torch.float64, device=dev, generator=g), dim=1).values + 1.02
+        At[c0:c1] = 1.0 / (x[:, None, :] - y[:, :, None])
+    ldt = 32
+    kd = torch.zeros(nb, dtype=torch.int64, device=dev)
+    pd = torch.zeros((nb, n), dtype=torch.int64, device=dev)
+    Td = torch.zeros((nb, n, ldt), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+
+    def step(sd):
+        return idfact_batched_device(At.data_ptr(), nb, m, n, m, m * n, kd.data_ptr(), pd.data_ptr(), Td.data_ptr(), ldt,
+                                     ldt * n, None, ctx=ctx, rtol=RTOL, sketch="sprn", seed=sd)
+
+    t, unfinished = _timed(ext, step, steps, 1)
+    ks = kd.cpu().numpy()
+    hist = {int(k): int(c) for k, c in zip(*[a.tolist() for a in __import__("numpy").unique(ks, return_counts=True)])}
+    peak, src = hbm_peak()
+    by = 8.0 * m * n * nb
+    return {"workload": f"C5: batched idfact, {nblocks_total} Cauchy 512x512 blocks (this rank: {nb}), sketch=sprn, "
+                        "rtol=1e-12, fast mode, blocks resident", "t": t, "blocks": nb,
+            "blocks_per_sec_this_rank": nb / t, "k_hist": hist, "unfinished_blocks": int(unfinished),
+            "roofline": {"bound": "hbm", "kernel": "idfact_batched_kernel (fused sprn sketch + QRCP + T solve)",
+                         "achieved": by / t / 1e9, "peak": peak, "unit": "GB/s", "frac": by / t / 1e9 / peak,
+                         "algorithmic_bytes": by, "peak_source": src}}
+
+
+def run_c4(ctx, ext, dev, rank, world, m_total=1048576, n=4096, steps=2):
+    """BASELINE config 4: tall pqrfact, rank=256 cap, row blocks per GPU, sketch all-reduced over NCCL once per round
+    (strong scaling: m_total fixed).  Needs ctx's communicator when world > 1."""
+    import torch
+    import brapprox
+    from brapprox._binding import DeviceMatrix
+    from brapprox._frontend import pqrfact_device
+    row0, ml = brapprox.row_shard(m_total, rank, world)
+    r = 512
+    g = torch.Generator(device=dev)
+    g.manual_seed(4)                                       # Y, sigma identical on every rank
+    Y, _ = torch.linalg.qr(torch.randn(n, r, dtype=torch.float64, device=dev, generator=g))
+    sig = 10.0 ** (-6.0 * torch.arange(r, dtype=torch.float64, device=dev) / 256.0)
+    Ys = (Y * sig).T.contiguous()                          # r x n
+    At = torch.empty((n, ml), dtype=torch.float64, device=dev)          # column-major ml x n
+    g2 = torch.Generator(device=dev)
+    g2.manual_seed(1000 + rank)
+    for c0 in range(0, ml, 65536):
+        c1 = min(ml, c0 + 65536)
+        X = torch.randn((c1 - c0, r), dtype=torch.float64, device=dev, generator=g2) / (m_total ** 0.5)
+        At[:, c0:c1] = (X @ Ys).T
+    del Y, Ys
+    A = DeviceMatrix(At.data_ptr(), ml, n, ml, keep=At)
+    ctx.set_row_shard(row0, m_total)
+    ctx.profile_enable(True)
+    t, inf = _timed(ext, lambda sd: pqrfact_device(A, rtol=RTOL, rank=256, seed=sd, ctx=ctx), steps, 1)
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    ctx.set_row_shard(0, 0)
+    rounds = [(int(inf.orders[i]), int(inf.ks[i])) for i in range(inf.rounds)]
+    f_sk = 2.0 * m_total * n * sum(l for l, _ in rounds)
+    k = int(inf.k)
+    f_tail = 4.0 * m_total * k * k * 2 + float(k) * k * (n - k)
+    nrun = steps + 1
+    return {"workload": f"C4: pqrfact {m_total}x{n} FP64 rank=256 cap, sketch=randn adaptive, rows sharded over "
+                        f"{world} GPU(s) ({ml} rows here), one sketch all-reduce per round", "t": t,
+            "rounds_order_k": rounds, "k": k, "algorithmic_gflop_total": (f_sk + f_tail) / 1e9,
+            "stage_ms": {k2: v[0] / nrun for k2, v in prof.items() if v[0] > 0},
+            "collectives_per_factorization": None}
 
 
 def main():
@@ -265,6 +404,22 @@ def main():
     gemm_ms, gemm_calls = prof["gemm"]
     gemm_tf = f_sk * args.steps / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
 
+    # ---- the other half of the headline metric ("idfact/psvdfact factorizations/sec"): idfact on the same A ----
+    idf = None
+    if what == "psvdfact":
+        ctx.profile_enable(True)
+        ti, infi = _timed(ext, lambda sd: idfact_device(A, rtol=RTOL, seed=sd, ctx=ctx), max(5, args.steps // 2), 2)
+        profi = ctx.profile_read()
+        ctx.profile_enable(False)
+        ri = [(int(infi.orders[t]), int(infi.ks[t])) for t in range(infi.rounds)]
+        si = [int(infi.steps[t]) for t in range(infi.rounds)]
+        fi = sum(algorithmic_flops(n, n, ri, si, int(infi.k)))
+        nrun = max(5, args.steps // 2) + 2
+        idf = {"value": 1.0 / ti, "unit": "factorizations/s", "ms_per_step": ti * 1e3, "k": int(infi.k),
+               "algorithmic_gflop": fi / 1e9, "achieved_tflops": fi / ti / 1e12,
+               "frac_of_fp64_peak": fi / ti / 1e12 / fp64_peak,
+               "stage_ms_per_step": {k2: v[0] / nrun for k2, v in profi.items() if v[0] > 0}}
+
     # ---- e2e: host-resident A through the C ABI, result fetched to the host, every step ----
     e2e = None
     if rank == 0 or world > 1:
@@ -294,6 +449,58 @@ def main():
             te = float(t.item())
         e2e = {"value": world * e2e_steps / te, "unit": "factorizations/s", "h2d_bytes_per_step": int(n * n * 8),
                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps}
+
+    # ---- side measurements of the other BASELINE configs (same run, same box): C3 single GPU; C4 (row-sharded,
+    # NCCL all-reduce) and C5 (batched, no collective) over all ranks, strong scaling, max over ranks ----
+    extra = {}
+    if not args.no_extra:
+        del A, At
+        torch.cuda.empty_cache()
+        fp64_tf = None
+
+        def over_ranks(val, op):
+            if world == 1:
+                return val
+            tt = torch.tensor([val], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=op)
+            return float(tt.item())
+
+        try:
+            if rank == 0:
+                extra["C3"] = run_c3(ctx, ext, dev)
+            torch.cuda.empty_cache()
+        except Exception as e:      # a side measurement must never take the headline down
+            extra["C3"] = {"error": repr(e)[:300]}
+        try:
+            barrier()
+            c5 = run_c5(ctx, ext, dev, rank, world, args.c5_blocks)
+            t5 = over_ranks(c5.pop("t"), dist.ReduceOp.MAX if world > 1 else None)
+            c5["blocks_per_sec_all_ranks"] = args.c5_blocks / t5
+            c5["ms_per_batch"] = t5 * 1e3
+            c5["n_gpus"] = world
+            c5["scaling"] = "strong"
+            extra["C5"] = c5
+            torch.cuda.empty_cache()
+        except Exception as e:
+            extra["C5"] = {"error": repr(e)[:300]}
+        try:
+            barrier()
+            if world > 1:
+                brapprox.init_comm(ctx, rank, world, device=dev)
+            c0 = ctx.collective_count()
+            c4 = run_c4(ctx, ext, dev, rank, world, args.c4_rows)
+            t4 = over_ranks(c4.pop("t"), dist.ReduceOp.MAX if world > 1 else None)
+            c4["collectives_per_factorization"] = (ctx.collective_count() - c0) / 3.0
+            c4["ms_per_factorization"] = t4 * 1e3
+            c4["factorizations_per_sec"] = 1.0 / t4
+            c4["achieved_tflops_all_ranks"] = c4["algorithmic_gflop_total"] / 1e3 / t4
+            c4["frac_of_fp64_peak_per_gpu"] = c4["achieved_tflops_all_ranks"] / world / fp64_peak
+            c4["n_gpus"] = world
+            c4["scaling"] = "strong"
+            extra["C4"] = c4
+            torch.cuda.empty_cache()
+        except Exception as e:
+            extra["C4"] = {"error": repr(e)[:300]}
 
     if rank != 0:
         if world > 1:
@@ -327,6 +534,8 @@ def main():
         "stage_ms_per_step": {k2: v[0] / args.steps for k2, v in prof.items()},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "fp64_peak_probes_tflops": peaks,
+        "idfact_same_matrix": idf,
+        "other_configs": extra,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -39,6 +39,7 @@ struct BatchParams {
   double* Tout;            // block b: k_b x (n - k_b) at Tout + b*strideT, leading dimension ldT
   int64_t ldT, strideT;
   int32_t* status;         // [block id]: 0 ok, 1 T slot too small (k_b > ldT)
+  long long* dbg;          // [CTA][4] cycles: tables+sketch, registers+norms, QRCP, outputs+T (diagnostic)
 };
 
 __global__ void __launch_bounds__(BT, 1) idfact_batched_kernel(BatchParams P) {
@@ -49,51 +50,84 @@ __global__ void __launch_bounds__(BT, 1) idfact_batched_kernel(BatchParams P) {
   constexpr int BSTR = BT + 1;                                   // padded row stride of the staged sketch
   double* Bs = reinterpret_cast<double*>(smem_raw);             // [BL][BSTR]
   double* colbuf = Bs + (size_t)BL * BSTR;                      // [BW][mpad]  (later: R11, [BL][BL+1])
-  double* sv = colbuf + (size_t)BW * mpad;                      // [mpad]
-  double* vv = sv + mpad;                                       // [BL] Householder vector
+  const int tpad = (((m / l) + 1) * l + 1) & ~1;                 // table entries, [t][i] layout
+  double* sv = colbuf + (size_t)BW * mpad;                      // [tpad]
+  double* vv = sv + tpad;                                       // [BL] Householder vector
   double* rdblk = vv + BL;                                      // [BL] diagonal of R within the current block
   double* cv = rdblk + BL;                                      // [BW] warp candidates: norm
   double* hh = cv + BW;                                         // tau, beta
   int* clp = reinterpret_cast<int*>(hh + 2);                    // [BW] logical position
   int* ctd = clp + BW;                                          // [BW] owning thread
-  int* permv = ctd + BW;                                        // [mpad] 0-based
+  int* permv = ctd + BW;                                        // [tpad] 0-based
   double* mycol = colbuf + (size_t)warp * mpad;
 
   const int lmin = min(l, n);
   const int64_t q = m / l, rem = m % l;                          // p_i = q + (i < rem), off_i = i*q + min(i, rem)
   bool tables_loaded = false;
+  long long tph[4] = {0, 0, 0, 0}, tlast = clock64();
+#define BTICK(i) { long long _t = clock64(); tph[i] += _t - tlast; tlast = _t; }
 
   for (int it = blockIdx.x; it < P.nblocks; it += gridDim.x) {
     const int b = P.blocks ? P.blocks[it] : it;
     const double* Ab = P.A + (int64_t)b * P.strideA;
     __syncthreads();
     if (!tables_loaded || P.perm_stride != 0 || P.s_stride != 0) {
+      // tables in [t][i] order (term t of sketch row i at t*l + i): lanes = sketch rows read consecutive words
       const int64_t* pb = P.perm + (int64_t)b * P.perm_stride;
       const double* sb = P.s + (int64_t)b * P.s_stride;
       for (int r = tid; r < m; r += BT) {
-        permv[r] = (int)(pb[r] - 1);
-        sv[r] = sb[r];
+        // r = off_i + t  ->  (i, t)
+        int i, t;
+        if (r < rem * (q + 1)) {
+          i = (int)(r / (q + 1));
+          t = (int)(r - (int64_t)i * (q + 1));
+        } else {
+          const int64_t r2 = r - rem * (q + 1);
+          i = (int)(rem + r2 / q);
+          t = (int)(r2 % q);
+        }
+        permv[t * l + i] = (int)(pb[r] - 1);
+        sv[t * l + i] = sb[r];
       }
       tables_loaded = true;
       __syncthreads();
     }
 
-    // ---- sparse-Gaussian sketch: warp w stages column j (coalesced), lane i forms B[i, j] ----
-    for (int j = warp; j < n; j += BW) {
-      const double* a = Ab + (int64_t)j * P.lda;
-#pragma unroll 8
-      for (int r = lane; r < m; r += 32) mycol[r] = a[r];
-      __syncwarp();
-      if (lane < l) {
-        const int64_t pi = q + (lane < rem ? 1 : 0);
-        const int64_t off = (int64_t)lane * q + (lane < rem ? lane : rem);
-        double acc = 0.0;
-        for (int64_t t = 0; t < pi; ++t) acc += sv[off + t] * mycol[permv[off + t]];
-        Bs[lane * BSTR + j] = acc;
+    // ---- sparse-Gaussian sketch: warp w stages column j (coalesced, next column prefetched into registers),
+    // lane i forms B[i, j] in the reference's summation order ----
+    {
+      constexpr int PF = 16;                       // prefetch registers: covers m <= 512 (longer columns: tail loop)
+      double pf[PF];
+      int j = warp;
+      if (j < n) {
+        const double* a = Ab + (int64_t)j * P.lda;
+#pragma unroll
+        for (int u = 0; u < PF; ++u) pf[u] = (lane + 32 * u < m) ? a[lane + 32 * u] : 0.0;
       }
-      __syncwarp();
+      for (; j < n; j += BW) {
+        const double* a = Ab + (int64_t)j * P.lda;
+#pragma unroll
+        for (int u = 0; u < PF; ++u)
+          if (lane + 32 * u < m) mycol[lane + 32 * u] = pf[u];
+        for (int r = lane + 32 * PF; r < m; r += 32) mycol[r] = a[r];
+        if (j + BW < n) {
+          const double* an = Ab + (int64_t)(j + BW) * P.lda;
+#pragma unroll
+          for (int u = 0; u < PF; ++u) pf[u] = (lane + 32 * u < m) ? an[lane + 32 * u] : 0.0;
+        }
+        __syncwarp();
+        if (lane < l) {
+          const int pi = (int)q + (lane < rem ? 1 : 0);
+          double acc = 0.0;
+#pragma unroll 4
+          for (int t = 0; t < pi; ++t) acc += sv[t * l + lane] * mycol[permv[t * l + lane]];
+          Bs[lane * BSTR + j] = acc;
+        }
+        __syncwarp();
+      }
     }
     __syncthreads();
+    BTICK(0)
 
     // ---- one column per thread, in registers ----
     const bool live = tid < n;
@@ -122,6 +156,7 @@ __global__ void __launch_bounds__(BT, 1) idfact_batched_kernel(BatchParams P) {
     }
     int lpos = live ? tid : 0x7fffffff;
 
+    BTICK(1)
     int s = 0, jblk = 0, cnt = 0, jb = min(P.nb, P.kcap), kres = (P.kcap == 0) ? 0 : -1;
     double ptol = 0.0;
     int pend_flag = 0;          // a column was flagged in the previous step
@@ -259,6 +294,7 @@ __global__ void __launch_bounds__(BT, 1) idfact_batched_kernel(BatchParams P) {
       }
     }
     const int k = kres;
+    BTICK(2)
 
     // ---- outputs: p, k, T = R11^{-1} R12 ----
     if (live) P.pout[(int64_t)b * n + lpos] = (int64_t)tid + 1;
@@ -291,7 +327,11 @@ __global__ void __launch_bounds__(BT, 1) idfact_batched_kernel(BatchParams P) {
       for (int i = 0; i < BL; ++i)
         if (i < k) t[i] = a[i];
     }
+    BTICK(3)
   }
+  if (tid == 0 && P.dbg)
+    for (int i = 0; i < 4; ++i) P.dbg[blockIdx.x * 4 + i] = tph[i];
+#undef BTICK
 }
 
 }  // namespace
@@ -330,7 +370,9 @@ int bra_idfact_batched_f64(bra_ctx* ctx, int64_t nblocks, int64_t m, int64_t n, 
   const bool adaptive = opts->sketchfact_adap || opts->rank < 0;
   const int64_t order = adaptive ? opts->nb : opts->rank;
   const int64_t mpad = (m + 1) & ~int64_t(1);
-  const size_t smem = ((size_t)BL * (BT + 1) + (size_t)BW * mpad + mpad + 2 * BL + BW + 2) * 8 + (2 * BW + mpad) * 4 + 64;
+  const int64_t ordc = order > 0 ? order : 1;
+  const int64_t tpad = (((m / ordc) + 1) * ordc + 1) & ~int64_t(1);
+  const size_t smem = ((size_t)BL * (BT + 1) + (size_t)BW * mpad + tpad + 2 * BL + BW + 2) * 8 + (2 * BW + tpad) * 4 + 64;
   if (order < 1 || order > BL || n > BT || order > m || smem > (size_t)ctx->smem_optin ||
       (size_t)BW * mpad < (size_t)BL * (BL + 1)) {
     ctx->set_error("batched idfact: shape outside the fused kernel (needs order = nb <= 32, n <= 512, "
@@ -378,6 +420,8 @@ int bra_idfact_batched_f64(bra_ctx* ctx, int64_t nblocks, int64_t m, int64_t n, 
   P.strideT = strideT;
   BRA_CUDA(ctx->scratch.reserve((size_t)nblocks * 4));
   P.status = ctx->scratch.as<int32_t>();
+  BRA_CUDA(ctx->scratch3.reserve((size_t)ctx->num_sms * 4 * 8));
+  P.dbg = ctx->scratch3.as<long long>();
   BRA_CUDA(cudaFuncSetAttribute(idfact_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<int64_t>(nblocks, ctx->num_sms);
   {
@@ -426,5 +470,13 @@ int bra_idfact_batched_f64(bra_ctx* ctx, int64_t nblocks, int64_t m, int64_t n, 
 }
 
 int64_t bra_batched_unfinished(bra_ctx* ctx) { return ctx ? ctx->batched_unfinished : -1; }
+
+int bra_debug_batched_phases(bra_ctx* ctx, int64_t* out4) {
+  if (!ctx || !out4) return -1;
+  long long h[4];
+  BRA_CUDA(cudaMemcpy(h, ctx->scratch3.p, 32, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 4; ++i) out4[i] = h[i];
+  return BRA_OK;
+}
 
 }  // extern "C"

@@ -11,7 +11,8 @@
 //    sampled frequencies are evaluated from the digit-reversed bins with the even/odd separation
 //    X^[c,2q] = (Z_q[c] + conj Z_q[l-c])/2, X^[c,2q+1] = -i (Z_q[c] - conj Z_q[l-c])/2.  Chunks (needed when a
 //    column does not fit in shared memory, and to get several CTAs per SM) produce partial sums that are added
-//    in a fixed order.  Twiddles come from sincospi (the reference multiplies them up, drifting by O(m' eps)).
+//    in a fixed order.  Twiddles come from sincospi-built tables (the reference multiplies them up, drifting by
+//    O(m' eps)); the passes are radix 8 (then 4 or 2), so a length-512 transform touches shared memory 3 times.
 //    Shapes the radix passes do not cover (l not a power of two, odd m') go through an explicitly generated
 //    SRFT matrix and the TMA + DMMA GEMM.
 //  * sparse Gaussian: every entry of A is read exactly once; a column is staged in shared memory (coalesced)
@@ -19,7 +20,10 @@
 //  * random subset: a gather.
 #include "common.cuh"
 #include <algorithm>
+#include <cstdlib>
 
+bool bra_make_map_3d_f64(CUtensorMap* map, const double* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1,
+                         uint64_t s2, uint32_t b0, uint32_t b1);
 int bra_splitk_reduce(bra_ctx* ctx, const double* part, int64_t split_stride, int splits, int64_t l, int64_t n,
                       double* out, int64_t ldo);
 
@@ -80,7 +84,11 @@ struct SrftParams {
   int l, logl;            // FFT length (power of two)
   int mp;                 // m / l
   int mc;                 // inner indices per chunk (even), mp % mc == 0
+  int tsplit, nhi;        // twiddle tables: exp(-2 pi i t/m) = Hi[t / tsplit] * Lo[t % tsplit], nhi = ceil(m / tsplit)
   const double* d;        // +-1, length m
+  const uint32_t* dbits;  // bit i set <=> d[i] < 0 (m bits, padded to a word)
+  int use_tma;            // stage the l x mc chunk with tiled TMA loads (3-D map over (kk, j, column))
+  int boxrows;            // rows per TMA box (<= 256)
   const int64_t* idx1;    // 1-based sampled frequencies, length order
   double* out;            // order x n (ld = ldo) [+ chunk * split_stride]
   int64_t ldo, split_stride;
@@ -90,21 +98,58 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
   return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
 }
 
-// position of frequency bin c after the in-place DIF passes (radix 4 while >= 2 stages remain, then radix 2)
+// position of frequency bin c after the in-place DIF passes (radix 8 while >= 3 stages remain, then 4 or 2)
 __device__ __forceinline__ int srft_binpos(int c, int l, int logl) {
   int pos = 0, N = l, rem = logl;
-  while (rem >= 2) {
-    pos += (c & 3) * (N >> 2);
-    c >>= 2;
-    N >>= 2;
-    rem -= 2;
+  while (rem >= 3) {
+    pos += (c & 7) * (N >> 3);
+    c >>= 3;
+    N >>= 3;
+    rem -= 3;
   }
-  if (rem == 1) pos += (c & 1) * (N >> 1);
+  if (rem == 2) pos += (c & 3) * (N >> 2);
+  else if (rem == 1) pos += (c & 1) * (N >> 1);
   return pos;
 }
 
-__global__ void __launch_bounds__(256) srft_kernel(SrftParams P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cmuli_neg(double2 a) { return make_double2(a.y, -a.x); }     // -i * a
+
+// 4-point forward DFT: y_k = sum_t u_t (-i)^{kt}
+__device__ __forceinline__ void dft4(double2 u0, double2 u1, double2 u2, double2 u3, double2& y0, double2& y1,
+                                     double2& y2, double2& y3) {
+  const double2 s02 = cadd(u0, u2), d02 = csub(u0, u2), s13 = cadd(u1, u3), d13 = cmuli_neg(csub(u1, u3));
+  y0 = cadd(s02, s13);
+  y2 = csub(s02, s13);
+  y1 = cadd(d02, d13);
+  y3 = csub(d02, d13);
+}
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(dst)),
+               "l"(src), "r"(bytes), "r"(s_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ double flip(double x, uint32_t neg) {      // neg in {0, 1}
+  return __hiloint2double(__double2hiint(x) ^ (int)(neg << 31), __double2loint(x));
+}
+
+__global__ void srft_signbits_kernel(const double* __restrict__ d, int64_t m, uint32_t* __restrict__ bits) {
+  const int64_t words = (m + 31) / 32;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t v = 0;
+    for (int b = 0; b < 32; ++b) {
+      const int64_t i = w * 32 + b;
+      if (i < m && d[i] < 0.0) v |= 1u << b;
+    }
+    bits[w] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256, 3) srft_kernel(const __grid_constant__ CUtensorMap mapA, SrftParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int l = P.l, mc = P.mc, Qc = mc >> 1;
   double* Xs = reinterpret_cast<double*>(smem_raw);                       // l * mc doubles = l * Qc complex
   double2* Z = reinterpret_cast<double2*>(smem_raw);
@@ -120,77 +165,198 @@ __global__ void __launch_bounds__(256) srft_kernel(SrftParams P) {
     sincospi(-2.0 * (double)t / (double)l, &sn, &cs);
     W[t] = make_double2(cs, sn);
   }
+  // twiddles of the sampled-frequency stage, exp(-2 pi i t / m), from two small tables (one complex multiply
+  // per twiddle instead of a sincospi): Lo[t] = exp(-2 pi i t/m), t < tsplit; Hi[u] = exp(-2 pi i u tsplit/m)
+  double2* Lo = W + l;
+  double2* Hi = Lo + P.tsplit;
+  for (int t = tid; t < P.tsplit + P.nhi; t += nthr) {
+    const int64_t tt = (t < P.tsplit) ? t : (int64_t)(t - P.tsplit) * P.tsplit;
+    double sn, cs;
+    sincospi(-2.0 * (double)(tt % P.m) / (double)P.m, &sn, &cs);
+    W[l + t] = make_double2(cs, sn);
+  }
+  const int tshift = 31 - __clz(P.tsplit);          // tsplit is a power of two
+  auto twiddle = [&](int64_t t) -> double2 {        // t in [0, m)
+    return cmul(Hi[(int)(t >> tshift)], Lo[(int)(t & (P.tsplit - 1))]);
+  };
+  // per-sample constants (the same for every column): frequency, bin positions of c and l - c
+  int* sf = reinterpret_cast<int*>(Hi + P.nhi);      // [nsamp] f
+  int* spc = sf + nsamp;                             // [nsamp] position of bin c
+  int* spn = spc + nsamp;                            // [nsamp] position of bin (l - c) mod l
+  for (int sp = tid; sp < nsamp; sp += nthr) {
+    const int64_t f = P.idx1[2 * sp] - 1;
+    const int c = (int)(f % l);
+    sf[sp] = (int)f;
+    spc[sp] = srft_binpos(c, l, P.logl);
+    spn[sp] = srft_binpos((l - c) & (l - 1), l, P.logl);
+  }
+  // sign bits of this chunk's rows and the mbarrier of the bulk loads
+  uint32_t* sbits = reinterpret_cast<uint32_t*>(spn + nsamp);           // [(m + 31) / 32]
+  const int nwords = (int)((P.m + 31) / 32);
+  uint64_t* bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sbits + nwords) + 7) & ~uintptr_t(7));
+  for (int w = tid; w < nwords; w += nthr) sbits[w] = P.dbits[w];
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t phase = 0;
+  const bool mpow2 = (P.m & (P.m - 1)) == 0;
+  // lanes of a warp are split into groups of GS lanes; a group evaluates one sampled frequency
+  int GS = 1;
+  while (GS < 32 && GS < Qc) GS <<= 1;
+  const int gpw = 32 / GS, sub = lane / GS, ql = lane % GS;
+  // division-free work distribution over (j or butterfly index, q): item w = tid + k*nthr <-> (w / Qc, w % Qc)
+  const int q0 = tid % Qc, b0 = tid / Qc, dq = nthr % Qc, db = nthr / Qc;
+  const int t0 = tid % mc, j0 = tid / mc, dt = nthr % mc, dj = nthr / mc;
 
   for (int64_t col = blockIdx.x; col < P.n; col += gridDim.x) {
     const double* x = P.A + col * P.lda;
     __syncthreads();
-    // ---- srft_reshape!: X[j, kk] = d[i] x[i], i = j*mp + kk, restricted to this chunk of kk ----
-    for (int e = tid; e < l * mc; e += nthr) {
-      const int j = e / mc, t = e - j * mc;
-      const int64_t i = (int64_t)j * P.mp + kk0 + t;
-      Xs[e] = P.d[i] * x[i];
-    }
-    __syncthreads();
-    // ---- length-l DFT along j of the Qc complex columns, in place, decimation in frequency ----
-    int N = l, rem = P.logl;
-    while (rem >= 2) {
-      const int h = N >> 2, tw = l / N;
-      const int items = (l >> 2) * Qc;
-      for (int w = tid; w < items; w += nthr) {
-        const int q = w % Qc, bf = w / Qc;
-        const int b = bf / h, j = bf - b * h;
-        double2* z = Z + ((size_t)(b * N + j)) * Qc + q;
-        const size_t hs = (size_t)h * Qc;
-        const double2 x0 = z[0], x1 = z[hs], x2 = z[2 * hs], x3 = z[3 * hs];
-        const double2 s02 = make_double2(x0.x + x2.x, x0.y + x2.y), d02 = make_double2(x0.x - x2.x, x0.y - x2.y);
-        const double2 s13 = make_double2(x1.x + x3.x, x1.y + x3.y), d13 = make_double2(x1.x - x3.x, x1.y - x3.y);
-        // -i * d13 = (d13.y, -d13.x)
-        const double2 y0 = make_double2(s02.x + s13.x, s02.y + s13.y);
-        const double2 y2 = make_double2(s02.x - s13.x, s02.y - s13.y);
-        const double2 y1 = make_double2(d02.x + d13.y, d02.y - d13.x);
-        const double2 y3 = make_double2(d02.x - d13.y, d02.y + d13.x);
-        z[0] = y0;
-        z[hs] = cmul(y1, W[(j * tw) & (l - 1)]);
-        z[2 * hs] = cmul(y2, W[(2 * j * tw) & (l - 1)]);
-        z[3 * hs] = cmul(y3, W[(3 * j * tw) & (l - 1)]);
+    // ---- srft_reshape!: X[j, kk] = d[i] x[i], i = j*mp + kk, restricted to this chunk of kk.  TMA path: the
+    // l x mc tile arrives by tiled TMA loads (<= 256 rows per box), the sign flip is folded into the first pass ----
+    if (P.use_tma) {
+      if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)),
+                     "r"((uint32_t)(l * mc * 8))
+                     : "memory");
+        for (int jr = 0; jr < l; jr += P.boxrows)
+          asm volatile(
+              "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
+                  "r"(s_u32(Xs + (size_t)jr * mc)),
+              "l"(&mapA), "r"(kk0), "r"(jr), "r"((int)col), "r"(s_u32(bar))
+              : "memory");
+      }
+      uint32_t ok;
+      do {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(s_u32(bar)), "r"(phase)
+            : "memory");
+      } while (!ok);
+      phase ^= 1;
+    } else {
+      int j = j0, t = t0;
+      for (int e = tid; e < l * mc; e += nthr) {
+        const int64_t i = (int64_t)j * P.mp + kk0 + t;
+        Xs[e] = P.d[i] * x[i];
+        t += dt;
+        j += dj;
+        if (t >= mc) {
+          t -= mc;
+          ++j;
+        }
       }
       __syncthreads();
-      N >>= 2;
-      rem -= 2;
     }
-    if (rem == 1) {
+    bool first = P.use_tma != 0;        // the first pass still has to apply d
+    auto ldz = [&](const double2* z, int row, int q) -> double2 {
+      double2 v = *z;
+      if (first) {
+        const int64_t i = (int64_t)row * P.mp + kk0 + 2 * q;          // even: both signs sit in one word
+        const uint32_t wbits = sbits[i >> 5] >> (i & 31);
+        v.x = flip(v.x, wbits & 1u);
+        v.y = flip(v.y, (wbits >> 1) & 1u);
+      }
+      return v;
+    };
+    // ---- length-l DFT along j of the Qc complex columns, in place, decimation in frequency ----
+    int N = l, rem = P.logl;
+    while (rem >= 3) {
+      // radix 8: y_s = (sum_t x_t W_8^{st}) W_N^{sj}, stored at b*N + s*(N/8) + j
+      const int h = N >> 3, tw = l / N, hmask = h - 1, hshift = 31 - __clz(h);
+      const int items = (l >> 3) * Qc;
+      int q = q0, bf = b0;
+      for (int w = tid; w < items; w += nthr) {
+        const int b = bf >> hshift, j = bf & hmask;
+        double2* z = Z + ((size_t)(b * N + j)) * Qc + q;
+        const size_t hs = (size_t)h * Qc;
+        double2 v[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = ldz(z + t * hs, b * N + j + t * h, q);
+        // first radix-2 stage: a_t = x_t + x_{t+4}, b_t = (x_t - x_{t+4}) W_8^t
+        const double r = 0.70710678118654752440;
+        const double2 a0 = cadd(v[0], v[4]), a1 = cadd(v[1], v[5]), a2 = cadd(v[2], v[6]), a3 = cadd(v[3], v[7]);
+        const double2 e0 = csub(v[0], v[4]), e1 = csub(v[1], v[5]), e2 = csub(v[2], v[6]), e3 = csub(v[3], v[7]);
+        const double2 c0 = e0;
+        const double2 c1 = make_double2(r * (e1.x + e1.y), r * (e1.y - e1.x));       // * (1 - i)/sqrt2
+        const double2 c2 = cmuli_neg(e2);                                            // * (-i)
+        const double2 c3 = make_double2(r * (e3.y - e3.x), -r * (e3.x + e3.y));      // * (-1 - i)/sqrt2
+        double2 y[8];
+        dft4(a0, a1, a2, a3, y[0], y[2], y[4], y[6]);
+        dft4(c0, c1, c2, c3, y[1], y[3], y[5], y[7]);
+        z[0] = y[0];
+        const int jt = j * tw;
+#pragma unroll
+        for (int sI = 1; sI < 8; ++sI) z[sI * hs] = cmul(y[sI], W[(sI * jt) & (l - 1)]);
+        q += dq;
+        bf += db;
+        if (q >= Qc) {
+          q -= Qc;
+          ++bf;
+        }
+      }
+      __syncthreads();
+      first = false;
+      N >>= 3;
+      rem -= 3;
+    }
+    if (rem == 2) {
+      const int h = N >> 2, tw = l / N, hmask = h - 1, hshift = 31 - __clz(h);
+      const int items = (l >> 2) * Qc;
+      int q = q0, bf = b0;
+      for (int w = tid; w < items; w += nthr) {
+        const int b = bf >> hshift, j = bf & hmask;
+        double2* z = Z + ((size_t)(b * N + j)) * Qc + q;
+        const size_t hs = (size_t)h * Qc;
+        double2 y0, y1, y2, y3;
+        dft4(ldz(z, b * N + j, q), ldz(z + hs, b * N + j + h, q), ldz(z + 2 * hs, b * N + j + 2 * h, q),
+             ldz(z + 3 * hs, b * N + j + 3 * h, q), y0, y1, y2, y3);
+        const int jt = j * tw;
+        z[0] = y0;
+        z[hs] = cmul(y1, W[jt & (l - 1)]);
+        z[2 * hs] = cmul(y2, W[(2 * jt) & (l - 1)]);
+        z[3 * hs] = cmul(y3, W[(3 * jt) & (l - 1)]);
+        q += dq;
+        bf += db;
+        if (q >= Qc) {
+          q -= Qc;
+          ++bf;
+        }
+      }
+      __syncthreads();
+    } else if (rem == 1) {
       // N == 2: last radix-2 stage, twiddle W_2^0 = 1
       const int items = (l >> 1) * Qc;
+      int q = q0, b = b0;
       for (int w = tid; w < items; w += nthr) {
-        const int q = w % Qc, b = w / Qc;
         double2* z = Z + ((size_t)(b * 2)) * Qc + q;
-        const double2 x0 = z[0], x1 = z[Qc];
-        z[0] = make_double2(x0.x + x1.x, x0.y + x1.y);
-        z[Qc] = make_double2(x0.x - x1.x, x0.y - x1.y);
+        const double2 x0 = ldz(z, b * 2, q), x1 = ldz(z + Qc, b * 2 + 1, q);
+        z[0] = cadd(x0, x1);
+        z[Qc] = csub(x0, x1);
+        q += dq;
+        b += db;
+        if (q >= Qc) {
+          q -= Qc;
+          ++b;
+        }
       }
       __syncthreads();
     }
     // ---- sampled frequencies (srft_apply!, src/sketch.jl:396-450): rows (i, i+1) <- (Re z, Im z) ----
     double* o = P.out + (int64_t)chunk * P.split_stride + col * P.ldo;
-    for (int sp = warp; sp < nsamp; sp += nwarp) {
+    for (int sp0 = warp * gpw; sp0 < nsamp; sp0 += nwarp * gpw) {
+      const int sp = sp0 + sub;
+      const bool on = sp < nsamp;
       const int i = 2 * sp;
-      const int64_t f = P.idx1[i] - 1;
-      const int c = (int)(f % l);
-      const int pc = srft_binpos(c, l, P.logl), pn = srft_binpos((l - c) & (l - 1), l, P.logl);
       double zr = 0.0, zi = 0.0;
-      if (lane < Qc) {
-        // w^kk = exp(-2 pi i kk f / m); per-lane start at kk = kk0 + 2 lane, stride 64 in kk
-        double sn, cs;
-        int64_t t0 = ((int64_t)(kk0 + 2 * lane) * f) % P.m;
-        sincospi(-2.0 * (double)t0 / (double)P.m, &sn, &cs);
-        double2 w = make_double2(cs, sn);
-        int64_t t1 = f % P.m;
-        sincospi(-2.0 * (double)t1 / (double)P.m, &sn, &cs);
-        const double2 w1 = make_double2(cs, sn);                 // w^1
-        int64_t t64 = (64 * f) % P.m;
-        sincospi(-2.0 * (double)t64 / (double)P.m, &sn, &cs);
-        const double2 w64 = make_double2(cs, sn);                // w^64
-        for (int q = lane; q < Qc; q += 32) {
+      if (on) {
+        const int64_t f = sf[sp];
+        const int pc = spc[sp], pn = spn[sp];
+        const double2 w1 = twiddle(f);                           // w = exp(-2 pi i f / m)
+        for (int q = ql; q < Qc; q += GS) {
+          const int64_t tq = (int64_t)(kk0 + 2 * q) * f;
+          const double2 w = twiddle(mpow2 ? (tq & (P.m - 1)) : (tq % P.m));      // w^kk, kk = kk0 + 2q
           const double2 E = Z[(size_t)pc * Qc + q];
           const double2 On = Z[(size_t)pn * Qc + q];             // O = conj(On)
           // even inner column: (E + O)/2 ; odd: -i (E - O)/2
@@ -201,15 +367,13 @@ __global__ void __launch_bounds__(256) srft_kernel(SrftParams P) {
                                                     xe.y + fma(w1.x, xo.y, w1.y * xo.x)));
           zr += term.x;
           zi += term.y;
-          w = cmul(w, w64);
         }
       }
-#pragma unroll
-      for (int s = 16; s > 0; s >>= 1) {
-        zr += __shfl_xor_sync(0xffffffffu, zr, s);
-        zi += __shfl_xor_sync(0xffffffffu, zi, s);
+      for (int sh = GS >> 1; sh > 0; sh >>= 1) {
+        zr += __shfl_xor_sync(0xffffffffu, zr, sh);
+        zi += __shfl_xor_sync(0xffffffffu, zi, sh);
       }
-      if (lane == 0) {
+      if (on && ql == 0) {
         o[i] = zr;
         if (i + 1 < P.order) o[i + 1] = zi;       // the last row alone gets Re only (src/sketch.jl:425, i == k)
       }
@@ -295,7 +459,8 @@ int bra_sketch_srft(bra_ctx* ctx, const double* A, int64_t lda, int64_t mA, int6
     int logl = 0;
     while ((int64_t(1) << logl) < l) ++logl;
     // chunk of the inner index: even divisor of mp with l*mc*8 <= ~64 KB (several CTAs per SM), at least 2
-    const size_t target = 64 * 1024;
+    const size_t target = (getenv("BRA_SRFT_KB") ? atoi(getenv("BRA_SRFT_KB")) : 64) * 1024;
+    const int nthreads = getenv("BRA_SRFT_THREADS") ? atoi(getenv("BRA_SRFT_THREADS")) : 256;
     int64_t mc = mp;
     while (mc > 2 && (size_t)l * mc * 8 > target) {
       // next smaller even divisor
@@ -304,7 +469,11 @@ int bra_sketch_srft(bra_ctx* ctx, const double* A, int64_t lda, int64_t mA, int6
       if (c < 2) break;
       mc = c;
     }
-    const size_t smem = (size_t)l * mc * 8 + (size_t)l * 16;
+    int64_t tsplit = 1;
+    while (tsplit * tsplit < mA) tsplit <<= 1;
+    const int64_t nhi = (mA + tsplit - 1) / tsplit;
+    const size_t smem = (size_t)l * mc * 8 + (size_t)(l + tsplit + nhi) * 16 + (size_t)3 * ((order + 1) / 2) * 4 +
+                        (size_t)((mA + 31) / 32) * 4 + 32;
     if (smem <= (size_t)ctx->smem_optin - 1024) {
       const int chunks = (int)(mp / mc);
       SrftParams P;
@@ -317,8 +486,26 @@ int bra_sketch_srft(bra_ctx* ctx, const double* A, int64_t lda, int64_t mA, int6
       P.logl = logl;
       P.mp = (int)mp;
       P.mc = (int)mc;
+      P.tsplit = (int)tsplit;
+      P.nhi = (int)nhi;
       P.d = d_dev;
       P.idx1 = idx1_dev;
+      BRA_CUDA(ctx->scratch3.reserve((size_t)((mA + 31) / 32) * 4 + 64));
+      P.dbits = ctx->scratch3.as<uint32_t>();
+      srft_signbits_kernel<<<std::max<int>(1, (int)std::min<int64_t>(((mA + 31) / 32 + 255) / 256, 1024)), 256, 0, ctx->stream>>>(
+          d_dev, mA, ctx->scratch3.as<uint32_t>());
+      ctx->launches++;
+      // TMA needs 16-byte aligned base and strides (even lda, even m'), box dims <= 256, 32-bit coordinates
+      CUtensorMap mapA;
+      std::memset(&mapA, 0, sizeof(mapA));
+      P.boxrows = (int)std::min<int64_t>(l, 256);
+      P.use_tma = 0;
+      if ((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (lda & 1) == 0 && (mp & 1) == 0 && mc <= 256 && (mc * 8) % 16 == 0 &&
+          nA < (int64_t(1) << 31) && ((size_t)P.boxrows * mc * 8) % 128 == 0)
+        P.use_tma = bra_make_map_3d_f64(&mapA, A, (uint64_t)mp, (uint64_t)l, (uint64_t)nA, (uint64_t)mp * 8,
+                                        (uint64_t)lda * 8, (uint32_t)mc, (uint32_t)P.boxrows)
+                        ? 1
+                        : 0;
       if (chunks > 1) {
         BRA_CUDA(ctx->partial.reserve((size_t)chunks * order * nA * 8));
         P.out = ctx->partial.as<double>();
@@ -334,7 +521,7 @@ int bra_sketch_srft(bra_ctx* ctx, const double* A, int64_t lda, int64_t mA, int6
       int gx = (int)std::min<int64_t>(nA, std::max<int64_t>(1, (int64_t)ctx->num_sms * per_sm / chunks));
       {
         ProfScope ps(ctx, BRA_PROF_SKETCH_OTHER);
-        srft_kernel<<<dim3(gx, chunks), 256, smem, ctx->stream>>>(P);
+        srft_kernel<<<dim3(gx, chunks), nthreads, smem, ctx->stream>>>(mapA, P);
       }
       ctx->launches++;
       BRA_CUDA(cudaGetLastError());

@@ -356,6 +356,25 @@ bool make_map(CUtensorMap* map, const double* base, int64_t d0, int64_t d1, int6
   return r == CUDA_SUCCESS;
 }
 
+}  // namespace
+
+// 3-D FP64 tensor map (dim0 contiguous) for the SRFT row staging: (d0, d1, d2) with byte strides (s1, s2), box (b0, b1, 1)
+bool bra_make_map_3d_f64(CUtensorMap* map, const double* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1,
+                         uint64_t s2, uint32_t b0, uint32_t b1) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1, s2};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+namespace {
+
 template <int WA>
 int launch_gemm(bra_ctx* ctx, const CUtensorMap& mapA, const double* Omt, int64_t ldt, int64_t l, int64_t m,
                 int64_t n, double* B, int64_t ldb) {
