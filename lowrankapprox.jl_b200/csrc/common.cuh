@@ -85,6 +85,7 @@ struct bra_ctx {
   DevBuf scratch, scratch2, scratch3;
   DevBuf aux_in1, aux_in2;     // staged random inputs (d, idx, perm, s, r)
   DevBuf jwork;                // Jacobi SVD: grid barrier, per-sweep flags
+  DevBuf rinv, yt;             // CholeskyQR: explicit triangular inverse, transposed panels
   int last_jacobi_sweeps = 0;
   int jacobi_kcycles[8] = {0};
   std::vector<unsigned char> h_meta;  // host scratch for fast-mode index/sign generation

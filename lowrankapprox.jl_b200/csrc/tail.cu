@@ -129,26 +129,32 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(int k, int j0, double* 
     D[rr][cc] = (rr < jbsz && cc < jbsz) ? G[(j0 + rr) + (int64_t)(j0 + cc) * ldg] : (rr == cc ? 1.0 : 0.0);
   }
   __syncthreads();
-  if (tid < 32) {
-    // unblocked Cholesky of D by one warp: lane = row
-    const int r = tid;
+  {
+    // unblocked Cholesky of the 32 x 32 block, all 256 threads: per column one pivot, one scaling, one rank-1
+    // update of the trailing part (thread (r, cc4) owns entries D[r][cc4*4 .. cc4*4+3])
+    const int r = tid & 31, c4 = tid >> 5;
     for (int c = 0; c < TB; ++c) {
       double d = D[c][c];
       if (!(d > 0.0)) {
-        if (r == 0 && c < jbsz) atomicExch(info, j0 + c + 1);
+        if (tid == 0 && c < jbsz) atomicExch(info, j0 + c + 1);
         d = 1.0;
       }
       const double piv = sqrt(d);
-      __syncwarp();
-      if (r == c) D[c][c] = piv;
-      if (r > c) D[r][c] = D[r][c] / piv;
-      __syncwarp();
-      if (r > c)
-        for (int cc = c + 1; cc <= r; ++cc) D[r][cc] = fma(-D[r][c], D[cc][c], D[r][cc]);
-      __syncwarp();
+      __syncthreads();
+      if (tid == c) D[c][c] = piv;
+      if (tid > c && tid < TB) D[tid][c] = D[tid][c] / piv;
+      __syncthreads();
+      if (r > c) {
+        const double lrc = D[r][c];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int cc = c4 * 4 + u;
+          if (cc > c && cc <= r) D[r][cc] = fma(-lrc, D[cc][c], D[r][cc]);
+        }
+      }
+      __syncthreads();
     }
   }
-  __syncthreads();
   const int rb = blockIdx.x;        // 0: the diagonal block itself; b > 0: row block j0 + 32*b
   if (rb == 0) {
     for (int e = tid; e < TB * TB; e += 256) {
@@ -473,13 +479,34 @@ int bra_transpose(bra_ctx* ctx, const double* src, int64_t lds, int64_t rows, in
   return BRA_OK;
 }
 
+// Y <- Y R^{-1}.  Tall Y: R^{-1} is formed once (k x k back substitution on the identity; for the graded R of a
+// pivoted QR the componentwise condition |R^{-1}||R| does not see the grading, so this is as backward stable as
+// the substitution) and applied as a GEMM on the TMA + DMMA kernel: (Y R^{-1})' = (R^{-1})' Y'.
 int bra_trsolve_right_upper(bra_ctx* ctx, int64_t rows, int k, const double* R, int64_t ldr, double* Y, int64_t ldy) {
   if (rows <= 0 || k <= 0) return BRA_OK;
-  ProfScope ps(ctx, BRA_PROF_QR);
-  trsolve_right_upper_kernel<<<(unsigned)((rows + 63) / 64), 256, 0, ctx->stream>>>(rows, k, R, ldr, Y, ldy);
-  ctx->launches++;
-  BRA_CUDA(cudaGetLastError());
-  return BRA_OK;
+  const int64_t ldk = (k + 1) & ~int64_t(1);
+  if (rows < 4 * (int64_t)k || !bra_gemm_tma_ok(Y, ldy, rows, k)) {
+    ProfScope ps(ctx, BRA_PROF_QR);
+    trsolve_right_upper_kernel<<<(unsigned)((rows + 63) / 64), 256, 0, ctx->stream>>>(rows, k, R, ldr, Y, ldy);
+    ctx->launches++;
+    BRA_CUDA(cudaGetLastError());
+    return BRA_OK;
+  }
+  BRA_CUDA(ctx->rinv.reserve((size_t)ldk * k * 8));
+  BRA_CUDA(ctx->yt.reserve((size_t)2 * ldk * rows * 8));
+  double* Rinv = ctx->rinv.as<double>();
+  double* Yt = ctx->yt.as<double>();
+  double* Ct = Yt + (size_t)ldk * rows;
+  int rc;
+  {
+    ProfScope ps(ctx, BRA_PROF_QR);
+    set_identity_kernel<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(k, Rinv, ldk);
+    ctx->launches++;
+  }
+  if ((rc = bra_trsolve_upper(ctx, k, k, R, ldr, Rinv, ldk))) return rc;                   // Rinv = R^{-1}
+  if ((rc = bra_transpose(ctx, Y, ldy, rows, k, Yt, ldk))) return rc;                       // Y' (k x rows)
+  if ((rc = bra_gemm_tn(ctx, Rinv, ldk, k, k, Yt, ldk, rows, Ct, ldk))) return rc;          // (Y Rinv)' = Rinv' Y'
+  return bra_transpose(ctx, Ct, ldk, k, rows, Y, ldy);
 }
 
 // G (k x k, symmetric positive definite, destroyed) -> Rout upper triangular with G = Rout^T Rout
