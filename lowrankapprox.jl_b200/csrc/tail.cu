@@ -231,10 +231,15 @@ __global__ void add_identity_kernel(int k, double* __restrict__ G, int64_t ldg) 
 }
 
 // ---- one-sided Jacobi (Hestenes) on the columns of X (k x k), rotations accumulated into J ----
-// Block-cyclic and persistent: the k columns form nblk blocks of BC columns; in every outer step each CTA owns one
+// Block-cyclic and persistent.  The k columns form nblk blocks of BC columns; in every outer step each CTA owns one
 // block PAIR (chess-tournament schedule over the blocks), stages its 2*BC columns of X and of J in shared memory and
-// runs one full round-robin sweep of plane rotations among them there (a team of 64 threads per column pair).  One
-// grid barrier per outer step (nblk-1 per sweep) instead of one launch per rotation round (k-1 per sweep).
+// runs one full round-robin sweep of plane rotations among them there.  A TEAM of TS threads works on one column
+// pair (thread e holds rows e, e+TS, ... in registers for the dot products and the rotation), so a panel round
+// costs a few hundred cycles instead of a warp-serial pass over the columns.
+// Synchronisation between outer steps is POINT TO POINT: block b carries a step counter in global memory; the CTA
+// that needs (bI, bJ) at step g waits until both counters reached g, and bumps them after writing the blocks back.
+// There is no grid-wide barrier on the step path (one per sweep only, for the convergence vote), so a CTA whose
+// pairs have converged runs ahead instead of waiting for the slowest.
 // The rotations themselves are the classical ones: computed from freshly accumulated a = |x_p|^2, b = |x_q|^2,
 // c = x_p.x_q of the CURRENT columns (no Gram-matrix shortcut), so small singular values keep their accuracy.
 struct JacobiParams {
@@ -246,6 +251,7 @@ struct JacobiParams {
   double tol;
   int max_sweeps;
   unsigned* bar;       // grid barrier counter (zeroed before launch)
+  unsigned* bstep;     // [nblk] outer steps completed per block (zeroed before launch)
   int* rotated;        // [max_sweeps] "a rotation happened in this sweep"
   int* out;            // [0] sweeps done, [1] converged
 };
@@ -285,137 +291,230 @@ __device__ __forceinline__ void rr_pair(int np, int stage, int i, int& p, int& q
   }
 }
 
-template <int BC>
-__global__ void __launch_bounds__(32 * BC, 1) jacobi_block_kernel(JacobiParams P) {
+template <int TS>
+__device__ __forceinline__ void team_sync(int team) {
+  if (TS == 32) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(TS) : "memory");
+}
+
+// One plane rotation of the column pair (p, q) of the panel by a team of TS threads (thread e: rows e, e+TS, ...).
+// Returns true if the pair was rotated.  cs/sn come from ONE warp of the team (the FP64 pipe is the scarce unit:
+// 64 DFMA/clk/SM), written with two reciprocal square roots and no division:
+//   cos(2 theta) = |d| / h,  sin(2 theta) = sign(d) 2c / h,  h = sqrt(d^2 + 4c^2),  d = b - a
+//   cs = sqrt((1 + cos 2theta) / 2),  sn = sin(2 theta) / (2 cs)         (|theta| <= pi/4)
+template <int TS, int R>
+__device__ __forceinline__ bool rotate_pair(double* __restrict__ Xs, double* __restrict__ Js, int kp, int k, int p, int q,
+                                            int team, int e, double* __restrict__ rb, double tol2, long long* tk) {
+#define RTICK(i) if (tk) { long long _t = clock64(); tk[i] += _t - tk[7]; tk[7] = _t; }
+  RTICK(6)
+  constexpr int WPT = TS / 32;
+  const int lane = e & 31, tw = e >> 5;
+  double* xp = Xs + (size_t)p * kp;
+  double* xq = Xs + (size_t)q * kp;
+  double u[R], v[R];
+  double a = 0.0, b = 0.0, c = 0.0, a1 = 0.0, b1 = 0.0, c1 = 0.0;      // two chains per sum: DFMA latency ~ 16 cycles
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const int r = e + TS * i;
+    u[i] = (r < k) ? xp[r] : 0.0;
+    v[i] = (r < k) ? xq[r] : 0.0;
+    if (i & 1) {
+      a1 = fma(u[i], u[i], a1);
+      b1 = fma(v[i], v[i], b1);
+      c1 = fma(u[i], v[i], c1);
+    } else {
+      a = fma(u[i], u[i], a);
+      b = fma(v[i], v[i], b);
+      c = fma(u[i], v[i], c);
+    }
+  }
+  a += a1;
+  b += b1;
+  c += c1;
+  RTICK(0)
+  // warp reduction of the three sums with 6 exchanges instead of 15: after the xor-16 stage a lane keeps (a, c) or
+  // (b, -), after the xor-8 stage one value; lane 0 ends with a, lane 8 with c, lane 16 with b.
+  {
+    const bool hi16 = lane & 16, hi8 = lane & 8;
+    const double s0 = hi16 ? a : b, k0 = hi16 ? b : a;          // send the one I do not own, keep the other
+    double w0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);      // lanes < 16: a, lanes >= 16: b
+    double w1 = c + __shfl_xor_sync(0xffffffffu, c, 16);        // c (both halves hold the same partial pair sum)
+    // xor 8: lanes with bit 3 clear keep w0, the others keep w1 (c only matters in the low half)
+    const double s1 = hi8 ? w0 : w1, k1 = hi8 ? w1 : w0;
+    double w = k1 + __shfl_xor_sync(0xffffffffu, s1, 8);
+    w += __shfl_xor_sync(0xffffffffu, w, 4);
+    w += __shfl_xor_sync(0xffffffffu, w, 2);
+    w += __shfl_xor_sync(0xffffffffu, w, 1);
+    if (WPT > 1) {
+      // rb: [WPT][4] partial sums, then [2] = (cs, sn) (sn == 2.0: no rotation)
+      if ((lane & 7) == 0 && lane < 24) rb[tw * 4 + (lane == 0 ? 0 : (lane == 16 ? 1 : 2))] = w;
+      team_sync<TS>(team);
+    } else {
+      a = __shfl_sync(0xffffffffu, w, 0);
+      c = __shfl_sync(0xffffffffu, w, 8);
+      b = __shfl_sync(0xffffffffu, w, 16);
+    }
+  }
+  RTICK(1)
+  RTICK(2)
+  if (tw == (team % WPT)) {
+    if (WPT > 1) {
+      a = b = c = 0.0;
+#pragma unroll
+      for (int w = 0; w < WPT; ++w) {
+        a += rb[w * 4 + 0];
+        b += rb[w * 4 + 1];
+        c += rb[w * 4 + 2];
+      }
+    }
+    double cs = 1.0, sn = 2.0;
+    if (c * c > tol2 * a * b) {          // converged pair: |c| <= tol * sqrt(a b)
+      const double d = b - a, c2 = 2.0 * c;
+      const double rh = rsqrt(fma(d, d, c2 * c2));
+      const double hc = fma(0.5 * fabs(d), rh, 0.5);          // (1 + cos 2theta) / 2  in [1/2, 1]
+      const double rc = rsqrt(hc);
+      cs = hc * rc;
+      sn = (d >= 0.0 ? 0.5 : -0.5) * (c2 * rh) * rc;
+    }
+    if (lane == 0) {
+      rb[WPT * 4 + 0] = cs;
+      rb[WPT * 4 + 1] = sn;
+    }
+  }
+  RTICK(3)
+  team_sync<TS>(team);
+  const double cs = rb[WPT * 4 + 0], sn = rb[WPT * 4 + 1];
+  RTICK(4)
+  if (sn == 2.0) return false;
+  double* jp = Js + (size_t)p * kp;
+  double* jq = Js + (size_t)q * kp;
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const int r = e + TS * i;
+    if (r < k) {
+      const double ju = jp[r], jv = jq[r];
+      xp[r] = fma(cs, u[i], -sn * v[i]);
+      xq[r] = fma(sn, u[i], cs * v[i]);
+      jp[r] = fma(cs, ju, -sn * jv);
+      jq[r] = fma(sn, ju, cs * jv);
+    }
+  }
+  RTICK(5)
+  return true;
+#undef RTICK
+}
+
+// BC = column pairs per panel (= columns per block), TS = threads per pair, R = rows per thread (k <= TS * R)
+template <int BC, int TS, int R>
+__global__ void __launch_bounds__(BC * TS, 1) jacobi_team_kernel(JacobiParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int NT = 32 * BC;                      // one warp per column pair
+  constexpr int NT = BC * TS;
   constexpr int NC = 2 * BC;                       // columns in a panel
+  constexpr int WPT = TS / 32;                     // warps per team
+  constexpr int RBS = WPT * 4 + 2;                 // doubles of reduction scratch per team and parity
   const int k = P.k, tid = threadIdx.x;
   const int kp = (k + 1) & ~1;                     // padded column length (16-byte aligned columns)
   double* Xs = reinterpret_cast<double*>(smem_raw);             // [NC][kp]
   double* Js = Xs + (size_t)NC * kp;                             // [NC][kp]
+  double* red = Js + (size_t)NC * kp;                            // [2][BC][RBS]
   __shared__ int s_rot;
-  const int warp = tid >> 5, lane = tid & 31;
-  const int npairs = P.nblk / 2;
+  const int team = tid / TS, e = tid % TS;
+  const int nsteps = P.nblk - 1;
   const double tol2 = P.tol * P.tol;
-  unsigned epoch = 0;
+  unsigned epoch = 0, gstep = 0;
   int sweep = 0, converged = 0;
-  long long tph[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+  long long tph[4] = {0, 0, 0, 0}, tlast = clock64();
+  long long rtk[8] = {0, 0, 0, 0, 0, 0, 0, clock64()};
 #define JTICK(i) if (tid == 0) { long long _t = clock64(); tph[i] += _t - tlast; tlast = _t; }
   for (; sweep < P.max_sweeps; ++sweep) {
     if (tid == 0) s_rot = 0;
-    for (int st = 0; st < P.nblk - 1; ++st) {
-      for (int pi = blockIdx.x; pi < npairs; pi += gridDim.x) {
-        int bI, bJ;
-        rr_pair(P.nblk, st, pi, bI, bJ);
-        // ---- stage the panel (L2 -> smem with cp.async.cg: no L1, other CTAs wrote these columns earlier) ----
-        __syncthreads();
-        for (int lc = warp; lc < NC; lc += BC) {
-          const int gc = (lc < BC ? bI * BC + lc : bJ * BC + (lc - BC));
-          double* xs = Xs + (size_t)lc * kp;
-          double* js = Js + (size_t)lc * kp;
-          if (gc < k) {
-            const double* gx = P.X + (int64_t)gc * P.ldx;
-            const double* gj = P.J + (int64_t)gc * P.ldj;
-            for (int r = 2 * lane; r < kp; r += 64) {
-              cp_async16(xs + r, gx + r);
-              cp_async16(js + r, gj + r);
-            }
-          } else {
-            for (int r = lane; r < kp; r += 32) {
-              xs[r] = 0.0;
-              js[r] = 0.0;
-            }
-          }
-        }
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        __syncthreads();
-        JTICK(0)
-        // ---- one round-robin sweep among the NC panel columns, one warp per pair ----
-        bool rot_any = false;
-        for (int rd = 0; rd < NC - 1; ++rd) {
-          int p, q;
-          rr_pair(NC, rd, warp, p, q);
-          double* xp = Xs + (size_t)p * kp;
-          double* xq = Xs + (size_t)q * kp;
-          double a0 = 0.0, b0 = 0.0, c0 = 0.0, a1 = 0.0, b1 = 0.0, c1 = 0.0;
-          int r = lane;
-          for (; r + 32 < k; r += 64) {
-            const double u0 = xp[r], v0 = xq[r], u1 = xp[r + 32], v1 = xq[r + 32];
-            a0 = fma(u0, u0, a0);
-            b0 = fma(v0, v0, b0);
-            c0 = fma(u0, v0, c0);
-            a1 = fma(u1, u1, a1);
-            b1 = fma(v1, v1, b1);
-            c1 = fma(u1, v1, c1);
-          }
-          if (r < k) {
-            const double u0 = xp[r], v0 = xq[r];
-            a0 = fma(u0, u0, a0);
-            b0 = fma(v0, v0, b0);
-            c0 = fma(u0, v0, c0);
-          }
-          double a = a0 + a1, b = b0 + b1, c = c0 + c1;
-          JTICK(4)
+    bool rot_any = false;
+    for (int st = 0; st < nsteps; ++st, ++gstep) {
+      int bI, bJ;
+      rr_pair(P.nblk, st, blockIdx.x, bI, bJ);
+      // ---- wait until both blocks have finished step gstep-1 (point to point, no grid barrier) ----
+      if (tid < 2) {
+        const unsigned* f = P.bstep + (tid == 0 ? bI : bJ);
+        unsigned v;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        } while (v < gstep);
+      }
+      __syncthreads();
+      JTICK(0)
+      // ---- stage the panel (L2 -> smem with cp.async.cg: no L1, other CTAs wrote these columns earlier) ----
+      // team t stages its own two columns (t of block I, t of block J) of X and of J: no index arithmetic
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, o);
-            b += __shfl_xor_sync(0xffffffffu, b, o);
-            c += __shfl_xor_sync(0xffffffffu, c, o);
+      for (int h = 0; h < 2; ++h) {
+        const int lc = h * BC + team;
+        const int gc = (h == 0 ? bI : bJ) * BC + team;
+        double* xs = Xs + (size_t)lc * kp;
+        double* js = Js + (size_t)lc * kp;
+        if (gc < k) {
+          const double* gx = P.X + (int64_t)gc * P.ldx;
+          const double* gj = P.J + (int64_t)gc * P.ldj;
+          for (int r = 2 * e; r < kp; r += 2 * TS) {
+            cp_async16(xs + r, gx + r);
+            cp_async16(js + r, gj + r);
           }
-          JTICK(5)
-          // converged pair: |c| <= tol * sqrt(a b)
-          if (c * c > tol2 * a * b) {
-            rot_any = true;
-            // t = tan(theta) = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (b - a) / (2c), written with one
-            // square root, one division and one reciprocal square root
-            const double d = b - a, c2 = 2.0 * c;
-            const double h = sqrt(fma(d, d, c2 * c2));
-            const double t = ((d >= 0.0) ? c2 : -c2) / (fabs(d) + h);
-            const double cs = rsqrt(fma(t, t, 1.0)), sn = cs * t;
-            if (tid == 0 && cs == 123.0) tph[8]++;
-            JTICK(6)
-            double* jp = Js + (size_t)p * kp;
-            double* jq = Js + (size_t)q * kp;
-#pragma unroll 4
-            for (int rr = lane; rr < k; rr += 32) {
-              const double u = xp[rr], v = xq[rr];
-              xp[rr] = fma(cs, u, -sn * v);
-              xq[rr] = fma(sn, u, cs * v);
-              const double ju = jp[rr], jv = jq[rr];
-              jp[rr] = fma(cs, ju, -sn * jv);
-              jq[rr] = fma(sn, ju, cs * jv);
-            }
-            JTICK(7)
+        } else {
+          for (int r = e; r < kp; r += TS) {
+            xs[r] = 0.0;
+            js[r] = 0.0;
           }
+        }
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncthreads();
+      JTICK(1)
+      int par = 0;
+      // ---- once per sweep: the pairs INSIDE each of the two blocks (round-robin over BC columns, both blocks at
+      // once: teams 0..BC/2-1 take block I, the rest block J) ----
+      if (st == 0 && BC > 1) {
+        for (int rd = 0; rd < BC - 1; ++rd, par ^= 1) {
+          int p, q;
+          rr_pair(BC, rd, team % (BC / 2 > 0 ? BC / 2 : 1), p, q);
+          const int off = (team < BC / 2) ? 0 : BC;
+          rot_any |= rotate_pair<TS, R>(Xs, Js, kp, k, off + p, off + q, team, e, red + (size_t)(par * BC + team) * RBS, tol2, tid == 0 ? rtk : nullptr);
           __syncthreads();
-          JTICK(1)
         }
-        if (rot_any && lane == 0) s_rot = 1;
-        // ---- write the panel back ----
-        for (int lc = warp; lc < NC; lc += BC) {
-          const int gc = (lc < BC ? bI * BC + lc : bJ * BC + (lc - BC));
-          if (gc < k) {
-            const double2* xs = reinterpret_cast<const double2*>(Xs + (size_t)lc * kp);
-            const double2* js = reinterpret_cast<const double2*>(Js + (size_t)lc * kp);
-            double2* gx = reinterpret_cast<double2*>(P.X + (int64_t)gc * P.ldx);
-            double2* gj = reinterpret_cast<double2*>(P.J + (int64_t)gc * P.ldj);
-            for (int r = lane; r < kp / 2; r += 32) {
-              __stcg(gx + r, xs[r]);
-              __stcg(gj + r, js[r]);
-            }
+      }
+      // ---- every step: each column of block I meets each column of block J once (BC rounds of BC disjoint pairs) ----
+      for (int rd = 0; rd < BC; ++rd, par ^= 1) {
+        const int p = team, q = BC + ((team + rd) % BC);
+        rot_any |= rotate_pair<TS, R>(Xs, Js, kp, k, p, q, team, e, red + (size_t)(par * BC + team) * RBS, tol2, tid == 0 ? rtk : nullptr);
+        __syncthreads();
+      }
+      JTICK(2)
+      // ---- write the panel back, then publish "block finished step gstep" ----
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int lc = h * BC + team;
+        const int gc = (h == 0 ? bI : bJ) * BC + team;
+        if (gc < k) {
+          const double2* xs = reinterpret_cast<const double2*>(Xs + (size_t)lc * kp);
+          const double2* js = reinterpret_cast<const double2*>(Js + (size_t)lc * kp);
+          double2* gx = reinterpret_cast<double2*>(P.X + (int64_t)gc * P.ldx);
+          double2* gj = reinterpret_cast<double2*>(P.J + (int64_t)gc * P.ldj);
+          for (int r = e; r < kp / 2; r += TS) {
+            __stcg(gx + r, xs[r]);
+            __stcg(gj + r, js[r]);
           }
         }
-        JTICK(2)
       }
-      if (st == P.nblk - 2) {
-        __syncthreads();
-        if (tid == 0 && s_rot) atomicExch(P.rotated + sweep, 1);
+      __syncthreads();
+      if (tid < 2) {        // st.release.gpu is cumulative over the CTA barrier above: no separate fence
+        unsigned* f = P.bstep + (tid == 0 ? bI : bJ);
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(f), "r"(gstep + 1) : "memory");
       }
-      ++epoch;
-      grid_barrier(P.bar, epoch * gridDim.x);
       JTICK(3)
     }
+    // ---- convergence vote: one grid barrier per sweep ----
+    if (rot_any) s_rot = 1;
+    __syncthreads();
+    if (tid == 0 && s_rot) atomicExch(P.rotated + sweep, 1);
+    ++epoch;
+    grid_barrier(P.bar, epoch * gridDim.x);
     int any;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(any) : "l"(P.rotated + sweep) : "memory");
     if (!any) {
@@ -424,20 +523,24 @@ __global__ void __launch_bounds__(32 * BC, 1) jacobi_block_kernel(JacobiParams P
       break;
     }
   }
-  if (blockIdx.x == 0 && tid == 0) {
+  // report from the LAST CTA (CTA 0 often owns the zero-padded block and is not representative)
+  if (blockIdx.x == 0 && tid == 0)
+    for (int i = 0; i < 7; ++i) P.out[16 + i] = (int)(rtk[i] >> 10);
+  if (blockIdx.x == gridDim.x - 1 && tid == 0) {
     P.out[0] = sweep;
     P.out[1] = converged;
-    for (int i = 0; i < 8; ++i) P.out[2 + i] = (int)(tph[i] >> 10);     // kilo-cycles: load, sync, store, barrier, dot, shuffle, math, apply
+    for (int i = 0; i < 4; ++i) P.out[2 + i] = (int)(tph[i] >> 10);     // kilo-cycles: wait, load, rotate, store
+    for (int i = 4; i < 8; ++i) P.out[2 + i] = 0;
   }
 #undef JTICK
 }
 
-template <int BC>
+template <int BC, int TS, int R>
 cudaError_t launch_jacobi(const JacobiParams& P, int grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(jacobi_block_kernel<BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(jacobi_team_kernel<BC, TS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   void* args[] = {(void*)&P};
-  return cudaLaunchCooperativeKernel((void*)jacobi_block_kernel<BC>, dim3(grid), dim3(32 * BC), args, smem, st);
+  return cudaLaunchCooperativeKernel((void*)jacobi_team_kernel<BC, TS, R>, dim3(grid), dim3(BC * TS), args, smem, st);
 }
 
 __global__ void set_identity_kernel(int k, double* __restrict__ J, int64_t ldj) {
@@ -583,25 +686,50 @@ int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64
     return -4;
   }
   if (k > 1) {
-    // widest block whose panel (2*BC columns of X and of J) fits in shared memory
-    const size_t budget = (size_t)ctx->smem_optin - 2048;
-    int bc = 8;
+    // team size: k <= TS * R rows in registers (R = 4, or 8 on request); panel = 2*BC columns of X and of J in
+    // shared memory
+    int ts = 32, rr = 4;
+    while (ts < 1024 && ts * 4 < k) ts <<= 1;
+    if (ts * 4 < k) {
+      ctx->set_error("Jacobi SVD: k too large for the register-resident team kernel (k <= 4096)");
+      return BRA_ERR_UNSUPPORTED;
+    }
+    // measured on B200 (k = 500): 8 rows per thread and blocks of 4 columns (63 CTAs) balance the per-round
+    // latency chain against the per-step exchange
+    bool r8 = ts >= 64 && ts <= 256;
+    if (const char* ev = getenv("BRA_JACOBI_R8")) r8 = r8 && atoi(ev) > 0;
+    if (r8) {
+      ts >>= 1;
+      rr = 8;
+    }
+    int bc = 1024 / ts;
+    if (bc > 4) bc = 4;
+    if (const char* ev = getenv("BRA_JACOBI_BC")) {
+      const int v = atoi(ev);
+      if (v > 0 && v <= 8 && v * ts <= 1024 && (v & (v - 1)) == 0) bc = v;
+    }
     const size_t kp = (size_t)((k + 1) & ~1);
-    while (bc > 1 && (size_t)32 * bc * kp > budget) bc >>= 1;
-    if ((size_t)32 * bc * kp > budget) {
+    const size_t budget = (size_t)ctx->smem_optin - 2048;
+    auto need = [&](int b) { return (size_t)32 * b * kp + (size_t)2 * b * ((ts / 32) * 4 + 2) * 8 + 64; };
+    while (bc > 1 && (need(bc) > budget || k <= bc)) bc >>= 1;   // tiny cores: keep at least two blocks of real columns
+    if (need(bc) > budget) {
       ctx->set_error("Jacobi SVD: k too large for the shared-memory panel");
       return BRA_ERR_UNSUPPORTED;
     }
-    // A round is shared-memory-bandwidth bound (every rotation streams its columns of X and J) while every outer
-    // step costs a grid barrier: measured on B200 at k = 500, blocks of 4 columns (64 CTAs) balance the two.
-    if (bc > 4) bc = 4;
-    if (const char* ev = getenv("BRA_JACOBI_BC")) bc = atoi(ev) > 0 ? atoi(ev) : bc;
-    while (bc > 1 && k <= bc) bc >>= 1;              // tiny cores: keep at least two blocks of real columns
-    const int nblk = 2 * ((k + 2 * bc - 1) / (2 * bc));
-    const int grid = std::min(nblk / 2, ctx->num_sms);
-    const size_t smem = (size_t)32 * bc * kp;
-    BRA_CUDA(ctx->jwork.reserve(256 + MAX_SWEEPS * 4));
-    BRA_CUDA(cudaMemsetAsync(ctx->jwork.p, 0, 256 + MAX_SWEEPS * 4, ctx->stream));
+    int nblk = 2 * ((k + 2 * bc - 1) / (2 * bc));
+    while (nblk / 2 > ctx->num_sms && bc < 8) {      // one CTA per block pair must be co-resident
+      bc <<= 1;
+      nblk = 2 * ((k + 2 * bc - 1) / (2 * bc));
+    }
+    if (nblk / 2 > ctx->num_sms || need(bc) > budget || bc * ts > 1024) {
+      ctx->set_error("Jacobi SVD: no co-resident configuration for this k");
+      return BRA_ERR_UNSUPPORTED;
+    }
+    const int grid = nblk / 2;
+    const size_t smem = need(bc);
+    const size_t wbytes = 1024 + (size_t)MAX_SWEEPS * 4 + (size_t)nblk * 4;
+    BRA_CUDA(ctx->jwork.reserve(wbytes));
+    BRA_CUDA(cudaMemsetAsync(ctx->jwork.p, 0, wbytes, ctx->stream));
     JacobiParams P;
     P.k = k;
     P.nblk = nblk;
@@ -614,21 +742,26 @@ int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64
     P.bar = ctx->jwork.as<unsigned>();
     P.out = ctx->jwork.as<int>() + 16;
     P.rotated = ctx->jwork.as<int>() + 64;
-    cudaError_t e;
-    switch (bc) {
-      case 8: e = launch_jacobi<8>(P, grid, smem, ctx->stream); break;
-      case 4: e = launch_jacobi<4>(P, grid, smem, ctx->stream); break;
-      case 2: e = launch_jacobi<2>(P, grid, smem, ctx->stream); break;
-      default: e = launch_jacobi<1>(P, grid, smem, ctx->stream); break;
-    }
+    P.bstep = ctx->jwork.as<unsigned>() + 256 + MAX_SWEEPS;
+    cudaError_t e = cudaErrorInvalidValue;
+#define JL(B_, T_, R_) if (bc == B_ && ts == T_ && rr == R_) e = launch_jacobi<B_, T_, R_>(P, grid, smem, ctx->stream);
+    JL(8, 32, 4) JL(4, 32, 4) JL(2, 32, 4) JL(1, 32, 4)
+    JL(8, 64, 4) JL(4, 64, 4) JL(2, 64, 4) JL(1, 64, 4)
+    JL(8, 128, 4) JL(4, 128, 4) JL(2, 128, 4) JL(1, 128, 4)
+    JL(4, 256, 4) JL(2, 256, 4) JL(1, 256, 4)
+    JL(2, 512, 4) JL(1, 512, 4)
+    JL(1, 1024, 4)
+    JL(8, 32, 8) JL(4, 32, 8) JL(8, 64, 8) JL(4, 64, 8) JL(8, 128, 8) JL(4, 128, 8)
+#undef JL
     BRA_CUDA(e);
     ctx->launches++;
-    int h[10] = {0};
-    BRA_CUDA(cudaMemcpyAsync(h, P.out, 40, cudaMemcpyDeviceToHost, ctx->stream));
+    int h[24] = {0};
+    BRA_CUDA(cudaMemcpyAsync(h, P.out, 96, cudaMemcpyDeviceToHost, ctx->stream));
     BRA_CUDA(cudaStreamSynchronize(ctx->stream));
     sweeps = h[0];
     converged = h[1];
     for (int i = 0; i < 8; ++i) ctx->jacobi_kcycles[i] = h[2 + i];
+    if (getenv("BRA_JACOBI_TICKS")) fprintf(stderr, "jacobi round ticks (kcyc, CTA0 thread0): dots %d shfl %d sync1 %d math %d sync2 %d apply %d between %d\n", h[16], h[17], h[18], h[19], h[20], h[21], h[22]);
   }
   ctx->last_jacobi_sweeps = sweeps;
   BRA_CUDA(ctx->S.reserve((size_t)k * 8));
