@@ -551,17 +551,19 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
   const int64_t k = res.k;
   if (k > 0) {
     BRA_CUDA(ctx->R11.reserve((size_t)k * k * 8));
-    BRA_CUDA(ctx->T.reserve((size_t)k * (nA - k > 0 ? nA - k : 1) * 8));
+    const int64_t ldT = (k + 1) & ~int64_t(1);
+    res.ldT = ldT;
+    BRA_CUDA(ctx->T.reserve((size_t)ldT * (nA - k > 0 ? nA - k : 1) * 8));
     int rc;
     {
       ProfScope ps(ctx, BRA_PROF_GATHER);
       rc = bra_gather_R(ctx, ctx->B.as<double>(), order, nA, (int)k, ctx->jpvt.as<int64_t>(), ctx->R11.as<double>(),
-                        ctx->T.as<double>());
+                        ctx->T.as<double>(), ldT);
     }
     if (rc) return rc;
     {
       ProfScope ps(ctx, BRA_PROF_TRSOLVE);
-      rc = bra_trsolve_upper(ctx, (int)k, nA - k, ctx->R11.as<double>(), k, ctx->T.as<double>(), k);
+      rc = bra_trsolve_upper(ctx, (int)k, nA - k, ctx->R11.as<double>(), k, ctx->T.as<double>(), ldT);
     }
     if (rc) return rc;
   }
@@ -644,7 +646,7 @@ int bra_fetch(bra_ctx* ctx, int which, void* dst, int64_t ld) {
     case BRA_F_T:
       if (!r.have_T) return BRA_ERR_NOTREADY;
       BRA_CHECK_ARG(ld >= (k > 1 ? k : 1), 4, "ld");
-      BRA_CUDA(copy2d(ctx, dst, ld, ctx->T.p, k, k, n - k));
+      BRA_CUDA(copy2d(ctx, dst, ld, ctx->T.p, r.ldT, k, n - k));
       break;
     case BRA_F_TAU:
       if (r.rounds == 0) return BRA_ERR_NOTREADY;

@@ -1,5 +1,6 @@
 // Fused pqrfact / psvdfact drivers over the idfact core (reference: src/pqr.jl:290-307, src/psvd.jl:238-272).
 #include "common.cuh"
+#include <algorithm>
 #include <vector>
 
 int bra_set_identity(bra_ctx* ctx, int k, double* J, int64_t ldj);
@@ -76,7 +77,7 @@ int bra_pqrfact_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double
       BRA_CUDA(ctx->scratch2.reserve((size_t)even(k) * k * 8));
       rc = bra_transpose(ctx, ctx->R1.as<double>(), k, k, k, ctx->scratch2.as<double>(), even(k));   // R1^T, K-major
       if (rc) return rc;
-      rc = bra_gemm_tn(ctx, ctx->scratch2.as<double>(), even(k), k, k, ctx->T.as<double>(), k, nA - k,
+      rc = bra_gemm_tn(ctx, ctx->scratch2.as<double>(), even(k), k, k, ctx->T.as<double>(), res.ldT, nA - k,
                        ctx->Rfull.as<double>() + (size_t)k * k, k);
       if (rc) return rc;
     }
@@ -129,7 +130,7 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
   rc = bra_set_identity(ctx, (int)k, Z, ldz);
   if (rc) return rc;
   if (nA > k) {
-    rc = bra_transpose(ctx, ctx->T.as<double>(), k, k, nA - k, Z + k, ldz);
+    rc = bra_transpose(ctx, ctx->T.as<double>(), res.ldT, k, nA - k, Z + k, ldz);
     if (rc) return rc;
   }
   const int64_t ldj = even(k);                // even leading dimension: 16-byte aligned columns for the Jacobi panels
@@ -138,8 +139,33 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
   double* X = Rz + (size_t)ldj * k;         // Jacobi matrix: X = M' = R_z R1'
   double* J = X + (size_t)ldj * k;
   double* Ysel = J + (size_t)ldj * k;
-  rc = bra_cholqr2(ctx, nA, (int)k, Z, ldz, nullptr, Rz);
-  if (rc) return rc;
+  // Z is well conditioned (kappa(Z) = sqrt(1 + ||T||^2) / sqrt(1 + smin(T)^2), a few tens for a rank-revealing T), so
+  // ONE Cholesky pass on the Gram matrix gives R_z with Q_z = Z R_z^{-1} orthonormal to eps*kappa^2, and Q_z itself is
+  // never formed: Vop' = Ysel' Q_z' = (R_z^{-1} Ysel)' [I T].  A badly conditioned Z (diag(R_z) spread > 1e3) takes the
+  // two-pass CholeskyQR2 with an explicit Q_z instead.
+  bool explicit_qz = false;
+  {
+    BRA_CUDA(ctx->G.reserve((size_t)k * k * 8));
+    rc = bra_gemm_tn(ctx, Z, ldz, k, nA, Z, ldz, k, ctx->G.as<double>(), k);              // G = Z'Z = I + T T'
+    if (rc) return rc;
+    rc = bra_cholesky_upper(ctx, (int)k, ctx->G.as<double>(), k, Rz, k);
+    if (rc) return rc;
+    std::vector<double> dz((size_t)k);
+    int hinfo = 0;
+    BRA_CUDA(cudaMemcpy2DAsync(dz.data(), 8, Rz, (size_t)(k + 1) * 8, 8, (size_t)k, cudaMemcpyDeviceToHost, ctx->stream));
+    BRA_CUDA(cudaMemcpyAsync(&hinfo, ctx->info.as<int>() + 12, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+    double dmin = dz[0], dmax = dz[0];
+    for (double d : dz) {
+      dmin = std::min(dmin, d);
+      dmax = std::max(dmax, d);
+    }
+    explicit_qz = hinfo != 0 || !(dmin > 0.0) || dmax > 1e3 * dmin;
+  }
+  if (explicit_qz) {
+    rc = bra_cholqr2(ctx, nA, (int)k, Z, ldz, nullptr, Rz);
+    if (rc) return rc;
+  }
   // X[i,j] = sum_t Rz[i,t] R1[j,t]
   rc = bra_gemm_generic(ctx, Rz, 1, k, ctx->R1.as<double>(), k, 1, k, k, k, X, ldj);
   if (rc) return rc;
@@ -174,11 +200,11 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
   double* Qt = ctx->scratch2.as<double>();
   double* Out = ctx->scratch3.as<double>();
   // left factor of op(A):  Uop = Q * J[:, order[:kk]]   (mA x kk)
-  rc = bra_gather_scale_cols(ctx, J, ldj, k, (int)kk, ctx->aux_in1.as<int>(), nullptr, Ysel, k);
+  rc = bra_gather_scale_cols(ctx, J, ldj, k, (int)kk, ctx->aux_in1.as<int>(), nullptr, Ysel, ldj);
   if (rc) return rc;
   rc = bra_transpose(ctx, ctx->Q.as<double>(), even(mA), mA, k, Qt, ldk);          // Q' (k x mA)
   if (rc) return rc;
-  rc = bra_gemm_tn(ctx, Ysel, k, kk, k, Qt, ldk, mA, Out, even(kk));                 // (kk x mA) = Jsel' Q'
+  rc = bra_gemm_tn(ctx, Ysel, ldj, kk, k, Qt, ldk, mA, Out, even(kk));                 // (kk x mA) = Jsel' Q'
   if (rc) return rc;
   double* Uop_t = Out;          // kk x mA, ld even(kk)
   if (trans == 'n') {
@@ -190,13 +216,26 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
   }
   if (rc) return rc;
   // right factor of op(A):  Vop' = Ysel' Qz' P'   with Ysel = X[:, order] / sigma
-  rc = bra_gather_scale_cols(ctx, X, ldj, k, (int)kk, ctx->aux_in1.as<int>(), ctx->S.as<double>(), Ysel, k);
-  if (rc) return rc;
-  rc = bra_transpose(ctx, Z, ldz, nA, k, Qt, ldk);                                   // Qz' (k x nA)
+  rc = bra_gather_scale_cols(ctx, X, ldj, k, (int)kk, ctx->aux_in1.as<int>(), ctx->S.as<double>(), Ysel, ldj);
   if (rc) return rc;
   BRA_CUDA(ctx->B2.reserve((size_t)even(kk) * nA * 8));
-  rc = bra_gemm_tn(ctx, Ysel, k, kk, k, Qt, ldk, nA, ctx->B2.as<double>(), even(kk));
-  if (rc) return rc;
+  if (explicit_qz) {
+    rc = bra_transpose(ctx, Z, ldz, nA, k, Qt, ldk);                                   // Qz' (k x nA)
+    if (rc) return rc;
+    rc = bra_gemm_tn(ctx, Ysel, ldj, kk, k, Qt, ldk, nA, ctx->B2.as<double>(), even(kk));
+    if (rc) return rc;
+  } else {
+    // Yh = R_z^{-1} Ysel (k x kk);  Vop' = Yh' [I T]: the first k columns are Yh' itself, the rest one TN product with T
+    rc = bra_trsolve_upper(ctx, (int)k, kk, Rz, k, Ysel, ldj);
+    if (rc) return rc;
+    rc = bra_transpose(ctx, Ysel, ldj, k, kk, ctx->B2.as<double>(), even(kk));
+    if (rc) return rc;
+    if (nA > k) {
+      rc = bra_gemm_tn(ctx, Ysel, ldj, kk, k, ctx->T.as<double>(), res.ldT, nA - k, ctx->B2.as<double>() + (size_t)even(kk) * k,
+                       even(kk));
+      if (rc) return rc;
+    }
+  }
   // undo the pivoting: columns j -> p[j]
   rc = bra_scatter_cols(ctx, ctx->B2.as<double>(), even(kk), kk, nA, ctx->jpvt.as<int64_t>(), Out, even(kk));
   if (rc) return rc;

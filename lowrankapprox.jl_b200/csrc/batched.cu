@@ -455,7 +455,7 @@ int bra_idfact_batched_f64(bra_ctx* ctx, int64_t nblocks, int64_t m, int64_t n, 
       if (kb > ldT) {
         ++tslot;
       } else if (kb > 0 && n > kb) {
-        BRA_CUDA(cudaMemcpy2DAsync(T_out + b * strideT, (size_t)ldT * 8, ctx->T.p, (size_t)kb * 8, (size_t)kb * 8,
+        BRA_CUDA(cudaMemcpy2DAsync(T_out + b * strideT, (size_t)ldT * 8, ctx->T.p, (size_t)ctx->res.ldT * 8, (size_t)kb * 8,
                                    (size_t)(n - kb), cudaMemcpyDeviceToDevice, ctx->stream));
       }
       BRA_CUDA(cudaStreamSynchronize(ctx->stream));

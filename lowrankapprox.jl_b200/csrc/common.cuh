@@ -57,6 +57,7 @@ struct FactResult {
   int64_t orders[BRA_MAX_ROUNDS];
   int64_t ks[BRA_MAX_ROUNDS];
   int64_t steps[BRA_MAX_ROUNDS];
+  int64_t ldT = 0;             // leading dimension of ctx->T (k rounded up to even: keeps the TMA GEMM path open)
   int64_t svd_m = 0, svd_n = 0;  // dims of the ORIGINAL A for psvdfact's U (svd_m x ksvd) and Vt (ksvd x svd_n)
   bool have_T = false, have_Q = false, have_R = false, have_svd = false;
 };
@@ -157,7 +158,7 @@ int bra_qrcp_run(bra_ctx* ctx, double* B, int64_t ldb, int l, int64_t n, int kca
 int bra_permute_cols(bra_ctx* ctx, const double* src, int64_t lds, double* dst, int64_t ldd,
                      int64_t rows, int64_t n, const int64_t* jpvt1);
 int bra_gather_R(bra_ctx* ctx, const double* B, int64_t ldb, int64_t n, int k,
-                 const int64_t* jpvt1, double* R11, double* R12);
+                 const int64_t* jpvt1, double* R11, double* R12, int64_t ld12);
 
 // sketch_randn.cu
 int bra_transpose_omega(bra_ctx* ctx, const double* Om, int64_t ldo, int64_t l, int64_t m, double* Omt);

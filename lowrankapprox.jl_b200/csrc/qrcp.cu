@@ -643,7 +643,7 @@ __global__ void permute_cols_kernel(const double* __restrict__ src, int64_t lds,
 
 __global__ void gather_R_kernel(const double* __restrict__ B, int64_t ldb, int64_t n, int k,
                                 const int64_t* __restrict__ jpvt1, double* __restrict__ R11,
-                                double* __restrict__ R12) {
+                                double* __restrict__ R12, int64_t ld12) {
   // R = triu(B[0:k, p]) split into R11 (k x k, ld k) and R12 (k x (n-k), ld k)  (src/pqr.jl:428)
   for (int64_t j = blockIdx.x; j < n; j += gridDim.x) {
     const double* s = B + (jpvt1[j] - 1) * ldb;
@@ -651,8 +651,9 @@ __global__ void gather_R_kernel(const double* __restrict__ B, int64_t ldb, int64
       double* d = R11 + j * (int64_t)k;
       for (int r = threadIdx.x; r < k; r += blockDim.x) d[r] = (r <= j) ? s[r] : 0.0;
     } else {
-      double* d = R12 + (j - k) * (int64_t)k;
+      double* d = R12 + (j - k) * ld12;
       for (int r = threadIdx.x; r < k; r += blockDim.x) d[r] = s[r];
+      if (threadIdx.x == 0 && ld12 > k) d[k] = 0.0;      // padding row
     }
   }
 }
@@ -773,10 +774,10 @@ int bra_permute_cols(bra_ctx* ctx, const double* src, int64_t lds, double* dst, 
 }
 
 int bra_gather_R(bra_ctx* ctx, const double* B, int64_t ldb, int64_t n, int k, const int64_t* jpvt1,
-                 double* R11, double* R12) {
+                 double* R11, double* R12, int64_t ld12) {
   if (n <= 0 || k <= 0) return BRA_OK;
   int grid = (int)(n < 148 * 8 ? n : 148 * 8);
-  gather_R_kernel<<<grid, 128, 0, ctx->stream>>>(B, ldb, n, k, jpvt1, R11, R12);
+  gather_R_kernel<<<grid, 128, 0, ctx->stream>>>(B, ldb, n, k, jpvt1, R11, R12, ld12);
   ctx->launches++;
   BRA_CUDA(cudaGetLastError());
   return BRA_OK;
