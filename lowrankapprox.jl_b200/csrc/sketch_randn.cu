@@ -187,46 +187,50 @@ __global__ void splitk_reduce_kernel(const double* __restrict__ part, int64_t sp
 }
 
 // ------------------------------------------------------------------ generic fallback (any alignment / trans)
-// C[i][j] = sum_k Om[i*osi + k*osk] * A[k*sk + j*sj];  64x64 tile, 4x4 per thread, DFMA.
+// C[i][j] = sum_k Om[i*osi + k*osk] * A[k*sk + j*sj];  T x T tile (T = 64: 4x4 per thread, T = 32: 2x2 per thread,
+// four times the CTAs -- the k x k x k products of the tails are latency-critical and too small to fill the machine
+// with 64 x 64 tiles), DFMA.
+template <int T>
 __global__ void __launch_bounds__(256) gemm_generic_kernel(const double* __restrict__ Om, int64_t osi, int64_t osk,
                                                            const double* __restrict__ A, int64_t sk, int64_t sj,
                                                            int64_t l, int64_t n, int64_t K, double* __restrict__ C,
                                                            int64_t ldc) {
-  __shared__ double Os[16][65];
-  __shared__ double As[16][65];
+  constexpr int MT = T / 16;          // micro-tile edge
+  __shared__ double Os[16][T + 1];
+  __shared__ double As[16][T + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int64_t i0 = (int64_t)blockIdx.y * 64, j0 = (int64_t)blockIdx.x * 64;
-  double acc[4][4] = {};
+  const int64_t i0 = (int64_t)blockIdx.y * T, j0 = (int64_t)blockIdx.x * T;
+  double acc[MT][MT] = {};
   for (int64_t k0 = 0; k0 < K; k0 += 16) {
-    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+    for (int e = threadIdx.x; e < 16 * T; e += 256) {
       // let the unit-stride index vary fastest across threads
-      int kk = (osk == 1) ? e % 16 : e / 64, ii = (osk == 1) ? e / 16 : e % 64;
+      int kk = (osk == 1) ? e % 16 : e / T, ii = (osk == 1) ? e / 16 : e % T;
       int64_t k = k0 + kk;
       Os[kk][ii] = (k < K && i0 + ii < l) ? Om[(i0 + ii) * osi + k * osk] : 0.0;
-      int kk2 = (sk == 1) ? e % 16 : e / 64, jj2 = (sk == 1) ? e / 16 : e % 64;
+      int kk2 = (sk == 1) ? e % 16 : e / T, jj2 = (sk == 1) ? e / 16 : e % T;
       int64_t k2 = k0 + kk2;
       As[kk2][jj2] = (k2 < K && j0 + jj2 < n) ? A[k2 * sk + (j0 + jj2) * sj] : 0.0;
     }
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
-      double o[4], a[4];
+      double o[MT], a[MT];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < MT; ++u) {
         o[u] = Os[kk][tx + 16 * u];
         a[u] = As[kk][ty + 16 * u];
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < MT; ++u)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) acc[u][v] = fma(o[u], a[v], acc[u][v]);
+        for (int v = 0; v < MT; ++v) acc[u][v] = fma(o[u], a[v], acc[u][v]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
+  for (int u = 0; u < MT; ++u)
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
+    for (int v = 0; v < MT; ++v) {
       int64_t i = i0 + tx + 16 * u, j = j0 + ty + 16 * v;
       if (i < l && j < n) C[i + j * ldc] = acc[u][v];
     }
@@ -506,9 +510,14 @@ int bra_gemm_tn(bra_ctx* ctx, const double* Omt, int64_t ldt, int64_t l, int64_t
 int bra_gemm_generic(bra_ctx* ctx, const double* Om, int64_t osi, int64_t osk, const double* A, int64_t sk,
                      int64_t sj, int64_t l, int64_t n, int64_t K, double* C, int64_t ldc) {
   if (l <= 0 || n <= 0) return BRA_OK;
-  dim3 grid((unsigned)((n + 63) / 64), (unsigned)((l + 63) / 64));
   ProfScope ps(ctx, ctx->gemm_tag);
-  gemm_generic_kernel<<<grid, 256, 0, ctx->stream>>>(Om, osi, osk, A, sk, sj, l, n, K, C, ldc);
+  if (((n + 63) / 64) * ((l + 63) / 64) < 2 * (int64_t)ctx->num_sms) {
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((l + 31) / 32));
+    gemm_generic_kernel<32><<<grid, 256, 0, ctx->stream>>>(Om, osi, osk, A, sk, sj, l, n, K, C, ldc);
+  } else {
+    dim3 grid((unsigned)((n + 63) / 64), (unsigned)((l + 63) / 64));
+    gemm_generic_kernel<64><<<grid, 256, 0, ctx->stream>>>(Om, osi, osk, A, sk, sj, l, n, K, C, ldc);
+  }
   ctx->launches++;
   BRA_CUDA(cudaGetLastError());
   return BRA_OK;

@@ -118,70 +118,61 @@ __global__ void __launch_bounds__(256) trsolve_right_upper_kernel(int64_t rows, 
 }
 
 // ---- blocked Cholesky G = L L^T (lower, in place), k x k ----
-// panel: every CTA factors the 32x32 diagonal block redundantly in smem, then solves its own 32-row block.
-__global__ void __launch_bounds__(256) chol_panel_kernel(int k, int j0, double* __restrict__ G, int64_t ldg, int* info) {
-  __shared__ double D[TB][TB + 1];
-  __shared__ double P[TB][TB + 1];
-  const int tid = threadIdx.x;
+// panel: ONE WARP per 32-row block.  Lane r keeps row r of the 32 x 32 diagonal block in registers and factors it
+// with shuffles (no shared memory, no barriers, reciprocal square roots instead of sqrt + divide); every warp does
+// this redundantly, then solves its own row block X L_jj^T = P in "axpy" form (independent FMAs per column instead of
+// a dependent dot-product chain), reading L_jj straight from the factoring lanes' registers.
+__global__ void __launch_bounds__(32) chol_panel_kernel(int k, int j0, double* __restrict__ G, int64_t ldg, int* info) {
+  const int lane = threadIdx.x;
   const int jbsz = min(TB, k - j0);
-  for (int e = tid; e < TB * TB; e += 256) {
-    const int rr = e & 31, cc = e >> 5;
-    D[rr][cc] = (rr < jbsz && cc < jbsz) ? G[(j0 + rr) + (int64_t)(j0 + cc) * ldg] : (rr == cc ? 1.0 : 0.0);
-  }
-  __syncthreads();
-  {
-    // unblocked Cholesky of the 32 x 32 block, all 256 threads: per column one pivot, one scaling, one rank-1
-    // update of the trailing part (thread (r, cc4) owns entries D[r][cc4*4 .. cc4*4+3])
-    const int r = tid & 31, c4 = tid >> 5;
-    for (int c = 0; c < TB; ++c) {
-      double d = D[c][c];
-      if (!(d > 0.0)) {
-        if (tid == 0 && c < jbsz) atomicExch(info, j0 + c + 1);
-        d = 1.0;
-      }
-      const double piv = sqrt(d);
-      __syncthreads();
-      if (tid == c) D[c][c] = piv;
-      if (tid > c && tid < TB) D[tid][c] = D[tid][c] / piv;
-      __syncthreads();
-      if (r > c) {
-        const double lrc = D[r][c];
+  double a[TB];      // row `lane` of the diagonal block (lower triangle meaningful)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int cc = c4 * 4 + u;
-          if (cc > c && cc <= r) D[r][cc] = fma(-lrc, D[cc][c], D[r][cc]);
-        }
-      }
-      __syncthreads();
+  for (int c = 0; c < TB; ++c)
+    a[c] = (lane < jbsz && c < jbsz) ? G[(j0 + lane) + (int64_t)(j0 + c) * ldg] : (lane == c ? 1.0 : 0.0);
+  double rs[TB];     // 1 / L[c][c]
+#pragma unroll
+  for (int c = 0; c < TB; ++c) {
+    double d = __shfl_sync(0xffffffffu, a[c], c);
+    if (!(d > 0.0)) {
+      if (lane == 0 && c < jbsz) atomicExch(info, j0 + c + 1);
+      d = 1.0;
+    }
+    rs[c] = rsqrt(d);
+    const double l = (lane == c) ? d * rs[c] : a[c] * rs[c];      // column c of L (rows >= c meaningful)
+    a[c] = l;
+#pragma unroll
+    for (int cc = c + 1; cc < TB; ++cc) {
+      const double lcc = __shfl_sync(0xffffffffu, l, cc);           // L[cc][c]
+      a[cc] = fma(-l, lcc, a[cc]);
     }
   }
   const int rb = blockIdx.x;        // 0: the diagonal block itself; b > 0: row block j0 + 32*b
   if (rb == 0) {
-    for (int e = tid; e < TB * TB; e += 256) {
-      const int rr = e & 31, cc = e >> 5;
-      if (rr < jbsz && cc < jbsz) G[(j0 + rr) + (int64_t)(j0 + cc) * ldg] = (rr >= cc) ? D[rr][cc] : 0.0;
+    if (lane < jbsz) {
+#pragma unroll
+      for (int c = 0; c < TB; ++c)
+        if (c < jbsz) G[(j0 + lane) + (int64_t)(j0 + c) * ldg] = (lane >= c) ? a[c] : 0.0;
     }
     return;
   }
   const int r0 = j0 + rb * TB;
-  for (int e = tid; e < TB * TB; e += 256) {
-    const int rr = e & 31, cc = e >> 5;
-    P[rr][cc] = (r0 + rr < k && cc < jbsz) ? G[(r0 + rr) + (int64_t)(j0 + cc) * ldg] : 0.0;
-  }
-  __syncthreads();
-  if (tid < 32) {
-    // X L_jj^T = P: forward substitution along columns, one row per lane
-    const int r = tid;
-    for (int c = 0; c < TB; ++c) {
-      double x = P[r][c];
-      for (int cc = 0; cc < c; ++cc) x = fma(-P[r][cc], D[c][cc], x);
-      P[r][c] = x / D[c][c];
+  const bool live = (r0 + lane < k);
+  double x[TB];      // row `lane` of the row block
+#pragma unroll
+  for (int c = 0; c < TB; ++c) x[c] = (live && c < jbsz) ? G[(r0 + lane) + (int64_t)(j0 + c) * ldg] : 0.0;
+#pragma unroll
+  for (int c = 0; c < TB; ++c) {
+    x[c] *= rs[c];
+#pragma unroll
+    for (int cc = c + 1; cc < TB; ++cc) {
+      const double lcc = __shfl_sync(0xffffffffu, a[c], cc);        // L[cc][c] lives in lane cc
+      x[cc] = fma(-x[c], lcc, x[cc]);
     }
   }
-  __syncthreads();
-  for (int e = tid; e < TB * TB; e += 256) {
-    const int rr = e & 31, cc = e >> 5;
-    if (r0 + rr < k && cc < jbsz) G[(r0 + rr) + (int64_t)(j0 + cc) * ldg] = P[rr][cc];
+  if (live) {
+#pragma unroll
+    for (int c = 0; c < TB; ++c)
+      if (c < jbsz) G[(r0 + lane) + (int64_t)(j0 + c) * ldg] = x[c];
   }
 }
 
@@ -304,9 +295,7 @@ __device__ __forceinline__ void team_sync(int team) {
 //   cs = sqrt((1 + cos 2theta) / 2),  sn = sin(2 theta) / (2 cs)         (|theta| <= pi/4)
 template <int TS, int R>
 __device__ __forceinline__ bool rotate_pair(double* __restrict__ Xs, double* __restrict__ Js, int kp, int k, int p, int q,
-                                            int team, int e, double* __restrict__ rb, double tol2, long long* tk) {
-#define RTICK(i) if (tk) { long long _t = clock64(); tk[i] += _t - tk[7]; tk[7] = _t; }
-  RTICK(6)
+                                            int team, int e, double* __restrict__ rb, double tol2, double thr2, int* s_big) {
   constexpr int WPT = TS / 32;
   const int lane = e & 31, tw = e >> 5;
   double* xp = Xs + (size_t)p * kp;
@@ -331,7 +320,6 @@ __device__ __forceinline__ bool rotate_pair(double* __restrict__ Xs, double* __r
   a += a1;
   b += b1;
   c += c1;
-  RTICK(0)
   // warp reduction of the three sums with 6 exchanges instead of 15: after the xor-16 stage a lane keeps (a, c) or
   // (b, -), after the xor-8 stage one value; lane 0 ends with a, lane 8 with c, lane 16 with b.
   {
@@ -355,8 +343,6 @@ __device__ __forceinline__ bool rotate_pair(double* __restrict__ Xs, double* __r
       b = __shfl_sync(0xffffffffu, w, 16);
     }
   }
-  RTICK(1)
-  RTICK(2)
   if (tw == (team % WPT)) {
     if (WPT > 1) {
       a = b = c = 0.0;
@@ -368,7 +354,9 @@ __device__ __forceinline__ bool rotate_pair(double* __restrict__ Xs, double* __r
       }
     }
     double cs = 1.0, sn = 2.0;
-    if (c * c > tol2 * a * b) {          // converged pair: |c| <= tol * sqrt(a b)
+    const double ab = a * b, cc2 = c * c;
+    if (cc2 > thr2 * ab && lane == 0) *s_big = 1;      // a rotation that is NOT tiny (see the convergence vote)
+    if (cc2 > tol2 * ab) {               // converged pair: |c| <= tol * sqrt(a b)
       const double d = b - a, c2 = 2.0 * c;
       const double rh = rsqrt(fma(d, d, c2 * c2));
       const double hc = fma(0.5 * fabs(d), rh, 0.5);          // (1 + cos 2theta) / 2  in [1/2, 1]
@@ -381,10 +369,8 @@ __device__ __forceinline__ bool rotate_pair(double* __restrict__ Xs, double* __r
       rb[WPT * 4 + 1] = sn;
     }
   }
-  RTICK(3)
   team_sync<TS>(team);
   const double cs = rb[WPT * 4 + 0], sn = rb[WPT * 4 + 1];
-  RTICK(4)
   if (sn == 2.0) return false;
   double* jp = Js + (size_t)p * kp;
   double* jq = Js + (size_t)q * kp;
@@ -399,137 +385,215 @@ __device__ __forceinline__ bool rotate_pair(double* __restrict__ Xs, double* __r
       jq[r] = fma(sn, ju, cs * jv);
     }
   }
-  RTICK(5)
   return true;
-#undef RTICK
 }
 
 // BC = column pairs per panel (= columns per block), TS = threads per pair, R = rows per thread (k <= TS * R)
+//
+// Ordering: ODD-EVEN TRANSPOSITION over the nblk block positions (Luk & Park): even steps pair positions (2i, 2i+1),
+// odd steps (2i+1, 2i+2); after every step the two blocks of a pair swap positions.  nblk steps make a sweep in which
+// every pair of blocks meets exactly once.  CTA i owns pair i of the current step, so between steps it KEEPS one of
+// its two blocks in shared memory and exchanges only the other one with a neighbour (half the traffic of a
+// round-robin tournament, where both blocks move every step).
 template <int BC, int TS, int R>
 __global__ void __launch_bounds__(BC * TS, 1) jacobi_team_kernel(JacobiParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int NT = BC * TS;
   constexpr int NC = 2 * BC;                       // columns in a panel
   constexpr int WPT = TS / 32;                     // warps per team
   constexpr int RBS = WPT * 4 + 2;                 // doubles of reduction scratch per team and parity
-  const int k = P.k, tid = threadIdx.x;
+  const int k = P.k, tid = threadIdx.x, N = P.nblk, cta = blockIdx.x, NP = N / 2;
   const int kp = (k + 1) & ~1;                     // padded column length (16-byte aligned columns)
-  double* Xs = reinterpret_cast<double*>(smem_raw);             // [NC][kp]
+  double* Xs = reinterpret_cast<double*>(smem_raw);             // [NC][kp]   slot s = columns s*BC .. s*BC+BC-1
   double* Js = Xs + (size_t)NC * kp;                             // [NC][kp]
   double* red = Js + (size_t)NC * kp;                            // [2][BC][RBS]
-  __shared__ int s_rot;
+  int* perm = reinterpret_cast<int*>(red + (size_t)2 * BC * RBS);   // [N] block id at each position
+  __shared__ int s_rot, s_big;
   const int team = tid / TS, e = tid % TS;
-  const int nsteps = P.nblk - 1;
   const double tol2 = P.tol * P.tol;
+  const double thr2 = P.tol / (4.0 * k);           // "tiny rotation": |cos| <= sqrt(tol / 4k)
+  for (int i = tid; i < N; i += BC * TS) perm[i] = i;
+  int spos[2] = {-1, -1};                          // position held by each slot (-1: slot empty)
   unsigned epoch = 0, gstep = 0;
   int sweep = 0, converged = 0;
   long long tph[4] = {0, 0, 0, 0}, tlast = clock64();
-  long long rtk[8] = {0, 0, 0, 0, 0, 0, 0, clock64()};
 #define JTICK(i) if (tid == 0) { long long _t = clock64(); tph[i] += _t - tlast; tlast = _t; }
-  for (; sweep < P.max_sweeps; ++sweep) {
-    if (tid == 0) s_rot = 0;
-    bool rot_any = false;
-    for (int st = 0; st < nsteps; ++st, ++gstep) {
-      int bI, bJ;
-      rr_pair(P.nblk, st, blockIdx.x, bI, bJ);
-      // ---- wait until both blocks have finished step gstep-1 (point to point, no grid barrier) ----
-      if (tid < 2) {
-        const unsigned* f = P.bstep + (tid == 0 ? bI : bJ);
-        unsigned v;
-        do {
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-        } while (v < gstep);
+  // copy one block between its home in global memory and a slot (team t moves column t of the block)
+  auto load_slot = [&](int slot, int blk) {
+    const int gc = blk * BC + team;
+    double* xs = Xs + (size_t)(slot * BC + team) * kp;
+    double* js = Js + (size_t)(slot * BC + team) * kp;
+    if (gc < k) {
+      const double* gx = P.X + (int64_t)gc * P.ldx;
+      const double* gj = P.J + (int64_t)gc * P.ldj;
+      for (int r = 2 * e; r < kp; r += 2 * TS) {
+        cp_async16(xs + r, gx + r);
+        cp_async16(js + r, gj + r);
       }
-      __syncthreads();
-      JTICK(0)
-      // ---- stage the panel (L2 -> smem with cp.async.cg: no L1, other CTAs wrote these columns earlier) ----
-      // team t stages its own two columns (t of block I, t of block J) of X and of J: no index arithmetic
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int lc = h * BC + team;
-        const int gc = (h == 0 ? bI : bJ) * BC + team;
-        double* xs = Xs + (size_t)lc * kp;
-        double* js = Js + (size_t)lc * kp;
-        if (gc < k) {
-          const double* gx = P.X + (int64_t)gc * P.ldx;
-          const double* gj = P.J + (int64_t)gc * P.ldj;
-          for (int r = 2 * e; r < kp; r += 2 * TS) {
-            cp_async16(xs + r, gx + r);
-            cp_async16(js + r, gj + r);
+    } else {
+      for (int r = e; r < kp; r += TS) {
+        xs[r] = 0.0;
+        js[r] = 0.0;
+      }
+    }
+  };
+  auto store_slot = [&](int slot, int blk) {
+    const int gc = blk * BC + team;
+    if (gc < k) {
+      const double2* xs = reinterpret_cast<const double2*>(Xs + (size_t)(slot * BC + team) * kp);
+      const double2* js = reinterpret_cast<const double2*>(Js + (size_t)(slot * BC + team) * kp);
+      double2* gx = reinterpret_cast<double2*>(P.X + (int64_t)gc * P.ldx);
+      double2* gj = reinterpret_cast<double2*>(P.J + (int64_t)gc * P.ldj);
+      for (int r = e; r < kp / 2; r += TS) {
+        __stcg(gx + r, xs[r]);
+        __stcg(gj + r, js[r]);
+      }
+    }
+  };
+  auto pair_of = [&](unsigned g, int& pL, int& pR) {       // positions CTA `cta` works on at step g (pL < 0: idle)
+    if ((g & 1) == 0) {
+      pL = 2 * cta;
+      pR = 2 * cta + 1;
+    } else if (cta < NP - 1) {
+      pL = 2 * cta + 1;
+      pR = 2 * cta + 2;
+    } else {
+      pL = pR = -1;
+    }
+  };
+  __syncthreads();
+  for (; sweep < P.max_sweeps; ++sweep) {
+    if (tid == 0) {
+      s_rot = 0;
+      s_big = 0;
+    }
+    bool rot_any = false;
+    for (int st = 0; st < N; ++st, ++gstep) {
+      int pL, pR;
+      pair_of(gstep, pL, pR);
+      if (pL >= 0) {
+        // ---- fetch the block(s) this step needs and the CTA does not hold ----
+        int sl = (spos[0] == pL) ? 0 : (spos[1] == pL ? 1 : -1);
+        int sr = (spos[0] == pR) ? 0 : (spos[1] == pR ? 1 : -1);
+        const bool needL = sl < 0, needR = sr < 0;
+        if (needL) sl = (sr == 0) ? 1 : 0;
+        if (needR) sr = 1 - sl;
+        if (needL || needR) {
+          if (tid < 2) {
+            // block at position p was last written after step gstep-1, or gstep-2 if it idled at an end position
+            const bool mine = (tid == 0) ? needL : needR;
+            const int pp = (tid == 0) ? pL : pR;
+            if (mine) {
+              const bool idled = (gstep > 0) && ((gstep - 1) & 1) && (pp == 0 || pp == N - 1);
+              const unsigned want = idled ? gstep - 1 : gstep;
+              const unsigned* f = P.bstep + perm[pp];
+              unsigned v;
+              do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+              } while (v < want);
+            }
           }
-        } else {
-          for (int r = e; r < kp; r += TS) {
-            xs[r] = 0.0;
-            js[r] = 0.0;
+          __syncthreads();
+          JTICK(0)
+          if (needL) load_slot(sl, perm[pL]);
+          if (needR) load_slot(sr, perm[pR]);
+          asm volatile("cp.async.wait_all;" ::: "memory");
+          __syncthreads();
+          JTICK(1)
+        }
+        spos[sl] = pL;
+        spos[sr] = pR;
+        int par = 0;
+        // ---- once per sweep: the pairs INSIDE each of the two blocks (round-robin over BC columns, both blocks at
+        // once: teams 0..BC/2-1 take slot 0, the rest slot 1) ----
+        if (st == 0 && BC > 1) {
+          for (int rd = 0; rd < BC - 1; ++rd, par ^= 1) {
+            int p, q;
+            rr_pair(BC, rd, team % (BC / 2 > 0 ? BC / 2 : 1), p, q);
+            const int off = (team < BC / 2) ? 0 : BC;
+            rot_any |= rotate_pair<TS, R>(Xs, Js, kp, k, off + p, off + q, team, e, red + (size_t)(par * BC + team) * RBS,
+                                          tol2, thr2, &s_big);
+            __syncthreads();
           }
         }
-      }
-      asm volatile("cp.async.wait_all;" ::: "memory");
-      __syncthreads();
-      JTICK(1)
-      int par = 0;
-      // ---- once per sweep: the pairs INSIDE each of the two blocks (round-robin over BC columns, both blocks at
-      // once: teams 0..BC/2-1 take block I, the rest block J) ----
-      if (st == 0 && BC > 1) {
-        for (int rd = 0; rd < BC - 1; ++rd, par ^= 1) {
-          int p, q;
-          rr_pair(BC, rd, team % (BC / 2 > 0 ? BC / 2 : 1), p, q);
-          const int off = (team < BC / 2) ? 0 : BC;
-          rot_any |= rotate_pair<TS, R>(Xs, Js, kp, k, off + p, off + q, team, e, red + (size_t)(par * BC + team) * RBS, tol2, tid == 0 ? rtk : nullptr);
+        // ---- every step: each column of one block meets each column of the other once (BC rounds of BC disjoint pairs) ----
+        for (int rd = 0; rd < BC; ++rd, par ^= 1) {
+          const int p = team, q = BC + ((team + rd) % BC);
+          rot_any |= rotate_pair<TS, R>(Xs, Js, kp, k, p, q, team, e, red + (size_t)(par * BC + team) * RBS, tol2, thr2,
+                                        &s_big);
           __syncthreads();
         }
+        JTICK(2)
+        // the two blocks swap positions
+        spos[sl] = pR;
+        spos[sr] = pL;
       }
-      // ---- every step: each column of block I meets each column of block J once (BC rounds of BC disjoint pairs) ----
-      for (int rd = 0; rd < BC; ++rd, par ^= 1) {
-        const int p = team, q = BC + ((team + rd) % BC);
-        rot_any |= rotate_pair<TS, R>(Xs, Js, kp, k, p, q, team, e, red + (size_t)(par * BC + team) * RBS, tol2, tid == 0 ? rtk : nullptr);
-        __syncthreads();
-      }
-      JTICK(2)
-      // ---- write the panel back, then publish "block finished step gstep" ----
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int lc = h * BC + team;
-        const int gc = (h == 0 ? bI : bJ) * BC + team;
-        if (gc < k) {
-          const double2* xs = reinterpret_cast<const double2*>(Xs + (size_t)lc * kp);
-          const double2* js = reinterpret_cast<const double2*>(Js + (size_t)lc * kp);
-          double2* gx = reinterpret_cast<double2*>(P.X + (int64_t)gc * P.ldx);
-          double2* gj = reinterpret_cast<double2*>(P.J + (int64_t)gc * P.ldj);
-          for (int r = e; r < kp / 2; r += TS) {
-            __stcg(gx + r, xs[r]);
-            __stcg(gj + r, js[r]);
-          }
+      // every CTA replays the whole permutation (N <= a few hundred entries)
+      {
+        const int npairs = ((gstep & 1) == 0) ? NP : NP - 1, o = (int)(gstep & 1);
+        for (int i = tid; i < npairs; i += BC * TS) {
+          const int t0 = perm[2 * i + o];
+          perm[2 * i + o] = perm[2 * i + o + 1];
+          perm[2 * i + o + 1] = t0;
         }
       }
       __syncthreads();
-      if (tid < 2) {        // st.release.gpu is cumulative over the CTA barrier above: no separate fence
-        unsigned* f = P.bstep + (tid == 0 ? bI : bJ);
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(f), "r"(gstep + 1) : "memory");
+      // ---- hand over: a held block that this CTA does not work on at the next step goes back to global memory ----
+      {
+        int nL, nR;
+        pair_of(gstep + 1, nL, nR);
+        bool sent[2] = {false, false};
+        int sblk[2] = {0, 0};
+        unsigned sver[2] = {0, 0};
+#pragma unroll
+        for (int sidx = 0; sidx < 2; ++sidx) {
+          const int pp = spos[sidx];
+          if (pp >= 0 && pp != nL && pp != nR) {
+            sent[sidx] = true;
+            sblk[sidx] = perm[pp];
+            // an end position idles during the next (odd) step: its next reader is two steps away
+            const bool idles = (((gstep + 1) & 1) != 0) && (pp == 0 || pp == N - 1);
+            sver[sidx] = gstep + 1 + (idles ? 1u : 0u);
+            store_slot(sidx, sblk[sidx]);
+            spos[sidx] = -1;
+          }
+        }
+        if (sent[0] || sent[1]) {
+          __syncthreads();
+          if (tid < 2 && sent[tid]) {       // st.release.gpu is cumulative over the CTA barrier above
+            unsigned* f = P.bstep + sblk[tid];
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(f), "r"(sver[tid]) : "memory");
+          }
+        }
       }
       JTICK(3)
     }
-    // ---- convergence vote: one grid barrier per sweep ----
+    // ---- convergence vote: one grid barrier per sweep.  Converged when no pair rotated, or when every rotation of
+    // the sweep was tiny (|cos| <= sqrt(tol/4k)): the perturbation a pair receives from the <= 2k later tiny rotations
+    // of its two columns is <= 2k * tol/4k = tol/2, so all cosines end below 1.5 tol and the confirming sweep is moot.
     if (rot_any) s_rot = 1;
     __syncthreads();
     if (tid == 0 && s_rot) atomicExch(P.rotated + sweep, 1);
+    if (tid == 0 && s_big) atomicExch(P.rotated + P.max_sweeps + sweep, 1);
     ++epoch;
     grid_barrier(P.bar, epoch * gridDim.x);
-    int any;
+    int any, big;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(any) : "l"(P.rotated + sweep) : "memory");
-    if (!any) {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(big) : "l"(P.rotated + P.max_sweeps + sweep) : "memory");
+    if (!any || !big) {
       converged = 1;
       ++sweep;
       break;
     }
   }
-  // report from the LAST CTA (CTA 0 often owns the zero-padded block and is not representative)
-  if (blockIdx.x == 0 && tid == 0)
-    for (int i = 0; i < 7; ++i) P.out[16 + i] = (int)(rtk[i] >> 10);
-  if (blockIdx.x == gridDim.x - 1 && tid == 0) {
+  // ---- blocks still held go home ----
+#pragma unroll
+  for (int sidx = 0; sidx < 2; ++sidx)
+    if (spos[sidx] >= 0) store_slot(sidx, perm[spos[sidx]]);
+  // report from a middle CTA (the end CTAs idle or hold the zero-padded block and are not representative)
+  if (cta == gridDim.x / 2 && tid == 0) {
     P.out[0] = sweep;
     P.out[1] = converged;
-    for (int i = 0; i < 4; ++i) P.out[2 + i] = (int)(tph[i] >> 10);     // kilo-cycles: wait, load, rotate, store
+    for (int i = 0; i < 4; ++i) P.out[2 + i] = (int)(tph[i] >> 10);     // kilo-cycles: wait, load, rotate, hand-over
     for (int i = 4; i < 8; ++i) P.out[2 + i] = 0;
   }
 #undef JTICK
@@ -606,7 +670,7 @@ int bra_trsolve_right_upper(bra_ctx* ctx, int64_t rows, int k, const double* R, 
     set_identity_kernel<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(k, Rinv, ldk);
     ctx->launches++;
   }
-  if ((rc = bra_trsolve_upper(ctx, k, k, R, ldr, Rinv, ldk))) return rc;                   // Rinv = R^{-1}
+  if ((rc = bra_tri_inverse_upper(ctx, k, R, ldr, Rinv, ldk))) return rc;                 // Rinv = R^{-1}
   if ((rc = bra_transpose(ctx, Y, ldy, rows, k, Yt, ldk))) return rc;                       // Y' (k x rows)
   if ((rc = bra_gemm_tn(ctx, Rinv, ldk, k, k, Yt, ldk, rows, Ct, ldk))) return rc;          // (Y Rinv)' = Rinv' Y'
   return bra_transpose(ctx, Ct, ldk, k, rows, Y, ldy);
@@ -622,7 +686,7 @@ int bra_cholesky_upper(bra_ctx* ctx, int k, double* G, int64_t ldg, double* Rout
   for (int jb = 0; jb < nblk; ++jb) {
     const int j0 = jb * TB;
     const int rowblocks = nblk - jb;
-    chol_panel_kernel<<<rowblocks, 256, 0, ctx->stream>>>(k, j0, G, ldg, info);
+    chol_panel_kernel<<<rowblocks, 32, 0, ctx->stream>>>(k, j0, G, ldg, info);
     const int nb = nblk - jb - 1;
     if (nb > 0) chol_update_kernel<<<nb * (nb + 1) / 2, 256, 0, ctx->stream>>>(k, j0, G, ldg);
     ctx->launches += 2;
@@ -710,7 +774,7 @@ int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64
     }
     const size_t kp = (size_t)((k + 1) & ~1);
     const size_t budget = (size_t)ctx->smem_optin - 2048;
-    auto need = [&](int b) { return (size_t)32 * b * kp + (size_t)2 * b * ((ts / 32) * 4 + 2) * 8 + 64; };
+    auto need = [&](int b) { return (size_t)32 * b * kp + (size_t)2 * b * ((ts / 32) * 4 + 2) * 8 + (size_t)4 * (2 * ((k + 2 * b - 1) / (2 * b))) + 64; };
     while (bc > 1 && (need(bc) > budget || k <= bc)) bc >>= 1;   // tiny cores: keep at least two blocks of real columns
     if (need(bc) > budget) {
       ctx->set_error("Jacobi SVD: k too large for the shared-memory panel");
@@ -727,7 +791,7 @@ int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64
     }
     const int grid = nblk / 2;
     const size_t smem = need(bc);
-    const size_t wbytes = 1024 + (size_t)MAX_SWEEPS * 4 + (size_t)nblk * 4;
+    const size_t wbytes = 1024 + (size_t)2 * MAX_SWEEPS * 4 + (size_t)nblk * 4;
     BRA_CUDA(ctx->jwork.reserve(wbytes));
     BRA_CUDA(cudaMemsetAsync(ctx->jwork.p, 0, wbytes, ctx->stream));
     JacobiParams P;
@@ -742,7 +806,7 @@ int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64
     P.bar = ctx->jwork.as<unsigned>();
     P.out = ctx->jwork.as<int>() + 16;
     P.rotated = ctx->jwork.as<int>() + 64;
-    P.bstep = ctx->jwork.as<unsigned>() + 256 + MAX_SWEEPS;
+    P.bstep = ctx->jwork.as<unsigned>() + 256 + 2 * MAX_SWEEPS;
     cudaError_t e = cudaErrorInvalidValue;
 #define JL(B_, T_, R_) if (bc == B_ && ts == T_ && rr == R_) e = launch_jacobi<B_, T_, R_>(P, grid, smem, ctx->stream);
     JL(8, 32, 4) JL(4, 32, 4) JL(2, 32, 4) JL(1, 32, 4)
@@ -755,13 +819,12 @@ int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64
 #undef JL
     BRA_CUDA(e);
     ctx->launches++;
-    int h[24] = {0};
-    BRA_CUDA(cudaMemcpyAsync(h, P.out, 96, cudaMemcpyDeviceToHost, ctx->stream));
+    int h[10] = {0};
+    BRA_CUDA(cudaMemcpyAsync(h, P.out, 40, cudaMemcpyDeviceToHost, ctx->stream));
     BRA_CUDA(cudaStreamSynchronize(ctx->stream));
     sweeps = h[0];
     converged = h[1];
     for (int i = 0; i < 8; ++i) ctx->jacobi_kcycles[i] = h[2 + i];
-    if (getenv("BRA_JACOBI_TICKS")) fprintf(stderr, "jacobi round ticks (kcyc, CTA0 thread0): dots %d shfl %d sync1 %d math %d sync2 %d apply %d between %d\n", h[16], h[17], h[18], h[19], h[20], h[21], h[22]);
   }
   ctx->last_jacobi_sweeps = sweeps;
   BRA_CUDA(ctx->S.reserve((size_t)k * 8));

@@ -11,33 +11,48 @@ namespace {
 
 constexpr int TB = 32;
 
+// NC = right-hand sides per CTA (32: the ID solve, thousands of columns; 8: k x k problems, where 32-wide panels
+// would leave most of the machine idle).  UPPER_RHS: the right-hand side is itself upper triangular (the identity,
+// when R11^{-1} is wanted), so rows below the panel's last column are zero and the walk starts at that block row.
+template <int NC, bool UPPER_RHS>
 __global__ void __launch_bounds__(256) trsolve_upper_kernel(int k, int64_t nrhs, const double* __restrict__ R,
                                                             int64_t ldr, double* __restrict__ X, int64_t ldx) {
+  constexpr int NG = 256 / NC;        // row groups
+  constexpr int RPT = TB / NG;        // rows per thread in a 32-row block
+  static_assert(RPT >= 1 && RPT * NG == TB, "NC must be 8, 16 or 32");
   __shared__ double Rs[TB][TB + 1];   // Rs[r][c] = R[ib*32 + r, jb*32 + c]
-  __shared__ double Xs[TB][TB + 1];   // Xs[r][c] = X[jb*32 + r, col0 + c]
-  __shared__ double Acc[TB][TB + 1];
+  __shared__ double Xs[TB][NC + 1];   // Xs[r][c] = X[jb*32 + r, col0 + c]
+  __shared__ double Acc[TB][NC + 1];
   const int tid = threadIdx.x;
-  const int tx = tid & 31;            // rhs column within the panel
-  const int ty = tid >> 5;            // row group: rows ty*4 .. ty*4+3
-  const int64_t col0 = (int64_t)blockIdx.x * TB;
+  const int tx = tid % NC;            // rhs column within the panel
+  const int ty = tid / NC;            // row group: rows ty*RPT .. ty*RPT+RPT-1
+  const int64_t col0 = (int64_t)blockIdx.x * NC;
   const int nblk = (k + TB - 1) / TB;
+  int ib_top = nblk - 1;
+  if (UPPER_RHS) {
+    const int64_t last = (col0 + NC - 1 < (int64_t)k - 1) ? col0 + NC - 1 : (int64_t)k - 1;
+    ib_top = (int)(last / TB);
+  }
 
-  for (int ib = nblk - 1; ib >= 0; --ib) {
+  for (int ib = ib_top; ib >= 0; --ib) {
     const int r0 = ib * TB;
-    double acc[4];
+    double acc[RPT];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int r = r0 + ty * 4 + u;
+    for (int u = 0; u < RPT; ++u) {
+      const int r = r0 + ty * RPT + u;
       acc[u] = (r < k && col0 + tx < nrhs) ? X[r + (col0 + tx) * ldx] : 0.0;
     }
-    for (int jb = ib + 1; jb < nblk; ++jb) {
+    for (int jb = ib + 1; jb <= ib_top; ++jb) {
       const int c0 = jb * TB;
       __syncthreads();
       for (int e = tid; e < TB * TB; e += 256) {
         const int rr = e & 31, cc = e >> 5;
         const int r = r0 + rr, c = c0 + cc;
         Rs[rr][cc] = (r < k && c < k) ? R[r + (int64_t)c * ldr] : 0.0;
+      }
+      for (int e = tid; e < TB * NC; e += 256) {
         // X rows of block jb were finalised earlier by this same CTA
+        const int rr = e % TB, cc = e / TB;
         const int xr = c0 + rr;
         Xs[rr][cc] = (xr < k && col0 + cc < nrhs) ? X[xr + (col0 + cc) * ldx] : 0.0;
       }
@@ -46,18 +61,18 @@ __global__ void __launch_bounds__(256) trsolve_upper_kernel(int k, int64_t nrhs,
       for (int kk = 0; kk < TB; ++kk) {
         const double x = Xs[kk][tx];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] = fma(-Rs[ty * 4 + u][kk], x, acc[u]);
+        for (int u = 0; u < RPT; ++u) acc[u] = fma(-Rs[ty * RPT + u][kk], x, acc[u]);
       }
     }
     __syncthreads();
-    // diagonal block: load R_ii, park acc in smem, one warp substitutes (lane = rhs column)
+    // diagonal block: load R_ii, park acc in smem, NC threads substitute (thread = rhs column)
     for (int e = tid; e < TB * TB; e += 256) {
       const int rr = e & 31, cc = e >> 5;
       const int r = r0 + rr, c = r0 + cc;
       Rs[rr][cc] = (r < k && c < k) ? R[r + (int64_t)c * ldr] : (rr == cc ? 1.0 : 0.0);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) Acc[ty * 4 + u][tx] = acc[u];
+    for (int u = 0; u < RPT; ++u) Acc[ty * RPT + u][tx] = acc[u];
     __syncthreads();
     if (ty == 0) {
       double x[TB];
@@ -84,8 +99,21 @@ __global__ void __launch_bounds__(256) trsolve_upper_kernel(int k, int64_t nrhs,
 // In place: X (k x nrhs, holds R12 on entry) <- R11^{-1} X
 int bra_trsolve_upper(bra_ctx* ctx, int k, int64_t nrhs, const double* R11, int64_t ldr, double* X, int64_t ldx) {
   if (k <= 0 || nrhs <= 0) return BRA_OK;
-  const unsigned grid = (unsigned)((nrhs + TB - 1) / TB);
-  trsolve_upper_kernel<<<grid, 256, 0, ctx->stream>>>(k, nrhs, R11, ldr, X, ldx);
+  if (nrhs >= 32 * (int64_t)ctx->num_sms) {
+    trsolve_upper_kernel<32, false><<<(unsigned)((nrhs + 31) / 32), 256, 0, ctx->stream>>>(k, nrhs, R11, ldr, X, ldx);
+  } else {
+    trsolve_upper_kernel<8, false><<<(unsigned)((nrhs + 7) / 8), 256, 0, ctx->stream>>>(k, nrhs, R11, ldr, X, ldx);
+  }
+  ctx->launches++;
+  BRA_CUDA(cudaGetLastError());
+  return BRA_OK;
+}
+
+// Rinv (k x k, ld ldx) <- R^{-1}; Rinv must hold the identity on entry.  The identity is upper triangular, so each
+// 8-column panel only walks the block rows at or above its own columns.
+int bra_tri_inverse_upper(bra_ctx* ctx, int k, const double* R, int64_t ldr, double* Rinv, int64_t ldx) {
+  if (k <= 0) return BRA_OK;
+  trsolve_upper_kernel<8, true><<<(unsigned)((k + 7) / 8), 256, 0, ctx->stream>>>(k, k, R, ldr, Rinv, ldx);
   ctx->launches++;
   BRA_CUDA(cudaGetLastError());
   return BRA_OK;
