@@ -390,11 +390,31 @@ int launch_gemm(bra_ctx* ctx, const CUtensorMap& mapA, const double* Omt, int64_
   }
   const int jt = (int)((n + TJ - 1) / TJ);
   const int itl = (int)((l + Cfg::TI - 1) / Cfg::TI);
-  // split-K so that the grid covers the machine about twice, each split >= 8 stages
-  int splits = (2 * ctx->num_sms + jt * itl - 1) / (jt * itl);
+  // split-K: every CTA does the same work, so a partial last wave is pure loss (352 tiles on 148 SMs run as 3
+  // waves at 79 %).  Pick the split count that minimises   waves(sp) * t_tile / sp  +  sp * t_reduce   with
+  // t_tile = one full-K tile at ~90 % of an SM's DMMA rate and t_reduce = writing and re-reading one set of partial
+  // sums; each split keeps >= 8 stages and the partial buffer stays under 512 MB.
   int64_t maxs = (m + 8 * KS - 1) / (8 * KS);
-  if (splits > maxs) splits = (int)maxs;
-  if (splits < 1) splits = 1;
+  if (maxs > 32) maxs = 32;
+  const int64_t memcap = (int64_t(512) << 20) / (l * n * 8 > 0 ? l * n * 8 : 1);
+  if (maxs > memcap) maxs = memcap;
+  if (maxs < 1) maxs = 1;
+  int splits = 1;
+  {
+    const int tiles = jt * itl, sms = ctx->num_sms;
+    const double t_tile = 2.0 * Cfg::TI * TJ * (double)m / 225e9;
+    const double t_red = 16.0 * (double)l * (double)n / 4e12 + 3e-6;
+    double best = 1e30;
+    for (int sp = 1; sp <= (int)maxs; ++sp) {
+      const int64_t total = (int64_t)tiles * sp;
+      const int64_t waves = (total + sms - 1) / sms;
+      const double t = (double)waves * t_tile / sp + (sp > 1 ? sp * t_red : 0.0);
+      if (t < best * 0.995) {
+        best = t;
+        splits = sp;
+      }
+    }
+  }
   int64_t kper = (m + splits - 1) / splits;
   kper = (kper + KS - 1) / KS * KS;
   splits = (int)((m + kper - 1) / kper);
