@@ -76,7 +76,28 @@ int sketch_randn_round(bra_ctx* ctx, char trans, int64_t m, int64_t n, const dou
   if (rc) return rc;
   BRA_CUDA(ctx->B.reserve((size_t)order * nA * 8));
   const int64_t ldt = (mA + 1) & ~int64_t(1);
-  if (trans == 'n') rc = bra_gemm_sketch(ctx, ctx->omega_t.as<double>(), order, mA, dA, lda, nA, ctx->B.as<double>(), order);
+  if (trans == 'n') {
+    if (ctx->Apanels_state == 0) {
+      // tall A: repack into row panels once per factorization if the device has room for the copy
+      ctx->Apanels_state = -1;
+      if (bra_gemm_wants_panels(dA, lda, mA, nA)) {
+        size_t fr = 0, tot = 0;
+        const size_t need = (size_t)bra_panel_bytes(mA, nA);
+        if (ctx->Apanels.cap >= need ||
+            (cudaMemGetInfo(&fr, &tot) == cudaSuccess && fr + ctx->Apanels.cap > need + need / 8 + (size_t(2) << 30))) {
+          BRA_CUDA(ctx->Apanels.reserve(need));
+          ProfScope ps(ctx, BRA_PROF_OMEGA);
+          if ((rc = bra_repack_panels(ctx, dA, lda, mA, nA, ctx->Apanels.as<double>()))) return rc;
+          ctx->Apanels_state = 1;
+        }
+      }
+    }
+    if (ctx->Apanels_state == 1)
+      rc = bra_gemm_sketch_panels(ctx, ctx->omega_t.as<double>(), order, mA, ctx->Apanels.as<double>(), nA,
+                                  ctx->B.as<double>(), order);
+    else
+      rc = bra_gemm_sketch(ctx, ctx->omega_t.as<double>(), order, mA, dA, lda, nA, ctx->B.as<double>(), order);
+  }
   else rc = bra_gemm_generic(ctx, ctx->omega_t.as<double>(), ldt, 1, dA, lda, 1, order, nA, mA, ctx->B.as<double>(), order);
   if (rc) return rc;
   // row-sharded A: B = sum over ranks of Omega_g * A_g  (one all-reduce of the l x n sketch per round)
@@ -238,7 +259,7 @@ int bra_destroy(bra_ctx* ctx) {
                     &ctx->vn2, &ctx->lpos, &ctx->fpend, &ctx->rec, &ctx->jpvt, &ctx->tau, &ctx->rdiag, &ctx->info,
                     &ctx->kbtrace, &ctx->R11, &ctx->T, &ctx->C, &ctx->Q, &ctx->R1, &ctx->Rfull, &ctx->W, &ctx->G,
                     &ctx->U, &ctx->S, &ctx->Vt, &ctx->Z, &ctx->scratch, &ctx->scratch2, &ctx->scratch3,
-                    &ctx->aux_in1, &ctx->aux_in2, &ctx->jwork, &ctx->At, &ctx->rinv, &ctx->yt};
+                    &ctx->aux_in1, &ctx->aux_in2, &ctx->jwork, &ctx->At, &ctx->rinv, &ctx->yt, &ctx->Apanels};
   for (DevBuf* b : bufs) b->release();
   bra_comm_destroy(ctx);
   if (ctx->h_info) cudaFreeHost(ctx->h_info);
@@ -358,6 +379,7 @@ int bra_sketch_randn_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const d
     BRA_CUDA(copy2d(ctx, ctx->scratch2.p, order, Omega, ldo, order, mA));
     oms[0] = ctx->scratch2.as<double>();
   }
+  ctx->Apanels_state = 0;
   rc = sketch_randn_round(ctx, trans, m, n, dA, dlda, &o, &rnd, 0, order);
   if (rc) return rc;
   BRA_CUDA(copy2d(ctx, B, ldb, ctx->B.p, order, order, nA));
@@ -409,6 +431,7 @@ static int sketch_structured(bra_ctx* ctx, int kind, char trans, int64_t m, int6
     rnd.idx = (const int64_t* const*)a2;
   }
   ctx->At_valid = false;
+  ctx->Apanels_state = -1;
   rc = sketch_round(ctx, trans, m, n, dA, dlda, &o, &rnd, 0, order);
   if (rc) return rc;
   BRA_CUDA(copy2d(ctx, B, ldb, ctx->B.p, order, order, nA));
@@ -506,6 +529,7 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
   res.m = (trans == 'n') ? m : n;
   res.n = nA;
   ctx->At_valid = false;
+  ctx->Apanels_state = 0;
   QrcpOut q = {0, 0, 0, 0};
   int64_t order = 0;
   if (o->sketchfact_adap || o->rank < 0) {

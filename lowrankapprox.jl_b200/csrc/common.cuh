@@ -92,6 +92,8 @@ struct bra_ctx {
   std::vector<unsigned char> h_meta;  // host scratch for fast-mode index/sign generation
   DevBuf At;                   // transposed copy of A for the (:left,:c) SRFT
   bool At_valid = false;
+  DevBuf Apanels;              // row-panel copy of a tall A for the Gaussian sketch (made once per factorization)
+  int Apanels_state = 0;       // 0: not tried, 1: valid, -1: not used (small A or not enough memory)
   // multi-GPU (comm.cu): NCCL communicator over the ranks that hold the row blocks of one tall matrix
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
@@ -170,6 +172,13 @@ int bra_gemm_sketch(bra_ctx* ctx, const double* Omt, int64_t l, int64_t m, const
 int bra_gemm_tn(bra_ctx* ctx, const double* X, int64_t ldx, int64_t l, int64_t m, const double* Y, int64_t ldy,
                 int64_t n, double* C, int64_t ldc);
 bool bra_gemm_tma_ok(const double* A, int64_t lda, int64_t m, int64_t n);
+bool bra_gemm_wants_panels(const double* A, int64_t lda, int64_t m, int64_t n);
+int64_t bra_panel_bytes(int64_t m, int64_t n);
+int bra_repack_panels(bra_ctx* ctx, const double* A, int64_t lda, int64_t m, int64_t n, double* P);
+int bra_gemm_sketch_panels(bra_ctx* ctx, const double* Omt, int64_t l, int64_t m, const double* P, int64_t n, double* B,
+                           int64_t ldb);
+bool bra_make_map_3d_f64(CUtensorMap* map, const double* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1,
+                         uint64_t s2, uint32_t b0, uint32_t b1);
 
 // comm.cu
 int bra_allreduce_sum_f64(bra_ctx* ctx, double* buf, int64_t count);

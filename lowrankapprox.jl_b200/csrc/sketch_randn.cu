@@ -49,6 +49,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
+          "r"(smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(d0), "+d"(d1)
@@ -76,7 +83,7 @@ template <int WA>
 __global__ void __launch_bounds__((GW + 1) * 32, 1)
 gemm_sketch_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapO,
                    int64_t m, int64_t n, int64_t l, int64_t kper, double* __restrict__ out, int64_t ldo,
-                   int64_t split_stride) {
+                   int64_t split_stride, int panel_h) {
   using Cfg = GemmCfg<WA>;
   constexpr int TI = Cfg::TI;
   constexpr int STAGES = Cfg::STAGES;
@@ -113,7 +120,13 @@ gemm_sketch_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         const int64_t k0 = kbeg + (int64_t)it * KS;
 #pragma unroll
         for (int c = 0; c < CHUNKS; ++c) {
-          tma_load_2d(st + c * (TJ + TI) * KC * 8, &mapA, (int)(k0 + c * KC), (int)j0, &full[s]);
+          const int64_t ka = k0 + c * KC;
+          if (panel_h) {        // A repacked into row panels (tall matrices): 3-D map (row in panel, column, panel)
+            const int64_t pn = ka / panel_h;
+            tma_load_3d(st + c * (TJ + TI) * KC * 8, &mapA, (int)(ka - pn * panel_h), (int)j0, (int)pn, &full[s]);
+          } else {
+            tma_load_2d(st + c * (TJ + TI) * KC * 8, &mapA, (int)ka, (int)j0, &full[s]);
+          }
           tma_load_2d(st + c * (TJ + TI) * KC * 8 + TJ * KC * 8, &mapO, (int)(k0 + c * KC), (int)i0, &full[s]);
         }
       }
@@ -381,7 +394,7 @@ namespace {
 
 template <int WA>
 int launch_gemm(bra_ctx* ctx, const CUtensorMap& mapA, const double* Omt, int64_t ldt, int64_t l, int64_t m,
-                int64_t n, double* B, int64_t ldb) {
+                int64_t n, double* B, int64_t ldb, int panel_h = 0) {
   using Cfg = GemmCfg<WA>;
   CUtensorMap mapO;
   if (!make_map(&mapO, Omt, m, l, ldt, Cfg::TI)) {
@@ -430,7 +443,8 @@ int launch_gemm(bra_ctx* ctx, const CUtensorMap& mapA, const double* Omt, int64_
   dim3 grid(jt, itl, splits);
   {
     ProfScope ps(ctx, ctx->gemm_tag);
-    gemm_sketch_kernel<WA><<<grid, (GW + 1) * 32, Cfg::SMEM, ctx->stream>>>(mapA, mapO, m, n, l, kper, out, ldo, sstride);
+    gemm_sketch_kernel<WA><<<grid, (GW + 1) * 32, Cfg::SMEM, ctx->stream>>>(mapA, mapO, m, n, l, kper, out, ldo, sstride,
+                                                                            panel_h);
   }
   ctx->launches++;
   BRA_CUDA(cudaGetLastError());
@@ -498,6 +512,77 @@ int bra_gemm_sketch(bra_ctx* ctx, const double* Omt, int64_t l, int64_t m, const
   return bra_gemm_tn(ctx, Omt, (m + 1) & ~int64_t(1), l, m, A, lda, n, B, ldb);
 }
 
+// A tall A (column stride >= 1 MB) puts every column of a 256-column tile in its own 2 MB page; the TMA stream then
+// thrashes the TLB (measured: 33 TF at 64 K rows, 24 TF at 256 K rows, 18.7 TF at 1 M rows).  Such an A is repacked
+// ONCE per factorization into row panels of PANEL_H rows, P[panel][column][row] (column stride 128 KB), and the
+// kernel walks it through a 3-D tensor map.  Costs one read + one write of A (a few % of one round's GEMM).
+constexpr int PANEL_H = 16384;
+
+__global__ void repack_panels_kernel(const double* __restrict__ A, int64_t lda, int64_t m, int64_t n,
+                                     double* __restrict__ P) {
+  // one CTA per (column, panel) segment: PANEL_H contiguous doubles in, PANEL_H contiguous doubles out
+  const int64_t npan = (m + PANEL_H - 1) / PANEL_H;
+  for (int64_t seg = blockIdx.x; seg < n * npan; seg += gridDim.x) {
+    const int64_t j = seg % n, p = seg / n;
+    const double2* src = reinterpret_cast<const double2*>(A + p * PANEL_H + j * lda);
+    double2* dst = reinterpret_cast<double2*>(P + (p * n + j) * (int64_t)PANEL_H);
+    const int64_t rows = min((int64_t)PANEL_H, m - p * PANEL_H);
+    for (int64_t r = threadIdx.x; r < PANEL_H / 2; r += blockDim.x) {
+      double2 v = make_double2(0.0, 0.0);
+      if (2 * r + 1 < rows) v = src[r];
+      else if (2 * r < rows) v.x = A[p * PANEL_H + j * lda + 2 * r];
+      dst[r] = v;
+    }
+  }
+}
+
+bool bra_gemm_wants_panels(const double* A, int64_t lda, int64_t m, int64_t n) {
+  return bra_gemm_tma_ok(A, lda, m, n) && lda * 8 >= (int64_t(1) << 20) && m >= 4 * (int64_t)PANEL_H;
+}
+
+int bra_repack_panels(bra_ctx* ctx, const double* A, int64_t lda, int64_t m, int64_t n, double* P) {
+  const int64_t npan = (m + PANEL_H - 1) / PANEL_H;
+  const int64_t segs = n * npan;
+  repack_panels_kernel<<<(unsigned)(segs < 148 * 16 ? segs : 148 * 16), 256, 0, ctx->stream>>>(A, lda, m, n, P);
+  ctx->launches++;
+  BRA_CUDA(cudaGetLastError());
+  return BRA_OK;
+}
+
+int64_t bra_panel_bytes(int64_t m, int64_t n) { return ((m + PANEL_H - 1) / PANEL_H) * n * (int64_t)PANEL_H * 8; }
+
+static int pick_wa(int64_t l) {
+  // the row-tile height that wastes the fewest padded sketch rows (l = 8a: 40, 72, 136, 264, 520, ...)
+  int best = 5;
+  int64_t bestpad = -1;
+  for (int wa : {5, 4, 3}) {
+    int64_t ti = 8 * wa, pad = (l + ti - 1) / ti * ti;
+    if (bestpad < 0 || pad < bestpad) {
+      bestpad = pad;
+      best = wa;
+    }
+  }
+  return best;
+}
+
+// B (l x n) = Omega * A with A given as row panels (bra_repack_panels)
+int bra_gemm_sketch_panels(bra_ctx* ctx, const double* Omt, int64_t l, int64_t m, const double* P, int64_t n, double* B,
+                           int64_t ldb) {
+  if (l <= 0 || n <= 0) return BRA_OK;
+  const int64_t ldt = (m + 1) & ~int64_t(1);
+  const int64_t npan = (m + PANEL_H - 1) / PANEL_H;
+  CUtensorMap mapA;
+  if (!bra_make_map_3d_f64(&mapA, P, PANEL_H, (uint64_t)n, (uint64_t)npan, (uint64_t)PANEL_H * 8,
+                           (uint64_t)PANEL_H * 8 * (uint64_t)n, KC, TJ)) {
+    ctx->set_error("cuTensorMapEncodeTiled(A panels) failed");
+    return BRA_ERR_CUDA;
+  }
+  const int best = pick_wa(l);
+  if (best == 5) return launch_gemm<5>(ctx, mapA, Omt, ldt, l, m, n, B, ldb, PANEL_H);
+  if (best == 4) return launch_gemm<4>(ctx, mapA, Omt, ldt, l, m, n, B, ldb, PANEL_H);
+  return launch_gemm<3>(ctx, mapA, Omt, ldt, l, m, n, B, ldb, PANEL_H);
+}
+
 // General "TN" product on the same TMA + DMMA kernel: C (l x n) = X^T Y with X (m x l, ldx) and Y (m x n, ldy)
 // both column-major, i.e. both contiguous along the contraction index.
 int bra_gemm_tn(bra_ctx* ctx, const double* Omt, int64_t ldt, int64_t l, int64_t m, const double* A, int64_t lda,
@@ -510,16 +595,7 @@ int bra_gemm_tn(bra_ctx* ctx, const double* Omt, int64_t ldt, int64_t l, int64_t
     ctx->set_error("cuTensorMapEncodeTiled(A) failed");
     return BRA_ERR_CUDA;
   }
-  // pick the row-tile height that wastes the fewest padded sketch rows (l = 8a: 40, 72, 136, 264, 520, ...)
-  int best = 5;
-  int64_t bestpad = -1;
-  for (int wa : {5, 4, 3}) {
-    int64_t ti = 8 * wa, pad = (l + ti - 1) / ti * ti;
-    if (bestpad < 0 || pad < bestpad) {
-      bestpad = pad;
-      best = wa;
-    }
-  }
+  const int best = pick_wa(l);
   if (best == 5) return launch_gemm<5>(ctx, mapA, Omt, ldt, l, m, n, B, ldb);
   if (best == 4) return launch_gemm<4>(ctx, mapA, Omt, ldt, l, m, n, B, ldb);
   return launch_gemm<3>(ctx, mapA, Omt, ldt, l, m, n, B, ldb);
