@@ -4,8 +4,9 @@
 // fused into ONE kernel, one CTA per block at a time:
 //   sparse-Gaussian sketch (src/sketch.jl:571-589)  ->  early-terminating QRCP with dlaqps semantics
 //   (src/pqr.jl:361-418)  ->  T = R11^{-1} R12 (src/pqr.jl:438-442),
-// with the l x n sketch living entirely on chip: shared memory while it is being formed (each entry of A_b is
-// read from HBM exactly once, coalesced, through a per-warp column stage), then one COLUMN PER THREAD in
+// with the l x n sketch living entirely on chip: A_b streams through shared memory in 16-column tiles (cp.async,
+// double buffered, each entry read from HBM exactly once, coalesced; stored row-major with an odd stride so that the
+// permuted row gather of the sparse sketch is bank-conflict free), then one COLUMN PER THREAD in
 // registers for the factorization, so that the Householder dot products and rank-1 updates need no cross-lane
 // traffic at all; only the pivot search (redux.sync argmax + 16-entry merge) and the pivot column broadcast go
 // through shared memory.  HBM-bound by design: 8 m n bytes per block in, p, k and the k x (n-k) T out.
@@ -15,6 +16,7 @@
 #include "common.cuh"
 #include "qrcp_common.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 namespace {
@@ -27,6 +29,7 @@ struct BatchParams {
   const double* A;
   int64_t lda, strideA;
   int m, n, l, kcap, nb;
+  int nstages;             // tile stages in shared memory (2 unless the block is too tall)
   double atol, rtol;
   const int64_t* perm;     // 1-based randperm(m); block b at perm + b*perm_stride (0 = shared by all blocks)
   int64_t perm_stride;
@@ -46,20 +49,21 @@ __global__ void __launch_bounds__(BT, 1) idfact_batched_kernel(BatchParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m = P.m, n = P.n, l = P.l;
-  const int mpad = (m + 1) & ~1;
-  constexpr int BSTR = BT + 1;                                   // padded row stride of the staged sketch
-  double* Bs = reinterpret_cast<double*>(smem_raw);             // [BL][BSTR]
-  double* colbuf = Bs + (size_t)BL * BSTR;                      // [BW][mpad]  (later: R11, [BL][BL+1])
+  constexpr int TC = 16;                                         // columns of A_b per tile
+  constexpr int TS = TC + 1;                                     // row stride of a tile (odd: conflict-free both ways)
+  const int nst = P.nstages;                                     // 2: double buffered; 1: tall blocks
+  const size_t tile_elems = (size_t)max(m, 2 * BL) * TS;
+  double* tiles = reinterpret_cast<double*>(smem_raw);          // [nst][m][TS]   (later: R11, [BL][BL+1])
+  double* Xb = tiles + (size_t)nst * tile_elems;                 // [BL][TS] sketch of the current tile
   const int tpad = (((m / l) + 1) * l + 1) & ~1;                 // table entries, [t][i] layout
-  double* sv = colbuf + (size_t)BW * mpad;                      // [tpad]
-  double* vv = sv + tpad;                                       // [BL] Householder vector
+  double2* tab = reinterpret_cast<double2*>(Xb + (size_t)BL * TS);   // [tpad] {weight, permuted row offset in a tile}
+  double* vv = reinterpret_cast<double*>(tab + tpad);           // [BL] Householder vector
   double* rdblk = vv + BL;                                      // [BL] diagonal of R within the current block
   double* cv = rdblk + BL;                                      // [BW] warp candidates: norm
   double* hh = cv + BW;                                         // tau, beta
   int* clp = reinterpret_cast<int*>(hh + 2);                    // [BW] logical position
   int* ctd = clp + BW;                                          // [BW] owning thread
-  int* permv = ctd + BW;                                        // [tpad] 0-based
-  double* mycol = colbuf + (size_t)warp * mpad;
+  double* colbuf = tiles;
 
   const int lmin = min(l, n);
   const int64_t q = m / l, rem = m % l;                          // p_i = q + (i < rem), off_i = i*q + min(i, rem)
@@ -86,54 +90,70 @@ __global__ void __launch_bounds__(BT, 1) idfact_batched_kernel(BatchParams P) {
           i = (int)(rem + r2 / q);
           t = (int)(r2 % q);
         }
-        permv[t * l + i] = (int)(pb[r] - 1);
-        sv[t * l + i] = sb[r];
+        tab[t * l + i] = make_double2(sb[r], __longlong_as_double((long long)(pb[r] - 1) * TS));
       }
       tables_loaded = true;
       __syncthreads();
     }
 
-    // ---- sparse-Gaussian sketch: warp w stages column j (coalesced, next column prefetched into registers),
-    // lane i forms B[i, j] in the reference's summation order ----
+    // ---- sparse-Gaussian sketch, tile by tile.  Tile T = columns 16T..16T+15 of A_b, all m rows, staged as
+    // tile[r][c] (row stride 17) by 8-byte cp.async: warp w copies column w (lanes = consecutive rows: coalesced
+    // global reads, conflict-free shared stores).  Thread (i = tid / 16, c = tid % 16) then forms B[i, 16T + c] in the
+    // reference's summation order; its 16 terms read tile[perm[t, i]][c] -- one permuted ROW, contiguous across the
+    // half-warp -- so the gather costs no bank conflicts.  The finished 32 x 16 piece goes through a small exchange
+    // buffer straight into the registers of the 16 threads that own those columns for the factorization.
+    const bool live = tid < n;
+    double a[BL];
+#pragma unroll
+    for (int i = 0; i < BL; ++i) a[i] = 0.0;
     {
-      constexpr int PF = 16;                       // prefetch registers: covers m <= 512 (longer columns: tail loop)
-      double pf[PF];
-      int j = warp;
-      if (j < n) {
-        const double* a = Ab + (int64_t)j * P.lda;
-#pragma unroll
-        for (int u = 0; u < PF; ++u) pf[u] = (lane + 32 * u < m) ? a[lane + 32 * u] : 0.0;
-      }
-      for (; j < n; j += BW) {
-        const double* a = Ab + (int64_t)j * P.lda;
-#pragma unroll
-        for (int u = 0; u < PF; ++u)
-          if (lane + 32 * u < m) mycol[lane + 32 * u] = pf[u];
-        for (int r = lane + 32 * PF; r < m; r += 32) mycol[r] = a[r];
-        if (j + BW < n) {
-          const double* an = Ab + (int64_t)(j + BW) * P.lda;
-#pragma unroll
-          for (int u = 0; u < PF; ++u) pf[u] = (lane + 32 * u < m) ? an[lane + 32 * u] : 0.0;
+      const int ntiles = (n + TC - 1) / TC;
+      auto issue = [&](int T) {
+        const int c = T * TC + warp;                 // BW == TC: one column per warp
+        if (c < n) {
+          const double* g = Ab + (int64_t)c * P.lda;
+          double* d = tiles + (size_t)(T % nst) * tile_elems + warp;
+          for (int r = lane; r < m; r += 32)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(d + (size_t)r * TS)),
+                         "l"(g + r)
+                         : "memory");
         }
-        __syncwarp();
-        if (lane < l) {
-          const int pi = (int)q + (lane < rem ? 1 : 0);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      issue(0);
+      const int si = tid >> 4, sc = tid & 15;        // sketch row / column within the tile
+      const int pi = (si < l) ? (int)q + (si < rem ? 1 : 0) : 0;
+      for (int T = 0; T < ntiles; ++T) {
+        if (nst > 1 && T + 1 < ntiles) {
+          issue(T + 1);                              // its stage was last read in iteration T-1 (barrier below)
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const double* tl = tiles + (size_t)(T % nst) * tile_elems;
+        if (si < l) {
           double acc = 0.0;
 #pragma unroll 4
-          for (int t = 0; t < pi; ++t) acc += sv[t * l + lane] * mycol[permv[t * l + lane]];
-          Bs[lane * BSTR + j] = acc;
+          for (int t = 0; t < pi; ++t) {
+            const double2 e = tab[t * l + si];                   // one 16-byte read: weight and row offset
+            acc += e.x * tl[__double_as_longlong(e.y) + sc];
+          }
+          Xb[si * TS + sc] = acc;
         }
-        __syncwarp();
+        __syncthreads();
+        if (nst == 1 && T + 1 < ntiles) issue(T + 1);
+        if ((tid >> 4) == T && live) {
+#pragma unroll
+          for (int i = 0; i < BL; ++i)
+            if (i < l) a[i] = Xb[i * TS + (tid & 15)];
+        }
       }
     }
     __syncthreads();
     BTICK(0)
 
     // ---- one column per thread, in registers ----
-    const bool live = tid < n;
-    double a[BL];
-#pragma unroll
-    for (int i = 0; i < BL; ++i) a[i] = (live && i < l) ? Bs[i * BSTR + tid] : 0.0;
     double vn1, vn2;
     {
       // initial norm (src/pqr.jl:376-385), power-of-two scaled like the grid-wide kernel
@@ -311,15 +331,15 @@ __global__ void __launch_bounds__(BT, 1) idfact_batched_kernel(BatchParams P) {
     }
     __syncthreads();
     if (live && lpos >= k && k <= P.ldT) {
-      // back substitution on my column of R12 (dtrsm L,U,N,N), entirely in registers
+      // back substitution on my column of R12 (dtrsm L,U,N,N), entirely in registers, column-oriented: once x_i is
+      // known it is eliminated from all rows above (independent FMAs instead of one dependent dot product per row)
 #pragma unroll
       for (int i = BL - 1; i >= 0; --i) {
         if (i < k) {
-          double x = a[i];
+          const double x = a[i] / R11[i * (BL + 1) + i];
+          a[i] = x;
 #pragma unroll
-          for (int j = i + 1; j < BL; ++j)
-            if (j < k) x = fma(-R11[i * (BL + 1) + j], a[j], x);
-          a[i] = x / R11[i * (BL + 1) + i];
+          for (int j = 0; j < i; ++j) a[j] = fma(-R11[j * (BL + 1) + i], x, a[j]);
         }
       }
       double* t = P.Tout + (int64_t)b * P.strideT + (int64_t)(lpos - k) * P.ldT;
@@ -369,14 +389,18 @@ int bra_idfact_batched_f64(bra_ctx* ctx, int64_t nblocks, int64_t m, int64_t n, 
   // first adaptive round: order = nb (src/sketch.jl:677-680); non-adaptive: order = rank (:686)
   const bool adaptive = opts->sketchfact_adap || opts->rank < 0;
   const int64_t order = adaptive ? opts->nb : opts->rank;
-  const int64_t mpad = (m + 1) & ~int64_t(1);
   const int64_t ordc = order > 0 ? order : 1;
   const int64_t tpad = (((m / ordc) + 1) * ordc + 1) & ~int64_t(1);
-  const size_t smem = ((size_t)BL * (BT + 1) + (size_t)BW * mpad + tpad + 2 * BL + BW + 2) * 8 + (2 * BW + tpad) * 4 + 64;
-  if (order < 1 || order > BL || n > BT || order > m || smem > (size_t)ctx->smem_optin ||
-      (size_t)BW * mpad < (size_t)BL * (BL + 1)) {
+  const int64_t tile_elems = (m > 2 * BL ? m : 2 * BL) * 17;
+  auto smem_for = [&](int nst) {
+    return ((size_t)nst * tile_elems + (size_t)BL * 17 + 2 * tpad + 2 * BL + BW + 2) * 8 + (2 * BW) * 4 + 64;
+  };
+  int nstages = 2;
+  if (smem_for(2) > (size_t)ctx->smem_optin) nstages = 1;
+  const size_t smem = smem_for(nstages);
+  if (order < 1 || order > BL || n > BT || order > m || smem > (size_t)ctx->smem_optin) {
     ctx->set_error("batched idfact: shape outside the fused kernel (needs order = nb <= 32, n <= 512, "
-                   "32 <= m <= ~1000); factor such blocks one by one with bra_idfact_f64");
+                   "32 <= m <= ~1500); factor such blocks one by one with bra_idfact_f64");
     return BRA_ERR_UNSUPPORTED;
   }
   const int64_t lmin = order < n ? order : n;
@@ -390,6 +414,7 @@ int bra_idfact_batched_f64(bra_ctx* ctx, int64_t nblocks, int64_t m, int64_t n, 
   P.n = (int)n;
   P.l = (int)order;
   P.kcap = (int)kcap;
+  P.nstages = nstages;
   P.nb = (int)(opts->nb < kcap ? opts->nb : (kcap > 0 ? kcap : 1));
   P.atol = opts->atol;
   P.rtol = opts->rtol;
