@@ -248,6 +248,7 @@ int bra_create(bra_ctx** out, int device) {
   ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
   BRA_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   BRA_CUDA(cudaMallocHost(&ctx->h_info, 64));
+  BRA_CUDA(cudaMallocHost(&ctx->h_pin, BRA_HPIN_BYTES));
   return BRA_OK;
 }
 
@@ -263,6 +264,7 @@ int bra_destroy(bra_ctx* ctx) {
   for (DevBuf* b : bufs) b->release();
   bra_comm_destroy(ctx);
   if (ctx->h_info) cudaFreeHost(ctx->h_info);
+  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return BRA_OK;

@@ -1,9 +1,13 @@
 // Fused pqrfact / psvdfact drivers over the idfact core (reference: src/pqr.jl:290-307, src/psvd.jl:238-272).
 #include "common.cuh"
 #include <algorithm>
+#include <cstring>
+#include <string>
 #include <vector>
 
 int bra_set_identity(bra_ctx* ctx, int k, double* J, int64_t ldj);
+int bra_chol_status_reset(bra_ctx* ctx);
+int bra_chol_status(bra_ctx* ctx);
 int bra_fix_signs(bra_ctx* ctx, int64_t rows, int k, double* Q, int64_t ldq, double* R, int64_t ldr);
 int bra_gather_scale_cols(bra_ctx* ctx, const double* X, int64_t ldx, int64_t rows, int kk, const int* order_dev,
                           const double* scale_dev, double* out, int64_t ldo);
@@ -25,7 +29,9 @@ int skeleton_qr(bra_ctx* ctx, char trans, const double* dA, int64_t lda, int64_t
   const int64_t ldq = even(mA);
   BRA_CUDA(ctx->Q.reserve((size_t)ldq * k * 8));
   BRA_CUDA(ctx->R1.reserve((size_t)k * k * 8));
-  int rc = bra_gather_cols(ctx, trans, dA, lda, mA, k, ctx->jpvt.as<int64_t>(), ctx->Q.as<double>(), ldq);   // getcols
+  int rc = bra_chol_status_reset(ctx);
+  if (rc) return rc;
+  rc = bra_gather_cols(ctx, trans, dA, lda, mA, k, ctx->jpvt.as<int64_t>(), ctx->Q.as<double>(), ldq);   // getcols
   if (rc) return rc;
   // Y = C R11^{-1}: R11 is the triangular factor of the SKETCH of these very columns (Omega*C = Q_B*R11)
   rc = bra_trsolve_right_upper(ctx, mA, (int)k, ctx->R11.as<double>(), k, ctx->Q.as<double>(), ldq);
@@ -84,8 +90,7 @@ int bra_pqrfact_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double
   }
   res.have_Q = true;
   res.have_R = true;
-  BRA_CUDA(cudaStreamSynchronize(ctx->stream));
-  return BRA_OK;
+  return bra_chol_status(ctx);      // the one host sync of the tail (also reports a Cholesky breakdown)
 }
 
 int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* opts,
@@ -146,25 +151,41 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
   bool explicit_qz = false;
   {
     BRA_CUDA(ctx->G.reserve((size_t)k * k * 8));
+    // park the skeleton QR's Cholesky status in info[13] and start a clean one for Z'Z (both read at the sync below)
+    BRA_CUDA(cudaMemcpyAsync(ctx->info.as<int>() + 13, ctx->info.as<int>() + 12, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    if ((rc = bra_chol_status_reset(ctx))) return rc;
     rc = bra_gemm_tn(ctx, Z, ldz, k, nA, Z, ldz, k, ctx->G.as<double>(), k);              // G = Z'Z = I + T T'
     if (rc) return rc;
     rc = bra_cholesky_upper(ctx, (int)k, ctx->G.as<double>(), k, Rz, k);
     if (rc) return rc;
-    std::vector<double> dz((size_t)k);
-    int hinfo = 0;
-    BRA_CUDA(cudaMemcpy2DAsync(dz.data(), 8, Rz, (size_t)(k + 1) * 8, 8, (size_t)k, cudaMemcpyDeviceToHost, ctx->stream));
-    BRA_CUDA(cudaMemcpyAsync(&hinfo, ctx->info.as<int>() + 12, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((size_t)k * 8 > BRA_HPIN_BYTES) {
+      ctx->set_error("psvdfact: k too large for the pinned read-back buffer");
+      return BRA_ERR_UNSUPPORTED;
+    }
+    double* dz = reinterpret_cast<double*>(ctx->h_pin);
+    BRA_CUDA(cudaMemcpy2DAsync(dz, 8, Rz, (size_t)(k + 1) * 8, 8, (size_t)k, cudaMemcpyDeviceToHost, ctx->stream));
+    BRA_CUDA(cudaMemcpyAsync(ctx->h_info + 12, ctx->info.as<int>() + 12, 8, cudaMemcpyDeviceToHost, ctx->stream));
     BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+    // a breakdown in the skeleton QR is an error; one in Z'Z only selects the two-pass path (which checks again)
+    if (ctx->h_info[13] != 0) {
+      ctx->set_error("CholeskyQR2 of the skeleton columns: Gram matrix not positive definite at pivot " +
+                     std::to_string(ctx->h_info[13]));
+      return BRA_ERR_INTERNAL;
+    }
+    const int hinfo = ctx->h_info[12];
     double dmin = dz[0], dmax = dz[0];
-    for (double d : dz) {
-      dmin = std::min(dmin, d);
-      dmax = std::max(dmax, d);
+    for (int64_t i = 0; i < k; ++i) {
+      dmin = std::min(dmin, dz[i]);
+      dmax = std::max(dmax, dz[i]);
     }
     explicit_qz = hinfo != 0 || !(dmin > 0.0) || dmax > 1e3 * dmin;
   }
   if (explicit_qz) {
+    // rebuild Z (the Gram pass left it untouched) and take the robust path; its status is checked before the SVD
+    if ((rc = bra_chol_status_reset(ctx))) return rc;
     rc = bra_cholqr2(ctx, nA, (int)k, Z, ldz, nullptr, Rz);
     if (rc) return rc;
+    if ((rc = bra_chol_status(ctx))) return rc;
   }
   // X[i,j] = sum_t Rz[i,t] R1[j,t]
   rc = bra_gemm_generic(ctx, Rz, 1, k, ctx->R1.as<double>(), k, 1, k, k, k, X, ldj);
@@ -186,10 +207,21 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
     }
   res.ksvd = kk;
   BRA_CUDA(ctx->aux_in1.reserve((size_t)k * 4));
-  BRA_CUDA(cudaMemcpyAsync(ctx->aux_in1.p, order.data(), (size_t)k * 4, cudaMemcpyHostToDevice, ctx->stream));
   BRA_CUDA(ctx->S.reserve((size_t)2 * k * 8));
   double* Ssorted = ctx->S.as<double>() + k;       // ctx->S[0:k] holds the unsorted norms (bra_jacobi_svd)
-  BRA_CUDA(cudaMemcpyAsync(Ssorted, ssort.data(), (size_t)k * 8, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    // uploads from the pinned scratch (a pageable source would make these copies synchronous)
+    int* ho = reinterpret_cast<int*>(ctx->h_pin);
+    double* hsrt = reinterpret_cast<double*>(ctx->h_pin + (((size_t)k * 4 + 63) & ~size_t(63)));
+    if ((((size_t)k * 4 + 63) & ~size_t(63)) + (size_t)k * 8 > BRA_HPIN_BYTES) {
+      ctx->set_error("psvdfact: k too large for the pinned upload buffer");
+      return BRA_ERR_UNSUPPORTED;
+    }
+    std::memcpy(ho, order.data(), (size_t)k * 4);
+    std::memcpy(hsrt, ssort.data(), (size_t)k * 8);
+    BRA_CUDA(cudaMemcpyAsync(ctx->aux_in1.p, ho, (size_t)k * 4, cudaMemcpyHostToDevice, ctx->stream));
+    BRA_CUDA(cudaMemcpyAsync(Ssorted, hsrt, (size_t)k * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
 
   // Ut (kk x mA) = Jsel' Q'   and   Vp (kk x nA) = Ysel' Qz'   -- both on the TMA + DMMA kernel (TN form)
   const int64_t ldk = even(k);

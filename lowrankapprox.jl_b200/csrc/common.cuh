@@ -62,6 +62,8 @@ struct FactResult {
   bool have_T = false, have_Q = false, have_R = false, have_svd = false;
 };
 
+constexpr size_t BRA_HPIN_BYTES = 256 * 1024;
+
 struct bra_ctx {
   int device = 0;
   int num_sms = 0;
@@ -105,6 +107,7 @@ struct bra_ctx {
   uint32_t rec_epoch = 1;
   size_t rec_zeroed = 0;
   int32_t* h_info = nullptr;   // pinned, 16 ints
+  unsigned char* h_pin = nullptr;   // pinned scratch for small read-backs / uploads (BRA_HPIN_BYTES)
 
   FactResult res;
 

@@ -680,8 +680,7 @@ int bra_trsolve_right_upper(bra_ctx* ctx, int64_t rows, int k, const double* R, 
 int bra_cholesky_upper(bra_ctx* ctx, int k, double* G, int64_t ldg, double* Rout, int64_t ldr) {
   if (k <= 0) return BRA_OK;
   ProfScope ps(ctx, BRA_PROF_QR);
-  int* info = ctx->info.as<int>() + 12;
-  BRA_CUDA(cudaMemsetAsync(info, 0, 4, ctx->stream));
+  int* info = ctx->info.as<int>() + 12;      // sticky: reset by bra_chol_status_reset, read by bra_chol_status
   const int nblk = (k + TB - 1) / TB;
   for (int jb = 0; jb < nblk; ++jb) {
     const int j0 = jb * TB;
@@ -725,11 +724,21 @@ int bra_cholqr2(bra_ctx* ctx, int64_t rows, int k, double* Y, int64_t ldy, const
     }
   }
   BRA_CUDA(cudaMemcpyAsync(Rout, Racc, (size_t)k * k * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-  int hinfo = 0;
-  BRA_CUDA(cudaMemcpyAsync(&hinfo, ctx->info.as<int>() + 12, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  return BRA_OK;      // a non-positive pivot is sticky in ctx->info[12]: the caller checks it at its next sync
+}
+
+int bra_chol_status_reset(bra_ctx* ctx) {
+  BRA_CUDA(ctx->info.reserve(64));
+  BRA_CUDA(cudaMemsetAsync(ctx->info.as<int>() + 12, 0, 4, ctx->stream));
+  return BRA_OK;
+}
+
+// Synchronises the stream and reports a Cholesky breakdown recorded since the last reset.
+int bra_chol_status(bra_ctx* ctx) {
+  BRA_CUDA(cudaMemcpyAsync(ctx->h_info + 12, ctx->info.as<int>() + 12, 4, cudaMemcpyDeviceToHost, ctx->stream));
   BRA_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (hinfo != 0) {
-    ctx->set_error("CholeskyQR2: Gram matrix not positive definite at pivot " + std::to_string(hinfo));
+  if (ctx->h_info[12] != 0) {
+    ctx->set_error("CholeskyQR2: Gram matrix not positive definite at pivot " + std::to_string(ctx->h_info[12]));
     return BRA_ERR_INTERNAL;
   }
   return BRA_OK;
@@ -745,6 +754,7 @@ int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64
   ctx->launches++;
   constexpr int MAX_SWEEPS = 48;
   int sweeps = 0, converged = 1;
+  bool have_out = false;
   if ((ldx & 1) || (ldj & 1) || (reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(J) & 15)) {
     ctx->set_error("Jacobi SVD: X and J need even leading dimensions and 16-byte aligned bases");
     return -4;
@@ -819,19 +829,28 @@ int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64
 #undef JL
     BRA_CUDA(e);
     ctx->launches++;
-    int h[10] = {0};
-    BRA_CUDA(cudaMemcpyAsync(h, P.out, 40, cudaMemcpyDeviceToHost, ctx->stream));
-    BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+    have_out = true;
+  }
+  // column norms = singular values; ONE host round trip for the kernel's report and the k norms (pinned scratch)
+  BRA_CUDA(ctx->S.reserve((size_t)k * 8));
+  col_norms_kernel<<<k, 128, 0, ctx->stream>>>(k, X, ldx, ctx->S.as<double>());
+  ctx->launches++;
+  int* h = reinterpret_cast<int*>(ctx->h_pin);
+  double* hs = reinterpret_cast<double*>(ctx->h_pin + 64);
+  if ((size_t)k * 8 + 64 > BRA_HPIN_BYTES) {
+    ctx->set_error("Jacobi SVD: k too large for the pinned read-back buffer");
+    return BRA_ERR_UNSUPPORTED;
+  }
+  if (have_out) BRA_CUDA(cudaMemcpyAsync(h, ctx->jwork.as<int>() + 16, 40, cudaMemcpyDeviceToHost, ctx->stream));
+  BRA_CUDA(cudaMemcpyAsync(hs, ctx->S.p, (size_t)k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (have_out) {
     sweeps = h[0];
     converged = h[1];
     for (int i = 0; i < 8; ++i) ctx->jacobi_kcycles[i] = h[2 + i];
   }
   ctx->last_jacobi_sweeps = sweeps;
-  BRA_CUDA(ctx->S.reserve((size_t)k * 8));
-  col_norms_kernel<<<k, 128, 0, ctx->stream>>>(k, X, ldx, ctx->S.as<double>());
-  ctx->launches++;
-  BRA_CUDA(cudaMemcpyAsync(sigma_host, ctx->S.p, (size_t)k * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::memcpy(sigma_host, hs, (size_t)k * 8);
   std::iota(order_host, order_host + k, 0);
   std::stable_sort(order_host, order_host + k, [&](int a, int b) { return sigma_host[a] > sigma_host[b]; });
   if (!converged) {
