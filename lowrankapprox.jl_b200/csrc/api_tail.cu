@@ -258,7 +258,10 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
     if (rc) return rc;
   } else {
     // Yh = R_z^{-1} Ysel (k x kk);  Vop' = Yh' [I T]: the first k columns are Yh' itself, the rest one TN product with T
-    rc = bra_trsolve_upper(ctx, (int)k, kk, Rz, k, Ysel, ldj);
+    {
+      ProfScope ps(ctx, BRA_PROF_QR);
+      rc = bra_trsolve_upper_fast(ctx, (int)k, kk, Rz, k, Ysel, ldj);
+    }
     if (rc) return rc;
     rc = bra_transpose(ctx, Ysel, ldj, k, kk, ctx->B2.as<double>(), even(kk));
     if (rc) return rc;

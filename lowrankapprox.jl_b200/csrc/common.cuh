@@ -218,4 +218,5 @@ int bra_gemm_generic(bra_ctx* ctx, const double* Om, int64_t osi, int64_t osk, c
 
 // trsolve.cu
 int bra_trsolve_upper(bra_ctx* ctx, int k, int64_t nrhs, const double* R11, int64_t ldr, double* X, int64_t ldx);
+int bra_trsolve_upper_fast(bra_ctx* ctx, int k, int64_t nrhs, const double* R, int64_t ldr, double* X, int64_t ldx);
 int bra_tri_inverse_upper(bra_ctx* ctx, int k, const double* R, int64_t ldr, double* Rinv, int64_t ldx);

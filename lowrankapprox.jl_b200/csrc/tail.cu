@@ -669,8 +669,8 @@ int bra_trsolve_right_upper(bra_ctx* ctx, int64_t rows, int k, const double* R, 
     ProfScope ps(ctx, BRA_PROF_QR);
     set_identity_kernel<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(k, Rinv, ldk);
     ctx->launches++;
+    if ((rc = bra_tri_inverse_upper(ctx, k, R, ldr, Rinv, ldk))) return rc;               // Rinv = R^{-1}
   }
-  if ((rc = bra_tri_inverse_upper(ctx, k, R, ldr, Rinv, ldk))) return rc;                 // Rinv = R^{-1}
   if ((rc = bra_transpose(ctx, Y, ldy, rows, k, Yt, ldk))) return rc;                       // Y' (k x rows)
   if ((rc = bra_gemm_tn(ctx, Rinv, ldk, k, k, Yt, ldk, rows, Ct, ldk))) return rc;          // (Y Rinv)' = Rinv' Y'
   return bra_transpose(ctx, Ct, ldk, k, rows, Y, ldy);
