@@ -72,6 +72,8 @@ lib.bra_chkopts.argtypes = [_vp, C.POINTER(bra_opts)]
 lib.bra_launch_count.argtypes = [_vp]
 lib.bra_launch_count.restype = C.c_uint64
 lib.bra_sync.argtypes = [_vp]
+lib.bra_debug_maxdet_swaps.argtypes = [_vp]
+lib.bra_debug_maxdet_swaps.restype = C.c_int64
 lib.bra_stream.argtypes = [_vp]
 lib.bra_stream.restype = _vp
 lib.bra_sketch_randn_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _i64]
@@ -252,6 +254,10 @@ class Context:
 
     def launch_count(self) -> int:
         return int(lib.bra_launch_count(self._h))
+
+    def maxdet_swaps(self) -> int:
+        """Column swaps made by the last maxdet post-processing (maxdet_swapcols!, src/pqr.jl:444-478)."""
+        return int(lib.bra_debug_maxdet_swaps(self._h))
 
     def collective_count(self) -> int:
         return int(lib.bra_collective_count(self._h))

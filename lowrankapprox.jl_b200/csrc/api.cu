@@ -325,6 +325,7 @@ int bra_debug_qrcp_phases(bra_ctx* ctx, int32_t* out6) {
 }
 
 int bra_debug_jacobi_sweeps(bra_ctx* ctx) { return ctx ? ctx->last_jacobi_sweeps : -1; }
+int64_t bra_debug_maxdet_swaps(bra_ctx* ctx) { return ctx ? ctx->last_maxdet_swaps : -1; }
 int bra_debug_jacobi_phases(bra_ctx* ctx, int32_t* out4) {
   if (!ctx || !out4) return -1;
   for (int i = 0; i < 8; ++i) out4[i] = ctx->jacobi_kcycles[i];
@@ -592,6 +593,15 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
       rc = bra_trsolve_upper(ctx, (int)k, nA - k, ctx->R11.as<double>(), k, ctx->T.as<double>(), ldT);
     }
     if (rc) return rc;
+    // strong RRQR post-processing (pqrback_postproc, src/pqr.jl:428-433): only p and T are maintained
+    ctx->last_maxdet_swaps = 0;
+    if (o->maxdet_tol >= 0 && k < nA) {
+      ProfScope ps(ctx, BRA_PROF_TRSOLVE);
+      rc = bra_maxdet_swapcols(ctx, (int)k, nA - k, ctx->T.as<double>(), ldT, ctx->jpvt.as<int64_t>(), o->maxdet_tol,
+                               o->maxdet_niter, &ctx->last_maxdet_swaps);
+      if (rc) return rc;
+      res.maxdet_done = ctx->last_maxdet_swaps > 0;
+    }
   }
   res.have_T = true;
   return BRA_OK;
@@ -607,10 +617,6 @@ int bra_check_fact_args(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
   if (bra_chkopts(ctx, opts)) return -7;
   if (opts->sketch_randn_niter > 0) {
     ctx->set_error("sketch_randn_niter > 0 is not built (SURVEY 8f-1)");
-    return BRA_ERR_UNSUPPORTED;
-  }
-  if (opts->maxdet_tol >= 0) {
-    ctx->set_error("maxdet_tol >= 0 (strong RRQR post-processing) is not built (SURVEY 8f-1)");
     return BRA_ERR_UNSUPPORTED;
   }
   if (opts->sketch == BRA_SKETCH_NONE) {

@@ -68,6 +68,12 @@ int bra_pqrfact_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double
       dA = ctx->A_stage.as<double>();
     }
   }
+  if (opts->maxdet_tol >= 0) {
+    // after a column swap the sketch's R11 is no longer the triangular factor of the skeleton's sketch, which is what
+    // preconditions the CholeskyQR2 of A[:, sk]; the pqr / psvd tails on a maxdet-refined ID are not built yet
+    ctx->set_error("pqrfact/psvdfact with maxdet_tol >= 0 are not built (idfact is); SURVEY 8f-1");
+    return BRA_ERR_UNSUPPORTED;
+  }
   rc = bra_sketchfact_core(ctx, trans, m, n, dA, dlda, opts, rnd);      // V = idfact(trans, A, opts)
   if (rc) return rc;
   FactResult& res = ctx->res;
@@ -112,6 +118,12 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
       BRA_CUDA(cudaMemcpy2DAsync(ctx->A_stage.p, (size_t)dlda * 8, A, (size_t)lda * 8, (size_t)m * 8, (size_t)n,
                                  cudaMemcpyDefault, ctx->stream));
     dA = ctx->A_stage.as<double>();
+  }
+  if (opts->maxdet_tol >= 0) {
+    // after a column swap the sketch's R11 is no longer the triangular factor of the skeleton's sketch, which is what
+    // preconditions the CholeskyQR2 of A[:, sk]; the pqr / psvd tails on a maxdet-refined ID are not built yet
+    ctx->set_error("pqrfact/psvdfact with maxdet_tol >= 0 are not built (idfact is); SURVEY 8f-1");
+    return BRA_ERR_UNSUPPORTED;
   }
   rc = bra_sketchfact_core(ctx, trans, m, n, dA, dlda, opts, rnd);      // V = idfact(trans, A, opts)
   if (rc) return rc;

@@ -60,6 +60,7 @@ struct FactResult {
   int64_t ldT = 0;             // leading dimension of ctx->T (k rounded up to even: keeps the TMA GEMM path open)
   int64_t svd_m = 0, svd_n = 0;  // dims of the ORIGINAL A for psvdfact's U (svd_m x ksvd) and Vt (ksvd x svd_n)
   bool have_T = false, have_Q = false, have_R = false, have_svd = false;
+  bool maxdet_done = false;    // maxdet swapped columns: R11 no longer belongs to the skeleton (tails must not use it)
 };
 
 constexpr size_t BRA_HPIN_BYTES = 256 * 1024;
@@ -102,6 +103,7 @@ struct bra_ctx {
   int64_t shard_row0 = 0, shard_m_global = 0;   // this rank's first global row / total rows (0: not sharded)
   uint64_t collectives = 0;
   int64_t batched_unfinished = 0;   // blocks of the last batched call that needed rounds beyond the fused one
+  int64_t last_maxdet_swaps = 0;    // column swaps done by the last maxdet post-processing
   int start_round = 0;              // adaptive loop resumes at this round (batched fallback)
   int gemm_tag = BRA_PROF_GEMM; // profiling tag the GEMM launchers record under (tails switch it)
   uint32_t rec_epoch = 1;
@@ -215,6 +217,10 @@ int bra_check_fact_args(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
 }
 int bra_gemm_generic(bra_ctx* ctx, const double* Om, int64_t osi, int64_t osk, const double* A, int64_t sk,
                      int64_t sj, int64_t l, int64_t n, int64_t K, double* C, int64_t ldc);
+
+// maxdet.cu
+int bra_maxdet_swapcols(bra_ctx* ctx, int k, int64_t ncols, double* T, int64_t ld, int64_t* jpvt, double tol,
+                        int64_t niter_max, int64_t* nswaps);
 
 // trsolve.cu
 int bra_trsolve_upper(bra_ctx* ctx, int k, int64_t nrhs, const double* R11, int64_t ldr, double* X, int64_t ldx);

@@ -485,16 +485,58 @@ def dorgqr(Bk: np.ndarray, tau: np.ndarray) -> np.ndarray:
     return Q
 
 
+def findmaxabs(x: np.ndarray) -> Tuple[float, int]:
+    """src/util.jl:13-23: largest |x[i]| in column-major order; among equal values the LAST index wins
+    (`t < m && continue`).  Returns (value, 0-based linear index)."""
+    a = np.abs(np.asarray(x)).ravel(order="F")
+    if a.size == 0:
+        return 0.0, -1
+    m = a.max()
+    return float(m), int(np.flatnonzero(a == m)[-1])
+
+
+def maxdet_swapcols(R: Optional[np.ndarray], p: np.ndarray, T: np.ndarray, opts: LRAOptions, retr: bool) -> int:
+    """src/pqr.jl:444-501 for the factors this path returns (p, T and, if requested, R1): while max|T| > 1 + tol,
+    swap skeleton column i with redundant column j and update T by Sherman-Morrison (maxdet_update!, :481-501).
+    The final re-triangularisation of R1 / update of Q (:467-476) is only needed when Q or R are returned from the
+    sketch itself, which no caller on this path does (pqrfact recomputes them from A[:, sk], src/pqr.jl:297-305).
+    Returns the number of swaps."""
+    k, nk = T.shape
+    niter = 0
+    while True:
+        tmax, idx = findmaxabs(T)
+        if tmax <= 1 + opts.maxdet_tol:
+            break
+        if niter == opts.maxdet_niter:
+            break
+        niter += 1
+        i, j = idx % k, idx // k
+        p[i], p[k + j] = p[k + j], p[i]
+        w1 = T[:, j].copy()
+        T[:, j] = 0.0
+        w1[i] -= 1.0
+        T[i, j] = 1.0
+        w2 = T[i, :].copy()
+        alpha = -1.0 / (1.0 + w1[i])
+        T += alpha * np.outer(w1, w2)              # BLAS.ger!
+        if retr and R is not None:
+            R[:, i] += R[:, :k] @ w1
+    return niter
+
+
 def pqrback_postproc(B: np.ndarray, p: np.ndarray, tau: np.ndarray, k: int, opts: LRAOptions) -> PQRFactors:
-    """src/pqr.jl:420-436 (maxdet branch not restated: maxdet_tol < 0 by default)."""
+    """src/pqr.jl:420-436."""
     retq = "q" in opts.pqrfact_retval
     retr = "r" in opts.pqrfact_retval
     rett = "t" in opts.pqrfact_retval
-    if 0 < k < B.shape[1] and opts.maxdet_tol >= 0:
-        raise NotImplementedError("maxdet_swapcols! is outside the restated path (SURVEY 8f-1)")
+    maxdet = 0 < k < B.shape[1] and opts.maxdet_tol >= 0
+    if maxdet and (retq or retr):
+        raise NotImplementedError("maxdet with Q/R returned from the sketch is outside the restated path")
     Q = dorgqr(B[:, :k], tau[:k]) if retq else None
-    R = np.triu(B[:k, :]) if (retr or rett) else None
-    T = dtrsm_upper(R[:, :k], R[:, k:]) if rett else None
+    R = np.triu(B[:k, :]) if (retr or rett or maxdet) else None
+    T = dtrsm_upper(R[:, :k], R[:, k:]) if (rett or maxdet) else None
+    if maxdet:
+        maxdet_swapcols(None, p, T, opts, False)
     return PQRFactors(Q, R if retr else None, p, k, T)
 
 

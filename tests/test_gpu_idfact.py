@@ -120,4 +120,44 @@ def test_errors_mirror_reference(ctx):
     with pytest.raises(ValueError):
         brapprox.idfact(A, trans="x", ctx=ctx)          # ArgumentError("trans")
     with pytest.raises(brapprox.BraError):
-        brapprox.idfact(A, maxdet_tol=0.0, ctx=ctx)     # unsupported -> loud, never a CPU fallback
+        brapprox.idfact(A, sketch_randn_niter=1, ctx=ctx)   # unsupported -> loud, never a CPU fallback
+    with pytest.raises(brapprox.BraError):
+        brapprox.pqrfact(np.ones((8, 8)), maxdet_tol=0.0, ctx=ctx)   # tails on a maxdet-refined ID: not built
+
+
+@pytest.mark.parametrize("m,n,r,rtol,tol", [(300, 200, 60, 1e-9, 0.0), (512, 640, 100, 1e-10, 0.0), (256, 384, 40, 1e-8, 0.25)])
+def test_idfact_maxdet_matches_oracle(ctx, m, n, r, rtol, tol):
+    """Strong-RRQR post-processing (maxdet_swapcols!, src/pqr.jl:444-501).
+    Stage-wise (the parity statement): the SAME (p, T) in => the same swap sequence, p and T out as the oracle's
+    restatement.  End to end T carries a forward sensitivity of eps/rtol (hard part 3), so the
+    arg-max sequence of two correct implementations may part ways at near-ties of |T|; there the invariants are
+    checked: k equal, max|T| <= 1 + tol, reconstruction error within 2x of the oracle's."""
+    import brapprox
+    A = o.decaying_matrix(m, n, r, 10.0, r, seed=m + 7 * n)
+    rin = o.RandomInputs(3)
+    Vo = o.idfact(A, o.LRAOptions(rtol=rtol, maxdet_tol=tol), rin)
+    V0 = brapprox.idfact(A, rtol=rtol, rand=rin.drawn, ctx=ctx)                       # GPU, no maxdet
+    Vg = brapprox.idfact(A, rtol=rtol, maxdet_tol=tol, rand=rin.drawn, ctx=ctx)       # GPU, maxdet
+    assert Vg.k == Vo.k == V0.k
+    assert np.abs(V0.T).max() > 1 + tol, "the case must actually trigger swaps"
+    assert np.abs(Vg.T).max() <= 1 + tol + 1e-12
+    # stage-wise: the oracle's swap loop on the GPU's own pre-maxdet (p, T)
+    p1, T1 = V0.p.copy(), np.array(V0.T, order="F", copy=True)
+    nsw = o.maxdet_swapcols(None, p1, T1, o.LRAOptions(maxdet_tol=tol), False)
+    assert nsw == ctx.maxdet_swaps() and nsw > 0
+    np.testing.assert_array_equal(Vg.p, p1)
+    assert np.max(np.abs(Vg.T - T1)) <= 1e-12 * max(1.0, np.abs(T1).max())
+    # end to end
+    assert o.id_error(A, Vg) <= 2 * o.id_error(A, Vo) + 1e-15
+    assert o.id_error(A, Vg) <= 2 * o.id_error(A, V0) + 1e-15
+
+
+def test_idfact_maxdet_niter_limit(ctx):
+    """maxdet_niter caps the number of swaps (src/pqr.jl:456-461)."""
+    import brapprox
+    A = o.decaying_matrix(300, 200, 60, 10.0, 60, seed=3)
+    rin = o.RandomInputs(0)
+    Vo = o.idfact(A, o.LRAOptions(rtol=1e-9, maxdet_tol=0.0, maxdet_niter=2), rin)
+    Vg = brapprox.idfact(A, rtol=1e-9, maxdet_tol=0.0, maxdet_niter=2, rand=rin.drawn, ctx=ctx)
+    np.testing.assert_array_equal(Vg.p, Vo.p)
+    assert ctx.maxdet_swaps() == 2
