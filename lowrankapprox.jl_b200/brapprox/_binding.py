@@ -13,7 +13,7 @@ SKETCH_CODES = {"none": 0, "randn": 1, "sprn": 2, "srft": 3, "sub": 4}
 RET_Q, RET_R, RET_T = 1, 2, 4
 F_P, F_T, F_Q, F_R, F_U, F_S, F_VT, F_TAU, F_BSKETCH = 1, 2, 3, 4, 5, 6, 7, 8, 9
 
-lib_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbrapprox.so")
+lib_path = os.environ.get("BRA_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbrapprox.so")
 
 
 class BraError(RuntimeError):

@@ -303,9 +303,11 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_kernel(QrcpParams p) {
       if (lane == 0) sred[warp] = ss;
       __syncthreads();
       if (cand_lc >= 0) {
-        double ssq = 0.0;
+        // pairwise (4 levels instead of a 16-long dependent chain of FP64 adds)
+        double t8[8];
 #pragma unroll
-        for (int w = 0; w < QR_WARPS; ++w) ssq += sred[w];
+        for (int w = 0; w < 8; ++w) t8[w] = sred[2 * w] + sred[2 * w + 1];
+        const double ssq = ((t8[0] + t8[1]) + (t8[2] + t8[3])) + ((t8[4] + t8[5]) + (t8[6] + t8[7]));
         const double alpha = a[s];
         double beta, tau, scale;
         if (s >= l - 1 || ssq == 0.0) {
@@ -331,40 +333,41 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_kernel(QrcpParams p) {
     QR_TICK(1)
 
     // ---- gather my inbox (G contiguous 32-byte words), pick the winner ----
-    if (tid < G) {
-      double v;
-      int lp, fl;
-      if (!ll32_load(p.inbox + ((size_t)par * G + cta) * G + tid, stamp, v, lp, fl)) s_fail = 1;
-      hv[tid] = v;
-      hlp[tid] = lp;
-      hflag[tid] = fl;
+    // two levels: the ceil(G/32) warps that hold the headers in registers reduce them with redux.sync right away and
+    // park one partial winner each; after the barrier every warp merges those <= 5 partials (instead of every warp
+    // scanning all G headers out of shared memory)
+    const int GW = (G + 31) >> 5;
+    if (warp < GW) {
+      double v = -1.0;
+      int lp = 0x7fffffff, fl = 0;
+      if (tid < G && !ll32_load(p.inbox + ((size_t)par * G + cta) * G + tid, stamp, v, lp, fl)) s_fail = 1;
+      const int wl = warp_argmax(v, lp);
+      const double bv = __shfl_sync(0xffffffffu, v, wl);
+      const int blp = __shfl_sync(0xffffffffu, lp, wl);
+      const unsigned af = __reduce_or_sync(0xffffffffu, (unsigned)fl);
+      if (lane == 0) {
+        hv[warp] = bv;
+        hlp[warp] = blp;
+        hflag[warp] = (int)af;
+        hflag[MAXG / 2 + warp] = (warp << 5) + wl;        // source CTA of this partial winner
+      }
     }
     __syncthreads();
     if (s_fail) {
       failed = true;
       break;
     }
-    // every warp reduces the G headers redundantly (no second barrier)
     int wcta;
     {
-      // lane-local best over its <= ceil(G/32) headers first, then one warp argmax
-      double bv = -1.0;
-      int blp = 0x7fffffff, bsrc = -1, aflag = 0;
-      for (int t = lane; t < G; t += 32) {
-        const double v = hv[t];
-        const int lp = hlp[t];
-        aflag |= hflag[t];
-        if (cand_better(v, lp, bv, blp)) {
-          bv = v;
-          blp = lp;
-          bsrc = t;
-        }
-      }
-      const int wl = warp_argmax(bv, blp);
-      wcta = __shfl_sync(0xffffffffu, bsrc, wl);
-      c.v = __shfl_sync(0xffffffffu, bv, wl);       // reuse c as the gathered result
-      c.lp = __shfl_sync(0xffffffffu, blp, wl);
-      c.flag = (int)__reduce_or_sync(0xffffffffu, (unsigned)aflag);
+      const double v = (lane < GW) ? hv[lane] : -1.0;
+      const int lp = (lane < GW) ? hlp[lane] : 0x7fffffff;
+      const int fl = (lane < GW) ? hflag[lane] : 0;
+      const int src = (lane < GW) ? hflag[MAXG / 2 + lane] : -1;
+      const int wl = warp_argmax(v, lp);
+      wcta = __shfl_sync(0xffffffffu, src, wl);
+      c.v = __shfl_sync(0xffffffffu, v, wl);        // reuse c as the gathered result
+      c.lp = __shfl_sync(0xffffffffu, lp, wl);
+      c.flag = (int)__reduce_or_sync(0xffffffffu, (unsigned)fl);
     }
     const int lw = c.lp;               // winner's logical position
     QR_TICK(2)
@@ -496,10 +499,34 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_kernel(QrcpParams p) {
               }
               dot[cc] = d0 + d1;
             }
+            // packed butterflies: each sum keeps the association of the plain xor butterfly (bitwise the same result),
+            // but CB sums cost CB+2 (CB = 4) or 6 (CB = 2) exchanges instead of 5 CB
+            if (CB == 4) {
+              const bool h16 = lane & 16, h8 = lane & 8;
+              const double wa = (h16 ? dot[2] : dot[0]) + __shfl_xor_sync(0xffffffffu, h16 ? dot[0] : dot[2], 16);
+              const double wb = (h16 ? dot[3] : dot[1]) + __shfl_xor_sync(0xffffffffu, h16 ? dot[1] : dot[3], 16);
+              double w = (h8 ? wb : wa) + __shfl_xor_sync(0xffffffffu, h8 ? wa : wb, 8);
+              w += __shfl_xor_sync(0xffffffffu, w, 4);
+              w += __shfl_xor_sync(0xffffffffu, w, 2);
+              w += __shfl_xor_sync(0xffffffffu, w, 1);
+              // sum 0 in lanes 0-7, sum 1 in 8-15, sum 2 in 16-23, sum 3 in 24-31
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
+              for (int cc = 0; cc < 4; ++cc) dot[cc] = __shfl_sync(0xffffffffu, w, 8 * cc);
+            } else if (CB == 2) {
+              const bool h16 = lane & 16;
+              double w = (h16 ? dot[1] : dot[0]) + __shfl_xor_sync(0xffffffffu, h16 ? dot[0] : dot[1], 16);
+              w += __shfl_xor_sync(0xffffffffu, w, 8);
+              w += __shfl_xor_sync(0xffffffffu, w, 4);
+              w += __shfl_xor_sync(0xffffffffu, w, 2);
+              w += __shfl_xor_sync(0xffffffffu, w, 1);
+              dot[0] = __shfl_sync(0xffffffffu, w, 0);
+              dot[1 % CB] = __shfl_sync(0xffffffffu, w, 16);
+            } else {
 #pragma unroll
-              for (int cc = 0; cc < CB; ++cc) dot[cc] += __shfl_xor_sync(0xffffffffu, dot[cc], o);
+              for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int cc = 0; cc < CB; ++cc) dot[cc] += __shfl_xor_sync(0xffffffffu, dot[cc], o);
+              }
             }
 #pragma unroll
             for (int cc = 0; cc < CB; ++cc) {
