@@ -260,7 +260,7 @@ int bra_destroy(bra_ctx* ctx) {
                     &ctx->vn2, &ctx->lpos, &ctx->fpend, &ctx->rec, &ctx->jpvt, &ctx->tau, &ctx->rdiag, &ctx->info,
                     &ctx->kbtrace, &ctx->R11, &ctx->T, &ctx->C, &ctx->Q, &ctx->R1, &ctx->Rfull, &ctx->W, &ctx->G,
                     &ctx->U, &ctx->S, &ctx->Vt, &ctx->Z, &ctx->scratch, &ctx->scratch2, &ctx->scratch3,
-                    &ctx->aux_in1, &ctx->aux_in2, &ctx->jwork, &ctx->At, &ctx->rinv, &ctx->yt, &ctx->Apanels};
+                    &ctx->aux_in1, &ctx->aux_in2, &ctx->jwork, &ctx->At, &ctx->rinv, &ctx->yt, &ctx->Apanels, &ctx->tritmp};
   for (DevBuf* b : bufs) b->release();
   bra_comm_destroy(ctx);
   if (ctx->h_info) cudaFreeHost(ctx->h_info);

@@ -314,10 +314,14 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
   } else {
     // Yh = R_z^{-1} Ysel (k x kk);  Vop' = Yh' [I T]: the first k columns are Yh' itself, the rest one TN product with T
     {
+      // R_z is well conditioned: explicit blocked inverse (log-depth, fully parallel) + one k x k x kk product
       ProfScope ps(ctx, BRA_PROF_QR);
-      rc = bra_trsolve_upper_fast(ctx, (int)k, kk, Rz, k, Ysel, ldj);
+      if ((rc = bra_set_identity(ctx, (int)k, Rinv2, ldj))) return rc;
+      if ((rc = bra_tri_inverse_upper(ctx, (int)k, Rz, k, Rinv2, ldj))) return rc;
     }
+    rc = bra_gemm_generic(ctx, Rinv2, 1, ldj, Ysel, 1, ldj, k, kk, k, Q2, ldj);              // Yh = R_z^{-1} Ysel
     if (rc) return rc;
+    BRA_CUDA(cudaMemcpyAsync(Ysel, Q2, (size_t)ldj * kk * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     rc = bra_transpose(ctx, Ysel, ldj, k, kk, ctx->B2.as<double>(), even(kk));
     if (rc) return rc;
     if (nA > k) {

@@ -90,6 +90,7 @@ struct bra_ctx {
   DevBuf aux_in1, aux_in2;     // staged random inputs (d, idx, perm, s, r)
   DevBuf jwork;                // Jacobi SVD: grid barrier, per-sweep flags
   DevBuf rinv, yt;             // CholeskyQR: explicit triangular inverse, transposed panels
+  DevBuf tritmp;               // blocked triangular inverse: B C^{-1} scratch
   int last_jacobi_sweeps = 0;
   int jacobi_kcycles[8] = {0};
   std::vector<unsigned char> h_meta;  // host scratch for fast-mode index/sign generation
@@ -226,3 +227,4 @@ int bra_maxdet_swapcols(bra_ctx* ctx, int k, int64_t ncols, double* T, int64_t l
 int bra_trsolve_upper(bra_ctx* ctx, int k, int64_t nrhs, const double* R11, int64_t ldr, double* X, int64_t ldx);
 int bra_trsolve_upper_fast(bra_ctx* ctx, int k, int64_t nrhs, const double* R, int64_t ldr, double* X, int64_t ldx);
 int bra_tri_inverse_upper(bra_ctx* ctx, int k, const double* R, int64_t ldr, double* Rinv, int64_t ldx);
+int bra_tri_inverse_upper_subst(bra_ctx* ctx, int k, const double* R, int64_t ldr, double* Rinv, int64_t ldx);
