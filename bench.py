@@ -144,7 +144,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    what = "idfact" if args.what == "auto" else args.what
+    # same metric as our arm: `auto` means psvdfact there (the library has the psvd tail), so it does here
+    what = "psvdfact" if args.what == "auto" else args.what
     base, times = cpu_sample(args.n, what, max_seconds=60.0)
     # honour --steps/--warmup within a bounded budget: the sample above already ran >= 2 factorizations
     v = base["value"]

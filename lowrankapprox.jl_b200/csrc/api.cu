@@ -14,6 +14,8 @@ namespace {
 cudaError_t copy2d(bra_ctx* ctx, void* dst, int64_t ldd, const void* src, int64_t lds, int64_t rows, int64_t cols,
                    size_t elem = 8) {
   if (rows <= 0 || cols <= 0) return cudaSuccess;
+  if (ldd == rows && lds == rows)      // contiguous on both sides: one linear copy (full PCIe rate for host sources)
+    return cudaMemcpyAsync(dst, src, (size_t)rows * (size_t)cols * elem, cudaMemcpyDefault, ctx->stream);
   return cudaMemcpy2DAsync(dst, (size_t)ldd * elem, src, (size_t)lds * elem, (size_t)rows * elem, (size_t)cols,
                            cudaMemcpyDefault, ctx->stream);
 }
@@ -260,7 +262,7 @@ int bra_destroy(bra_ctx* ctx) {
                     &ctx->vn2, &ctx->lpos, &ctx->fpend, &ctx->rec, &ctx->jpvt, &ctx->tau, &ctx->rdiag, &ctx->info,
                     &ctx->kbtrace, &ctx->R11, &ctx->T, &ctx->C, &ctx->Q, &ctx->R1, &ctx->Rfull, &ctx->W, &ctx->G,
                     &ctx->U, &ctx->S, &ctx->Vt, &ctx->Z, &ctx->scratch, &ctx->scratch2, &ctx->scratch3,
-                    &ctx->aux_in1, &ctx->aux_in2, &ctx->jwork, &ctx->At, &ctx->rinv, &ctx->yt, &ctx->Apanels, &ctx->tritmp};
+                    &ctx->aux_in1, &ctx->aux_in2, &ctx->jwork, &ctx->At, &ctx->rinv, &ctx->yt, &ctx->Apanels, &ctx->tritmp, &ctx->cholscr};
   for (DevBuf* b : bufs) b->release();
   bra_comm_destroy(ctx);
   if (ctx->h_info) cudaFreeHost(ctx->h_info);

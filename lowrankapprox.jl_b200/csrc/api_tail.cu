@@ -63,9 +63,13 @@ int bra_pqrfact_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double
     } else {
       dlda = even(m);
       BRA_CUDA(ctx->A_stage.reserve((size_t)dlda * (n > 0 ? n : 1) * 8));
-      if (m > 0 && n > 0)
-        BRA_CUDA(cudaMemcpy2DAsync(ctx->A_stage.p, (size_t)dlda * 8, A, (size_t)lda * 8, (size_t)m * 8, (size_t)n,
-                                   cudaMemcpyDefault, ctx->stream));
+      if (m > 0 && n > 0) {
+        if (dlda == m && lda == m)
+          BRA_CUDA(cudaMemcpyAsync(ctx->A_stage.p, A, (size_t)m * n * 8, cudaMemcpyDefault, ctx->stream));
+        else
+          BRA_CUDA(cudaMemcpy2DAsync(ctx->A_stage.p, (size_t)dlda * 8, A, (size_t)lda * 8, (size_t)m * 8, (size_t)n,
+                                     cudaMemcpyDefault, ctx->stream));
+      }
       dA = ctx->A_stage.as<double>();
     }
   }
@@ -115,9 +119,13 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
   } else {
     dlda = even(m);
     BRA_CUDA(ctx->A_stage.reserve((size_t)dlda * (n > 0 ? n : 1) * 8));
-    if (m > 0 && n > 0)
-      BRA_CUDA(cudaMemcpy2DAsync(ctx->A_stage.p, (size_t)dlda * 8, A, (size_t)lda * 8, (size_t)m * 8, (size_t)n,
-                                 cudaMemcpyDefault, ctx->stream));
+    if (m > 0 && n > 0) {
+      if (dlda == m && lda == m)
+        BRA_CUDA(cudaMemcpyAsync(ctx->A_stage.p, A, (size_t)m * n * 8, cudaMemcpyDefault, ctx->stream));
+      else
+        BRA_CUDA(cudaMemcpy2DAsync(ctx->A_stage.p, (size_t)dlda * 8, A, (size_t)lda * 8, (size_t)m * 8, (size_t)n,
+                                   cudaMemcpyDefault, ctx->stream));
+    }
     dA = ctx->A_stage.as<double>();
   }
   if (opts->maxdet_tol >= 0) {

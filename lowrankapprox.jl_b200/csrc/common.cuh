@@ -91,6 +91,7 @@ struct bra_ctx {
   DevBuf jwork;                // Jacobi SVD: grid barrier, per-sweep flags
   DevBuf rinv, yt;             // CholeskyQR: explicit triangular inverse, transposed panels
   DevBuf tritmp;               // blocked triangular inverse: B C^{-1} scratch
+  DevBuf cholscr;              // blocked Cholesky: inverse of the current diagonal block
   int last_jacobi_sweeps = 0;
   int jacobi_kcycles[8] = {0};
   std::vector<unsigned char> h_meta;  // host scratch for fast-mode index/sign generation

@@ -117,19 +117,27 @@ __global__ void __launch_bounds__(256) trsolve_right_upper_kernel(int64_t rows, 
   }
 }
 
-// ---- blocked Cholesky G = L L^T (lower, in place), k x k ----
-// panel: ONE WARP per 32-row block.  Lane r keeps row r of the 32 x 32 diagonal block in registers and factors it
-// with shuffles (no shared memory, no barriers, reciprocal square roots instead of sqrt + divide); every warp does
-// this redundantly, then solves its own row block X L_jj^T = P in "axpy" form (independent FMAs per column instead of
-// a dependent dot-product chain), reading L_jj straight from the factoring lanes' registers.
-__global__ void __launch_bounds__(32) chol_panel_kernel(int k, int j0, double* __restrict__ G, int64_t ldg, int* info) {
+// ---- blocked Cholesky G = L L^T, k x k; the factor is written TRANSPOSED (R = L^T, upper) into a separate matrix ----
+// Per 32-column panel j two launches:
+//  chol_diag_kernel   one warp: lane r keeps row r of the diagonal block in registers and factors it with shuffles
+//                     (no barriers, reciprocal square roots), then inverts L_jj by column-oriented substitution; L_jj
+//                     goes to R, L_jj^{-1} to a 32 x 32 scratch.
+//  chol_trail_kernel  one CTA per trailing tile (I >= J): forms the two panel blocks it needs itself,
+//                     L_I = P_I L_jj^{-T} and L_J = P_J L_jj^{-T} (small products, no substitution chain, no separate
+//                     panel-solve launch), updates G[I,J] -= L_I L_J^T, and the J = 0 column of CTAs stores L_I into R.
+//                     The unsolved panel blocks P stay untouched in G (nobody reads them after this launch), so there
+//                     is no read/write race between CTAs.
+__global__ void __launch_bounds__(32) chol_diag_kernel(int k, int j0, const double* __restrict__ G, int64_t ldg,
+                                                       double* __restrict__ R, int64_t ldr, double* __restrict__ Dinv,
+                                                       int* info) {
+  __shared__ double Ls[TB][TB + 1];
   const int lane = threadIdx.x;
   const int jbsz = min(TB, k - j0);
   double a[TB];      // row `lane` of the diagonal block (lower triangle meaningful)
 #pragma unroll
   for (int c = 0; c < TB; ++c)
     a[c] = (lane < jbsz && c < jbsz) ? G[(j0 + lane) + (int64_t)(j0 + c) * ldg] : (lane == c ? 1.0 : 0.0);
-  double rs[TB];     // 1 / L[c][c]
+  double rsd = 1.0;  // lane c keeps 1 / L[c][c]
 #pragma unroll
   for (int c = 0; c < TB; ++c) {
     double d = __shfl_sync(0xffffffffu, a[c], c);
@@ -137,8 +145,9 @@ __global__ void __launch_bounds__(32) chol_panel_kernel(int k, int j0, double* _
       if (lane == 0 && c < jbsz) atomicExch(info, j0 + c + 1);
       d = 1.0;
     }
-    rs[c] = rsqrt(d);
-    const double l = (lane == c) ? d * rs[c] : a[c] * rs[c];      // column c of L (rows >= c meaningful)
+    const double rs = rsqrt(d);
+    if (lane == c) rsd = rs;
+    const double l = (lane == c) ? d * rs : a[c] * rs;              // column c of L (rows >= c meaningful)
     a[c] = l;
 #pragma unroll
     for (int cc = c + 1; cc < TB; ++cc) {
@@ -146,42 +155,37 @@ __global__ void __launch_bounds__(32) chol_panel_kernel(int k, int j0, double* _
       a[cc] = fma(-l, lcc, a[cc]);
     }
   }
-  const int rb = blockIdx.x;        // 0: the diagonal block itself; b > 0: row block j0 + 32*b
-  if (rb == 0) {
-    if (lane < jbsz) {
 #pragma unroll
-      for (int c = 0; c < TB; ++c)
-        if (c < jbsz) G[(j0 + lane) + (int64_t)(j0 + c) * ldg] = (lane >= c) ? a[c] : 0.0;
-    }
-    return;
-  }
-  const int r0 = j0 + rb * TB;
-  const bool live = (r0 + lane < k);
-  double x[TB];      // row `lane` of the row block
-#pragma unroll
-  for (int c = 0; c < TB; ++c) x[c] = (live && c < jbsz) ? G[(r0 + lane) + (int64_t)(j0 + c) * ldg] : 0.0;
-#pragma unroll
-  for (int c = 0; c < TB; ++c) {
-    x[c] *= rs[c];
-#pragma unroll
-    for (int cc = c + 1; cc < TB; ++cc) {
-      const double lcc = __shfl_sync(0xffffffffu, a[c], cc);        // L[cc][c] lives in lane cc
-      x[cc] = fma(-x[c], lcc, x[cc]);
-    }
-  }
-  if (live) {
+  for (int c = 0; c < TB; ++c) Ls[lane][c] = (c <= lane) ? a[c] : 0.0;
+  if (lane < jbsz) {
 #pragma unroll
     for (int c = 0; c < TB; ++c)
-      if (c < jbsz) G[(r0 + lane) + (int64_t)(j0 + c) * ldg] = x[c];
+      if (c <= lane) R[(j0 + c) + (int64_t)(j0 + lane) * ldr] = a[c];      // R = L^T
   }
+  __syncwarp();
+  // lane j solves L v = e_j (column j of L^{-1}); once v_c is known it is eliminated from the rows below
+  double v[TB];
+#pragma unroll
+  for (int r = 0; r < TB; ++r) v[r] = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+  for (int c = 0; c < TB; ++c) {
+    v[c] *= __shfl_sync(0xffffffffu, rsd, c);
+#pragma unroll
+    for (int r = c + 1; r < TB; ++r) v[r] = fma(-Ls[r][c], v[c], v[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < TB; ++r) Dinv[r + lane * TB] = v[r];        // Dinv[r][j] = (L^{-1})[r][j], column-major 32 x 32
 }
 
-// trailing update: G[I,J] -= L[I,j] L[J,j]^T for 32x32 tiles I >= J > j
-__global__ void __launch_bounds__(256) chol_update_kernel(int k, int j0, double* __restrict__ G, int64_t ldg) {
+__global__ void __launch_bounds__(256) chol_trail_kernel(int k, int j0, double* __restrict__ G, int64_t ldg,
+                                                         double* __restrict__ R, int64_t ldr,
+                                                         const double* __restrict__ Dinv) {
+  __shared__ double Pi[TB][TB + 1];   // P_I, then reused
+  __shared__ double Pj[TB][TB + 1];
+  __shared__ double Di[TB][TB + 1];   // L_jj^{-1}
   __shared__ double Li[TB][TB + 1];
   __shared__ double Lj[TB][TB + 1];
   const int tid = threadIdx.x;
-  const int nb = (k - j0 - 1) / TB;          // trailing blocks (those after block j)
   // linear index -> (I, J), I >= J
   int t = blockIdx.x, I = 0;
   while (t > I) {
@@ -189,22 +193,49 @@ __global__ void __launch_bounds__(256) chol_update_kernel(int k, int j0, double*
     ++I;
   }
   const int J = t;
-  if (I >= nb) return;
   const int ri = j0 + (I + 1) * TB, rj = j0 + (J + 1) * TB;
   for (int e = tid; e < TB * TB; e += 256) {
     const int rr = e & 31, cc = e >> 5;
-    Li[rr][cc] = (ri + rr < k && j0 + cc < k && cc < TB) ? G[(ri + rr) + (int64_t)(j0 + cc) * ldg] : 0.0;
-    Lj[rr][cc] = (rj + rr < k && j0 + cc < k && cc < TB) ? G[(rj + rr) + (int64_t)(j0 + cc) * ldg] : 0.0;
+    Pi[rr][cc] = (ri + rr < k && j0 + cc < k) ? G[(ri + rr) + (int64_t)(j0 + cc) * ldg] : 0.0;
+    Pj[rr][cc] = (rj + rr < k && j0 + cc < k) ? G[(rj + rr) + (int64_t)(j0 + cc) * ldg] : 0.0;
+    Di[rr][cc] = Dinv[rr + cc * TB];
   }
   __syncthreads();
   const int tx = tid & 31, ty = tid >> 5;
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int c = ty * 4 + u;
-    double acc = 0.0;
+  // L_I[r][c] = sum_{t <= c} P_I[r][t] * Linv[c][t]
+  {
+    double ai[4] = {0.0, 0.0, 0.0, 0.0}, aj[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 8
-    for (int kk = 0; kk < TB; ++kk) acc = fma(Li[tx][kk], Lj[c][kk], acc);
-    if (ri + tx < k && rj + c < k) G[(ri + tx) + (int64_t)(rj + c) * ldg] -= acc;
+    for (int kk = 0; kk < TB; ++kk) {
+      const double pi = Pi[tx][kk], pj = Pj[tx][kk];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double dv = Di[ty * 4 + u][kk];       // zero above the diagonal (kk > c)
+        ai[u] = fma(pi, dv, ai[u]);
+        aj[u] = fma(pj, dv, aj[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      Li[tx][ty * 4 + u] = ai[u];
+      Lj[tx][ty * 4 + u] = aj[u];
+      if (J == 0 && ri + tx < k && j0 + ty * 4 + u < k) R[(j0 + ty * 4 + u) + (int64_t)(ri + tx) * ldr] = ai[u];
+    }
+  }
+  __syncthreads();
+  {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 8
+    for (int kk = 0; kk < TB; ++kk) {
+      const double x = Li[tx][kk];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] = fma(x, Lj[ty * 4 + u][kk], acc[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = ty * 4 + u;
+      if (ri + tx < k && rj + c < k) G[(ri + tx) + (int64_t)(rj + c) * ldg] -= acc[u];
+    }
   }
 }
 
@@ -681,17 +712,20 @@ int bra_cholesky_upper(bra_ctx* ctx, int k, double* G, int64_t ldg, double* Rout
   if (k <= 0) return BRA_OK;
   ProfScope ps(ctx, BRA_PROF_QR);
   int* info = ctx->info.as<int>() + 12;      // sticky: reset by bra_chol_status_reset, read by bra_chol_status
+  BRA_CUDA(ctx->cholscr.reserve((size_t)TB * TB * 8));
+  double* Dinv = ctx->cholscr.as<double>();
+  BRA_CUDA(cudaMemset2DAsync(Rout, (size_t)ldr * 8, 0, (size_t)k * 8, (size_t)k, ctx->stream));    // zeros below the diagonal
   const int nblk = (k + TB - 1) / TB;
   for (int jb = 0; jb < nblk; ++jb) {
     const int j0 = jb * TB;
-    const int rowblocks = nblk - jb;
-    chol_panel_kernel<<<rowblocks, 32, 0, ctx->stream>>>(k, j0, G, ldg, info);
+    chol_diag_kernel<<<1, 32, 0, ctx->stream>>>(k, j0, G, ldg, Rout, ldr, Dinv, info);
+    ctx->launches++;
     const int nb = nblk - jb - 1;
-    if (nb > 0) chol_update_kernel<<<nb * (nb + 1) / 2, 256, 0, ctx->stream>>>(k, j0, G, ldg);
-    ctx->launches += 2;
+    if (nb > 0) {
+      chol_trail_kernel<<<nb * (nb + 1) / 2, 256, 0, ctx->stream>>>(k, j0, G, ldg, Rout, ldr, Dinv);
+      ctx->launches++;
+    }
   }
-  tri_transpose_kernel<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(k, G, ldg, Rout, ldr);
-  ctx->launches++;
   BRA_CUDA(cudaGetLastError());
   return BRA_OK;
 }
