@@ -226,6 +226,4 @@ int bra_maxdet_swapcols(bra_ctx* ctx, int k, int64_t ncols, double* T, int64_t l
 
 // trsolve.cu
 int bra_trsolve_upper(bra_ctx* ctx, int k, int64_t nrhs, const double* R11, int64_t ldr, double* X, int64_t ldx);
-int bra_trsolve_upper_fast(bra_ctx* ctx, int k, int64_t nrhs, const double* R, int64_t ldr, double* X, int64_t ldx);
 int bra_tri_inverse_upper(bra_ctx* ctx, int k, const double* R, int64_t ldr, double* Rinv, int64_t ldx);
-int bra_tri_inverse_upper_subst(bra_ctx* ctx, int k, const double* R, int64_t ldr, double* Rinv, int64_t ldx);

@@ -239,19 +239,6 @@ __global__ void __launch_bounds__(256) chol_trail_kernel(int k, int j0, double* 
   }
 }
 
-// Rout (upper) = L^T, zeros below the diagonal
-__global__ void tri_transpose_kernel(int k, const double* __restrict__ L, int64_t ldl, double* __restrict__ R,
-                                     int64_t ldr) {
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)k * k; e += (int64_t)gridDim.x * blockDim.x) {
-    const int i = (int)(e % k), j = (int)(e / k);
-    R[i + (int64_t)j * ldr] = (i <= j) ? L[j + (int64_t)i * ldl] : 0.0;
-  }
-}
-
-__global__ void add_identity_kernel(int k, double* __restrict__ G, int64_t ldg) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) G[i + (int64_t)i * ldg] += 1.0;
-}
-
 // ---- one-sided Jacobi (Hestenes) on the columns of X (k x k), rotations accumulated into J ----
 // Block-cyclic and persistent.  The k columns form nblk blocks of BC columns; in every outer step each CTA owns one
 // block PAIR (chess-tournament schedule over the blocks), stages its 2*BC columns of X and of J in shared memory and

@@ -11,12 +11,9 @@ namespace {
 
 constexpr int TB = 32;
 
-// NC = right-hand sides per CTA (32: the ID solve, thousands of columns; 8: k x k problems, where 32-wide panels
-// would leave most of the machine idle).  RECIP: multiply by reciprocals of the diagonal, formed in parallel once per
-// block, instead of one dependent division per row (the tails' auxiliary solves; the ID solve keeps true division).
-// UPPER_RHS: the right-hand side is itself upper triangular (the identity,
-// when R11^{-1} is wanted), so rows below the panel's last column are zero and the walk starts at that block row.
-template <int NC, bool UPPER_RHS, bool RECIP>
+// NC = right-hand sides per CTA (32: the ID solve, thousands of columns; 8: narrow problems, where 32-wide panels
+// would leave most of the machine idle).
+template <int NC>
 __global__ void __launch_bounds__(256) trsolve_upper_kernel(int k, int64_t nrhs, const double* __restrict__ R,
                                                             int64_t ldr, double* __restrict__ X, int64_t ldx) {
   constexpr int NG = 256 / NC;        // row groups
@@ -25,17 +22,12 @@ __global__ void __launch_bounds__(256) trsolve_upper_kernel(int k, int64_t nrhs,
   __shared__ double Rs[TB][TB + 1];   // Rs[r][c] = R[ib*32 + r, jb*32 + c]
   __shared__ double Xs[TB][NC + 1];   // Xs[r][c] = X[jb*32 + r, col0 + c]
   __shared__ double Acc[TB][NC + 1];
-  __shared__ double Rd[TB];           // reciprocals of the diagonal block's diagonal (RECIP)
   const int tid = threadIdx.x;
   const int tx = tid % NC;            // rhs column within the panel
   const int ty = tid / NC;            // row group: rows ty*RPT .. ty*RPT+RPT-1
   const int64_t col0 = (int64_t)blockIdx.x * NC;
   const int nblk = (k + TB - 1) / TB;
-  int ib_top = nblk - 1;
-  if (UPPER_RHS) {
-    const int64_t last = (col0 + NC - 1 < (int64_t)k - 1) ? col0 + NC - 1 : (int64_t)k - 1;
-    ib_top = (int)(last / TB);
-  }
+  const int ib_top = nblk - 1;
 
   for (int ib = ib_top; ib >= 0; --ib) {
     const int r0 = ib * TB;
@@ -76,7 +68,6 @@ __global__ void __launch_bounds__(256) trsolve_upper_kernel(int k, int64_t nrhs,
     }
 #pragma unroll
     for (int u = 0; u < RPT; ++u) Acc[ty * RPT + u][tx] = acc[u];
-    if (RECIP && tid < TB) Rd[tid] = (r0 + tid < k) ? 1.0 / R[(r0 + tid) + (int64_t)(r0 + tid) * ldr] : 1.0;
     __syncthreads();
     if (ty == 0) {
       double x[TB];
@@ -84,7 +75,7 @@ __global__ void __launch_bounds__(256) trsolve_upper_kernel(int k, int64_t nrhs,
       for (int r = 0; r < TB; ++r) x[r] = Acc[r][tx];
 #pragma unroll
       for (int r = TB - 1; r >= 0; --r) {
-        x[r] = RECIP ? x[r] * Rd[r] : x[r] / Rs[r][r];
+        x[r] = x[r] / Rs[r][r];
 #pragma unroll
         for (int rr = 0; rr < r; ++rr) x[rr] = fma(-Rs[rr][r], x[r], x[rr]);
       }
@@ -104,20 +95,10 @@ __global__ void __launch_bounds__(256) trsolve_upper_kernel(int k, int64_t nrhs,
 int bra_trsolve_upper(bra_ctx* ctx, int k, int64_t nrhs, const double* R11, int64_t ldr, double* X, int64_t ldx) {
   if (k <= 0 || nrhs <= 0) return BRA_OK;
   if (nrhs >= 32 * (int64_t)ctx->num_sms) {
-    trsolve_upper_kernel<32, false, false><<<(unsigned)((nrhs + 31) / 32), 256, 0, ctx->stream>>>(k, nrhs, R11, ldr, X, ldx);
+    trsolve_upper_kernel<32><<<(unsigned)((nrhs + 31) / 32), 256, 0, ctx->stream>>>(k, nrhs, R11, ldr, X, ldx);
   } else {
-    trsolve_upper_kernel<8, false, false><<<(unsigned)((nrhs + 7) / 8), 256, 0, ctx->stream>>>(k, nrhs, R11, ldr, X, ldx);
+    trsolve_upper_kernel<8><<<(unsigned)((nrhs + 7) / 8), 256, 0, ctx->stream>>>(k, nrhs, R11, ldr, X, ldx);
   }
-  ctx->launches++;
-  BRA_CUDA(cudaGetLastError());
-  return BRA_OK;
-}
-
-// X <- R^{-1} X for the tails' auxiliary solves (well-conditioned R or results that only feed orthogonal factors):
-// 8-column panels, reciprocal diagonal.
-int bra_trsolve_upper_fast(bra_ctx* ctx, int k, int64_t nrhs, const double* R, int64_t ldr, double* X, int64_t ldx) {
-  if (k <= 0 || nrhs <= 0) return BRA_OK;
-  trsolve_upper_kernel<8, false, true><<<(unsigned)((nrhs + 7) / 8), 256, 0, ctx->stream>>>(k, nrhs, R, ldr, X, ldx);
   ctx->launches++;
   BRA_CUDA(cudaGetLastError());
   return BRA_OK;
@@ -221,16 +202,6 @@ int bra_tri_inverse_upper(bra_ctx* ctx, int k, const double* R, int64_t ldr, dou
       ctx->launches++;
     }
   }
-  BRA_CUDA(cudaGetLastError());
-  return BRA_OK;
-}
-
-// The substitution-based variant (8-column panels that skip the zero block rows); kept for cross-checking.
-// Rinv (k x k, ld ldx) <- R^{-1}; Rinv must hold the identity on entry.
-int bra_tri_inverse_upper_subst(bra_ctx* ctx, int k, const double* R, int64_t ldr, double* Rinv, int64_t ldx) {
-  if (k <= 0) return BRA_OK;
-  trsolve_upper_kernel<8, true, true><<<(unsigned)((k + 7) / 8), 256, 0, ctx->stream>>>(k, k, R, ldr, Rinv, ldx);
-  ctx->launches++;
   BRA_CUDA(cudaGetLastError());
   return BRA_OK;
 }

@@ -76,7 +76,9 @@ function idfact(trans::Symbol, A::Matrix{Float64}, opts::LRAOptions=LRAOptions()
   opts = copy(opts; args...)
   opts.pqrfact_retval = "t"
   chkopts!(opts, A)
-  (opts.sketch == :none || opts.maxdet_tol >= 0 || opts.sketch_randn_niter > 0) &&
+  # maxdet_tol / maxdet_niter run on the device (bra_maxdet: src/pqr.jl:444-501); power iteration and sketch = :none
+  # are not built and take the untouched reference path
+  (opts.sketch == :none || opts.sketch_randn_niter > 0) &&
     return invoke(LowRankApprox.idfact, Tuple{Symbol,AbstractMatrix,LRAOptions}, trans, A, opts)   # untouched path
   m, n = size(A)
   Ωs = draw_omegas(opts, trans == :n ? m : n)

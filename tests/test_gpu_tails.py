@@ -22,7 +22,7 @@ def _pair(fn_o, fn_g, A, kw, seed=0, **extra):
 
 
 @pytest.mark.parametrize("m,n,r,rtol,trans", [(1024, 768, 100, 1e-11, "n"), (600, 900, 64, 1e-9, "n"),
-                                               (512, 400, 80, 1e-10, "c")])
+                                               (512, 400, 80, 1e-10, "c"), (1600, 1300, 420, 1e-11, "n")])
 def test_pqrfact_matches_oracle(ctx, m, n, r, rtol, trans):
     import brapprox
     A = o.decaying_matrix(m, n, r, 13.0, r, seed=m + n)
@@ -53,7 +53,8 @@ def _signfix(U, Vt, Uref):
     return U * s, Vt * s[:, None]
 
 
-@pytest.mark.parametrize("m,n,r,rtol", [(1024, 768, 100, 1e-11), (700, 500, 64, 1e-8), (400, 640, 80, 1e-10)])
+@pytest.mark.parametrize("m,n,r,rtol", [(1024, 768, 100, 1e-11), (700, 500, 64, 1e-8), (400, 640, 80, 1e-10),
+                                        (1600, 1300, 420, 1e-11), (300, 260, 20, 1e-7)])
 def test_psvdfact_matches_oracle(ctx, m, n, r, rtol):
     import brapprox
     A = o.decaying_matrix(m, n, r, 13.0, r, seed=3 * m + n)
