@@ -69,6 +69,117 @@ int prepare_omega_t(bra_ctx* ctx, const bra_opts* o, const bra_rand* rnd, int ro
   return bra_fill_randn(ctx, ctx->omega_t.as<double>(), order * ldt, o->seed, (uint64_t)round);
 }
 
+// ---- Gaussian power iteration (sketch_randn_niter > 0; src/sketch.jl:140-149, 163-172; orthrows!, src/util.jl:87-97) ----
+// dst[i, jpvt[j]-1] = (i < r) ? Qp[i, j] : 0    (rows beyond the numerical rank are zero, like orthrows!(thin=false)
+// zeroes the rows beyond min(m, n))
+__global__ void orth_scatter_kernel(const double* __restrict__ Qp, int64_t ldq, int r, int64_t l, int64_t nn,
+                                    const int64_t* __restrict__ jpvt1, double* __restrict__ dst) {
+  for (int64_t j = blockIdx.x; j < nn; j += gridDim.x) {
+    const double* s = Qp + j * ldq;
+    double* d = dst + (jpvt1[j] - 1) * l;
+    for (int64_t i = threadIdx.x; i < l; i += blockDim.x) d[i] = (i < r) ? s[i] : 0.0;
+  }
+}
+
+__global__ void is_symmetric_kernel(const double* __restrict__ A, int64_t lda, int64_t n, int* __restrict__ flag) {
+  // flag = 1 on any A[i,j] != A[j,i]
+  for (int64_t j = blockIdx.x; j < n; j += gridDim.x)
+    for (int64_t i = j + 1 + threadIdx.x; i < n; i += blockDim.x)
+      if (A[i + j * lda] != A[j + i * lda]) *flag = 1;
+}
+
+// Rows of Bm (l x nn, ld = l, on the device) <- an orthonormal basis of its numerical row space, zero rows after it.
+// The reference runs LAPACK's LQ (gelqf + orglq); any orthonormal basis W Q (W orthogonal) gives the same pivots, R (up
+// to row signs) and T downstream, so the basis is built from the pieces this library already has: the
+// early-terminating QRCP of Bm (numerical rank r, pivots), its ID  Bm P = Q_s R11 [I T], and one Cholesky pass on the
+// well-conditioned Z = [I T]':  rows of R_z^{-T} [I T] P' are orthonormal and span the row space.
+int orthrows_dev(bra_ctx* ctx, const bra_opts* o, int64_t l, int64_t nn, double* Bm) {
+  const int64_t lmin = l < nn ? l : nn;
+  QrcpOut q = {0, 0, 0, 0};
+  int rc = bra_qrcp_run(ctx, Bm, l, (int)l, nn, (int)lmin, (int)o->nb, 0.0, 1e-13, &q);
+  if (rc) return rc;
+  const int64_t r = q.k;
+  if (r <= 0) {
+    BRA_CUDA(cudaMemsetAsync(Bm, 0, (size_t)l * nn * 8, ctx->stream));
+    return BRA_OK;
+  }
+  const int64_t ldr = (r + 1) & ~int64_t(1), ldz = (nn + 1) & ~int64_t(1);
+  BRA_CUDA(ctx->R11.reserve((size_t)r * r * 8));
+  BRA_CUDA(ctx->T.reserve((size_t)ldr * (nn - r > 0 ? nn - r : 1) * 8));
+  if ((rc = bra_gather_R(ctx, Bm, l, nn, (int)r, ctx->jpvt.as<int64_t>(), ctx->R11.as<double>(), ctx->T.as<double>(), ldr)))
+    return rc;
+  if (nn > r && (rc = bra_trsolve_upper(ctx, (int)r, nn - r, ctx->R11.as<double>(), r, ctx->T.as<double>(), ldr))) return rc;
+  BRA_CUDA(ctx->Z.reserve((size_t)ldz * r * 8));
+  double* Z = ctx->Z.as<double>();
+  if ((rc = bra_set_identity(ctx, (int)r, Z, ldz))) return rc;
+  if (nn > r && (rc = bra_transpose(ctx, ctx->T.as<double>(), ldr, r, nn - r, Z + r, ldz))) return rc;
+  BRA_CUDA(ctx->G.reserve((size_t)r * r * 8));
+  BRA_CUDA(ctx->W.reserve((size_t)2 * ldr * r * 8 + 64));
+  double* Rz = ctx->W.as<double>();
+  double* Rinv = Rz + (size_t)ldr * r;
+  if ((rc = bra_chol_status_reset(ctx))) return rc;
+  if ((rc = bra_gemm_tn(ctx, Z, ldz, r, nn, Z, ldz, r, ctx->G.as<double>(), r))) return rc;        // Z'Z = I + T T'
+  if ((rc = bra_cholesky_upper(ctx, (int)r, ctx->G.as<double>(), r, Rz, ldr))) return rc;
+  if ((rc = bra_set_identity(ctx, (int)r, Rinv, ldr))) return rc;
+  if ((rc = bra_tri_inverse_upper(ctx, (int)r, Rz, ldr, Rinv, ldr))) return rc;
+  // Qp = R_z^{-T} [I T]  (r x nn, pivoted column order)
+  BRA_CUDA(ctx->B2.reserve((size_t)ldr * nn * 8));
+  double* Qp = ctx->B2.as<double>();
+  if ((rc = bra_transpose(ctx, Rinv, ldr, r, r, Qp, ldr))) return rc;
+  if (nn > r && (rc = bra_gemm_tn(ctx, Rinv, ldr, r, r, ctx->T.as<double>(), ldr, nn - r, Qp + (size_t)ldr * r, ldr))) return rc;
+  orth_scatter_kernel<<<(unsigned)(nn < 148 * 8 ? nn : 148 * 8), 128, 0, ctx->stream>>>(Qp, ldr, (int)r, l, nn,
+                                                                                     ctx->jpvt.as<int64_t>(), Bm);
+  ctx->launches++;
+  BRA_CUDA(cudaGetLastError());
+  return bra_chol_status(ctx);
+}
+
+// out (order x N) = Om * op(A) for a device-resident Om (order x K, ld = order); t = 'n': op(A) = A, t = 'c': A'
+int apply_rows(bra_ctx* ctx, char t, int64_t m, int64_t n, const double* dA, int64_t lda, const double* Om, int64_t order,
+               double* out) {
+  const int64_t K = (t == 'n') ? m : n, N = (t == 'n') ? n : m;
+  const int64_t ldt = (K + 1) & ~int64_t(1);
+  BRA_CUDA(ctx->omega_t.reserve((size_t)order * ldt * 8));
+  int rc = bra_transpose_omega(ctx, Om, order, order, K, ctx->omega_t.as<double>());
+  if (rc) return rc;
+  if (t == 'n') return bra_gemm_sketch(ctx, ctx->omega_t.as<double>(), order, K, dA, lda, N, out, order);
+  return bra_gemm_generic(ctx, ctx->omega_t.as<double>(), ldt, 1, dA, lda, 1, order, N, K, out, order);
+}
+
+// the loop of sketch_randn_ln / sketch_randn_lc after the first product (ctx->B holds Bp = Omega op(A))
+int power_iterations(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* dA, int64_t lda, const bra_opts* o,
+                     int64_t order) {
+  const int64_t nA = (trans == 'n') ? n : m, mA = (trans == 'n') ? m : n;
+  const char other = (trans == 'n') ? 'c' : 'n';
+  if (ctx->A_sym_state == 0) {
+    ctx->A_sym_state = -1;
+    if (m == n) {
+      BRA_CUDA(ctx->info.reserve(64));
+      BRA_CUDA(cudaMemsetAsync(ctx->info.as<int>() + 14, 0, 4, ctx->stream));
+      is_symmetric_kernel<<<(unsigned)(n < 148 * 8 ? n : 148 * 8), 256, 0, ctx->stream>>>(dA, lda, n, ctx->info.as<int>() + 14);
+      ctx->launches++;
+      BRA_CUDA(cudaMemcpyAsync(ctx->h_info + 14, ctx->info.as<int>() + 14, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (ctx->h_info[14] == 0) ctx->A_sym_state = 1;
+    }
+  }
+  BRA_CUDA(ctx->Bq.reserve((size_t)order * mA * 8));
+  double* Bp = ctx->B.as<double>();
+  double* Bq = ctx->Bq.as<double>();
+  for (int it = 0; it < o->sketch_randn_niter; ++it) {
+    int rc = orthrows_dev(ctx, o, order, nA, Bp);
+    if (rc) return rc;
+    if ((rc = apply_rows(ctx, other, m, n, dA, lda, Bp, order, Bq))) return rc;               // Bq = Bp op(A)'
+    if (ctx->A_sym_state == 1) {
+      BRA_CUDA(cudaMemcpyAsync(Bp, Bq, (size_t)order * nA * 8, cudaMemcpyDeviceToDevice, ctx->stream));   // Bp, Bq = Bq, Bp
+    } else {
+      if ((rc = orthrows_dev(ctx, o, order, mA, Bq))) return rc;
+      if ((rc = apply_rows(ctx, trans, m, n, dA, lda, Bq, order, Bp))) return rc;             // Bp = Bq op(A)
+    }
+  }
+  return BRA_OK;
+}
+
 // B (order x nA) = Omega * op(A) into ctx->B (ld = order)
 int sketch_randn_round(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* dA, int64_t lda,
                        const bra_opts* o, const bra_rand* rnd, int round, int64_t order) {
@@ -103,7 +214,10 @@ int sketch_randn_round(bra_ctx* ctx, char trans, int64_t m, int64_t n, const dou
   else rc = bra_gemm_generic(ctx, ctx->omega_t.as<double>(), ldt, 1, dA, lda, 1, order, nA, mA, ctx->B.as<double>(), order);
   if (rc) return rc;
   // row-sharded A: B = sum over ranks of Omega_g * A_g  (one all-reduce of the l x n sketch per round)
-  return bra_allreduce_sum_f64(ctx, ctx->B.as<double>(), order * nA);
+  rc = bra_allreduce_sum_f64(ctx, ctx->B.as<double>(), order * nA);
+  if (rc) return rc;
+  if (o->sketch_randn_niter > 0) return power_iterations(ctx, trans, m, n, dA, lda, o, order);
+  return BRA_OK;
 }
 
 // a per-round random input array: device pointer to it (staging host data into `buf`)
@@ -262,7 +376,7 @@ int bra_destroy(bra_ctx* ctx) {
                     &ctx->vn2, &ctx->lpos, &ctx->fpend, &ctx->rec, &ctx->jpvt, &ctx->tau, &ctx->rdiag, &ctx->info,
                     &ctx->kbtrace, &ctx->R11, &ctx->T, &ctx->C, &ctx->Q, &ctx->R1, &ctx->Rfull, &ctx->W, &ctx->G,
                     &ctx->U, &ctx->S, &ctx->Vt, &ctx->Z, &ctx->scratch, &ctx->scratch2, &ctx->scratch3,
-                    &ctx->aux_in1, &ctx->aux_in2, &ctx->jwork, &ctx->At, &ctx->rinv, &ctx->yt, &ctx->Apanels, &ctx->tritmp, &ctx->cholscr};
+                    &ctx->aux_in1, &ctx->aux_in2, &ctx->jwork, &ctx->At, &ctx->rinv, &ctx->yt, &ctx->Apanels, &ctx->tritmp, &ctx->cholscr, &ctx->Bq};
   for (DevBuf* b : bufs) b->release();
   bra_comm_destroy(ctx);
   if (ctx->h_info) cudaFreeHost(ctx->h_info);
@@ -535,6 +649,7 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
   res.n = nA;
   ctx->At_valid = false;
   ctx->Apanels_state = 0;
+  ctx->A_sym_state = 0;
   QrcpOut q = {0, 0, 0, 0};
   int64_t order = 0;
   if (o->sketchfact_adap || o->rank < 0) {
@@ -617,8 +732,8 @@ int bra_check_fact_args(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
   BRA_CHECK_ARG(A != nullptr || m * n == 0, 5, "A");
   BRA_CHECK_ARG(lda >= (m > 1 ? m : 1), 6, "lda");
   if (bra_chkopts(ctx, opts)) return -7;
-  if (opts->sketch_randn_niter > 0) {
-    ctx->set_error("sketch_randn_niter > 0 is not built (SURVEY 8f-1)");
+  if (opts->sketch_randn_niter > 0 && ctx->world > 1) {
+    ctx->set_error("sketch_randn_niter > 0 on a row-sharded matrix is not built");
     return BRA_ERR_UNSUPPORTED;
   }
   if (opts->sketch == BRA_SKETCH_NONE) {

@@ -92,6 +92,8 @@ struct bra_ctx {
   DevBuf rinv, yt;             // CholeskyQR: explicit triangular inverse, transposed panels
   DevBuf tritmp;               // blocked triangular inverse: B C^{-1} scratch
   DevBuf cholscr;              // blocked Cholesky: inverse of the current diagonal block
+  DevBuf Bq;                   // power iteration: the sketch on the other side of A
+  int A_sym_state = 0;         // power iteration: 0 unknown, 1 A == A' exactly, -1 not (checked once per factorization)
   int last_jacobi_sweeps = 0;
   int jacobi_kcycles[8] = {0};
   std::vector<unsigned char> h_meta;  // host scratch for fast-mode index/sign generation
@@ -223,6 +225,12 @@ int bra_gemm_generic(bra_ctx* ctx, const double* Om, int64_t osi, int64_t osk, c
 // maxdet.cu
 int bra_maxdet_swapcols(bra_ctx* ctx, int k, int64_t ncols, double* T, int64_t ld, int64_t* jpvt, double tol,
                         int64_t niter_max, int64_t* nswaps);
+
+// tail.cu helpers shared with the sketch driver
+int bra_set_identity(bra_ctx* ctx, int k, double* J, int64_t ldj);
+int bra_cholesky_upper(bra_ctx* ctx, int k, double* G, int64_t ldg, double* Rout, int64_t ldr);
+int bra_chol_status_reset(bra_ctx* ctx);
+int bra_chol_status(bra_ctx* ctx);
 
 // trsolve.cu
 int bra_trsolve_upper(bra_ctx* ctx, int k, int64_t nrhs, const double* R11, int64_t ldr, double* X, int64_t ldx);

@@ -76,9 +76,9 @@ function idfact(trans::Symbol, A::Matrix{Float64}, opts::LRAOptions=LRAOptions()
   opts = copy(opts; args...)
   opts.pqrfact_retval = "t"
   chkopts!(opts, A)
-  # maxdet_tol / maxdet_niter run on the device (bra_maxdet: src/pqr.jl:444-501); power iteration and sketch = :none
-  # are not built and take the untouched reference path
-  (opts.sketch == :none || opts.sketch_randn_niter > 0) &&
+  # maxdet_tol / maxdet_niter (src/pqr.jl:444-501) and sketch_randn_niter (src/sketch.jl:140-149) run on the device;
+  # sketch = :none is not built and takes the untouched reference path
+  opts.sketch == :none &&
     return invoke(LowRankApprox.idfact, Tuple{Symbol,AbstractMatrix,LRAOptions}, trans, A, opts)   # untouched path
   m, n = size(A)
   Ωs = draw_omegas(opts, trans == :n ? m : n)

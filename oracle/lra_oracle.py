@@ -297,6 +297,42 @@ def sketch_randn(A: np.ndarray, Omega: np.ndarray, trans: str = "n") -> np.ndarr
     return dgemm(Omega, A, transb=(trans == "c"))
 
 
+def orthrows(B: np.ndarray) -> np.ndarray:
+    """orthrows!(A; thin=false) (src/util.jl:87-97): LAPACK dgelqf + dorglq, rows beyond min(m, n) zeroed."""
+    B = _fortran(B).copy(order="F")
+    m, n = B.shape
+    k = min(m, n)
+    if k == 0:
+        return B
+    tau = np.zeros(k)
+    lwork = max(1, 64 * max(m, 1))
+    work = np.zeros(lwork)
+    info = _c_int(0)
+    _lib.scipy_dgelqf_(_ref(m), _ref(n), _dptr(B), _ref(max(1, m)), _dptr(tau), _dptr(work), _ref(lwork), ctypes.byref(info))
+    _lib.scipy_dorglq_(_ref(k), _ref(n), _ref(k), _dptr(B), _ref(max(1, m)), _dptr(tau), _dptr(work), _ref(lwork),
+                       ctypes.byref(info))
+    B[k:, :] = 0.0
+    return B
+
+
+def sketch_randn_power(A: np.ndarray, Omega: np.ndarray, trans: str, niter: int) -> np.ndarray:
+    """sketch_randn_ln / sketch_randn_lc with sketch_randn_niter power steps (src/sketch.jl:129-151, 152-173):
+    Bp = Omega op(A); repeat: orthonormalise the rows, multiply by op(A)', (unless A is Hermitian) orthonormalise
+    again and multiply by op(A)."""
+    Bp = sketch_randn(A, Omega, trans)
+    isherm = A.shape[0] == A.shape[1] and np.array_equal(A, A.T)
+    other = "c" if trans == "n" else "n"
+    for _ in range(niter):
+        Bp = orthrows(Bp)
+        Bq = sketch_randn(A, Bp, other)          # Bp * op(A)'
+        if isherm:
+            Bp = Bq
+        else:
+            Bq = orthrows(Bq)
+            Bp = sketch_randn(A, Bq, trans)      # Bq * op(A)
+    return Bp
+
+
 def sketch_sub(A: np.ndarray, r: np.ndarray, trans: str = "n") -> np.ndarray:
     """B[i,:] = op(A)[r_i,:], r 1-based with replacement (src/sketch.jl:248-257,268-279)."""
     r0 = np.asarray(r, dtype=np.int64) - 1
@@ -582,8 +618,10 @@ class RandomInputs:
         return out
 
 
-def apply_sketch(kind: str, A: np.ndarray, order: int, rin: dict, trans: str) -> np.ndarray:
+def apply_sketch(kind: str, A: np.ndarray, order: int, rin: dict, trans: str, niter: int = 0) -> np.ndarray:
     if kind == "randn":
+        if niter > 0:
+            return sketch_randn_power(A, rin["Omega"], trans, niter)
         return sketch_randn(A, rin["Omega"], trans)
     if kind == "sub":
         return sketch_sub(A, rin["r"], trans)
@@ -608,7 +646,7 @@ def sketchfact(A: np.ndarray, opts: LRAOptions, rand: RandomInputs, trans: str =
         rnd = 0
         while True:
             order = sketch_order(kind, n, opts)
-            B = apply_sketch(kind, A, order, rand.draw(kind, rnd, order, m), trans)
+            B = apply_sketch(kind, A, order, rand.draw(kind, rnd, order, m), trans, opts.sketch_randn_niter)
             tr = QRCPTrace()
             p, tau, k = geqp3_adap(B, opts_, laqps, tr)
             rounds.append((order, k))
@@ -620,7 +658,7 @@ def sketchfact(A: np.ndarray, opts: LRAOptions, rand: RandomInputs, trans: str =
             n *= 2
             rnd += 1
     order = sketch_order(kind, opts.rank, opts) if kind != "sprn" else opts.rank
-    B = apply_sketch(kind, A, order, rand.draw(kind, 0, order, m), trans)
+    B = apply_sketch(kind, A, order, rand.draw(kind, 0, order, m), trans, opts.sketch_randn_niter)
     tr = QRCPTrace()
     p, tau, k = geqp3_adap(B, opts, laqps, tr)
     F = pqrback_postproc(B, p, tau, k, opts)

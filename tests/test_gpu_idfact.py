@@ -120,8 +120,6 @@ def test_errors_mirror_reference(ctx):
     with pytest.raises(ValueError):
         brapprox.idfact(A, trans="x", ctx=ctx)          # ArgumentError("trans")
     with pytest.raises(brapprox.BraError):
-        brapprox.idfact(A, sketch_randn_niter=1, ctx=ctx)   # unsupported -> loud, never a CPU fallback
-    with pytest.raises(brapprox.BraError):
         brapprox.pqrfact(np.ones((8, 8)), maxdet_tol=0.0, ctx=ctx)   # tails on a maxdet-refined ID: not built
 
 
@@ -161,3 +159,59 @@ def test_idfact_maxdet_niter_limit(ctx):
     Vg = brapprox.idfact(A, rtol=1e-9, maxdet_tol=0.0, maxdet_niter=2, rand=rin.drawn, ctx=ctx)
     np.testing.assert_array_equal(Vg.p, Vo.p)
     assert ctx.maxdet_swaps() == 2
+
+
+@pytest.mark.parametrize("case", ["decay_n", "decay_c", "symmetric", "rank_deficient", "niter2"])
+def test_idfact_power_iteration_matches_oracle(ctx, case):
+    """sketch_randn_niter > 0 (src/sketch.jl:140-149, 163-172): Omega op(A), then rounds of row orthonormalisation and
+    multiplication by op(A)' and op(A).  The reference orthonormalises with LAPACK's LQ; the device builds another
+    orthonormal basis of the same row space, which leaves the pivots, R (up to row signs) and T of the following QRCP
+    unchanged up to rounding.  On identical Omega: rounds, k and p equal the oracle's, C*T within 1e-10 ||A||, error
+    within 2x; power iteration must not make the ID worse than niter = 0."""
+    import brapprox
+    niter, trans, rtol = 1, "n", 1e-9
+    if case == "decay_n":
+        A = o.decaying_matrix(300, 200, 60, 10.0, 60, seed=3)
+    elif case == "decay_c":
+        A, trans = o.decaying_matrix(220, 320, 70, 10.0, 70, seed=5), "c"
+    elif case == "symmetric":
+        A, rtol = o.matrixlib_hilb(256), 1e-10
+    elif case == "rank_deficient":
+        rng = np.random.default_rng(7)
+        A = np.asfortranarray(rng.standard_normal((260, 20)) @ rng.standard_normal((20, 180)))   # rank 20 < order 40
+    else:
+        A, niter = o.decaying_matrix(400, 300, 90, 11.0, 90, seed=9), 2
+    rin = o.RandomInputs(4)
+    Vo = o.idfact(A, o.LRAOptions(rtol=rtol, sketch_randn_niter=niter), rin, trans)
+    Vg = brapprox.idfact(A, rtol=rtol, sketch_randn_niter=niter, trans=trans, rand=rin.drawn, ctx=ctx)
+    V0 = brapprox.idfact(A, rtol=rtol, trans=trans, rand=rin.drawn, ctx=ctx)
+    Aop = A if trans == "n" else np.asfortranarray(A.T)
+    assert Vg.rounds == Vo.rounds
+    assert Vg.k == Vo.k
+    np.testing.assert_array_equal(Vg.p[:Vg.k], Vo.p[:Vo.k])            # the skeleton, in pivot order
+    C = Aop[:, Vo.sk - 1]
+    nrm = np.linalg.norm(Aop, 2)
+    if case != "rank_deficient":        # beyond the numerical rank the order of p is rounding noise
+        np.testing.assert_array_equal(Vg.p, Vo.p)
+        assert np.max(np.abs(C @ Vg.T - C @ Vo.T)) <= 1e-10 * nrm
+    eg, eo, e0 = o.id_error(Aop, Vg), o.id_error(Aop, Vo), o.id_error(Aop, V0)
+    assert eg <= 2 * eo + 1e-14
+    assert eg <= 2 * e0 + 1e-14
+
+
+@pytest.mark.parametrize("sketch", ["randn", "sub", "srft", "sprn"])
+def test_reference_id_test_with_its_own_options(ctx, sketch):
+    """test/id.jl:4-32 with the options the reference's suite actually uses -- LRAOptions(maxdet_tol=0.,
+    sketch_randn_niter=1), rtol = 5 eps -- on the 128 x 64 Fourier (real part) matrix, both transposes, Float64:
+    ||A - A[:,sk] [I T] P'|| < 100 rtol ||A||.  (sketch = :none and the other element types are not built.)"""
+    import brapprox
+    rng = np.random.default_rng(11)
+    A = np.asfortranarray(o.matrixlib_fourier(rng.random(128), rng.random(64)).real)
+    rtol = 5 * o.EPS
+    nrm = np.linalg.norm(A)
+    for trans in ("n", "c"):
+        V = brapprox.idfact(A, rtol=rtol, sketch=sketch, maxdet_tol=0.0, sketch_randn_niter=1, trans=trans, seed=5, ctx=ctx)
+        Aop = A if trans == "n" else A.T
+        assert np.linalg.norm(Aop - Aop[:, V.sk - 1] @ V.matrix()) < 100 * rtol * nrm      # ID(:n, A, V)
+        if V.k < Aop.shape[1]:
+            assert np.abs(V.T).max() <= 1.0 + 1e-12
