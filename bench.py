@@ -168,6 +168,26 @@ def hbm_peak():
         return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback; MEASURED_PEAKS.json absent)"
 
 
+def ncu_traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the sketch GEMM from the committed `ncu --set full` capture
+    (profiles/r01e_gemm_sketch_raw.csv: one psvdfact at the C2 shape, five sketch launches), averaged per launch."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01e_gemm_sketch_raw.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        H, U = rows[0], rows[1]
+        ik, ir, iw = H.index("Kernel Name"), H.index("dram__bytes_read.sum"), H.index("dram__bytes_write.sum")
+        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot, cnt = 0.0, 0
+        for r in rows[2:]:
+            if len(r) > max(ir, iw) and "gemm_sketch" in r[ik]:
+                tot += float(r[ir].replace(",", "")) * mult[U[ir]] + float(r[iw].replace(",", "")) * mult[U[iw]]
+                cnt += 1
+        return (tot / cnt, cnt) if cnt else (None, 0)
+    except Exception:
+        return None, 0
+
+
 def _timed(ext, fn, steps, warmup, after_warmup=None):
     """CUDA events on the library's own stream around `steps` calls of fn (after `warmup` untimed calls)."""
     import torch
@@ -529,7 +549,9 @@ def main():
                                 "frac_of_fp64_peak": f_total * args.steps / tmax / 1e12 / fp64_peak},
         "roofline": {"bound": "tensor", "kernel": "gemm_sketch_kernel (TMA + DMMA m8n8k4 FP64)",
                      "achieved": gemm_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": (gemm_tf / fp64_peak) if gemm_tf else None, "traffic": None,
+                     "frac": (gemm_tf / fp64_peak) if gemm_tf else None, "traffic": ncu_traffic_per_launch()[0],
+                     "traffic_note": "bytes per launch, mean over the 5 sketch launches of one factorization, from "
+                                     "profiles/r01e_gemm_sketch_raw.csv (algorithmic: 537 MB of A + l x 8192 x 16 B)",
                      "peak_source": f"measured in this run: cuBLAS DGEMM 8192^3 = {cublas_tf:.1f} TF, "
                                     f"DMMA issue probes = {max(peaks.values()):.1f} TF "
                                     "(MEASURED_PEAKS.json has no FP64 figure)",

@@ -6,7 +6,7 @@ TAG=${1:-r01}; shift
 FAM=${@:-launches gemm qrcp tails srft batched}
 OUT=gpurun_out/prof_$TAG
 mkdir -p $OUT
-OURS='gemm_sketch|splitk|qrcp_kernel|gather_R|trsolve|fill_randn|transpose|chol_|jacobi|set_identity|col_norms|scale_cols|scatter_cols|fix_signs|gemm_generic|permute_cols|gather_cols|srft|sprn|sub_|batched|fill_meta'
+OURS='gemm_sketch|splitk|qrcp_kernel|gather_R|trsolve|fill_randn|transpose|chol_|triinv|jacobi|set_identity|col_norms|scale_cols|scatter_cols|fix_signs|gemm_generic|permute_cols|gather_cols|srft|sprn|sub_|batched|fill_meta|repack|maxabs|maxdet|orth_scatter|is_symmetric'
 FULL="ncu --set full --clock-control none --import-source on"
 export_rep () {   # name [source]
   ncu -i $OUT/$1.ncu-rep --page details --csv > $OUT/$1_details.csv 2>/dev/null
@@ -23,7 +23,8 @@ gemm)
 qrcp)
   $FULL -k regex:qrcp_kernel -c 5 -o $OUT/qrcp -f python tools/ncu_targets.py c2 > $OUT/qrcp.log 2>&1; export_rep qrcp src ;;
 tails)
-  $FULL -k regex:'trsolve_upper|jacobi|gather_R|chol_panel' -c 8 -o $OUT/tails -f python tools/ncu_targets.py c2 > $OUT/tails.log 2>&1; export_rep tails src ;;
+  $FULL -k regex:'trsolve_upper|gather_R|jacobi' -c 3 -o $OUT/tails -f python tools/ncu_targets.py c2 > $OUT/tails.log 2>&1; export_rep tails src
+  $FULL -k regex:'chol_diag|chol_trail|triinv' -s 20 -c 6 -o $OUT/chol -f python tools/ncu_targets.py c2 > $OUT/chol.log 2>&1; export_rep chol ;;
 srft)
   $FULL -k regex:'srft' -c 6 -o $OUT/srft -f python tools/ncu_targets.py c3 > $OUT/srft.log 2>&1; export_rep srft src ;;
 batched)
