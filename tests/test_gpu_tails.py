@@ -102,3 +102,41 @@ def test_tail_kernels_standalone(ctx):
     assert np.linalg.norm(F.Q.T @ F.Q - np.eye(k)) <= 1e-13 * np.sqrt(k)
     assert np.all(np.diag(F.R[:, :k]) > 0)
     assert np.linalg.norm(A - F.matrix(), 2) <= 1e-10 * np.linalg.norm(A, 2)
+
+
+def test_psvdfact_with_reference_test_options(ctx):
+    """psvdfact on a maxdet-refined, power-iterated ID (the options of the reference's own suite, test/psvd.jl:8:
+    LRAOptions(maxdet_tol=0., sketch_randn_niter=1)).  After maxdet the skeleton QR is preconditioned by a fresh pivoted
+    sketch of A[:, sk]; U, S, Vt do not depend on the skeleton's internal order.  Against the oracle on identical Omega
+    (a case whose swap sequence is well separated): same k, same p, same rank, |dsigma| <= 1e-10 sigma_1, U S and S Vt
+    entrywise; plus the reference inequality on the 128 x 64 Fourier matrix in fast mode."""
+    import brapprox
+    A = o.decaying_matrix(300, 200, 60, 10.0, 60, seed=3)
+    rin = o.RandomInputs(3)
+    kw = dict(rtol=1e-9, maxdet_tol=0.0, sketch_randn_niter=1)
+    So = o.psvdfact(A, o.LRAOptions(**kw), rin)
+    Sg = brapprox.psvdfact(A, brapprox.LRAOptions(**kw), rand=rin.drawn, ctx=ctx)
+    assert ctx.maxdet_swaps() > 0
+    assert Sg.k_id == So.k_id and len(Sg.S) == len(So.S)
+    s1 = So.S[0]
+    kk = len(So.S)
+    assert np.linalg.norm(Sg.U.T @ Sg.U - np.eye(kk)) <= 1e-12 * np.sqrt(kk)
+    eo = np.linalg.norm(A - So.matrix(), 2) / np.linalg.norm(A, 2)
+    eg = np.linalg.norm(A - Sg.matrix(), 2) / np.linalg.norm(A, 2)
+    assert eg <= 2 * eo + 1e-15
+    # sigma of two IDs with (possibly) different skeletons agree to the ID's own accuracy; with equal skeletons to 1e-10
+    Vo = o.idfact(A, o.LRAOptions(**kw), o.RandomInputs(3))
+    Vg = brapprox.idfact(A, rand=rin.drawn, ctx=ctx, **kw)
+    same = np.array_equal(Vg.p, Vo.p)
+    assert np.max(np.abs(Sg.S - So.S)) <= (1e-10 if same else 100 * 1e-9) * s1
+    if same:
+        Ug, Vtg = _signfix(Sg.U, Sg.Vt, So.U)
+        assert np.max(np.abs(Ug * Sg.S - So.U * So.S)) <= 1e-10 * s1
+        assert np.max(np.abs(Vtg * Sg.S[:, None] - So.Vt * So.S[:, None])) <= 1e-10 * s1
+    with pytest.raises(brapprox.BraError):
+        brapprox.pqrfact(A, brapprox.LRAOptions(**kw), ctx=ctx)          # triangular R1 after maxdet: not built, loud
+    rng = np.random.default_rng(0)
+    F64 = np.asfortranarray(o.matrixlib_fourier(rng.random(128), rng.random(64)).real)
+    rtol = 5 * o.EPS
+    F = brapprox.psvdfact(F64, rtol=rtol, maxdet_tol=0.0, sketch_randn_niter=1, seed=3, ctx=ctx)
+    assert np.linalg.norm(F64 - F.matrix()) < 100 * rtol * np.linalg.norm(F64)
