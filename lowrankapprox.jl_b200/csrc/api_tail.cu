@@ -25,19 +25,11 @@ struct GemmTagGuard {
 
 inline int64_t even(int64_t x) { return (x + 1) & ~int64_t(1); }
 
-// idx[j] = p[pic[j] - 1]  (1-based index arrays)
-__global__ void compose_index_kernel(const int64_t* __restrict__ p, const int64_t* __restrict__ pic, int64_t k,
-                                     int64_t* __restrict__ idx) {
-  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < k; j += (int64_t)gridDim.x * blockDim.x)
-    idx[j] = p[pic[j] - 1];
-}
-
 // After maxdet swapped columns, the sketch's R11 is no longer the triangular factor of the skeleton's sketch.  A fresh
-// (k + 8)-row Gaussian sketch of C = A[:, sk] and its pivoted QR give a new one: Omega_c C Pi = Q_c R', so C Pi R'^{-1}
-// is well conditioned.  On return ctx->Q holds C Pi (gathered in the permuted order), ctx->R11 holds R', and
-// ctx->aux_in1 the permutation Pi (k entries, 1-based).  ctx->jpvt (the factorization's p) is preserved.
-int fresh_preconditioner(bra_ctx* ctx, char trans, const double* dA, int64_t lda, int64_t mA, int64_t k,
-                         const bra_opts* o) {
+// (k + 8)-row Gaussian sketch of C = A[:, sk] and its UNPIVOTED Householder QR (the persistent QRCP kernel with the
+// pivot search switched off) give a new one in the skeleton's own column order: Omega_c C = Q_c R', so C R'^{-1} is
+// well conditioned.  On return ctx->R11 holds R'; ctx->jpvt (the factorization's p) is preserved.
+int fresh_preconditioner(bra_ctx* ctx, int64_t mA, int64_t k, const bra_opts* o) {
   const int64_t ldq = even(mA), nfull = ctx->res.n;
   const int64_t lc = (k + 8 < mA) ? k + 8 : mA;
   const int64_t ldt = even(mA);
@@ -48,29 +40,19 @@ int fresh_preconditioner(bra_ctx* ctx, char trans, const double* dA, int64_t lda
   double* Bc = ctx->B2.as<double>();
   if ((rc = bra_gemm_sketch(ctx, ctx->omega_t.as<double>(), lc, mA, ctx->Q.as<double>(), ldq, k, Bc, lc))) return rc;
   if ((rc = bra_allreduce_sum_f64(ctx, Bc, lc * k))) return rc;
-  // the QRCP driver writes its pivots into ctx->jpvt: park the factorization's p meanwhile
+  // the QR driver writes its (identity) pivots into ctx->jpvt: park the factorization's p meanwhile
   BRA_CUDA(ctx->aux_in2.reserve((size_t)nfull * 8));
   BRA_CUDA(cudaMemcpyAsync(ctx->aux_in2.p, ctx->jpvt.p, (size_t)nfull * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   QrcpOut q = {0, 0, 0, 0};
-  if ((rc = bra_qrcp_run(ctx, Bc, lc, (int)lc, k, (int)k, (int)o->nb, 0.0, 0.0, &q))) return rc;
-  BRA_CUDA(ctx->aux_in1.reserve((size_t)2 * k * 8));
-  int64_t* pic = ctx->aux_in1.as<int64_t>();
-  int64_t* idx = pic + k;
-  BRA_CUDA(cudaMemcpyAsync(pic, ctx->jpvt.p, (size_t)k * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-  BRA_CUDA(cudaMemcpyAsync(ctx->jpvt.p, ctx->aux_in2.p, (size_t)nfull * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  if ((rc = bra_qrcp_run(ctx, Bc, lc, (int)lc, k, (int)k, (int)o->nb, 0.0, 0.0, &q, /*nopivot=*/true))) return rc;
   BRA_CUDA(ctx->R11.reserve((size_t)k * k * 8));
-  if ((rc = bra_gather_R(ctx, Bc, lc, k, (int)k, pic, ctx->R11.as<double>(), ctx->R11.as<double>(), k))) return rc;   // R' (no R12)
-  compose_index_kernel<<<(unsigned)((k + 255) / 256), 256, 0, ctx->stream>>>(ctx->jpvt.as<int64_t>(), pic, k, idx);
-  ctx->launches++;
-  BRA_CUDA(cudaGetLastError());
-  return bra_gather_cols(ctx, trans, dA, lda, mA, k, idx, ctx->Q.as<double>(), ldq);                // C Pi
+  rc = bra_gather_R(ctx, Bc, lc, k, (int)k, ctx->jpvt.as<int64_t>(), ctx->R11.as<double>(), ctx->R11.as<double>(), k);   // R'
+  BRA_CUDA(cudaMemcpyAsync(ctx->jpvt.p, ctx->aux_in2.p, (size_t)nfull * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  return rc;
 }
 
-// QR of the skeleton columns: ctx->Q (mA x k, ld = even(mA)) and ctx->R1 (k x k).
-// With `o` given and a maxdet-refined skeleton, R1 comes back as the (column-permuted, no longer triangular) factor
-// with C = Q R1 in the skeleton's own order -- enough for psvdfact, which only multiplies by it.
-int skeleton_qr(bra_ctx* ctx, char trans, const double* dA, int64_t lda, int64_t mA, int64_t k,
-                const bra_opts* o = nullptr) {
+// QR of the skeleton columns: ctx->Q (mA x k, ld = even(mA)) and ctx->R1 (k x k, upper triangular).
+int skeleton_qr(bra_ctx* ctx, char trans, const double* dA, int64_t lda, int64_t mA, int64_t k, const bra_opts* o) {
   const int64_t ldq = even(mA);
   BRA_CUDA(ctx->Q.reserve((size_t)ldq * k * 8));
   BRA_CUDA(ctx->R1.reserve((size_t)k * k * 8));
@@ -78,21 +60,12 @@ int skeleton_qr(bra_ctx* ctx, char trans, const double* dA, int64_t lda, int64_t
   if (rc) return rc;
   rc = bra_gather_cols(ctx, trans, dA, lda, mA, k, ctx->jpvt.as<int64_t>(), ctx->Q.as<double>(), ldq);   // getcols
   if (rc) return rc;
-  const bool permuted = o != nullptr && ctx->res.maxdet_done;
-  if (permuted && (rc = fresh_preconditioner(ctx, trans, dA, lda, mA, k, o))) return rc;
+  if (ctx->res.maxdet_done && (rc = fresh_preconditioner(ctx, mA, k, o))) return rc;
   // Y = C R11^{-1}: R11 is the triangular factor of the SKETCH of these very columns (Omega*C = Q_B*R11)
   rc = bra_trsolve_right_upper(ctx, mA, (int)k, ctx->R11.as<double>(), k, ctx->Q.as<double>(), ldq);
   if (rc) return rc;
   rc = bra_cholqr2(ctx, mA, (int)k, ctx->Q.as<double>(), ldq, ctx->R11.as<double>(), ctx->R1.as<double>(), true);
   if (rc) return rc;
-  if (permuted) {
-    // C Pi = Q R1'  =>  C = Q (R1' Pi'): put the columns of R1' back into the skeleton's order
-    rc = bra_fix_signs(ctx, mA, (int)k, ctx->Q.as<double>(), ldq, ctx->R1.as<double>(), k);
-    if (rc) return rc;
-    BRA_CUDA(ctx->G.reserve((size_t)k * k * 8));
-    BRA_CUDA(cudaMemcpyAsync(ctx->G.p, ctx->R1.p, (size_t)k * k * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    return bra_scatter_cols(ctx, ctx->G.as<double>(), k, k, k, ctx->aux_in1.as<int64_t>(), ctx->R1.as<double>(), k);
-  }
   // R1 = R_y2 R_y1 R11 inherits the signs of diag(R11) (Householder: -sign(alpha)); normalise to diag(R1) >= 0
   return bra_fix_signs(ctx, mA, (int)k, ctx->Q.as<double>(), ldq, ctx->R1.as<double>(), k);
 }
@@ -127,19 +100,13 @@ int bra_pqrfact_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double
       dA = ctx->A_stage.as<double>();
     }
   }
-  if (opts->maxdet_tol >= 0) {
-    // a maxdet-refined skeleton gets its QR through a fresh, PIVOTED sketch preconditioner, which leaves R1 column
-    // permuted: fine for psvdfact, but pqrfact must return a triangular R1 in the reference's column order
-    ctx->set_error("pqrfact with maxdet_tol >= 0 is not built (idfact and psvdfact are); SURVEY 8f-1");
-    return BRA_ERR_UNSUPPORTED;
-  }
   rc = bra_sketchfact_core(ctx, trans, m, n, dA, dlda, opts, rnd);      // V = idfact(trans, A, opts)
   if (rc) return rc;
   FactResult& res = ctx->res;
   const int64_t k = res.k, mA = res.m, nA = res.n;
   GemmTagGuard gtag(ctx);
   if (k > 0) {
-    rc = skeleton_qr(ctx, trans, dA, dlda, mA, k);                      // F = qr!(getcols(trans, A, V[:sk]))
+    rc = skeleton_qr(ctx, trans, dA, dlda, mA, k, opts);                // F = qr!(getcols(trans, A, V[:sk]))
     if (rc) return rc;
     // R = pqrr(F.R, V[:T]) = [R1 | R1*T]   (src/pqr.jl:330-340)
     BRA_CUDA(ctx->Rfull.reserve((size_t)k * nA * 8));

@@ -56,6 +56,7 @@ struct QrcpParams {
   int64_t n;
   int kcap;
   int nb;           // effective block size = min(opts.nb, kcap)
+  int nopivot;      // 1: plain (unpivoted) Householder QR -- the pivot of step s is the column at position s
   double atol, rtol;
   int cpc;          // columns per CTA
   int csm;          // of those, cached in shared memory
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_kernel(QrcpParams p) {
       if (lc < ncols) {
         const int q = lpos[lc];
         if (q >= snext) {
-          v = vn1[lc];
+          v = p.nopivot ? (q == snext ? 1.0 : -1.0) : vn1[lc];
           lp = q;
           if (q == snext) bps = (int)(col0 + lc);
         }
@@ -450,7 +451,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_kernel(QrcpParams p) {
     }
 
     // ---- apply H to the warp's unpivoted columns; downdate their norms (vectorised across lanes) ----
-    const bool downdate = (s < lastrk - 1);
+    const bool downdate = (s < lastrk - 1) && !p.nopivot;      // no pivoting: the norms are never looked at
     int wflag = 0;
     double vr[NR > 0 ? NR : 1];
     if (NR > 0) {
@@ -696,7 +697,7 @@ cudaError_t launch_qrcp(const QrcpParams& p, int G, size_t smem, cudaStream_t st
 }  // namespace
 
 int bra_qrcp_run(bra_ctx* ctx, double* B, int64_t ldb, int l, int64_t n, int kcap, int nb, double atol,
-                 double rtol, QrcpOut* out) {
+                 double rtol, QrcpOut* out, bool nopivot) {
   out->k = 0;
   out->nsteps = 0;
   out->nblocks = 0;
@@ -747,6 +748,7 @@ int bra_qrcp_run(bra_ctx* ctx, double* B, int64_t ldb, int l, int64_t n, int kca
   p.n = n;
   p.kcap = kcap;
   p.nb = nbe;
+  p.nopivot = nopivot ? 1 : 0;
   p.atol = atol;
   p.rtol = rtol;
   p.cpc = cpc;

@@ -120,7 +120,7 @@ def test_errors_mirror_reference(ctx):
     with pytest.raises(ValueError):
         brapprox.idfact(A, trans="x", ctx=ctx)          # ArgumentError("trans")
     with pytest.raises(brapprox.BraError):
-        brapprox.pqrfact(np.ones((8, 8)), maxdet_tol=0.0, ctx=ctx)   # tails on a maxdet-refined ID: not built
+        brapprox.idfact(A, sketch="none", ctx=ctx)          # sketch = :none is not built: loud, never a CPU fallback
 
 
 @pytest.mark.parametrize("m,n,r,rtol,tol", [(300, 200, 60, 1e-9, 0.0), (512, 640, 100, 1e-10, 0.0), (256, 384, 40, 1e-8, 0.25)])

@@ -106,8 +106,8 @@ def test_tail_kernels_standalone(ctx):
 
 def test_psvdfact_with_reference_test_options(ctx):
     """psvdfact on a maxdet-refined, power-iterated ID (the options of the reference's own suite, test/psvd.jl:8:
-    LRAOptions(maxdet_tol=0., sketch_randn_niter=1)).  After maxdet the skeleton QR is preconditioned by a fresh pivoted
-    sketch of A[:, sk]; U, S, Vt do not depend on the skeleton's internal order.  Against the oracle on identical Omega
+    LRAOptions(maxdet_tol=0., sketch_randn_niter=1)).  After maxdet the skeleton QR is preconditioned by a fresh sketch of
+    A[:, sk] factored WITHOUT pivoting (R1 stays triangular in the reference's column order).  Against the oracle on identical Omega
     (a case whose swap sequence is well separated): same k, same p, same rank, |dsigma| <= 1e-10 sigma_1, U S and S Vt
     entrywise; plus the reference inequality on the 128 x 64 Fourier matrix in fast mode."""
     import brapprox
@@ -133,8 +133,19 @@ def test_psvdfact_with_reference_test_options(ctx):
         Ug, Vtg = _signfix(Sg.U, Sg.Vt, So.U)
         assert np.max(np.abs(Ug * Sg.S - So.U * So.S)) <= 1e-10 * s1
         assert np.max(np.abs(Vtg * Sg.S[:, None] - So.Vt * So.S[:, None])) <= 1e-10 * s1
-    with pytest.raises(brapprox.BraError):
-        brapprox.pqrfact(A, brapprox.LRAOptions(**kw), ctx=ctx)          # triangular R1 after maxdet: not built, loud
+    # pqrfact on the same refined ID: Q orthonormal, R1 upper triangular in the reference's column order
+    Fo = o.pqrfact(A, o.LRAOptions(**kw), o.RandomInputs(3))
+    Fg = brapprox.pqrfact(A, brapprox.LRAOptions(**kw), rand=rin.drawn, ctx=ctx)
+    k = Fo.k
+    assert Fg.k == k
+    assert np.linalg.norm(Fg.Q.T @ Fg.Q - np.eye(k)) <= 1e-13 * np.sqrt(k)
+    assert np.all(np.diag(Fg.R[:, :k]) > 0) and np.max(np.abs(np.tril(Fg.R[:, :k], -1))) == 0.0
+    nrm = np.linalg.norm(A)
+    assert np.linalg.norm(A - Fg.matrix()) / nrm <= 2 * np.linalg.norm(A - Fo.matrix()) / nrm + 1e-15
+    if np.array_equal(Fg.p, Fo.p):
+        d = np.sign(np.diag(Fo.R[:, :k]))
+        Ro = Fo.R * d[:, None]
+        assert np.max(np.abs(Fg.R - Ro)) <= 1e-10 * abs(Ro[0, 0])
     rng = np.random.default_rng(0)
     F64 = np.asfortranarray(o.matrixlib_fourier(rng.random(128), rng.random(64)).real)
     rtol = 5 * o.EPS
