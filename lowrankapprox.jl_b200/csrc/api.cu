@@ -652,7 +652,30 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
   ctx->A_sym_state = 0;
   QrcpOut q = {0, 0, 0, 0};
   int64_t order = 0;
-  if (o->sketchfact_adap || o->rank < 0) {
+  if (o->sketch == BRA_SKETCH_NONE) {
+    // sketch = :none (pqrfact_none, src/pqr.jl:323-327): the early-terminating QRCP runs on a copy of op(A) itself.
+    // Same persistent kernel (generic row loop; the column slabs of a tall matrix live in L2/HBM, not in shared
+    // memory), so this is the classical expensive path -- functional, not a benchmarked one.
+    const int64_t mA = res.m;
+    order = mA;
+    if (mA >= (int64_t(1) << 14) + 4096) {
+      ctx->set_error("sketch = :none needs the Householder vector in shared memory: at most ~20000 rows of op(A)");
+      return BRA_ERR_UNSUPPORTED;
+    }
+    BRA_CUDA(ctx->B.reserve((size_t)(mA > 0 ? mA : 1) * (nA > 0 ? nA : 1) * 8));
+    int rc;
+    if (trans == 'n') {
+      BRA_CUDA(copy2d(ctx, ctx->B.p, mA, dA, lda, mA, nA));
+    } else if ((rc = bra_transpose(ctx, dA, lda, m, n, ctx->B.as<double>(), mA))) {
+      return rc;
+    }
+    rc = run_round_qrcp(ctx, o, order, nA, &q);
+    if (rc) return rc;
+    res.orders[0] = order;
+    res.ks[0] = q.k;
+    res.steps[0] = q.nsteps;
+    res.rounds = 1;
+  } else if (o->sketchfact_adap || o->rank < 0) {
     int64_t nn = o->nb << ctx->start_round;                          // src/sketch.jl:226 (n doubles every round)
     for (int round = ctx->start_round;; ++round) {
       if (round >= BRA_MAX_ROUNDS) {
@@ -736,8 +759,8 @@ int bra_check_fact_args(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
     ctx->set_error("sketch_randn_niter > 0 on a row-sharded matrix is not built");
     return BRA_ERR_UNSUPPORTED;
   }
-  if (opts->sketch == BRA_SKETCH_NONE) {
-    ctx->set_error("sketch = :none is not built (SURVEY 8f-3)");
+  if (opts->sketch == BRA_SKETCH_NONE && ctx->world > 1) {
+    ctx->set_error("sketch = :none on a row-sharded matrix is not built");
     return BRA_ERR_UNSUPPORTED;
   }
   if (ctx->world > 1 && (opts->sketch != BRA_SKETCH_RANDN || trans != 'n')) {

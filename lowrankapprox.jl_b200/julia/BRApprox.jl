@@ -76,10 +76,8 @@ function idfact(trans::Symbol, A::Matrix{Float64}, opts::LRAOptions=LRAOptions()
   opts = copy(opts; args...)
   opts.pqrfact_retval = "t"
   chkopts!(opts, A)
-  # maxdet_tol / maxdet_niter (src/pqr.jl:444-501) and sketch_randn_niter (src/sketch.jl:140-149) run on the device;
-  # sketch = :none is not built and takes the untouched reference path
-  opts.sketch == :none &&
-    return invoke(LowRankApprox.idfact, Tuple{Symbol,AbstractMatrix,LRAOptions}, trans, A, opts)   # untouched path
+  # every LRAOptions combination of the Float64 dense path runs on the device: all five sketches (:none included),
+  # maxdet_tol / maxdet_niter (src/pqr.jl:444-501) and sketch_randn_niter (src/sketch.jl:140-149)
   m, n = size(A)
   Ωs = draw_omegas(opts, trans == :n ? m : n)
   ptrs = [pointer(Ω) for Ω in Ωs]
