@@ -9,6 +9,7 @@ C ABI is Python here, mirroring the reference's entry points for the hot path
     idfact / id                    src/id.jl:434-456
     pqrfact / pqr                  src/pqr.jl:285-320
     psvdfact / psvd / psvdvals     src/psvd.jl:238-308
+    curfact / cur                  src/cur.jl:532-571 (index selection: two sketch-and-pivot passes)
 
 The product path is the CUDA library only: importing this package without a
 loadable libbrapprox.so raises, and every call fails loudly (BraError) when no
@@ -16,6 +17,7 @@ B200 is usable.  Nothing here imports ``oracle/``.
 """
 from ._binding import (  # noqa: F401
     BraError,
+    CURPackedU,
     Context,
     IDPackedV,
     LRAOptions,
@@ -27,6 +29,8 @@ from ._binding import (  # noqa: F401
 )
 from ._dist import block_shard, broadcast_bytes, init_comm, row_shard  # noqa: F401
 from ._frontend import (  # noqa: F401
+    cur,
+    curfact,
     default_context,
     geqp3_adap,
     id,

@@ -300,6 +300,23 @@ class Context:
 
 
 @dataclass
+class CURPackedU:
+    """CURPackedU / HermCURPackedU (src/cur.jl:14-26): 1-based row and column index sets."""
+    rows: np.ndarray
+    cols: np.ndarray
+    hermitian: bool = False
+
+    def __getitem__(self, key):
+        if key == "rows":
+            return self.rows
+        if key == "cols":
+            return self.cols
+        if key == "k":
+            return len(self.cols)
+        raise KeyError(key)
+
+
+@dataclass
 class IDPackedV:
     """IDPackedV (src/id.jl:15-19): sk, rd are 1-based like the reference."""
     sk: np.ndarray

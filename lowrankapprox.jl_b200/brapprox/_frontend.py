@@ -185,6 +185,46 @@ def idfact(A, opts: Optional[LRAOptions] = None, trans: str = "n", rand=None,
     return IDPackedV(p[:k].copy(), p[k:].copy(), T, rounds, steps)
 
 
+def _skeleton(A, opts, trans, rand, ctx, kw):
+    """sketchfact(:left, trans, A, opts)[:p][1:k] (the index set only; src/cur.jl:538-556 asks for retval "")."""
+    idfact_device(A, opts, trans, rand, ctx, **kw)
+    inf, _, _ = _rounds(ctx)
+    k, n = int(inf.k), int(inf.n)
+    return ctx.fetch(B.F_P, (n,), np.int64)[:k].copy()
+
+
+def curfact(A, opts: Optional[LRAOptions] = None, rand=None, ctx: Optional[Context] = None, **kw):
+    """curfact(A, opts; kw...) -> CURPackedU(rows, cols) / HermCURPackedU(cols) (src/cur.jl:532-566).
+
+    The control flow of the reference -- which side is sketched first, the second sketch on the selected rows or
+    columns only, the truncation to k = min(kr, kc) -- with both sketch-and-pivot passes on the device.  `rand` is an
+    optional pair (first pass, second pass) of per-round random inputs (parity mode).  A Hermitian (real: exactly
+    symmetric) A takes one pass and returns the column set for both sides, like HermCURPackedU."""
+    ctx = ctx or default_context()
+    A = np.asarray(A)
+    if A.ndim != 2:
+        raise ValueError("A")
+    r1, r2 = (rand if rand is not None else (None, None))
+    m, n = A.shape
+    if m == n and np.array_equal(A, A.T):
+        cols = _skeleton(A, opts, "n", r1, ctx, kw)
+        return B.CURPackedU(cols.copy(), cols, hermitian=True)
+    if m >= n:
+        rows = _skeleton(A, opts, "c", r1, ctx, kw)
+        cols = _skeleton(np.asfortranarray(A[rows - 1, :]), opts, "n", r2, ctx, kw)
+    else:
+        cols = _skeleton(A, opts, "n", r1, ctx, kw)
+        rows = _skeleton(np.asfortranarray(A[:, cols - 1]), opts, "c", r2, ctx, kw)
+    k = min(len(rows), len(cols))
+    return B.CURPackedU(rows[:k], cols[:k])
+
+
+def cur(A, *args, **kw):
+    """cur(A, ...) -> (rows, cols) (src/cur.jl:568-571)."""
+    U = curfact(A, *args, **kw)
+    return U.rows, U.cols
+
+
 def idfact_batched_device(a_ptr: int, nblocks: int, m: int, n: int, lda: int, stride_a: int, k_ptr: int, p_ptr: int,
                           t_ptr: int, ld_t: int, stride_t: int, opts: Optional[LRAOptions] = None,
                           perm_ptr: int = 0, perm_stride: int = 0, s_ptr: int = 0, s_stride: int = 0,

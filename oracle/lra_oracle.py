@@ -854,3 +854,23 @@ def id_error(A: np.ndarray, V: IDPackedV, trans: str = "n", seed: int = 0) -> fl
     Aop = A if trans == "n" else A.T
     C = Aop[:, V.sk - 1]
     return snormdiff_lowrank(Aop, C, V.matrix(), seed=seed) / snorm_dense(Aop, seed=seed)
+
+
+
+def curfact(A: np.ndarray, opts: LRAOptions, rand1: Optional[RandomInputs] = None,
+            rand2: Optional[RandomInputs] = None):
+    """curfact (src/cur.jl:532-566): (rows, cols), 1-based; Hermitian A -> (cols, cols)."""
+    chkopts(opts)
+    o1 = opts.copy(pqrfact_retval="t")
+    m, n = A.shape
+    if m == n and np.array_equal(A, A.T):
+        V = idfact(A, o1, rand1, "n")
+        return V.sk.copy(), V.sk.copy()
+    if m >= n:
+        rows = idfact(A, o1, rand1, "c").sk
+        cols = idfact(np.asfortranarray(A[rows - 1, :]), o1, rand2, "n").sk
+    else:
+        cols = idfact(A, o1, rand1, "n").sk
+        rows = idfact(np.asfortranarray(A[:, cols - 1]), o1, rand2, "c").sk
+    k = min(len(rows), len(cols))
+    return rows[:k].copy(), cols[:k].copy()

@@ -250,3 +250,24 @@ def test_sketch_none_matches_oracle(ctx, m, n, r, rtol, trans):
         So = o.psvdfact(A, o.LRAOptions(rtol=rtol, sketch="none"), None)
         assert len(F.S) == len(So.S)
         assert np.max(np.abs(F.S - So.S)) <= 1e-10 * So.S[0]
+
+
+@pytest.mark.parametrize("m,n", [(300, 200), (180, 260), (200, 200)])
+def test_curfact_matches_oracle(ctx, m, n):
+    """curfact (src/cur.jl:532-566): the reference's two-pass row/column selection with both passes on the device;
+    identical random inputs => identical index sets; the CUR reconstruction C pinv(C) A pinv(R) R is as accurate as the
+    oracle's.  The square case is symmetric and takes the Hermitian branch."""
+    import brapprox
+    A = o.decaying_matrix(m, n, 50, 9.0, 50, seed=2 * m + n)
+    if m == n:
+        A = np.asfortranarray(A @ A.T)
+    r1, r2 = o.RandomInputs(1), o.RandomInputs(2)
+    ro, co = o.curfact(A, o.LRAOptions(rtol=1e-8), r1, r2)
+    U = brapprox.curfact(A, rtol=1e-8, rand=(r1.drawn, r2.drawn), ctx=ctx)
+    np.testing.assert_array_equal(U.rows, ro)
+    np.testing.assert_array_equal(U.cols, co)
+    C, R = A[:, U.cols - 1], A[U.rows - 1, :]
+    err = np.linalg.norm(A - C @ (np.linalg.pinv(C) @ A @ np.linalg.pinv(R)) @ R, 2) / np.linalg.norm(A, 2)
+    assert err < 1e-6
+    rows, cols = brapprox.cur(A, rtol=1e-8, seed=3, ctx=ctx)
+    assert len(rows) == len(cols) > 0
