@@ -184,6 +184,12 @@ int bra_pqrfact_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double
 int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* opts,
                      const bra_rand* rnd);
 
+/* pheigfact(A, opts) (src/pheig.jl:276-296) for a real symmetric n x n A (-3: "matrix must be Hermitian", :279):
+ * idfact, QR of [I; T'] (one Cholesky pass), the k x k eigenproblem of R (A[sk,sk] R') on the device (one-sided
+ * Jacobi + Rayleigh quotients), truncation with pheigrank (:322-341).  Fetch BRA_F_S (kk eigenvalues, ascending,
+ * negative part first) and BRA_F_U (n x kk eigenvectors); bra_get_info().ksvd = kk.  pheigvals = fetch BRA_F_S only. */
+int bra_pheigfact_f64(bra_ctx* ctx, int64_t n, const double* A, int64_t lda, const bra_opts* opts, const bra_rand* rnd);
+
 /* ---- batched idfact of independent blocks (BASELINE config 5; additive: the reference loops idfact) --------
  * nblocks column-major m x n blocks, block b at A + b*strideA (leading dimension lda), all DEVICE resident.
  * opts as for idfact with sketch = :sprn.  Random inputs in reference order per block (src/sketch.jl:575-579):

@@ -10,6 +10,7 @@ C ABI is Python here, mirroring the reference's entry points for the hot path
     pqrfact / pqr                  src/pqr.jl:285-320
     psvdfact / psvd / psvdvals     src/psvd.jl:238-308
     curfact / cur                  src/cur.jl:532-571 (index selection: two sketch-and-pivot passes)
+    pheigfact / pheig / pheigvals  src/pheig.jl:276-319
 
 The product path is the CUDA library only: importing this package without a
 loadable libbrapprox.so raises, and every call fails loudly (BraError) when no
@@ -21,6 +22,7 @@ from ._binding import (  # noqa: F401
     Context,
     IDPackedV,
     LRAOptions,
+    PartialHermEigen,
     PartialQR,
     PartialSVD,
     SKETCH_CODES,
@@ -38,6 +40,9 @@ from ._frontend import (  # noqa: F401
     idfact_batched,
     idfact_batched_device,
     idfact_device,
+    pheig,
+    pheigfact,
+    pheigvals,
     pqr,
     pqrfact,
     pqrfact_device,

@@ -95,6 +95,7 @@ lib.bra_geqp3_adap_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, C.POINTER(bra_opt
 lib.bra_trsolve_T_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, _vp, _i64]
 lib.bra_idfact_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand)]
 lib.bra_pqrfact_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand)]
+lib.bra_pheigfact_f64.argtypes = [_vp, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand)]
 lib.bra_psvdfact_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand)]
 lib.bra_get_info.argtypes = [_vp, C.POINTER(bra_info)]
 lib.bra_fetch.argtypes = [_vp, C.c_int, _vp, _i64]
@@ -297,6 +298,27 @@ class Context:
         ld = max(shape[0], 1) if len(shape) == 2 else 1
         self.check(lib.bra_fetch(self._h, which, C.c_void_p(out.ctypes.data), ld))
         return out
+
+
+@dataclass
+class PartialHermEigen:
+    """PartialHermEigen (src/pheig.jl:4-8): values ascending (negative part, then positive part), vectors n x k."""
+    values: np.ndarray
+    vectors: np.ndarray
+    k_id: int = 0
+    rounds: List[Tuple[int, int]] = field(default_factory=list)
+
+    def __getitem__(self, key):
+        if key == "values":
+            return self.values
+        if key == "vectors":
+            return self.vectors
+        if key == "k":
+            return len(self.values)
+        raise KeyError(key)
+
+    def matrix(self) -> np.ndarray:
+        return (self.vectors * self.values) @ self.vectors.T
 
 
 @dataclass

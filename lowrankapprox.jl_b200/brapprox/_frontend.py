@@ -345,6 +345,38 @@ def psvdfact(A, opts: Optional[LRAOptions] = None, rand=None, ctx: Optional[Cont
     return B.PartialSVD(U, S, Vt, int(inf.k), rounds)
 
 
+def pheigfact(A, opts: Optional[LRAOptions] = None, rand=None, ctx: Optional[Context] = None, **kw):
+    """pheigfact(A, opts; kw...) -> PartialHermEigen(values, vectors) (src/pheig.jl:276-296); A real symmetric,
+    otherwise ValueError("matrix must be Hermitian") (:279)."""
+    o = _opts(opts, kw)
+    ctx = ctx or default_context()
+    pA, m, n, lda, keepA = mat_arg(A)
+    if m != n:
+        raise ValueError("matrix is not square")            # checksquare
+    rp = _RandPack(rand)
+    co = o.to_c()
+    rc = lib.bra_pheigfact_f64(ctx.handle, n, pA, lda, C.byref(co), C.byref(rp.c))
+    if rc == -3:
+        raise ValueError("matrix must be Hermitian")          # error("matrix must be Hermitian"), src/pheig.jl:279
+    ctx.check(rc)
+    inf, rounds, steps = _rounds(ctx)
+    kk = int(inf.ksvd)
+    if kk == 0:
+        return B.PartialHermEigen(np.zeros(0), np.zeros((n, 0)), int(inf.k), rounds)
+    return B.PartialHermEigen(ctx.fetch(B.F_S, (kk,)), ctx.fetch(B.F_U, (n, kk)), int(inf.k), rounds)
+
+
+def pheig(A, *args, **kw):
+    """pheig(A, ...) -> (values, vectors) (src/pheig.jl:316-319)."""
+    F = pheigfact(A, *args, **kw)
+    return F.values, F.vectors
+
+
+def pheigvals(A, *args, **kw):
+    """pheigvals(A, ...) (src/pheig.jl:298-311)."""
+    return pheigfact(A, *args, **kw).values
+
+
 def psvd(A, *args, **kw):
     """psvd(A, ...) -> (U, S, V) with V = Vt' (src/psvd.jl:296-299)."""
     F = psvdfact(A, *args, **kw)

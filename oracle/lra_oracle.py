@@ -874,3 +874,42 @@ def curfact(A: np.ndarray, opts: LRAOptions, rand1: Optional[RandomInputs] = Non
         rows = idfact(np.asfortranarray(A[:, cols - 1]), o1, rand2, "c").sk
     k = min(len(rows), len(cols))
     return rows[:k].copy(), cols[:k].copy()
+
+
+def pheigrank(w: np.ndarray, opts: LRAOptions) -> Tuple[int, int]:
+    """src/pheig.jl:322-341 on ascending w: (kn, kp) kept at the negative / positive end."""
+    n = len(w)
+    wmax = max(abs(w[0]), abs(w[-1]))
+    lo = int(np.searchsorted(w, 0.0, side="left"))
+    hi = int(np.searchsorted(w, 0.0, side="right"))
+    ptol = max(opts.atol, opts.rtol * wmax)
+
+    def rank1(v):
+        k = len(v)
+        k = min(opts.rank, k) if opts.rank >= 0 else k
+        for i in range(1, k):
+            if abs(v[i]) <= ptol:
+                return i
+        return k
+    return rank1(w[:lo]), rank1(w[::-1][:n - hi])
+
+
+def pheigfact(A: np.ndarray, opts: LRAOptions, rand: Optional[RandomInputs] = None):
+    """pheigfact (src/pheig.jl:276-296): (values, vectors); the eigen cluster re-orthonormalisation (pheigorth!,
+    :344-364) is a no-op for numpy's eigh, whose vectors are orthonormal to machine precision."""
+    if A.shape[0] != A.shape[1] or not np.array_equal(A, A.T):
+        raise ValueError("matrix must be Hermitian")
+    V = idfact(A, opts, rand, "n")
+    k, n = V.k, A.shape[0]
+    if k == 0:
+        return np.zeros(0), np.zeros((n, 0)), V
+    Z = np.zeros((n, k))
+    Z[V.p - 1, :] = np.vstack([np.eye(k), V.T.T])              # Matrix(:c, V) = P [I; T']
+    Q, R = qr_thin(Z)
+    Bm = R @ (A[np.ix_(V.sk - 1, V.sk - 1)] @ R.T)
+    w, X = np.linalg.eigh((Bm + Bm.T) / 2)
+    kn, kp = pheigrank(w, opts)
+    if kn + kp < k:
+        idx = np.r_[0:kn, k - kp:k]
+        w, X = w[idx], X[:, idx]
+    return w, Q @ X, V

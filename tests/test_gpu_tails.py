@@ -151,3 +151,41 @@ def test_psvdfact_with_reference_test_options(ctx):
     rtol = 5 * o.EPS
     F = brapprox.psvdfact(F64, rtol=rtol, maxdet_tol=0.0, sketch_randn_niter=1, seed=3, ctx=ctx)
     assert np.linalg.norm(F64 - F.matrix()) < 100 * rtol * np.linalg.norm(F64)
+
+
+@pytest.mark.parametrize("kind", ["psd", "indefinite", "hilbert"])
+def test_pheigfact_matches_oracle(ctx, kind):
+    """pheigfact (src/pheig.jl:276-296) on identical Omega: same ID rank, same number of eigenvalues after pheigrank,
+    values within 1e-10 |lambda|_max, vectors entrywise (after sign-fixing, scaled by lambda / |lambda|_max),
+    orthonormal vectors, reconstruction error within 2x of the oracle's."""
+    import brapprox
+    rng = np.random.default_rng(4)
+    if kind == "hilbert":
+        A, rtol = o.matrixlib_hilb(200), 1e-10
+    else:
+        n, r = 240, 40
+        Qm, _ = np.linalg.qr(rng.standard_normal((n, r)))
+        lam = 10.0 ** (-8.0 * np.arange(r) / r)
+        if kind == "indefinite":
+            lam = lam * np.where(np.arange(r) % 3 == 0, -0.7, 1.0)
+        A = (Qm * lam) @ Qm.T
+        A, rtol = np.asfortranarray((A + A.T) / 2), 1e-9
+    rin = o.RandomInputs(6)
+    wo, Xo, Vo = o.pheigfact(A, o.LRAOptions(rtol=rtol), rin)
+    F = brapprox.pheigfact(A, rtol=rtol, rand=rin.drawn, ctx=ctx)
+    assert F.k_id == Vo.k
+    assert len(F.values) == len(wo)
+    wmax = np.abs(wo).max()
+    assert np.max(np.abs(F.values - wo)) <= 1e-10 * wmax
+    kk = len(wo)
+    assert np.linalg.norm(F.vectors.T @ F.vectors - np.eye(kk)) <= 1e-11 * np.sqrt(kk)
+    sgn = np.sign(np.sum(F.vectors * Xo, axis=0))
+    sgn[sgn == 0] = 1.0
+    assert np.max(np.abs(F.vectors * sgn * F.values - Xo * wo)) <= 1e-9 * wmax
+    nrm = np.linalg.norm(A, 2)
+    eo = np.linalg.norm(A - (Xo * wo) @ Xo.T, 2) / nrm
+    eg = np.linalg.norm(A - F.matrix(), 2) / nrm
+    assert eg <= 2 * eo + 1e-12          # exact-rank inputs: both errors are rounding level (Q_z is orthonormal to ~1e-13)
+    np.testing.assert_allclose(brapprox.pheigvals(A, rtol=rtol, rand=rin.drawn, ctx=ctx), F.values, rtol=0, atol=1e-13 * wmax)
+    with pytest.raises(ValueError):
+        brapprox.pheigfact(np.asfortranarray(rng.standard_normal((8, 8))), ctx=ctx)      # "matrix must be Hermitian"
