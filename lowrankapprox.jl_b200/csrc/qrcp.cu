@@ -303,7 +303,9 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_kernel(QrcpParams p) {
       ss = warp_sum(ss);
       if (lane == 0) sred[warp] = ss;
       __syncthreads();
-      if (cand_lc >= 0) {
+      // only warps that still hold rows of the candidate (and warp 0, which publishes tau and beta) run the FP64
+      // square root and divisions: the FP64 pipe issues per warp, not per active lane
+      if (cand_lc >= 0 && (warp == 0 || s + 1 + (warp << 5) < l)) {
         // pairwise (4 levels instead of a 16-long dependent chain of FP64 adds)
         double t8[8];
 #pragma unroll
