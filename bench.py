@@ -452,9 +452,16 @@ def main():
         from brapprox._frontend import idfact, _rounds
         e2e_steps = max(3, min(args.steps, 10))
 
+        # results land in caller-owned pinned buffers (the ABI's ownership model; sized for k <= 640): both directions
+        # of the end-to-end step then run at the PCIe rate and the step allocates nothing
+        kmax = RANK_GEN
+        Ub = torch.empty((kmax, n), dtype=torch.float64, pin_memory=True).numpy().T        # n x kmax, column-major
+        Sb = torch.empty((kmax,), dtype=torch.float64, pin_memory=True).numpy()
+        Vb = torch.empty((n, kmax), dtype=torch.float64, pin_memory=True).numpy().T        # kmax x n, column-major
+
         def e2e_step(seed):
             if what == "psvdfact":
-                F = brapprox.psvdfact(Ahn, rtol=RTOL, seed=seed, ctx=ctx)
+                F = brapprox.psvdfact(Ahn, rtol=RTOL, seed=seed, ctx=ctx, out=(Ub, Sb, Vb))
                 return F.U.nbytes + F.S.nbytes + F.Vt.nbytes
             Vv = idfact(Ahn, rtol=RTOL, seed=seed, ctx=ctx)
             return Vv.sk.nbytes + Vv.rd.nbytes + Vv.T.nbytes

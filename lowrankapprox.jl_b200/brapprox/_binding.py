@@ -291,11 +291,28 @@ class Context:
         self.check(lib.bra_get_info(self._h, C.byref(inf)))
         return inf
 
-    def fetch(self, which: int, shape, dtype=np.float64) -> np.ndarray:
-        out = np.zeros(shape, dtype=dtype, order="F")
+    def fetch(self, which: int, shape, dtype=np.float64, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Copies one factor of the last call into host memory.  `out` (optional) is a caller-owned column-major
+        buffer of at least `shape` (e.g. pinned memory: the copy then runs at the full PCIe rate and nothing is
+        allocated); the returned array is the leading `shape` block of it."""
+        if out is None:
+            out = np.empty(shape, dtype=dtype, order="F")
+            ld = max(shape[0], 1) if len(shape) == 2 else 1
+        else:
+            if out.dtype != dtype or out.ndim != len(shape) or any(o < s_ for o, s_ in zip(out.shape, shape)):
+                raise ValueError("out: wrong dtype or too small")
+            if len(shape) == 2:
+                if out.strides[0] != out.itemsize:
+                    raise ValueError("out: must be column-major (unit stride along rows)")
+                ld = max(out.strides[1] // out.itemsize, 1)
+                out = out[:shape[0], :shape[1]]
+            else:
+                if out.strides[0] != out.itemsize:
+                    raise ValueError("out: must be contiguous")
+                ld = 1
+                out = out[:shape[0]]
         if out.size == 0:
             return out
-        ld = max(shape[0], 1) if len(shape) == 2 else 1
         self.check(lib.bra_fetch(self._h, which, C.c_void_p(out.ctypes.data), ld))
         return out
 

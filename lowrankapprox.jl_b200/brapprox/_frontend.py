@@ -330,8 +330,12 @@ def psvdfact_device(A, opts: Optional[LRAOptions] = None, rand=None, ctx: Option
     return ctx.info()
 
 
-def psvdfact(A, opts: Optional[LRAOptions] = None, rand=None, ctx: Optional[Context] = None, **kw):
-    """psvdfact(A, opts; kw...) -> PartialSVD(U, S, Vt) (src/psvd.jl:238-272)."""
+def psvdfact(A, opts: Optional[LRAOptions] = None, rand=None, ctx: Optional[Context] = None, out=None, **kw):
+    """psvdfact(A, opts; kw...) -> PartialSVD(U, S, Vt) (src/psvd.jl:238-272).
+
+    `out` (optional) = (U, S, Vt) caller-owned column-major host buffers at least m x k, k and k x n large (the C ABI's
+    ownership model: results go into caller memory); with pinned buffers the read-back runs at the PCIe rate and the
+    returned factors are views of them."""
     ctx = ctx or default_context()
     pA, m, n, lda, keepA = mat_arg(A)
     psvdfact_device(A, opts, rand, ctx, **kw)
@@ -339,9 +343,10 @@ def psvdfact(A, opts: Optional[LRAOptions] = None, rand=None, ctx: Optional[Cont
     ks = int(inf.ksvd)
     if ks == 0:
         return B.PartialSVD(np.zeros((m, 0)), np.zeros(0), np.zeros((0, n)), int(inf.k), rounds)
-    U = ctx.fetch(B.F_U, (m, ks))
-    S = ctx.fetch(B.F_S, (ks,))
-    Vt = ctx.fetch(B.F_VT, (ks, n))
+    oU, oS, oV = out if out is not None else (None, None, None)
+    U = ctx.fetch(B.F_U, (m, ks), out=oU)
+    S = ctx.fetch(B.F_S, (ks,), out=oS)
+    Vt = ctx.fetch(B.F_VT, (ks, n), out=oV)
     return B.PartialSVD(U, S, Vt, int(inf.k), rounds)
 
 

@@ -189,3 +189,22 @@ def test_pheigfact_matches_oracle(ctx, kind):
     np.testing.assert_allclose(brapprox.pheigvals(A, rtol=rtol, rand=rin.drawn, ctx=ctx), F.values, rtol=0, atol=1e-13 * wmax)
     with pytest.raises(ValueError):
         brapprox.pheigfact(np.asfortranarray(rng.standard_normal((8, 8))), ctx=ctx)      # "matrix must be Hermitian"
+
+
+def test_psvdfact_into_caller_buffers(ctx):
+    """`out=`: the factors are written into caller-owned column-major buffers (the ABI's ownership model) and the
+    returned arrays are views of them; results equal the allocating call's."""
+    import brapprox
+    A = o.decaying_matrix(320, 260, 50, 9.0, 50, seed=8)
+    F0 = brapprox.psvdfact(A, rtol=1e-9, seed=4, ctx=ctx)
+    Ub = np.zeros((320, 64), order="F")
+    Sb = np.zeros(64)
+    Vb = np.zeros((64, 260), order="F")
+    F1 = brapprox.psvdfact(A, rtol=1e-9, seed=4, ctx=ctx, out=(Ub, Sb, Vb))
+    kk = len(F0.S)
+    assert len(F1.S) == kk and np.shares_memory(F1.U, Ub) and np.shares_memory(F1.Vt, Vb)
+    np.testing.assert_array_equal(F1.S, F0.S)
+    np.testing.assert_array_equal(F1.U, F0.U)
+    np.testing.assert_array_equal(F1.Vt, F0.Vt)
+    with pytest.raises(ValueError):
+        brapprox.psvdfact(A, rtol=1e-9, seed=4, ctx=ctx, out=(np.zeros((320, 4), order="F"), Sb, Vb))
