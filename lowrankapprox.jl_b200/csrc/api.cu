@@ -6,6 +6,7 @@
 //   idfact                      src/id.jl:434-447
 #include "common.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <new>
 
 namespace {
@@ -318,7 +319,7 @@ int run_round_qrcp(bra_ctx* ctx, const bra_opts* o, int64_t order, int64_t nA, Q
   ProfScope ps(ctx, BRA_PROF_QRCP);
   const int64_t lmin = order < nA ? order : nA;
   const int64_t kcap = (o->rank < 0 || o->rank > lmin) ? lmin : o->rank;       // src/pqr.jl:350-352
-  return bra_qrcp_run(ctx, ctx->B.as<double>(), order, (int)order, nA, (int)kcap, (int)o->nb, o->atol, o->rtol, q);
+  return bra_qrcp_run(ctx, ctx->cur_B, ctx->cur_ldb, (int)order, nA, (int)kcap, (int)o->nb, o->atol, o->rtol, q);
 }
 
 }  // namespace
@@ -376,11 +377,13 @@ int bra_destroy(bra_ctx* ctx) {
                     &ctx->vn2, &ctx->lpos, &ctx->fpend, &ctx->rec, &ctx->jpvt, &ctx->tau, &ctx->rdiag, &ctx->info,
                     &ctx->kbtrace, &ctx->R11, &ctx->T, &ctx->C, &ctx->Q, &ctx->R1, &ctx->Rfull, &ctx->W, &ctx->G,
                     &ctx->U, &ctx->S, &ctx->Vt, &ctx->Z, &ctx->scratch, &ctx->scratch2, &ctx->scratch3,
-                    &ctx->aux_in1, &ctx->aux_in2, &ctx->jwork, &ctx->At, &ctx->rinv, &ctx->yt, &ctx->Apanels, &ctx->tritmp, &ctx->cholscr, &ctx->Bq};
+                    &ctx->aux_in1, &ctx->aux_in2, &ctx->jwork, &ctx->At, &ctx->rinv, &ctx->yt, &ctx->Apanels, &ctx->tritmp, &ctx->cholscr, &ctx->Bq, &ctx->omega_spec, &ctx->Bspec};
   for (DevBuf* b : bufs) b->release();
   bra_comm_destroy(ctx);
   if (ctx->h_info) cudaFreeHost(ctx->h_info);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  for (cudaEvent_t e : ctx->copy_events) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return BRA_OK;
@@ -669,6 +672,8 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
     } else if ((rc = bra_transpose(ctx, dA, lda, m, n, ctx->B.as<double>(), mA))) {
       return rc;
     }
+    ctx->cur_B = ctx->B.as<double>();
+    ctx->cur_ldb = order;
     rc = run_round_qrcp(ctx, o, order, nA, &q);
     if (rc) return rc;
     res.orders[0] = order;
@@ -683,7 +688,16 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
         return BRA_ERR_ROUNDS;
       }
       order = default_order(o, nn);
-      int rc = sketch_round(ctx, trans, m, n, dA, lda, o, rnd, round, order);
+      int rc = BRA_OK;
+      if (round < ctx->spec_rounds) {
+        // this round's sketch was formed while A was still arriving from the host (bra_stage_A)
+        ctx->cur_B = ctx->Bspec.as<double>() + ctx->spec_off[round];
+        ctx->cur_ldb = ctx->spec_ld;
+      } else {
+        rc = sketch_round(ctx, trans, m, n, dA, lda, o, rnd, round, order);
+        ctx->cur_B = ctx->B.as<double>();
+        ctx->cur_ldb = order;
+      }
       if (rc) return rc;
       rc = run_round_qrcp(ctx, o, order, nA, &q);
       if (rc) return rc;
@@ -698,6 +712,8 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
     order = (o->sketch == BRA_SKETCH_SPRN) ? o->rank : default_order(o, o->rank);   // src/sketch.jl:236,686
     int rc = sketch_round(ctx, trans, m, n, dA, lda, o, rnd, 0, order);
     if (rc) return rc;
+    ctx->cur_B = ctx->B.as<double>();
+    ctx->cur_ldb = order;
     rc = run_round_qrcp(ctx, o, order, nA, &q);
     if (rc) return rc;
     res.orders[0] = order;
@@ -724,7 +740,7 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
     int rc;
     {
       ProfScope ps(ctx, BRA_PROF_GATHER);
-      rc = bra_gather_R(ctx, ctx->B.as<double>(), order, nA, (int)k, ctx->jpvt.as<int64_t>(), ctx->R11.as<double>(),
+      rc = bra_gather_R(ctx, ctx->cur_B, ctx->cur_ldb, nA, (int)k, ctx->jpvt.as<int64_t>(), ctx->R11.as<double>(),
                         ctx->T.as<double>(), ldT);
     }
     if (rc) return rc;
@@ -744,6 +760,7 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
     }
   }
   res.have_T = true;
+  ctx->spec_rounds = 0;
   return BRA_OK;
 }
 
@@ -771,6 +788,86 @@ int bra_check_fact_args(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
   return BRA_OK;
 }
 
+// Device copy of A for a fused factorization.  A device-resident A is used in place.  A large host-resident A headed
+// for the adaptive Gaussian path is uploaded in column panels on a second stream while the sketch products of the
+// first adaptive rounds run on the panels that have already arrived: all those rounds share one stacked Omega (the
+// same Philox streams the round-by-round path draws), so by the time the upload ends their sketches exist and only the
+// pivoted QRs remain.  Rounds beyond the speculative ones fall back to the ordinary per-round sketch; sketches of rounds
+// that turn out not to be needed cost nothing visible (they hide behind the PCIe transfer).
+int bra_stage_A(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* o,
+                const bra_rand* rnd, const double** dA, int64_t* dlda) {
+  ctx->spec_rounds = 0;
+  if (is_device_ptr(A)) {
+    *dA = A;
+    *dlda = lda;
+    return BRA_OK;
+  }
+  const int64_t ld = (m + 1) & ~int64_t(1);
+  BRA_CUDA(ctx->A_stage.reserve((size_t)ld * (n > 0 ? n : 1) * 8));
+  *dA = ctx->A_stage.as<double>();
+  *dlda = ld;
+  if (m <= 0 || n <= 0) return BRA_OK;
+  const bool spec = trans == 'n' && o->sketch == BRA_SKETCH_RANDN && (o->sketchfact_adap || o->rank < 0) &&
+                    !(rnd && rnd->n_rounds > 0) && o->sketch_randn_niter == 0 && ctx->world == 1 &&
+                    ctx->start_round == 0 && (int64_t)m * n * 8 >= (int64_t(64) << 20) && n >= 2048 &&
+                    getenv("BRA_NO_SPEC_UPLOAD") == nullptr;
+  if (!spec) {
+    BRA_CUDA(copy2d(ctx, ctx->A_stage.p, ld, A, lda, m, n));
+    return BRA_OK;
+  }
+  // speculative rounds: orders 40, 72, 136, 264, 520 with the default sampler (stop before the order passes min(m, n))
+  int T = 0;
+  int64_t lsum = 0, orders[5];
+  for (int64_t nn = o->nb; T < 5; nn *= 2, ++T) {
+    const int64_t ord = default_order(o, nn);
+    if (ord > m || ord > n || ord <= 0) break;
+    orders[T] = ord;
+    ctx->spec_off[T] = lsum;
+    lsum += ord;
+  }
+  if (T == 0) {
+    BRA_CUDA(copy2d(ctx, ctx->A_stage.p, ld, A, lda, m, n));
+    return BRA_OK;
+  }
+  const int64_t ldt = ld;
+  BRA_CUDA(ctx->omega_spec.reserve((size_t)lsum * ldt * 8));
+  BRA_CUDA(ctx->Bspec.reserve((size_t)lsum * n * 8));
+  {
+    ProfScope ps(ctx, BRA_PROF_OMEGA);
+    for (int t = 0; t < T; ++t) {
+      int rc = bra_fill_randn(ctx, ctx->omega_spec.as<double>() + ctx->spec_off[t] * ldt, orders[t] * ldt, o->seed, (uint64_t)t);
+      if (rc) return rc;
+    }
+  }
+  if (!ctx->copy_stream) BRA_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  constexpr int PANELS = 8;
+  while ((int)ctx->copy_events.size() < PANELS) {
+    cudaEvent_t e;
+    BRA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->copy_events.push_back(e);
+  }
+  BRA_CUDA(cudaStreamSynchronize(ctx->stream));        // earlier users of A_stage are done
+  const int64_t cper = ((n + PANELS - 1) / PANELS + 255) / 256 * 256;
+  int pi = 0;
+  for (int64_t c0 = 0; c0 < n; c0 += cper, ++pi) {
+    const int64_t cp = (n - c0 < cper) ? n - c0 : cper;
+    double* dst = ctx->A_stage.as<double>() + c0 * ld;
+    const double* src = A + c0 * lda;
+    if (ld == m && lda == m)
+      BRA_CUDA(cudaMemcpyAsync(dst, src, (size_t)m * cp * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+    else
+      BRA_CUDA(cudaMemcpy2DAsync(dst, (size_t)ld * 8, src, (size_t)lda * 8, (size_t)m * 8, (size_t)cp, cudaMemcpyHostToDevice,
+                                 ctx->copy_stream));
+    BRA_CUDA(cudaEventRecord(ctx->copy_events[pi], ctx->copy_stream));
+    BRA_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_events[pi], 0));
+    int rc = bra_gemm_sketch(ctx, ctx->omega_spec.as<double>(), lsum, m, dst, ld, cp, ctx->Bspec.as<double>() + c0 * lsum, lsum);
+    if (rc) return rc;
+  }
+  ctx->spec_rounds = T;
+  ctx->spec_ld = lsum;
+  return BRA_OK;
+}
+
 int bra_idfact_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A, int64_t lda,
                    const bra_opts* opts, const bra_rand* rnd) {
   if (!ctx) return -1;
@@ -779,7 +876,7 @@ int bra_idfact_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double*
   BRA_CUDA(cudaSetDevice(ctx->device));
   const double* dA;
   int64_t dlda;
-  rc = to_device(ctx, ctx->A_stage, A, lda, m, n, &dA, &dlda);
+  rc = bra_stage_A(ctx, trans, m, n, A, lda, opts, rnd, &dA, &dlda);
   if (rc) return rc;
   rc = bra_sketchfact_core(ctx, trans, m, n, dA, dlda, opts, rnd);
   if (rc) return rc;
@@ -829,7 +926,7 @@ int bra_fetch(bra_ctx* ctx, int which, void* dst, int64_t ld) {
       const int64_t l = r.orders[r.rounds - 1];
       BRA_CHECK_ARG(ld >= l, 4, "ld");
       BRA_CUDA(ctx->B2.reserve((size_t)l * n * 8));
-      int rc = bra_permute_cols(ctx, ctx->B.as<double>(), l, ctx->B2.as<double>(), l, l, n, ctx->jpvt.as<int64_t>());
+      int rc = bra_permute_cols(ctx, ctx->cur_B, ctx->cur_ldb, ctx->B2.as<double>(), l, l, n, ctx->jpvt.as<int64_t>());
       if (rc) return rc;
       BRA_CUDA(copy2d(ctx, dst, ld, ctx->B2.p, l, l, n));
       break;

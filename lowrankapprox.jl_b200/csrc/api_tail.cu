@@ -82,24 +82,7 @@ int bra_pqrfact_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double
   BRA_CUDA(cudaSetDevice(ctx->device));
   const double* dA;
   int64_t dlda;
-  {
-    // stage a host-resident A once (same helper as idfact: is_device_ptr + copy)
-    if (is_device_ptr(A)) {
-      dA = A;
-      dlda = lda;
-    } else {
-      dlda = even(m);
-      BRA_CUDA(ctx->A_stage.reserve((size_t)dlda * (n > 0 ? n : 1) * 8));
-      if (m > 0 && n > 0) {
-        if (dlda == m && lda == m)
-          BRA_CUDA(cudaMemcpyAsync(ctx->A_stage.p, A, (size_t)m * n * 8, cudaMemcpyDefault, ctx->stream));
-        else
-          BRA_CUDA(cudaMemcpy2DAsync(ctx->A_stage.p, (size_t)dlda * 8, A, (size_t)lda * 8, (size_t)m * 8, (size_t)n,
-                                     cudaMemcpyDefault, ctx->stream));
-      }
-      dA = ctx->A_stage.as<double>();
-    }
-  }
+  if ((rc = bra_stage_A(ctx, trans, m, n, A, lda, opts, rnd, &dA, &dlda))) return rc;
   rc = bra_sketchfact_core(ctx, trans, m, n, dA, dlda, opts, rnd);      // V = idfact(trans, A, opts)
   if (rc) return rc;
   FactResult& res = ctx->res;
@@ -134,21 +117,7 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
   BRA_CUDA(cudaSetDevice(ctx->device));
   const double* dA;
   int64_t dlda;
-  if (is_device_ptr(A)) {
-    dA = A;
-    dlda = lda;
-  } else {
-    dlda = even(m);
-    BRA_CUDA(ctx->A_stage.reserve((size_t)dlda * (n > 0 ? n : 1) * 8));
-    if (m > 0 && n > 0) {
-      if (dlda == m && lda == m)
-        BRA_CUDA(cudaMemcpyAsync(ctx->A_stage.p, A, (size_t)m * n * 8, cudaMemcpyDefault, ctx->stream));
-      else
-        BRA_CUDA(cudaMemcpy2DAsync(ctx->A_stage.p, (size_t)dlda * 8, A, (size_t)lda * 8, (size_t)m * 8, (size_t)n,
-                                   cudaMemcpyDefault, ctx->stream));
-    }
-    dA = ctx->A_stage.as<double>();
-  }
+  if ((rc = bra_stage_A(ctx, trans, m, n, A, lda, opts, rnd, &dA, &dlda))) return rc;
   rc = bra_sketchfact_core(ctx, trans, m, n, dA, dlda, opts, rnd);      // V = idfact(trans, A, opts)
   if (rc) return rc;
   FactResult& res = ctx->res;

@@ -93,6 +93,14 @@ struct bra_ctx {
   DevBuf tritmp;               // blocked triangular inverse: B C^{-1} scratch
   DevBuf cholscr;              // blocked Cholesky: inverse of the current diagonal block
   DevBuf Bq;                   // power iteration: the sketch on the other side of A
+  // host-resident A: the upload is pipelined with the sketch products of the first adaptive rounds (api.cu: bra_stage_A)
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> copy_events;
+  DevBuf omega_spec, Bspec;    // stacked Omega^T / sketches of the speculative rounds
+  int spec_rounds = 0;         // rounds whose sketch is already in Bspec (0: none)
+  int64_t spec_ld = 0, spec_off[BRA_MAX_ROUNDS] = {0};
+  double* cur_B = nullptr;     // sketch of the current round and its leading dimension
+  int64_t cur_ldb = 0;
   int A_sym_state = 0;         // power iteration: 0 unknown, 1 A == A' exactly, -1 not (checked once per factorization)
   int last_jacobi_sweeps = 0;
   int jacobi_kcycles[8] = {0};
@@ -218,6 +226,8 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
                         const bra_opts* o, const bra_rand* rnd);
 int bra_check_fact_args(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A, int64_t lda,
                         const bra_opts* opts);
+int bra_stage_A(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* opts,
+                const bra_rand* rnd, const double** dA, int64_t* dlda);
 }
 int bra_gemm_generic(bra_ctx* ctx, const double* Om, int64_t osi, int64_t osk, const double* A, int64_t sk,
                      int64_t sj, int64_t l, int64_t n, int64_t K, double* C, int64_t ldc);

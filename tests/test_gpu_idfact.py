@@ -271,3 +271,26 @@ def test_curfact_matches_oracle(ctx, m, n):
     assert err < 1e-6
     rows, cols = brapprox.cur(A, rtol=1e-8, seed=3, ctx=ctx)
     assert len(rows) == len(cols) > 0
+
+
+def test_pipelined_upload_equals_plain_upload(ctx):
+    """A large host-resident A is uploaded in column panels while the sketches of the first adaptive rounds are formed on
+    the panels already on the device (bra_stage_A).  Same Philox Omega, same rounds, same k and p as the plain upload;
+    T to rounding (the stacked product splits the contraction differently)."""
+    import os
+    import brapprox
+    A = o.decaying_matrix(4096, 2304, 120, 11.0, 120, seed=12)         # 75 MB: above the 64 MB threshold
+    os.environ["BRA_NO_SPEC_UPLOAD"] = "1"
+    try:
+        V0 = brapprox.idfact(A, rtol=1e-10, seed=9, ctx=ctx)
+    finally:
+        del os.environ["BRA_NO_SPEC_UPLOAD"]
+    V1 = brapprox.idfact(A, rtol=1e-10, seed=9, ctx=ctx)
+    assert V1.rounds == V0.rounds and V1.k == V0.k
+    np.testing.assert_array_equal(V1.p[:V1.k], V0.p[:V0.k])
+    C = A[:, V0.sk - 1]
+    T0 = np.zeros((V0.k, A.shape[1])); T0[:, V0.rd - 1] = V0.T
+    T1 = np.zeros((V1.k, A.shape[1])); T1[:, V1.rd - 1] = V1.T
+    assert np.max(np.abs(C @ T1 - C @ T0)) <= 1e-10 * np.linalg.norm(A, 2)
+    F = brapprox.psvdfact(A, rtol=1e-10, seed=9, ctx=ctx)
+    assert np.linalg.norm(A - F.matrix(), 2) <= 1e-8 * np.linalg.norm(A, 2)
