@@ -284,6 +284,38 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
                : "memory");
 }
 
+// ---- bulk (TMA 1-D) copies for the block hand-over: one elected thread moves a whole column per instruction ----
+__device__ __forceinline__ uint32_t jsmem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void jmbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(jsmem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void jmbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(jsmem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void jmbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(jsmem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(jsmem_u32(sdst)),
+               "l"(gsrc), "r"(bytes), "r"(jsmem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(jsmem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+
 __device__ __forceinline__ void rr_pair(int np, int stage, int i, int& p, int& q) {
   // round-robin (chess tournament) over np = even number of players: np-1 stages of np/2 disjoint pairs
   if (i == 0) {
@@ -435,35 +467,44 @@ __global__ void __launch_bounds__(BC * TS, 1) jacobi_team_kernel(JacobiParams P)
   int sweep = 0, converged = 0;
   long long tph[4] = {0, 0, 0, 0}, tlast = clock64();
 #define JTICK(i) if (tid == 0) { long long _t = clock64(); tph[i] += _t - tlast; tlast = _t; }
-  // copy one block between its home in global memory and a slot (team t moves column t of the block)
-  auto load_slot = [&](int slot, int blk) {
-    const int gc = blk * BC + team;
-    double* xs = Xs + (size_t)(slot * BC + team) * kp;
-    double* js = Js + (size_t)(slot * BC + team) * kp;
-    if (gc < k) {
-      const double* gx = P.X + (int64_t)gc * P.ldx;
-      const double* gj = P.J + (int64_t)gc * P.ldj;
-      for (int r = 2 * e; r < kp; r += 2 * TS) {
-        cp_async16(xs + r, gx + r);
-        cp_async16(js + r, gj + r);
+  // copy one block between its home in global memory and a slot: ONE thread issues a bulk copy per column (the copy
+  // engine moves the 4 KB columns; completion through an mbarrier for loads, a bulk group for stores)
+  __shared__ __align__(8) uint64_t s_mbar;
+  uint32_t mphase = 0;
+  if (tid == 0) {
+    jmbar_init(&s_mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const uint32_t colbytes = (uint32_t)kp * 8;
+  auto load_slot_bulk = [&](int slot, int blk) {        // tid 0 only; returns the bytes it asked for
+    uint32_t bytes = 0;
+    for (int c = 0; c < BC; ++c) {
+      const int gc = blk * BC + c;
+      if (gc < k) {
+        bulk_g2s(Xs + (size_t)(slot * BC + c) * kp, P.X + (int64_t)gc * P.ldx, colbytes, &s_mbar);
+        bulk_g2s(Js + (size_t)(slot * BC + c) * kp, P.J + (int64_t)gc * P.ldj, colbytes, &s_mbar);
+        bytes += 2 * colbytes;
       }
-    } else {
+    }
+    return bytes;
+  };
+  auto zero_slot_tail = [&](int slot, int blk) {        // all threads: columns beyond k are zero
+    const int gc = blk * BC + team;
+    if (gc >= k) {
+      double* xs = Xs + (size_t)(slot * BC + team) * kp;
+      double* js = Js + (size_t)(slot * BC + team) * kp;
       for (int r = e; r < kp; r += TS) {
         xs[r] = 0.0;
         js[r] = 0.0;
       }
     }
   };
-  auto store_slot = [&](int slot, int blk) {
-    const int gc = blk * BC + team;
-    if (gc < k) {
-      const double2* xs = reinterpret_cast<const double2*>(Xs + (size_t)(slot * BC + team) * kp);
-      const double2* js = reinterpret_cast<const double2*>(Js + (size_t)(slot * BC + team) * kp);
-      double2* gx = reinterpret_cast<double2*>(P.X + (int64_t)gc * P.ldx);
-      double2* gj = reinterpret_cast<double2*>(P.J + (int64_t)gc * P.ldj);
-      for (int r = e; r < kp / 2; r += TS) {
-        __stcg(gx + r, xs[r]);
-        __stcg(gj + r, js[r]);
+  auto store_slot_bulk = [&](int slot, int blk) {       // tid 0 only
+    for (int c = 0; c < BC; ++c) {
+      const int gc = blk * BC + c;
+      if (gc < k) {
+        bulk_s2g(P.X + (int64_t)gc * P.ldx, Xs + (size_t)(slot * BC + c) * kp, colbytes);
+        bulk_s2g(P.J + (int64_t)gc * P.ldj, Js + (size_t)(slot * BC + c) * kp, colbytes);
       }
     }
   };
@@ -512,9 +553,21 @@ __global__ void __launch_bounds__(BC * TS, 1) jacobi_team_kernel(JacobiParams P)
           }
           __syncthreads();
           JTICK(0)
-          if (needL) load_slot(sl, perm[pL]);
-          if (needR) load_slot(sr, perm[pR]);
-          asm volatile("cp.async.wait_all;" ::: "memory");
+          if (tid == 0) {
+            // expect_tx first (the barrier cannot complete before the byte count is known), then the copies
+            uint32_t want = 0;
+            if (needL)
+              for (int c = 0; c < BC; ++c) want += (perm[pL] * BC + c < k) ? 2 * colbytes : 0;
+            if (needR)
+              for (int c = 0; c < BC; ++c) want += (perm[pR] * BC + c < k) ? 2 * colbytes : 0;
+            jmbar_expect_tx(&s_mbar, want);
+            if (needL) load_slot_bulk(sl, perm[pL]);
+            if (needR) load_slot_bulk(sr, perm[pR]);
+          }
+          if (needL) zero_slot_tail(sl, perm[pL]);
+          if (needR) zero_slot_tail(sr, perm[pR]);
+          jmbar_wait(&s_mbar, mphase);
+          mphase ^= 1;
           __syncthreads();
           JTICK(1)
         }
@@ -571,16 +624,27 @@ __global__ void __launch_bounds__(BC * TS, 1) jacobi_team_kernel(JacobiParams P)
             // an end position idles during the next (odd) step: its next reader is two steps away
             const bool idles = (((gstep + 1) & 1) != 0) && (pp == 0 || pp == N - 1);
             sver[sidx] = gstep + 1 + (idles ? 1u : 0u);
-            store_slot(sidx, sblk[sidx]);
             spos[sidx] = -1;
           }
         }
         if (sent[0] || sent[1]) {
+          // the rotations wrote the slots through the generic proxy: order them before the bulk (async proxy) reads
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncthreads();
-          if (tid < 2 && sent[tid]) {       // st.release.gpu is cumulative over the CTA barrier above
-            unsigned* f = P.bstep + sblk[tid];
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(f), "r"(sver[tid]) : "memory");
+          if (tid == 0) {
+#pragma unroll
+            for (int sidx = 0; sidx < 2; ++sidx)
+              if (sent[sidx]) store_slot_bulk(sidx, sblk[sidx]);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // the global writes are complete
+#pragma unroll
+            for (int sidx = 0; sidx < 2; ++sidx)
+              if (sent[sidx]) {
+                unsigned* f = P.bstep + sblk[sidx];
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(f), "r"(sver[sidx]) : "memory");
+              }
           }
+          __syncthreads();       // the slots may be refilled only after the bulk store has read them
         }
       }
       JTICK(3)
@@ -604,9 +668,15 @@ __global__ void __launch_bounds__(BC * TS, 1) jacobi_team_kernel(JacobiParams P)
     }
   }
   // ---- blocks still held go home ----
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (tid == 0) {
 #pragma unroll
-  for (int sidx = 0; sidx < 2; ++sidx)
-    if (spos[sidx] >= 0) store_slot(sidx, perm[spos[sidx]]);
+    for (int sidx = 0; sidx < 2; ++sidx)
+      if (spos[sidx] >= 0) store_slot_bulk(sidx, perm[spos[sidx]]);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
   // report from a middle CTA (the end CTAs idle or hold the zero-padded block and are not representative)
   if (cta == gridDim.x / 2 && tid == 0) {
     P.out[0] = sweep;
