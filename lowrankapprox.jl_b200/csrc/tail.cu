@@ -130,14 +130,18 @@ __global__ void __launch_bounds__(256) trsolve_right_upper_kernel(int64_t rows, 
 __global__ void __launch_bounds__(32) chol_diag_kernel(int k, int j0, const double* __restrict__ G, int64_t ldg,
                                                        double* __restrict__ R, int64_t ldr, double* __restrict__ Dinv,
                                                        int* info) {
-  __shared__ double Ls[TB][TB + 1];
   const int lane = threadIdx.x;
   const int jbsz = min(TB, k - j0);
   double a[TB];      // row `lane` of the diagonal block (lower triangle meaningful)
 #pragma unroll
   for (int c = 0; c < TB; ++c)
     a[c] = (lane < jbsz && c < jbsz) ? G[(j0 + lane) + (int64_t)(j0 + c) * ldg] : (lane == c ? 1.0 : 0.0);
-  double rsd = 1.0;  // lane c keeps 1 / L[c][c]
+  // Factorization and inversion run in ONE loop over the columns: as soon as column c of L exists, unknown c of the
+  // substitution L v = e_j (lane j = column j of L^{-1}) is resolved and eliminated from the rows below.  The two
+  // instruction streams are independent within a step, which is what hides the shuffle / FP64 latencies of a lone warp.
+  double v[TB];
+#pragma unroll
+  for (int r = 0; r < TB; ++r) v[r] = (r == lane) ? 1.0 : 0.0;
 #pragma unroll
   for (int c = 0; c < TB; ++c) {
     double d = __shfl_sync(0xffffffffu, a[c], c);
@@ -146,32 +150,20 @@ __global__ void __launch_bounds__(32) chol_diag_kernel(int k, int j0, const doub
       d = 1.0;
     }
     const double rs = rsqrt(d);
-    if (lane == c) rsd = rs;
     const double l = (lane == c) ? d * rs : a[c] * rs;              // column c of L (rows >= c meaningful)
     a[c] = l;
+    v[c] *= rs;                                                     // 1 / L[c][c]
 #pragma unroll
     for (int cc = c + 1; cc < TB; ++cc) {
       const double lcc = __shfl_sync(0xffffffffu, l, cc);           // L[cc][c]
       a[cc] = fma(-l, lcc, a[cc]);
+      v[cc] = fma(-lcc, v[c], v[cc]);                                // the same L[cc][c] serves both streams
     }
   }
-#pragma unroll
-  for (int c = 0; c < TB; ++c) Ls[lane][c] = (c <= lane) ? a[c] : 0.0;
   if (lane < jbsz) {
 #pragma unroll
     for (int c = 0; c < TB; ++c)
       if (c <= lane) R[(j0 + c) + (int64_t)(j0 + lane) * ldr] = a[c];      // R = L^T
-  }
-  __syncwarp();
-  // lane j solves L v = e_j (column j of L^{-1}); once v_c is known it is eliminated from the rows below
-  double v[TB];
-#pragma unroll
-  for (int r = 0; r < TB; ++r) v[r] = (r == lane) ? 1.0 : 0.0;
-#pragma unroll
-  for (int c = 0; c < TB; ++c) {
-    v[c] *= __shfl_sync(0xffffffffu, rsd, c);
-#pragma unroll
-    for (int r = c + 1; r < TB; ++r) v[r] = fma(-Ls[r][c], v[c], v[r]);
   }
 #pragma unroll
   for (int r = 0; r < TB; ++r) Dinv[r + lane * TB] = v[r];        // Dinv[r][j] = (L^{-1})[r][j], column-major 32 x 32
