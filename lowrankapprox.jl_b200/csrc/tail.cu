@@ -879,7 +879,8 @@ int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64
       nblk = 2 * ((k + 2 * bc - 1) / (2 * bc));
     }
     if (nblk / 2 > ctx->num_sms || need(bc) > budget || bc * ts > 1024) {
-      ctx->set_error("Jacobi SVD: no co-resident configuration for this k");
+      ctx->set_error("Jacobi SVD: core too large -- one CTA per pair of 4-column blocks must be co-resident (k <= 8 * #SMs = "
+                     "1184 on B200)");
       return BRA_ERR_UNSUPPORTED;
     }
     const int grid = nblk / 2;
