@@ -273,13 +273,14 @@ def test_curfact_matches_oracle(ctx, m, n):
     assert len(rows) == len(cols) > 0
 
 
-def test_pipelined_upload_equals_plain_upload(ctx):
+@pytest.mark.parametrize("m,n", [(4096, 2304), (4097, 2100)])
+def test_pipelined_upload_equals_plain_upload(ctx, m, n):
     """A large host-resident A is uploaded in column panels while the sketches of the first adaptive rounds are formed on
     the panels already on the device (bra_stage_A).  Same Philox Omega, same rounds, same k and p as the plain upload;
     T to rounding (the stacked product splits the contraction differently)."""
     import os
     import brapprox
-    A = o.decaying_matrix(4096, 2304, 120, 11.0, 120, seed=12)         # 75 MB: above the 64 MB threshold
+    A = o.decaying_matrix(m, n, 120, 11.0, 120, seed=12)     # > 64 MB: pipelined; odd m: padded device ld, 2-D panel copies
     os.environ["BRA_NO_SPEC_UPLOAD"] = "1"
     try:
         V0 = brapprox.idfact(A, rtol=1e-10, seed=9, ctx=ctx)
