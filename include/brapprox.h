@@ -190,6 +190,14 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
  * negative part first) and BRA_F_U (n x kk eigenvectors); bra_get_info().ksvd = kk.  pheigvals = fetch BRA_F_S only. */
 int bra_pheigfact_f64(bra_ctx* ctx, int64_t n, const double* A, int64_t lda, const bra_opts* opts, const bra_rand* rnd);
 
+/* snorm(A - L R) (snorm / snormdiff, src/snorm.jl:14-53): randomised power iteration on DEVICE-resident operands,
+ * A m x n, L m x k, R k x n (k = 0: snorm(A); a Hermitian A then takes one product per iteration, :33-35).  Stops when
+ * |s - s_prev| <= max(opts->atol, s_prev * opts->rtol) or after niter_max iterations (LRAOptions.snorm_niter).
+ * x0: optional device start vector (the reference's crandn(n)); NULL = device Philox keyed by opts->seed. */
+int bra_snorm_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, int64_t k, const double* L, int64_t ldl,
+                  const double* R, int64_t ldr, const bra_opts* opts, int64_t niter_max, const double* x0, double* result,
+                  int64_t* niter_out);
+
 /* ---- batched idfact of independent blocks (BASELINE config 5; additive: the reference loops idfact) --------
  * nblocks column-major m x n blocks, block b at A + b*strideA (leading dimension lda), all DEVICE resident.
  * opts as for idfact with sketch = :sprn.  Random inputs in reference order per block (src/sketch.jl:575-579):

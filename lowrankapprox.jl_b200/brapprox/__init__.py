@@ -11,6 +11,7 @@ C ABI is Python here, mirroring the reference's entry points for the hot path
     psvdfact / psvd / psvdvals     src/psvd.jl:238-308
     curfact / cur                  src/cur.jl:532-571 (index selection: two sketch-and-pivot passes)
     pheigfact / pheig / pheigvals  src/pheig.jl:276-319
+    snorm / snormdiff              src/snorm.jl:14-53
 
 The product path is the CUDA library only: importing this package without a
 loadable libbrapprox.so raises, and every call fails loudly (BraError) when no
@@ -53,5 +54,7 @@ from ._frontend import (  # noqa: F401
     probe_exchange_latency,
     probe_fp64_peak,
     sketch,
+    snorm,
+    snormdiff,
     trsolve_T,
 )

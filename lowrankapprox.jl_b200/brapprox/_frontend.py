@@ -393,6 +393,64 @@ def psvdvals(A, *args, **kw):
     return psvdfact(A, *args, **kw).S
 
 
+def _dev(a):
+    """Column-major device copy of a host array (torch is the device allocator of this host mirror); cuda tensors and
+    DeviceMatrix pass through.  Returns (DeviceMatrix, keepalive)."""
+    import torch
+    if isinstance(a, DeviceMatrix):
+        return a, a
+    if hasattr(a, "is_cuda"):
+        return DeviceMatrix.from_torch(a), a
+    h = np.asarray(a, dtype=np.float64)
+    if h.ndim == 1:
+        h = h.reshape(-1, 1)
+    t = torch.from_numpy(np.ascontiguousarray(h.T)).cuda()         # row-major (n x m) == column-major m x n
+    return DeviceMatrix(t.data_ptr(), h.shape[0], h.shape[1], max(h.shape[0], 1), keep=t), t
+
+
+def snormdiff(A, left=None, right=None, opts: Optional[LRAOptions] = None, x0=None, ctx: Optional[Context] = None, **kw):
+    """snormdiff(A, F) = snorm(A - F) for F = left @ right (src/snorm.jl:14-53) on the device; left = right = None gives
+    snorm(A).  `left` may also be a factorization of this package: PartialSVD, PartialQR (with its permutation), or
+    PartialHermEigen.  x0: the reference's crandn(n) start vector (parity); default: device Philox keyed by opts.seed."""
+    o = _opts(opts, kw)
+    ctx = ctx or default_context()
+    if isinstance(left, B.PartialSVD):
+        left, right = left.U * left.S, left.Vt
+    elif isinstance(left, B.PartialHermEigen):
+        left, right = left.vectors * left.values, left.vectors.T
+    elif isinstance(left, B.PartialQR):
+        R = np.zeros_like(left.R)
+        R[:, left.p - 1] = left.R
+        left, right = left.Q, R
+    dA, kA = _dev(A)
+    k = 0
+    pL = pR = C.c_void_p(0)
+    ldl = ldr = 1
+    keep = []
+    if left is not None:
+        dL, kL = _dev(left)
+        dR, kR = _dev(right)
+        if dL.m != dA.m or dR.n != dA.n or dL.n != dR.m:
+            raise ValueError("DimensionMismatch")
+        k, pL, pR, ldl, ldr = dL.n, C.c_void_p(dL.ptr), C.c_void_p(dR.ptr), dL.ld, dR.ld
+        keep += [kL, kR]
+    px = C.c_void_p(0)
+    if x0 is not None:
+        dx, kx = _dev(np.asarray(x0, dtype=np.float64).reshape(-1, 1))
+        px = C.c_void_p(dx.ptr)
+        keep.append(kx)
+    co = o.to_c()
+    res, nit = C.c_double(0.0), C.c_int64(0)
+    ctx.check(lib.bra_snorm_f64(ctx.handle, dA.m, dA.n, C.c_void_p(dA.ptr), dA.ld, k, pL, ldl, pR, ldr, C.byref(co),
+                                int(o.snorm_niter), px, C.byref(res), C.byref(nit)))
+    return float(res.value)
+
+
+def snorm(A, opts: Optional[LRAOptions] = None, x0=None, ctx: Optional[Context] = None, **kw):
+    """snorm(A, opts; kw...) (src/snorm.jl:14-44)."""
+    return snormdiff(A, None, None, opts, x0, ctx, **kw)
+
+
 def probe_fp64_peak(ctx: Optional[Context] = None) -> dict:
     ctx = ctx or default_context()
     out = (C.c_double * 8)()

@@ -819,11 +819,15 @@ def psvdfact(A: np.ndarray, opts: LRAOptions, rand: Optional[RandomInputs] = Non
 # Error metric (src/snorm.jl:14-53)
 # --------------------------------------------------------------------------
 
-def snorm(matvec, rmatvec, n: int, opts: Optional[LRAOptions] = None, seed: int = 0) -> float:
-    """Randomised power iteration on a (non-Hermitian) operator given by closures."""
+def snorm(matvec, rmatvec, n: int, opts: Optional[LRAOptions] = None, seed: int = 0, x0=None,
+          herm: bool = False) -> float:
+    """Randomised power iteration (src/snorm.jl:14-44).  x0: the start vector in place of crandn(n); herm: the
+    reference's ishermitian branch (one product per iteration, s = ||x|| instead of sqrt)."""
     opts = opts or LRAOptions()
-    rng = np.random.default_rng(seed)
-    xn = rng.standard_normal(n)
+    if x0 is None:
+        xn = np.random.default_rng(seed).standard_normal(n)
+    else:
+        xn = np.array(x0, dtype=np.float64).reshape(n)
     xnrm = np.linalg.norm(xn)
     s, t, niter = 1.0, 0.0, 0
     while s > 0 and abs(s - t) > max(opts.atol, t * opts.rtol):
@@ -831,22 +835,23 @@ def snorm(matvec, rmatvec, n: int, opts: Optional[LRAOptions] = None, seed: int 
             break
         niter += 1
         xn = xn / xnrm
-        xn = rmatvec(matvec(xn))
+        xn = matvec(xn) if herm else rmatvec(matvec(xn))
         xnrm = np.linalg.norm(xn)
         t = s
-        s = float(np.sqrt(xnrm))
+        s = float(xnrm) if herm else float(np.sqrt(xnrm))
     return s
 
 
-def snorm_dense(A: np.ndarray, opts: Optional[LRAOptions] = None, seed: int = 0) -> float:
-    return snorm(lambda x: A @ x, lambda y: A.T @ y, A.shape[1], opts, seed)
+def snorm_dense(A: np.ndarray, opts: Optional[LRAOptions] = None, seed: int = 0, x0=None) -> float:
+    herm = A.shape[0] == A.shape[1] and np.array_equal(A, A.T)
+    return snorm(lambda x: A @ x, lambda y: A.T @ y, A.shape[1], opts, seed, x0, herm)
 
 
 def snormdiff_lowrank(A: np.ndarray, left: np.ndarray, right: np.ndarray,
-                      opts: Optional[LRAOptions] = None, seed: int = 0) -> float:
+                      opts: Optional[LRAOptions] = None, seed: int = 0, x0=None) -> float:
     """snormdiff(A, F) for F = left @ right without forming F (src/snorm.jl:49-53)."""
     return snorm(lambda x: A @ x - left @ (right @ x),
-                 lambda y: A.T @ y - right.T @ (left.T @ y), A.shape[1], opts, seed)
+                 lambda y: A.T @ y - right.T @ (left.T @ y), A.shape[1], opts, seed, x0)
 
 
 def id_error(A: np.ndarray, V: IDPackedV, trans: str = "n", seed: int = 0) -> float:
