@@ -21,6 +21,7 @@ from ._binding import (  # noqa: F401
     BraError,
     CURPackedU,
     Context,
+    DeviceMatrix,
     IDPackedV,
     LRAOptions,
     PartialHermEigen,
