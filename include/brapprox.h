@@ -190,6 +190,15 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
  * negative part first) and BRA_F_U (n x kk eigenvectors); bra_get_info().ksvd = kk.  pheigvals = fetch BRA_F_S only. */
 int bra_pheigfact_f64(bra_ctx* ctx, int64_t n, const double* A, int64_t lda, const bra_opts* opts, const bra_rand* rnd);
 
+/* prange(trans, A, opts) (src/prange.jl:14-62): an orthonormal basis of the range of A (trans 'n'), of A' ('c') or of
+ * both ('b', square A; a Hermitian A falls back to 'n', :26).  sketch = :none -> pqrfact(op(A))[:Q] (:50-52); :sub ->
+ * prange_sub (:64-77); otherwise the pivoted QR of the right-hand sketch B = op(A) S, sketchfact(:right, trans, A, opts)
+ * (src/sketch.jl:52-66), S on the same random inputs as the left-hand sketch of op(A)' (the contracted dimension is
+ * size(op(A), 2)).  rnd2: the inputs of the second sketch of trans 'b' (the reference factors A' first, then A).
+ * Result: Q = BRA_F_Q, info.m x info.k, equal to the reference's Householder Q up to the sign of each column. */
+int bra_prange_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* opts,
+                   const bra_rand* rnd, const bra_rand* rnd2);
+
 /* snorm(A - L R) (snorm / snormdiff, src/snorm.jl:14-53): randomised power iteration on DEVICE-resident operands,
  * A m x n, L m x k, R k x n (k = 0: snorm(A); a Hermitian A then takes one product per iteration, :33-35).  Stops when
  * |s - s_prev| <= max(opts->atol, s_prev * opts->rtol) or after niter_max iterations (LRAOptions.snorm_niter).

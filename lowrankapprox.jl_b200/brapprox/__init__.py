@@ -12,6 +12,7 @@ C ABI is Python here, mirroring the reference's entry points for the hot path
     curfact / cur                  src/cur.jl:532-571 (index selection: two sketch-and-pivot passes)
     pheigfact / pheig / pheigvals  src/pheig.jl:276-319
     snorm / snormdiff              src/snorm.jl:14-53
+    prange                         src/prange.jl:14-62
 
 The product path is the CUDA library only: importing this package without a
 loadable libbrapprox.so raises, and every call fails loudly (BraError) when no
@@ -55,6 +56,7 @@ from ._frontend import (  # noqa: F401
     probe_exchange_latency,
     probe_fp64_peak,
     sketch,
+    prange,
     snorm,
     snormdiff,
     trsolve_T,

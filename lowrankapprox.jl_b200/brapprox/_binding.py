@@ -96,6 +96,8 @@ lib.bra_trsolve_T_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, _vp, _i64]
 lib.bra_idfact_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand)]
 lib.bra_pqrfact_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand)]
 lib.bra_pheigfact_f64.argtypes = [_vp, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand)]
+lib.bra_prange_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand),
+                               C.POINTER(bra_rand)]
 lib.bra_snorm_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _i64, C.POINTER(bra_opts), _i64, _vp,
                               C.POINTER(C.c_double), C.POINTER(_i64)]
 lib.bra_psvdfact_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand)]

@@ -81,7 +81,10 @@ def sketch(A, order: int, opts: Optional[LRAOptions] = None, side: str = "left",
         raise ValueError("order")
     o = _opts(opts, kw)
     if str(side).lstrip(":") == "right":
-        raise BraError(2, "side = :right is not built (SURVEY 8f-3)")
+        # B = op(A) S is the transpose of the left sketch of op(A)' on the same random inputs (real arithmetic; the
+        # mul! forms at src/sketch.jl:91-110, 248-293, 474-522, 571-653 are transposes of each other)
+        flipped = "c" if tr == b"n" else "n"
+        return np.asfortranarray(sketch(A, order, o, "left", flipped, rand, ctx).T)
     ctx = ctx or default_context()
     pA, m, n, lda, keepA = mat_arg(A)
     mA, nA = (m, n) if tr == b"n" else (n, m)
@@ -311,6 +314,26 @@ def pqrfact(A, opts: Optional[LRAOptions] = None, trans: str = "n", rand=None,
     if "t" in o.pqrfact_retval:
         F.T = ctx.fetch(B.F_T, (k, n - k))
     return F
+
+
+def prange(A, opts: Optional[LRAOptions] = None, trans: str = "n", rand=None, rand2=None,
+           ctx: Optional[Context] = None, **kw):
+    """prange(trans, A, opts; kw...) -> Q (src/prange.jl:14-62): an orthonormal basis of the range of A (trans "n"), of
+    A' ("c") or of both ("b").  rand / rand2: the per-round random inputs of the (first / second) right-hand sketch."""
+    if trans not in ("n", "c", "b"):
+        raise ValueError("trans")                                   # prange_chktrans
+    ctx = ctx or default_context()
+    o = _opts(opts, kw)
+    pA, m, n, lda, keepA = mat_arg(A)
+    rp, rp2 = _RandPack(rand), _RandPack(rand2)
+    co = o.to_c()
+    rc = lib.bra_prange_f64(ctx.handle, trans.encode(), m, n, pA, lda, C.byref(co), C.byref(rp.c), C.byref(rp2.c))
+    if rc == -3:
+        raise ValueError(lib.bra_last_error(ctx.handle).decode())   # checksquare -> DimensionMismatch
+    ctx.check(rc)
+    inf, rounds, steps = _rounds(ctx)
+    k, M = int(inf.k), int(inf.m)
+    return ctx.fetch(B.F_Q, (M, k)) if k > 0 else np.zeros((M, 0), order="F")
 
 
 def pqr(A, *args, **kw):

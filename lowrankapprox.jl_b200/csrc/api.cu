@@ -147,23 +147,28 @@ int apply_rows(bra_ctx* ctx, char t, int64_t m, int64_t n, const double* dA, int
   return bra_gemm_generic(ctx, ctx->omega_t.as<double>(), ldt, 1, dA, lda, 1, order, N, K, out, order);
 }
 
+// ishermitian(A) on the device, cached per factorization in ctx->A_sym_state (1: symmetric, -1: not)
+int check_symmetric(bra_ctx* ctx, int64_t m, int64_t n, const double* dA, int64_t lda) {
+  if (ctx->A_sym_state != 0) return BRA_OK;
+  ctx->A_sym_state = -1;
+  if (m != n) return BRA_OK;
+  BRA_CUDA(ctx->info.reserve(64));
+  BRA_CUDA(cudaMemsetAsync(ctx->info.as<int>() + 14, 0, 4, ctx->stream));
+  is_symmetric_kernel<<<(unsigned)(n < 148 * 8 ? n : 148 * 8), 256, 0, ctx->stream>>>(dA, lda, n, ctx->info.as<int>() + 14);
+  ctx->launches++;
+  BRA_CUDA(cudaMemcpyAsync(ctx->h_info + 14, ctx->info.as<int>() + 14, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->h_info[14] == 0) ctx->A_sym_state = 1;
+  return BRA_OK;
+}
+
 // the loop of sketch_randn_ln / sketch_randn_lc after the first product (ctx->B holds Bp = Omega op(A))
 int power_iterations(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* dA, int64_t lda, const bra_opts* o,
                      int64_t order) {
   const int64_t nA = (trans == 'n') ? n : m, mA = (trans == 'n') ? m : n;
   const char other = (trans == 'n') ? 'c' : 'n';
-  if (ctx->A_sym_state == 0) {
-    ctx->A_sym_state = -1;
-    if (m == n) {
-      BRA_CUDA(ctx->info.reserve(64));
-      BRA_CUDA(cudaMemsetAsync(ctx->info.as<int>() + 14, 0, 4, ctx->stream));
-      is_symmetric_kernel<<<(unsigned)(n < 148 * 8 ? n : 148 * 8), 256, 0, ctx->stream>>>(dA, lda, n, ctx->info.as<int>() + 14);
-      ctx->launches++;
-      BRA_CUDA(cudaMemcpyAsync(ctx->h_info + 14, ctx->info.as<int>() + 14, 4, cudaMemcpyDeviceToHost, ctx->stream));
-      BRA_CUDA(cudaStreamSynchronize(ctx->stream));
-      if (ctx->h_info[14] == 0) ctx->A_sym_state = 1;
-    }
-  }
+  int rcs = check_symmetric(ctx, m, n, dA, lda);
+  if (rcs) return rcs;
   BRA_CUDA(ctx->Bq.reserve((size_t)order * mA * 8));
   double* Bp = ctx->B.as<double>();
   double* Bq = ctx->Bq.as<double>();
@@ -377,7 +382,7 @@ int bra_destroy(bra_ctx* ctx) {
                     &ctx->vn2, &ctx->lpos, &ctx->fpend, &ctx->rec, &ctx->jpvt, &ctx->tau, &ctx->rdiag, &ctx->info,
                     &ctx->kbtrace, &ctx->R11, &ctx->T, &ctx->C, &ctx->Q, &ctx->R1, &ctx->Rfull, &ctx->W, &ctx->G,
                     &ctx->U, &ctx->S, &ctx->Vt, &ctx->Z, &ctx->scratch, &ctx->scratch2, &ctx->scratch3,
-                    &ctx->aux_in1, &ctx->aux_in2, &ctx->jwork, &ctx->At, &ctx->rinv, &ctx->yt, &ctx->Apanels, &ctx->tritmp, &ctx->cholscr, &ctx->Bq, &ctx->omega_spec, &ctx->Bspec};
+                    &ctx->aux_in1, &ctx->aux_in2, &ctx->jwork, &ctx->At, &ctx->rinv, &ctx->yt, &ctx->Apanels, &ctx->tritmp, &ctx->cholscr, &ctx->Bq, &ctx->omega_spec, &ctx->Bspec, &ctx->Bt, &ctx->Bcat};
   for (DevBuf* b : bufs) b->release();
   bra_comm_destroy(ctx);
   if (ctx->h_info) cudaFreeHost(ctx->h_info);
@@ -762,6 +767,92 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
   res.have_T = true;
   ctx->spec_rounds = 0;
   return BRA_OK;
+}
+
+// sketchfact(:right, trans, A, opts) (src/sketch.jl:52-66 with side = :right; the drivers at :213-236, :313-330,
+// :545-562, :674-690): B = op(A) S is the transpose of the left sketch of op(A)' on the same random inputs (the four
+// mul! forms of every sketch type are transposes of each other in real arithmetic), so each round forms
+// S' op(A)' (order x M) with the left-sketch kernels, transposes it to the tall M x order matrix B and runs the
+// early-terminating QRCP on B's columns (the persistent kernel's tall-slab path, as for sketch = :none).
+// On return: ctx->B holds the last round's S' op(A)' (= B', intact), ctx->jpvt the column pivots of B, ctx->R11 the
+// triangular factor of B[:, p[1:k]], res.m = M, res.n = order, res.k = k.  with_maxdet: also T and the maxdet swaps
+// (only the two-sided form keeps them: with retval "q" alone the reference's Q ignores the swaps, src/pqr.jl:469-470).
+int bra_prange_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* dA, int64_t lda, const bra_opts* o,
+                    const bra_rand* rnd, bool with_maxdet) {
+  const char ft = (trans == 'n') ? 'c' : 'n';
+  const int64_t M = (trans == 'n') ? m : n;                           // rows of op(A) = rows of B
+  FactResult& res = ctx->res;
+  res = FactResult();
+  res.m = M;
+  ctx->At_valid = false;
+  ctx->Apanels_state = 0;
+  ctx->A_sym_state = 0;
+  ctx->spec_rounds = 0;
+  if (M >= (int64_t(1) << 14) + 4096) {
+    ctx->set_error("prange needs the Householder vector of the tall sketch in shared memory: at most ~20000 rows of op(A)");
+    return BRA_ERR_UNSUPPORTED;
+  }
+  QrcpOut q = {0, 0, 0, 0};
+  int64_t order = 0;
+  const bool adaptive = o->sketchfact_adap || o->rank < 0;
+  int64_t nn = adaptive ? o->nb : o->rank;
+  for (int round = 0;; ++round) {
+    if (round >= BRA_MAX_ROUNDS) {
+      ctx->set_error("adaptive loop exceeded BRA_MAX_ROUNDS");
+      return BRA_ERR_ROUNDS;
+    }
+    order = (!adaptive && o->sketch == BRA_SKETCH_SPRN) ? o->rank : default_order(o, nn);
+    int rc = sketch_round(ctx, ft, m, n, dA, lda, o, rnd, round, order);
+    if (rc) return rc;
+    BRA_CUDA(ctx->Bt.reserve((size_t)(M > 0 ? M : 1) * (order > 0 ? order : 1) * 8));
+    if (M > 0 && order > 0 && (rc = bra_transpose(ctx, ctx->B.as<double>(), order, order, M, ctx->Bt.as<double>(), M)))
+      return rc;
+    ctx->cur_B = ctx->Bt.as<double>();
+    ctx->cur_ldb = M > 0 ? M : 1;
+    if ((rc = run_round_qrcp(ctx, o, M, order, &q))) return rc;
+    res.orders[round] = order;
+    res.ks[round] = q.k;
+    res.steps[round] = q.nsteps;
+    res.rounds = round + 1;
+    if (!adaptive || q.k < nn) break;                                 // src/sketch.jl:232
+    nn *= 2;
+  }
+  res.n = order;
+  res.k = q.k;
+  if (q.nsteps == 0) {
+    BRA_CUDA(ctx->jpvt.reserve((size_t)(order > 0 ? order : 1) * 8));
+    std::vector<int64_t> id((size_t)order);
+    for (int64_t j = 0; j < order; ++j) id[(size_t)j] = j + 1;
+    BRA_CUDA(cudaMemcpyAsync(ctx->jpvt.p, id.data(), (size_t)order * 8, cudaMemcpyHostToDevice, ctx->stream));
+    BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  const int64_t k = res.k;
+  if (k > 0) {
+    BRA_CUDA(ctx->R11.reserve((size_t)k * k * 8));
+    const int64_t ldT = (k + 1) & ~int64_t(1);
+    res.ldT = ldT;
+    BRA_CUDA(ctx->T.reserve((size_t)ldT * (order - k > 0 ? order - k : 1) * 8));
+    int rc = bra_gather_R(ctx, ctx->cur_B, ctx->cur_ldb, order, (int)k, ctx->jpvt.as<int64_t>(), ctx->R11.as<double>(),
+                          ctx->T.as<double>(), ldT);
+    if (rc) return rc;
+    ctx->last_maxdet_swaps = 0;
+    if (with_maxdet && o->maxdet_tol >= 0 && k < order) {
+      if ((rc = bra_trsolve_upper(ctx, (int)k, order - k, ctx->R11.as<double>(), k, ctx->T.as<double>(), ldT))) return rc;
+      rc = bra_maxdet_swapcols(ctx, (int)k, order - k, ctx->T.as<double>(), ldT, ctx->jpvt.as<int64_t>(), o->maxdet_tol,
+                               o->maxdet_niter, &ctx->last_maxdet_swaps);
+      if (rc) return rc;
+      res.maxdet_done = ctx->last_maxdet_swaps > 0;
+    }
+  }
+  return BRA_OK;
+}
+
+int bra_is_symmetric_dev(bra_ctx* ctx, int64_t n, const double* dA, int64_t lda, int* sym) {
+  ctx->A_sym_state = 0;
+  int rc = check_symmetric(ctx, n, n, dA, lda);
+  *sym = ctx->A_sym_state == 1;
+  ctx->A_sym_state = 0;
+  return rc;
 }
 
 int bra_check_fact_args(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A, int64_t lda,

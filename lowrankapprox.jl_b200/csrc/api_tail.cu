@@ -108,6 +108,89 @@ int bra_pqrfact_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double
   return bra_chol_status(ctx);      // the one host sync of the tail (also reports a Cholesky breakdown)
 }
 
+// prange(trans, A, opts) (src/prange.jl:14-62): an orthonormal basis Q of the range of A (trans = 'n'), of A'
+// ('c'), or of both at once ('b', square A).  Result: Q, res.m x res.k (BRA_F_Q).
+//   sketch = :none -> pqrfact(op(A))[:Q];  :sub -> prange_sub (:64-77) = the Q of pqrfact with the :sub sketch;
+//   otherwise sketchfact(:right, trans, A, opts)[:Q]: the pivoted QR of the tall sketch B = op(A) S.
+// The Q returned is the Cholesky-QR2 factor of the selected columns (diag(R) > 0): equal to the reference's
+// Householder Q up to the sign of each column.
+namespace {
+// two_sided: one half of prange(:b, ...) -- sketchfact(:right, ...) with retval "qr", of which only the selected columns
+// Q R1 = B[:, p[1:k]] are used (written to `cols`, ld = ldc); otherwise Q itself is formed (ctx->Q).
+int prange_one_sided(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* dA, int64_t dlda, const bra_opts* opts,
+                     const bra_rand* rnd, bool two_sided, double* cols, int64_t ldc) {
+  int rc;
+  const bool direct = opts->sketch == BRA_SKETCH_NONE || (opts->sketch == BRA_SKETCH_SUB && !two_sided);
+  bra_opts o = *opts;
+  if (!two_sided) o.maxdet_tol = -1.0;       // retval "q" alone: the swaps do not reach Q (src/pqr.jl:469-470)
+  if (direct) {
+    if ((rc = bra_sketchfact_core(ctx, trans, m, n, dA, dlda, &o, rnd))) return rc;
+  } else if ((rc = bra_prange_core(ctx, trans, m, n, dA, dlda, &o, rnd, two_sided))) {
+    return rc;
+  }
+  const int64_t k = ctx->res.k, M = ctx->res.m;
+  if (k == 0) return BRA_OK;
+  // C = B[:, p[1:k]]: for the sketched forms rows p[1:k] of ctx->B (order x M) transposed = getcols(:c, B', p[1:k])
+  const char gt = direct ? trans : 'c';
+  const double* src = direct ? dA : ctx->B.as<double>();
+  const int64_t lds = direct ? dlda : ctx->res.n;
+  if (two_sided) return bra_gather_cols(ctx, gt, src, lds, M, k, ctx->jpvt.as<int64_t>(), cols, ldc);
+  return skeleton_qr(ctx, gt, src, lds, M, k, &o);
+}
+}  // namespace
+
+int bra_prange_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* opts,
+                   const bra_rand* rnd, const bra_rand* rnd2) {
+  if (!ctx) return -1;
+  BRA_CHECK_ARG(trans == 'n' || trans == 'c' || trans == 'b', 2, "trans");      // prange_chktrans, src/prange.jl:79-80
+  int rc = bra_check_fact_args(ctx, trans == 'b' ? 'n' : trans, m, n, A, lda, opts);
+  if (rc) return rc;
+  if (ctx->world > 1) {
+    ctx->set_error("prange on a row-sharded matrix is not built");
+    return BRA_ERR_UNSUPPORTED;
+  }
+  if (trans == 'b' && m != n) {                                                 // checksquare, src/prange.jl:25
+    ctx->set_error("DimensionMismatch: matrix is not square");
+    return -3;
+  }
+  BRA_CUDA(cudaSetDevice(ctx->device));
+  const double* dA;
+  int64_t dlda;
+  bra_opts onone = *opts;            // staging must not start the speculative left-sketch pipeline
+  onone.sketch = BRA_SKETCH_NONE;
+  if ((rc = bra_stage_A(ctx, 'n', m, n, A, lda, &onone, rnd, &dA, &dlda))) return rc;
+  GemmTagGuard gtag(ctx);
+  if (trans == 'b') {
+    int sym = 0;
+    if ((rc = bra_is_symmetric_dev(ctx, n, dA, dlda, &sym))) return rc;
+    if (sym) trans = 'n';                                                        // src/prange.jl:26
+  }
+  if (trans != 'b') {
+    if ((rc = prange_one_sided(ctx, trans, m, n, dA, dlda, opts, rnd, false, nullptr, 0))) return rc;
+    ctx->res.have_Q = true;
+    ctx->res.have_T = false;
+    return ctx->res.k > 0 ? bra_chol_status(ctx) : BRA_OK;
+  }
+  // trans = :b (src/prange.jl:24-46): B = [Q_r R_r1, Q_c R_c1] = the selected (after maxdet: swapped) columns of the
+  // two sketches side by side, then Q = pqrfact_backend!(B)[:Q]
+  const int64_t ldc = even(n);
+  BRA_CUDA(ctx->Bcat.reserve((size_t)ldc * (size_t)(2 * n > 0 ? 2 * n : 1) * 8));      // k <= n columns per side
+  int64_t kk[2] = {0, 0};
+  for (int side = 0; side < 2; ++side) {
+    double* dst = ctx->Bcat.as<double>() + (size_t)ldc * (side == 0 ? 0 : kk[0]);
+    rc = prange_one_sided(ctx, side == 0 ? 'c' : 'n', m, n, dA, dlda, opts, side == 0 ? rnd : rnd2, true, dst, ldc);
+    if (rc) return rc;
+    kk[side] = ctx->res.k;
+  }
+  onone.maxdet_tol = -1.0;           // retval "q" alone: the swaps do not reach Q (src/pqr.jl:469-470)
+  const int64_t kc = kk[0] + kk[1];
+  if ((rc = bra_sketchfact_core(ctx, 'n', n, kc, ctx->Bcat.as<double>(), ldc, &onone, nullptr))) return rc;
+  if (ctx->res.k > 0 && (rc = skeleton_qr(ctx, 'n', ctx->Bcat.as<double>(), ldc, n, ctx->res.k, &onone))) return rc;
+  ctx->res.have_Q = true;
+  ctx->res.have_T = false;
+  return ctx->res.k > 0 ? bra_chol_status(ctx) : BRA_OK;
+}
+
 int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* opts,
                      const bra_rand* rnd) {
   if (!ctx) return -1;

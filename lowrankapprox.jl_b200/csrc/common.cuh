@@ -93,6 +93,7 @@ struct bra_ctx {
   DevBuf tritmp;               // blocked triangular inverse: B C^{-1} scratch
   DevBuf cholscr;              // blocked Cholesky: inverse of the current diagonal block
   DevBuf Bq;                   // power iteration: the sketch on the other side of A
+  DevBuf Bt, Bcat;             // prange: the tall right-hand sketch B = op(A) S; [B_r[:,p_r] B_c[:,p_c]] of the two-sided form
   // host-resident A: the upload is pipelined with the sketch products of the first adaptive rounds (api.cu: bra_stage_A)
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> copy_events;
@@ -226,6 +227,9 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
                         const bra_opts* o, const bra_rand* rnd);
 int bra_check_fact_args(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A, int64_t lda,
                         const bra_opts* opts);
+int bra_prange_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* dA, int64_t lda, const bra_opts* o,
+                    const bra_rand* rnd, bool with_maxdet);
+int bra_is_symmetric_dev(bra_ctx* ctx, int64_t n, const double* dA, int64_t lda, int* sym);
 int bra_stage_A(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* opts,
                 const bra_rand* rnd, const double** dA, int64_t* dlda);
 }

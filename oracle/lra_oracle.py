@@ -534,8 +534,7 @@ def findmaxabs(x: np.ndarray) -> Tuple[float, int]:
 def maxdet_swapcols(R: Optional[np.ndarray], p: np.ndarray, T: np.ndarray, opts: LRAOptions, retr: bool) -> int:
     """src/pqr.jl:444-501 for the factors this path returns (p, T and, if requested, R1): while max|T| > 1 + tol,
     swap skeleton column i with redundant column j and update T by Sherman-Morrison (maxdet_update!, :481-501).
-    The final re-triangularisation of R1 / update of Q (:467-476) is only needed when Q or R are returned from the
-    sketch itself, which no caller on this path does (pqrfact recomputes them from A[:, sk], src/pqr.jl:297-305).
+    The final re-triangularisation of R1 / update of Q (:467-476) is done by the caller (pqrback_postproc).
     Returns the number of swaps."""
     k, nk = T.shape
     niter = 0
@@ -566,13 +565,20 @@ def pqrback_postproc(B: np.ndarray, p: np.ndarray, tau: np.ndarray, k: int, opts
     retr = "r" in opts.pqrfact_retval
     rett = "t" in opts.pqrfact_retval
     maxdet = 0 < k < B.shape[1] and opts.maxdet_tol >= 0
-    if maxdet and (retq or retr):
-        raise NotImplementedError("maxdet with Q/R returned from the sketch is outside the restated path")
     Q = dorgqr(B[:, :k], tau[:k]) if retq else None
     R = np.triu(B[:k, :]) if (retr or rett or maxdet) else None
     T = dtrsm_upper(R[:, :k], R[:, k:]) if (rett or maxdet) else None
     if maxdet:
-        maxdet_swapcols(None, p, T, opts, False)
+        nsw = maxdet_swapcols(R, p, T, opts, retr)
+        if nsw > 0 and (retq or retr):
+            # src/pqr.jl:467-476: re-triangularise R1 (only retr keeps it updated: with "q" alone R1 is still
+            # triangular, the QR below is the identity and Q ignores the swaps)
+            Qf, Rf = qr_thin(R[:, :k])
+            if retq:
+                Q = Q @ Qf
+            if retr:
+                R[:, :k] = Rf
+                R[:, k:] = Rf @ T
     return PQRFactors(Q, R if retr else None, p, k, T)
 
 
@@ -633,11 +639,23 @@ def apply_sketch(kind: str, A: np.ndarray, order: int, rin: dict, trans: str, ni
 
 
 def sketchfact(A: np.ndarray, opts: LRAOptions, rand: RandomInputs, trans: str = "n",
-               laqps=dlaqps_real) -> PQRFactors:
-    """sketchfact(:left, trans, A, opts) (src/sketch.jl:52-66 + the four drivers)."""
+               laqps=dlaqps_real, side: str = "left") -> PQRFactors:
+    """sketchfact(side, trans, A, opts) (src/sketch.jl:52-66 + the four drivers).  side = "right": B = op(A) S, which in
+    real arithmetic is the transpose of the left sketch of op(A)' on the same draws (the mul! forms at
+    src/sketch.jl:91-110, 248-293, 474-522, 571-653 are transposes of each other), so the random inputs are recorded in
+    the left-sketch format with the contracted dimension size(op(A), 2)."""
     chkopts(opts)
     kind = opts.sketch
-    m = A.shape[0] if trans == "n" else A.shape[1]
+    if side == "right":
+        ft = "c" if trans == "n" else "n"
+
+        def apply_right(kind_, A_, order_, rin_, trans_, niter_=0):
+            return np.asfortranarray(apply_sketch(kind_, A_, order_, rin_, ft, niter_).T)
+        sk = apply_right
+        m = A.shape[1] if trans == "n" else A.shape[0]
+    else:
+        sk = apply_sketch
+        m = A.shape[0] if trans == "n" else A.shape[1]
     rounds: List[Tuple[int, int]] = []
     traces: List[QRCPTrace] = []
     if opts.sketchfact_adap or opts.rank < 0:
@@ -646,7 +664,7 @@ def sketchfact(A: np.ndarray, opts: LRAOptions, rand: RandomInputs, trans: str =
         rnd = 0
         while True:
             order = sketch_order(kind, n, opts)
-            B = apply_sketch(kind, A, order, rand.draw(kind, rnd, order, m), trans, opts.sketch_randn_niter)
+            B = sk(kind, A, order, rand.draw(kind, rnd, order, m), trans, opts.sketch_randn_niter)
             tr = QRCPTrace()
             p, tau, k = geqp3_adap(B, opts_, laqps, tr)
             rounds.append((order, k))
@@ -658,7 +676,7 @@ def sketchfact(A: np.ndarray, opts: LRAOptions, rand: RandomInputs, trans: str =
             n *= 2
             rnd += 1
     order = sketch_order(kind, opts.rank, opts) if kind != "sprn" else opts.rank
-    B = apply_sketch(kind, A, order, rand.draw(kind, 0, order, m), trans, opts.sketch_randn_niter)
+    B = sk(kind, A, order, rand.draw(kind, 0, order, m), trans, opts.sketch_randn_niter)
     tr = QRCPTrace()
     p, tau, k = geqp3_adap(B, opts, laqps, tr)
     F = pqrback_postproc(B, p, tau, k, opts)
@@ -860,6 +878,36 @@ def id_error(A: np.ndarray, V: IDPackedV, trans: str = "n", seed: int = 0) -> fl
     C = Aop[:, V.sk - 1]
     return snormdiff_lowrank(Aop, C, V.matrix(), seed=seed) / snorm_dense(Aop, seed=seed)
 
+
+
+def prange(A: np.ndarray, opts: LRAOptions, rand: Optional[RandomInputs] = None, trans: str = "n",
+           rand2: Optional[RandomInputs] = None) -> np.ndarray:
+    """prange(trans, A, opts) (src/prange.jl:14-62) -> Q.  trans "b": rand drives the sketch of A' (factored first),
+    rand2 the sketch of A."""
+    chkopts(opts)
+    if trans not in ("n", "c", "b"):
+        raise ValueError("trans")
+    if trans == "b":
+        if A.shape[0] != A.shape[1]:
+            raise ValueError("DimensionMismatch: matrix is not square")
+        if np.array_equal(A, A.T):
+            return prange(A, opts, rand, "n")
+        o = opts.copy(pqrfact_retval="qr")
+        if o.sketch == "none":
+            Fr, Fc = pqrfact_none(A, o, "c"), pqrfact_none(A, o, "n")
+        else:
+            Fr = sketchfact(A, o, rand, "c", side="right")
+            Fc = sketchfact(A, o, rand2, "n", side="right")
+        B = np.asfortranarray(np.hstack([Fr.Q @ Fr.R[:, :Fr.k], Fc.Q @ Fc.R[:, :Fc.k]]))
+        return pqrfact_none(B, opts.copy(pqrfact_retval="q"), "n").Q
+    o = opts.copy(pqrfact_retval="q")
+    if o.sketch == "none":
+        return pqrfact_none(A, o, trans).Q
+    if o.sketch == "sub":                                  # prange_sub (src/prange.jl:64-77)
+        F = sketchfact(A, o.copy(pqrfact_retval="t"), rand, trans)
+        C = getcols(A, F.p[:F.k], trans)
+        return qr_thin(C)[0]
+    return sketchfact(A, o, rand, trans, side="right").Q
 
 
 def curfact(A: np.ndarray, opts: LRAOptions, rand1: Optional[RandomInputs] = None,
