@@ -312,7 +312,10 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
     if (ctx->h_info[12] != 0) precond = false;      // X'X not numerically positive definite: plain Jacobi on X
   }
   double* Xj = precond ? Xp : X;                   // the matrix the Jacobi orthogonalises
-  rc = bra_jacobi_svd(ctx, (int)k, Xj, ldj, J, ldj, sig.data(), order.data());
+  // preconditioned: the Jacobi starts from the triangular R2', so the accumulated rotations can be recovered afterwards
+  // as J' = R2^{-T} (Y' Sigma) (row-wise backward stable, R2 = (well conditioned) D) and the kernel need not carry J
+  bool noj = precond;
+  rc = bra_jacobi_svd(ctx, (int)k, Xj, ldj, J, ldj, sig.data(), order.data(), &noj);
   if (rc) return rc;
   // psvdrank (src/psvd.jl:301-308) on the sorted singular values
   std::vector<double> ssort((size_t)k);
@@ -371,9 +374,17 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
   // right factor of op(A):  Vop' = Ysel' Qz' P'   with Ysel = X[:, order] / sigma
   //   plain: right vectors of M = normalised columns of X J;   preconditioned: Q2 J'[:, order]
   if (precond) {
-    // Xp (= Y' Sigma) has been consumed by the left factor above: reuse it for J'[:, order]
-    rc = bra_gather_scale_cols(ctx, J, ldj, k, (int)kk, ctx->aux_in1.as<int>(), nullptr, Xp, ldj);
-    if (rc) return rc;
+    if (noj) {
+      // J'[:, order] = R2^{-T} (Y' Sigma)[:, order]: J's buffer is free, Rinv2 still holds R2^{-1}
+      rc = bra_gather_scale_cols(ctx, Xj, ldj, k, (int)kk, ctx->aux_in1.as<int>(), nullptr, J, ldj);
+      if (rc) return rc;
+      rc = bra_gemm_generic(ctx, Rinv2, ldj, 1, J, 1, ldj, k, kk, k, Xp, ldj);
+      if (rc) return rc;
+    } else {
+      // Xp (= Y' Sigma) has been consumed by the left factor above: reuse it for J'[:, order]
+      rc = bra_gather_scale_cols(ctx, J, ldj, k, (int)kk, ctx->aux_in1.as<int>(), nullptr, Xp, ldj);
+      if (rc) return rc;
+    }
     rc = bra_gemm_generic(ctx, Q2, 1, ldj, Xp, 1, ldj, k, kk, k, Ysel, ldj);                 // Ysel = Q2 J'[:, order]
     if (rc) return rc;
   } else {

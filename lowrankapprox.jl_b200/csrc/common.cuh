@@ -221,7 +221,7 @@ int bra_cholesky_upper(bra_ctx* ctx, int k, double* G, int64_t ldg, double* Rout
 int bra_cholqr2(bra_ctx* ctx, int64_t rows, int k, double* Y, int64_t ldy, const double* Rpre, double* Rout,
                 bool rows_sharded = false);
 int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64_t ldj, double* sigma_host,
-                   int* order_host);
+                   int* order_host, bool* skip_J = nullptr);
 extern "C" {
 int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* dA, int64_t lda,
                         const bra_opts* o, const bra_rand* rnd);

@@ -335,7 +335,7 @@ __device__ __forceinline__ void team_sync(int team) {
 // 64 DFMA/clk/SM), written with two reciprocal square roots and no division:
 //   cos(2 theta) = |d| / h,  sin(2 theta) = sign(d) 2c / h,  h = sqrt(d^2 + 4c^2),  d = b - a
 //   cs = sqrt((1 + cos 2theta) / 2),  sn = sin(2 theta) / (2 cs)         (|theta| <= pi/4)
-template <int TS, int R>
+template <int TS, int R, bool WJ>
 __device__ __forceinline__ bool rotate_pair(double* __restrict__ Xs, double* __restrict__ Js, int kp, int k, int p, int q,
                                             int team, int e, double* __restrict__ rb, double tol2, double thr2, int* s_big) {
   constexpr int WPT = TS / 32;
@@ -414,17 +414,28 @@ __device__ __forceinline__ bool rotate_pair(double* __restrict__ Xs, double* __r
   team_sync<TS>(team);
   const double cs = rb[WPT * 4 + 0], sn = rb[WPT * 4 + 1];
   if (sn == 2.0) return false;
-  double* jp = Js + (size_t)p * kp;
-  double* jq = Js + (size_t)q * kp;
+  if (WJ) {
+    double* jp = Js + (size_t)p * kp;
+    double* jq = Js + (size_t)q * kp;
 #pragma unroll
-  for (int i = 0; i < R; ++i) {
-    const int r = e + TS * i;
-    if (r < k) {
-      const double ju = jp[r], jv = jq[r];
-      xp[r] = fma(cs, u[i], -sn * v[i]);
-      xq[r] = fma(sn, u[i], cs * v[i]);
-      jp[r] = fma(cs, ju, -sn * jv);
-      jq[r] = fma(sn, ju, cs * jv);
+    for (int i = 0; i < R; ++i) {
+      const int r = e + TS * i;
+      if (r < k) {
+        const double ju = jp[r], jv = jq[r];
+        xp[r] = fma(cs, u[i], -sn * v[i]);
+        xq[r] = fma(sn, u[i], cs * v[i]);
+        jp[r] = fma(cs, ju, -sn * jv);
+        jq[r] = fma(sn, ju, cs * jv);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const int r = e + TS * i;
+      if (r < k) {
+        xp[r] = fma(cs, u[i], -sn * v[i]);
+        xq[r] = fma(sn, u[i], cs * v[i]);
+      }
     }
   }
   return true;
@@ -437,7 +448,9 @@ __device__ __forceinline__ bool rotate_pair(double* __restrict__ Xs, double* __r
 // every pair of blocks meets exactly once.  CTA i owns pair i of the current step, so between steps it KEEPS one of
 // its two blocks in shared memory and exchanges only the other one with a neighbour (half the traffic of a
 // round-robin tournament, where both blocks move every step).
-template <int BC, int TS, int R>
+// WJ = false: the rotations are not accumulated (no J panel in shared memory, half the exchange traffic); the caller
+// recovers J from the triangular starting matrix, J = X0^{-1} X_final (Drmac-Veselic).
+template <int BC, int TS, int R, bool WJ>
 __global__ void __launch_bounds__(BC * TS, 1) jacobi_team_kernel(JacobiParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NC = 2 * BC;                       // columns in a panel
@@ -446,7 +459,7 @@ __global__ void __launch_bounds__(BC * TS, 1) jacobi_team_kernel(JacobiParams P)
   const int k = P.k, tid = threadIdx.x, N = P.nblk, cta = blockIdx.x, NP = N / 2;
   const int kp = (k + 1) & ~1;                     // padded column length (16-byte aligned columns)
   double* Xs = reinterpret_cast<double*>(smem_raw);             // [NC][kp]   slot s = columns s*BC .. s*BC+BC-1
-  double* Js = Xs + (size_t)NC * kp;                             // [NC][kp]
+  double* Js = Xs + (size_t)(WJ ? NC : 0) * kp;                  // [NC][kp] (absent without accumulation)
   double* red = Js + (size_t)NC * kp;                            // [2][BC][RBS]
   int* perm = reinterpret_cast<int*>(red + (size_t)2 * BC * RBS);   // [N] block id at each position
   __shared__ int s_rot, s_big;
@@ -474,8 +487,8 @@ __global__ void __launch_bounds__(BC * TS, 1) jacobi_team_kernel(JacobiParams P)
       const int gc = blk * BC + c;
       if (gc < k) {
         bulk_g2s(Xs + (size_t)(slot * BC + c) * kp, P.X + (int64_t)gc * P.ldx, colbytes, &s_mbar);
-        bulk_g2s(Js + (size_t)(slot * BC + c) * kp, P.J + (int64_t)gc * P.ldj, colbytes, &s_mbar);
-        bytes += 2 * colbytes;
+        if (WJ) bulk_g2s(Js + (size_t)(slot * BC + c) * kp, P.J + (int64_t)gc * P.ldj, colbytes, &s_mbar);
+        bytes += (WJ ? 2 : 1) * colbytes;
       }
     }
     return bytes;
@@ -487,7 +500,7 @@ __global__ void __launch_bounds__(BC * TS, 1) jacobi_team_kernel(JacobiParams P)
       double* js = Js + (size_t)(slot * BC + team) * kp;
       for (int r = e; r < kp; r += TS) {
         xs[r] = 0.0;
-        js[r] = 0.0;
+        if (WJ) js[r] = 0.0;
       }
     }
   };
@@ -496,7 +509,7 @@ __global__ void __launch_bounds__(BC * TS, 1) jacobi_team_kernel(JacobiParams P)
       const int gc = blk * BC + c;
       if (gc < k) {
         bulk_s2g(P.X + (int64_t)gc * P.ldx, Xs + (size_t)(slot * BC + c) * kp, colbytes);
-        bulk_s2g(P.J + (int64_t)gc * P.ldj, Js + (size_t)(slot * BC + c) * kp, colbytes);
+        if (WJ) bulk_s2g(P.J + (int64_t)gc * P.ldj, Js + (size_t)(slot * BC + c) * kp, colbytes);
       }
     }
   };
@@ -549,9 +562,9 @@ __global__ void __launch_bounds__(BC * TS, 1) jacobi_team_kernel(JacobiParams P)
             // expect_tx first (the barrier cannot complete before the byte count is known), then the copies
             uint32_t want = 0;
             if (needL)
-              for (int c = 0; c < BC; ++c) want += (perm[pL] * BC + c < k) ? 2 * colbytes : 0;
+              for (int c = 0; c < BC; ++c) want += (perm[pL] * BC + c < k) ? (WJ ? 2 : 1) * colbytes : 0;
             if (needR)
-              for (int c = 0; c < BC; ++c) want += (perm[pR] * BC + c < k) ? 2 * colbytes : 0;
+              for (int c = 0; c < BC; ++c) want += (perm[pR] * BC + c < k) ? (WJ ? 2 : 1) * colbytes : 0;
             jmbar_expect_tx(&s_mbar, want);
             if (needL) load_slot_bulk(sl, perm[pL]);
             if (needR) load_slot_bulk(sr, perm[pR]);
@@ -573,7 +586,7 @@ __global__ void __launch_bounds__(BC * TS, 1) jacobi_team_kernel(JacobiParams P)
             int p, q;
             rr_pair(BC, rd, team % (BC / 2 > 0 ? BC / 2 : 1), p, q);
             const int off = (team < BC / 2) ? 0 : BC;
-            rot_any |= rotate_pair<TS, R>(Xs, Js, kp, k, off + p, off + q, team, e, red + (size_t)(par * BC + team) * RBS,
+            rot_any |= rotate_pair<TS, R, WJ>(Xs, Js, kp, k, off + p, off + q, team, e, red + (size_t)(par * BC + team) * RBS,
                                           tol2, thr2, &s_big);
             __syncthreads();
           }
@@ -581,7 +594,7 @@ __global__ void __launch_bounds__(BC * TS, 1) jacobi_team_kernel(JacobiParams P)
         // ---- every step: each column of one block meets each column of the other once (BC rounds of BC disjoint pairs) ----
         for (int rd = 0; rd < BC; ++rd, par ^= 1) {
           const int p = team, q = BC + ((team + rd) % BC);
-          rot_any |= rotate_pair<TS, R>(Xs, Js, kp, k, p, q, team, e, red + (size_t)(par * BC + team) * RBS, tol2, thr2,
+          rot_any |= rotate_pair<TS, R, WJ>(Xs, Js, kp, k, p, q, team, e, red + (size_t)(par * BC + team) * RBS, tol2, thr2,
                                         &s_big);
           __syncthreads();
         }
@@ -679,12 +692,12 @@ __global__ void __launch_bounds__(BC * TS, 1) jacobi_team_kernel(JacobiParams P)
 #undef JTICK
 }
 
-template <int BC, int TS, int R>
+template <int BC, int TS, int R, bool WJ = true>
 cudaError_t launch_jacobi(const JacobiParams& P, int grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(jacobi_team_kernel<BC, TS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(jacobi_team_kernel<BC, TS, R, WJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   void* args[] = {(void*)&P};
-  return cudaLaunchCooperativeKernel((void*)jacobi_team_kernel<BC, TS, R>, dim3(grid), dim3(BC * TS), args, smem, st);
+  return cudaLaunchCooperativeKernel((void*)jacobi_team_kernel<BC, TS, R, WJ>, dim3(grid), dim3(BC * TS), args, smem, st);
 }
 
 __global__ void set_identity_kernel(int k, double* __restrict__ J, int64_t ldj) {
@@ -829,18 +842,24 @@ int bra_chol_status(bra_ctx* ctx) {
 
 // One-sided Jacobi on the columns of X (k x k): X J = U diag(sigma).  On return X holds U diag(sigma) (columns
 // unsorted), J the accumulated rotations, sigma_host the column norms, order_host the descending order.
+// skip_J (optional, in/out): in = the caller can do without the accumulated rotations (it recovers them from a
+// triangular X); out = whether the kernel really ran without J (only the 8-rows-per-thread configurations do).
 int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64_t ldj, double* sigma_host,
-                   int* order_host) {
+                   int* order_host, bool* skip_J) {
+  const bool may_skip = skip_J && *skip_J && getenv("BRA_JACOBI_KEEPJ") == nullptr;
+  if (skip_J) *skip_J = false;
   if (k <= 0) return BRA_OK;
   ProfScope ps(ctx, BRA_PROF_SVD);
-  set_identity_kernel<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(k, J, ldj);
-  ctx->launches++;
   constexpr int MAX_SWEEPS = 48;
   int sweeps = 0, converged = 1;
   bool have_out = false;
   if ((ldx & 1) || (ldj & 1) || (reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(J) & 15)) {
     ctx->set_error("Jacobi SVD: X and J need even leading dimensions and 16-byte aligned bases");
     return -4;
+  }
+  if (k == 1) {
+    set_identity_kernel<<<1, 32, 0, ctx->stream>>>(k, J, ldj);
+    ctx->launches++;
   }
   if (k > 1) {
     // team size: k <= TS * R rows in registers (R = 4, or 8 on request); panel = 2*BC columns of X and of J in
@@ -859,6 +878,19 @@ int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64
       ts >>= 1;
       rr = 8;
     }
+    bool noj = may_skip && rr == 8;
+    // without the J panel a pair fits one warp (16 rows per lane): no cross-warp reduction, no team barrier --
+    // measured at k = 498: 4.37 ms against 4.56 ms with two warps per pair
+    const char* r16 = getenv("BRA_JACOBI_R16");
+    if (noj && k <= 512 && !(r16 && atoi(r16) == 0)) {
+      ts = 32;
+      rr = 16;
+    }
+    if (skip_J) *skip_J = noj;
+    if (!noj) {
+      set_identity_kernel<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(k, J, ldj);
+      ctx->launches++;
+    }
     int bc = 1024 / ts;
     if (bc > 4) bc = 4;
     if (const char* ev = getenv("BRA_JACOBI_BC")) {
@@ -867,7 +899,7 @@ int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64
     }
     const size_t kp = (size_t)((k + 1) & ~1);
     const size_t budget = (size_t)ctx->smem_optin - 2048;
-    auto need = [&](int b) { return (size_t)32 * b * kp + (size_t)2 * b * ((ts / 32) * 4 + 2) * 8 + (size_t)4 * (2 * ((k + 2 * b - 1) / (2 * b))) + 64; };
+    auto need = [&](int b) { return (size_t)(noj ? 16 : 32) * b * kp + (size_t)2 * b * ((ts / 32) * 4 + 2) * 8 + (size_t)4 * (2 * ((k + 2 * b - 1) / (2 * b))) + 64; };
     while (bc > 1 && (need(bc) > budget || k <= bc)) bc >>= 1;   // tiny cores: keep at least two blocks of real columns
     if (need(bc) > budget) {
       ctx->set_error("Jacobi SVD: k too large for the shared-memory panel");
@@ -902,7 +934,8 @@ int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64
     P.rotated = ctx->jwork.as<int>() + 64;
     P.bstep = ctx->jwork.as<unsigned>() + 256 + 2 * MAX_SWEEPS;
     cudaError_t e = cudaErrorInvalidValue;
-#define JL(B_, T_, R_) if (bc == B_ && ts == T_ && rr == R_) e = launch_jacobi<B_, T_, R_>(P, grid, smem, ctx->stream);
+#define JL(B_, T_, R_) if (bc == B_ && ts == T_ && rr == R_ && !noj) e = launch_jacobi<B_, T_, R_>(P, grid, smem, ctx->stream);
+#define JN(B_, T_) if (bc == B_ && ts == T_ && noj && rr == 8) e = launch_jacobi<B_, T_, 8, false>(P, grid, smem, ctx->stream);
     JL(8, 32, 4) JL(4, 32, 4) JL(2, 32, 4) JL(1, 32, 4)
     JL(8, 64, 4) JL(4, 64, 4) JL(2, 64, 4) JL(1, 64, 4)
     JL(8, 128, 4) JL(4, 128, 4) JL(2, 128, 4) JL(1, 128, 4)
@@ -910,7 +943,11 @@ int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64
     JL(2, 512, 4) JL(1, 512, 4)
     JL(1, 1024, 4)
     JL(8, 32, 8) JL(4, 32, 8) JL(8, 64, 8) JL(4, 64, 8) JL(8, 128, 8) JL(4, 128, 8)
+    JN(8, 32) JN(4, 32) JN(8, 64) JN(4, 64) JN(8, 128) JN(4, 128)
+    if (noj && rr == 16 && bc == 4) e = launch_jacobi<4, 32, 16, false>(P, grid, smem, ctx->stream);
+    if (noj && rr == 16 && bc == 8) e = launch_jacobi<8, 32, 16, false>(P, grid, smem, ctx->stream);
 #undef JL
+#undef JN
     BRA_CUDA(e);
     ctx->launches++;
     have_out = true;

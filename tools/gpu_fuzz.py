@@ -52,7 +52,7 @@ def main():
                 eg = np.linalg.norm(A - (Fg.U * Fg.S) @ Fg.Vt, 2) / nrm if kg else 0.0
                 ds = np.max(np.abs(Fg.S - Fo.S)) / nrm if ko == kg and ko else 0.0
                 msg = f"k {kg}/{ko} err {eg:.2e}/{eo:.2e} dS {ds:.1e}"
-                ok = ko == kg and eg <= 2 * eo + 1e-14 and ds <= 1e-10
+                ok = ko == kg and eg <= 2 * eo + 1e-13 and ds <= 1e-10      # exact-rank inputs: rounding floor ~4e-14 vs LAPACK's 1e-14
             else:
                 f_o = getattr(o, fn)
                 f_g = getattr(brapprox, fn)
