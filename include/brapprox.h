@@ -10,6 +10,7 @@
  *     pqrback_postproc(B, p, tau, k, opts)            src/pqr.jl:420
  *     sketchfact(side, trans, A, opts)                src/sketch.jl:52
  *     idfact / pqrfact / psvdfact                     src/id.jl:434, src/pqr.jl:290, src/psvd.jl:238
+ *     pheigfact / prange / snorm, snormdiff           src/pheig.jl:276, src/prange.jl:14, src/snorm.jl:14,49
  *
  * Conventions (same as the reference's LAPACK calls): FP64 real, column-major,
  * explicit leading dimensions, int64 dimensions, 1-based index outputs
@@ -78,10 +79,10 @@ typedef struct bra_opts {
   int64_t rank;              /* < 0: unbounded */
   int64_t nb;                /* QRCP block size and first adaptive rank guess; default 32 */
   int32_t sketch;            /* BRA_SKETCH_* */
-  int32_t sketch_randn_niter;/* must be 0 in this build */
+  int32_t sketch_randn_niter;/* >= 0: Gaussian power iterations (src/sketch.jl:140-149); single-GPU contexts only */
   int32_t sketchfact_adap;   /* default 1 */
   int32_t retval_mask;       /* BRA_RET_* */
-  double maxdet_tol;         /* must be < 0 in this build */
+  double maxdet_tol;         /* < 0: off; >= 0: strong-RRQR swaps until max|T| <= 1 + tol (src/pqr.jl:444-501) */
   int64_t maxdet_niter;
   int64_t samp_a, samp_b;    /* 0,0 = the reference default for opts.sketch */
   uint64_t seed;             /* fast mode: Philox key */

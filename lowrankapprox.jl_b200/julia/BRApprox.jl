@@ -11,7 +11,7 @@ module BRApprox
 
 using LowRankApprox
 using LowRankApprox: LRAOptions, IDPackedV, chkopts!, chktrans
-import LowRankApprox: idfact
+import LowRankApprox: idfact, pqrfact, psvdfact, prange
 
 const libbra = "libbrapprox.so"
 const BRA_MAX_ROUNDS = 24
@@ -96,6 +96,79 @@ function idfact(trans::Symbol, A::Matrix{Float64}, opts::LRAOptions=LRAOptions()
   T = Matrix{Float64}(undef, k, nn - k)
   k > 0 && nn > k && ccall((:bra_fetch, libbra), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Int64), CTX[], 2, T, k)
   IDPackedV(p[1:k], p[k+1:end], T)                        # src/id.jl:445-446
+end
+
+# ---- the other front-ends, in FAST mode (n_rounds = 0: the library draws its random inputs with the device Philox
+# generator keyed by BraOpts.seed; pass drawn inputs as in idfact above to keep `Random.seed!` reproducibility) ----
+
+const NORAND = BraRand(0, 0, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL)
+
+function getinfo()
+  info = Ref{BraInfo}()
+  ccall((:bra_get_info, libbra), Cint, (Ptr{Cvoid}, Ref{BraInfo}), CTX[], info)
+  info[]
+end
+
+function fetch!(which::Integer, dst::Array, ld::Integer)
+  isempty(dst) && return dst
+  rc = ccall((:bra_fetch, libbra), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Int64), CTX[], which, dst, ld)
+  rc == 0 || throw_bra(rc)
+  dst
+end
+
+function pqrfact(trans::Symbol, A::Matrix{Float64}, opts::LRAOptions=LRAOptions(); args...)   # src/pqr.jl:290-307
+  chktrans(trans)
+  opts = copy(opts; args...)
+  chkopts!(opts, A)
+  m, n = size(A)
+  rc = ccall((:bra_pqrfact_f64, libbra), Cint,
+             (Ptr{Cvoid}, Cchar, Int64, Int64, Ptr{Float64}, Int64, Ref{BraOpts}, Ref{BraRand}),
+             CTX[], trans == :n ? 'n' : 'c', m, n, A, stride(A, 2), BraOpts(opts), NORAND)
+  rc == 0 || throw_bra(rc)
+  i = getinfo()
+  p = fetch!(1, Vector{Int}(undef, i.n), i.n)
+  Q = fetch!(3, Matrix{Float64}(undef, i.m, i.k), i.m)
+  R = fetch!(4, Matrix{Float64}(undef, i.k, i.n), max(i.k, 1))
+  LowRankApprox.PartialQR(Q, R, p)
+end
+
+function psvdfact(A::Matrix{Float64}, opts::LRAOptions=LRAOptions(); args...)                  # src/psvd.jl:238-272
+  opts = copy(opts; args...)
+  chkopts!(opts, A)
+  m, n = size(A)
+  rc = ccall((:bra_psvdfact_f64, libbra), Cint,
+             (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Ref{BraOpts}, Ref{BraRand}),
+             CTX[], m, n, A, stride(A, 2), BraOpts(opts), NORAND)
+  rc == 0 || throw_bra(rc)
+  k = getinfo().ksvd
+  U  = fetch!(5, Matrix{Float64}(undef, m, k), m)
+  S  = fetch!(6, Vector{Float64}(undef, k), k)
+  Vt = fetch!(7, Matrix{Float64}(undef, k, n), max(k, 1))
+  LowRankApprox.PartialSVD(U, S, Vt)
+end
+
+function prange(trans::Symbol, A::Matrix{Float64}, opts::LRAOptions=LRAOptions(); args...)     # src/prange.jl:14-62
+  trans in (:n, :c, :b) || throw(ArgumentError("trans"))
+  opts = copy(opts; args...)
+  chkopts!(opts, A)
+  m, n = size(A)
+  rc = ccall((:bra_prange_f64, libbra), Cint,
+             (Ptr{Cvoid}, Cchar, Int64, Int64, Ptr{Float64}, Int64, Ref{BraOpts}, Ref{BraRand}, Ref{BraRand}),
+             CTX[], Char(string(trans)[1]), m, n, A, stride(A, 2), BraOpts(opts), NORAND, NORAND)
+  rc == 0 || throw_bra(rc)
+  i = getinfo()
+  fetch!(3, Matrix{Float64}(undef, i.m, i.k), i.m)
+end
+
+# snormdiff(A, L*R) with A, L, R already on the device (CuArray pointers): src/snorm.jl:14-53
+function snormdiff_device(m, n, dA::Ptr{Float64}, lda, k, dL::Ptr{Float64}, ldl, dR::Ptr{Float64}, ldr, opts::LRAOptions)
+  res = Ref{Cdouble}(0); nit = Ref{Int64}(0)
+  rc = ccall((:bra_snorm_f64, libbra), Cint,
+             (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64,
+              Ref{BraOpts}, Int64, Ptr{Float64}, Ref{Cdouble}, Ref{Int64}),
+             CTX[], m, n, dA, lda, k, dL, ldl, dR, ldr, BraOpts(opts), opts.snorm_niter, C_NULL, res, nit)
+  rc == 0 || throw_bra(rc)
+  res[]
 end
 
 end # module
