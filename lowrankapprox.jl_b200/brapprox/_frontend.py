@@ -179,6 +179,7 @@ def idfact_device(A, opts: Optional[LRAOptions] = None, trans: str = "n", rand=N
 def idfact(A, opts: Optional[LRAOptions] = None, trans: str = "n", rand=None,
            ctx: Optional[Context] = None, **kw) -> IDPackedV:
     """idfact(trans, A, opts; kw...) -> IDPackedV(sk, rd, T) (src/id.jl:434-447)."""
+    _trans(trans)                                       # chktrans first, like the reference (src/id.jl:436)
     ctx = ctx or default_context()
     idfact_device(A, opts, trans, rand, ctx, **kw)
     inf, rounds, steps = _rounds(ctx)

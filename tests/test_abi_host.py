@@ -129,3 +129,18 @@ def test_product_never_imports_oracle():
                 bad = re.findall(r"^\s*(?:import|from)\s+(?:lra_oracle|oracle)\b|#include\s+[\"<][^\">]*oracle",
                                  txt, flags=re.M)
                 assert not bad, (f, bad)
+
+
+def test_frontend_argument_checks_without_gpu():
+    """The reference's argument checks fire before any device work (prange_chktrans src/prange.jl:79-80,
+    sketchfact_chkargs src/sketch.jl:80-84, chktrans src/LowRankApprox.jl:150)."""
+    import brapprox
+    A = np.zeros((4, 4))
+    with pytest.raises(ValueError):
+        brapprox.prange(A, trans="x")
+    with pytest.raises(ValueError):
+        brapprox.sketch(A, 2, side="middle")
+    with pytest.raises(ValueError):
+        brapprox.sketch(A, -1)
+    with pytest.raises(ValueError):
+        brapprox.idfact(A, trans="t")
