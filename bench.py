@@ -237,6 +237,23 @@ def run_c3(ctx, ext, dev, steps=5, n=16384):
                          "algorithmic_bytes": bytes_sk, "peak_source": src}}
 
 
+def run_c1(ctx, ext, dev, steps=50, n=1024):
+    """BASELINE config 1 (the reference's own CPU-runnable case): Hilbert 1024^2, rtol=1e-15, sketch=:randn -- one round
+    of order 40, k ~ 26: pure latency, reported in microseconds (a roofline fraction is not meaningful here)."""
+    import torch
+    from brapprox._binding import DeviceMatrix
+    from brapprox._frontend import idfact_device, pqrfact_device
+    i = torch.arange(n, dtype=torch.float64, device=dev)
+    At = (1.0 / (i[:, None] + i[None, :] + 1.0)).contiguous()            # symmetric: row-major == column-major
+    A = DeviceMatrix(At.data_ptr(), n, n, n, keep=At)
+    out = {"workload": f"C1: Hilbert {n}x{n} FP64, rtol=1e-15, sketch=randn, A resident (latency case)"}
+    for name, fn in (("idfact", idfact_device), ("pqrfact", pqrfact_device)):
+        t, inf = _timed(ext, lambda sd: fn(A, rtol=1e-15, seed=sd, ctx=ctx), steps, 3)
+        out[name + "_us"] = t * 1e6
+        out[name + "_rounds_order_k"] = [(int(inf.orders[r]), int(inf.ks[r])) for r in range(inf.rounds)]
+    return out
+
+
 def run_c5(ctx, ext, dev, rank, world, nblocks_total=16384, steps=3, m=512):
     """BASELINE config 5: batched idfact of independent 512x512 Cauchy blocks, sketch=:sprn, rtol=1e-12; blocks are
     dealt out in contiguous groups, one group per GPU, no collective (strong scaling: total block count fixed)."""
@@ -495,6 +512,11 @@ def main():
             dist.all_reduce(tt, op=op)
             return float(tt.item())
 
+        try:
+            if rank == 0:
+                extra["C1"] = run_c1(ctx, ext, dev)
+        except Exception as e:      # a side measurement must never take the headline down
+            extra["C1"] = {"error": repr(e)[:300]}
         try:
             if rank == 0:
                 extra["C3"] = run_c3(ctx, ext, dev)
