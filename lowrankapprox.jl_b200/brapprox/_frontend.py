@@ -460,6 +460,8 @@ def snormdiff(A, left=None, right=None, opts: Optional[LRAOptions] = None, x0=No
         keep += [kL, kR]
     px = C.c_void_p(0)
     if x0 is not None:
+        if np.size(x0) != dA.n:
+            raise ValueError("DimensionMismatch: x0")
         dx, kx = _dev(np.asarray(x0, dtype=np.float64).reshape(-1, 1))
         px = C.c_void_p(dx.ptr)
         keep.append(kx)
