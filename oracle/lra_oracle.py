@@ -93,6 +93,8 @@ def dgemm(A: np.ndarray, B: np.ndarray, transa: bool = False, transb: bool = Fal
     m = A.shape[1] if transa else A.shape[0]
     k = A.shape[0] if transa else A.shape[1]
     n = B.shape[0] if transb else B.shape[1]
+    if k != (B.shape[1] if transb else B.shape[0]):
+        raise ValueError(f"DimensionMismatch: op(A) is {m}x{k}, op(B) has {B.shape[1] if transb else B.shape[0]} rows")
     C = np.zeros((m, n), order="F")
     one, zero = _c_dbl(1.0), _c_dbl(0.0)
     _lib.scipy_dgemm_(

@@ -37,6 +37,38 @@ def id_case(name, A, seed, trans="n", **kw):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
 
 
+def _rand_fields(rin, d):
+    for t, r in enumerate(rin.drawn):
+        for key, val in r.items():
+            if key not in ("kind", "round", "order"):
+                d[f"rand{t}_{key}"] = val
+    d["n_rand"] = len(rin.drawn)
+
+
+def psvd_case(name, A, seed, **kw):
+    """psvdfact + pqrfact of the same matrix on the same draws; factors stored with the sign convention
+    'largest-magnitude entry of every left vector positive' so that any correct implementation can be compared."""
+    rin = o.RandomInputs(seed)
+    F = o.psvdfact(A, o.LRAOptions(**kw), rin)
+    sgn = np.sign(F.U[np.argmax(np.abs(F.U), axis=0), np.arange(F.U.shape[1])])
+    d = {"A": A, "S": F.S, "US": F.U * sgn * F.S, "SVt": (F.Vt * sgn[:, None]) * F.S[:, None], "k_id": F.k_id,
+         "opts": np.array(sorted(kw.items()), dtype=object)}
+    _rand_fields(rin, d)
+    trans = "n" if A.shape[0] >= A.shape[1] else "c"          # the side psvdfact factors (src/psvd.jl:242,256): same draws
+    rin2 = o.RandomInputs(seed)
+    Q = o.pqrfact(A, o.LRAOptions(**kw), rin2, trans)
+    dq = np.sign(np.diag(Q.R[:, :Q.Q.shape[1]]))
+    d.update({"p": Q.p, "Q": Q.Q * dq, "R": Q.R * dq[:, None], "trans": trans})
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+
+
+def new_cases_r01f():
+    """Fixtures added late in round 1 (kept apart so that regenerating them never rewrites the older files)."""
+    A = o.decaying_matrix(120, 90, 36, 11.0, 36, seed=7)
+    psvd_case("psvd_decay_120x90", A, seed=6, rtol=1e-10)
+    psvd_case("psvd_decay_90x120", np.asfortranarray(A.T), seed=8, rtol=1e-9)
+
+
 def main():
     rng = np.random.default_rng(2024)
     A = o.decaying_matrix(96, 80, 40, 13.0, 40, seed=1)
@@ -52,4 +84,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "r01f":
+        new_cases_r01f()
+    else:
+        main()
+        new_cases_r01f()
