@@ -113,8 +113,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_sample(n: int, what: str, max_seconds: float = 25.0, threads: int = 0):
-    """Times the oracle on the host cores: factorizations/s on a bounded sample of the same workload."""
+def cpu_sample(n: int, what: str, max_seconds: float = 25.0, threads: int = 0, steps: int = 0, warmup: int = 0):
+    """Times the oracle on the host cores: factorizations/s on a bounded sample of the same workload.
+    steps == 0: the cpu_baseline leg (median of up to 12 factorizations within max_seconds).
+    steps > 0: the reference arm -- `warmup` untimed factorizations, then `steps` timed ones (value = count / total time,
+    like the GPU arm), cut short only if max_seconds is exceeded (the counts actually run are reported)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import lra_oracle as o
@@ -125,6 +128,13 @@ def cpu_sample(n: int, what: str, max_seconds: float = 25.0, threads: int = 0):
     fn = o.psvdfact if what == "psvdfact" else o.idfact
     times, ks = [], []
     t_start = time.perf_counter()
+    nwarm = 0
+    for w in range(warmup if steps > 0 else 0):
+        if w >= 1 and time.perf_counter() - t_start > max_seconds / 4:
+            break
+        fn(A, opts, o.RandomInputs(1000 + w))
+        nwarm += 1
+    t_start = time.perf_counter()
     rep = 0
     while True:
         t0 = time.perf_counter()
@@ -132,12 +142,16 @@ def cpu_sample(n: int, what: str, max_seconds: float = 25.0, threads: int = 0):
         times.append(time.perf_counter() - t0)
         ks.append(len(F.S) if what == "psvdfact" else F.k)
         rep += 1
-        if rep >= 2 and (time.perf_counter() - t_start > max_seconds or rep >= 12):
+        if steps > 0:
+            if rep >= steps or (rep >= 2 and time.perf_counter() - t_start > max_seconds):
+                break
+        elif rep >= 2 and (time.perf_counter() - t_start > max_seconds or rep >= 12):
             break
-    best = sorted(times)[len(times) // 2]
-    return {"value": 1.0 / best, "unit": "factorizations/s", "cores": cores, "kind": "port",
-            "sample": f"{rep} x {what} of the same {n}x{n} workload on the host (median; includes drawing Omega "
-                      f"with numpy), OpenBLAS threads={o.get_blas_threads()}, k={ks[-1]}"}, times
+    per = (sum(times) / len(times)) if steps > 0 else sorted(times)[len(times) // 2]
+    stat = "mean" if steps > 0 else "median"
+    return {"value": 1.0 / per, "unit": "factorizations/s", "cores": cores, "kind": "port",
+            "sample": f"{rep} x {what} of the same {n}x{n} workload on the host ({stat}; includes drawing Omega "
+                      f"with numpy), OpenBLAS threads={o.get_blas_threads()}, k={ks[-1]}"}, times, nwarm
 
 
 def run_reference(args):
@@ -146,11 +160,11 @@ def run_reference(args):
         return
     # same metric as our arm: `auto` means psvdfact there (the library has the psvd tail), so it does here
     what = "psvdfact" if args.what == "auto" else args.what
-    base, times = cpu_sample(args.n, what, max_seconds=60.0)
-    # honour --steps/--warmup within a bounded budget: the sample above already ran >= 2 factorizations
+    # --steps / --warmup are honoured inside a bounded budget (one factorization takes seconds on the host)
+    base, times, nwarm = cpu_sample(args.n, what, max_seconds=150.0, steps=max(1, args.steps), warmup=args.warmup)
     v = base["value"]
     line = {"impl": "reference", "metric": f"{what}_factorizations_per_sec", "value": v, "unit": "factorizations/s",
-            "n_gpus": args.gpus, "steps": len(times), "warmup": 0, "ms_per_step": 1e3 / v, "higher_is_better": True,
+            "n_gpus": args.gpus, "steps": len(times), "warmup": nwarm, "ms_per_step": 1e3 / v, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"C2: {what} of {args.n}x{args.n} FP64, sigma_j=10^(-12j/500), rtol=1e-12, "
                                    "sketch=randn (oracle = reference's LAPACK/BLAS CPU path restated)"},
@@ -561,7 +575,7 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu, _ = cpu_sample(n, what)
+        cpu, _, _ = cpu_sample(n, what)
 
     line = {
         "metric": f"{what}_factorizations_per_sec", "value": value, "unit": "factorizations/s", "n_gpus": world,
