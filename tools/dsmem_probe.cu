@@ -123,6 +123,64 @@ __global__ void __launch_bounds__(128, 1) k_dsmem(int iters, int bytes, long lon
   cluster_sync();                                                    // nobody exits while the partner may still write here
 }
 
+// ---- path B': PULL -- the consumer reads the partner's block out of the partner's shared memory with ld.shared::cluster
+// after a `ready` arrive, and frees it with a `consumed` arrive (the protocol planned for the Jacobi kernel) -------------
+__global__ void __launch_bounds__(128, 1) k_dsmem_pull(int iters, int bytes, long long* cyc, double* check) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  double* send = reinterpret_cast<double*>(sm);
+  __shared__ __align__(8) uint64_t ready, consumed;
+  const uint32_t rank = cluster_rank(), partner = rank ^ 1u;
+  const int nd = bytes / 8;
+  if (threadIdx.x == 0) {
+    mbar_init(&ready, 1);
+    mbar_init(&consumed, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < nd; i += blockDim.x) send[i] = (double)(blockIdx.x + 1);
+  __syncthreads();
+  cluster_sync();
+  const uint32_t rsend = mapa(s32(send), partner);
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    __syncthreads();                                                 // every thread's writes to `send` are done
+    if (threadIdx.x == 0) {
+      mbar_arrive_remote(mapa(s32(&ready), partner));                // release.cluster: my block may be read
+      mbar_wait(&ready, it & 1);                                     // the partner's block may be read
+    }
+    __syncthreads();
+    asm volatile("fence.acq_rel.cluster;" ::: "memory");
+    double v[MAXR];
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < MAXR / 2; ++j) {
+      const int i = 2 * (threadIdx.x + j * 128);                     // 16-byte remote loads
+      double a = 0.0, c = 0.0;
+      if (i < nd) asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(c) : "r"(rsend + 8u * (uint32_t)i) : "memory");
+      v[2 * j] = a;
+      v[2 * j + 1] = c;
+      acc += a + c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_arrive_remote(mapa(s32(&consumed), partner));             // the partner may overwrite its block
+      mbar_wait(&consumed, it & 1);                                  // I may overwrite mine
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < MAXR / 2; ++j) {
+      const int i = 2 * (threadIdx.x + j * 128);
+      if (i < nd) {
+        send[i] = v[2 * j] + 1.0;
+        send[i + 1] = v[2 * j + 1] + 1.0;
+      }
+    }
+    if (it == iters - 1 && threadIdx.x == 0) check[blockIdx.x] = acc;
+  }
+  long long t1 = clock64();
+  if (threadIdx.x == 0) cyc[blockIdx.x] = (t1 - t0) / iters;
+  cluster_sync();
+}
+
 // ---- path A: the same pair exchange through global memory (bulk store + flag, poll + bulk load) ---------------------
 __global__ void __launch_bounds__(128, 1) k_global(int iters, int bytes, double* gbuf, unsigned* flags, long long* cyc,
                                                    double* check) {
@@ -215,7 +273,15 @@ int main() {
       CK(cudaDeviceSynchronize());
       long long mx = 0;
       for (int i = 0; i < G; ++i) mx = cyc[i] > mx ? cyc[i] : mx;
-      std::printf("dsmem pair   %6d B, cluster %d: %lld cycles / exchange (max over %d CTAs), check %.0f\n", bytes, cs, mx, G,
+      std::printf("dsmem push   %6d B, cluster %d: %lld cycles / exchange (max over %d CTAs), check %.0f\n", bytes, cs, mx, G,
+                  check[0]);
+      cfg.dynamicSmemBytes = (size_t)bytes;
+      CK(cudaFuncSetAttribute(k_dsmem_pull, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      CK(cudaLaunchKernelEx(&cfg, k_dsmem_pull, iters, bytes, cyc, check));
+      CK(cudaDeviceSynchronize());
+      mx = 0;
+      for (int i = 0; i < G; ++i) mx = cyc[i] > mx ? cyc[i] : mx;
+      std::printf("dsmem pull   %6d B, cluster %d: %lld cycles / exchange (max over %d CTAs), check %.0f\n", bytes, cs, mx, G,
                   check[0]);
     }
   }
