@@ -1,0 +1,86 @@
+"""GPU tests written after round 1's GPU minutes were spent: they have never run on hardware, so they are SKIPPED until
+their first supervised run next round (remove the module-level skip then).  They cover: the committed psvd / pqr golden
+fixtures through the C ABI, the two bra_fetch selectors no other test touches, and the experimental cluster / DSMEM
+Jacobi kernel (BRA_JACOBI_DSMEM=1) against the default kernel."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import lra_oracle as o
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skip(reason="pending first supervised GPU run (written without GPU budget)")]
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _replay(z):
+    drawn = []
+    for t in range(int(z["n_rand"])):
+        drawn.append({k[len(f"rand{t}_"):]: z[k] for k in z.files if k.startswith(f"rand{t}_")})
+    return drawn
+
+
+def _opts_from(z):
+    return {k: (v if not isinstance(v, np.generic) else v.item()) for k, v in z["opts"].tolist()}
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "psvd_*.npz"))))
+def test_golden_psvd_pqr_gpu(ctx, path):
+    import brapprox
+    z = np.load(path, allow_pickle=True)
+    kw = _opts_from(z)
+    F = brapprox.psvdfact(z["A"], brapprox.LRAOptions(**kw), rand=_replay(z), ctx=ctx)
+    s1 = z["S"][0]
+    assert len(F.S) == len(z["S"])
+    assert np.max(np.abs(F.S - z["S"])) <= 1e-10 * s1
+    US, SVt = F.U * F.S, F.Vt * F.S[:, None]
+    sgn = np.sign(np.sum(US * z["US"], axis=0))
+    assert np.max(np.abs(US * sgn - z["US"])) <= 1e-10 * s1
+    assert np.max(np.abs(SVt * sgn[:, None] - z["SVt"])) <= 1e-10 * s1
+    Q = brapprox.pqrfact(z["A"], brapprox.LRAOptions(**kw), trans=str(z["trans"]), rand=_replay(z), ctx=ctx)
+    np.testing.assert_array_equal(Q.p, z["p"])
+    assert np.max(np.abs(Q.R - z["R"])) <= 1e-10 * abs(z["R"][0, 0])
+
+
+def test_fetch_tau_and_sketch_selectors(ctx):
+    """BRA_F_TAU / BRA_F_BSKETCH after an idfact: the LAPACK-layout sketch (R on and above the diagonal, reflectors
+    below) and tau reproduce the oracle's geqp3_adap output on the same Omega."""
+    import brapprox
+    from brapprox import _binding as B
+    A = o.decaying_matrix(300, 260, 30, 9.0, 30, seed=5)
+    rin = o.RandomInputs(2)
+    Fo = o.sketchfact(A, o.LRAOptions(rtol=1e-9, pqrfact_retval="t"), rin, "n")
+    brapprox.idfact(A, brapprox.LRAOptions(rtol=1e-9), rand=rin.drawn, ctx=ctx)
+    inf = ctx.info()
+    order, n = int(inf.orders[inf.rounds - 1]), int(inf.n)
+    steps = int(inf.steps[inf.rounds - 1])
+    Bg = ctx.fetch(B.F_BSKETCH, (order, n))
+    tau = ctx.fetch(B.F_TAU, (steps,))
+    tr = Fo.traces[-1]
+    k = Fo.k
+    Bo = o.apply_sketch("randn", A, order, rin.drawn[-1], "n")
+    p, tau_o, k_o = o.geqp3_adap(Bo, o.LRAOptions(rtol=1e-9))
+    assert k_o == k == int(inf.k)
+    r11 = abs(Bo[0, 0])
+    assert np.max(np.abs(np.triu(Bg[:k, :]) - np.triu(Bo[:k, :]))) <= 1e-12 * r11
+    w = np.abs(np.diag(Bo[:k, :k])) / r11
+    assert np.max(np.abs(tau[:k] - tau_o[:k]) * w) <= 1e-10
+    assert tr.steps == steps
+
+
+def test_dsmem_jacobi_matches_default(ctx, monkeypatch):
+    """The cluster / DSMEM hand-over kernel must give the same singular values and subspaces as the default kernel
+    (rotation order is identical, only the transport differs: results should agree to rounding)."""
+    import brapprox
+    A = o.decaying_matrix(1400, 1200, 420, 11.0, 420, seed=9)
+    ref = brapprox.psvdfact(A, rtol=1e-11, seed=3, ctx=ctx)
+    for cl in ("2", "4", "8"):
+        monkeypatch.setenv("BRA_JACOBI_DSMEM", "1")
+        monkeypatch.setenv("BRA_JACOBI_CLUSTER", cl)
+        F = brapprox.psvdfact(A, rtol=1e-11, seed=3, ctx=ctx)
+        monkeypatch.delenv("BRA_JACOBI_DSMEM")
+        assert len(F.S) == len(ref.S)
+        assert np.max(np.abs(F.S - ref.S)) <= 1e-13 * ref.S[0]
+        assert np.linalg.norm((F.U * F.S) @ F.Vt - (ref.U * ref.S) @ ref.Vt, 2) <= 1e-12 * ref.S[0]
