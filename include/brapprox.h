@@ -285,6 +285,8 @@ int64_t bra_debug_maxdet_swaps(bra_ctx* ctx);
 int bra_debug_jacobi_phases(bra_ctx* ctx, int32_t* out8);
 /* Same, for every CTA of the last QRCP launch: out[cta*8 + phase], ctas <= 160. */
 int bra_debug_qrcp_phases_all(bra_ctx* ctx, int32_t* out, int ctas);
+/* diagnostic: clock64 stamps [ctas][16][16] of the pivot step named by BRA_QRCP_TS_STEP in the last QRCP launch */
+int bra_debug_qrcp_trace(bra_ctx* ctx, int64_t* out, int ctas);
 
 #ifdef __cplusplus
 }

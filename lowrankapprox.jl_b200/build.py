@@ -18,7 +18,7 @@ OUT = os.path.join(HERE, "brapprox", "libbrapprox.so")
 OBJ = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("BRA_EXTRA_NVCC_FLAGS", "").split()
 
 
 def sources():

@@ -462,6 +462,15 @@ int bra_debug_qrcp_phases_all(bra_ctx* ctx, int32_t* out, int ctas) {
   return BRA_OK;
 }
 
+int bra_debug_qrcp_trace(bra_ctx* ctx, int64_t* out, int ctas) {
+  // clock64 stamps of one pivot step of the last QRCP launch (BRA_QRCP_TS_STEP): [ctas][16 warps][16 points]
+  if (!ctx || !out) return -1;
+  if (ctx->scratch3.cap < (size_t)160 * 8 * 4 + (size_t)ctas * 16 * 16 * 8) return BRA_ERR_NOTREADY;
+  BRA_CUDA(cudaMemcpy(out, reinterpret_cast<unsigned char*>(ctx->scratch3.p) + (size_t)160 * 8 * 4,
+                      (size_t)ctas * 16 * 16 * 8, cudaMemcpyDeviceToHost));
+  return BRA_OK;
+}
+
 int bra_chkopts(bra_ctx* ctx, const bra_opts* o) {
   if (!ctx) return -1;
   BRA_CHECK_ARG(o != nullptr, 2, "opts is null");

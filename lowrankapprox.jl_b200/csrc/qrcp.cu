@@ -30,104 +30,12 @@
 //    LAWN-176 arithmetic is vectorised across lanes (lane j <-> j-th column of the warp).
 //  * The rank/rtol termination test stays on the device.
 #include "common.cuh"
+#include <cstdlib>
 #include <type_traits>
 #include "qrcp_common.cuh"
+#include "qrcp_exchange.cuh"
 
 namespace {
-
-constexpr int QR_THREADS = 512;
-constexpr int QR_WARPS = QR_THREADS / 32;
-constexpr int RECH = 4;                        // record header words: tau, beta, physical column, (pad)
-constexpr int MAXG = 160;                      // >= number of SMs
-constexpr uint32_t SPIN_LIMIT = 1u << 22;      // exchange timeout (never hang the box)
-
-struct __align__(16) LL16 {
-  uint32_t lo, s0, hi, s1;
-};
-
-struct __align__(32) LL32 {
-  uint32_t w[8];
-};
-
-struct QrcpParams {
-  double* B;
-  int64_t ldb;
-  int l;
-  int64_t n;
-  int kcap;
-  int nb;           // effective block size = min(opts.nb, kcap)
-  int nopivot;      // 1: plain (unpivoted) Householder QR -- the pivot of step s is the column at position s
-  double atol, rtol;
-  int cpc;          // columns per CTA
-  int csm;          // of those, cached in shared memory
-  int meta_smem;    // vn1/vn2/lpos in shared memory?
-  double* vn1g;
-  double* vn2g;
-  int* lposg;
-  LL16* rec;        // [2][G][l]        candidate columns
-  LL32* inbox;      // [2][G dst][G src] headers
-  uint32_t epoch;
-  int64_t* jpvt;    // n, 1-based, LAPACK layout
-  double* tau;      // kcap
-  double* rdiag;    // kcap
-  int* info;        // k, nsteps, nblocks, status, phase kilo-cycles...
-  int* kbtrace;
-  int kbcap;
-  int* dbg;         // [G][8] per-CTA phase kilo-cycles (diagnostic)
-};
-
-__device__ __forceinline__ void ll_store(LL16* p, uint32_t lo, uint32_t hi, uint32_t stamp) {
-  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(lo), "r"(stamp), "r"(hi),
-               "r"(stamp)
-               : "memory");
-}
-__device__ __forceinline__ void ll_store_d(LL16* p, double x, uint32_t stamp) {
-  ll_store(p, (uint32_t)__double2loint(x), (uint32_t)__double2hiint(x), stamp);
-}
-__device__ __forceinline__ void ll_ld(const LL16* p, uint32_t& lo, uint32_t& s0, uint32_t& hi, uint32_t& s1) {
-  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(lo), "=r"(s0), "=r"(hi), "=r"(s1)
-               : "l"(p)
-               : "memory");
-}
-__device__ __forceinline__ bool ll_load(const LL16* p, uint32_t stamp, uint32_t& lo, uint32_t& hi) {
-  uint32_t s0, s1, spins = 0;
-  do {
-    ll_ld(p, lo, s0, hi, s1);
-    if (s0 == stamp && s1 == stamp) return true;
-  } while (++spins < SPIN_LIMIT);
-  return false;
-}
-
-// header word: (v.lo, v.hi, lp, flag) as four 4-byte payloads, each followed by the step stamp
-__device__ __forceinline__ void ll32_store(LL32* p, double v, int lp, int flag, uint32_t stamp) {
-  asm volatile("st.relaxed.gpu.global.v8.b32 [%0], {%1,%2,%3,%2,%4,%2,%5,%2};" ::"l"(p),
-               "r"((uint32_t)__double2loint(v)), "r"(stamp), "r"((uint32_t)__double2hiint(v)), "r"((uint32_t)lp),
-               "r"((uint32_t)flag)
-               : "memory");
-}
-__device__ __forceinline__ void ll32_ld(const LL32* p, uint32_t (&q)[8]) {
-  asm volatile("ld.relaxed.gpu.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])
-               : "l"(p)
-               : "memory");
-}
-__device__ __forceinline__ bool ll32_load(const LL32* p, uint32_t stamp, double& v, int& lp, int& flag) {
-  uint32_t a, s0, b, s1, c, s2, d, s3, spins = 0;
-  do {
-    asm volatile("ld.relaxed.gpu.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(a), "=r"(s0), "=r"(b), "=r"(s1), "=r"(c), "=r"(s2), "=r"(d), "=r"(s3)
-                 : "l"(p)
-                 : "memory");
-    if (s0 == stamp && s1 == stamp && s2 == stamp && s3 == stamp) {
-      v = __hiloint2double((int)b, (int)a);
-      lp = (int)c;
-      flag = (int)d;
-      return true;
-    }
-  } while (++spins < SPIN_LIMIT);
-  return false;
-}
 
 struct Cand {
   double v;       // downdated norm vn1 (-1: none)
@@ -728,7 +636,7 @@ int bra_qrcp_run(bra_ctx* ctx, double* B, int64_t ldb, int l, int64_t n, int kca
   BRA_CUDA(ctx->lpos.reserve((size_t)n * 4));
   // LL exchange buffers: [candidate columns | header inboxes]; zeroed when (re)allocated or when the
   // 32-bit stamp epoch is about to wrap, otherwise reused across launches with a fresh epoch.
-  const size_t col_bytes = (((size_t)2 * G * (l + RECH) * sizeof(LL16)) + 31) & ~size_t(31);
+  const size_t col_bytes = (((size_t)2 * G * (((l + 1) & ~1) + RECH) * sizeof(LL16)) + 31) & ~size_t(31);
   const size_t inbox_bytes = (size_t)2 * G * G * sizeof(LL32);
   const size_t rec_bytes = col_bytes + inbox_bytes;
   if (ctx->rec.cap < rec_bytes || ctx->rec_zeroed < ctx->rec.cap || ctx->rec_epoch > 0xF0000000u) {
@@ -770,10 +678,33 @@ int bra_qrcp_run(bra_ctx* ctx, double* B, int64_t ldb, int l, int64_t n, int kca
   p.kbcap = kcap + 1;
   BRA_CUDA(ctx->scratch3.reserve((size_t)MAXG * 8 * 4));
   p.dbg = ctx->scratch3.as<int>();
+  p.lds = l;
+  p.fast = 0;
+  p.ts = nullptr;
+  p.ts_step = -1;
+  if (const char* ev = getenv("BRA_QRCP_TS_STEP")) {
+    BRA_CUDA(ctx->scratch3.reserve((size_t)MAXG * 8 * 4 + (size_t)MAXG * QR_WARPS * 16 * 8));
+    p.dbg = ctx->scratch3.as<int>();
+    p.ts = reinterpret_cast<long long*>(reinterpret_cast<unsigned char*>(ctx->scratch3.p) + (size_t)MAXG * 8 * 4);
+    p.ts_step = atoi(ev);
+    BRA_CUDA(cudaMemsetAsync(p.ts, 0, (size_t)MAXG * QR_WARPS * 16 * 8, ctx->stream));
+  }
   ctx->rec_epoch += (uint32_t)l + 8;
 
   cudaError_t e;
-  if (l <= 64) e = launch_qrcp<2>(p, G, smem, ctx->stream);
+  static const bool use_v1 = getenv("BRA_QRCP_V1") != nullptr;
+  // short sketches (l <= 576, <= 120 columns per CTA): the warp-specialised kernel of qrcp_fast.cu
+  const bool aligned = ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && (ldb % 2 == 0);
+  int jw = 0, lds_f = 0, csm_f = 0;
+  size_t smem_f = 0;
+  const bool use_fast = !use_v1 && bra_qrcp_fast_plan(l, cpc, nbe, budget, aligned, &jw, &lds_f, &csm_f, &smem_f);
+  if (use_fast) {
+    p.lds = lds_f;
+    p.csm = csm_f;
+    p.meta_smem = 1;
+    p.fast = 1;
+    e = bra_qrcp_fast_launch(p, G, jw, smem_f, ctx->stream);
+  } else if (l <= 64) e = launch_qrcp<2>(p, G, smem, ctx->stream);
   else if (l <= 96) e = launch_qrcp<3>(p, G, smem, ctx->stream);
   else if (l <= 160) e = launch_qrcp<5>(p, G, smem, ctx->stream);
   else if (l <= 288) e = launch_qrcp<9>(p, G, smem, ctx->stream);

@@ -1,0 +1,870 @@
+// Early-terminating Householder QRCP of a SHORT sketch (l <= 576 rows): the warp-specialised persistent kernel.
+// Semantics: geqp3_adap_main! + LAPACK dlaqps (reference: src/pqr.jl:361-418, src/lapack.jl:117-139), exactly as
+// the general kernel of qrcp.cu (first-maximum pivots, norm hand-over on a swap, LAWN-176 downdate, a flagged column
+// ends the block, rank test at block ends only, pivoting continues to the block end).
+//
+// Why a second kernel: measured on B200 (tools/gpu_qrcp_trace.py, ncu source counters) the pivot step is bound by
+// DEPENDENT-INSTRUCTION latency -- about 8 cycles per instruction per warp, ~1250 instructions per warp and step in the
+// general kernel -- not by bandwidth.  So the critical chain of a step is cut to the bone and everything else runs
+// beside it:
+//   * 15 COMPUTE warps own the columns (lc = warp + 15 j, at most JW = 4 or 8 per warp: straight-line code, no loops).
+//     Fixed row map: lane owns rows (64 c + 2 lane, +1) of every 64-row chunk c, so every slab access is a 128-bit
+//     LDS/STS, v lives in 2 NCH registers per lane and the code is re-dispatched on the number of live chunks
+//     NCH = ceil(l/64) - floor(s/64), which shrinks as the factorization proceeds.
+//       pass 1 (critical, read-only): dots v.a_j -> f_j = tau v.a_j, the pivot-row entry R[s,j] = a_j[s] - f_j, the
+//              LAWN-176 downdate in a division-free form (1/vn1 and (vn1/vn2)^2 are kept per column and refreshed
+//              OFF the chain) and the candidate key vn1^2 temp, which orders like the downdated norm: no square root,
+//              no division on the chain;
+//       pass 2 (hidden behind the header exchange): a_j -= f_j v.  The CTA's candidate column goes first: its owner
+//              warp alone finishes it, runs dlarfg for the next step and publishes the Householder vector.
+//   * 1 COMM warp: merges the 15 warp candidates, pushes one 32-byte header into every CTA's inbox, polls its own
+//     inbox, picks the winner, keeps the dlaqps block bookkeeping, fetches the winner's record into shared memory
+//     (double buffered: it runs ahead of pass 2) and stores the winner column in LAPACK layout.
+//   Two named barriers per step; shared arrays are addressed by 32-bit offsets (no generic pointers in registers).
+#include "common.cuh"
+#include <type_traits>
+#include "qrcp_common.cuh"
+#include "qrcp_exchange.cuh"
+
+namespace {
+
+constexpr int QF_MAXCH = 9;               // 64-row chunks: l <= 576
+constexpr int QF_CW = QR_WARPS - 1;       // compute warps
+constexpr long long QF_NONE = -1;         // "no candidate" key (valid keys are bit patterns of non-negative doubles)
+
+struct QfCtrl {
+  double tau;
+  int stop;       // 0: apply step s and go on; 1: apply step s in full, then exit; 2: exit now; 3: exchange failure
+  int nsteps;
+};
+struct __align__(16) QfSlotA {     // one LDS.128 / STS.128
+  long long key;
+  int lp, ps;
+};
+struct __align__(8) QfSlotB {
+  int lc, flag;
+};
+
+__device__ __forceinline__ void qf_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(QR_THREADS) : "memory"); }
+
+// argmax of (key, lp) over the warp (key: i64, larger wins; ties: smaller lp); returns the winning lane
+__device__ __forceinline__ int warp_argmax_key(long long key, int lp) {
+  const int hi = (int)(key >> 32);
+  const unsigned lo = (unsigned)key;
+  const int mh = __reduce_max_sync(0xffffffffu, hi);
+  const bool c1 = (hi == mh);
+  const unsigned ml = __reduce_max_sync(0xffffffffu, c1 ? lo : 0u);
+  const bool c2 = c1 && (lo == ml);
+  const int mlp = __reduce_min_sync(0xffffffffu, c2 ? lp : 0x7fffffff);
+  return __ffs(__ballot_sync(0xffffffffu, c2 && lp == mlp)) - 1;
+}
+
+#ifdef BRA_QRCP_TRACE
+#define QF_TS(k) if (p.ts && lane == 0 && s == p.ts_step) p.ts[((size_t)cta * QR_WARPS + warp) * 16 + (k)] = clock64();
+#define QF_TICK(i) { long long _t = clock64(); s_tph[i] += _t - tlast; tlast = _t; }
+#else
+#define QF_TS(k)
+#define QF_TICK(i)
+#endif
+
+#define QF_DISPATCH(nchv, FN, ...)                                           \
+  switch (nchv) {                                                            \
+    case 1: FN(std::integral_constant<int, 1>{}, __VA_ARGS__); break;        \
+    case 2: FN(std::integral_constant<int, 2>{}, __VA_ARGS__); break;        \
+    case 3: FN(std::integral_constant<int, 3>{}, __VA_ARGS__); break;        \
+    case 4: FN(std::integral_constant<int, 4>{}, __VA_ARGS__); break;        \
+    case 5: FN(std::integral_constant<int, 5>{}, __VA_ARGS__); break;        \
+    case 6: FN(std::integral_constant<int, 6>{}, __VA_ARGS__); break;        \
+    case 7: FN(std::integral_constant<int, 7>{}, __VA_ARGS__); break;        \
+    case 8: FN(std::integral_constant<int, 8>{}, __VA_ARGS__); break;        \
+    default: FN(std::integral_constant<int, 9>{}, __VA_ARGS__); break;       \
+  }
+
+template <int JW>
+__global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x, cta = blockIdx.x;
+  const int l = p.l;
+  const int lds = p.lds;
+  const int64_t col0 = (int64_t)cta * p.cpc;
+  const int ncols = (int)max((int64_t)0, min((int64_t)p.cpc, p.n - col0));
+  const int csm = min(p.csm, ncols);
+  const int nchtot = (l + 63) >> 6;
+  const int LV = nchtot << 6;
+  const int cpe = (p.cpc + 1) & ~1;
+
+  // ---- shared memory carve-up (every array starts 16-byte aligned; 32-bit byte offsets from the dynamic base) ----
+  const int off_ctrl = 2 * LV * 8;                    // vbuf [2][LV]: Householder vector by ABSOLUTE row, zero padded;
+                                                      //   step s uses buffer s & 1 (the comm warp runs ahead of pass 2)
+  const int off_rd = off_ctrl + 16;                   // rdblk: nb (even) diagonal entries of the current block
+  const int off_sa = off_rd + ((p.nb + 1) & ~1) * 8;  // warp candidates: QfSlotA[16], QfSlotB[16]
+  const int off_sb = off_sa + 16 * 16;
+  const int off_f = off_sb + 16 * 8;                  // fbuf: f_j of the current step                        cpe doubles
+  const int off_st = off_f + cpe * 8;                 // st2: {1/vn1, (vn1/vn2)^2} per column                 cpe double2
+  const int off_sq = off_st + cpe * 16;               // ssq = vn1^2, then sv1 = vn1, then srv2 = 1/vn2       3 cpe doubles
+  const int off_lpos = off_sq + 3 * cpe * 8;          // lpos: logical LAPACK position per column             cpe ints (x4)
+  const int off_cache = off_lpos + ((cpe + 3) & ~3) * 4;   // the slab: csm columns of lds doubles
+#define vbuf reinterpret_cast<double*>(smem_raw)
+#define ctrl reinterpret_cast<QfCtrl*>(smem_raw + off_ctrl)
+#define rdblk reinterpret_cast<double*>(smem_raw + off_rd)
+#define slotA reinterpret_cast<QfSlotA*>(smem_raw + off_sa)
+#define slotB reinterpret_cast<QfSlotB*>(smem_raw + off_sb)
+#define fbuf reinterpret_cast<double*>(smem_raw + off_f)
+#define st2 reinterpret_cast<double2*>(smem_raw + off_st)
+#define ssq reinterpret_cast<double*>(smem_raw + off_sq)
+#define sv1 (ssq + cpe)
+#define srv2 (ssq + 2 * cpe)
+#define lpos reinterpret_cast<int*>(smem_raw + off_lpos)
+#define cache reinterpret_cast<double*>(smem_raw + off_cache)
+  const int recs = lds + RECH;                        // record stride (even: 32-byte aligned row pairs)
+#ifdef BRA_QRCP_TRACE
+  __shared__ long long s_tph[6];                      // per-phase cycle totals (diagnostic)
+  if (tid < 6) s_tph[tid] = 0;
+#endif
+
+  for (int r = tid; r < 2 * LV; r += QR_THREADS) vbuf[r] = 0.0;
+  if (tid == 0) {
+    ctrl->tau = 0.0;
+    ctrl->stop = 0;
+    ctrl->nsteps = 0;
+  }
+
+  // ---- prologue: stage the slab, initial column norms (src/pqr.jl:376-385) ----
+  for (int lc = warp; lc < ncols; lc += QR_WARPS) {
+    const double* g = p.B + (col0 + lc) * p.ldb;
+    double amax = 0.0;
+    for (int r = lane; r < l; r += 32) {
+      double x = g[r];
+      if (lc < csm) cache[(size_t)lc * lds + r] = x;
+      amax = fmax(amax, fabs(x));
+    }
+    if (lc < csm && lane == 0 && lds > l) cache[(size_t)lc * lds + l] = 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    double nrm = 0.0;
+    if (amax > 0.0) {
+      // exact power-of-two scaling: same rounding as the unscaled sum, no overflow/underflow
+      int e = ilogb(amax);
+      double sc = scalbn(1.0, -e);
+      double ss = 0.0;
+      for (int r = lane; r < l; r += 32) {
+        double x = g[r] * sc;
+        ss = fma(x, x, ss);
+      }
+      ss = warp_sum(ss);
+      nrm = scalbn(sqrt(ss), e);
+    }
+    if (lane == 0) {
+      const double rn = nrm != 0.0 ? 1.0 / nrm : 0.0;
+      st2[lc] = make_double2(rn, 1.0);
+      ssq[lc] = nrm * nrm;
+      sv1[lc] = nrm;
+      srv2[lc] = rn;
+      lpos[lc] = (int)(col0 + lc);
+    }
+  }
+  __syncthreads();
+
+  const int lastrk = (int)min((int64_t)l, p.n);
+  int s = 0;                                  // current pivot step (every warp keeps its own copy)
+
+  if (warp == QF_CW) {
+    // =================================== COMM warp ===================================
+    int jblk = 0, cnt = 0, jb = min(p.nb, p.kcap), nblocks = 0, kres = -1;
+    double ptol = 0.0;
+    bool failed = false, prev_block_end = true;     // no flags exist before step 0
+#ifdef BRA_QRCP_TRACE
+    long long tlast = clock64();
+#endif
+    // lane-invariant exchange addresses: my inbox slots (src = lane + 32 i) and my slot in everybody's inbox
+    unsigned pend0 = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+      if (lane + 32 * i < G) pend0 |= 1u << i;
+    const size_t push_stride = (size_t)32 * G;      // LL32 words between destinations lane + 32 i and lane + 32 (i+1)
+
+    // fetch of the winner's record (tau, beta, physical column, v) -> vbuf; the winner CTA also stores the column
+    double tau = 0.0, beta = 0.0;
+    int pw = 0;
+    auto fetch = [&](const int s, const int wcta, const uint32_t stamp) {
+      constexpr int FB = 5;                       // chunks per batch of loads in flight (register budget)
+      const int par = s & 1;
+      const int nch = nchtot - (s >> 6);
+      const LL16* wrec = p.rec + ((size_t)par * G + wcta) * recs;
+      double* vb = vbuf + par * LV;
+      const int rbase = ((s >> 6) << 6) + 2 * lane;
+      uint32_t h[3][4];
+      ll_ld(wrec + 0, h[0][0], h[0][1], h[0][2], h[0][3]);
+      ll_ld(wrec + 1, h[1][0], h[1][1], h[1][2], h[1][3]);
+      ll_ld(wrec + 2, h[2][0], h[2][1], h[2][2], h[2][3]);
+      double* wa = nullptr;
+      bool wsm = false;
+      for (int cb = 0; cb < nch && !failed; cb += FB) {
+        // rows (r, r+1) of a chunk are two adjacent 16-byte LL words: one 32-byte load; rows <= s are not in the record
+        uint32_t q[FB][8];
+        bool need[FB];
+#pragma unroll
+        for (int c = 0; c < FB; ++c) {
+          const int r = rbase + 64 * (cb + c);
+          need[c] = cb + c < nch && r + 1 > s && r < l;
+          if (need[c]) ll32_ld(reinterpret_cast<const LL32*>(wrec + RECH + r), q[c]);
+        }
+        uint32_t spins = 0;
+        while (true) {
+          bool ok = true;
+          if (cb == 0) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+              if (h[i][1] != stamp || h[i][3] != stamp) {
+                ok = false;
+                ll_ld(wrec + i, h[i][0], h[i][1], h[i][2], h[i][3]);
+              }
+          }
+#pragma unroll
+          for (int c = 0; c < FB; ++c) {
+            if (need[c]) {
+              const int r = rbase + 64 * (cb + c);
+              const bool ok0 = (r <= s) || ((q[c][1] ^ stamp) | (q[c][3] ^ stamp)) == 0;
+              const bool ok1 = (r + 1 >= l) || ((q[c][5] ^ stamp) | (q[c][7] ^ stamp)) == 0;
+              if (!(ok0 && ok1)) {
+                ok = false;
+                ll32_ld(reinterpret_cast<const LL32*>(wrec + RECH + r), q[c]);
+              }
+            }
+          }
+          if (__all_sync(0xffffffffu, ok)) break;
+          if (++spins > SPIN_LIMIT) {
+            failed = true;
+            break;
+          }
+        }
+        if (cb == 0) {
+          tau = __hiloint2double((int)h[0][2], (int)h[0][0]);
+          beta = __hiloint2double((int)h[1][2], (int)h[1][0]);
+          pw = (int)h[2][0];
+          if (wcta == cta) {
+            const int wlc = (int)(pw - col0);
+            wsm = wlc < csm;
+            wa = wsm ? cache + (size_t)wlc * lds : p.B + (col0 + wlc) * p.ldb;
+          }
+        }
+        // vbuf by absolute row: 0 below s, 1 at s, v above; winner column: beta at row s, v below (LAPACK layout)
+#pragma unroll
+        for (int c = 0; c < FB; ++c) {
+          const int r = rbase + 64 * (cb + c);
+          if (cb + c < nch && r < l) {
+            double2 v;
+            v.x = r > s ? __hiloint2double((int)q[c][2], (int)q[c][0]) : (r == s ? 1.0 : 0.0);
+            v.y = r + 1 > s ? __hiloint2double((int)q[c][6], (int)q[c][4]) : (r + 1 == s ? 1.0 : 0.0);
+            if (r + 1 >= l) v.y = 0.0;
+            *reinterpret_cast<double2*>(vb + r) = v;
+            if (wa) {
+              if (r >= s) {
+                const double x0 = r == s ? beta : v.x;
+                if (wsm) wa[r] = x0;
+                else __stcg(wa + r, x0);
+              }
+              if (r + 1 >= s && r + 1 < l) {
+                const double x1 = r + 1 == s ? beta : v.y;
+                if (wsm) wa[r + 1] = x1;
+                else __stcg(wa + r + 1, x1);
+              }
+            }
+          }
+        }
+      }
+    };
+
+    qf_bar(2);                                      // candidates for step 0
+    while (true) {
+      QF_TS(0)
+      // ---- merge the warp candidates -> this CTA's candidate for step s ----
+      long long key = QF_NONE;
+      int lp = 0x7fffffff, psx = -1, fl = 0;
+      if (lane < QF_CW) {
+        const QfSlotA a = slotA[lane];
+        key = a.key;
+        lp = a.lp;
+        psx = a.ps;
+        fl = slotB[lane].flag;
+      }
+      const int wl = warp_argmax_key(key, lp);
+      const long long ckey = __shfl_sync(0xffffffffu, key, wl);
+      const int clp = __shfl_sync(0xffffffffu, lp, wl);
+      const int my_ps = __reduce_max_sync(0xffffffffu, psx);     // physical column at logical position s, if owned here
+      const int cflag = prev_block_end ? 0 : (int)__reduce_or_sync(0xffffffffu, (unsigned)fl);
+
+      // ---- publish: one 32-byte header word into every CTA's inbox ----
+      const uint32_t stamp = p.epoch + (uint32_t)s;
+      const int par = s & 1;
+      {
+        LL32* dst = p.inbox + ((size_t)par * G + lane) * G + cta;
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+          if (pend0 & (1u << i)) ll32_store(dst + i * push_stride, __longlong_as_double(ckey), clp, cflag, stamp);
+      }
+      QF_TS(1)
+#ifdef BRA_QRCP_TRACE
+      if (lane == 0) QF_TICK(0)
+#endif
+
+      // ---- gather my inbox (G contiguous 32-byte words), pick the winner ----
+      long long bkey = QF_NONE;
+      int blp = 0x7fffffff, bsrc = -1, bfl = 0;
+      {
+        const LL32* src = p.inbox + ((size_t)par * G + cta) * G + lane;
+        unsigned pend = pend0;
+        uint32_t spins = 0;
+        while (__any_sync(0xffffffffu, pend != 0)) {
+          uint32_t q[5][8];
+#pragma unroll
+          for (int i = 0; i < 5; ++i)
+            if (pend & (1u << i)) ll32_ld(src + 32 * i, q[i]);
+#pragma unroll
+          for (int i = 0; i < 5; ++i)
+            if ((pend & (1u << i)) && ((q[i][1] ^ stamp) | (q[i][3] ^ stamp) | (q[i][5] ^ stamp) | (q[i][7] ^ stamp)) == 0) {
+              pend &= ~(1u << i);
+              const long long k2 = ((long long)q[i][2] << 32) | (long long)q[i][0];
+              const int lp2 = (int)q[i][4];
+              bfl |= (int)q[i][6];
+              if (k2 > bkey || (k2 == bkey && lp2 < blp)) {
+                bkey = k2;
+                blp = lp2;
+                bsrc = lane + 32 * i;
+              }
+            }
+          if (++spins > SPIN_LIMIT) {
+            failed = true;
+            break;
+          }
+        }
+      }
+      const int wl2 = warp_argmax_key(bkey, blp);
+      const int wcta = __shfl_sync(0xffffffffu, bsrc, wl2);
+      const long long gkey = __shfl_sync(0xffffffffu, bkey, wl2);
+      const int lw = __shfl_sync(0xffffffffu, blp, wl2);          // winner's logical position
+      const int gflag = (int)__reduce_or_sync(0xffffffffu, (unsigned)bfl);
+      failed = __any_sync(0xffffffffu, failed) || wcta < 0;
+      QF_TS(2)
+#ifdef BRA_QRCP_TRACE
+      if (lane == 0) QF_TICK(2)
+#endif
+      int stop = failed ? 3 : 0;
+
+      // ---- block bookkeeping for the previous step (needs the gathered flags) ----
+      if (!stop && cnt > 0 && gflag) {
+        // a column was flagged during step s-1: dlaqps ended its block there
+        if (cta == 0 && lane == 0 && nblocks < p.kbcap) p.kbtrace[nblocks] = cnt;
+        ++nblocks;
+        const int jn = jblk + cnt;
+        if (fabs(rdblk[cnt - 1]) <= ptol) {
+          for (int i = 0; i < cnt; ++i)
+            if (fabs(rdblk[i]) <= ptol) {
+              kres = jblk + i;
+              break;
+            }
+        }
+        if (kres >= 0) stop = 2;
+        jblk = jn;
+        cnt = 0;
+        jb = min(p.nb, p.kcap - jblk);
+      }
+      if (stop) {
+        if (lane == 0) {
+          ctrl->stop = stop;
+          ctrl->nsteps = s;
+        }
+        qf_bar(1);
+        break;
+      }
+      if (s == 0) ptol = fmax(p.atol, p.rtol * __longlong_as_double(gkey));   // src/pqr.jl:386-389 (step-0 keys are norms)
+
+      // ---- the winner's Householder vector (already scaled by its owner), tau, beta, physical column ----
+      fetch(s, wcta, stamp);
+      failed = __any_sync(0xffffffffu, failed);
+      if (failed) {
+        if (lane == 0) {
+          ctrl->stop = 3;
+          ctrl->nsteps = s;
+        }
+        qf_bar(1);
+        break;
+      }
+      if (lane == 0) {
+        rdblk[cnt] = beta;
+        // ---- ownership updates ----
+        if (my_ps >= 0 && my_ps != pw) lpos[my_ps - col0] = lw;   // column K moves to pvt
+        if (wcta == cta) {
+          lpos[pw - col0] = s;
+          p.jpvt[s] = (int64_t)pw + 1;
+          p.tau[s] = tau;
+          p.rdiag[s] = beta;
+        }
+      }
+      __syncwarp();
+      // ---- end-of-step bookkeeping, known as soon as beta is (the rank test only looks at the diagonal) ----
+      ++cnt;
+      const bool block_end = (cnt == jb);
+      if (block_end) {
+        // block ends by count; flags raised in this step are irrelevant
+        if (cta == 0 && lane == 0 && nblocks < p.kbcap) p.kbtrace[nblocks] = cnt;
+        ++nblocks;
+        const int jn = jblk + cnt;
+        if (fabs(rdblk[cnt - 1]) <= ptol) {
+          for (int i = 0; i < cnt; ++i)
+            if (fabs(rdblk[i]) <= ptol) {
+              kres = jblk + i;
+              break;
+            }
+        }
+        if (kres < 0) {
+          jblk = jn;
+          cnt = 0;
+          if (jblk >= p.kcap) kres = p.kcap;
+          else jb = min(p.nb, p.kcap - jblk);
+        }
+      }
+      prev_block_end = block_end;
+      stop = kres >= 0 ? 1 : 0;
+      if (lane == 0) {
+        ctrl->tau = tau;
+        ctrl->stop = stop;
+        ctrl->nsteps = s + 1;
+      }
+      QF_TS(3)
+#ifdef BRA_QRCP_TRACE
+      if (lane == 0) QF_TICK(3)
+#endif
+      qf_bar(1);                  // vbuf, tau, lpos are ready: the compute warps run pass 1 of step s
+      if (stop) break;
+      ++s;
+      qf_bar(2);                  // candidates for step s
+    }
+    if (cta == 0 && lane == 0) {
+      p.info[0] = failed ? -1 : kres;
+      p.info[2] = nblocks;
+      p.info[3] = failed ? 1 : 0;
+    }
+  } else {
+    // ================================= COMPUTE warps =================================
+    const int jtot = ncols > warp ? min(JW, (ncols - warp + QF_CW - 1) / QF_CW) : 0;   // this warp's columns lc = warp + 15 j
+    const int jsm = csm > warp ? min(jtot, (csm - warp + QF_CW - 1) / QF_CW) : 0;      // ... of which in shared memory
+    const bool mycol = lane < jtot;                                                     // lane j < jtot <-> column j
+    const int mylc = mycol ? warp + QF_CW * lane : 0;
+#ifdef BRA_QRCP_TRACE
+    long long tlast = clock64();
+#endif
+
+    // warp candidate -> slot
+    auto publish = [&](long long key, int lp, int ps, int flag) {
+      const int wl = warp_argmax_key(key, lp);
+      const int bps = __reduce_max_sync(0xffffffffu, ps);
+      if (lane == wl) {
+        QfSlotA a;
+        a.key = key;
+        a.lp = lp;
+        a.ps = bps;
+        slotA[warp] = a;
+        QfSlotB b;
+        b.lc = key >= 0 ? mylc : -1;
+        b.flag = flag;
+        slotB[warp] = b;
+      }
+    };
+
+    // ---- pass 1 of step s.  Out: live mask (bit j: column j takes part in step s), and for lane j the downdate
+    //      factor temp with dd = "refresh my column's norm state after the candidate is out" ----
+    auto pass1 = [&](auto tag, const int s, const double tau, const bool downdate, const bool want_cand, unsigned& live,
+                     double& temp, bool& dd) {
+      constexpr int NCH = decltype(tag)::value;
+      const int par = s & 1;
+      const int rbase = ((s >> 6) << 6) + 2 * lane;
+      double2 vr[NCH];
+      {
+        const double2* v2 = reinterpret_cast<const double2*>(vbuf + par * LV + rbase);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) vr[c] = v2[32 * c];
+      }
+      // lane j: state of column j
+      const int qpos = mycol ? lpos[mylc] : -1;
+      const double2 stj = st2[mylc];
+      const double sq = ssq[mylc];
+      live = __ballot_sync(0xffffffffu, qpos > s);
+      double myas = 0.0;
+      if (mycol) myas = lane < jsm ? cache[(size_t)mylc * lds + s] : __ldcg(p.B + (col0 + mylc) * p.ldb + s);
+
+      // dots, four columns per packed butterfly; L2-resident columns (the highest j) issue their loads first
+      double fmine = 0.0;
+#pragma unroll
+      for (int b = JW / 4 - 1; b >= 0; --b) {
+        double dot[4];
+#pragma unroll
+        for (int cc = 3; cc >= 0; --cc) {
+          const int j = 4 * b + cc;
+          double d0 = 0.0, d1 = 0.0;
+          if (j < jsm) {                          // warp-uniform
+            const double2* a2 = reinterpret_cast<const double2*>(cache + (size_t)(warp + QF_CW * j) * lds + rbase);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+              double2 x = make_double2(0.0, 0.0);
+              if (c < NCH - 1 || rbase + 64 * c < l) x = a2[32 * c];
+              d0 = fma(x.x, vr[c].x, d0);
+              d1 = fma(x.y, vr[c].y, d1);
+            }
+          } else if (j < jtot) {
+            const double2* a2 = reinterpret_cast<const double2*>(p.B + (col0 + warp + QF_CW * j) * p.ldb + rbase);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+              double2 x = make_double2(0.0, 0.0);
+              if (c < NCH - 1 || rbase + 64 * c < l) x = __ldcg(a2 + 32 * c);
+              d0 = fma(x.x, vr[c].x, d0);
+              d1 = fma(x.y, vr[c].y, d1);
+            }
+          }
+          dot[cc] = d0 + d1;
+        }
+        // packed butterfly: four sums for 6 exchanges; each keeps the association of the plain xor butterfly
+        const bool h16 = lane & 16, h8 = lane & 8;
+        const double wa = (h16 ? dot[2] : dot[0]) + __shfl_xor_sync(0xffffffffu, h16 ? dot[0] : dot[2], 16);
+        const double wb = (h16 ? dot[3] : dot[1]) + __shfl_xor_sync(0xffffffffu, h16 ? dot[1] : dot[3], 16);
+        double w = (h8 ? wb : wa) + __shfl_xor_sync(0xffffffffu, h8 ? wa : wb, 8);
+        w += __shfl_xor_sync(0xffffffffu, w, 4);
+        w += __shfl_xor_sync(0xffffffffu, w, 2);
+        w += __shfl_xor_sync(0xffffffffu, w, 1);
+        // the sum of column 4b + q sits in lanes 8q..8q+7: lane 8q stores f, lane j = 4b + q picks it up
+        const double f = tau * w;
+        const int jq = 4 * b + (lane >> 3);
+        if ((lane & 7) == 0 && ((live >> jq) & 1)) fbuf[warp + QF_CW * jq] = f;
+        const double fm = __shfl_sync(0xffffffffu, f, (lane & 3) << 3);
+        if ((lane >> 2) == b) fmine = fm;
+      }
+
+      // LAWN-176 downdate (dlaqps step 8), one column per lane, division-free on the chain:
+      //   t = |r| / vn1, temp = max(0, (1+t)(1-t)), temp2 = temp (vn1/vn2)^2; flagged iff temp2 <= tol3z,
+      //   else vn1 *= sqrt(temp).  The candidate key vn1^2 temp orders like the downdated norm.
+      long long key = QF_NONE;
+      int lp = 0x7fffffff, ps = -1;
+      bool flagged = false;
+      temp = 1.0;
+      dd = false;
+      if (qpos > s) {
+        lp = qpos;
+        if (qpos == s + 1) ps = (int)(col0 + mylc);
+        if (p.nopivot) {
+          key = qpos == s + 1 ? __double_as_longlong(1.0) : QF_NONE;
+        } else if (downdate && sq != 0.0) {
+          const double t = fabs(myas - fmine) * stj.x;
+          temp = fmax(0.0, (1.0 + t) * (1.0 - t));
+          flagged = temp * stj.y <= TOL3Z;
+          dd = !flagged;
+          key = __double_as_longlong(sq * temp);
+        } else {
+          key = __double_as_longlong(sq);
+        }
+      }
+      unsigned fmk = __ballot_sync(0xffffffffu, flagged);
+      const int wflag = fmk != 0;
+      while (fmk) {
+        // flagged: dlaqps ends the block and recomputes the norm from rows s+1..l-1 of the UPDATED column, so this
+        // column gets its pass 2 right here (f is cleared: the regular pass 2 skips it)
+        const int fl = __ffs(fmk) - 1;
+        fmk &= fmk - 1;
+        const int lc = warp + QF_CW * fl;
+        __syncwarp();
+        const double f = fbuf[lc];
+        const double* vb = vbuf + par * LV;
+        double ss2 = 0.0;
+        if (fl < jsm) {
+          double* a = cache + (size_t)lc * lds;
+          for (int r = s + lane; r < l; r += 32) {
+            const double x = fma(-f, vb[r], a[r]);
+            a[r] = x;
+            if (r > s) ss2 = fma(x, x, ss2);
+          }
+        } else {
+          double* a = p.B + (col0 + lc) * p.ldb;
+          for (int r = s + lane; r < l; r += 32) {
+            const double x = fma(-f, vb[r], __ldcg(a + r));
+            __stcg(a + r, x);
+            if (r > s) ss2 = fma(x, x, ss2);
+          }
+        }
+        ss2 = warp_sum(ss2);
+        __syncwarp();
+        const double nn = sqrt(ss2);
+        if (lane == fl) {
+          const double rn = nn != 0.0 ? 1.0 / nn : 0.0;
+          key = __double_as_longlong(nn * nn);
+          st2[lc] = make_double2(rn, 1.0);
+          ssq[lc] = nn * nn;
+          sv1[lc] = nn;
+          srv2[lc] = rn;
+          fbuf[lc] = 0.0;
+        }
+      }
+      if (want_cand) publish(key, lp, ps, wflag);
+    };
+
+    // refresh of lane j's norm state after a plain downdate (OFF the candidate chain)
+    auto refresh = [&](const double temp) {
+      const double v1n = sv1[mylc] * sqrt(temp);
+      const double qn = v1n * srv2[mylc];
+      sv1[mylc] = v1n;
+      ssq[mylc] = v1n * v1n;
+      st2[mylc] = make_double2(v1n != 0.0 ? 1.0 / v1n : 0.0, qn * qn);
+    };
+
+    // ---- candidate column: finish step sp on it (if sp >= 0), then dlarfg for step sp+1 -> this CTA's record ----
+    auto cand_dlarfg = [&](auto tag, const int sp, const int cand_lc) {
+      constexpr int NCH = decltype(tag)::value;
+      const int sn = sp + 1;
+      const uint32_t stamp = p.epoch + (uint32_t)sn;
+      LL16* myrec = p.rec + ((size_t)(sn & 1) * G + cta) * recs + RECH;
+      const bool insm = cand_lc < csm;
+      double* a = insm ? cache + (size_t)cand_lc * lds : p.B + (col0 + cand_lc) * p.ldb;
+      double f = 0.0;
+      if (sp >= 0) {
+        f = fbuf[cand_lc];
+        __syncwarp();
+        if (lane == 0) fbuf[cand_lc] = 0.0;
+      }
+      const int rb = ((sp >= 0 ? sp : 0) >> 6) << 6;
+      const int rbase = rb + 2 * lane;
+      const double* vb = vbuf + (sp & 1) * LV;
+      double ss = 0.0, al = 0.0;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int r = rbase + 64 * c;
+        if (c < NCH - 1 || r < l) {
+          double2 x = insm ? *reinterpret_cast<const double2*>(a + r) : __ldcg(reinterpret_cast<const double2*>(a + r));
+          if (f != 0.0) {
+            const double2 v = *reinterpret_cast<const double2*>(vb + r);
+            x.x = fma(-f, v.x, x.x);
+            x.y = fma(-f, v.y, x.y);
+            if (insm) *reinterpret_cast<double2*>(a + r) = x;
+            else __stcg(reinterpret_cast<double2*>(a + r), x);
+          }
+          if (r == sn) al = x.x;
+          if (r + 1 == sn) al = x.y;
+          if (r > sn) ss = fma(x.x, x.x, ss);
+          if (r + 1 > sn) ss = fma(x.y, x.y, ss);
+        }
+      }
+      if (sn >= l) return;
+      // row sn sits in exactly one lane
+      const double alpha = __shfl_sync(0xffffffffu, al, ((sn - rb) & 63) >> 1);
+      ss = warp_sum(ss);
+      double beta, tau, scale;
+      if (sn >= l - 1 || ss == 0.0) {
+        beta = alpha;
+        tau = 0.0;
+        scale = 0.0;        // v = e_1
+      } else {
+        beta = -copysign(sqrt(fma(alpha, alpha, ss)), alpha);
+        tau = (beta - alpha) / beta;
+        scale = 1.0 / (alpha - beta);
+      }
+      __syncwarp();
+      // second sweep over the (just updated) column: scaled entries into the record
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int r = rbase + 64 * c;
+        if (r + 1 > sn && (c < NCH - 1 || r < l)) {
+          const double2 x = insm ? *reinterpret_cast<const double2*>(a + r) : __ldcg(reinterpret_cast<const double2*>(a + r));
+          if (r > sn) ll_store_d(myrec + r, x.x * scale, stamp);
+          if (r + 1 < l) ll_store_d(myrec + r + 1, x.y * scale, stamp);
+        }
+      }
+      if (lane == 0) {
+        ll_store_d(myrec - RECH + 0, tau, stamp);
+        ll_store_d(myrec - RECH + 1, beta, stamp);
+        ll_store(myrec - RECH + 2, (uint32_t)(col0 + cand_lc), 0u, stamp);
+      }
+    };
+
+    // ---- pass 2 of step sp: a_j -= f_j v on every live column that still carries a non-zero f ----
+    auto pass2 = [&](auto tag, const int sp, const unsigned live) {
+      constexpr int NCH = decltype(tag)::value;
+      const int rbase = ((sp >> 6) << 6) + 2 * lane;
+      double2 vr[NCH];
+      {
+        const double2* v2 = reinterpret_cast<const double2*>(vbuf + (sp & 1) * LV + rbase);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) vr[c] = v2[32 * c];
+      }
+      double fj[JW];
+#pragma unroll
+      for (int j = 0; j < JW; ++j) fj[j] = ((live >> j) & 1) ? fbuf[warp + QF_CW * j] : 0.0;
+#pragma unroll
+      for (int j = JW - 1; j >= 0; --j) {
+        const double f = fj[j];
+        if (f == 0.0) continue;               // warp-uniform: dead, flagged (done in pass 1) or the candidate (done)
+        if (j < jsm) {
+          double2* a2 = reinterpret_cast<double2*>(cache + (size_t)(warp + QF_CW * j) * lds + rbase);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            if (c < NCH - 1 || rbase + 64 * c < l) {
+              double2 x = a2[32 * c];
+              x.x = fma(-f, vr[c].x, x.x);
+              x.y = fma(-f, vr[c].y, x.y);
+              a2[32 * c] = x;
+            }
+          }
+        } else {
+          double2* a2 = reinterpret_cast<double2*>(p.B + (col0 + warp + QF_CW * j) * p.ldb + rbase);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            if (c < NCH - 1 || rbase + 64 * c < l) {
+              double2 x = __ldcg(a2 + 32 * c);
+              x.x = fma(-f, vr[c].x, x.x);
+              x.y = fma(-f, vr[c].y, x.y);
+              __stcg(a2 + 32 * c, x);
+            }
+          }
+        }
+      }
+    };
+
+    // candidates for step 0: the initial norms themselves (step-0 keys are norms, later keys squared norms: keys are
+    // only ever compared within one step)
+    {
+      long long key = QF_NONE;
+      int lp = 0x7fffffff, ps = -1;
+      if (mycol) {
+        lp = lpos[mylc];
+        key = p.nopivot ? (lp == 0 ? __double_as_longlong(1.0) : QF_NONE) : __double_as_longlong(sv1[mylc]);
+        if (lp == 0) ps = (int)(col0 + mylc);
+      }
+      publish(key, lp, ps, 0);
+    }
+    qf_bar(2);
+
+    unsigned live = 0;
+    double temp = 1.0;
+    bool dd = false, pend2 = false;
+    while (true) {
+      QF_TS(4)
+      // ---- am I the owner of this CTA's candidate for step s?  (my candidate beats the 14 others) ----
+      {
+        const QfSlotA mine = slotA[warp];
+        const int cand_lc = slotB[warp].lc;
+        bool better = false;
+        if (lane < QF_CW && lane != warp) {
+          const QfSlotA o = slotA[lane];
+          better = (o.key > mine.key) || (o.key == mine.key && o.lp < mine.lp);
+        }
+        const bool owner = cand_lc >= 0 && !__any_sync(0xffffffffu, better);
+        const int sp = s - 1;
+        const int nchv = nchtot - ((sp >= 0 ? sp : 0) >> 6);
+        if (owner) { QF_DISPATCH(nchv, cand_dlarfg, sp, cand_lc) }
+        QF_TS(5)
+        if (dd) refresh(temp);
+        if (pend2) { QF_DISPATCH(nchv, pass2, sp, live) }
+        pend2 = false;
+      }
+      QF_TS(6)
+#ifdef BRA_QRCP_TRACE
+      if (warp == 0 && lane == 0) QF_TICK(1)
+#endif
+      qf_bar(1);                  // the comm warp has fetched step s: vbuf, tau, lpos
+      const int stop = ctrl->stop;
+      if (stop >= 2) break;
+      const double tau = ctrl->tau;
+      QF_TS(7)
+      const bool downdate = (s < lastrk - 1) && !p.nopivot;      // no pivoting: the norms are never looked at
+      {
+        const int nchv = nchtot - (s >> 6);
+        QF_DISPATCH(nchv, pass1, s, tau, downdate, stop == 0, live, temp, dd)
+      }
+      pend2 = true;
+      QF_TS(8)
+#ifdef BRA_QRCP_TRACE
+      if (warp == 0 && lane == 0) QF_TICK(4)
+#endif
+      if (stop == 1) {
+        // the reflector of the last executed step is applied in full (B keeps every update to the block end)
+        const int nchv = nchtot - (s >> 6);
+        QF_DISPATCH(nchv, pass2, s, live)
+        break;
+      }
+      ++s;
+      qf_bar(2);                  // candidates for step s are published
+    }
+  }
+
+  // ---- epilogue: write the cached slab back, finish jpvt, report ----
+  __syncthreads();
+  const int nsteps = ctrl->nsteps;     // pivoted columns
+  for (int lc = warp; lc < csm; lc += QR_WARPS) {
+    double* g = p.B + (col0 + lc) * p.ldb;
+    const double* d = cache + (size_t)lc * lds;
+    for (int r = lane; r < l; r += 32) g[r] = d[r];
+  }
+  for (int lc = tid; lc < ncols; lc += QR_THREADS) {
+    int lp = lpos[lc];
+    if (lp >= nsteps) p.jpvt[lp] = col0 + lc + 1;
+  }
+  if (cta == 0 && tid == 0) {
+    p.info[1] = nsteps;
+#ifdef BRA_QRCP_TRACE
+    for (int i = 0; i < 5; ++i) p.info[4 + i] = (int)(s_tph[i] >> 10);   // kilo-cycles per phase
+#else
+    for (int i = 0; i < 5; ++i) p.info[4 + i] = 0;
+#endif
+  }
+#ifdef BRA_QRCP_TRACE
+  if (tid == 0 && p.dbg)
+    for (int i = 0; i < 5; ++i) p.dbg[cta * 8 + i] = (int)(s_tph[i] >> 10);
+#endif
+#undef vbuf
+#undef ctrl
+#undef rdblk
+#undef slotA
+#undef slotB
+#undef fbuf
+#undef st2
+#undef ssq
+#undef sv1
+#undef srv2
+#undef lpos
+#undef cache
+}
+
+size_t fast_fixed_bytes(int l, int cpc, int nbe) {
+  const int LV = ((l + 63) >> 6) << 6;
+  const int cpe = (cpc + 1) & ~1;
+  return (size_t)2 * LV * 8 + 16 + (size_t)((nbe + 1) & ~1) * 8 + 16 * 16 + 16 * 8 + (size_t)cpe * 8 * 6 +
+         (size_t)((cpe + 3) & ~3) * 4 + 64;
+}
+
+}  // namespace
+
+// Can the fast kernel take this shape?  Fills the column-per-warp variant, the slab stride, the number of columns that
+// fit in shared memory and the dynamic shared-memory size.
+bool bra_qrcp_fast_plan(int l, int cpc, int nbe, size_t budget, bool aligned, int* jw, int* lds, int* csm, size_t* smem) {
+  if (l > 64 * QF_MAXCH || cpc > QF_CW * 8) return false;
+  const int ld = (l + 1) & ~1;
+  const size_t fixed = fast_fixed_bytes(l, cpc, nbe);
+  if (fixed + (size_t)ld * 8 > budget) return false;
+  int c = (int)((budget - fixed) / ((size_t)ld * 8));
+  if (c > cpc) c = cpc;
+  if (c < cpc && !aligned) return false;      // L2-resident columns need 16-byte aligned 128-bit accesses
+  *jw = cpc <= QF_CW * 4 ? 4 : 8;
+  *lds = ld;
+  *csm = c;
+  *smem = fixed + (size_t)c * ld * 8;
+  return true;
+}
+
+cudaError_t bra_qrcp_fast_launch(const QrcpParams& p, int G, int jw, size_t smem, cudaStream_t st) {
+  void* args[] = {(void*)&p};
+  if (jw == 4) {
+    cudaError_t e = cudaFuncSetAttribute(qrcp_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaLaunchCooperativeKernel((void*)qrcp_fast_kernel<4>, dim3(G), dim3(QR_THREADS), args, smem, st);
+  }
+  cudaError_t e = cudaFuncSetAttribute(qrcp_fast_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaLaunchCooperativeKernel((void*)qrcp_fast_kernel<8>, dim3(G), dim3(QR_THREADS), args, smem, st);
+}

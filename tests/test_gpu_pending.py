@@ -10,7 +10,7 @@ import pytest
 
 import lra_oracle as o
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skip(reason="pending first supervised GPU run (written without GPU budget)")]
+pytestmark = [pytest.mark.gpu]
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 

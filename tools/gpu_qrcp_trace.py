@@ -1,0 +1,27 @@
+"""Timeline of ONE pivot step of the persistent QRCP kernel (diagnostic): clock64 stamps per warp and CTA.
+   BRA_QRCP_TS_STEP=<step> python tools/gpu_qrcp_trace.py l n rank"""
+import ctypes as C, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "lowrankapprox.jl_b200"))
+import numpy as np
+import brapprox
+l, n, rank = (int(a) for a in sys.argv[1:4])
+ctx = brapprox.Context(0)
+B = np.asfortranarray(np.random.default_rng(0).standard_normal((l, n)))
+for rep in range(2):
+    _, _, _, k, tr = brapprox.geqp3_adap(B, rank=rank, rtol=0.0, ctx=ctx)
+G = 148
+out = (C.c_int64 * (G * 16 * 16))()
+brapprox.lib.bra_debug_qrcp_trace.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]
+rc = brapprox.lib.bra_debug_qrcp_trace(ctx.handle, out, G)
+t = np.array(out[:], dtype=np.int64).reshape(G, 16, 16)
+names = {0: "comm: step top (after bar2)", 1: "comm: header pushed", 2: "comm: winner known", 3: "comm: fetched (-> bar1)",
+         4: "cmp: top (after bar2)", 5: "cmp: owner dlarfg done", 6: "cmp: pass2 done (-> bar1)", 7: "cmp: after bar1", 8: "cmp: pass1+publish done"}
+print("rc", rc, "step", os.environ.get("BRA_QRCP_TS_STEP"), "l", l, "n", n, "steps", tr["steps"])
+for c in (0, 73, 140):
+    base = t[c, 15, 0]
+    print("CTA", c, "stamps relative to the comm warp's step top; compute warps 0..14")
+    for k_, nm in names.items():
+        row = t[c, :, k_]
+        if k_ < 4: print(f"  {nm:30s} {row[15] - base:6d}")
+        else: print(f"  {nm:30s}", " ".join(f"{(v - base) if v else -1:6d}" for v in row[:15]))
