@@ -14,8 +14,8 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "brapprox", "libbrapprox.so")
-OBJ = os.path.join(HERE, "build")
+OUT = os.environ.get("BRA_OUT") or os.path.join(HERE, "brapprox", "libbrapprox.so")
+OBJ = os.environ.get("BRA_OBJ") or os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("BRA_EXTRA_NVCC_FLAGS", "").split()

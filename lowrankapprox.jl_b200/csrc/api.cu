@@ -610,7 +610,10 @@ int bra_geqp3_adap_f64(bra_ctx* ctx, int64_t l, int64_t n, double* B, int64_t ld
   if (kcap > 0) {
     BRA_CUDA(ctx->B.reserve((size_t)l * n * 8));
     BRA_CUDA(copy2d(ctx, ctx->B.p, l, B, ldb, l, n));
-    rc = bra_qrcp_run(ctx, ctx->B.as<double>(), l, (int)l, n, (int)kcap, (int)opts->nb, opts->atol, opts->rtol, &q);
+    {
+      ProfScope ps(ctx, BRA_PROF_QRCP);
+      rc = bra_qrcp_run(ctx, ctx->B.as<double>(), l, (int)l, n, (int)kcap, (int)opts->nb, opts->atol, opts->rtol, &q);
+    }
     if (rc) return rc;
     BRA_CUDA(ctx->B2.reserve((size_t)l * n * 8));
     rc = bra_permute_cols(ctx, ctx->B.as<double>(), l, ctx->B2.as<double>(), l, l, n, ctx->jpvt.as<int64_t>());

@@ -637,7 +637,7 @@ int bra_qrcp_run(bra_ctx* ctx, double* B, int64_t ldb, int l, int64_t n, int kca
   // LL exchange buffers: [candidate columns | header inboxes]; zeroed when (re)allocated or when the
   // 32-bit stamp epoch is about to wrap, otherwise reused across launches with a fresh epoch.
   const size_t col_bytes = (((size_t)2 * G * (((l + 1) & ~1) + RECH) * sizeof(LL16)) + 31) & ~size_t(31);
-  const size_t inbox_bytes = (size_t)2 * G * G * sizeof(LL32);
+  const size_t inbox_bytes = (size_t)2 * MAXG * MAXG * sizeof(LL32);   // the fast kernel pads the inbox rows to MAXG
   const size_t rec_bytes = col_bytes + inbox_bytes;
   if (ctx->rec.cap < rec_bytes || ctx->rec_zeroed < ctx->rec.cap || ctx->rec_epoch > 0xF0000000u) {
     BRA_CUDA(ctx->rec.reserve(rec_bytes));

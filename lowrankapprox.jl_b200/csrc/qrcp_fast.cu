@@ -34,8 +34,12 @@ constexpr long long QF_NONE = -1;         // "no candidate" key (valid keys are 
 
 struct QfCtrl {
   double tau;
-  int stop;       // 0: apply step s and go on; 1: apply step s in full, then exit; 2: exit now; 3: exchange failure
+  int stop;       // after the fetch: 0: apply step s and go on; 1: apply step s in full, then exit
   int nsteps;
+  int pre;        // before the fetch: 0: fetch the record of CTA wcta; 2: exit now (rank found); 3: exchange failure
+  int wcta;
+  int fail;       // a fetching warp timed out
+  int pad;
 };
 struct __align__(16) QfSlotA {     // one LDS.128 / STS.128
   long long key;
@@ -97,7 +101,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
   // ---- shared memory carve-up (every array starts 16-byte aligned; 32-bit byte offsets from the dynamic base) ----
   const int off_ctrl = 2 * LV * 8;                    // vbuf [2][LV]: Householder vector by ABSOLUTE row, zero padded;
                                                       //   step s uses buffer s & 1 (the comm warp runs ahead of pass 2)
-  const int off_rd = off_ctrl + 16;                   // rdblk: nb (even) diagonal entries of the current block
+  const int off_rd = off_ctrl + 32;                   // rdblk: nb (even) diagonal entries of the current block
   const int off_sa = off_rd + ((p.nb + 1) & ~1) * 8;  // warp candidates: QfSlotA[16], QfSlotB[16]
   const int off_sb = off_sa + 16 * 16;
   const int off_f = off_sb + 16 * 8;                  // fbuf: f_j of the current step                        cpe doubles
@@ -128,6 +132,9 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
     ctrl->tau = 0.0;
     ctrl->stop = 0;
     ctrl->nsteps = 0;
+    ctrl->pre = 0;
+    ctrl->wcta = 0;
+    ctrl->fail = 0;
   }
 
   // ---- prologue: stage the slab, initial column norms (src/pqr.jl:376-385) ----
@@ -166,6 +173,69 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
   }
   __syncthreads();
 
+  // ---- fetch of one 64-row chunk of the winner's record (v already scaled by its owner) into vbuf, by absolute row:
+  //      0 below s, 1 at s, v above.  In the winner CTA the same warp stores the chunk of the pivot column in LAPACK
+  //      layout (beta at row s, v below).  Every warp takes one chunk: the record is fetched in ONE L2 round trip. ----
+  auto fetch_chunk = [&](const int s, const int wcta, const int c) {
+    const int par = s & 1;
+    const uint32_t stamp = p.epoch + (uint32_t)s;
+    const LL16* wrec = p.rec + ((size_t)par * G + wcta) * recs;
+    const int r = ((s >> 6) << 6) + 64 * c + 2 * lane;
+    const bool need = r + 1 > s && r < l;
+    const bool isw = wcta == cta;
+    uint32_t q[8], hb[4], hp[4];
+    if (need) ll32_ld(reinterpret_cast<const LL32*>(wrec + RECH + r), q);
+    if (isw) {
+      ll_ld(wrec + 1, hb[0], hb[1], hb[2], hb[3]);
+      ll_ld(wrec + 2, hp[0], hp[1], hp[2], hp[3]);
+    }
+    uint32_t spins = 0;
+    while (true) {
+      bool ok = true;
+      if (need) {
+        const bool ok0 = (r <= s) || ((q[1] ^ stamp) | (q[3] ^ stamp)) == 0;
+        const bool ok1 = (r + 1 >= l) || ((q[5] ^ stamp) | (q[7] ^ stamp)) == 0;
+        if (!(ok0 && ok1)) {
+          ok = false;
+          ll32_ld(reinterpret_cast<const LL32*>(wrec + RECH + r), q);
+        }
+      }
+      if (isw && (((hb[1] ^ stamp) | (hb[3] ^ stamp) | (hp[1] ^ stamp) | (hp[3] ^ stamp)) != 0)) {
+        ok = false;
+        ll_ld(wrec + 1, hb[0], hb[1], hb[2], hb[3]);
+        ll_ld(wrec + 2, hp[0], hp[1], hp[2], hp[3]);
+      }
+      if (__all_sync(0xffffffffu, ok)) break;
+      if (++spins > SPIN_LIMIT) {
+        if (lane == 0) ctrl->fail = 1;
+        return;
+      }
+    }
+    if (r < l) {
+      double2 v;
+      v.x = r > s ? __hiloint2double((int)q[2], (int)q[0]) : (r == s ? 1.0 : 0.0);
+      v.y = r + 1 > s ? __hiloint2double((int)q[6], (int)q[4]) : (r + 1 == s ? 1.0 : 0.0);
+      if (r + 1 >= l) v.y = 0.0;
+      *reinterpret_cast<double2*>(vbuf + par * LV + r) = v;
+      if (isw) {
+        const double beta = __hiloint2double((int)hb[2], (int)hb[0]);
+        const int wlc = (int)((int)hp[0] - col0);
+        const bool wsm = wlc < csm;
+        double* wa = wsm ? cache + (size_t)wlc * lds : p.B + (col0 + wlc) * p.ldb;
+        if (r >= s) {
+          const double x0 = r == s ? beta : v.x;
+          if (wsm) wa[r] = x0;
+          else __stcg(wa + r, x0);
+        }
+        if (r + 1 >= s && r + 1 < l) {
+          const double x1 = r + 1 == s ? beta : v.y;
+          if (wsm) wa[r + 1] = x1;
+          else __stcg(wa + r + 1, x1);
+        }
+      }
+    }
+  };
+
   const int lastrk = (int)min((int64_t)l, p.n);
   int s = 0;                                  // current pivot step (every warp keeps its own copy)
 
@@ -177,104 +247,13 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
 #ifdef BRA_QRCP_TRACE
     long long tlast = clock64();
 #endif
-    // lane-invariant exchange addresses: my inbox slots (src = lane + 32 i) and my slot in everybody's inbox
-    unsigned pend0 = 0;
+    // the inbox rows are padded to MAXG words, so the five words of a lane (CTAs lane + 32 i) sit at compile-time
+    // offsets from one base address; lanes whose CTA does not exist alias a valid slot and ignore it
+    bool have[5];
 #pragma unroll
-    for (int i = 0; i < 5; ++i)
-      if (lane + 32 * i < G) pend0 |= 1u << i;
-    const size_t push_stride = (size_t)32 * G;      // LL32 words between destinations lane + 32 i and lane + 32 (i+1)
-
-    // fetch of the winner's record (tau, beta, physical column, v) -> vbuf; the winner CTA also stores the column
-    double tau = 0.0, beta = 0.0;
-    int pw = 0;
-    auto fetch = [&](const int s, const int wcta, const uint32_t stamp) {
-      constexpr int FB = 5;                       // chunks per batch of loads in flight (register budget)
-      const int par = s & 1;
-      const int nch = nchtot - (s >> 6);
-      const LL16* wrec = p.rec + ((size_t)par * G + wcta) * recs;
-      double* vb = vbuf + par * LV;
-      const int rbase = ((s >> 6) << 6) + 2 * lane;
-      uint32_t h[3][4];
-      ll_ld(wrec + 0, h[0][0], h[0][1], h[0][2], h[0][3]);
-      ll_ld(wrec + 1, h[1][0], h[1][1], h[1][2], h[1][3]);
-      ll_ld(wrec + 2, h[2][0], h[2][1], h[2][2], h[2][3]);
-      double* wa = nullptr;
-      bool wsm = false;
-      for (int cb = 0; cb < nch && !failed; cb += FB) {
-        // rows (r, r+1) of a chunk are two adjacent 16-byte LL words: one 32-byte load; rows <= s are not in the record
-        uint32_t q[FB][8];
-        bool need[FB];
-#pragma unroll
-        for (int c = 0; c < FB; ++c) {
-          const int r = rbase + 64 * (cb + c);
-          need[c] = cb + c < nch && r + 1 > s && r < l;
-          if (need[c]) ll32_ld(reinterpret_cast<const LL32*>(wrec + RECH + r), q[c]);
-        }
-        uint32_t spins = 0;
-        while (true) {
-          bool ok = true;
-          if (cb == 0) {
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-              if (h[i][1] != stamp || h[i][3] != stamp) {
-                ok = false;
-                ll_ld(wrec + i, h[i][0], h[i][1], h[i][2], h[i][3]);
-              }
-          }
-#pragma unroll
-          for (int c = 0; c < FB; ++c) {
-            if (need[c]) {
-              const int r = rbase + 64 * (cb + c);
-              const bool ok0 = (r <= s) || ((q[c][1] ^ stamp) | (q[c][3] ^ stamp)) == 0;
-              const bool ok1 = (r + 1 >= l) || ((q[c][5] ^ stamp) | (q[c][7] ^ stamp)) == 0;
-              if (!(ok0 && ok1)) {
-                ok = false;
-                ll32_ld(reinterpret_cast<const LL32*>(wrec + RECH + r), q[c]);
-              }
-            }
-          }
-          if (__all_sync(0xffffffffu, ok)) break;
-          if (++spins > SPIN_LIMIT) {
-            failed = true;
-            break;
-          }
-        }
-        if (cb == 0) {
-          tau = __hiloint2double((int)h[0][2], (int)h[0][0]);
-          beta = __hiloint2double((int)h[1][2], (int)h[1][0]);
-          pw = (int)h[2][0];
-          if (wcta == cta) {
-            const int wlc = (int)(pw - col0);
-            wsm = wlc < csm;
-            wa = wsm ? cache + (size_t)wlc * lds : p.B + (col0 + wlc) * p.ldb;
-          }
-        }
-        // vbuf by absolute row: 0 below s, 1 at s, v above; winner column: beta at row s, v below (LAPACK layout)
-#pragma unroll
-        for (int c = 0; c < FB; ++c) {
-          const int r = rbase + 64 * (cb + c);
-          if (cb + c < nch && r < l) {
-            double2 v;
-            v.x = r > s ? __hiloint2double((int)q[c][2], (int)q[c][0]) : (r == s ? 1.0 : 0.0);
-            v.y = r + 1 > s ? __hiloint2double((int)q[c][6], (int)q[c][4]) : (r + 1 == s ? 1.0 : 0.0);
-            if (r + 1 >= l) v.y = 0.0;
-            *reinterpret_cast<double2*>(vb + r) = v;
-            if (wa) {
-              if (r >= s) {
-                const double x0 = r == s ? beta : v.x;
-                if (wsm) wa[r] = x0;
-                else __stcg(wa + r, x0);
-              }
-              if (r + 1 >= s && r + 1 < l) {
-                const double x1 = r + 1 == s ? beta : v.y;
-                if (wsm) wa[r + 1] = x1;
-                else __stcg(wa + r + 1, x1);
-              }
-            }
-          }
-        }
-      }
-    };
+    for (int i = 0; i < 5; ++i) have[i] = lane + 32 * i < G;
+    constexpr size_t PUSH_STRIDE = (size_t)32 * MAXG;      // LL32 words between destinations lane + 32 i and lane + 32 (i+1)
+    constexpr size_t PAR_STRIDE = (size_t)MAXG * MAXG;
 
     qf_bar(2);                                      // candidates for step 0
     while (true) {
@@ -293,50 +272,53 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
       const long long ckey = __shfl_sync(0xffffffffu, key, wl);
       const int clp = __shfl_sync(0xffffffffu, lp, wl);
       const int my_ps = __reduce_max_sync(0xffffffffu, psx);     // physical column at logical position s, if owned here
-      const int cflag = prev_block_end ? 0 : (int)__reduce_or_sync(0xffffffffu, (unsigned)fl);
+      const int cflag = prev_block_end ? 0 : (__any_sync(0xffffffffu, fl != 0) ? 1 : 0);
 
       // ---- publish: one 32-byte header word into every CTA's inbox ----
       const uint32_t stamp = p.epoch + (uint32_t)s;
       const int par = s & 1;
       {
-        LL32* dst = p.inbox + ((size_t)par * G + lane) * G + cta;
+        LL32* dst = p.inbox + par * PAR_STRIDE + (size_t)lane * MAXG + cta;
 #pragma unroll
         for (int i = 0; i < 5; ++i)
-          if (pend0 & (1u << i)) ll32_store(dst + i * push_stride, __longlong_as_double(ckey), clp, cflag, stamp);
+          if (have[i]) ll32_store(dst + i * PUSH_STRIDE, __longlong_as_double(ckey), clp, cflag, stamp);
       }
       QF_TS(1)
 #ifdef BRA_QRCP_TRACE
       if (lane == 0) QF_TICK(0)
 #endif
 
-      // ---- gather my inbox (G contiguous 32-byte words), pick the winner ----
-      long long bkey = QF_NONE;
-      int blp = 0x7fffffff, bsrc = -1, bfl = 0;
+      // ---- gather my inbox: light polling loop (loads + stamp test only), the winner is picked once all are in ----
+      uint32_t q[5][8];
       {
-        const LL32* src = p.inbox + ((size_t)par * G + cta) * G + lane;
-        unsigned pend = pend0;
+        const LL32* src = p.inbox + par * PAR_STRIDE + (size_t)cta * MAXG + min(lane, G - 1);   // lanes >= G alias slot G-1
         uint32_t spins = 0;
-        while (__any_sync(0xffffffffu, pend != 0)) {
-          uint32_t q[5][8];
+        while (true) {
+          uint32_t bad = 0;
 #pragma unroll
-          for (int i = 0; i < 5; ++i)
-            if (pend & (1u << i)) ll32_ld(src + 32 * i, q[i]);
+          for (int i = 0; i < 5; ++i) ll32_ld(src + (have[i] ? 32 * i : 0), q[i]);
 #pragma unroll
-          for (int i = 0; i < 5; ++i)
-            if ((pend & (1u << i)) && ((q[i][1] ^ stamp) | (q[i][3] ^ stamp) | (q[i][5] ^ stamp) | (q[i][7] ^ stamp)) == 0) {
-              pend &= ~(1u << i);
-              const long long k2 = ((long long)q[i][2] << 32) | (long long)q[i][0];
-              const int lp2 = (int)q[i][4];
-              bfl |= (int)q[i][6];
-              if (k2 > bkey || (k2 == bkey && lp2 < blp)) {
-                bkey = k2;
-                blp = lp2;
-                bsrc = lane + 32 * i;
-              }
-            }
+          for (int i = 0; i < 5; ++i) bad |= (q[i][1] ^ stamp) | (q[i][3] ^ stamp) | (q[i][5] ^ stamp) | (q[i][7] ^ stamp);
+          if (!__any_sync(0xffffffffu, bad != 0)) break;
           if (++spins > SPIN_LIMIT) {
             failed = true;
             break;
+          }
+        }
+      }
+      long long bkey = QF_NONE;
+      int blp = 0x7fffffff, bsrc = -1;
+      uint32_t bfl = 0;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        if (have[i]) {
+          const long long k2 = ((long long)q[i][2] << 32) | (long long)q[i][0];
+          const int lp2 = (int)q[i][4];
+          bfl |= q[i][6];
+          if (k2 > bkey || (k2 == bkey && lp2 < blp)) {
+            bkey = k2;
+            blp = lp2;
+            bsrc = lane + 32 * i;
           }
         }
       }
@@ -344,16 +326,16 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
       const int wcta = __shfl_sync(0xffffffffu, bsrc, wl2);
       const long long gkey = __shfl_sync(0xffffffffu, bkey, wl2);
       const int lw = __shfl_sync(0xffffffffu, blp, wl2);          // winner's logical position
-      const int gflag = (int)__reduce_or_sync(0xffffffffu, (unsigned)bfl);
-      failed = __any_sync(0xffffffffu, failed) || wcta < 0;
+      const bool gflag = __any_sync(0xffffffffu, bfl != 0);
+      failed = failed || wcta < 0;
       QF_TS(2)
 #ifdef BRA_QRCP_TRACE
       if (lane == 0) QF_TICK(2)
 #endif
-      int stop = failed ? 3 : 0;
+      int pre = failed ? 3 : 0;
 
       // ---- block bookkeeping for the previous step (needs the gathered flags) ----
-      if (!stop && cnt > 0 && gflag) {
+      if (!pre && cnt > 0 && gflag) {
         // a column was flagged during step s-1: dlaqps ended its block there
         if (cta == 0 && lane == 0 && nblocks < p.kbcap) p.kbtrace[nblocks] = cnt;
         ++nblocks;
@@ -365,33 +347,49 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
               break;
             }
         }
-        if (kres >= 0) stop = 2;
+        if (kres >= 0) pre = 2;
         jblk = jn;
         cnt = 0;
         jb = min(p.nb, p.kcap - jblk);
       }
-      if (stop) {
-        if (lane == 0) {
-          ctrl->stop = stop;
-          ctrl->nsteps = s;
-        }
-        qf_bar(1);
-        break;
+      if (lane == 0) {
+        ctrl->pre = pre;
+        ctrl->wcta = wcta;
+        if (pre) ctrl->nsteps = s;
       }
+      qf_bar(3);                  // winner known: every warp fetches one chunk of its record
+      if (pre) break;
       if (s == 0) ptol = fmax(p.atol, p.rtol * __longlong_as_double(gkey));   // src/pqr.jl:386-389 (step-0 keys are norms)
 
-      // ---- the winner's Householder vector (already scaled by its owner), tau, beta, physical column ----
-      fetch(s, wcta, stamp);
-      failed = __any_sync(0xffffffffu, failed);
-      if (failed) {
-        if (lane == 0) {
-          ctrl->stop = 3;
-          ctrl->nsteps = s;
+      // ---- tau, beta, physical column of the winner ----
+      double tau, beta;
+      int pw;
+      {
+        const LL16* wrec = p.rec + ((size_t)par * G + wcta) * recs;
+        uint32_t h[3][4];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ll_ld(wrec + i, h[i][0], h[i][1], h[i][2], h[i][3]);
+        uint32_t spins = 0;
+        while (true) {
+          bool ok = true;
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            if (((h[i][1] ^ stamp) | (h[i][3] ^ stamp)) != 0) {
+              ok = false;
+              ll_ld(wrec + i, h[i][0], h[i][1], h[i][2], h[i][3]);
+            }
+          if (ok) break;
+          if (++spins > SPIN_LIMIT) {
+            failed = true;
+            break;
+          }
         }
-        qf_bar(1);
-        break;
+        tau = __hiloint2double((int)h[0][2], (int)h[0][0]);
+        beta = __hiloint2double((int)h[1][2], (int)h[1][0]);
+        pw = (int)h[2][0];
       }
-      if (lane == 0) {
+      if (failed && lane == 0) ctrl->fail = 1;
+      if (lane == 0 && !failed) {
         rdblk[cnt] = beta;
         // ---- ownership updates ----
         if (my_ps >= 0 && my_ps != pw) lpos[my_ps - col0] = lw;   // column K moves to pvt
@@ -406,7 +404,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
       // ---- end-of-step bookkeeping, known as soon as beta is (the rank test only looks at the diagonal) ----
       ++cnt;
       const bool block_end = (cnt == jb);
-      if (block_end) {
+      if (block_end && !failed) {
         // block ends by count; flags raised in this step are irrelevant
         if (cta == 0 && lane == 0 && nblocks < p.kbcap) p.kbtrace[nblocks] = cnt;
         ++nblocks;
@@ -426,7 +424,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
         }
       }
       prev_block_end = block_end;
-      stop = kres >= 0 ? 1 : 0;
+      const int stop = kres >= 0 ? 1 : 0;
       if (lane == 0) {
         ctrl->tau = tau;
         ctrl->stop = stop;
@@ -437,6 +435,10 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
       if (lane == 0) QF_TICK(3)
 #endif
       qf_bar(1);                  // vbuf, tau, lpos are ready: the compute warps run pass 1 of step s
+      if (ctrl->fail) {
+        failed = true;
+        break;
+      }
       if (stop) break;
       ++s;
       qf_bar(2);                  // candidates for step s
@@ -767,9 +769,12 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
 #ifdef BRA_QRCP_TRACE
       if (warp == 0 && lane == 0) QF_TICK(1)
 #endif
-      qf_bar(1);                  // the comm warp has fetched step s: vbuf, tau, lpos
+      qf_bar(3);                  // the comm warp knows the winner of step s
+      if (ctrl->pre) break;
+      if (warp < nchtot - (s >> 6)) fetch_chunk(s, ctrl->wcta, warp);
+      qf_bar(1);                  // the record of step s is in vbuf; tau, lpos are set
+      if (ctrl->fail) break;
       const int stop = ctrl->stop;
-      if (stop >= 2) break;
       const double tau = ctrl->tau;
       QF_TS(7)
       const bool downdate = (s < lastrk - 1) && !p.nopivot;      // no pivoting: the norms are never looked at
@@ -834,7 +839,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
 size_t fast_fixed_bytes(int l, int cpc, int nbe) {
   const int LV = ((l + 63) >> 6) << 6;
   const int cpe = (cpc + 1) & ~1;
-  return (size_t)2 * LV * 8 + 16 + (size_t)((nbe + 1) & ~1) * 8 + 16 * 16 + 16 * 8 + (size_t)cpe * 8 * 6 +
+  return (size_t)2 * LV * 8 + 32 + (size_t)((nbe + 1) & ~1) * 8 + 16 * 16 + 16 * 8 + (size_t)cpe * 8 * 6 +
          (size_t)((cpe + 3) & ~3) * 4 + 64;
 }
 

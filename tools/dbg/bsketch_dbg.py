@@ -11,12 +11,17 @@ V = brapprox.idfact(A, brapprox.LRAOptions(rtol=1e-9), rand=rin.drawn, ctx=ctx)
 inf = ctx.info()
 order, n = int(inf.orders[inf.rounds - 1]), int(inf.n)
 steps = int(inf.steps[inf.rounds - 1])
-print("rounds", inf.rounds, "order", order, "n", n, "steps", steps, "k", inf.k, "oracle k", Fo.k, "n drawn", len(rin.drawn))
 Bg = ctx.fetch(B.F_BSKETCH, (order, n))
+pg = ctx.fetch(B.F_P, (n,), dtype=np.int64)
 Bo = o.apply_sketch("randn", A, order, rin.drawn[-1], "n")
+B0 = Bo.copy(order="F")
 p, tau_o, k_o = o.geqp3_adap(Bo, o.LRAOptions(rtol=1e-9))
-print("p equal:", np.array_equal(p, V.p), "k_o", k_o)
-d = np.abs(np.triu(Bg[:k_o, :]) - np.triu(Bo[:k_o, :])).max(axis=0)
-bad = np.nonzero(d > 1e-10)[0]
-print("bad columns", bad[:40], len(bad))
-print("p[bad]", p[bad[:20]], "V.p[bad]", V.p[bad[:20]])
+k = k_o
+print("V1" if os.environ.get("BRA_QRCP_V1") else "FAST", "steps", steps, "k", inf.k, k_o, "p[:k] equal", np.array_equal(pg[:k], p[:k]), "p equal", np.array_equal(pg, p))
+inv_g, inv_o = np.argsort(pg), np.argsort(p)
+D = np.abs(Bg[:k, inv_g] - Bo[:k, inv_o])
+print("max diff per row:", " ".join(f"{x:.1e}" for x in D.max(axis=1)))
+j = np.unravel_index(np.argmax(D), D.shape); print("argmax", j, "orig col", j[1], "pos_g", inv_g[j[1]], "pos_o", inv_o[j[1]], Bg[j[0], inv_g[j[1]]], Bo[j[0], inv_o[j[1]]])
+# geqp3 directly on the same B through the stage-wise entry
+pj, tau, Rg, kk, tr = brapprox.geqp3_adap(B0, rtol=1e-9, ctx=ctx)
+print("stagewise k", kk, "steps", tr["steps"], "kb", tr.get("kb"))
