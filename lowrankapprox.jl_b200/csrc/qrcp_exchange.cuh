@@ -82,6 +82,13 @@ __device__ __forceinline__ void ll32_store(LL32* p, double v, int lp, int flag, 
                "r"((uint32_t)flag)
                : "memory");
 }
+// two doubles (rows r, r+1 of a record) as two adjacent LL16 words in one 32-byte store
+__device__ __forceinline__ void ll32_store2(LL32* p, double x, double y, uint32_t stamp) {
+  asm volatile("st.relaxed.gpu.global.v8.b32 [%0], {%1,%2,%3,%2,%4,%2,%5,%2};" ::"l"(p),
+               "r"((uint32_t)__double2loint(x)), "r"(stamp), "r"((uint32_t)__double2hiint(x)),
+               "r"((uint32_t)__double2loint(y)), "r"((uint32_t)__double2hiint(y))
+               : "memory");
+}
 __device__ __forceinline__ void ll32_ld(const LL32* p, uint32_t (&q)[8]) {
   asm volatile("ld.relaxed.gpu.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])

@@ -64,7 +64,16 @@ __device__ __forceinline__ int warp_argmax_key(long long key, int lp) {
 }
 
 #ifdef BRA_QRCP_TRACE
-#define QF_TS(k) if (p.ts && lane == 0 && s == p.ts_step) p.ts[((size_t)cta * QR_WARPS + warp) * 16 + (k)] = clock64();
+__device__ __forceinline__ long long qf_gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define QF_TS(k)                                                                                   \
+  if (p.ts && lane == 0 && s == p.ts_step) {                                                       \
+    p.ts[((size_t)cta * QR_WARPS + warp) * 16 + (k)] = clock64();                                  \
+    if ((k) < 4) p.ts[((size_t)cta * QR_WARPS + warp) * 16 + 9 + (k)] = qf_gtime();                \
+  }
 #define QF_TICK(i) { long long _t = clock64(); s_tph[i] += _t - tlast; tlast = _t; }
 #else
 #define QF_TS(k)
@@ -183,8 +192,9 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
     const int r = ((s >> 6) << 6) + 64 * c + 2 * lane;
     const bool need = r + 1 > s && r < l;
     const bool isw = wcta == cta;
-    uint32_t q[8], hb[4], hp[4];
+    uint32_t q[8], hb[4], hp[4], hs[4];
     if (need) ll32_ld(reinterpret_cast<const LL32*>(wrec + RECH + r), q);
+    ll_ld(wrec + 3, hs[0], hs[1], hs[2], hs[3]);
     if (isw) {
       ll_ld(wrec + 1, hb[0], hb[1], hb[2], hb[3]);
       ll_ld(wrec + 2, hp[0], hp[1], hp[2], hp[3]);
@@ -200,6 +210,10 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
           ll32_ld(reinterpret_cast<const LL32*>(wrec + RECH + r), q);
         }
       }
+      if (((hs[1] ^ stamp) | (hs[3] ^ stamp)) != 0) {
+        ok = false;
+        ll_ld(wrec + 3, hs[0], hs[1], hs[2], hs[3]);
+      }
       if (isw && (((hb[1] ^ stamp) | (hb[3] ^ stamp) | (hp[1] ^ stamp) | (hp[3] ^ stamp)) != 0)) {
         ok = false;
         ll_ld(wrec + 1, hb[0], hb[1], hb[2], hb[3]);
@@ -212,9 +226,10 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
       }
     }
     if (r < l) {
+      const double scale = __hiloint2double((int)hs[2], (int)hs[0]);
       double2 v;
-      v.x = r > s ? __hiloint2double((int)q[2], (int)q[0]) : (r == s ? 1.0 : 0.0);
-      v.y = r + 1 > s ? __hiloint2double((int)q[6], (int)q[4]) : (r + 1 == s ? 1.0 : 0.0);
+      v.x = r > s ? __hiloint2double((int)q[2], (int)q[0]) * scale : (r == s ? 1.0 : 0.0);
+      v.y = r + 1 > s ? __hiloint2double((int)q[6], (int)q[4]) * scale : (r + 1 == s ? 1.0 : 0.0);
       if (r + 1 >= l) v.y = 0.0;
       *reinterpret_cast<double2*>(vbuf + par * LV + r) = v;
       if (isw) {
@@ -329,6 +344,9 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
       const bool gflag = __any_sync(0xffffffffu, bfl != 0);
       failed = failed || wcta < 0;
       QF_TS(2)
+#ifdef BRA_QRCP_TRACE
+      if (p.ts && lane == 0 && s == p.ts_step) p.ts[((size_t)cta * QR_WARPS + warp) * 16 + 13] = wcta;
+#endif
 #ifdef BRA_QRCP_TRACE
       if (lane == 0) QF_TICK(2)
 #endif
@@ -617,7 +635,9 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
       st2[mylc] = make_double2(v1n != 0.0 ? 1.0 / v1n : 0.0, qn * qn);
     };
 
-    // ---- candidate column: finish step sp on it (if sp >= 0), then dlarfg for step sp+1 -> this CTA's record ----
+    // ---- candidate column: finish step sp on it (if sp >= 0), then dlarfg for step sp+1 -> this CTA's record.
+    //      ONE sweep: the updated entries go into the record unscaled while the sum of squares accumulates; tau, beta
+    //      and the scaling 1/(alpha - beta) follow in the header (the receivers scale while they build v). ----
     auto cand_dlarfg = [&](auto tag, const int sp, const int cand_lc) {
       constexpr int NCH = decltype(tag)::value;
       const int sn = sp + 1;
@@ -647,10 +667,12 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
             if (insm) *reinterpret_cast<double2*>(a + r) = x;
             else __stcg(reinterpret_cast<double2*>(a + r), x);
           }
+          // rows (r, r+1) are two adjacent LL words: one 32-byte store (rows <= sn are never read)
+          if (r + 1 > sn) ll32_store2(reinterpret_cast<LL32*>(myrec + r), x.x, x.y, stamp);
           if (r == sn) al = x.x;
           if (r + 1 == sn) al = x.y;
           if (r > sn) ss = fma(x.x, x.x, ss);
-          if (r + 1 > sn) ss = fma(x.y, x.y, ss);
+          if (r + 1 > sn && r + 1 < l) ss = fma(x.y, x.y, ss);
         }
       }
       if (sn >= l) return;
@@ -667,21 +689,9 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
         tau = (beta - alpha) / beta;
         scale = 1.0 / (alpha - beta);
       }
-      __syncwarp();
-      // second sweep over the (just updated) column: scaled entries into the record
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int r = rbase + 64 * c;
-        if (r + 1 > sn && (c < NCH - 1 || r < l)) {
-          const double2 x = insm ? *reinterpret_cast<const double2*>(a + r) : __ldcg(reinterpret_cast<const double2*>(a + r));
-          if (r > sn) ll_store_d(myrec + r, x.x * scale, stamp);
-          if (r + 1 < l) ll_store_d(myrec + r + 1, x.y * scale, stamp);
-        }
-      }
-      if (lane == 0) {
-        ll_store_d(myrec - RECH + 0, tau, stamp);
-        ll_store_d(myrec - RECH + 1, beta, stamp);
-        ll_store(myrec - RECH + 2, (uint32_t)(col0 + cand_lc), 0u, stamp);
+      if (lane < 4) {
+        const double hv = lane == 0 ? tau : lane == 1 ? beta : lane == 2 ? __longlong_as_double((long long)(uint32_t)(col0 + cand_lc)) : scale;
+        ll_store_d(myrec - RECH + lane, hv, stamp);
       }
     };
 

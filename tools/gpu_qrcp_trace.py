@@ -25,3 +25,21 @@ for c in (0, 73, 140):
         row = t[c, :, k_]
         if k_ < 4: print(f"  {nm:30s} {row[15] - base:6d}")
         else: print(f"  {nm:30s}", " ".join(f"{(v - base) if v else -1:6d}" for v in row[:15]))
+# global-timer view (ns) of the comm warps: when did every CTA push its header / learn the winner / finish the fetch
+g = t[:, 15, 9:13].astype(float)
+g0 = g[:, 0].min()
+for k_, nm in enumerate(["top", "pushed", "winner known", "fetched"]):
+    x = g[:, k_] - g0
+    print(f"globaltimer ns  {nm:13s} min {x.min():8.0f} med {np.median(x):8.0f} max {x.max():8.0f}  argmax CTA {int(x.argmax())}  argmin CTA {int(x.argmin())}")
+late = np.argsort(g[:, 1])[-8:]
+print("latest pushers (CTA: top, pushed):", [(int(c), int(g[c, 0] - g0), int(g[c, 1] - g0)) for c in late])
+wc = int(t[0, 15, 13])
+print("winner CTA of this step:", wc)
+c64 = t.astype(float)
+dur = {"top->push": c64[:, 15, 1] - c64[:, 15, 0], "push->winner": c64[:, 15, 2] - c64[:, 15, 1], "winner->fetched": c64[:, 15, 3] - c64[:, 15, 2],
+       "pass2 (max warp)": (c64[:, :15, 6] - c64[:, :15, 4]).max(axis=1), "owner dlarfg (max)": (c64[:, :15, 5] - c64[:, :15, 4]).max(axis=1),
+       "pass1 (max warp)": (c64[:, :15, 8] - c64[:, :15, 7]).max(axis=1), "pass1 (min warp)": (c64[:, :15, 8] - c64[:, :15, 7]).min(axis=1)}
+order = np.argsort(g[:, 0])
+print("CTAs by step-top time (ns):  first 5", [(int(c), int(g[c, 0] - g0)) for c in order[:5]], " last 8", [(int(c), int(g[c, 0] - g0)) for c in order[-8:]])
+for nm, d in dur.items():
+    print(f"{nm:20s} median {np.median(d):7.0f}  max {d.max():7.0f} (CTA {int(d.argmax())})   late CTAs:", [int(d[c]) for c in order[-8:]])
