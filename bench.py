@@ -36,6 +36,12 @@ RANK_GEN = 640
 DECADES, JDIV = 12.0, 500.0
 
 
+def workload_label(what: str, n: int) -> str:
+    """The SAME string in both arms (ours and --impl reference): the two lines describe one workload."""
+    return (f"C2: {what} of {n}x{n} FP64, A = U diag(10^(-12j/500)) V^T (rank-640 factors from thin QRs of seeded "
+            "Gaussians), rtol=1e-12, sketch=randn, adaptive rounds")
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -149,7 +155,16 @@ def cpu_sample(n: int, what: str, max_seconds: float = 25.0, threads: int = 0, s
             break
     per = (sum(times) / len(times)) if steps > 0 else sorted(times)[len(times) // 2]
     stat = "mean" if steps > 0 else "median"
+    # the error metric of BASELINE.json on the last factorization: snormdiff(A, F) / snorm(A)   (||A||_2 = 1 here)
+    try:
+        if what == "psvdfact":
+            err = o.snormdiff_lowrank(A, F.U * F.S, F.Vt) / o.snorm_dense(A)
+        else:
+            err = o.id_error(A, F)
+    except Exception:
+        err = None
     return {"value": 1.0 / per, "unit": "factorizations/s", "cores": cores, "kind": "port",
+            "snormdiff_over_snorm": err,
             "sample": f"{rep} x {what} of the same {n}x{n} workload on the host ({stat}; includes drawing Omega "
                       f"with numpy), OpenBLAS threads={o.get_blas_threads()}, k={ks[-1]}"}, times, nwarm
 
@@ -166,8 +181,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": f"{what}_factorizations_per_sec", "value": v, "unit": "factorizations/s",
             "n_gpus": args.gpus, "steps": len(times), "warmup": nwarm, "ms_per_step": 1e3 / v, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C2: {what} of {args.n}x{args.n} FP64, sigma_j=10^(-12j/500), rtol=1e-12, "
-                                   "sketch=randn (oracle = reference's LAPACK/BLAS CPU path restated)"},
+            "config": {"workload": workload_label(what, args.n),
+                       "arm": "oracle = the reference's LAPACK/BLAS CPU path restated (Omega drawn with numpy)"},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "factorizations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -510,6 +525,22 @@ def main():
             te = float(t.item())
         e2e = {"value": world * e2e_steps / te, "unit": "factorizations/s", "h2d_bytes_per_step": int(n * n * 8),
                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps}
+    # ---- the error metric of BASELINE.json for OUR factorization: snormdiff(A, F) / snorm(A), on the device
+    #      (bra_snorm_f64: the reference's power iteration, src/snorm.jl:14-53) ----
+    our_err = None
+    if rank == 0:
+        try:
+            if what == "psvdfact":
+                Fh = brapprox.psvdfact(A, rtol=RTOL, seed=12345, ctx=ctx)
+                our_err = brapprox.snormdiff(A, Fh, ctx=ctx) / brapprox.snorm(A, ctx=ctx)
+            else:
+                from brapprox._frontend import idfact as _idf
+                Vh = _idf(A, rtol=RTOL, seed=12345, ctx=ctx)
+                Cs = At[torch.as_tensor(Vh.sk - 1, device=dev), :].T      # A[:, sk] (At holds A^T row by row)
+                our_err = (brapprox.snormdiff(A, Cs.contiguous().cpu().numpy(), Vh.matrix(), ctx=ctx)
+                           / brapprox.snorm(A, ctx=ctx))
+        except Exception as e:
+            our_err = repr(e)[:200]
 
     # ---- side measurements of the other BASELINE configs (same run, same box): C3 single GPU; C4 (row-sharded,
     # NCCL all-reduce) and C5 (batched, no collective) over all ranks, strong scaling, max over ranks ----
@@ -576,29 +607,51 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu, _, _ = cpu_sample(n, what)
+        one, _, _ = cpu_sample(n, what, max_seconds=12.0, threads=1)
+        cpu["one_thread"] = {"value": one["value"], "unit": one["unit"], "cores": 1, "sample": one["sample"]}
 
     line = {
         "metric": f"{what}_factorizations_per_sec", "value": value, "unit": "factorizations/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * tmax / args.steps,
         "host_wall_ms_per_step": 1e3 * wall_host / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C2: {what} of {n}x{n} FP64, A=U diag(10^(-12j/500)) V^T (rank-640 factors), "
-                               "rtol=1e-12, sketch=randn, adaptive, device Philox Omega, A resident in HBM",
+        "config": {"workload": workload_label(what, n),
+                   "arm": "libbrapprox on B200: device Philox Omega, A resident in HBM for `value`, host A for `e2e`",
                    "rounds_order_k": rounds, "pivot_steps": steps, "k": k,
                    "l2": "inputs (537 MB) larger than L2 (126 MB); no flush needed",
                    "parallelism": "replicas only" if world > 1 else "single GPU"},
         "whole_factorization": {"algorithmic_gflop": f_total / 1e9,
                                 "achieved_tflops": f_total * world * args.steps / tmax / 1e12 / world,
                                 "frac_of_fp64_peak": f_total * args.steps / tmax / 1e12 / fp64_peak},
-        "roofline": {"bound": "tensor", "kernel": "gemm_sketch_kernel (TMA + DMMA m8n8k4 FP64)",
-                     "achieved": gemm_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": (gemm_tf / fp64_peak) if gemm_tf else None, "traffic": ncu_traffic_per_launch()[0],
-                     "traffic_note": "bytes per launch, mean over the 5 sketch launches of one factorization, from "
-                                     "profiles/r01e_gemm_sketch_raw.csv (algorithmic: 537 MB of A + l x 8192 x 16 B)",
+        # config-level roofline: ALL algorithmic flops of the factorization over the whole step time; the
+        # dominant kernels follow in `kernels` (the FP64 tensor GEMM against the same peak; the pivoted-QR chain is
+        # latency-bound: reported in microseconds per dependent pivot step)
+        "roofline": {"bound": "tensor", "scope": f"whole {what} (sketch GEMMs + pivoted QR + T solve"
+                                                 + (" + QR of A[:,sk] + psvd core + U, Vt)" if what == "psvdfact" else ")"),
+                     "achieved": f_total * args.steps / tmax / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": f_total * args.steps / tmax / 1e12 / fp64_peak, "traffic": None,
+                     "algorithmic_flops_per_step": f_total,
                      "peak_source": f"measured in this run: cuBLAS DGEMM 8192^3 = {cublas_tf:.1f} TF, "
                                     f"DMMA issue probes = {max(peaks.values()):.1f} TF "
                                     "(MEASURED_PEAKS.json has no FP64 figure)",
-                     "algorithmic_flops_per_step": f_sk, "gemm_launches": gemm_calls, "gemm_ms_total": gemm_ms},
+                     "kernels": [
+                         {"kernel": "gemm_sketch_kernel (TMA + DMMA m8n8k4 FP64)", "bound": "tensor",
+                          "achieved": gemm_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                          "frac": (gemm_tf / fp64_peak) if gemm_tf else None,
+                          "share_of_step": gemm_ms / args.steps / (1e3 * tmax / args.steps),
+                          "traffic": ncu_traffic_per_launch()[0],
+                          "traffic_note": "DRAM bytes per launch, mean over the 5 sketch launches of one factorization "
+                                          "(ncu --set full); algorithmic: 537 MB of A + l x 8192 x 16 B",
+                          "algorithmic_flops_per_step": f_sk, "launches": gemm_calls, "ms_total": gemm_ms},
+                         {"kernel": "qrcp_fast_kernel (persistent warp-specialised pivoted QR)", "bound": "latency",
+                          "us_per_pivot_step": 1e3 * prof["qrcp"][0] / args.steps / max(1, sum(steps)),
+                          "pivot_steps": sum(steps), "algorithmic_flops_per_step": f_qr,
+                          "achieved": f_qr * args.steps / (prof["qrcp"][0] * 1e-3) / 1e12 if prof["qrcp"][0] > 0 else None,
+                          "unit": "TFLOP/s", "share_of_step": prof["qrcp"][0] / args.steps / (1e3 * tmax / args.steps)}]},
+        "error": {"metric": "snormdiff(A, F) / snorm(A)", "ours": our_err,
+                  "oracle": (cpu or {}).get("snormdiff_over_snorm"),
+                  "note": "ours: bra_snorm_f64 on the device for a fresh factorization of the benchmark matrix; oracle: "
+                          "the same metric for the CPU arm's own instance of the workload (same spectrum, numpy seed)"},
         "stage_ms_per_step": {k2: v[0] / args.steps for k2, v in prof.items()},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "fp64_peak_probes_tflops": peaks,
