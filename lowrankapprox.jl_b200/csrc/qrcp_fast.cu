@@ -29,7 +29,10 @@
 namespace {
 
 constexpr int QF_MAXCH = 9;               // 64-row chunks: l <= 576
-constexpr int QF_CW = QR_WARPS - 1;       // compute warps
+constexpr int QF_THREADS = QR_THREADS;    // 512: 15 compute warps + the comm warp (registers are allocated per 4 warps: fewer
+                                          // threads would not buy more registers until 384)
+constexpr int QF_WARPS = QF_THREADS / 32;
+constexpr int QF_CW = QF_WARPS - 1;       // compute warps
 constexpr long long QF_NONE = -1;         // "no candidate" key (valid keys are bit patterns of non-negative doubles)
 
 struct QfCtrl {
@@ -49,7 +52,7 @@ struct __align__(8) QfSlotB {
   int lc, flag;
 };
 
-__device__ __forceinline__ void qf_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(QR_THREADS) : "memory"); }
+__device__ __forceinline__ void qf_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(QF_THREADS) : "memory"); }
 
 // argmax of (key, lp) over the warp (key: i64, larger wins; ties: smaller lp); returns the winning lane
 __device__ __forceinline__ int warp_argmax_key(long long key, int lp) {
@@ -80,21 +83,23 @@ __device__ __forceinline__ long long qf_gtime() {
 #define QF_TICK(i)
 #endif
 
-#define QF_DISPATCH(nchv, FN, ...)                                           \
-  switch (nchv) {                                                            \
-    case 1: FN(std::integral_constant<int, 1>{}, __VA_ARGS__); break;        \
-    case 2: FN(std::integral_constant<int, 2>{}, __VA_ARGS__); break;        \
-    case 3: FN(std::integral_constant<int, 3>{}, __VA_ARGS__); break;        \
-    case 4: FN(std::integral_constant<int, 4>{}, __VA_ARGS__); break;        \
-    case 5: FN(std::integral_constant<int, 5>{}, __VA_ARGS__); break;        \
-    case 6: FN(std::integral_constant<int, 6>{}, __VA_ARGS__); break;        \
-    case 7: FN(std::integral_constant<int, 7>{}, __VA_ARGS__); break;        \
-    case 8: FN(std::integral_constant<int, 8>{}, __VA_ARGS__); break;        \
-    default: FN(std::integral_constant<int, 9>{}, __VA_ARGS__); break;       \
+// NMAX = ceil(l / 64) bound of the launch: instances above it are never generated, so the register peak of the long
+// instances (v in 2 NCH registers per lane) does not spill the step loop of the short, latency-critical sketches
+#define QF_DISPATCH(nchv, FN, ...)                                                                     \
+  switch (nchv) {                                                                                      \
+    case 1: FN(std::integral_constant<int, 1>{}, __VA_ARGS__); break;                                  \
+    case 2: if constexpr (NMAX >= 2) FN(std::integral_constant<int, 2>{}, __VA_ARGS__); break;         \
+    case 3: if constexpr (NMAX >= 3) FN(std::integral_constant<int, 3>{}, __VA_ARGS__); break;         \
+    case 4: if constexpr (NMAX >= 4) FN(std::integral_constant<int, 4>{}, __VA_ARGS__); break;         \
+    case 5: if constexpr (NMAX >= 5) FN(std::integral_constant<int, 5>{}, __VA_ARGS__); break;         \
+    case 6: if constexpr (NMAX >= 6) FN(std::integral_constant<int, 6>{}, __VA_ARGS__); break;         \
+    case 7: if constexpr (NMAX >= 7) FN(std::integral_constant<int, 7>{}, __VA_ARGS__); break;         \
+    case 8: if constexpr (NMAX >= 8) FN(std::integral_constant<int, 8>{}, __VA_ARGS__); break;         \
+    default: if constexpr (NMAX >= 9) FN(std::integral_constant<int, 9>{}, __VA_ARGS__); break;        \
   }
 
-template <int JW>
-__global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) {
+template <int JW, int NMAX>
+__global__ void __launch_bounds__(QF_THREADS, 1) qrcp_fast_kernel(QrcpParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x, cta = blockIdx.x;
@@ -113,21 +118,25 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
   const int off_rd = off_ctrl + 32;                   // rdblk: nb (even) diagonal entries of the current block
   const int off_sa = off_rd + ((p.nb + 1) & ~1) * 8;  // warp candidates: QfSlotA[16], QfSlotB[16]
   const int off_sb = off_sa + 16 * 16;
-  const int off_f = off_sb + 16 * 8;                  // fbuf: f_j of the current step                        cpe doubles
+  const int off_lv = off_sb + 16 * 8;                 // slive[16]: live-column mask of each compute warp for the current step
+  const int off_f = off_lv + 16 * 4;                  // fbuf: f_j of the current step                        cpe doubles
   const int off_st = off_f + cpe * 8;                 // st2: {1/vn1, (vn1/vn2)^2} per column                 cpe double2
-  const int off_sq = off_st + cpe * 16;               // ssq = vn1^2, then sv1 = vn1, then srv2 = 1/vn2       3 cpe doubles
-  const int off_lpos = off_sq + 3 * cpe * 8;          // lpos: logical LAPACK position per column             cpe ints (x4)
+  const int off_sq = off_st + cpe * 16;               // ssq = vn1^2, sv1 = vn1, srv2 = 1/vn2, stmp = downdate factor of
+                                                      //   the current step (< 0: nothing to refresh)            4 cpe doubles
+  const int off_lpos = off_sq + 4 * cpe * 8;          // lpos: logical LAPACK position per column             cpe ints (x4)
   const int off_cache = off_lpos + ((cpe + 3) & ~3) * 4;   // the slab: csm columns of lds doubles
 #define vbuf reinterpret_cast<double*>(smem_raw)
 #define ctrl reinterpret_cast<QfCtrl*>(smem_raw + off_ctrl)
 #define rdblk reinterpret_cast<double*>(smem_raw + off_rd)
 #define slotA reinterpret_cast<QfSlotA*>(smem_raw + off_sa)
 #define slotB reinterpret_cast<QfSlotB*>(smem_raw + off_sb)
+#define slive reinterpret_cast<unsigned*>(smem_raw + off_lv)
 #define fbuf reinterpret_cast<double*>(smem_raw + off_f)
 #define st2 reinterpret_cast<double2*>(smem_raw + off_st)
 #define ssq reinterpret_cast<double*>(smem_raw + off_sq)
 #define sv1 (ssq + cpe)
 #define srv2 (ssq + 2 * cpe)
+#define stmp (ssq + 3 * cpe)
 #define lpos reinterpret_cast<int*>(smem_raw + off_lpos)
 #define cache reinterpret_cast<double*>(smem_raw + off_cache)
   const int recs = lds + RECH;                        // record stride (even: 32-byte aligned row pairs)
@@ -136,7 +145,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
   if (tid < 6) s_tph[tid] = 0;
 #endif
 
-  for (int r = tid; r < 2 * LV; r += QR_THREADS) vbuf[r] = 0.0;
+  for (int r = tid; r < 2 * LV; r += QF_THREADS) vbuf[r] = 0.0;
   if (tid == 0) {
     ctrl->tau = 0.0;
     ctrl->stop = 0;
@@ -147,7 +156,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
   }
 
   // ---- prologue: stage the slab, initial column norms (src/pqr.jl:376-385) ----
-  for (int lc = warp; lc < ncols; lc += QR_WARPS) {
+  for (int lc = warp; lc < ncols; lc += QF_WARPS) {
     const double* g = p.B + (col0 + lc) * p.ldb;
     double amax = 0.0;
     for (int r = lane; r < l; r += 32) {
@@ -495,8 +504,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
 
     // ---- pass 1 of step s.  Out: live mask (bit j: column j takes part in step s), and for lane j the downdate
     //      factor temp with dd = "refresh my column's norm state after the candidate is out" ----
-    auto pass1 = [&](auto tag, const int s, const double tau, const bool downdate, const bool want_cand, unsigned& live,
-                     double& temp, bool& dd) {
+    auto pass1 = [&](auto tag, const int s, const double tau, const bool downdate, const bool want_cand) {
       constexpr int NCH = decltype(tag)::value;
       const int par = s & 1;
       const int rbase = ((s >> 6) << 6) + 2 * lane;
@@ -510,7 +518,8 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
       const int qpos = mycol ? lpos[mylc] : -1;
       const double2 stj = st2[mylc];
       const double sq = ssq[mylc];
-      live = __ballot_sync(0xffffffffu, qpos > s);
+      const unsigned live = __ballot_sync(0xffffffffu, qpos > s);
+      if (lane == 0) slive[warp] = live;
       double myas = 0.0;
       if (mycol) myas = lane < jsm ? cache[(size_t)mylc * lds + s] : __ldcg(p.B + (col0 + mylc) * p.ldb + s);
 
@@ -566,8 +575,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
       long long key = QF_NONE;
       int lp = 0x7fffffff, ps = -1;
       bool flagged = false;
-      temp = 1.0;
-      dd = false;
+      double temp = -1.0;                 // >= 0: plain downdate, the norm state of my column is refreshed after bar 2
       if (qpos > s) {
         lp = qpos;
         if (qpos == s + 1) ps = (int)(col0 + mylc);
@@ -575,10 +583,10 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
           key = qpos == s + 1 ? __double_as_longlong(1.0) : QF_NONE;
         } else if (downdate && sq != 0.0) {
           const double t = fabs(myas - fmine) * stj.x;
-          temp = fmax(0.0, (1.0 + t) * (1.0 - t));
-          flagged = temp * stj.y <= TOL3Z;
-          dd = !flagged;
-          key = __double_as_longlong(sq * temp);
+          const double tt = fmax(0.0, (1.0 + t) * (1.0 - t));
+          flagged = tt * stj.y <= TOL3Z;
+          if (!flagged) temp = tt;
+          key = __double_as_longlong(sq * tt);
         } else {
           key = __double_as_longlong(sq);
         }
@@ -623,6 +631,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
           fbuf[lc] = 0.0;
         }
       }
+      if (mycol) stmp[mylc] = temp;
       if (want_cand) publish(key, lp, ps, wflag);
     };
 
@@ -644,7 +653,6 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
       const uint32_t stamp = p.epoch + (uint32_t)sn;
       LL16* myrec = p.rec + ((size_t)(sn & 1) * G + cta) * recs + RECH;
       const bool insm = cand_lc < csm;
-      double* a = insm ? cache + (size_t)cand_lc * lds : p.B + (col0 + cand_lc) * p.ldb;
       double f = 0.0;
       if (sp >= 0) {
         f = fbuf[cand_lc];
@@ -653,32 +661,60 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
       }
       const int rb = ((sp >= 0 ? sp : 0) >> 6) << 6;
       const int rbase = rb + 2 * lane;
-      const double* vb = vbuf + (sp & 1) * LV;
       double ss = 0.0, al = 0.0;
+      // two separate code paths (not one generic pointer): the shared-memory column must compile to LDS/STS
+      auto sweep = [&](auto smtag) {
+        constexpr bool SM = decltype(smtag)::value;
+        double2* a2 = reinterpret_cast<double2*>((SM ? cache + (size_t)cand_lc * lds : p.B + (col0 + cand_lc) * p.ldb) + rbase);
+        const double2* v2 = reinterpret_cast<const double2*>(vbuf + (sp & 1) * LV + rbase);
+        // every load before the first store: the shared-memory pipe is saturated by the other warps' pass 2, and a
+        // load behind a (possibly aliasing) store would pay the full queueing delay once per chunk
+        double2 x[NCH], v[NCH];
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int r = rbase + 64 * c;
-        if (c < NCH - 1 || r < l) {
-          double2 x = insm ? *reinterpret_cast<const double2*>(a + r) : __ldcg(reinterpret_cast<const double2*>(a + r));
-          if (f != 0.0) {
-            const double2 v = *reinterpret_cast<const double2*>(vb + r);
-            x.x = fma(-f, v.x, x.x);
-            x.y = fma(-f, v.y, x.y);
-            if (insm) *reinterpret_cast<double2*>(a + r) = x;
-            else __stcg(reinterpret_cast<double2*>(a + r), x);
+        for (int c = 0; c < NCH; ++c) {
+          x[c] = make_double2(0.0, 0.0);
+          v[c] = make_double2(0.0, 0.0);
+          if (c < NCH - 1 || rbase + 64 * c < l) {
+            x[c] = SM ? a2[32 * c] : __ldcg(a2 + 32 * c);
+            v[c] = v2[32 * c];
           }
-          // rows (r, r+1) are two adjacent LL words: one 32-byte store (rows <= sn are never read)
-          if (r + 1 > sn) ll32_store2(reinterpret_cast<LL32*>(myrec + r), x.x, x.y, stamp);
-          if (r == sn) al = x.x;
-          if (r + 1 == sn) al = x.y;
-          if (r > sn) ss = fma(x.x, x.x, ss);
-          if (r + 1 > sn && r + 1 < l) ss = fma(x.y, x.y, ss);
         }
-      }
+        if (f != 0.0) {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            if (c < NCH - 1 || rbase + 64 * c < l) {
+              x[c].x = fma(-f, v[c].x, x[c].x);
+              x[c].y = fma(-f, v[c].y, x[c].y);
+              if (SM) a2[32 * c] = x[c];
+              else __stcg(a2 + 32 * c, x[c]);
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int r = rbase + 64 * c;
+          if (c < NCH - 1 || r < l) {
+            // rows (r, r+1) are two adjacent LL words: one 32-byte store (rows <= sn are never read)
+            if (r + 1 > sn) ll32_store2(reinterpret_cast<LL32*>(myrec + r), x[c].x, x[c].y, stamp);
+            if (r == sn) al = x[c].x;
+            if (r + 1 == sn) al = x[c].y;
+            if (r > sn) ss = fma(x[c].x, x[c].x, ss);
+            if (r + 1 > sn && r + 1 < l) ss = fma(x[c].y, x[c].y, ss);
+          }
+        }
+      };
+      if (insm) sweep(std::true_type{});
+      else sweep(std::false_type{});
       if (sn >= l) return;
+#ifdef BRA_QRCP_TRACE
+      if (p.ts && lane == 0 && sn == p.ts_step) p.ts[((size_t)cta * QR_WARPS + warp) * 16 + 14] = clock64();
+#endif
       // row sn sits in exactly one lane
       const double alpha = __shfl_sync(0xffffffffu, al, ((sn - rb) & 63) >> 1);
       ss = warp_sum(ss);
+#ifdef BRA_QRCP_TRACE
+      if (p.ts && lane == 0 && sn == p.ts_step) p.ts[((size_t)cta * QR_WARPS + warp) * 16 + 15] = clock64();
+#endif
       double beta, tau, scale;
       if (sn >= l - 1 || ss == 0.0) {
         beta = alpha;
@@ -722,6 +758,9 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
               x.y = fma(-f, vr[c].y, x.y);
               a2[32 * c] = x;
             }
+            // at most two 128-bit loads in flight per warp: 15 warps x 2 already saturate the shared-memory pipe, and a
+            // short queue keeps the latency of the owner warp's dlarfg (and of the comm warp) out of the hundreds
+            if ((c & 1) == 1) asm volatile("" ::: "memory");
           }
         } else {
           double2* a2 = reinterpret_cast<double2*>(p.B + (col0 + warp + QF_CW * j) * p.ldb + rbase);
@@ -752,9 +791,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
     }
     qf_bar(2);
 
-    unsigned live = 0;
-    double temp = 1.0;
-    bool dd = false, pend2 = false;
+    bool pend2 = false;
     while (true) {
       QF_TS(4)
       // ---- am I the owner of this CTA's candidate for step s?  (my candidate beats the 14 others) ----
@@ -771,8 +808,12 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
         const int nchv = nchtot - ((sp >= 0 ? sp : 0) >> 6);
         if (owner) { QF_DISPATCH(nchv, cand_dlarfg, sp, cand_lc) }
         QF_TS(5)
-        if (dd) refresh(temp);
-        if (pend2) { QF_DISPATCH(nchv, pass2, sp, live) }
+        if (pend2) {
+          const double temp = mycol ? stmp[mylc] : -1.0;
+          if (temp >= 0.0) refresh(temp);
+          const unsigned live = slive[warp];
+          QF_DISPATCH(nchv, pass2, sp, live)
+        }
         pend2 = false;
       }
       QF_TS(6)
@@ -790,7 +831,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
       const bool downdate = (s < lastrk - 1) && !p.nopivot;      // no pivoting: the norms are never looked at
       {
         const int nchv = nchtot - (s >> 6);
-        QF_DISPATCH(nchv, pass1, s, tau, downdate, stop == 0, live, temp, dd)
+        QF_DISPATCH(nchv, pass1, s, tau, downdate, stop == 0)
       }
       pend2 = true;
       QF_TS(8)
@@ -800,6 +841,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
       if (stop == 1) {
         // the reflector of the last executed step is applied in full (B keeps every update to the block end)
         const int nchv = nchtot - (s >> 6);
+        const unsigned live = slive[warp];
         QF_DISPATCH(nchv, pass2, s, live)
         break;
       }
@@ -811,12 +853,12 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
   // ---- epilogue: write the cached slab back, finish jpvt, report ----
   __syncthreads();
   const int nsteps = ctrl->nsteps;     // pivoted columns
-  for (int lc = warp; lc < csm; lc += QR_WARPS) {
+  for (int lc = warp; lc < csm; lc += QF_WARPS) {
     double* g = p.B + (col0 + lc) * p.ldb;
     const double* d = cache + (size_t)lc * lds;
     for (int r = lane; r < l; r += 32) g[r] = d[r];
   }
-  for (int lc = tid; lc < ncols; lc += QR_THREADS) {
+  for (int lc = tid; lc < ncols; lc += QF_THREADS) {
     int lp = lpos[lc];
     if (lp >= nsteps) p.jpvt[lp] = col0 + lc + 1;
   }
@@ -842,6 +884,8 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
 #undef ssq
 #undef sv1
 #undef srv2
+#undef stmp
+#undef slive
 #undef lpos
 #undef cache
 }
@@ -849,7 +893,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
 size_t fast_fixed_bytes(int l, int cpc, int nbe) {
   const int LV = ((l + 63) >> 6) << 6;
   const int cpe = (cpc + 1) & ~1;
-  return (size_t)2 * LV * 8 + 32 + (size_t)((nbe + 1) & ~1) * 8 + 16 * 16 + 16 * 8 + (size_t)cpe * 8 * 6 +
+  return (size_t)2 * LV * 8 + 32 + (size_t)((nbe + 1) & ~1) * 8 + 16 * 16 + 16 * 8 + 16 * 4 + (size_t)cpe * 8 * 7 +
          (size_t)((cpe + 3) & ~3) * 4 + 64;
 }
 
@@ -872,14 +916,22 @@ bool bra_qrcp_fast_plan(int l, int cpc, int nbe, size_t budget, bool aligned, in
   return true;
 }
 
-cudaError_t bra_qrcp_fast_launch(const QrcpParams& p, int G, int jw, size_t smem, cudaStream_t st) {
+template <int JW, int NMAX>
+static cudaError_t fast_launch(const QrcpParams& p, int G, size_t smem, cudaStream_t st) {
   void* args[] = {(void*)&p};
-  if (jw == 4) {
-    cudaError_t e = cudaFuncSetAttribute(qrcp_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaLaunchCooperativeKernel((void*)qrcp_fast_kernel<4>, dim3(G), dim3(QR_THREADS), args, smem, st);
-  }
-  cudaError_t e = cudaFuncSetAttribute(qrcp_fast_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(qrcp_fast_kernel<JW, NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return cudaLaunchCooperativeKernel((void*)qrcp_fast_kernel<8>, dim3(G), dim3(QR_THREADS), args, smem, st);
+  return cudaLaunchCooperativeKernel((void*)qrcp_fast_kernel<JW, NMAX>, dim3(G), dim3(QF_THREADS), args, smem, st);
+}
+
+cudaError_t bra_qrcp_fast_launch(const QrcpParams& p, int G, int jw, size_t smem, cudaStream_t st) {
+  const int nch = (p.l + 63) >> 6;
+  if (jw == 4) {
+    if (nch <= 3) return fast_launch<4, 3>(p, G, smem, st);
+    if (nch <= 5) return fast_launch<4, 5>(p, G, smem, st);
+    return fast_launch<4, 9>(p, G, smem, st);
+  }
+  if (nch <= 3) return fast_launch<8, 3>(p, G, smem, st);
+  if (nch <= 5) return fast_launch<8, 5>(p, G, smem, st);
+  return fast_launch<8, 9>(p, G, smem, st);
 }

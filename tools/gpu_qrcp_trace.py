@@ -43,3 +43,8 @@ order = np.argsort(g[:, 0])
 print("CTAs by step-top time (ns):  first 5", [(int(c), int(g[c, 0] - g0)) for c in order[:5]], " last 8", [(int(c), int(g[c, 0] - g0)) for c in order[-8:]])
 for nm, d in dur.items():
     print(f"{nm:20s} median {np.median(d):7.0f}  max {d.max():7.0f} (CTA {int(d.argmax())})   late CTAs:", [int(d[c]) for c in order[-8:]])
+# inside the owner's dlarfg: sweep done / reduction done, relative to the warp's own step top
+own = [(c, w) for c in range(G) for w in range(15) if t[c, w, 14] > 0]
+if own:
+    d1 = np.array([t[c, w, 14] - t[c, w, 4] for c, w in own]); d2 = np.array([t[c, w, 15] - t[c, w, 4] for c, w in own]); d3 = np.array([t[c, w, 5] - t[c, w, 4] for c, w in own])
+    print(f"owner warps ({len(own)}): sweep done median {np.median(d1):.0f}, +reduction {np.median(d2):.0f}, dlarfg done {np.median(d3):.0f} cycles after their step top")
