@@ -10,6 +10,7 @@
 //    CholeskyQR2, so W = (R1 R_z') Q_z' P' and the ill-conditioning lives in the k x k core M = R1 R_z'
 //    only, whose SVD is a one-sided Jacobi (Hestenes) on the graded matrix M' (accurate for small sigma).
 #include "common.cuh"
+#include "qrcp_exchange.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -255,6 +256,8 @@ struct JacobiParams {
   unsigned* bstep;     // [nblk] outer steps completed per block (zeroed before launch)
   int* rotated;        // [max_sweeps] "a rotation happened in this sweep"
   int* out;            // [0] sweeps done, [1] converged
+  LL32* mbox;          // [nblk][mbox_words] hand-over mailboxes: self-validating 32-byte words (two doubles + the step stamp)
+  size_t mbox_words;   // words per block: BC * kp / 2 (x2 with the J panel)
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
@@ -513,6 +516,54 @@ __global__ void __launch_bounds__(BC * TS, 1) jacobi_team_kernel(JacobiParams P)
       }
     }
   };
+  // hand-over through the mailbox of a block: [BC][kp] doubles of X (then of J) as LL32 words, two doubles per word
+  constexpr int NT = BC * TS;
+  const int nwx = BC * kp / 2;                          // words of the X part
+  auto send_ll = [&](int slot, int blk, unsigned ver) {
+    LL32* mb = P.mbox + (size_t)blk * P.mbox_words;
+    const double2* xs = reinterpret_cast<const double2*>(Xs + (size_t)slot * BC * kp);
+    for (int w = tid; w < nwx; w += NT) {
+      const double2 v = xs[w];
+      ll32_store2(mb + w, v.x, v.y, ver);
+    }
+    if (WJ) {
+      const double2* js = reinterpret_cast<const double2*>(Js + (size_t)slot * BC * kp);
+      for (int w = tid; w < nwx; w += NT) {
+        const double2 v = js[w];
+        ll32_store2(mb + nwx + w, v.x, v.y, ver);
+      }
+    }
+  };
+  auto fetch_ll = [&](int slot, int blk, unsigned ver) {
+    const LL32* mb = P.mbox + (size_t)blk * P.mbox_words;
+    constexpr int UB = 8;                               // words in flight per thread
+    for (int part = 0; part < (WJ ? 2 : 1); ++part) {
+      double2* dst = reinterpret_cast<double2*>((part ? Js : Xs) + (size_t)slot * BC * kp);
+      const LL32* src = mb + (part ? nwx : 0);
+      for (int w0 = tid; w0 < nwx; w0 += NT * UB) {
+        uint32_t q[UB][8];
+        unsigned pend = 0;
+#pragma unroll
+        for (int u = 0; u < UB; ++u)
+          if (w0 + u * NT < nwx) pend |= 1u << u;
+        // poll in batches: every round re-issues ALL words still pending (one L2 round trip per round, not per word)
+        uint32_t spins = 0;
+        while (pend) {
+#pragma unroll
+          for (int u = 0; u < UB; ++u)
+            if (pend & (1u << u)) ll32_ld(src + w0 + u * NT, q[u]);
+#pragma unroll
+          for (int u = 0; u < UB; ++u)
+            if ((pend & (1u << u)) && ((q[u][1] ^ ver) | (q[u][3] ^ ver) | (q[u][5] ^ ver) | (q[u][7] ^ ver)) == 0) {
+              pend &= ~(1u << u);
+              dst[w0 + u * NT] = make_double2(__hiloint2double((int)q[u][2], (int)q[u][0]),
+                                              __hiloint2double((int)q[u][6], (int)q[u][4]));
+            }
+          if (++spins > (1u << 22)) break;              // never hang the box: garbage then fails the convergence check
+        }
+      }
+    }
+  };
   auto pair_of = [&](unsigned g, int& pL, int& pR) {       // positions CTA `cta` works on at step g (pL < 0: idle)
     if ((g & 1) == 0) {
       pL = 2 * cta;
@@ -542,39 +593,34 @@ __global__ void __launch_bounds__(BC * TS, 1) jacobi_team_kernel(JacobiParams P)
         if (needL) sl = (sr == 0) ? 1 : 0;
         if (needR) sr = 1 - sl;
         if (needL || needR) {
-          if (tid < 2) {
-            // block at position p was last written after step gstep-1, or gstep-2 if it idled at an end position
-            const bool mine = (tid == 0) ? needL : needR;
-            const int pp = (tid == 0) ? pL : pR;
-            if (mine) {
-              const bool idled = (gstep > 0) && ((gstep - 1) & 1) && (pp == 0 || pp == N - 1);
-              const unsigned want = idled ? gstep - 1 : gstep;
-              const unsigned* f = P.bstep + perm[pp];
-              unsigned v;
-              do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-              } while (v < want);
+          if (gstep == 0) {
+            // first step of the factorization: the blocks come from their home in global memory (bulk copies)
+            JTICK(0)
+            if (tid == 0) {
+              // expect_tx first (the barrier cannot complete before the byte count is known), then the copies
+              uint32_t want = 0;
+              if (needL)
+                for (int c = 0; c < BC; ++c) want += (perm[pL] * BC + c < k) ? (WJ ? 2 : 1) * colbytes : 0;
+              if (needR)
+                for (int c = 0; c < BC; ++c) want += (perm[pR] * BC + c < k) ? (WJ ? 2 : 1) * colbytes : 0;
+              jmbar_expect_tx(&s_mbar, want);
+              if (needL) load_slot_bulk(sl, perm[pL]);
+              if (needR) load_slot_bulk(sr, perm[pR]);
             }
+            if (needL) zero_slot_tail(sl, perm[pL]);
+            if (needR) zero_slot_tail(sr, perm[pR]);
+            jmbar_wait(&s_mbar, mphase);
+            mphase ^= 1;
+            __syncthreads();
+            JTICK(1)
+          } else {
+            // every later step: the neighbour left the block in its mailbox as self-validating words stamped with this
+            // step -- ONE L2 hop (poll the data itself), no flag, no second round trip
+            if (needL) fetch_ll(sl, perm[pL], gstep);
+            if (needR) fetch_ll(sr, perm[pR], gstep);
+            __syncthreads();
+            JTICK(1)
           }
-          __syncthreads();
-          JTICK(0)
-          if (tid == 0) {
-            // expect_tx first (the barrier cannot complete before the byte count is known), then the copies
-            uint32_t want = 0;
-            if (needL)
-              for (int c = 0; c < BC; ++c) want += (perm[pL] * BC + c < k) ? (WJ ? 2 : 1) * colbytes : 0;
-            if (needR)
-              for (int c = 0; c < BC; ++c) want += (perm[pR] * BC + c < k) ? (WJ ? 2 : 1) * colbytes : 0;
-            jmbar_expect_tx(&s_mbar, want);
-            if (needL) load_slot_bulk(sl, perm[pL]);
-            if (needR) load_slot_bulk(sr, perm[pR]);
-          }
-          if (needL) zero_slot_tail(sl, perm[pL]);
-          if (needR) zero_slot_tail(sr, perm[pR]);
-          jmbar_wait(&s_mbar, mphase);
-          mphase ^= 1;
-          __syncthreads();
-          JTICK(1)
         }
         spos[sl] = pL;
         spos[sr] = pR;
@@ -633,23 +679,10 @@ __global__ void __launch_bounds__(BC * TS, 1) jacobi_team_kernel(JacobiParams P)
           }
         }
         if (sent[0] || sent[1]) {
-          // the rotations wrote the slots through the generic proxy: order them before the bulk (async proxy) reads
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncthreads();
-          if (tid == 0) {
 #pragma unroll
-            for (int sidx = 0; sidx < 2; ++sidx)
-              if (sent[sidx]) store_slot_bulk(sidx, sblk[sidx]);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // the global writes are complete
-#pragma unroll
-            for (int sidx = 0; sidx < 2; ++sidx)
-              if (sent[sidx]) {
-                unsigned* f = P.bstep + sblk[sidx];
-                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(f), "r"(sver[sidx]) : "memory");
-              }
-          }
-          __syncthreads();       // the slots may be refilled only after the bulk store has read them
+          for (int sidx = 0; sidx < 2; ++sidx)
+            if (sent[sidx]) send_ll(sidx, sblk[sidx], sver[sidx]);
+          __syncthreads();       // the slots may be refilled only after they have been read
         }
       }
       JTICK(3)
@@ -672,7 +705,23 @@ __global__ void __launch_bounds__(BC * TS, 1) jacobi_team_kernel(JacobiParams P)
       break;
     }
   }
-  // ---- blocks still held go home ----
+  // ---- drain: a sweep ends on an odd step, so the next step would be an even one in which CTA i works on positions
+  // 2i and 2i+1 -- every block is wanted by exactly one CTA.  Blocks this CTA does not hold sit in their mailboxes
+  // (stamp gstep); fetch them, then every block goes home. ----
+  if (gstep > 0) {
+    int pL, pR;
+    pair_of(gstep, pL, pR);
+    int sl = (spos[0] == pL) ? 0 : (spos[1] == pL ? 1 : -1);
+    int sr = (spos[0] == pR) ? 0 : (spos[1] == pR ? 1 : -1);
+    const bool needL = sl < 0, needR = sr < 0;
+    if (needL) sl = (sr == 0) ? 1 : 0;
+    if (needR) sr = 1 - sl;
+    if (needL) fetch_ll(sl, perm[pL], gstep);
+    if (needR) fetch_ll(sr, perm[pR], gstep);
+    spos[sl] = pL;
+    spos[sr] = pR;
+  }
+  // ---- blocks go home ----
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
   if (tid == 0) {
@@ -690,317 +739,6 @@ __global__ void __launch_bounds__(BC * TS, 1) jacobi_team_kernel(JacobiParams P)
     for (int i = 4; i < 8; ++i) P.out[2 + i] = 0;
   }
 #undef JTICK
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// EXPERIMENTAL (selected only with BRA_JACOBI_DSMEM=1; written after the round's GPU minutes were spent, NOT YET RUN ON
-// HARDWARE): the same odd-even block Jacobi without the J panel, with the block hand-over between ring neighbours of a
-// thread-block cluster done through distributed shared memory instead of L2.
-//
-// In the odd-even ordering a block stays exactly two steps in a CTA: at step t the pair is (old, new) with `new` the
-// block that arrived at step t and `old` the one that arrived at t-1; after the step `old` leaves -- to the LEFT
-// neighbour after even steps, to the RIGHT one after odd steps -- and the incoming block of step t+1 comes from the
-// other side.  The end blocks idle in place (CTA 0 keeps position 0 during odd steps; the last CTA does not work at odd
-// steps and keeps position N-1).
-// Slots: three per CTA.  A block arriving at step t lands in slot t mod 3 (last CTA: (t+1) mod 3, its blocks stay three
-// steps), so the consumer of step t+2 knows it sits in slot ((t+2) - 2) mod 3 of its producer: no mailbox.
-// Hand-over inside a cluster is a PULL: the producer arrives (release.cluster) on the consumer's ready[dir] mbarrier when
-// its rounds are done; the consumer copies the slot out of the producer's shared memory (ld.shared::cluster) and arrives
-// on the producer's consumed[dir] mbarrier, which frees the slot.  ready / consumed exist once per direction, so at most
-// one event is outstanding per barrier (events on one barrier are two steps apart and a neighbour cannot run two steps
-// ahead).  Neighbours in different clusters use the global-memory path of jacobi_team_kernel (bulk store + flag, poll +
-// bulk load).  The grid is padded to a multiple of the cluster size; padding CTAs only take part in the barriers.
-__device__ __forceinline__ uint32_t jc_mapa(uint32_t local, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void jc_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void jc_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(jsmem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void jc_cluster_sync() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-template <int BC, int TS, int R>
-__global__ void __launch_bounds__(BC * TS, 1) jacobi_cluster_kernel(JacobiParams P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int NS = 3, NC = NS * BC, WPT = TS / 32, RBS = WPT * 4 + 2;
-  const int k = P.k, tid = threadIdx.x, N = P.nblk, NP = N / 2, cta = blockIdx.x;
-  const int kp = (k + 1) & ~1;
-  double* Xs = reinterpret_cast<double*>(smem_raw);                    // [NC][kp]
-  double* red = Xs + (size_t)NC * kp;                                  // [2][BC][RBS]
-  int* perm = reinterpret_cast<int*>(red + (size_t)2 * BC * RBS);      // [N] block id at each position
-  __shared__ int s_rot, s_big;
-  __shared__ __align__(8) uint64_t s_mbar, s_ready[2], s_cons[2];      // [0]: left neighbour, [1]: right neighbour
-  uint32_t crank, csize;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
-  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
-  const int CS = (int)csize;
-  const bool active = cta < NP;
-  const bool has[2] = {active && cta > 0, active && cta + 1 < NP};                     // a neighbour exists
-  const bool dsm[2] = {has[0] && (cta - 1) / CS == cta / CS, has[1] && (cta + 1) / CS == cta / CS};
-  const uint32_t nrank[2] = {crank - 1u, crank + 1u};                                   // only used when dsm[d]
-  const int team = tid / TS, e = tid % TS;
-  const double tol2 = P.tol * P.tol;
-  const double thr2 = P.tol / (4.0 * k);
-  for (int i = tid; i < N; i += BC * TS) perm[i] = i;
-  uint32_t mphase = 0;
-  unsigned nready[2] = {0, 0}, ncons[2] = {0, 0};                      // events consumed per barrier
-  int sblk[NS] = {-1, -1, -1};                                         // block held by each slot (-1: none / already pulled)
-  int gone = -1;                                                       // slot whose block left at the end of the last step
-  if (tid == 0) {
-    jmbar_init(&s_mbar, 1);
-    for (int d = 0; d < 2; ++d) {
-      jmbar_init(&s_ready[d], 1);
-      jmbar_init(&s_cons[d], 1);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  const uint32_t colbytes = (uint32_t)kp * 8;
-  auto set_blk = [&](int slot, int blk) {
-#pragma unroll
-    for (int i = 0; i < NS; ++i)
-      if (i == slot) sblk[i] = blk;
-  };
-  auto get_blk = [&](int slot) {
-    int b = -1;
-#pragma unroll
-    for (int i = 0; i < NS; ++i)
-      if (i == slot) b = sblk[i];
-    return b;
-  };
-  auto load_slot_global = [&](int slot, int blk) {      // all threads call; tid 0 issues; returns after the data landed
-    if (tid == 0) {
-      uint32_t want = 0;
-      for (int c = 0; c < BC; ++c) want += (blk * BC + c < k) ? colbytes : 0;
-      jmbar_expect_tx(&s_mbar, want);
-      for (int c = 0; c < BC; ++c) {
-        const int gc = blk * BC + c;
-        if (gc < k) bulk_g2s(Xs + (size_t)(slot * BC + c) * kp, P.X + (int64_t)gc * P.ldx, colbytes, &s_mbar);
-      }
-    }
-    const int gc = blk * BC + team;
-    if (gc >= k) {
-      double* xs = Xs + (size_t)(slot * BC + team) * kp;
-      for (int r = e; r < kp; r += TS) xs[r] = 0.0;
-    }
-    jmbar_wait(&s_mbar, mphase);
-    mphase ^= 1;
-    __syncthreads();
-  };
-  auto store_slot_global = [&](int slot, int blk) {     // tid 0 only; the caller fences and waits
-    for (int c = 0; c < BC; ++c) {
-      const int gc = blk * BC + c;
-      if (gc < k) bulk_s2g(P.X + (int64_t)gc * P.ldx, Xs + (size_t)(slot * BC + c) * kp, colbytes);
-    }
-  };
-  auto pair_of = [&](unsigned g, int& pL, int& pR) {
-    if ((g & 1) == 0) {
-      pL = 2 * cta;
-      pR = 2 * cta + 1;
-    } else if (cta < NP - 1) {
-      pL = 2 * cta + 1;
-      pR = 2 * cta + 2;
-    } else {
-      pL = pR = -1;
-    }
-  };
-  __syncthreads();
-  jc_cluster_sync();                                    // every barrier of the cluster is initialised
-  unsigned epoch = 0, gstep = 0;
-  int sweep = 0, converged = 0;
-  const bool last = active && cta == NP - 1;
-  for (; sweep < P.max_sweeps; ++sweep) {
-    if (tid == 0) {
-      s_rot = 0;
-      s_big = 0;
-    }
-    bool rot_any = false;
-    for (int st = 0; st < N; ++st, ++gstep) {
-      const unsigned t = gstep;
-      int pL = -1, pR = -1;
-      if (active) pair_of(t, pL, pR);
-      if (gone >= 0) {                                  // the neighbour pulls (or has loaded) the block that left last step
-        set_blk(gone, -1);
-        gone = -1;
-      }
-      if (pL >= 0) {
-        const int s_new = last ? (int)((t + 1) % 3) : (int)(t % 3);
-        const int s_old = (int)((t + 2) % 3);           // (t - 1) mod 3
-        // at even steps the old block sits at position pR and the new one at pL; at odd steps the other way round
-        const int pos_new = (t & 1) ? pR : pL, pos_old = (t & 1) ? pL : pR;
-        if (t == 0) {
-          load_slot_global(s_old, perm[pos_old]);
-          set_blk(s_old, perm[pos_old]);
-          load_slot_global(s_new, perm[pos_new]);
-          set_blk(s_new, perm[pos_new]);
-        } else {
-          // the slot being refilled was vacated by the block that left at the end of step t-2, in direction dir(t-2):
-          // even -> left (0), odd -> right (1); a pulled block frees its slot with the consumer's arrive
-          const int dprev = (int)(t & 1);               // same parity as t-2
-          if (t >= 2 && dsm[dprev]) {
-            if (tid == 0) jc_wait_cluster(&s_cons[dprev], ncons[dprev] & 1);
-            ncons[dprev]++;
-          }
-          // incoming: from the right neighbour at odd steps, from the left one at even steps; CTA 0 at even steps takes
-          // back its idling end block, which already sits in slot t mod 3
-          const int din = (t & 1) ? 1 : 0;
-          if (has[din]) {
-            if (dsm[din]) {
-              if (tid == 0) jc_wait_cluster(&s_ready[din], nready[din] & 1);
-              nready[din]++;
-              __syncthreads();
-              asm volatile("fence.acq_rel.cluster;" ::: "memory");
-              const uint32_t src = jc_mapa(jsmem_u32(Xs + (size_t)(((t + 1) % 3) * BC) * kp), nrank[din]);   // slot (t-2) mod 3
-              double* dst = Xs + (size_t)(s_new * BC) * kp;
-              for (int i = 2 * tid; i < BC * kp; i += 2 * BC * TS) {
-                double a, c;
-                asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(c) : "r"(src + 8u * (uint32_t)i) : "memory");
-                dst[i] = a;
-                dst[i + 1] = c;
-              }
-              __syncthreads();
-              if (tid == 0) jc_arrive_remote(jc_mapa(jsmem_u32(&s_cons[1 - din]), nrank[din]));   // I am its neighbour on the other side
-            } else {
-              if (tid == 0) {
-                const unsigned* f = P.bstep + perm[pos_new];
-                unsigned v;
-                do {
-                  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-                } while (v < t);
-              }
-              __syncthreads();
-              load_slot_global(s_new, perm[pos_new]);
-            }
-            set_blk(s_new, perm[pos_new]);
-          }
-        }
-        const int offL = ((t & 1) ? s_old : s_new) * BC, offR = ((t & 1) ? s_new : s_old) * BC;
-        int par = 0;
-        if (st == 0 && BC > 1) {
-          for (int rd = 0; rd < BC - 1; ++rd, par ^= 1) {
-            int p, q;
-            rr_pair(BC, rd, team % (BC / 2 > 0 ? BC / 2 : 1), p, q);
-            const int off = (team < BC / 2) ? offL : offR;
-            rot_any |= rotate_pair<TS, R, false>(Xs, Xs, kp, k, off + p, off + q, team, e,
-                                                 red + (size_t)(par * BC + team) * RBS, tol2, thr2, &s_big);
-            __syncthreads();
-          }
-        }
-        for (int rd = 0; rd < BC; ++rd, par ^= 1) {
-          const int p = offL + team, q = offR + ((team + rd) % BC);
-          rot_any |= rotate_pair<TS, R, false>(Xs, Xs, kp, k, p, q, team, e, red + (size_t)(par * BC + team) * RBS, tol2,
-                                               thr2, &s_big);
-          __syncthreads();
-        }
-      }
-      // every CTA replays the whole permutation
-      {
-        const int npairs = ((gstep & 1) == 0) ? NP : NP - 1, o = (int)(gstep & 1);
-        for (int i = tid; i < npairs; i += BC * TS) {
-          const int t0 = perm[2 * i + o];
-          perm[2 * i + o] = perm[2 * i + o + 1];
-          perm[2 * i + o + 1] = t0;
-        }
-      }
-      __syncthreads();
-      // ---- hand over the old block: left after even steps, right after odd ones (the end blocks idle in place) ----
-      if (pL >= 0) {
-        const int dout = (t & 1) ? 1 : 0;
-        const int s_old = (int)((t + 2) % 3);
-        if (has[dout]) {
-          if (dsm[dout]) {
-            if (tid == 0) {
-              asm volatile("fence.acq_rel.cluster;" ::: "memory");
-              jc_arrive_remote(jc_mapa(jsmem_u32(&s_ready[1 - dout]), nrank[dout]));
-            }
-            gone = s_old;                               // stays readable until the consumer's arrive (waited at step t+2)
-          } else {
-            const int blk = get_blk(s_old);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncthreads();
-            if (tid == 0) {
-              store_slot_global(s_old, blk);
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-              asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-              unsigned* f = P.bstep + blk;
-              asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(f), "r"(t + 1u) : "memory");
-            }
-            __syncthreads();
-            set_blk(s_old, -1);                         // the block is home
-          }
-        }
-      }
-    }
-    // ---- convergence vote (as in jacobi_team_kernel) ----
-    if (rot_any) s_rot = 1;
-    __syncthreads();
-    if (tid == 0 && s_rot) atomicExch(P.rotated + sweep, 1);
-    if (tid == 0 && s_big) atomicExch(P.rotated + P.max_sweeps + sweep, 1);
-    ++epoch;
-    grid_barrier(P.bar, epoch * gridDim.x);
-    int any, big;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(any) : "l"(P.rotated + sweep) : "memory");
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(big) : "l"(P.rotated + P.max_sweeps + sweep) : "memory");
-    if (!any || !big) {
-      converged = 1;
-      ++sweep;
-      break;
-    }
-  }
-  // ---- every block goes home from the CTA that worked on it last (a block signalled at the very last step was never
-  // pulled: it is still here and still marked) ----
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncthreads();
-  if (tid == 0) {
-#pragma unroll
-    for (int sidx = 0; sidx < NS; ++sidx)
-      if (sblk[sidx] >= 0) store_slot_global(sidx, sblk[sidx]);
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  }
-  if (cta == NP / 2 && tid == 0) {
-    P.out[0] = sweep;
-    P.out[1] = converged;
-    for (int i = 2; i < 10; ++i) P.out[i] = 0;
-  }
-  jc_cluster_sync();                                    // nobody exits while a neighbour may still read its slots
-}
-
-template <int BC, int TS, int R>
-cudaError_t launch_jacobi_cluster(const JacobiParams& P, int grid, int cluster, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(jacobi_cluster_kernel<BC, TS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(BC * TS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute at[2];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = (unsigned)cluster;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  at[1].id = cudaLaunchAttributeCooperative;
-  at[1].val.cooperative = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 2;
-  return cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<BC, TS, R>, P);
 }
 
 template <int BC, int TS, int R, bool WJ = true>
@@ -1228,9 +966,11 @@ int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64
     }
     const int grid = nblk / 2;
     const size_t smem = need(bc);
-    const size_t wbytes = 1024 + (size_t)2 * MAX_SWEEPS * 4 + (size_t)nblk * 4;
+    const size_t wbytes0 = ((1024 + (size_t)2 * MAX_SWEEPS * 4 + (size_t)nblk * 4) + 255) & ~size_t(255);
+    const size_t mbox_words = (size_t)bc * kp / 2 * (noj ? 1 : 2);
+    const size_t wbytes = wbytes0 + (size_t)nblk * mbox_words * sizeof(LL32);
     BRA_CUDA(ctx->jwork.reserve(wbytes));
-    BRA_CUDA(cudaMemsetAsync(ctx->jwork.p, 0, wbytes, ctx->stream));
+    BRA_CUDA(cudaMemsetAsync(ctx->jwork.p, 0, wbytes, ctx->stream));      // stamps 0 are invalid: the steps count from 1
     JacobiParams P;
     P.k = k;
     P.nblk = nblk;
@@ -1244,6 +984,8 @@ int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64
     P.out = ctx->jwork.as<int>() + 16;
     P.rotated = ctx->jwork.as<int>() + 64;
     P.bstep = ctx->jwork.as<unsigned>() + 256 + 2 * MAX_SWEEPS;
+    P.mbox = reinterpret_cast<LL32*>(reinterpret_cast<unsigned char*>(ctx->jwork.p) + wbytes0);
+    P.mbox_words = mbox_words;
     cudaError_t e = cudaErrorInvalidValue;
 #define JL(B_, T_, R_) if (bc == B_ && ts == T_ && rr == R_ && !noj) e = launch_jacobi<B_, T_, R_>(P, grid, smem, ctx->stream);
 #define JN(B_, T_) if (bc == B_ && ts == T_ && noj && rr == 8) e = launch_jacobi<B_, T_, 8, false>(P, grid, smem, ctx->stream);
@@ -1255,16 +997,6 @@ int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64
     JL(1, 1024, 4)
     JL(8, 32, 8) JL(4, 32, 8) JL(8, 64, 8) JL(4, 64, 8) JL(8, 128, 8) JL(4, 128, 8)
     JN(8, 32) JN(4, 32) JN(8, 64) JN(4, 64) JN(8, 128) JN(4, 128)
-    const char* dsmem_env = getenv("BRA_JACOBI_DSMEM");
-    if (noj && rr == 16 && bc == 4 && dsmem_env && atoi(dsmem_env) > 0) {
-      // experimental cluster / DSMEM hand-over (see jacobi_cluster_kernel): grid padded to a multiple of the cluster size
-      int cl = 8;
-      if (const char* ev = getenv("BRA_JACOBI_CLUSTER")) {
-        const int v = atoi(ev);
-        if (v == 2 || v == 4 || v == 8) cl = v;
-      }
-      e = launch_jacobi_cluster<4, 32, 16>(P, ((grid + cl - 1) / cl) * cl, cl, smem, ctx->stream);
-    } else
     if (noj && rr == 16 && bc == 4) e = launch_jacobi<4, 32, 16, false>(P, grid, smem, ctx->stream);
     if (noj && rr == 16 && bc == 8) e = launch_jacobi<8, 32, 16, false>(P, grid, smem, ctx->stream);
 #undef JL
