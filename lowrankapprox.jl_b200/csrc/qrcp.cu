@@ -702,7 +702,7 @@ int bra_qrcp_run(bra_ctx* ctx, double* B, int64_t ldb, int l, int64_t n, int kca
     p.lds = lds_f;
     p.csm = csm_f;
     p.meta_smem = 1;
-    p.fast = 1;
+    p.fast = getenv("BRA_QRCP_NOTMEM") ? 1 : 2;      // 2: the slab lives in tensor memory first
     e = bra_qrcp_fast_launch(p, G, jw, smem_f, ctx->stream);
   } else if (l <= 64) e = launch_qrcp<2>(p, G, smem, ctx->stream);
   else if (l <= 96) e = launch_qrcp<3>(p, G, smem, ctx->stream);

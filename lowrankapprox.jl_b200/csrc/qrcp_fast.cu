@@ -22,6 +22,7 @@
 //     (double buffered: it runs ahead of pass 2) and stores the winner column in LAPACK layout.
 //   Two named barriers per step; shared arrays are addressed by 32-bit offsets (no generic pointers in registers).
 #include "common.cuh"
+#include <cstdlib>
 #include <type_traits>
 #include "qrcp_common.cuh"
 #include "qrcp_exchange.cuh"
@@ -65,6 +66,33 @@ __device__ __forceinline__ int warp_argmax_key(long long key, int lp) {
   const int mlp = __reduce_min_sync(0xffffffffu, c2 ? lp : 0x7fffffff);
   return __ffs(__ballot_sync(0xffffffffu, c2 && lp == mlp)) - 1;
 }
+
+// ---- tensor memory as the home of the slab.  Measured on B200 (tools/tmem_probe.cu): tcgen05.ld 32x32b streams at
+// ~810 B/clk/SM and tcgen05.st at ~750 B/clk/SM with 16 warps -- six times the 128 B/clk of shared memory -- on a pipe
+// of its own (LDS and TMEM loads overlap fully), 23 cycles dependent-load latency, 256 KB per SM.  A warp reaches the 32
+// TMEM lanes of its quadrant (warp % 4); thread t of the warp owns lane t, so "lane owns rows (64 c + 2 lane, +1)" maps
+// one 64-row chunk of a column onto 4 consecutive 32-bit TMEM columns (x4 shape: two doubles per thread). ----
+__device__ __forceinline__ void tm_ld2(uint32_t taddr, double2& x) {
+  uint32_t r0, r1, r2, r3;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(taddr)
+               : "memory");
+  // NOTE: valid only after tm_wait_ld(); the conversions below are register pairings, scheduled after the wait by the
+  // volatile ordering of the two asm statements
+  x.x = __hiloint2double((int)r1, (int)r0);
+  x.y = __hiloint2double((int)r3, (int)r2);
+}
+__device__ __forceinline__ void tm_st2(uint32_t taddr, const double2 x) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"((uint32_t)__double2loint(x.x)),
+               "r"((uint32_t)__double2hiint(x.x)), "r"((uint32_t)__double2loint(x.y)), "r"((uint32_t)__double2hiint(x.y))
+               : "memory");
+}
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// TMEM columns of a compute warp: quadrants 0-2 are shared by four compute warps (128 columns each), quadrant 3 by three
+// (the comm warp keeps no columns): 168 each
+__host__ __device__ __forceinline__ int qf_twin(int warp) { return (warp & 3) < 3 ? 128 : 168; }
 
 #ifdef BRA_QRCP_TRACE
 __device__ __forceinline__ long long qf_gtime() {
@@ -155,39 +183,74 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
     ctrl->fail = 0;
   }
 
-  // ---- prologue: stage the slab, initial column norms (src/pqr.jl:376-385) ----
-  for (int lc = warp; lc < ncols; lc += QF_WARPS) {
-    const double* g = p.B + (col0 + lc) * p.ldb;
-    double amax = 0.0;
-    for (int r = lane; r < l; r += 32) {
-      double x = g[r];
-      if (lc < csm) cache[(size_t)lc * lds + r] = x;
-      amax = fmax(amax, fabs(x));
+  // ---- tensor memory: all 512 columns, allocated (and released at the end) by the comm warp ----
+  __shared__ uint32_t s_tbase;
+  if (warp == QF_CW) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(&s_tbase))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tbase = s_tbase;
+
+  // ---- where column j of compute warp w lives: class 0 = tensor memory (the first tcap columns of every warp),
+  //      class 1 = shared memory slot (j - tcap) * 15 + w while slots last, class 2 = global memory (L2) ----
+  const int tchunk = 4 * nchtot;                       // TMEM columns per slab column
+  auto tcap_of = [&](int w) { return p.fast >= 2 ? qf_twin(w) / tchunk : 0; };
+  auto tm_col = [&](int w, int j) -> uint32_t {        // TMEM address of chunk 0 of column j of warp w
+    return tbase + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(qf_twin(w) * (w >> 2) + j * tchunk);
+  };
+  auto class_of = [&](int w, int j, int& slot) -> int {
+    const int tc = tcap_of(w);
+    if (j < tc) {
+      slot = j;
+      return 0;
     }
-    if (lc < csm && lane == 0 && lds > l) cache[(size_t)lc * lds + l] = 0.0;
+    slot = (j - tc) * QF_CW + w;
+    return slot < p.csm ? 1 : 2;
+  };
+
+  // ---- prologue: every compute warp stages its own columns (only the owner reaches its TMEM lanes) and takes the
+  //      initial column norms (src/pqr.jl:376-385) ----
+  if (warp < QF_CW) {
+    for (int j = 0; warp + QF_CW * j < ncols; ++j) {
+      const int lc = warp + QF_CW * j;
+      const double* g = p.B + (col0 + lc) * p.ldb;
+      int slot;
+      const int cls = class_of(warp, j, slot);
+      double amax = 0.0;
+      for (int r = lane; r < l; r += 32) amax = fmax(amax, fabs(g[r]));
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-    double nrm = 0.0;
-    if (amax > 0.0) {
+      for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
       // exact power-of-two scaling: same rounding as the unscaled sum, no overflow/underflow
-      int e = ilogb(amax);
-      double sc = scalbn(1.0, -e);
+      const int e = amax > 0.0 ? ilogb(amax) : 0;
+      const double sc = scalbn(1.0, -e);
       double ss = 0.0;
-      for (int r = lane; r < l; r += 32) {
-        double x = g[r] * sc;
-        ss = fma(x, x, ss);
+      for (int c = 0; c < nchtot; ++c) {
+        const int r = 64 * c + 2 * lane;
+        double2 x;
+        x.x = r < l ? g[r] : 0.0;
+        x.y = r + 1 < l ? g[r + 1] : 0.0;
+        ss = fma(x.x * sc, x.x * sc, ss);
+        ss = fma(x.y * sc, x.y * sc, ss);
+        if (cls == 0) tm_st2(tm_col(warp, j) + 4 * c, x);
+        else if (cls == 1 && r < lds) *reinterpret_cast<double2*>(cache + (size_t)slot * lds + r) = x;
       }
       ss = warp_sum(ss);
-      nrm = scalbn(sqrt(ss), e);
+      const double nrm = amax > 0.0 ? scalbn(sqrt(ss), e) : 0.0;
+      if (lane == 0) {
+        const double rn = nrm != 0.0 ? 1.0 / nrm : 0.0;
+        st2[lc] = make_double2(rn, 1.0);
+        ssq[lc] = nrm * nrm;
+        sv1[lc] = nrm;
+        srv2[lc] = rn;
+        lpos[lc] = (int)(col0 + lc);
+      }
     }
-    if (lane == 0) {
-      const double rn = nrm != 0.0 ? 1.0 / nrm : 0.0;
-      st2[lc] = make_double2(rn, 1.0);
-      ssq[lc] = nrm * nrm;
-      sv1[lc] = nrm;
-      srv2[lc] = rn;
-      lpos[lc] = (int)(col0 + lc);
-    }
+    tm_wait_st();
   }
   __syncthreads();
 
@@ -242,10 +305,13 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
       if (r + 1 >= l) v.y = 0.0;
       *reinterpret_cast<double2*>(vbuf + par * LV + r) = v;
       if (isw) {
+        // the pivot column in LAPACK layout: into its shared-memory slot, or straight to its final place in global
+        // memory when it lives in tensor memory (only its owner warp could write it there) or in L2
         const double beta = __hiloint2double((int)hb[2], (int)hb[0]);
         const int wlc = (int)((int)hp[0] - col0);
-        const bool wsm = wlc < csm;
-        double* wa = wsm ? cache + (size_t)wlc * lds : p.B + (col0 + wlc) * p.ldb;
+        int wslot;
+        const bool wsm = class_of(wlc % QF_CW, wlc / QF_CW, wslot) == 1;
+        double* wa = wsm ? cache + (size_t)wslot * lds : p.B + (col0 + wlc) * p.ldb;
         if (r >= s) {
           const double x0 = r == s ? beta : v.x;
           if (wsm) wa[r] = x0;
@@ -478,12 +544,61 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
   } else {
     // ================================= COMPUTE warps =================================
     const int jtot = ncols > warp ? min(JW, (ncols - warp + QF_CW - 1) / QF_CW) : 0;   // this warp's columns lc = warp + 15 j
-    const int jsm = csm > warp ? min(jtot, (csm - warp + QF_CW - 1) / QF_CW) : 0;      // ... of which in shared memory
     const bool mycol = lane < jtot;                                                     // lane j < jtot <-> column j
     const int mylc = mycol ? warp + QF_CW * lane : 0;
+    const int tcap = tcap_of(warp);                                                     // columns j < tcap: tensor memory
+    const uint32_t tcol0 = tm_col(warp, 0);
 #ifdef BRA_QRCP_TRACE
     long long tlast = clock64();
 #endif
+    // residency of my column j (warp-uniform): 0 TMEM, 1 shared memory, 2 L2
+    auto cls_of = [&](int j) { return j < tcap ? 0 : ((j - tcap) * QF_CW + warp < p.csm ? 1 : 2); };
+    auto sm_col = [&](int j) -> double* { return cache + (size_t)((j - tcap) * QF_CW + warp) * lds; };
+    auto gl_col = [&](int j) -> double* { return p.B + (col0 + warp + QF_CW * j) * p.ldb; };
+    // chunks i0 .. i0+NCH-1 of my column j: lane gets rows (64 (i0 + c) + 2 lane, +1).  Rows >= l read as zero.
+    auto load_col = [&](auto tag, const int j, const int cls, const int i0, double2* x) {
+      constexpr int NCH = decltype(tag)::value;
+      const int rbase = (i0 << 6) + 2 * lane;
+      if (cls == 0) {
+        const uint32_t ta = tcol0 + (uint32_t)(j * tchunk + 4 * i0);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) tm_ld2(ta + 4 * c, x[c]);
+        tm_wait_ld();
+      } else if (cls == 1) {
+        const double2* a2 = reinterpret_cast<const double2*>(sm_col(j) + rbase);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          x[c] = make_double2(0.0, 0.0);
+          if (c < NCH - 1 || rbase + 64 * c < l) x[c] = a2[32 * c];
+        }
+      } else {
+        const double2* a2 = reinterpret_cast<const double2*>(gl_col(j) + rbase);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          x[c] = make_double2(0.0, 0.0);
+          if (c < NCH - 1 || rbase + 64 * c < l) x[c] = __ldcg(a2 + 32 * c);
+        }
+      }
+    };
+    auto store_col = [&](auto tag, const int j, const int cls, const int i0, const double2* x) {
+      constexpr int NCH = decltype(tag)::value;
+      const int rbase = (i0 << 6) + 2 * lane;
+      if (cls == 0) {
+        const uint32_t ta = tcol0 + (uint32_t)(j * tchunk + 4 * i0);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) tm_st2(ta + 4 * c, x[c]);
+      } else if (cls == 1) {
+        double2* a2 = reinterpret_cast<double2*>(sm_col(j) + rbase);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+          if (c < NCH - 1 || rbase + 64 * c < l) a2[32 * c] = x[c];
+      } else {
+        double2* a2 = reinterpret_cast<double2*>(gl_col(j) + rbase);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+          if (c < NCH - 1 || rbase + 64 * c < l) __stcg(a2 + 32 * c, x[c]);
+      }
+    };
 
     // warp candidate -> slot
     auto publish = [&](long long key, int lp, int ps, int flag) {
@@ -502,12 +617,12 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
       }
     };
 
-    // ---- pass 1 of step s.  Out: live mask (bit j: column j takes part in step s), and for lane j the downdate
-    //      factor temp with dd = "refresh my column's norm state after the candidate is out" ----
+    // ---- pass 1 of step s: dots, f_j, pivot-row entry, norm downdate, candidate for step s + 1 ----
     auto pass1 = [&](auto tag, const int s, const double tau, const bool downdate, const bool want_cand) {
       constexpr int NCH = decltype(tag)::value;
       const int par = s & 1;
-      const int rbase = ((s >> 6) << 6) + 2 * lane;
+      const int i0 = s >> 6;
+      const int rbase = (i0 << 6) + 2 * lane;
       double2 vr[NCH];
       {
         const double2* v2 = reinterpret_cast<const double2*>(vbuf + par * LV + rbase);
@@ -520,11 +635,10 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
       const double sq = ssq[mylc];
       const unsigned live = __ballot_sync(0xffffffffu, qpos > s);
       if (lane == 0) slive[warp] = live;
-      double myas = 0.0;
-      if (mycol) myas = lane < jsm ? cache[(size_t)mylc * lds + s] : __ldcg(p.B + (col0 + mylc) * p.ldb + s);
+      const int ls = (s & 63) >> 1;           // the lane that holds row s (first live chunk), component s & 1
 
-      // dots, four columns per packed butterfly; L2-resident columns (the highest j) issue their loads first
-      double fmine = 0.0;
+      // dots, four columns per packed butterfly; the slowest residency class (the highest j) goes first
+      double fmine = 0.0, myas = 0.0;
 #pragma unroll
       for (int b = JW / 4 - 1; b >= 0; --b) {
         double dot[4];
@@ -532,24 +646,17 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
         for (int cc = 3; cc >= 0; --cc) {
           const int j = 4 * b + cc;
           double d0 = 0.0, d1 = 0.0;
-          if (j < jsm) {                          // warp-uniform
-            const double2* a2 = reinterpret_cast<const double2*>(cache + (size_t)(warp + QF_CW * j) * lds + rbase);
+          if (j < jtot) {                         // warp-uniform
+            double2 x[NCH];
+            load_col(tag, j, cls_of(j), i0, x);
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-              double2 x = make_double2(0.0, 0.0);
-              if (c < NCH - 1 || rbase + 64 * c < l) x = a2[32 * c];
-              d0 = fma(x.x, vr[c].x, d0);
-              d1 = fma(x.y, vr[c].y, d1);
+              d0 = fma(x[c].x, vr[c].x, d0);
+              d1 = fma(x[c].y, vr[c].y, d1);
             }
-          } else if (j < jtot) {
-            const double2* a2 = reinterpret_cast<const double2*>(p.B + (col0 + warp + QF_CW * j) * p.ldb + rbase);
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-              double2 x = make_double2(0.0, 0.0);
-              if (c < NCH - 1 || rbase + 64 * c < l) x = __ldcg(a2 + 32 * c);
-              d0 = fma(x.x, vr[c].x, d0);
-              d1 = fma(x.y, vr[c].y, d1);
-            }
+            // a_j[s] sits in lane ls of the first chunk; lane j keeps it
+            const double asj = __shfl_sync(0xffffffffu, (s & 1) ? x[0].y : x[0].x, ls);
+            if (lane == j) myas = asj;
           }
           dot[cc] = d0 + d1;
         }
@@ -601,29 +708,26 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
         const int lc = warp + QF_CW * fl;
         __syncwarp();
         const double f = fbuf[lc];
-        const double* vb = vbuf + par * LV;
+        const int cls = cls_of(fl);
+        double2 x[NCH];
+        load_col(tag, fl, cls, i0, x);
         double ss2 = 0.0;
-        if (fl < jsm) {
-          double* a = cache + (size_t)lc * lds;
-          for (int r = s + lane; r < l; r += 32) {
-            const double x = fma(-f, vb[r], a[r]);
-            a[r] = x;
-            if (r > s) ss2 = fma(x, x, ss2);
-          }
-        } else {
-          double* a = p.B + (col0 + lc) * p.ldb;
-          for (int r = s + lane; r < l; r += 32) {
-            const double x = fma(-f, vb[r], __ldcg(a + r));
-            __stcg(a + r, x);
-            if (r > s) ss2 = fma(x, x, ss2);
-          }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int r = rbase + 64 * c;
+          x[c].x = fma(-f, vr[c].x, x[c].x);
+          x[c].y = fma(-f, vr[c].y, x[c].y);
+          if (r > s) ss2 = fma(x[c].x, x[c].x, ss2);
+          if (r + 1 > s) ss2 = fma(x[c].y, x[c].y, ss2);
         }
+        store_col(tag, fl, cls, i0, x);
         ss2 = warp_sum(ss2);
         __syncwarp();
         const double nn = sqrt(ss2);
         if (lane == fl) {
           const double rn = nn != 0.0 ? 1.0 / nn : 0.0;
           key = __double_as_longlong(nn * nn);
+          temp = -1.0;
           st2[lc] = make_double2(rn, 1.0);
           ssq[lc] = nn * nn;
           sv1[lc] = nn;
@@ -631,6 +735,7 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
           fbuf[lc] = 0.0;
         }
       }
+      if (wflag) tm_wait_st();
       if (mycol) stmp[mylc] = temp;
       if (want_cand) publish(key, lp, ps, wflag);
     };
@@ -652,59 +757,42 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
       const int sn = sp + 1;
       const uint32_t stamp = p.epoch + (uint32_t)sn;
       LL16* myrec = p.rec + ((size_t)(sn & 1) * G + cta) * recs + RECH;
-      const bool insm = cand_lc < csm;
+      const int cj = cand_lc / QF_CW;           // my column index of the candidate
+      const int cls = cls_of(cj);
       double f = 0.0;
       if (sp >= 0) {
         f = fbuf[cand_lc];
         __syncwarp();
         if (lane == 0) fbuf[cand_lc] = 0.0;
       }
-      const int rb = ((sp >= 0 ? sp : 0) >> 6) << 6;
+      const int i0 = (sp >= 0 ? sp : 0) >> 6;
+      const int rb = i0 << 6;
       const int rbase = rb + 2 * lane;
       double ss = 0.0, al = 0.0;
-      // two separate code paths (not one generic pointer): the shared-memory column must compile to LDS/STS
-      auto sweep = [&](auto smtag) {
-        constexpr bool SM = decltype(smtag)::value;
-        double2* a2 = reinterpret_cast<double2*>((SM ? cache + (size_t)cand_lc * lds : p.B + (col0 + cand_lc) * p.ldb) + rbase);
+      double2 x[NCH];
+      load_col(tag, cj, cls, i0, x);
+      if (f != 0.0) {
         const double2* v2 = reinterpret_cast<const double2*>(vbuf + (sp & 1) * LV + rbase);
-        // every load before the first store: the shared-memory pipe is saturated by the other warps' pass 2, and a
-        // load behind a (possibly aliasing) store would pay the full queueing delay once per chunk
-        double2 x[NCH], v[NCH];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          x[c] = make_double2(0.0, 0.0);
-          v[c] = make_double2(0.0, 0.0);
-          if (c < NCH - 1 || rbase + 64 * c < l) {
-            x[c] = SM ? a2[32 * c] : __ldcg(a2 + 32 * c);
-            v[c] = v2[32 * c];
-          }
+          const double2 v = v2[32 * c];
+          x[c].x = fma(-f, v.x, x[c].x);
+          x[c].y = fma(-f, v.y, x[c].y);
         }
-        if (f != 0.0) {
+        store_col(tag, cj, cls, i0, x);
+      }
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            if (c < NCH - 1 || rbase + 64 * c < l) {
-              x[c].x = fma(-f, v[c].x, x[c].x);
-              x[c].y = fma(-f, v[c].y, x[c].y);
-              if (SM) a2[32 * c] = x[c];
-              else __stcg(a2 + 32 * c, x[c]);
-            }
-          }
+      for (int c = 0; c < NCH; ++c) {
+        const int r = rbase + 64 * c;
+        if (c < NCH - 1 || r < l) {
+          // rows (r, r+1) are two adjacent LL words: one 32-byte store (rows <= sn are never read)
+          if (r + 1 > sn) ll32_store2(reinterpret_cast<LL32*>(myrec + r), x[c].x, x[c].y, stamp);
+          if (r == sn) al = x[c].x;
+          if (r + 1 == sn) al = x[c].y;
+          if (r > sn) ss = fma(x[c].x, x[c].x, ss);
+          if (r + 1 > sn && r + 1 < l) ss = fma(x[c].y, x[c].y, ss);
         }
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const int r = rbase + 64 * c;
-          if (c < NCH - 1 || r < l) {
-            // rows (r, r+1) are two adjacent LL words: one 32-byte store (rows <= sn are never read)
-            if (r + 1 > sn) ll32_store2(reinterpret_cast<LL32*>(myrec + r), x[c].x, x[c].y, stamp);
-            if (r == sn) al = x[c].x;
-            if (r + 1 == sn) al = x[c].y;
-            if (r > sn) ss = fma(x[c].x, x[c].x, ss);
-            if (r + 1 > sn && r + 1 < l) ss = fma(x[c].y, x[c].y, ss);
-          }
-        }
-      };
-      if (insm) sweep(std::true_type{});
-      else sweep(std::false_type{});
+      }
       if (sn >= l) return;
 #ifdef BRA_QRCP_TRACE
       if (p.ts && lane == 0 && sn == p.ts_step) p.ts[((size_t)cta * QR_WARPS + warp) * 16 + 14] = clock64();
@@ -734,7 +822,8 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
     // ---- pass 2 of step sp: a_j -= f_j v on every live column that still carries a non-zero f ----
     auto pass2 = [&](auto tag, const int sp, const unsigned live) {
       constexpr int NCH = decltype(tag)::value;
-      const int rbase = ((sp >> 6) << 6) + 2 * lane;
+      const int i0 = sp >> 6;
+      const int rbase = (i0 << 6) + 2 * lane;
       double2 vr[NCH];
       {
         const double2* v2 = reinterpret_cast<const double2*>(vbuf + (sp & 1) * LV + rbase);
@@ -748,33 +837,17 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
       for (int j = JW - 1; j >= 0; --j) {
         const double f = fj[j];
         if (f == 0.0) continue;               // warp-uniform: dead, flagged (done in pass 1) or the candidate (done)
-        if (j < jsm) {
-          double2* a2 = reinterpret_cast<double2*>(cache + (size_t)(warp + QF_CW * j) * lds + rbase);
+        const int cls = cls_of(j);
+        double2 x[NCH];
+        load_col(tag, j, cls, i0, x);
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            if (c < NCH - 1 || rbase + 64 * c < l) {
-              double2 x = a2[32 * c];
-              x.x = fma(-f, vr[c].x, x.x);
-              x.y = fma(-f, vr[c].y, x.y);
-              a2[32 * c] = x;
-            }
-            // at most two 128-bit loads in flight per warp: 15 warps x 2 already saturate the shared-memory pipe, and a
-            // short queue keeps the latency of the owner warp's dlarfg (and of the comm warp) out of the hundreds
-            if ((c & 1) == 1) asm volatile("" ::: "memory");
-          }
-        } else {
-          double2* a2 = reinterpret_cast<double2*>(p.B + (col0 + warp + QF_CW * j) * p.ldb + rbase);
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            if (c < NCH - 1 || rbase + 64 * c < l) {
-              double2 x = __ldcg(a2 + 32 * c);
-              x.x = fma(-f, vr[c].x, x.x);
-              x.y = fma(-f, vr[c].y, x.y);
-              __stcg(a2 + 32 * c, x);
-            }
-          }
+        for (int c = 0; c < NCH; ++c) {
+          x[c].x = fma(-f, vr[c].x, x[c].x);
+          x[c].y = fma(-f, vr[c].y, x[c].y);
         }
+        store_col(tag, j, cls, i0, x);
       }
+      tm_wait_st();
     };
 
     // candidates for step 0: the initial norms themselves (step-0 keys are norms, later keys squared norms: keys are
@@ -806,7 +879,10 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
         const bool owner = cand_lc >= 0 && !__any_sync(0xffffffffu, better);
         const int sp = s - 1;
         const int nchv = nchtot - ((sp >= 0 ? sp : 0) >> 6);
-        if (owner) { QF_DISPATCH(nchv, cand_dlarfg, sp, cand_lc) }
+        if (owner) {
+          QF_DISPATCH(nchv, cand_dlarfg, sp, cand_lc)
+          tm_wait_st();
+        }
         QF_TS(5)
         if (pend2) {
           const double temp = mycol ? stmp[mylc] : -1.0;
@@ -850,13 +926,32 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
     }
   }
 
-  // ---- epilogue: write the cached slab back, finish jpvt, report ----
+  // ---- epilogue: the slab goes back to global memory (every warp its own columns), jpvt is completed ----
   __syncthreads();
   const int nsteps = ctrl->nsteps;     // pivoted columns
-  for (int lc = warp; lc < csm; lc += QF_WARPS) {
-    double* g = p.B + (col0 + lc) * p.ldb;
-    const double* d = cache + (size_t)lc * lds;
-    for (int r = lane; r < l; r += 32) g[r] = d[r];
+  if (warp < QF_CW) {
+    for (int j = 0; warp + QF_CW * j < ncols; ++j) {
+      const int lc = warp + QF_CW * j;
+      double* g = p.B + (col0 + lc) * p.ldb;
+      int slot;
+      const int cls = class_of(warp, j, slot);
+      if (cls == 0) {
+        // a pivoted column was stored from its pivot row down when it was chosen (fetch_chunk): only R above it is here
+        const int lp = lpos[lc];
+        const int rlim = lp < nsteps ? lp : l;
+        for (int c = 0; c < nchtot && 64 * c < rlim; ++c) {
+          double2 x;
+          tm_ld2(tm_col(warp, j) + 4 * c, x);
+          tm_wait_ld();
+          const int r = 64 * c + 2 * lane;
+          if (r < rlim) g[r] = x.x;
+          if (r + 1 < rlim) g[r + 1] = x.y;
+        }
+      } else if (cls == 1) {
+        const double* d = cache + (size_t)slot * lds;
+        for (int r = lane; r < l; r += 32) g[r] = d[r];
+      }
+    }
   }
   for (int lc = tid; lc < ncols; lc += QF_THREADS) {
     int lp = lpos[lc];
@@ -874,6 +969,8 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
   if (tid == 0 && p.dbg)
     for (int i = 0; i < 5; ++i) p.dbg[cta * 8 + i] = (int)(s_tph[i] >> 10);
 #endif
+  __syncthreads();
+  if (warp == QF_CW) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase) : "memory");
 #undef vbuf
 #undef ctrl
 #undef rdblk
@@ -904,11 +1001,18 @@ size_t fast_fixed_bytes(int l, int cpc, int nbe) {
 bool bra_qrcp_fast_plan(int l, int cpc, int nbe, size_t budget, bool aligned, int* jw, int* lds, int* csm, size_t* smem) {
   if (l > 64 * QF_MAXCH || cpc > QF_CW * 8) return false;
   const int ld = (l + 1) & ~1;
+  const int nch = (l + 63) >> 6;
   const size_t fixed = fast_fixed_bytes(l, cpc, nbe);
-  if (fixed + (size_t)ld * 8 > budget) return false;
+  if (fixed > budget) return false;
+  // columns per warp beyond the tensor-memory capacity of the tightest quadrant go to shared-memory slots
+  // ((j - tcap) * 15 + warp), what does not fit there stays in global memory (L2)
+  static const bool no_tmem = getenv("BRA_QRCP_NOTMEM") != nullptr;
+  const int cpw = (cpc + QF_CW - 1) / QF_CW;
+  const int tcap_min = no_tmem ? 0 : 128 / (4 * nch);
+  int want = cpw > tcap_min ? (cpw - tcap_min) * QF_CW : 0;
   int c = (int)((budget - fixed) / ((size_t)ld * 8));
-  if (c > cpc) c = cpc;
-  if (c < cpc && !aligned) return false;      // L2-resident columns need 16-byte aligned 128-bit accesses
+  if (c > want) c = want;
+  if (c < want && !aligned) return false;      // L2-resident columns need 16-byte aligned 128-bit accesses
   *jw = cpc <= QF_CW * 4 ? 4 : 8;
   *lds = ld;
   *csm = c;
