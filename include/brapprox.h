@@ -278,6 +278,9 @@ int bra_probe_exchange2(bra_ctx* ctx, int ctas, int hw, int mode, int leaders, i
 int bra_debug_qrcp_phases(bra_ctx* ctx, int32_t* out6);
 /* Sweeps the last psvd core (k x k Jacobi SVD) needed. */
 int bra_debug_jacobi_sweeps(bra_ctx* ctx);
+/* Skeleton QRs (the QR of A[:, sk] in pqrfact / psvdfact / prange, src/pqr.jl:297-305) this context had to redo with a
+ * fresh Gaussian preconditioner after the Gram Cholesky of the first attempt broke down (cumulative). */
+int bra_debug_skeleton_retries(bra_ctx* ctx);
 /* column swaps made by the last maxdet post-processing (maxdet_swapcols!, src/pqr.jl:444-478) */
 int64_t bra_debug_maxdet_swaps(bra_ctx* ctx);
 /* Kilo-cycles thread 0 spent in the last Jacobi launch: panel load, round sync, panel store, grid barrier,

@@ -449,6 +449,7 @@ int bra_debug_qrcp_phases(bra_ctx* ctx, int32_t* out6) {
 }
 
 int bra_debug_jacobi_sweeps(bra_ctx* ctx) { return ctx ? ctx->last_jacobi_sweeps : -1; }
+int bra_debug_skeleton_retries(bra_ctx* ctx) { return ctx ? ctx->skeleton_retries : -1; }
 int64_t bra_debug_maxdet_swaps(bra_ctx* ctx) { return ctx ? ctx->last_maxdet_swaps : -1; }
 int bra_debug_jacobi_phases(bra_ctx* ctx, int32_t* out4) {
   if (!ctx || !out4) return -1;
@@ -663,6 +664,12 @@ int bra_trsolve_T_f64(bra_ctx* ctx, int64_t k, int64_t n, const double* R, int64
 int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* dA, int64_t lda,
                         const bra_opts* o, const bra_rand* rnd) {
   const int64_t nA = (trans == 'n') ? n : m;
+  // the speculative sketches of bra_stage_A belong to THIS call only: whatever way it ends (errors included), a later
+  // factorization must never find them
+  struct SpecGuard {
+    bra_ctx* c;
+    ~SpecGuard() { c->spec_rounds = 0; }
+  } spec_guard{ctx};
   FactResult& res = ctx->res;
   res = FactResult();
   res.m = (trans == 'n') ? m : n;

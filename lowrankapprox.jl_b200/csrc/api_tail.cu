@@ -52,7 +52,19 @@ int fresh_preconditioner(bra_ctx* ctx, int64_t mA, int64_t k, const bra_opts* o)
 }
 
 // QR of the skeleton columns: ctx->Q (mA x k, ld = even(mA)) and ctx->R1 (k x k, upper triangular).
-int skeleton_qr(bra_ctx* ctx, char trans, const double* dA, int64_t lda, int64_t mA, int64_t k, const bra_opts* o) {
+// The sketch's R11 preconditions C = A[:, sk] only when the sketch embeds range(C): true for the oversampled Gaussian and
+// SRFT sketches, NOT for :sub (a row subset: rows of low leverage are missed) and :sprn (no oversampling); there, and
+// after a maxdet swap, a fresh (k + 8)-row Gaussian sketch of C is factored instead (fresh_preconditioner).  The callers
+// also retry with fresh = true when the Gram Cholesky of the R11 path breaks down (the reference's Householder qr!
+// cannot fail, src/pqr.jl:297-305).
+bool skeleton_needs_fresh(const bra_ctx* ctx, const bra_opts* o) {
+  if (ctx->res.maxdet_done) return true;
+  static const bool off = getenv("BRA_SKELETON_NOFRESH") != nullptr;      // test hook: exercise the retry path
+  return !off && (o->sketch == BRA_SKETCH_SUB || o->sketch == BRA_SKETCH_SPRN);
+}
+
+int skeleton_qr(bra_ctx* ctx, char trans, const double* dA, int64_t lda, int64_t mA, int64_t k, const bra_opts* o,
+                bool fresh) {
   const int64_t ldq = even(mA);
   BRA_CUDA(ctx->Q.reserve((size_t)ldq * k * 8));
   BRA_CUDA(ctx->R1.reserve((size_t)k * k * 8));
@@ -60,7 +72,7 @@ int skeleton_qr(bra_ctx* ctx, char trans, const double* dA, int64_t lda, int64_t
   if (rc) return rc;
   rc = bra_gather_cols(ctx, trans, dA, lda, mA, k, ctx->jpvt.as<int64_t>(), ctx->Q.as<double>(), ldq);   // getcols
   if (rc) return rc;
-  if (ctx->res.maxdet_done && (rc = fresh_preconditioner(ctx, mA, k, o))) return rc;
+  if (fresh && (rc = fresh_preconditioner(ctx, mA, k, o))) return rc;
   // Y = C R11^{-1}: R11 is the triangular factor of the SKETCH of these very columns (Omega*C = Q_B*R11)
   rc = bra_trsolve_right_upper(ctx, mA, (int)k, ctx->R11.as<double>(), k, ctx->Q.as<double>(), ldq);
   if (rc) return rc;
@@ -88,8 +100,12 @@ int bra_pqrfact_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double
   FactResult& res = ctx->res;
   const int64_t k = res.k, mA = res.m, nA = res.n;
   GemmTagGuard gtag(ctx);
-  if (k > 0) {
-    rc = skeleton_qr(ctx, trans, dA, dlda, mA, k, opts);                // F = qr!(getcols(trans, A, V[:sk]))
+  res.have_Q = true;
+  res.have_R = true;
+  if (k == 0) return bra_chol_status(ctx);
+  bool fresh = skeleton_needs_fresh(ctx, opts);
+  for (;;) {
+    rc = skeleton_qr(ctx, trans, dA, dlda, mA, k, opts, fresh);         // F = qr!(getcols(trans, A, V[:sk]))
     if (rc) return rc;
     // R = pqrr(F.R, V[:T]) = [R1 | R1*T]   (src/pqr.jl:330-340)
     BRA_CUDA(ctx->Rfull.reserve((size_t)k * nA * 8));
@@ -102,10 +118,11 @@ int bra_pqrfact_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double
                        ctx->Rfull.as<double>() + (size_t)k * k, k);
       if (rc) return rc;
     }
+    rc = bra_chol_status(ctx);      // the one host sync of the tail (also reports a Cholesky breakdown)
+    if (rc != BRA_ERR_INTERNAL || fresh) return rc;
+    fresh = true;                   // R11 was a poor preconditioner for these columns: once more with a fresh one
+    ctx->skeleton_retries++;
   }
-  res.have_Q = true;
-  res.have_R = true;
-  return bra_chol_status(ctx);      // the one host sync of the tail (also reports a Cholesky breakdown)
 }
 
 // prange(trans, A, opts) (src/prange.jl:14-62): an orthonormal basis Q of the range of A (trans = 'n'), of A'
@@ -122,7 +139,9 @@ int prange_one_sided(bra_ctx* ctx, char trans, int64_t m, int64_t n, const doubl
   int rc;
   const bool direct = opts->sketch == BRA_SKETCH_NONE || (opts->sketch == BRA_SKETCH_SUB && !two_sided);
   bra_opts o = *opts;
-  if (!two_sided) o.maxdet_tol = -1.0;       // retval "q" alone: the swaps do not reach Q (src/pqr.jl:469-470)
+  // retval "q" alone: the swaps do not reach Q (src/pqr.jl:469-470) -- except in prange_sub (src/prange.jl:64-77), which
+  // takes the COLUMNS A[:, p[1:k]] of the left sketch factorization: there the swapped p selects other columns
+  if (!two_sided && opts->sketch != BRA_SKETCH_SUB) o.maxdet_tol = -1.0;
   if (direct) {
     if ((rc = bra_sketchfact_core(ctx, trans, m, n, dA, dlda, &o, rnd))) return rc;
   } else if ((rc = bra_prange_core(ctx, trans, m, n, dA, dlda, &o, rnd, two_sided))) {
@@ -135,7 +154,14 @@ int prange_one_sided(bra_ctx* ctx, char trans, int64_t m, int64_t n, const doubl
   const double* src = direct ? dA : ctx->B.as<double>();
   const int64_t lds = direct ? dlda : ctx->res.n;
   if (two_sided) return bra_gather_cols(ctx, gt, src, lds, M, k, ctx->jpvt.as<int64_t>(), cols, ldc);
-  return skeleton_qr(ctx, gt, src, lds, M, k, &o);
+  bool fresh = skeleton_needs_fresh(ctx, &o);
+  for (;;) {
+    if ((rc = skeleton_qr(ctx, gt, src, lds, M, k, &o, fresh))) return rc;
+    rc = bra_chol_status(ctx);
+    if (rc != BRA_ERR_INTERNAL || fresh) return rc;
+    fresh = true;
+    ctx->skeleton_retries++;
+  }
 }
 }  // namespace
 
@@ -185,10 +211,16 @@ int bra_prange_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double*
   onone.maxdet_tol = -1.0;           // retval "q" alone: the swaps do not reach Q (src/pqr.jl:469-470)
   const int64_t kc = kk[0] + kk[1];
   if ((rc = bra_sketchfact_core(ctx, 'n', n, kc, ctx->Bcat.as<double>(), ldc, &onone, nullptr))) return rc;
-  if (ctx->res.k > 0 && (rc = skeleton_qr(ctx, 'n', ctx->Bcat.as<double>(), ldc, n, ctx->res.k, &onone))) return rc;
   ctx->res.have_Q = true;
   ctx->res.have_T = false;
-  return ctx->res.k > 0 ? bra_chol_status(ctx) : BRA_OK;
+  if (ctx->res.k == 0) return BRA_OK;
+  // sketch = :none: R11 is the triangular factor of these very columns
+  if ((rc = skeleton_qr(ctx, 'n', ctx->Bcat.as<double>(), ldc, n, ctx->res.k, &onone, false))) return rc;
+  rc = bra_chol_status(ctx);
+  if (rc != BRA_ERR_INTERNAL) return rc;
+  ctx->skeleton_retries++;
+  if ((rc = skeleton_qr(ctx, 'n', ctx->Bcat.as<double>(), ldc, n, ctx->res.k, &onone, true))) return rc;
+  return bra_chol_status(ctx);
 }
 
 int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* opts,
@@ -213,7 +245,9 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
     res.have_svd = true;
     return BRA_OK;
   }
-  rc = skeleton_qr(ctx, trans, dA, dlda, mA, k, opts);                  // Q, R = qr!(getcols(...))
+  bool fresh = skeleton_needs_fresh(ctx, opts);
+skeleton_again:
+  rc = skeleton_qr(ctx, trans, dA, dlda, mA, k, opts, fresh);           // Q, R = qr!(getcols(...))
   if (rc) return rc;
 
   // Z = [I; T'] (nA x k): Q_z R_z by CholeskyQR2  (W = R1 [I T] P' = (R1 R_z') Q_z' P')
@@ -259,6 +293,12 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
     BRA_CUDA(cudaMemcpyAsync(ctx->h_info + 12, ctx->info.as<int>() + 12, 8, cudaMemcpyDeviceToHost, ctx->stream));
     BRA_CUDA(cudaStreamSynchronize(ctx->stream));
     // a breakdown in the skeleton QR is an error; one in Z'Z only selects the two-pass path (which checks again)
+    if (ctx->h_info[13] != 0 && !fresh) {
+      // R11 was a poor preconditioner for these columns: once more with a fresh Gaussian sketch of them
+      fresh = true;
+      ctx->skeleton_retries++;
+      goto skeleton_again;
+    }
     if (ctx->h_info[13] != 0) {
       ctx->set_error("CholeskyQR2 of the skeleton columns: Gram matrix not positive definite at pivot " +
                      std::to_string(ctx->h_info[13]));

@@ -118,6 +118,7 @@ struct bra_ctx {
   int64_t batched_unfinished = 0;   // blocks of the last batched call that needed rounds beyond the fused one
   int64_t last_maxdet_swaps = 0;    // column swaps done by the last maxdet post-processing
   int start_round = 0;              // adaptive loop resumes at this round (batched fallback)
+  int skeleton_retries = 0;         // skeleton QRs redone with a fresh preconditioner after a Cholesky breakdown
   int gemm_tag = BRA_PROF_GEMM; // profiling tag the GEMM launchers record under (tails switch it)
   uint32_t rec_epoch = 1;
   size_t rec_zeroed = 0;

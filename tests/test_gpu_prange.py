@@ -5,6 +5,8 @@ Criteria: k identical; Q orthonormal to 1e-13*sqrt(k); Q equal to the oracle's H
 per-column sign, weighted by |R_jj|/|R_11| (column j of the Q of a graded matrix is determined to eps*|R_11|/|R_jj|);
 the range error within 2x of the oracle's; the reference's own test inequality (test/prange.jl) with its own options.
 """
+import ctypes
+
 import numpy as np
 import pytest
 
@@ -132,3 +134,28 @@ def test_sketch_right_forms(ctx, kind):
         else:
             Bo = o.apply_sketch(kind, A, order, rin, trans)
         assert np.linalg.norm(Bg - Bo) <= 1e-12 * np.linalg.norm(Bo)
+
+
+@pytest.mark.parametrize("trans", ["n", "c"])
+def test_prange_sub_keeps_maxdet_swaps(ctx, trans):
+    """prange_sub (src/prange.jl:64-77) takes the COLUMNS A[:, p[1:k]] of sketchfact(:left, ...): the maxdet swaps of
+    pqrback_postproc (src/pqr.jl:428-433) change p even with retval "q", so they select other columns."""
+    import brapprox
+    from brapprox import _binding as B
+    m, n, r, rtol = 640, 480, 48, 1e-7
+    A = o.decaying_matrix(m, n, r, 9.0, r, seed=21)
+    A = np.asfortranarray(A * (10.0 ** (-3.0 * np.random.default_rng(5).random(m)))[:, None])
+    rin = o.RandomInputs(8)
+    kw = dict(rtol=rtol, sketch="sub", maxdet_tol=0.0)
+    Qo = o.prange(A, o.LRAOptions(**kw), rin, trans)
+    Qg = brapprox.prange(A, brapprox.LRAOptions(**kw), trans=trans, rand=rin.drawn, ctx=ctx)
+    B.lib.bra_debug_maxdet_swaps.restype = ctypes.c_int64
+    swaps = B.lib.bra_debug_maxdet_swaps(ctx.handle)
+    print("maxdet swaps:", swaps)
+    assert Qg.shape == Qo.shape
+    k = Qo.shape[1]
+    assert np.linalg.norm(Qg.T @ Qg - np.eye(k)) <= 1e-13 * np.sqrt(k)
+    # same columns in the same order => same Q up to the sign of each column
+    d = np.sign(np.sum(Qg * Qo, axis=0))
+    assert np.max(np.abs(Qg * d - Qo)) <= 1e-7        # kappa(C) ~ 1/rtol: columns determined to eps/rtol
+    assert _rel_range_err(A, Qg, trans) <= 2 * _rel_range_err(A, Qo, trans) + 1e-15

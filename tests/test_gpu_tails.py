@@ -208,3 +208,68 @@ def test_psvdfact_into_caller_buffers(ctx):
     np.testing.assert_array_equal(F1.Vt, F0.Vt)
     with pytest.raises(ValueError):
         brapprox.psvdfact(A, rtol=1e-9, seed=4, ctx=ctx, out=(np.zeros((320, 4), order="F"), Sb, Vb))
+
+
+def _leverage_matrix(m, n, r, seed):
+    """Rows of wildly different weight: a row-subset sketch misses most of the range, a sparse sketch has no
+    oversampling -- the cases where the sketch's R11 is a poor preconditioner for A[:, sk]."""
+    A = o.decaying_matrix(m, n, r, 10.0, r, seed=seed)
+    w = 10.0 ** (-6.0 * np.random.default_rng(seed + 1).random(m))
+    return np.asfortranarray(A * w[:, None])
+
+
+@pytest.mark.parametrize("kind", ["sub", "sprn", "srft", "randn"])
+def test_pqrfact_nonuniform_leverage_all_sketches(ctx, kind):
+    """The reference's Householder qr! of A[:, sk] cannot fail (src/pqr.jl:297-305); neither may the preconditioned
+    CholeskyQR2: k, p identical to the oracle, Q orthonormal, error within 2x."""
+    import brapprox
+    A = _leverage_matrix(900, 600, 60, 5)
+    rin = o.RandomInputs(4)
+    Fo = o.pqrfact(A, o.LRAOptions(rtol=1e-9, sketch=kind), rin)
+    Fg = brapprox.pqrfact(A, brapprox.LRAOptions(rtol=1e-9, sketch=kind), rand=rin.drawn, ctx=ctx)
+    assert Fg.k == Fo.k
+    k = Fo.k
+    same = int(np.flatnonzero(np.append(Fg.p[:k] != Fo.p[:k], True))[0])
+    assert same >= k - 8          # pivots at the noise floor may flip (SRFT butterflies vs FFTW)
+    assert np.linalg.norm(Fg.Q.T @ Fg.Q - np.eye(k)) <= 1e-13 * np.sqrt(k)
+    nrm = np.linalg.norm(A)
+    eo = np.linalg.norm(A - Fo.matrix()) / nrm
+    eg = np.linalg.norm(A - Fg.matrix()) / nrm
+    assert eg <= 2 * eo + 1e-15
+
+
+@pytest.mark.parametrize("kind", ["sub", "sprn", "srft"])
+def test_psvdfact_nonuniform_leverage_all_sketches(ctx, kind):
+    import brapprox
+    A = _leverage_matrix(800, 500, 50, 9)
+    rin = o.RandomInputs(6)
+    So = o.psvdfact(A, o.LRAOptions(rtol=1e-9, sketch=kind), rin)
+    Sg = brapprox.psvdfact(A, brapprox.LRAOptions(rtol=1e-9, sketch=kind), rand=rin.drawn, ctx=ctx)
+    assert Sg.k_id == So.k_id
+    assert len(Sg.S) == len(So.S)
+    assert np.max(np.abs(Sg.S - So.S)) <= 1e-10 * So.S[0]
+    kk = len(So.S)
+    assert np.linalg.norm(Sg.U.T @ Sg.U - np.eye(kk)) <= 1e-12 * np.sqrt(kk)
+    nrm = np.linalg.norm(A, 2)
+    eo = np.linalg.norm(A - So.matrix(), 2) / nrm
+    eg = np.linalg.norm(A - Sg.matrix(), 2) / nrm
+    assert eg <= 2 * eo + 1e-15
+
+
+def test_skeleton_qr_retries_after_breakdown(ctx, monkeypatch):
+    """With the a-priori choice switched off (BRA_SKELETON_NOFRESH) the :sub sketch's R11 preconditions A[:, sk]: whether
+    or not the Gram Cholesky breaks down, the call must succeed (a breakdown is retried with a fresh preconditioner)."""
+    import brapprox
+    from brapprox import _binding as B
+    monkeypatch.setenv("BRA_SKELETON_NOFRESH", "1")
+    A = _leverage_matrix(900, 600, 60, 5)
+    rin = o.RandomInputs(4)
+    Fo = o.pqrfact(A, o.LRAOptions(rtol=1e-9, sketch="sub"), rin)
+    B.lib.bra_debug_skeleton_retries.restype = int
+    r0 = B.lib.bra_debug_skeleton_retries(ctx.handle)
+    Fg = brapprox.pqrfact(A, brapprox.LRAOptions(rtol=1e-9, sketch="sub"), rand=rin.drawn, ctx=ctx)
+    print("skeleton retries:", B.lib.bra_debug_skeleton_retries(ctx.handle) - r0)
+    assert Fg.k == Fo.k
+    assert np.linalg.norm(Fg.Q.T @ Fg.Q - np.eye(Fo.k)) <= 1e-12 * np.sqrt(Fo.k)
+    nrm = np.linalg.norm(A)
+    assert np.linalg.norm(A - Fg.matrix()) / nrm <= 2 * np.linalg.norm(A - Fo.matrix()) / nrm + 1e-15
