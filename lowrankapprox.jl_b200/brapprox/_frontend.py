@@ -34,7 +34,8 @@ def _opts(opts: Optional[LRAOptions], kw) -> LRAOptions:
 class _RandPack:
     """Marshals per-round random inputs into a bra_rand (keeps the arrays alive)."""
 
-    def __init__(self, rounds: Optional[Sequence[dict]]):
+    def __init__(self, rounds: Optional[Sequence[dict]], opts: Optional[LRAOptions] = None,
+                 contracted: Optional[int] = None):
         self.keep = []
         self.c = B.bra_rand()
         self.c.n_rounds = 0
@@ -42,6 +43,8 @@ class _RandPack:
             return
         n = len(rounds)
         self.c.n_rounds = n
+        if opts is not None and contracted is not None:
+            self._check_shapes(rounds, opts, int(contracted))
 
         def column(key, dtype):
             arr = (C.c_void_p * n)()
@@ -68,6 +71,37 @@ class _RandPack:
         self.c.perm = column("perm", np.int64)
         self.c.s = column("s", np.float64)
         self.c.r = column("r", np.int64)
+
+
+    @staticmethod
+    def _round_order(o: LRAOptions, t: int) -> int:
+        """Sketch order of adaptive round t / of the single non-adaptive round (src/sketch.jl:226-236, 680-686)."""
+        adaptive = o.sketchfact_adap or o.rank < 0
+        nn = (o.nb << t) if adaptive else o.rank
+        if o.sketch == "sprn":
+            return nn
+        a, b = o._samp_affine()
+        if a == 0 and b == 0:
+            a, b = (4, 8) if o.sketch == "sub" else (1, 8)
+        return a * nn + b
+
+    @classmethod
+    def _check_shapes(cls, rounds, o: LRAOptions, contracted: int) -> None:
+        """The C side reads Omega as order x contracted (ld = order) and the vectors at their nominal lengths: a
+        wrongly shaped input would be read past its end, so it is refused here (DimensionMismatch in the reference)."""
+        want = {"Omega": lambda l: (l, contracted), "d": lambda l: (contracted,), "idx": lambda l: (l,),
+                "perm": lambda l: (contracted,), "s": lambda l: (contracted,), "r": lambda l: (l,)}
+        for t, r in enumerate(rounds):
+            l = cls._round_order(o, t)
+            for key, shp in want.items():
+                v = r.get(key)
+                if v is None:
+                    continue
+                got = v.shape if isinstance(v, DeviceMatrix) else np.shape(v)
+                if isinstance(v, DeviceMatrix) and v.ld != max(v.m, 1):
+                    raise ValueError(f"DimensionMismatch: round {t} {key} must be stored with ld == rows")
+                if tuple(got) != shp(l):
+                    raise ValueError(f"DimensionMismatch: round {t} {key} has shape {tuple(got)}, expected {shp(l)}")
 
 
 def sketch(A, order: int, opts: Optional[LRAOptions] = None, side: str = "left", trans: str = "n",
@@ -170,7 +204,7 @@ def idfact_device(A, opts: Optional[LRAOptions] = None, trans: str = "n", rand=N
     o.pqrfact_retval = "t"                              # src/id.jl:438
     ctx = ctx or default_context()
     pA, m, n, lda, keepA = mat_arg(A)
-    rp = _RandPack(rand)
+    rp = _RandPack(rand, o, m if _trans(trans) == b"n" else n)
     co = o.to_c()
     ctx.check(lib.bra_idfact_f64(ctx.handle, _trans(trans), m, n, pA, lda, C.byref(co), C.byref(rp.c)))
     return ctx.info()
@@ -293,7 +327,7 @@ def pqrfact_device(A, opts: Optional[LRAOptions] = None, trans: str = "n", rand=
     o = _opts(opts, kw)
     ctx = ctx or default_context()
     pA, m, n, lda, keepA = mat_arg(A)
-    rp = _RandPack(rand)
+    rp = _RandPack(rand, o, m if _trans(trans) == b"n" else n)
     co = o.to_c()
     ctx.check(lib.bra_pqrfact_f64(ctx.handle, _trans(trans), m, n, pA, lda, C.byref(co), C.byref(rp.c)))
     return ctx.info()
@@ -348,7 +382,7 @@ def psvdfact_device(A, opts: Optional[LRAOptions] = None, rand=None, ctx: Option
     o = _opts(opts, kw)
     ctx = ctx or default_context()
     pA, m, n, lda, keepA = mat_arg(A)
-    rp = _RandPack(rand)
+    rp = _RandPack(rand, o, max(m, n))                  # trans = :n if m >= n else :c (src/psvd.jl:242,256)
     co = o.to_c()
     ctx.check(lib.bra_psvdfact_f64(ctx.handle, m, n, pA, lda, C.byref(co), C.byref(rp.c)))
     return ctx.info()
@@ -382,7 +416,7 @@ def pheigfact(A, opts: Optional[LRAOptions] = None, rand=None, ctx: Optional[Con
     pA, m, n, lda, keepA = mat_arg(A)
     if m != n:
         raise ValueError("matrix is not square")            # checksquare
-    rp = _RandPack(rand)
+    rp = _RandPack(rand, o, n)
     co = o.to_c()
     rc = lib.bra_pheigfact_f64(ctx.handle, n, pA, lda, C.byref(co), C.byref(rp.c))
     if rc == -3:

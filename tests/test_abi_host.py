@@ -144,3 +144,31 @@ def test_frontend_argument_checks_without_gpu():
         brapprox.sketch(A, -1)
     with pytest.raises(ValueError):
         brapprox.idfact(A, trans="t")
+
+
+def test_random_input_shapes_are_checked_on_the_host():
+    """Caller-supplied per-round random inputs (bra_rand) are validated against the round's sketch order and the
+    contracted dimension before they cross the C ABI (the C side reads them at their nominal sizes)."""
+    import brapprox
+    from brapprox._frontend import _RandPack
+    o = brapprox.LRAOptions(rtol=1e-9)                      # randn, adaptive: orders 40, 72, ...
+    good = [{"Omega": np.zeros((40, 100))}, {"Omega": np.zeros((72, 100))}]
+    _RandPack(good, o, 100)
+    for bad in ([{"Omega": np.zeros((40, 99))}], [{"Omega": np.zeros((41, 100))}],
+                [{"Omega": np.zeros((40, 100))}, {"Omega": np.zeros((40, 100))}]):
+        with pytest.raises(ValueError, match="DimensionMismatch"):
+            _RandPack(bad, o, 100)
+    o = brapprox.LRAOptions(sketch="srft", rank=10, sketchfact_adap=False)      # one round of order 18
+    _RandPack([{"d": np.ones(64), "idx": np.ones(18, dtype=np.int64)}], o, 64)
+    with pytest.raises(ValueError, match="DimensionMismatch"):
+        _RandPack([{"d": np.ones(63), "idx": np.ones(18, dtype=np.int64)}], o, 64)
+    with pytest.raises(ValueError, match="DimensionMismatch"):
+        _RandPack([{"d": np.ones(64), "idx": np.ones(10, dtype=np.int64)}], o, 64)
+    o = brapprox.LRAOptions(sketch="sprn")                  # order 32 in round 0, no oversampling
+    _RandPack([{"perm": np.arange(50), "s": np.ones(50)}], o, 50)
+    with pytest.raises(ValueError, match="DimensionMismatch"):
+        _RandPack([{"perm": np.arange(49), "s": np.ones(50)}], o, 50)
+    o = brapprox.LRAOptions(sketch="sub")                   # order 4*32 + 8
+    _RandPack([{"r": np.ones(136, dtype=np.int64)}], o, 50)
+    with pytest.raises(ValueError, match="DimensionMismatch"):
+        _RandPack([{"r": np.ones(40, dtype=np.int64)}], o, 50)
