@@ -135,6 +135,26 @@ int orthrows_dev(bra_ctx* ctx, const bra_opts* o, int64_t l, int64_t nn, double*
   return bra_chol_status(ctx);
 }
 
+// A' (n x m, ld = roundup(n, 2)) in ctx->At, made once per factorization (At_valid): every product with op(A) = A'
+// -- the (:left, :c) sketches (src/sketch.jl:101-110), the A' passes of the power iteration (:140-149, 163-172) and the
+// SRFT of the rows -- then contracts along contiguous memory, i.e. runs on the TMA + DMMA kernel like the :n form.
+// One read + one write of A (HBM-bound, ~0.2 ms at 8192^2) against 2 l m n flops per round.  Returns false (no error)
+// when the device has no room for the copy; the callers then take the strided generic kernel.
+bool transposed_A(bra_ctx* ctx, int64_t m, int64_t n, const double* dA, int64_t lda, const double** At, int64_t* ldat) {
+  const int64_t ld = (n + 1) & ~int64_t(1);
+  if (!ctx->At_valid) {
+    if (ctx->At.reserve((size_t)ld * (m > 0 ? m : 1) * 8) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    if (bra_transpose(ctx, dA, lda, m, n, ctx->At.as<double>(), ld)) return false;
+    ctx->At_valid = true;
+  }
+  *At = ctx->At.as<double>();
+  *ldat = ld;
+  return true;
+}
+
 // out (order x N) = Om * op(A) for a device-resident Om (order x K, ld = order); t = 'n': op(A) = A, t = 'c': A'
 int apply_rows(bra_ctx* ctx, char t, int64_t m, int64_t n, const double* dA, int64_t lda, const double* Om, int64_t order,
                double* out) {
@@ -144,6 +164,10 @@ int apply_rows(bra_ctx* ctx, char t, int64_t m, int64_t n, const double* dA, int
   int rc = bra_transpose_omega(ctx, Om, order, order, K, ctx->omega_t.as<double>());
   if (rc) return rc;
   if (t == 'n') return bra_gemm_sketch(ctx, ctx->omega_t.as<double>(), order, K, dA, lda, N, out, order);
+  const double* At;
+  int64_t ldat;
+  if (K >= 256 && transposed_A(ctx, m, n, dA, lda, &At, &ldat))
+    return bra_gemm_sketch(ctx, ctx->omega_t.as<double>(), order, K, At, ldat, N, out, order);
   return bra_gemm_generic(ctx, ctx->omega_t.as<double>(), ldt, 1, dA, lda, 1, order, N, K, out, order);
 }
 
@@ -217,7 +241,15 @@ int sketch_randn_round(bra_ctx* ctx, char trans, int64_t m, int64_t n, const dou
     else
       rc = bra_gemm_sketch(ctx, ctx->omega_t.as<double>(), order, mA, dA, lda, nA, ctx->B.as<double>(), order);
   }
-  else rc = bra_gemm_generic(ctx, ctx->omega_t.as<double>(), ldt, 1, dA, lda, 1, order, nA, mA, ctx->B.as<double>(), order);
+  else {
+    // (:left, :c): B = Omega A' contracts along the rows of A -- on the transposed copy it is the :n product
+    const double* At;
+    int64_t ldat;
+    if (mA >= 256 && transposed_A(ctx, m, n, dA, lda, &At, &ldat))
+      rc = bra_gemm_sketch(ctx, ctx->omega_t.as<double>(), order, mA, At, ldat, nA, ctx->B.as<double>(), order);
+    else
+      rc = bra_gemm_generic(ctx, ctx->omega_t.as<double>(), ldt, 1, dA, lda, 1, order, nA, mA, ctx->B.as<double>(), order);
+  }
   if (rc) return rc;
   // row-sharded A: B = sum over ranks of Omega_g * A_g  (one all-reduce of the l x n sketch per round)
   rc = bra_allreduce_sum_f64(ctx, ctx->B.as<double>(), order * nA);
@@ -304,14 +336,10 @@ int sketch_round(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* d
     int64_t ldop = lda;
     if (trans == 'c') {
       // sequences are the rows of A: work on a transposed copy (made once per factorization, see At_valid)
-      const int64_t ldat = (n + 1) & ~int64_t(1);
-      if (!ctx->At_valid) {
-        BRA_CUDA(ctx->At.reserve((size_t)ldat * m * 8));
-        if ((rc = bra_transpose(ctx, dA, lda, m, n, ctx->At.as<double>(), ldat))) return rc;
-        ctx->At_valid = true;
+      if (!transposed_A(ctx, m, n, dA, lda, &Aop, &ldop)) {
+        ctx->set_error("sketch = :srft with trans = :c needs room for a transposed copy of A on the device");
+        return BRA_ERR_CUDA;
       }
-      Aop = ctx->At.as<double>();
-      ldop = ldat;
     }
     return bra_sketch_srft(ctx, Aop, ldop, mA, nA, order, (const double*)d, (const int64_t*)idx, ctx->B.as<double>(),
                            order);
@@ -517,6 +545,7 @@ int bra_sketch_randn_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const d
     oms[0] = ctx->scratch2.as<double>();
   }
   ctx->Apanels_state = 0;
+  ctx->At_valid = false;
   rc = sketch_randn_round(ctx, trans, m, n, dA, dlda, &o, &rnd, 0, order);
   if (rc) return rc;
   BRA_CUDA(copy2d(ctx, B, ldb, ctx->B.p, order, order, nA));
