@@ -410,13 +410,17 @@ int bra_destroy(bra_ctx* ctx) {
                     &ctx->vn2, &ctx->lpos, &ctx->fpend, &ctx->rec, &ctx->jpvt, &ctx->tau, &ctx->rdiag, &ctx->info,
                     &ctx->kbtrace, &ctx->R11, &ctx->T, &ctx->C, &ctx->Q, &ctx->R1, &ctx->Rfull, &ctx->W, &ctx->G,
                     &ctx->U, &ctx->S, &ctx->Vt, &ctx->Z, &ctx->scratch, &ctx->scratch2, &ctx->scratch3,
-                    &ctx->aux_in1, &ctx->aux_in2, &ctx->jwork, &ctx->At, &ctx->rinv, &ctx->yt, &ctx->Apanels, &ctx->tritmp, &ctx->cholscr, &ctx->Bq, &ctx->omega_spec, &ctx->Bspec, &ctx->Bt, &ctx->Bcat};
+                    &ctx->aux_in1, &ctx->aux_in2, &ctx->jwork, &ctx->At, &ctx->rinv, &ctx->yt, &ctx->Apanels, &ctx->tritmp, &ctx->cholscr, &ctx->Bq, &ctx->omega_spec, &ctx->Bspec, &ctx->Bt, &ctx->Bcat,
+                    &ctx->partial_l1, &ctx->cholscr_l1, &ctx->tritmp_l1, &ctx->G_l1};
   for (DevBuf* b : bufs) b->release();
   bra_comm_destroy(ctx);
   if (ctx->h_info) cudaFreeHost(ctx->h_info);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   for (cudaEvent_t e : ctx->copy_events) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return BRA_OK;

@@ -8,6 +8,9 @@
 
 int bra_set_identity(bra_ctx* ctx, int k, double* J, int64_t ldj);
 int bra_chol_status_reset(bra_ctx* ctx);
+int bra_lane_fork(bra_ctx* ctx);
+int bra_lane_end(bra_ctx* ctx);
+int bra_lane_join(bra_ctx* ctx);
 int bra_chol_status(bra_ctx* ctx);
 int bra_fix_signs(bra_ctx* ctx, int64_t rows, int k, double* Q, int64_t ldq, double* R, int64_t ldr);
 int bra_gather_scale_cols(bra_ctx* ctx, const double* X, int64_t ldx, int64_t rows, int kk, const int* order_dev,
@@ -245,23 +248,20 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
     res.have_svd = true;
     return BRA_OK;
   }
-  bool fresh = skeleton_needs_fresh(ctx, opts);
-skeleton_again:
-  rc = skeleton_qr(ctx, trans, dA, dlda, mA, k, opts, fresh);           // Q, R = qr!(getcols(...))
-  if (rc) return rc;
-
-  // Z = [I; T'] (nA x k): Q_z R_z by CholeskyQR2  (W = R1 [I T] P' = (R1 R_z') Q_z' P')
+  // Z = [I; T'] (nA x k): Q_z R_z by Cholesky QR  (W = R1 [I T] P' = (R1 R_z') Q_z' P').
+  // Z is well conditioned (kappa(Z) = sqrt(1 + ||T||^2) / sqrt(1 + smin(T)^2), a few tens for a rank-revealing T), so
+  // ONE Cholesky pass on the Gram matrix gives R_z with Q_z = Z R_z^{-1} orthonormal to eps*kappa^2, and Q_z itself is
+  // never formed: Vop' = Ysel' Q_z' = (R_z^{-1} Ysel)' [I T].  A badly conditioned Z (diag(R_z) spread > 1e3) takes the
+  // two-pass CholeskyQR2 with an explicit Q_z instead.
+  // This chain (Z, Z'Z, R_z, R_z^{-1}) needs only T: it runs on the side lane NEXT TO the QR of the skeleton columns,
+  // whose chain of small Cholesky / inverse kernels leaves most of the machine idle.
   const int64_t ldz = even(nA);
-  BRA_CUDA(ctx->Z.reserve((size_t)ldz * k * 8));
-  double* Z = ctx->Z.as<double>();
-  rc = bra_set_identity(ctx, (int)k, Z, ldz);
-  if (rc) return rc;
-  if (nA > k) {
-    rc = bra_transpose(ctx, ctx->T.as<double>(), res.ldT, k, nA - k, Z + k, ldz);
-    if (rc) return rc;
-  }
   const int64_t ldj = even(k);                // even leading dimension: 16-byte aligned columns for the Jacobi panels
-  BRA_CUDA(ctx->W.reserve((size_t)8 * ldj * k * 8 + 64));
+  BRA_CUDA(ctx->Z.reserve((size_t)ldz * k * 8));
+  BRA_CUDA(ctx->W.reserve((size_t)9 * ldj * k * 8 + 64));
+  BRA_CUDA(ctx->G_l1.reserve((size_t)k * k * 8));
+  BRA_CUDA(ctx->info.reserve(64));
+  double* Z = ctx->Z.as<double>();
   double* Rz = ctx->W.as<double>();
   double* X = Rz + (size_t)ldj * k;         // Jacobi matrix: X = M' = R_z R1'
   double* J = X + (size_t)ldj * k;
@@ -270,41 +270,50 @@ skeleton_again:
   double* Q2 = R2 + (size_t)ldj * k;
   double* Xp = Q2 + (size_t)ldj * k;        // R2' (the matrix the Jacobi runs on when preconditioned)
   double* Rinv2 = Xp + (size_t)ldj * k;
-  // Z is well conditioned (kappa(Z) = sqrt(1 + ||T||^2) / sqrt(1 + smin(T)^2), a few tens for a rank-revealing T), so
-  // ONE Cholesky pass on the Gram matrix gives R_z with Q_z = Z R_z^{-1} orthonormal to eps*kappa^2, and Q_z itself is
-  // never formed: Vop' = Ysel' Q_z' = (R_z^{-1} Ysel)' [I T].  A badly conditioned Z (diag(R_z) spread > 1e3) takes the
-  // two-pass CholeskyQR2 with an explicit Q_z instead.
+  double* Rzinv = Rinv2 + (size_t)ldj * k;  // R_z^{-1} (side lane)
+  if ((size_t)k * 8 > BRA_HPIN_BYTES) {
+    ctx->set_error("psvdfact: k too large for the pinned read-back buffer");
+    return BRA_ERR_UNSUPPORTED;
+  }
+  {
+    if ((rc = bra_lane_fork(ctx))) return rc;
+    struct LaneEnd {
+      bra_ctx* c;
+      ~LaneEnd() { bra_lane_end(c); }
+    } lane_end{ctx};
+    if ((rc = bra_chol_status_reset(ctx))) return rc;                                       // info[13] on this lane
+    if ((rc = bra_set_identity(ctx, (int)k, Z, ldz))) return rc;
+    if (nA > k && (rc = bra_transpose(ctx, ctx->T.as<double>(), res.ldT, k, nA - k, Z + k, ldz))) return rc;
+    if ((rc = bra_gemm_tn(ctx, Z, ldz, k, nA, Z, ldz, k, ctx->G_l1.as<double>(), k))) return rc;   // G = Z'Z = I + T T'
+    if ((rc = bra_cholesky_upper(ctx, (int)k, ctx->G_l1.as<double>(), k, Rz, k))) return rc;
+    if ((rc = bra_set_identity(ctx, (int)k, Rzinv, ldj))) return rc;
+    if ((rc = bra_tri_inverse_upper(ctx, (int)k, Rz, k, Rzinv, ldj))) return rc;
+  }
+  bool fresh = skeleton_needs_fresh(ctx, opts);
+skeleton_again:
+  rc = skeleton_qr(ctx, trans, dA, dlda, mA, k, opts, fresh);           // Q, R = qr!(getcols(...))
+  if (rc) return rc;
   bool explicit_qz = false;
   {
-    BRA_CUDA(ctx->G.reserve((size_t)k * k * 8));
-    // park the skeleton QR's Cholesky status in info[13] and start a clean one for Z'Z (both read at the sync below)
-    BRA_CUDA(cudaMemcpyAsync(ctx->info.as<int>() + 13, ctx->info.as<int>() + 12, 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    if ((rc = bra_chol_status_reset(ctx))) return rc;
-    rc = bra_gemm_tn(ctx, Z, ldz, k, nA, Z, ldz, k, ctx->G.as<double>(), k);              // G = Z'Z = I + T T'
-    if (rc) return rc;
-    rc = bra_cholesky_upper(ctx, (int)k, ctx->G.as<double>(), k, Rz, k);
-    if (rc) return rc;
-    if ((size_t)k * 8 > BRA_HPIN_BYTES) {
-      ctx->set_error("psvdfact: k too large for the pinned read-back buffer");
-      return BRA_ERR_UNSUPPORTED;
-    }
+    if ((rc = bra_lane_join(ctx))) return rc;
     double* dz = reinterpret_cast<double*>(ctx->h_pin);
     BRA_CUDA(cudaMemcpy2DAsync(dz, 8, Rz, (size_t)(k + 1) * 8, 8, (size_t)k, cudaMemcpyDeviceToHost, ctx->stream));
+    // info[12]: Cholesky status of the skeleton QR (main lane), info[13]: of Z'Z (side lane)
     BRA_CUDA(cudaMemcpyAsync(ctx->h_info + 12, ctx->info.as<int>() + 12, 8, cudaMemcpyDeviceToHost, ctx->stream));
     BRA_CUDA(cudaStreamSynchronize(ctx->stream));
     // a breakdown in the skeleton QR is an error; one in Z'Z only selects the two-pass path (which checks again)
-    if (ctx->h_info[13] != 0 && !fresh) {
+    if (ctx->h_info[12] != 0 && !fresh) {
       // R11 was a poor preconditioner for these columns: once more with a fresh Gaussian sketch of them
       fresh = true;
       ctx->skeleton_retries++;
       goto skeleton_again;
     }
-    if (ctx->h_info[13] != 0) {
+    if (ctx->h_info[12] != 0) {
       ctx->set_error("CholeskyQR2 of the skeleton columns: Gram matrix not positive definite at pivot " +
-                     std::to_string(ctx->h_info[13]));
+                     std::to_string(ctx->h_info[12]));
       return BRA_ERR_INTERNAL;
     }
-    const int hinfo = ctx->h_info[12];
+    const int hinfo = ctx->h_info[13];
     double dmin = dz[0], dmax = dz[0];
     for (int64_t i = 0; i < k; ++i) {
       dmin = std::min(dmin, dz[i]);
@@ -439,13 +448,8 @@ skeleton_again:
     if (rc) return rc;
   } else {
     // Yh = R_z^{-1} Ysel (k x kk);  Vop' = Yh' [I T]: the first k columns are Yh' itself, the rest one TN product with T
-    {
-      // R_z is well conditioned: explicit blocked inverse (log-depth, fully parallel) + one k x k x kk product
-      ProfScope ps(ctx, BRA_PROF_QR);
-      if ((rc = bra_set_identity(ctx, (int)k, Rinv2, ldj))) return rc;
-      if ((rc = bra_tri_inverse_upper(ctx, (int)k, Rz, k, Rinv2, ldj))) return rc;
-    }
-    rc = bra_gemm_generic(ctx, Rinv2, 1, ldj, Ysel, 1, ldj, k, kk, k, Q2, ldj);              // Yh = R_z^{-1} Ysel
+    // R_z is well conditioned: its explicit blocked inverse (side lane, above) + one k x k x kk product
+    rc = bra_gemm_generic(ctx, Rzinv, 1, ldj, Ysel, 1, ldj, k, kk, k, Q2, ldj);              // Yh = R_z^{-1} Ysel
     if (rc) return rc;
     BRA_CUDA(cudaMemcpyAsync(Ysel, Q2, (size_t)ldj * kk * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     rc = bra_transpose(ctx, Ysel, ldj, k, kk, ctx->B2.as<double>(), even(kk));

@@ -93,6 +93,15 @@ struct bra_ctx {
   DevBuf tritmp;               // blocked triangular inverse: B C^{-1} scratch
   DevBuf cholscr;              // blocked Cholesky: inverse of the current diagonal block
   DevBuf Bq;                   // power iteration: the sketch on the other side of A
+  // side lane: an independent chain of small kernels (psvdfact: Z'Z -> R_z -> R_z^{-1}) runs on a second stream next to
+  // the main chain; the helpers that own a workspace or a status word pick the lane's copy (bra_lane_* in tail.cu)
+  int lane = 0;
+  cudaStream_t side_stream = nullptr, lane_saved = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  DevBuf partial_l1, cholscr_l1, tritmp_l1, G_l1;
+  DevBuf& ws_partial() { return lane ? partial_l1 : partial; }
+  DevBuf& ws_cholscr() { return lane ? cholscr_l1 : cholscr; }
+  DevBuf& ws_tritmp() { return lane ? tritmp_l1 : tritmp; }
   DevBuf Bt, Bcat;             // prange: the tall right-hand sketch B = op(A) S; [B_r[:,p_r] B_c[:,p_c]] of the two-sided form
   // host-resident A: the upload is pipelined with the sketch products of the first adaptive rounds (api.cu: bra_stage_A)
   cudaStream_t copy_stream = nullptr;
@@ -139,13 +148,13 @@ struct bra_ctx {
     cudaEvent_t e; cudaEventCreate(&e); return e;
   }
   void prof_begin(int tag) {
-    if (!prof_on) return;
+    if (!prof_on || lane) return;      // side-lane work hides behind the main chain: not a stage of its own
     ProfSpan sp{tag, prof_event(), prof_event()};
     cudaEventRecord(sp.e0, stream);
     prof_spans.push_back(sp);
   }
   void prof_end() {
-    if (!prof_on || prof_spans.empty()) return;
+    if (!prof_on || lane || prof_spans.empty()) return;
     // close the most recent open span
     cudaEventRecord(prof_spans.back().e1, stream);
   }

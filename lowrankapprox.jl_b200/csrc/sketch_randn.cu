@@ -434,8 +434,8 @@ int launch_gemm(bra_ctx* ctx, const CUtensorMap& mapA, const double* Omt, int64_
   double* out = B;
   int64_t ldo = ldb, sstride = 0;
   if (splits > 1) {
-    BRA_CUDA(ctx->partial.reserve((size_t)splits * l * n * 8));
-    out = ctx->partial.as<double>();
+    BRA_CUDA(ctx->ws_partial().reserve((size_t)splits * l * n * 8));
+    out = ctx->ws_partial().as<double>();
     ldo = l;
     sstride = l * n;
   }

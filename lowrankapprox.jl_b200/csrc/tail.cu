@@ -822,9 +822,10 @@ int bra_trsolve_right_upper(bra_ctx* ctx, int64_t rows, int k, const double* R, 
 int bra_cholesky_upper(bra_ctx* ctx, int k, double* G, int64_t ldg, double* Rout, int64_t ldr) {
   if (k <= 0) return BRA_OK;
   ProfScope ps(ctx, BRA_PROF_QR);
-  int* info = ctx->info.as<int>() + 12;      // sticky: reset by bra_chol_status_reset, read by bra_chol_status
-  BRA_CUDA(ctx->cholscr.reserve((size_t)TB * TB * 8));
-  double* Dinv = ctx->cholscr.as<double>();
+  // sticky status: reset by bra_chol_status_reset, read by bra_chol_status; the side lane reports in the next word
+  int* info = ctx->info.as<int>() + 12 + (ctx->lane ? 1 : 0);
+  BRA_CUDA(ctx->ws_cholscr().reserve((size_t)TB * TB * 8));
+  double* Dinv = ctx->ws_cholscr().as<double>();
   BRA_CUDA(cudaMemset2DAsync(Rout, (size_t)ldr * 8, 0, (size_t)k * 8, (size_t)k, ctx->stream));    // zeros below the diagonal
   const int nblk = (k + TB - 1) / TB;
   for (int jb = 0; jb < nblk; ++jb) {
@@ -874,7 +875,35 @@ int bra_cholqr2(bra_ctx* ctx, int64_t rows, int k, double* Y, int64_t ldy, const
 
 int bra_chol_status_reset(bra_ctx* ctx) {
   BRA_CUDA(ctx->info.reserve(64));
-  BRA_CUDA(cudaMemsetAsync(ctx->info.as<int>() + 12, 0, 4, ctx->stream));
+  BRA_CUDA(cudaMemsetAsync(ctx->info.as<int>() + 12 + (ctx->lane ? 1 : 0), 0, 4, ctx->stream));
+  return BRA_OK;
+}
+
+// ---- side lane: launches between bra_lane_fork and bra_lane_end go to a second stream that starts after everything
+// queued on the main stream so far; bra_lane_join makes the main stream wait for them ----
+int bra_lane_fork(bra_ctx* ctx) {
+  if (!ctx->side_stream) {
+    BRA_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+    BRA_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    BRA_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  }
+  BRA_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  BRA_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+  ctx->lane_saved = ctx->stream;
+  ctx->stream = ctx->side_stream;
+  ctx->lane = 1;
+  return BRA_OK;
+}
+int bra_lane_end(bra_ctx* ctx) {
+  if (!ctx->lane) return BRA_OK;
+  cudaError_t e = cudaEventRecord(ctx->ev_join, ctx->side_stream);
+  ctx->stream = ctx->lane_saved;
+  ctx->lane = 0;
+  BRA_CUDA(e);
+  return BRA_OK;
+}
+int bra_lane_join(bra_ctx* ctx) {
+  BRA_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
   return BRA_OK;
 }
 

@@ -307,8 +307,8 @@ __global__ void __launch_bounds__(256) triinv_join_kernel(int k, int s, int phas
 int bra_tri_inverse_upper(bra_ctx* ctx, int k, const double* R, int64_t ldr, double* Rinv, int64_t ldx) {
   if (k <= 0) return BRA_OK;
   const int nblk = (k + TB - 1) / TB;
-  BRA_CUDA(ctx->tritmp.reserve((size_t)k * k * 8));
-  double* tmp = ctx->tritmp.as<double>();
+  BRA_CUDA(ctx->ws_tritmp().reserve((size_t)k * k * 8));
+  double* tmp = ctx->ws_tritmp().as<double>();
   triinv_diag_kernel<<<nblk, 32, 0, ctx->stream>>>(k, R, ldr, Rinv, ldx);
   ctx->launches++;
   for (int s = TB; s < k; s *= 2) {
