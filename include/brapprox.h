@@ -191,6 +191,16 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
  * negative part first) and BRA_F_U (n x kk eigenvectors); bra_get_info().ksvd = kk.  pheigvals = fetch BRA_F_S only. */
 int bra_pheigfact_f64(bra_ctx* ctx, int64_t n, const double* A, int64_t lda, const bra_opts* opts, const bra_rand* rnd);
 
+/* sketchfact(side, trans, A, opts) (src/sketch.jl:52-66; drivers :213-240, 313-330, 545-562, 674-690): the
+ * early-terminating pivoted QR of the SKETCH of op(A).  side 'l': B = S op(A) (order x n_op) -- the first stage of
+ * idfact / pqrfact / psvdfact; fetch BRA_F_P, BRA_F_T, BRA_F_TAU and BRA_F_BSKETCH (LAPACK layout: R = triu of the first
+ * k rows, reflectors below the diagonal).  side 'r': B = op(A) S (m_op x order), the range-finder form behind prange;
+ * fetch BRA_F_Q (m_op x k, the Householder Q up to the sign of each column), BRA_F_P (order entries), BRA_F_TAU,
+ * BRA_F_BSKETCH (m_op x order), and BRA_F_T when maxdet_tol >= 0.  bra_get_info: k, rounds, orders.  Errors: -2 side
+ * (sketchfact_chkargs, :80-84), the bra_idfact_f64 argument numbers shifted by one, -8 for sketch = :none. */
+int bra_sketchfact_f64(bra_ctx* ctx, char side, char trans, int64_t m, int64_t n, const double* A, int64_t lda,
+                       const bra_opts* opts, const bra_rand* rnd);
+
 /* prange(trans, A, opts) (src/prange.jl:14-62): an orthonormal basis of the range of A (trans 'n'), of A' ('c') or of
  * both ('b', square A; a Hermitian A falls back to 'n', :26).  sketch = :none -> pqrfact(op(A))[:Q] (:50-52); :sub ->
  * prange_sub (:64-77); otherwise the pivoted QR of the right-hand sketch B = op(A) S, sketchfact(:right, trans, A, opts)

@@ -27,6 +27,7 @@ from ._binding import (  # noqa: F401
     LRAOptions,
     PartialHermEigen,
     PartialQR,
+    PQRFactors,
     PartialSVD,
     SKETCH_CODES,
     lib,
@@ -56,6 +57,7 @@ from ._frontend import (  # noqa: F401
     probe_exchange_latency,
     probe_fp64_peak,
     sketch,
+    sketchfact,
     prange,
     snorm,
     snormdiff,

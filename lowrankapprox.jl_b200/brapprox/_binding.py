@@ -96,6 +96,8 @@ lib.bra_trsolve_T_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, _vp, _i64]
 lib.bra_idfact_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand)]
 lib.bra_pqrfact_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand)]
 lib.bra_pheigfact_f64.argtypes = [_vp, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand)]
+lib.bra_sketchfact_f64.argtypes = [_vp, C.c_char, C.c_char, _i64, _i64, _vp, _i64, C.POINTER(bra_opts),
+                                   C.POINTER(bra_rand)]
 lib.bra_prange_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand),
                                C.POINTER(bra_rand)]
 lib.bra_snorm_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _i64, C.POINTER(bra_opts), _i64, _vp,
@@ -424,6 +426,23 @@ class PartialQR:
         M = np.zeros((self.Q.shape[0], self.R.shape[1]))
         M[:, self.p - 1] = self.Q @ self.R
         return M
+
+
+@dataclass
+class PQRFactors:
+    """PartialQRFactors (src/pqr.jl:44-50): what pqrback_postproc returns unless retval is exactly "qr"; the result of
+    sketchfact.  Q / R / T are None when pqrfact_retval does not ask for them."""
+    Q: Optional[np.ndarray]
+    R: Optional[np.ndarray]
+    p: np.ndarray
+    k: int
+    T: Optional[np.ndarray]
+    rounds: List[Tuple[int, int]] = field(default_factory=list)
+
+    def __getitem__(self, key):
+        if key in ("Q", "R", "p", "k", "T"):
+            return getattr(self, key)
+        raise KeyError(key)
 
 
 @dataclass

@@ -351,6 +351,71 @@ def pqrfact(A, opts: Optional[LRAOptions] = None, trans: str = "n", rand=None,
     return F
 
 
+def _orgqr(Bl: np.ndarray, tau: np.ndarray, k: int) -> np.ndarray:
+    """LAPACK.orgqr!(A[:, 1:k], tau, k) (src/pqr.jl:427) on the host: the first k columns of H_1 ... H_k from the
+    reflectors below the diagonal of the factored sketch (result-type arithmetic: order x k, a few hundred rows)."""
+    l = Bl.shape[0]
+    Q = np.zeros((l, k), order="F")
+    Q[np.arange(k), np.arange(k)] = 1.0
+    for j in range(k - 1, -1, -1):
+        v = np.zeros(l)
+        v[j] = 1.0
+        v[j + 1:] = Bl[j + 1:, j]
+        Q[j:, j:] -= tau[j] * np.outer(v[j:], v[j:] @ Q[j:, j:])
+    return Q
+
+
+def sketchfact(A, opts: Optional[LRAOptions] = None, side: str = "left", trans: str = "n", rand=None,
+               ctx: Optional[Context] = None, **kw):
+    """sketchfact(side, trans, A, opts; kw...) (src/sketch.jl:52-66): the early-terminating pivoted QR of the SKETCH of
+    op(A) -- side "left": B = S op(A) (order x n_op), side "right": B = op(A) S (m_op x order).  Returns PartialQR(Q, R, p)
+    when pqrfact_retval is "qr", otherwise PQRFactors(Q, R, p, k, T) with the pieces retval names (src/pqr.jl:434-435).
+    Left side: Q = orgqr of the sketch's reflectors (formed on the host from BRA_F_BSKETCH / BRA_F_TAU; R = triu(B[1:k, :])).
+    Right side: Q is the device's CholeskyQR2 factor of B[:, p[1:k]] (the Householder Q with diag(R) > 0), R follows the same
+    sign convention.  With maxdet swaps, q / r of the swapped factorization are not maintained on the device (only p and
+    T are): asking for them then raises."""
+    sd = str(side).lstrip(":")
+    if sd not in ("left", "right"):
+        raise ValueError("side")                       # sketchfact_chkargs (src/sketch.jl:80-84)
+    tr = _trans(trans)
+    o = _opts(opts, kw)
+    if o.sketch == "none":
+        raise ValueError("sketch")                     # src/sketch.jl:62
+    ctx = ctx or default_context()
+    pA, m, n, lda, keepA = mat_arg(A)
+    contracted = (m if tr == b"n" else n) if sd == "left" else (n if tr == b"n" else m)
+    rp = _RandPack(rand, o, contracted)
+    co = o.to_c()
+    ctx.check(lib.bra_sketchfact_f64(ctx.handle, sd[0].encode(), tr, m, n, pA, lda, C.byref(co), C.byref(rp.c)))
+    inf, rounds, steps = _rounds(ctx)
+    k, nB, mB = int(inf.k), int(inf.n), int(inf.m)
+    rows = int(inf.orders[inf.rounds - 1]) if sd == "left" else mB
+    p = ctx.fetch(B.F_P, (nB,), np.int64)
+    rv = o.pqrfact_retval
+    want_q, want_r, want_t = "q" in rv, "r" in rv, "t" in rv
+    maxdet = 0 < k < nB and o.maxdet_tol >= 0
+    T = ctx.fetch(B.F_T, (k, nB - k)) if (want_t or maxdet) and k > 0 else (np.zeros((0, nB), order="F") if want_t else None)
+    if (want_q or want_r) and maxdet and ctx.maxdet_swaps() > 0:
+        raise ValueError("sketchfact: Q / R after maxdet column swaps are not maintained on the device (p and T are)")
+    Q = R = None
+    if want_q or want_r:
+        Bl = ctx.fetch(B.F_BSKETCH, (rows, nB)) if rows > 0 and nB > 0 else np.zeros((rows, nB), order="F")
+        R = np.asfortranarray(np.triu(Bl[:k, :]))
+        if sd == "left":
+            tau = ctx.fetch(B.F_TAU, (steps[-1],)) if steps[-1] > 0 else np.zeros(0)
+            Q = _orgqr(Bl, tau, k) if want_q else None
+        else:
+            d = np.sign(np.diag(R[:, :k]))
+            d[d == 0] = 1.0
+            R = np.asfortranarray(R * d[:, None])      # the device Q has diag(R) > 0
+            Q = (ctx.fetch(B.F_Q, (mB, k)) if k > 0 else np.zeros((mB, 0), order="F")) if want_q else None
+        if not want_r:
+            R = None
+    if want_q and want_r and not want_t:
+        return B.PartialQR(Q, R, p, rounds)
+    return B.PQRFactors(Q, R, p, k, T if want_t else None, rounds)
+
+
 def prange(A, opts: Optional[LRAOptions] = None, trans: str = "n", rand=None, rand2=None,
            ctx: Optional[Context] = None, **kw):
     """prange(trans, A, opts; kw...) -> Q (src/prange.jl:14-62): an orthonormal basis of the range of A (trans "n"), of

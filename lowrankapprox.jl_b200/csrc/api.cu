@@ -731,6 +731,7 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
     }
     ctx->cur_B = ctx->B.as<double>();
     ctx->cur_ldb = order;
+    ctx->cur_rows = order;
     rc = run_round_qrcp(ctx, o, order, nA, &q);
     if (rc) return rc;
     res.orders[0] = order;
@@ -750,10 +751,12 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
         // this round's sketch was formed while A was still arriving from the host (bra_stage_A)
         ctx->cur_B = ctx->Bspec.as<double>() + ctx->spec_off[round];
         ctx->cur_ldb = ctx->spec_ld;
+        ctx->cur_rows = order;
       } else {
         rc = sketch_round(ctx, trans, m, n, dA, lda, o, rnd, round, order);
         ctx->cur_B = ctx->B.as<double>();
         ctx->cur_ldb = order;
+        ctx->cur_rows = order;
       }
       if (rc) return rc;
       rc = run_round_qrcp(ctx, o, order, nA, &q);
@@ -771,6 +774,7 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
     if (rc) return rc;
     ctx->cur_B = ctx->B.as<double>();
     ctx->cur_ldb = order;
+    ctx->cur_rows = order;
     rc = run_round_qrcp(ctx, o, order, nA, &q);
     if (rc) return rc;
     res.orders[0] = order;
@@ -861,6 +865,7 @@ int bra_prange_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double
       return rc;
     ctx->cur_B = ctx->Bt.as<double>();
     ctx->cur_ldb = M > 0 ? M : 1;
+    ctx->cur_rows = M;
     if ((rc = run_round_qrcp(ctx, o, M, order, &q))) return rc;
     res.orders[round] = order;
     res.ks[round] = q.k;
@@ -1066,8 +1071,9 @@ int bra_fetch(bra_ctx* ctx, int which, void* dst, int64_t ld) {
       break;
     case BRA_F_BSKETCH: {
       if (r.rounds == 0) return BRA_ERR_NOTREADY;
-      const int64_t l = r.orders[r.rounds - 1];
-      BRA_CHECK_ARG(ld >= l, 4, "ld");
+      const int64_t l = ctx->cur_rows;          // sketch order (left sketch) or size(op(A), 1) (right sketch)
+      BRA_CHECK_ARG(ld >= (l > 1 ? l : 1), 4, "ld");
+      if (l <= 0 || n <= 0) break;
       BRA_CUDA(ctx->B2.reserve((size_t)l * n * 8));
       int rc = bra_permute_cols(ctx, ctx->cur_B, ctx->cur_ldb, ctx->B2.as<double>(), l, l, n, ctx->jpvt.as<int64_t>());
       if (rc) return rc;

@@ -226,6 +226,54 @@ int bra_prange_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double*
   return bra_chol_status(ctx);
 }
 
+// sketchfact(side, trans, A, opts) (src/sketch.jl:52-66): the pivoted QR of the SKETCH of op(A) itself.
+//   side 'l': B = S op(A) (order x n_op), its early-terminating QRCP and the ID post-processing -- exactly the first
+//             stage of idfact / pqrfact / psvdfact.  Fetch BRA_F_P, BRA_F_T, BRA_F_TAU, BRA_F_BSKETCH (R on and above the
+//             diagonal of the first k rows, reflectors below: Q = orgqr, R = triu(B[1:k, :])).
+//   side 'r': B = op(A) S (m_op x order), the range-finder form behind prange: additionally Q (BRA_F_Q, m_op x k, the
+//             CholeskyQR2 factor of B[:, p[1:k]]: the Householder Q up to the sign of each column).
+int bra_sketchfact_f64(bra_ctx* ctx, char side, char trans, int64_t m, int64_t n, const double* A, int64_t lda,
+                       const bra_opts* opts, const bra_rand* rnd) {
+  if (!ctx) return -1;
+  BRA_CHECK_ARG(side == 'l' || side == 'r', 2, "side");                 // sketchfact_chkargs, src/sketch.jl:80-84
+  int rc = bra_check_fact_args(ctx, trans, m, n, A, lda, opts);
+  if (rc) return rc < -1 ? rc - 1 : rc;                                  // argument numbers shift by one (side)
+  if (opts->sketch == BRA_SKETCH_NONE) {
+    ctx->set_error("sketchfact: sketch = :none is not a sketch (src/sketch.jl:62)");
+    return -8;
+  }
+  BRA_CUDA(cudaSetDevice(ctx->device));
+  const double* dA;
+  int64_t dlda;
+  if (side == 'l') {
+    if ((rc = bra_stage_A(ctx, trans, m, n, A, lda, opts, rnd, &dA, &dlda))) return rc;
+    if ((rc = bra_sketchfact_core(ctx, trans, m, n, dA, dlda, opts, rnd))) return rc;
+    BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BRA_OK;
+  }
+  if (ctx->world > 1) {
+    ctx->set_error("sketchfact(:right) on a row-sharded matrix is not built");
+    return BRA_ERR_UNSUPPORTED;
+  }
+  bra_opts onone = *opts;            // staging must not start the speculative left-sketch pipeline
+  onone.sketch = BRA_SKETCH_NONE;
+  if ((rc = bra_stage_A(ctx, 'n', m, n, A, lda, &onone, rnd, &dA, &dlda))) return rc;
+  GemmTagGuard gtag(ctx);
+  if ((rc = bra_prange_core(ctx, trans, m, n, dA, dlda, opts, rnd, true))) return rc;
+  ctx->res.have_T = opts->maxdet_tol >= 0 && ctx->res.k > 0 && ctx->res.k < ctx->res.n;
+  const int64_t k = ctx->res.k, M = ctx->res.m;
+  if (k == 0) return BRA_OK;
+  bool fresh = ctx->res.maxdet_done;
+  for (;;) {
+    if ((rc = skeleton_qr(ctx, 'c', ctx->B.as<double>(), ctx->res.n, M, k, opts, fresh))) return rc;
+    ctx->res.have_Q = true;
+    rc = bra_chol_status(ctx);
+    if (rc != BRA_ERR_INTERNAL || fresh) return rc;
+    fresh = true;
+    ctx->skeleton_retries++;
+  }
+}
+
 int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* opts,
                      const bra_rand* rnd) {
   if (!ctx) return -1;

@@ -111,6 +111,7 @@ struct bra_ctx {
   int64_t spec_ld = 0, spec_off[BRA_MAX_ROUNDS] = {0};
   double* cur_B = nullptr;     // sketch of the current round and its leading dimension
   int64_t cur_ldb = 0;
+  int64_t cur_rows = 0;        // rows of cur_B (the sketch order for a left sketch, size(op(A), 1) for a right one)
   int A_sym_state = 0;         // power iteration: 0 unknown, 1 A == A' exactly, -1 not (checked once per factorization)
   int last_jacobi_sweeps = 0;
   int jacobi_kcycles[8] = {0};

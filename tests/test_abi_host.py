@@ -172,3 +172,15 @@ def test_random_input_shapes_are_checked_on_the_host():
     _RandPack([{"r": np.ones(136, dtype=np.int64)}], o, 50)
     with pytest.raises(ValueError, match="DimensionMismatch"):
         _RandPack([{"r": np.ones(40, dtype=np.int64)}], o, 50)
+
+
+def test_sketchfact_argument_checks_without_gpu():
+    """sketchfact_chkargs (src/sketch.jl:80-84) and chktrans fire before any device work."""
+    import brapprox
+    A = np.zeros((4, 4))
+    with pytest.raises(ValueError):
+        brapprox.sketchfact(A, side="up")
+    with pytest.raises(ValueError):
+        brapprox.sketchfact(A, trans="x")
+    with pytest.raises(ValueError):
+        brapprox.sketchfact(A, sketch="none")
