@@ -88,6 +88,7 @@ typedef struct bra_opts {
   uint64_t seed;             /* fast mode: Philox key */
   int32_t verb;
   int32_t reserved;
+  double pheig_orthtol;      /* >= 0; default sqrt(eps): pheigorth! cluster tolerance (src/pheig.jl:342-364) */
 } bra_opts;
 
 /* Per-round random inputs in the order the reference draws them (SURVEY.md
@@ -201,6 +202,16 @@ int bra_pheigfact_f64(bra_ctx* ctx, int64_t n, const double* A, int64_t lda, con
 int bra_sketchfact_f64(bra_ctx* ctx, char side, char trans, int64_t m, int64_t n, const double* A, int64_t lda,
                        const bra_opts* opts, const bra_rand* rnd);
 
+/* CUR(A, rows, cols) / HermCUR(A, cols) (src/cur.jl:85-109): the factors of a CUR decomposition from its index sets
+ * (1-based, k entries each; what curfact returns).  C = A[:, cols] (BRA_F_Q, m x k), R = A[rows, :] (BRA_F_R, k x n), and
+ * the k x k core on the device (one-sided Jacobi):
+ *   hermitian == 0:  U, s, V = svd!(C[rows, :]);  U2 = PartialSVD(V, 1 ./ s, U'):
+ *                    BRA_F_U = V (k x k), BRA_F_S = 1 ./ s (s descending), BRA_F_VT = U' (k x k);
+ *   hermitian != 0:  F = eigen!(Hermitian(C[cols, :])) (rows is ignored, A must be square):
+ *                    BRA_F_S = 1 ./ F.values (values ascending), BRA_F_U = F.vectors (k x k); no R. */
+int bra_cur_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, int64_t k, const int64_t* rows1,
+                const int64_t* cols1, int hermitian);
+
 /* prange(trans, A, opts) (src/prange.jl:14-62): an orthonormal basis of the range of A (trans 'n'), of A' ('c') or of
  * both ('b', square A; a Hermitian A falls back to 'n', :26).  sketch = :none -> pqrfact(op(A))[:Q] (:50-52); :sub ->
  * prange_sub (:64-77); otherwise the pivoted QR of the right-hand sketch B = op(A) S, sketchfact(:right, trans, A, opts)
@@ -288,6 +299,8 @@ int bra_probe_exchange2(bra_ctx* ctx, int ctas, int hw, int mode, int leaders, i
 int bra_debug_qrcp_phases(bra_ctx* ctx, int32_t* out6);
 /* Sweeps the last psvd core (k x k Jacobi SVD) needed. */
 int bra_debug_jacobi_sweeps(bra_ctx* ctx);
+/* test hook: pheigorth! (src/pheig.jl:342-364) on host arrays, in place (vals ascending, V rows x kk, ld) */
+int bra_debug_pheigorth(bra_ctx* ctx, const double* vals, double* V, int64_t ld, int rows, int kk, double orthtol);
 /* Skeleton QRs (the QR of A[:, sk] in pqrfact / psvdfact / prange, src/pqr.jl:297-305) this context had to redo with a
  * fresh Gaussian preconditioner after the Gram Cholesky of the first attempt broke down (cumulative). */
 int bra_debug_skeleton_retries(bra_ctx* ctx);

@@ -35,6 +35,7 @@ from ._binding import (  # noqa: F401
 )
 from ._dist import block_shard, broadcast_bytes, init_comm, row_shard  # noqa: F401
 from ._frontend import (  # noqa: F401
+    CUR,
     cur,
     curfact,
     default_context,

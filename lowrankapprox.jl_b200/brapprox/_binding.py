@@ -28,7 +28,7 @@ class bra_opts(C.Structure):
         ("sketch", C.c_int32), ("sketch_randn_niter", C.c_int32), ("sketchfact_adap", C.c_int32),
         ("retval_mask", C.c_int32), ("maxdet_tol", C.c_double), ("maxdet_niter", C.c_int64),
         ("samp_a", C.c_int64), ("samp_b", C.c_int64), ("seed", C.c_uint64), ("verb", C.c_int32),
-        ("reserved", C.c_int32),
+        ("reserved", C.c_int32), ("pheig_orthtol", C.c_double),
     ]
 
 
@@ -98,6 +98,7 @@ lib.bra_pqrfact_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, C.POINTER(
 lib.bra_pheigfact_f64.argtypes = [_vp, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand)]
 lib.bra_sketchfact_f64.argtypes = [_vp, C.c_char, C.c_char, _i64, _i64, _vp, _i64, C.POINTER(bra_opts),
                                    C.POINTER(bra_rand)]
+lib.bra_cur_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, C.c_int]
 lib.bra_prange_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand),
                                C.POINTER(bra_rand)]
 lib.bra_snorm_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _i64, C.POINTER(bra_opts), _i64, _vp,
@@ -185,6 +186,7 @@ class LRAOptions:
         o.samp_a, o.samp_b = self._samp_affine()
         o.seed = self.seed
         o.verb = int(bool(self.verb))
+        o.pheig_orthtol = self.pheig_orthtol
         return o
 
 
@@ -359,6 +361,29 @@ class CURPackedU:
         if key == "k":
             return len(self.cols)
         raise KeyError(key)
+
+
+@dataclass
+class CUR:
+    """CUR / HermCUR (src/cur.jl:60-72): A ~ C U R with C = A[:, cols], R = A[rows, :] and U the pseudo-inverse of the
+    k x k core A[rows, cols], kept factored: PartialSVD(V, 1 ./ s, U') (general) or PartialHermEigen(1 ./ values,
+    vectors) (Hermitian; then R = C')."""
+    rows: np.ndarray
+    cols: np.ndarray
+    C: np.ndarray
+    U: object
+    R: Optional[np.ndarray]
+
+    def __getitem__(self, key):
+        if key in ("rows", "cols", "C", "U", "R"):
+            return getattr(self, key) if not (key == "R" and self.R is None) else self.C.T
+        if key == "k":
+            return len(self.cols)
+        raise KeyError(key)
+
+    def matrix(self) -> np.ndarray:
+        R = self.R if self.R is not None else self.C.T
+        return self.C @ (self.U.matrix() @ R)
 
 
 @dataclass

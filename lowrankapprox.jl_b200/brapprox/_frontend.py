@@ -257,6 +257,40 @@ def curfact(A, opts: Optional[LRAOptions] = None, rand=None, ctx: Optional[Conte
     return B.CURPackedU(rows[:k], cols[:k])
 
 
+def CUR(A, rows, cols=None, ctx: Optional[Context] = None):
+    """CUR(A, U::CURPackedU) / CUR(A, rows, cols) / HermCUR(A, cols) (src/cur.jl:85-109): the factors of the CUR
+    decomposition named by the index sets curfact returned -- C, R and the pseudo-inverse of the k x k core
+    (svd! / eigen!(Hermitian(.)) in the reference; the one-sided Jacobi on the device here)."""
+    herm = False
+    if isinstance(rows, B.CURPackedU):
+        U = rows
+        rows, cols, herm = U.rows, U.cols, U.hermitian
+    elif cols is None:
+        cols, herm = rows, True                         # HermCUR(A, cols)
+    ctx = ctx or default_context()
+    pA, m, n, lda, keepA = mat_arg(A)
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    cols = np.ascontiguousarray(cols, dtype=np.int64)
+    k = len(cols)
+    if len(rows) != k:
+        raise ValueError("DimensionMismatch: rows and cols")
+    if herm and m != n:
+        raise ValueError("matrix is not square")
+    for idx, lim in ((rows, m), (cols, n)):
+        if k and (idx.min() < 1 or idx.max() > lim):
+            raise IndexError("BoundsError")
+    ctx.check(lib.bra_cur_f64(ctx.handle, m, n, pA, lda, k, C.c_void_p(rows.ctypes.data), C.c_void_p(cols.ctypes.data),
+                              int(herm)))
+    Cm = ctx.fetch(B.F_Q, (m, k)) if k else np.zeros((m, 0), order="F")
+    s = ctx.fetch(B.F_S, (k,)) if k else np.zeros(0)
+    V = ctx.fetch(B.F_U, (k, k)) if k else np.zeros((0, 0), order="F")
+    if herm:
+        return B.CUR(rows, cols, Cm, B.PartialHermEigen(s, V), None)
+    Ut = ctx.fetch(B.F_VT, (k, k)) if k else np.zeros((0, 0), order="F")
+    Rm = ctx.fetch(B.F_R, (k, n)) if k else np.zeros((0, n), order="F")
+    return B.CUR(rows, cols, Cm, B.PartialSVD(V, s, Ut), Rm)
+
+
 def cur(A, *args, **kw):
     """cur(A, ...) -> (rows, cols) (src/cur.jl:568-571)."""
     U = curfact(A, *args, **kw)

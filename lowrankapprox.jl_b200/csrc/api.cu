@@ -377,6 +377,7 @@ void bra_opts_default(bra_opts* o) {
   o->samp_b = 0;
   o->seed = 0;
   o->verb = 1;
+  o->pheig_orthtol = 1.4901161193847656e-08;      // sqrt(eps(Float64)), src/LowRankApprox.jl:102
 }
 
 int bra_create(bra_ctx** out, int device) {
@@ -512,6 +513,7 @@ int bra_chkopts(bra_ctx* ctx, const bra_opts* o) {
   BRA_CHECK_ARG(o->nb > 0, 2, "nb");
   BRA_CHECK_ARG(o->rtol >= 0, 2, "rtol");
   BRA_CHECK_ARG(o->sketch >= BRA_SKETCH_NONE && o->sketch <= BRA_SKETCH_SUB, 2, "sketch");
+  BRA_CHECK_ARG(o->pheig_orthtol >= 0, 2, "pheig_orthtol");           // src/LowRankApprox.jl:136
   return BRA_OK;
 }
 

@@ -967,4 +967,50 @@ def pheigfact(A: np.ndarray, opts: LRAOptions, rand: Optional[RandomInputs] = No
     if kn + kp < k:
         idx = np.r_[0:kn, k - kp:k]
         w, X = w[idx], X[:, idx]
+    X = np.array(X, order="F")
+    pheigorth(w, X, opts)
     return w, Q @ X, V
+
+
+def pheigorth(values: np.ndarray, vectors: np.ndarray, opts: LRAOptions) -> None:
+    """pheigorth! (src/pheig.jl:342-364): runs of adjacent eigenvalues with symrelerr(va, vb) = 2|va - vb| / |va + vb|
+    (src/util.jl:118) <= pheig_orthtol are re-orthogonalised in place, v_j -= <v_i, v_j> v_i for i < j in the run (no
+    normalisation)."""
+    n = len(values)
+    a = 0
+    while a < n:
+        va = values[a]
+        b = a + 1
+        while b < n:
+            vb = values[b]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                err = 2 * abs((va - vb) / (va + vb))
+            if err > opts.pheig_orthtol:
+                break
+            b += 1
+        b -= 1
+        for i in range(a, b + 1):
+            for j in range(i + 1, b + 1):
+                vectors[:, j] -= (vectors[:, i] @ vectors[:, j]) * vectors[:, i]
+        a = b + 1
+
+
+def cur_core(A: np.ndarray, rows: np.ndarray, cols: np.ndarray):
+    """CUR(A, U::CURPackedU) (src/cur.jl:85-93): C = A[:, cols], R = A[rows, :], U, s, V = svd!(C[rows, :]) and
+    U2 = PartialSVD(V, 1 ./ s, U') -> (C, (V, 1/s, U'), R).  rows / cols 1-based."""
+    C = np.asfortranarray(A[:, cols - 1])
+    R = np.asfortranarray(A[rows - 1, :])
+    import scipy.linalg as sla
+    U, s, Vt = sla.svd(np.asfortranarray(C[rows - 1, :]), full_matrices=False, lapack_driver="gesdd")
+    with np.errstate(divide="ignore"):
+        return C, (np.asfortranarray(Vt.T), 1.0 / s, np.asfortranarray(U.T)), R
+
+
+def hermcur_core(A: np.ndarray, cols: np.ndarray):
+    """HermCUR(A, U) (src/cur.jl:99-105): C = A[:, cols], F = eigen!(Hermitian(C[cols, :])),
+    U = PartialHermEigen(1 ./ F.values, F.vectors) -> (C, (1/values, vectors))."""
+    C = np.asfortranarray(A[:, cols - 1])
+    W = C[cols - 1, :]
+    w, X = np.linalg.eigh(np.triu(W) + np.triu(W, 1).T)      # Hermitian(.) reads the upper triangle
+    with np.errstate(divide="ignore"):
+        return C, (1.0 / w, X)
