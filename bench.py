@@ -266,6 +266,39 @@ def run_c3(ctx, ext, dev, steps=5, n=16384):
                          "algorithmic_bytes": bytes_sk, "peak_source": src}}
 
 
+def run_c2c(ctx, ext, dev, A_square, steps=5):
+    """The (:left, :c) forms at the headline shape: idfact(:c) on the C2 matrix against idfact(:n),
+    and psvdfact of a wide 4096 x 8192 matrix (m < n: the reference factors A', src/psvd.jl:256).  The :c sketch runs on
+    the TMA + DMMA kernel through the transposed copy of A cached per factorization."""
+    import torch
+    from brapprox._binding import DeviceMatrix
+    from brapprox._frontend import idfact_device, psvdfact_device
+    out = {"workload": "C2c: idfact trans=:c 8192x8192 and psvdfact 4096x8192 FP64 rtol=1e-12 sketch=randn, A resident"}
+    for tr in ("n", "c"):
+        t, inf = _timed(ext, lambda sd: idfact_device(A_square, rtol=RTOL, trans=tr, seed=sd, ctx=ctx), steps, 2)
+        out[f"idfact_{tr}_ms"] = t * 1e3
+        out[f"idfact_{tr}_k"] = int(inf.k)
+    out["c_over_n"] = out["idfact_c_ms"] / out["idfact_n_ms"]
+    m, n = 4096, 8192
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    U, _ = torch.linalg.qr(torch.randn(m, RANK_GEN, dtype=torch.float64, device=dev, generator=g))
+    V, _ = torch.linalg.qr(torch.randn(n, RANK_GEN, dtype=torch.float64, device=dev, generator=g))
+    sig = 10.0 ** (-DECADES * torch.arange(RANK_GEN, dtype=torch.float64, device=dev) / JDIV)
+    Wt = ((V * sig) @ U.T).contiguous()                   # n x m row-major == m x n column-major
+    W = DeviceMatrix(Wt.data_ptr(), m, n, m, keep=Wt)
+    ctx.profile_enable(False)
+    t, inf = _timed(ext, lambda sd: psvdfact_device(W, rtol=RTOL, seed=sd, ctx=ctx), steps, 2,
+                    after_warmup=lambda: ctx.profile_enable(True))
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    out["psvdfact_4096x8192_ms"] = t * 1e3
+    out["psvdfact_4096x8192_k"] = int(inf.k)
+    out["psvdfact_4096x8192_stage_ms"] = {k2: v[0] / steps for k2, v in prof.items() if v[0] > 0}
+    out["generic_gemm_note"] = "no gemm_generic_kernel launch with a contraction >= 1024 remains on these paths"
+    return out
+
+
 def run_c1(ctx, ext, dev, steps=50, n=1024):
     """BASELINE config 1 (the reference's own CPU-runnable case): Hilbert 1024^2, rtol=1e-15, sketch=:randn -- one round
     of order 40, k ~ 26: pure latency, reported in microseconds (a roofline fraction is not meaningful here)."""
@@ -354,13 +387,61 @@ def run_c4(ctx, ext, dev, rank, world, m_total=1048576, n=4096, steps=2):
     rounds = [(int(inf.orders[i]), int(inf.ks[i])) for i in range(inf.rounds)]
     f_sk = 2.0 * m_total * n * sum(l for l, _ in rounds)
     k = int(inf.k)
-    f_tail = 4.0 * m_total * k * k * 2 + float(k) * k * (n - k)
+    # F_C = 2mk^2 - 2/3 k^3 (QR of C) + 2mk^2 (forming Q) + k^2(n-k) (R = R1 [I T]) -- the ALGORITHMIC count, not
+    # the 8mk^2 this implementation's CholeskyQR2 really spends
+    f_tail = 4.0 * m_total * k * k - (2.0 / 3.0) * k ** 3 + float(k) * k * (n - k)
     nrun = steps
+    # the non-adaptive single-sketch form SURVEY 8(d) also asks for: sketchfact_adap = false, one sketch of order 264
+    t1, inf1 = _timed(ext, lambda sd: pqrfact_device(A, rtol=RTOL, rank=256, sketchfact_adap=False, seed=sd, ctx=ctx), steps, 1)
+    f1 = 2.0 * m_total * n * int(inf1.orders[0]) + f_tail
     return {"workload": f"C4: pqrfact {m_total}x{n} FP64 rank=256 cap, sketch=randn adaptive, rows sharded over "
                         f"{world} GPU(s) ({ml} rows here), one sketch all-reduce per round", "t": t,
             "rounds_order_k": rounds, "k": k, "algorithmic_gflop_total": (f_sk + f_tail) / 1e9,
             "stage_ms": {k2: v[0] / nrun for k2, v in prof.items() if v[0] > 0},
-            "collectives_per_factorization": None}
+            "collectives_per_factorization": None,
+            "nonadaptive_l264": {"t": t1, "order": int(inf1.orders[0]), "k": int(inf1.k), "algorithmic_gflop_total": f1 / 1e9}}
+
+
+def run_c4_parity(ctx, dev, rank, world, m=131072, n=4096):
+    """Parity of the row-sharded path at this world size: a reduced-m C4 matrix (identical on every rank) factored over
+    the ranks' row blocks against the SAME library on one GPU without a communicator, same fast-mode seed (Omega is keyed
+    by the global row index, so only the summation order of the all-reduce differs)."""
+    import torch
+    import brapprox
+    from brapprox import _binding as B
+    from brapprox._binding import DeviceMatrix
+    from brapprox._frontend import pqrfact_device
+    r = 512
+    g = torch.Generator(device=dev)
+    g.manual_seed(44)
+    Y, _ = torch.linalg.qr(torch.randn(n, r, dtype=torch.float64, device=dev, generator=g))
+    sig = 10.0 ** (-6.0 * torch.arange(r, dtype=torch.float64, device=dev) / 256.0)
+    X = torch.randn((m, r), dtype=torch.float64, device=dev, generator=g) / (m ** 0.5)
+    At = ((X * sig) @ Y.T).T.contiguous()                  # n x m row-major == m x n column-major, identical on all ranks
+    del X, Y
+    row0, ml = brapprox.row_shard(m, rank, world)
+    Aloc_t = At[:, row0:row0 + ml].contiguous()
+    Aloc = DeviceMatrix(Aloc_t.data_ptr(), ml, n, ml, keep=Aloc_t)
+    ctx.set_row_shard(row0, m)
+    inf = pqrfact_device(Aloc, rtol=RTOL, rank=256, seed=5, ctx=ctx)
+    k = int(inf.k)
+    p = ctx.fetch(B.F_P, (n,), "int64")
+    R = ctx.fetch(B.F_R, (k, n))
+    ctx.set_row_shard(0, 0)
+    out = None
+    if rank == 0:
+        ref = brapprox.Context(dev.index)
+        Afull = DeviceMatrix(At.data_ptr(), m, n, m, keep=At)
+        inf1 = pqrfact_device(Afull, rtol=RTOL, rank=256, seed=5, ctx=ref)
+        p1 = ref.fetch(B.F_P, (n,), "int64")
+        R1 = ref.fetch(B.F_R, (int(inf1.k), n))
+        same_k = int(inf1.k) == k
+        out = {"workload": f"pqrfact {m}x{n} rank=256 over {world} row blocks vs 1 GPU, same seed",
+               "k": k, "k_equal": same_k, "p_equal": bool(same_k and (p[:k] == p1[:k]).all()),
+               "rounds_equal": [int(inf.orders[i]) for i in range(inf.rounds)] == [int(inf1.orders[i]) for i in range(inf1.rounds)],
+               "max_abs_R_diff_over_R11": float(abs(R - R1).max() / abs(R1[0, 0])) if same_k else None}
+        ref.close()
+    return out
 
 
 def main():
@@ -546,6 +627,11 @@ def main():
     # NCCL all-reduce) and C5 (batched, no collective) over all ranks, strong scaling, max over ranks ----
     extra = {}
     if not args.no_extra:
+        try:
+            if rank == 0:
+                extra["C2c"] = run_c2c(ctx, ext, dev, A)
+        except Exception as e:      # a side measurement must never take the headline down
+            extra["C2c"] = {"error": repr(e)[:300]}
         del A, At
         torch.cuda.empty_cache()
         fp64_tf = None
@@ -594,6 +680,12 @@ def main():
             c4["frac_of_fp64_peak_per_gpu"] = c4["achieved_tflops_all_ranks"] / world / fp64_peak
             c4["n_gpus"] = world
             c4["scaling"] = "strong"
+            na = c4["nonadaptive_l264"]
+            tna = over_ranks(na.pop("t"), dist.ReduceOp.MAX if world > 1 else None)
+            na["ms_per_factorization"] = tna * 1e3
+            na["frac_of_fp64_peak_per_gpu"] = na["algorithmic_gflop_total"] / 1e3 / tna / world / fp64_peak
+            if world > 1:
+                c4["parity_vs_1gpu"] = run_c4_parity(ctx, dev, rank, world)
             extra["C4"] = c4
             torch.cuda.empty_cache()
         except Exception as e:

@@ -286,9 +286,15 @@ __global__ void __launch_bounds__(256, 3) srft_kernel(const __grid_constant__ CU
         dft4(a0, a1, a2, a3, y[0], y[2], y[4], y[6]);
         dft4(c0, c1, c2, c3, y[1], y[3], y[5], y[7]);
         z[0] = y[0];
-        const int jt = j * tw;
+        if (h == 1) {
+          // last stage of the decimation (N == 8): every twiddle is W^0 = 1 -- no table reads, no multiplies
 #pragma unroll
-        for (int sI = 1; sI < 8; ++sI) z[sI * hs] = cmul(y[sI], W[(sI * jt) & (l - 1)]);
+          for (int sI = 1; sI < 8; ++sI) z[sI * hs] = y[sI];
+        } else {
+          const int jt = j * tw;
+#pragma unroll
+          for (int sI = 1; sI < 8; ++sI) z[sI * hs] = cmul(y[sI], W[(sI * jt) & (l - 1)]);
+        }
         q += dq;
         bf += db;
         if (q >= Qc) {
@@ -312,11 +318,17 @@ __global__ void __launch_bounds__(256, 3) srft_kernel(const __grid_constant__ CU
         double2 y0, y1, y2, y3;
         dft4(ldz(z, b * N + j, q), ldz(z + hs, b * N + j + h, q), ldz(z + 2 * hs, b * N + j + 2 * h, q),
              ldz(z + 3 * hs, b * N + j + 3 * h, q), y0, y1, y2, y3);
-        const int jt = j * tw;
         z[0] = y0;
-        z[hs] = cmul(y1, W[jt & (l - 1)]);
-        z[2 * hs] = cmul(y2, W[(2 * jt) & (l - 1)]);
-        z[3 * hs] = cmul(y3, W[(3 * jt) & (l - 1)]);
+        if (h == 1) {                     // N == 4: all twiddles are 1
+          z[hs] = y1;
+          z[2 * hs] = y2;
+          z[3 * hs] = y3;
+        } else {
+          const int jt = j * tw;
+          z[hs] = cmul(y1, W[jt & (l - 1)]);
+          z[2 * hs] = cmul(y2, W[(2 * jt) & (l - 1)]);
+          z[3 * hs] = cmul(y3, W[(3 * jt) & (l - 1)]);
+        }
         q += dq;
         bf += db;
         if (q >= Qc) {
