@@ -720,8 +720,9 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
     // memory), so this is the classical expensive path -- functional, not a benchmarked one.
     const int64_t mA = res.m;
     order = mA;
-    if (mA >= (int64_t(1) << 14) + 4096) {
-      ctx->set_error("sketch = :none needs the Householder vector in shared memory: at most ~20000 rows of op(A)");
+    if (mA >= (int64_t(1) << 14) + 4096 && !bra_qrcp_blocked_ok(mA, nA, (int)(o->nb < 32 ? o->nb : 32), ctx->num_sms)) {
+      ctx->set_error("sketch = :none on more than ~20000 rows needs the blocked kernel: nb <= 32 and at most 128 columns "
+                     "of op(A) per SM");
       return BRA_ERR_UNSUPPORTED;
     }
     BRA_CUDA(ctx->B.reserve((size_t)(mA > 0 ? mA : 1) * (nA > 0 ? nA : 1) * 8));
@@ -846,8 +847,8 @@ int bra_prange_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double
   ctx->Apanels_state = 0;
   ctx->A_sym_state = 0;
   ctx->spec_rounds = 0;
-  if (M >= (int64_t(1) << 14) + 4096) {
-    ctx->set_error("prange needs the Householder vector of the tall sketch in shared memory: at most ~20000 rows of op(A)");
+  if (M >= (int64_t(1) << 14) + 4096 && o->nb > 32) {
+    ctx->set_error("prange on more than ~20000 rows of op(A) needs the blocked QR kernel: nb <= 32");
     return BRA_ERR_UNSUPPORTED;
   }
   QrcpOut q = {0, 0, 0, 0};

@@ -186,6 +186,10 @@ struct QrcpOut {
 };
 int bra_qrcp_run(bra_ctx* ctx, double* B, int64_t ldb, int l, int64_t n, int kcap, int nb,
                  double atol, double rtol, QrcpOut* out, bool nopivot = false);
+// qrcp_blocked.cu: blocked dlaqps for tall matrices (trailing update on DMMA)
+bool bra_qrcp_blocked_ok(int64_t l, int64_t n, int nb, int num_sms);
+int bra_qrcp_blocked_run(bra_ctx* ctx, double* B, int64_t ldb, int64_t l, int64_t n, int kcap, int nb, double atol,
+                         double rtol, QrcpOut* out);
 int bra_permute_cols(bra_ctx* ctx, const double* src, int64_t lds, double* dst, int64_t ldd,
                      int64_t rows, int64_t n, const int64_t* jpvt1);
 int bra_gather_R(bra_ctx* ctx, const double* B, int64_t ldb, int64_t n, int k,

@@ -614,6 +614,10 @@ int bra_qrcp_run(bra_ctx* ctx, double* B, int64_t ldb, int l, int64_t n, int kca
   out->status = 0;
   if (kcap <= 0 || n <= 0 || l <= 0) return BRA_OK;
   const int nbe = nb < kcap ? nb : kcap;
+  // tall problems (more rows than the on-chip kernel of qrcp_fast.cu takes): the blocked dlaqps with the trailing update
+  // on the FP64 tensor cores (qrcp_blocked.cu)
+  if (!nopivot && l > 576 && bra_qrcp_blocked_ok(l, n, nbe, ctx->num_sms))
+    return bra_qrcp_blocked_run(ctx, B, ldb, l, n, kcap, nb, atol, rtol, out);
 
   // grid: one CTA per SM, but keep >= 8 columns per CTA
   int G = ctx->num_sms < MAXG ? ctx->num_sms : MAXG;
