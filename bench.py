@@ -248,6 +248,7 @@ def run_c3(ctx, ext, dev, steps=5, n=16384):
     At = ((V * sig) @ U.T).contiguous()
     del U, V
     A = DeviceMatrix(At.data_ptr(), n, n, n, keep=At)
+    torch.cuda.synchronize(dev)
     t, inf = _timed(ext, lambda sd: idfact_device(A, rtol=RTOL, sketch="srft", seed=sd, ctx=ctx), steps, 2,
                     after_warmup=lambda: ctx.profile_enable(True))
     prof = ctx.profile_read()
@@ -287,6 +288,7 @@ def run_c2c(ctx, ext, dev, A_square, steps=5):
     sig = 10.0 ** (-DECADES * torch.arange(RANK_GEN, dtype=torch.float64, device=dev) / JDIV)
     Wt = ((V * sig) @ U.T).contiguous()                   # n x m row-major == m x n column-major
     W = DeviceMatrix(Wt.data_ptr(), m, n, m, keep=Wt)
+    torch.cuda.synchronize(dev)
     ctx.profile_enable(False)
     t, inf = _timed(ext, lambda sd: psvdfact_device(W, rtol=RTOL, seed=sd, ctx=ctx), steps, 2,
                     after_warmup=lambda: ctx.profile_enable(True))
@@ -378,11 +380,14 @@ def run_c4(ctx, ext, dev, rank, world, m_total=1048576, n=4096, steps=2):
         At[:, c0:c1] = (X @ Ys).T
     del Y, Ys
     A = DeviceMatrix(At.data_ptr(), ml, n, ml, keep=At)
+    torch.cuda.synchronize(dev)
     ctx.set_row_shard(row0, m_total)
     t, inf = _timed(ext, lambda sd: pqrfact_device(A, rtol=RTOL, rank=256, seed=sd, ctx=ctx), steps, 1,
                     after_warmup=lambda: ctx.profile_enable(True))
     prof = ctx.profile_read()
     ctx.profile_enable(False)
+    # the non-adaptive single-sketch form SURVEY 8(d) also asks for: sketchfact_adap = false, one sketch of order 264
+    t1, inf1 = _timed(ext, lambda sd: pqrfact_device(A, rtol=RTOL, rank=256, sketchfact_adap=False, seed=sd, ctx=ctx), steps, 1)
     ctx.set_row_shard(0, 0)
     rounds = [(int(inf.orders[i]), int(inf.ks[i])) for i in range(inf.rounds)]
     f_sk = 2.0 * m_total * n * sum(l for l, _ in rounds)
@@ -391,8 +396,6 @@ def run_c4(ctx, ext, dev, rank, world, m_total=1048576, n=4096, steps=2):
     # the 8mk^2 this implementation's CholeskyQR2 really spends
     f_tail = 4.0 * m_total * k * k - (2.0 / 3.0) * k ** 3 + float(k) * k * (n - k)
     nrun = steps
-    # the non-adaptive single-sketch form SURVEY 8(d) also asks for: sketchfact_adap = false, one sketch of order 264
-    t1, inf1 = _timed(ext, lambda sd: pqrfact_device(A, rtol=RTOL, rank=256, sketchfact_adap=False, seed=sd, ctx=ctx), steps, 1)
     f1 = 2.0 * m_total * n * int(inf1.orders[0]) + f_tail
     return {"workload": f"C4: pqrfact {m_total}x{n} FP64 rank=256 cap, sketch=randn adaptive, rows sharded over "
                         f"{world} GPU(s) ({ml} rows here), one sketch all-reduce per round", "t": t,
@@ -422,6 +425,7 @@ def run_c4_parity(ctx, dev, rank, world, m=131072, n=4096):
     row0, ml = brapprox.row_shard(m, rank, world)
     Aloc_t = At[:, row0:row0 + ml].contiguous()
     Aloc = DeviceMatrix(Aloc_t.data_ptr(), ml, n, ml, keep=Aloc_t)
+    torch.cuda.synchronize(dev)        # the library runs on its own stream: torch must have finished writing the inputs
     ctx.set_row_shard(row0, m)
     inf = pqrfact_device(Aloc, rtol=RTOL, rank=256, seed=5, ctx=ctx)
     k = int(inf.k)
