@@ -31,7 +31,10 @@ struct BatchParams {
   int m, n, l, kcap, nb;
   int nstages;             // tile stages in shared memory (2 unless the block is too tall)
   double atol, rtol;
-  const int64_t* perm;     // 1-based randperm(m); block b at perm + b*perm_stride (0 = shared by all blocks)
+  const int64_t* perm;     // 1-based randperm(m); block b at perm + b*perm_stride (0 = shared by all blocks);
+                           // nullptr: fast mode -- every block draws its OWN permutation and weights in the kernel
+                           // (the reference draws per call of sketch_sprn, i.e. per block: src/sketch.jl:575-579)
+  uint64_t seed;           // fast mode: key of the per-block streams
   int64_t perm_stride;
   const double* s;         // weights, same layout
   int64_t s_stride;
@@ -44,6 +47,13 @@ struct BatchParams {
   int32_t* status;         // [block id]: 0 ok, 1 T slot too small (k_b > ldT)
   long long* dbg;          // [CTA][4] cycles: tables+sketch, registers+norms, QRCP, outputs+T (diagnostic)
 };
+
+__device__ __forceinline__ uint64_t bsplitmix(uint64_t s0, uint64_t i) {      // (i+1)-th output of SplitMix64 seeded s0
+  uint64_t z = s0 + (i + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
 
 __global__ void __launch_bounds__(BT, 1) idfact_batched_kernel(BatchParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -75,22 +85,105 @@ __global__ void __launch_bounds__(BT, 1) idfact_batched_kernel(BatchParams P) {
     const int b = P.blocks ? P.blocks[it] : it;
     const double* Ab = P.A + (int64_t)b * P.strideA;
     __syncthreads();
-    if (!tables_loaded || P.perm_stride != 0 || P.s_stride != 0) {
+    // tile T = columns 16T..16T+15 of A_b, all m rows, staged as tile[r][c] (row stride 17) by 8-byte cp.async: warp w
+    // copies column w (lanes = consecutive rows: coalesced global reads, conflict-free shared stores)
+    auto issue = [&](int T) {
+      const int c = T * TC + warp;                 // BW == TC: one column per warp
+      if (c < n) {
+        const double* g = Ab + (int64_t)c * P.lda;
+        double* d = tiles + (size_t)(T % nst) * tile_elems + warp;
+        for (int r = lane; r < m; r += 32)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(d + (size_t)r * TS)),
+                       "l"(g + r)
+                       : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // double buffered: the first tile is already on its way while the tables (and, in fast mode, this block's own
+    // permutation) are built in the second stage's memory
+    const bool early = nst > 1;
+    if (early) issue(0);
+    if (!tables_loaded || P.perm_stride != 0 || P.s_stride != 0 || P.perm == nullptr) {
       // tables in [t][i] order (term t of sketch row i at t*l + i): lanes = sketch rows read consecutive words
-      const int64_t* pb = P.perm + (int64_t)b * P.perm_stride;
-      const double* sb = P.s + (int64_t)b * P.s_stride;
+      const int64_t* pb = P.perm ? P.perm + (int64_t)b * P.perm_stride : nullptr;
+      const double* sb = P.perm ? P.s + (int64_t)b * P.s_stride : nullptr;
+      unsigned long long* skey = reinterpret_cast<unsigned long long*>(tiles + (early ? tile_elems : 0));   // a free stage
+      const uint64_t bkey = P.seed * 0x9E3779B97F4A7C15ull + (uint64_t)(b + 1) * 0xD1B54A32D192ED03ull;
+      if (!P.perm) {
+        // randperm(m) for THIS block: m random 53-bit keys with the row index in the low 11 bits, bitonic sort in
+        // shared memory (m <= ~1500 < 2048), the sorted indices are the permutation
+        int n2 = 1;
+        while (n2 < m) n2 <<= 1;
+        if (n2 == BT) {
+          // one key per thread (the C5 shape, 256 < m <= 512): bitonic network with the intra-warp stages on shuffles,
+          // 32-bit keys (21 random bits | 11 index bits: ties are broken by the index, still a permutation)
+          unsigned* sk32 = reinterpret_cast<unsigned*>(skey) + 2 * BT;        // exchange buffer behind the result
+          unsigned v = tid < m ? (((unsigned)(bsplitmix(bkey, (uint64_t)tid) >> 32) & ~0x7FFu) | (unsigned)tid) : 0xFFFFFFFFu;
+          for (int kk = 2; kk <= BT; kk <<= 1)
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+              unsigned o;
+              if (j >= 32) {
+                sk32[tid] = v;
+                __syncthreads();
+                o = sk32[tid ^ j];
+                __syncthreads();
+              } else {
+                o = __shfl_xor_sync(0xffffffffu, v, j);
+              }
+              const bool keep_min = ((tid & j) == 0) == ((tid & kk) == 0);
+              v = keep_min ? min(v, o) : max(v, o);
+            }
+          skey[tid] = (unsigned long long)v;
+          __syncthreads();
+        } else {
+        for (int r = tid; r < n2; r += BT)
+          skey[r] = r < m ? ((bsplitmix(bkey, (uint64_t)r) & ~0x7FFull) | (unsigned long long)r) : ~0ull;
+        __syncthreads();
+        for (int kk = 2; kk <= n2; kk <<= 1)
+          for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n2; i += BT) {
+              const int ixj = i ^ j;
+              if (ixj > i) {
+                const unsigned long long a0 = skey[i], a1 = skey[ixj];
+                if (((i & kk) == 0) ? (a0 > a1) : (a0 < a1)) {
+                  skey[i] = a1;
+                  skey[ixj] = a0;
+                }
+              }
+            }
+            __syncthreads();
+          }
+        }
+      }
       for (int r = tid; r < m; r += BT) {
         // r = off_i + t  ->  (i, t)
         int i, t;
-        if (r < rem * (q + 1)) {
-          i = (int)(r / (q + 1));
-          t = (int)(r - (int64_t)i * (q + 1));
+        const int q32 = (int)q, rem32 = (int)rem;          // m < 2^31: 32-bit divisions
+        if (r < rem32 * (q32 + 1)) {
+          i = r / (q32 + 1);
+          t = r - i * (q32 + 1);
         } else {
-          const int64_t r2 = r - rem * (q + 1);
-          i = (int)(rem + r2 / q);
-          t = (int)(r2 % q);
+          const int r2 = r - rem32 * (q32 + 1);
+          i = rem32 + r2 / q32;
+          t = r2 % q32;
         }
-        tab[t * l + i] = make_double2(sb[r], __longlong_as_double((long long)(pb[r] - 1) * TS));
+        double wgt;
+        long long prow;
+        if (P.perm) {
+          wgt = sb[r];
+          prow = pb[r] - 1;
+        } else {
+          // N(0,1) weight of term r of this block: Box-Muller on two counter-based uniforms
+          const uint64_t z1 = bsplitmix(bkey ^ 0xA5A5A5A5A5A5A5A5ull, (uint64_t)(2 * r));
+          const uint64_t z2 = bsplitmix(bkey ^ 0xA5A5A5A5A5A5A5A5ull, (uint64_t)(2 * r + 1));
+          const double u1 = ((double)(z1 >> 11) + 1.0) * (1.0 / 9007199254740992.0);
+          const double u2 = ((double)(z2 >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+          double sn, cs;
+          sincospi(2.0 * u2, &sn, &cs);
+          wgt = sqrt(-2.0 * log(u1)) * cs;
+          prow = (long long)(skey[r] & 0x7FFull);
+        }
+        tab[t * l + i] = make_double2(wgt, __longlong_as_double(prow * TS));
       }
       tables_loaded = true;
       __syncthreads();
@@ -108,19 +201,7 @@ __global__ void __launch_bounds__(BT, 1) idfact_batched_kernel(BatchParams P) {
     for (int i = 0; i < BL; ++i) a[i] = 0.0;
     {
       const int ntiles = (n + TC - 1) / TC;
-      auto issue = [&](int T) {
-        const int c = T * TC + warp;                 // BW == TC: one column per warp
-        if (c < n) {
-          const double* g = Ab + (int64_t)c * P.lda;
-          double* d = tiles + (size_t)(T % nst) * tile_elems + warp;
-          for (int r = lane; r < m; r += 32)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(d + (size_t)r * TS)),
-                         "l"(g + r)
-                         : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      };
-      issue(0);
+      if (!early) issue(0);
       const int si = tid >> 4, sc = tid & 15;        // sketch row / column within the tile
       const int pi = (si < l) ? (int)q + (si < rem ? 1 : 0) : 0;
       for (int T = 0; T < ntiles; ++T) {
@@ -424,18 +505,13 @@ int bra_idfact_batched_f64(bra_ctx* ctx, int64_t nblocks, int64_t m, int64_t n, 
     P.s = s;
     P.s_stride = s_stride;
   } else {
-    // fast mode: ONE (perm, s) draw per call, shared by all blocks of the batch (device Philox weights)
-    BRA_CUDA(ctx->aux_in1.reserve((size_t)m * 8));
-    BRA_CUDA(ctx->aux_in2.reserve((size_t)(m + 1) * 8));
-    int rc = bra_fill_meta(ctx, 2, ctx->aux_in1.p, m, m, opts->seed, 0);
-    if (rc) return rc;
-    rc = bra_fill_randn(ctx, ctx->aux_in2.as<double>(), m, opts->seed, 0);
-    if (rc) return rc;
-    P.perm = ctx->aux_in1.as<int64_t>();
+    // fast mode: every block draws its own permutation and weights inside the kernel (keyed by opts.seed and the block id)
+    P.perm = nullptr;
     P.perm_stride = 0;
-    P.s = ctx->aux_in2.as<double>();
+    P.s = nullptr;
     P.s_stride = 0;
   }
+  P.seed = opts->seed;
   P.blocks = nullptr;
   P.nblocks = (int)nblocks;
   P.kout = k_out;

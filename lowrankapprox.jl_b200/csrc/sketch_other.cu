@@ -427,6 +427,20 @@ struct SplitMix {
   }
 };
 
+__device__ __forceinline__ uint64_t splitmix_at(uint64_t s0, uint64_t i) {      // (i+1)-th output of SplitMix64 seeded s0
+  uint64_t z = s0 + (i + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__global__ void meta_fill_kernel(int kind, void* __restrict__ dst, int64_t count, int64_t range, uint64_t s0) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t z = splitmix_at(s0, (uint64_t)i);
+    if (kind == 0) reinterpret_cast<double*>(dst)[i] = (z >> 63) ? 1.0 : -1.0;
+    else reinterpret_cast<int64_t*>(dst)[i] = (int64_t)__umul64hi(z, (uint64_t)range) + 1;
+  }
+}
+
 }  // namespace
 
 int bra_sketch_sub(bra_ctx* ctx, char trans, const double* A, int64_t lda, int64_t mA, int64_t nA, int64_t order,
@@ -557,19 +571,24 @@ int bra_sketch_srft(bra_ctx* ctx, const double* A, int64_t lda, int64_t mA, int6
   return bra_gemm_tn(ctx, ctx->omega_t.as<double>(), ldt, order, mA, A, lda, nA, B, ldb);
 }
 
-// Fast-mode random inputs (host SplitMix64 -> device; O(m) metadata, Gaussians stay on the device Philox path).
-// kind: 0 = signs d (+-1, double, count), 1 = uniform indices in [1, range] (int64, count), 2 = permutation of 1..count
+// Fast-mode random inputs: O(m) metadata from SplitMix64 (the Gaussians stay on the Philox path).
+// kind: 0 = signs d (+-1, double, count), 1 = uniform indices in [1, range] (int64, count), 2 = permutation of 1..count.
+// Signs and indices are counter-based -- element i is the (i+1)-th output of the SplitMix64 stream of (seed, stream, kind) --
+// and generated ON THE DEVICE (no host loop, no copy, no synchronisation); the permutation is a sequential Fisher-Yates
+// shuffle and stays on the host.
 int bra_fill_meta(bra_ctx* ctx, int kind, void* dst_dev, int64_t count, int64_t range, uint64_t seed, uint64_t stream_id) {
   if (count <= 0) return BRA_OK;
-  SplitMix g(seed * 0x9E3779B97F4A7C15ull + stream_id * 0xD1B54A32D192ED03ull + (uint64_t)kind + 1);
+  const uint64_t s0 = seed * 0x9E3779B97F4A7C15ull + stream_id * 0xD1B54A32D192ED03ull + (uint64_t)kind + 1;
+  if (kind == 0 || kind == 1) {
+    const int64_t blocks = (count + 255) / 256;
+    meta_fill_kernel<<<(unsigned)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, ctx->stream>>>(kind, dst_dev, count, range, s0);
+    ctx->launches++;
+    BRA_CUDA(cudaGetLastError());
+    return BRA_OK;
+  }
+  SplitMix g(s0);
   ctx->h_meta.resize((size_t)count * 8);
-  if (kind == 0) {
-    double* h = reinterpret_cast<double*>(ctx->h_meta.data());
-    for (int64_t i = 0; i < count; ++i) h[i] = (g.next() >> 63) ? 1.0 : -1.0;
-  } else if (kind == 1) {
-    int64_t* h = reinterpret_cast<int64_t*>(ctx->h_meta.data());
-    for (int64_t i = 0; i < count; ++i) h[i] = (int64_t)g.below((uint64_t)range) + 1;
-  } else {
+  {
     int64_t* h = reinterpret_cast<int64_t*>(ctx->h_meta.data());
     for (int64_t i = 0; i < count; ++i) h[i] = i + 1;
     for (int64_t i = count - 1; i > 0; --i) std::swap(h[i], h[(int64_t)g.below((uint64_t)i + 1)]);

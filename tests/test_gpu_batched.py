@@ -79,3 +79,49 @@ def test_batched_fast_mode_error(ctx):
     assert 8 <= min(ks) and max(ks) <= 31
     errs = [o.id_error(blocks[b], V[b]) for b in range(0, 32, 8)]
     assert max(errs) <= 1e-8, errs
+
+
+def _splitmix_at(s0, i):
+    M = (1 << 64) - 1
+    z = (s0 + (i + 1) * 0x9E3779B97F4A7C15) & M
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+    return z ^ (z >> 31)
+
+
+def _fast_mode_draws(seed, b, m):
+    """Host emulation of the per-block random inputs the fused kernel draws in fast mode (csrc/batched.cu): the
+    permutation = argsort of 21 random bits | 11 index bits, the weights = Box-Muller on counter-based uniforms."""
+    M = (1 << 64) - 1
+    bkey = (seed * 0x9E3779B97F4A7C15 + (b + 1) * 0xD1B54A32D192ED03) & M
+    keys = np.array([(((_splitmix_at(bkey, r) >> 32) & ~0x7FF) & 0xFFFFFFFF) | r for r in range(m)], dtype=np.uint64)
+    perm = np.argsort(keys, kind="stable").astype(np.int64) + 1
+    wkey = bkey ^ 0xA5A5A5A5A5A5A5A5
+    s = np.empty(m)
+    for r in range(m):
+        z1, z2 = _splitmix_at(wkey, 2 * r), _splitmix_at(wkey, 2 * r + 1)
+        u1 = ((z1 >> 11) + 1.0) / 9007199254740992.0
+        u2 = ((z2 >> 11) + 0.5) / 9007199254740992.0
+        s[r] = np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+    return {"perm": perm, "s": s}
+
+
+@pytest.mark.parametrize("m", [512, 300, 200, 700])
+def test_batched_fast_mode_draws_a_permutation_per_block(ctx, m):
+    """Fast mode: every block gets its OWN randperm(m) and weights (the reference draws per sketch call, i.e. per block:
+    src/sketch.jl:575-579), generated inside the kernel.  Replaying the same draws through the parity interface must give
+    the same k, p and T -- which also proves the in-kernel sort yields a true permutation."""
+    import brapprox
+    n, nb, seed = 384, 5, 23
+    blocks = np.stack([_cauchy_block(m, n, 60 + b) for b in range(nb)])
+    Vf = brapprox.idfact_batched(blocks, rtol=1e-11, sketch="sprn", seed=seed, ctx=ctx)
+    rands = [_fast_mode_draws(seed, b, m) for b in range(nb)]
+    for r in rands:
+        assert sorted(r["perm"]) == list(range(1, m + 1))
+    assert any(not np.array_equal(rands[0]["perm"], r["perm"]) for r in rands[1:])
+    Vp = brapprox.idfact_batched(blocks, brapprox.LRAOptions(rtol=1e-11, sketch="sprn"), rand=rands, ctx=ctx)
+    for b in range(nb):
+        assert Vf[b].k == Vp[b].k
+        np.testing.assert_array_equal(Vf[b].p[:Vf[b].k], Vp[b].p[:Vp[b].k])
+        C = blocks[b][:, Vp[b].sk - 1]
+        assert np.max(np.abs(C @ Vf[b].T - C @ Vp[b].T)) <= 1e-9 * np.linalg.norm(blocks[b], 2)
