@@ -412,7 +412,7 @@ int bra_destroy(bra_ctx* ctx) {
                     &ctx->kbtrace, &ctx->R11, &ctx->T, &ctx->C, &ctx->Q, &ctx->R1, &ctx->Rfull, &ctx->W, &ctx->G,
                     &ctx->U, &ctx->S, &ctx->Vt, &ctx->Z, &ctx->scratch, &ctx->scratch2, &ctx->scratch3,
                     &ctx->aux_in1, &ctx->aux_in2, &ctx->jwork, &ctx->At, &ctx->rinv, &ctx->yt, &ctx->Apanels, &ctx->tritmp, &ctx->cholscr, &ctx->Bq, &ctx->omega_spec, &ctx->Bspec, &ctx->Bt, &ctx->Bcat,
-                    &ctx->partial_l1, &ctx->cholscr_l1, &ctx->tritmp_l1, &ctx->G_l1};
+                    &ctx->partial_l1, &ctx->cholscr_l1, &ctx->tritmp_l1, &ctx->G_l1, &ctx->Qt_l1, &ctx->Out_l1};
   for (DevBuf* b : bufs) b->release();
   bra_comm_destroy(ctx);
   if (ctx->h_info) cudaFreeHost(ctx->h_info);

@@ -66,8 +66,10 @@ bool skeleton_needs_fresh(const bra_ctx* ctx, const bra_opts* o) {
   return !off && (o->sketch == BRA_SKETCH_SUB || o->sketch == BRA_SKETCH_SPRN);
 }
 
+// defer_q (psvdfact): the second CholeskyQR pass stops after its Cholesky and the sign normalisation is skipped (U S Vt
+// does not depend on it): ctx->Q holds Y1 with Q = Y1 R_y2^{-1}, R_y2 in ctx->scratch (k x k); finish_skeleton_q completes Q.
 int skeleton_qr(bra_ctx* ctx, char trans, const double* dA, int64_t lda, int64_t mA, int64_t k, const bra_opts* o,
-                bool fresh) {
+                bool fresh, bool defer_q = false) {
   const int64_t ldq = even(mA);
   BRA_CUDA(ctx->Q.reserve((size_t)ldq * k * 8));
   BRA_CUDA(ctx->R1.reserve((size_t)k * k * 8));
@@ -79,10 +81,18 @@ int skeleton_qr(bra_ctx* ctx, char trans, const double* dA, int64_t lda, int64_t
   // Y = C R11^{-1}: R11 is the triangular factor of the SKETCH of these very columns (Omega*C = Q_B*R11)
   rc = bra_trsolve_right_upper(ctx, mA, (int)k, ctx->R11.as<double>(), k, ctx->Q.as<double>(), ldq);
   if (rc) return rc;
-  rc = bra_cholqr2(ctx, mA, (int)k, ctx->Q.as<double>(), ldq, ctx->R11.as<double>(), ctx->R1.as<double>(), true);
-  if (rc) return rc;
+  rc = bra_cholqr2(ctx, mA, (int)k, ctx->Q.as<double>(), ldq, ctx->R11.as<double>(), ctx->R1.as<double>(), true, defer_q);
+  if (rc || defer_q) return rc;
   // R1 = R_y2 R_y1 R11 inherits the signs of diag(R11) (Householder: -sign(alpha)); normalise to diag(R1) >= 0
   return bra_fix_signs(ctx, mA, (int)k, ctx->Q.as<double>(), ldq, ctx->R1.as<double>(), k);
+}
+
+// Q = Y1 R_y2^{-1} after a deferred skeleton QR, then Q' (k x mA, K-major for the U product) into ctx->Qt_l1
+int finish_skeleton_q(bra_ctx* ctx, int64_t mA, int64_t k) {
+  const int64_t ldq = even(mA), ldk = even(k);
+  int rc = bra_trsolve_right_upper(ctx, mA, (int)k, ctx->scratch.as<double>(), k, ctx->Q.as<double>(), ldq);
+  if (rc) return rc;
+  return bra_transpose(ctx, ctx->Q.as<double>(), ldq, mA, k, ctx->Qt_l1.as<double>(), ldk);
 }
 
 }  // namespace
@@ -306,7 +316,7 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
   const int64_t ldz = even(nA);
   const int64_t ldj = even(k);                // even leading dimension: 16-byte aligned columns for the Jacobi panels
   BRA_CUDA(ctx->Z.reserve((size_t)ldz * k * 8));
-  BRA_CUDA(ctx->W.reserve((size_t)9 * ldj * k * 8 + 64));
+  BRA_CUDA(ctx->W.reserve((size_t)10 * ldj * k * 8 + 64));
   BRA_CUDA(ctx->G_l1.reserve((size_t)k * k * 8));
   BRA_CUDA(ctx->info.reserve(64));
   double* Z = ctx->Z.as<double>();
@@ -319,6 +329,7 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
   double* Xp = Q2 + (size_t)ldj * k;        // R2' (the matrix the Jacobi runs on when preconditioned)
   double* Rinv2 = Xp + (size_t)ldj * k;
   double* Rzinv = Rinv2 + (size_t)ldj * k;  // R_z^{-1} (side lane)
+  double* YselU = Rzinv + (size_t)ldj * k;  // selected left vectors of the core (U chain, side lane)
   if ((size_t)k * 8 > BRA_HPIN_BYTES) {
     ctx->set_error("psvdfact: k too large for the pinned read-back buffer");
     return BRA_ERR_UNSUPPORTED;
@@ -339,7 +350,7 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
   }
   bool fresh = skeleton_needs_fresh(ctx, opts);
 skeleton_again:
-  rc = skeleton_qr(ctx, trans, dA, dlda, mA, k, opts, fresh);           // Q, R = qr!(getcols(...))
+  rc = skeleton_qr(ctx, trans, dA, dlda, mA, k, opts, fresh, /*defer_q=*/true);      // R = qr!(getcols(...)).R; Q deferred
   if (rc) return rc;
   bool explicit_qz = false;
   {
@@ -368,6 +379,20 @@ skeleton_again:
       dmax = std::max(dmax, dz[i]);
     }
     explicit_qz = hinfo != 0 || !(dmin > 0.0) || dmax > 1e3 * dmin;
+  }
+  // Q = Y1 R_y2^{-1} and Q' are not needed before the U product: they are formed on the side lane, next to the k x k
+  // products, the Cholesky / inverse of the Jacobi preconditioner and the Jacobi SVD itself (63 CTAs: most SMs are idle)
+  const int64_t ldk = even(k);
+  BRA_CUDA(ctx->Qt_l1.reserve((size_t)ldk * std::max(mA, nA) * 8));
+  BRA_CUDA(ctx->rinv.reserve((size_t)ldk * k * 8));
+  BRA_CUDA(ctx->yt.reserve((size_t)2 * ldk * mA * 8));
+  if (explicit_qz) {
+    if ((rc = finish_skeleton_q(ctx, mA, k))) return rc;       // the robust Z path below reuses ctx->scratch / rinv / yt
+  } else {
+    if ((rc = bra_lane_fork(ctx))) return rc;
+    rc = finish_skeleton_q(ctx, mA, k);
+    const int rc2 = bra_lane_end(ctx);
+    if (rc || rc2) return rc ? rc : rc2;
   }
   if (explicit_qz) {
     // rebuild Z (the Gram pass left it untouched) and take the robust path; its status is checked before the SVD
@@ -443,31 +468,38 @@ skeleton_again:
   }
 
   // Ut (kk x mA) = Jsel' Q'   and   Vp (kk x nA) = Ysel' Qz'   -- both on the TMA + DMMA kernel (TN form)
-  const int64_t ldk = even(k);
   BRA_CUDA(ctx->scratch2.reserve((size_t)ldk * std::max(mA, nA) * 8));
   BRA_CUDA(ctx->scratch3.reserve((size_t)even(kk) * std::max(mA, nA) * 8 + 64));
+  BRA_CUDA(ctx->Out_l1.reserve((size_t)even(kk) * std::max(mA, nA) * 8 + 64));
   BRA_CUDA(ctx->U.reserve((size_t)std::max(m, n) * kk * 8 + 64));
   BRA_CUDA(ctx->Vt.reserve((size_t)std::max(m, n) * kk * 8 + 64));
   double* Qt = ctx->scratch2.as<double>();
   double* Out = ctx->scratch3.as<double>();
   // left factor of op(A):  Uop = Q * (left singular vectors of M)[:, order[:kk]]   (mA x kk)
   //   plain: M' J = Y Sigma  =>  left vectors of M = J;   preconditioned: left vectors = normalised columns of R2' J'
-  if (precond) rc = bra_gather_scale_cols(ctx, Xj, ldj, k, (int)kk, ctx->aux_in1.as<int>(), ctx->S.as<double>(), Ysel, ldj);
-  else rc = bra_gather_scale_cols(ctx, J, ldj, k, (int)kk, ctx->aux_in1.as<int>(), nullptr, Ysel, ldj);
+  // The U chain (one tall product + a transpose) runs on the side lane -- behind the Q it needs -- while the main stream
+  // forms the right factor.  YselU is its own buffer: the right factor reuses Ysel.
+  if (precond) rc = bra_gather_scale_cols(ctx, Xj, ldj, k, (int)kk, ctx->aux_in1.as<int>(), ctx->S.as<double>(), YselU, ldj);
+  else rc = bra_gather_scale_cols(ctx, J, ldj, k, (int)kk, ctx->aux_in1.as<int>(), nullptr, YselU, ldj);
   if (rc) return rc;
-  rc = bra_transpose(ctx, ctx->Q.as<double>(), even(mA), mA, k, Qt, ldk);          // Q' (k x mA)
-  if (rc) return rc;
-  rc = bra_gemm_tn(ctx, Ysel, ldj, kk, k, Qt, ldk, mA, Out, even(kk));                 // (kk x mA) = Jsel' Q'
-  if (rc) return rc;
-  double* Uop_t = Out;          // kk x mA, ld even(kk)
-  if (trans == 'n') {
-    rc = bra_transpose(ctx, Uop_t, even(kk), kk, mA, ctx->U.as<double>(), mA);      // U (m x kk)
-  } else {
-    // op(A) = A': A ~ Vop S Uop'  =>  Vt = Uop' (kk x n), ld = kk
-    BRA_CUDA(cudaMemcpy2DAsync(ctx->Vt.p, (size_t)kk * 8, Uop_t, (size_t)even(kk) * 8, (size_t)kk * 8, (size_t)mA,
-                               cudaMemcpyDeviceToDevice, ctx->stream));
+  {
+    if ((rc = bra_lane_fork(ctx))) return rc;
+    struct LaneEnd {
+      bra_ctx* c;
+      ~LaneEnd() { bra_lane_end(c); }
+    } lane_end{ctx};
+    double* Uop_t = ctx->Out_l1.as<double>();          // kk x mA, ld even(kk)
+    rc = bra_gemm_tn(ctx, YselU, ldj, kk, k, ctx->Qt_l1.as<double>(), ldk, mA, Uop_t, even(kk));     // (kk x mA) = Jsel' Q'
+    if (rc) return rc;
+    if (trans == 'n') {
+      rc = bra_transpose(ctx, Uop_t, even(kk), kk, mA, ctx->U.as<double>(), mA);      // U (m x kk)
+      if (rc) return rc;
+    } else {
+      // op(A) = A': A ~ Vop S Uop'  =>  Vt = Uop' (kk x n), ld = kk
+      BRA_CUDA(cudaMemcpy2DAsync(ctx->Vt.p, (size_t)kk * 8, Uop_t, (size_t)even(kk) * 8, (size_t)kk * 8, (size_t)mA,
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
+    }
   }
-  if (rc) return rc;
   // right factor of op(A):  Vop' = Ysel' Qz' P'   with Ysel = X[:, order] / sigma
   //   plain: right vectors of M = normalised columns of X J;   preconditioned: Q2 J'[:, order]
   if (precond) {
@@ -524,6 +556,7 @@ skeleton_again:
   // bra_fetch reports U as m x ksvd and Vt as ksvd x n of the ORIGINAL A
   res.svd_m = m;
   res.svd_n = n;
+  if ((rc = bra_lane_join(ctx))) return rc;
   BRA_CUDA(cudaStreamSynchronize(ctx->stream));
   return BRA_OK;
 }

@@ -99,6 +99,7 @@ struct bra_ctx {
   cudaStream_t side_stream = nullptr, lane_saved = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   DevBuf partial_l1, cholscr_l1, tritmp_l1, G_l1;
+  DevBuf Qt_l1, Out_l1;         // psvdfact: Q' and U' formed on the side lane
   DevBuf& ws_partial() { return lane ? partial_l1 : partial; }
   DevBuf& ws_cholscr() { return lane ? cholscr_l1 : cholscr; }
   DevBuf& ws_tritmp() { return lane ? tritmp_l1 : tritmp; }
@@ -234,7 +235,7 @@ int bra_transpose(bra_ctx* ctx, const double* src, int64_t lds, int64_t rows, in
 int bra_trsolve_right_upper(bra_ctx* ctx, int64_t rows, int k, const double* R, int64_t ldr, double* Y, int64_t ldy);
 int bra_cholesky_upper(bra_ctx* ctx, int k, double* G, int64_t ldg, double* Rout, int64_t ldr);
 int bra_cholqr2(bra_ctx* ctx, int64_t rows, int k, double* Y, int64_t ldy, const double* Rpre, double* Rout,
-                bool rows_sharded = false);
+                bool rows_sharded = false, bool defer_last_solve = false);
 int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64_t ldj, double* sigma_host,
                    int* order_host, bool* skip_J = nullptr);
 extern "C" {

@@ -844,8 +844,11 @@ int bra_cholesky_upper(bra_ctx* ctx, int k, double* G, int64_t ldg, double* Rout
 
 // Two Cholesky-QR passes on Y (rows x k, well conditioned): on return Y holds Q (orthonormal columns) and
 // Rout (k x k, ld k) = R_y2 * R_y1 * Rpre (Rpre = the preconditioner already divided out of Y, or null).
+// defer_last_solve: the second pass stops after its Cholesky -- Y still holds the once-orthogonalised Y1 and the caller
+// applies R_y2^{-1} (left in ctx->scratch, k x k, ld k) when and where it wants (psvdfact: on the side lane, next to the
+// Jacobi SVD, which only needs Rout).
 int bra_cholqr2(bra_ctx* ctx, int64_t rows, int k, double* Y, int64_t ldy, const double* Rpre, double* Rout,
-                bool rows_sharded) {
+                bool rows_sharded, bool defer_last_solve) {
   if (k <= 0) return BRA_OK;
   BRA_CUDA(ctx->G.reserve((size_t)k * k * 8));
   BRA_CUDA(ctx->scratch.reserve((size_t)3 * k * k * 8));
@@ -858,7 +861,7 @@ int bra_cholqr2(bra_ctx* ctx, int64_t rows, int k, double* Y, int64_t ldy, const
     if ((rc = bra_gemm_tn(ctx, Y, ldy, k, rows, Y, ldy, k, G, k))) return rc;          // G = Y^T Y
     if (rows_sharded && (rc = bra_allreduce_sum_f64(ctx, G, (int64_t)k * k))) return rc;   // sum over the row blocks
     if ((rc = bra_cholesky_upper(ctx, k, G, k, Ry, k))) return rc;
-    if ((rc = bra_trsolve_right_upper(ctx, rows, k, Ry, k, Y, ldy))) return rc;         // Y <- Y Ry^{-1}
+    if (!(defer_last_solve && pass == 1) && (rc = bra_trsolve_right_upper(ctx, rows, k, Ry, k, Y, ldy))) return rc;   // Y <- Y Ry^{-1}
     // Racc <- Ry * (pass == 0 ? Rpre : Racc)     (k x k upper-triangular products)
     const double* prev = (pass == 0) ? Rpre : Racc;
     if (prev) {
