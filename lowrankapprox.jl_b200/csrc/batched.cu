@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(BT, 1) idfact_batched_kernel(BatchParams P) {
           __syncthreads();
         } else {
         for (int r = tid; r < n2; r += BT)
-          skey[r] = r < m ? ((bsplitmix(bkey, (uint64_t)r) & ~0x7FFull) | (unsigned long long)r) : ~0ull;
+          skey[r] = r < m ? (((bsplitmix(bkey, (uint64_t)r) >> 32) & ~0x7FFull) | (unsigned long long)r) : ~0ull;   // same keys as above
         __syncthreads();
         for (int kk = 2; kk <= n2; kk <<= 1)
           for (int j = kk >> 1; j > 0; j >>= 1) {
