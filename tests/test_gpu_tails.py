@@ -273,3 +273,52 @@ def test_skeleton_qr_retries_after_breakdown(ctx, monkeypatch):
     assert np.linalg.norm(Fg.Q.T @ Fg.Q - np.eye(Fo.k)) <= 1e-12 * np.sqrt(Fo.k)
     nrm = np.linalg.norm(A)
     assert np.linalg.norm(A - Fg.matrix()) / nrm <= 2 * np.linalg.norm(A - Fo.matrix()) / nrm + 1e-15
+
+
+def _spectrum_matrix(m, n, sig, seed):
+    rng = np.random.default_rng(seed)
+    U, _ = np.linalg.qr(rng.standard_normal((m, len(sig))))
+    V, _ = np.linalg.qr(rng.standard_normal((n, len(sig))))
+    return np.asfortranarray((U * sig) @ V.T)
+
+
+@pytest.mark.parametrize("name", ["clusters", "steps", "one_gap", "flat_then_cliff"])
+@pytest.mark.parametrize("noprecond", [False, True])
+def test_psvdfact_core_on_non_geometric_spectra(ctx, monkeypatch, name, noprecond):
+    """The k x k core SVD (Cholesky-of-Gram preconditioned one-sided Jacobi) on spectra that are NOT a
+    geometric decay: repeated singular values, plateaus separated by big steps, a single 1e10 gap, a flat spectrum ending
+    in a cliff -- with the preconditioner and (BRA_JACOBI_NOPRECOND) on the plain path.  Same criteria as the geometric
+    cases: rank identical, |dsigma| <= 1e-10 sigma_1, U orthonormal, error within 2x of the oracle's."""
+    import brapprox
+    r = 120
+    if name == "clusters":
+        sig = np.repeat(10.0 ** -np.arange(0, 12, 1.0), 10)
+    elif name == "steps":
+        sig = np.concatenate([np.full(40, 1.0), np.full(40, 1e-4) * np.linspace(1, 0.5, 40), np.full(40, 1e-9) * np.linspace(1, 0.9, 40)])
+    elif name == "one_gap":
+        sig = np.concatenate([np.linspace(1.0, 0.5, 60), 1e-10 * np.linspace(1.0, 0.5, 60)])
+    else:
+        sig = np.concatenate([np.full(100, 1.0) * np.linspace(1.0, 0.99, 100), 10.0 ** -np.linspace(3, 13, 20)])
+    assert len(sig) == r
+    A = _spectrum_matrix(900, 700, sig, 17)
+    if noprecond:
+        monkeypatch.setenv("BRA_JACOBI_NOPRECOND", "1")
+    rin = o.RandomInputs(3)
+    So = o.psvdfact(A, o.LRAOptions(rtol=1e-12), rin)
+    Sg = brapprox.psvdfact(A, brapprox.LRAOptions(rtol=1e-12), rand=rin.drawn, ctx=ctx)
+    assert Sg.k_id == So.k_id
+    assert len(Sg.S) == len(So.S)
+    s1 = So.S[0]
+    assert np.max(np.abs(Sg.S - So.S)) <= 1e-10 * s1
+    kk = len(So.S)
+    assert np.linalg.norm(Sg.U.T @ Sg.U - np.eye(kk)) <= 1e-12 * np.sqrt(kk)
+    nrm = np.linalg.norm(A, 2)
+    eo = np.linalg.norm(A - So.matrix(), 2) / nrm
+    eg = np.linalg.norm(A - Sg.matrix(), 2) / nrm
+    assert eg <= 2 * eo + 1e-15
+    # the leading singular subspaces agree wherever the spectrum separates them (gap > 1e-3 sigma_1)
+    true_sig = np.sort(sig)[::-1]
+    cut = [i for i in range(1, min(kk, r)) if true_sig[i - 1] - true_sig[i] > 1e-3 * true_sig[i - 1] and true_sig[i - 1] > 1e-6]
+    for c in cut[:3]:
+        Pg, Po = Sg.U[:, :c] @ Sg.U[:, :c].T, So.U[:, :c] @ So.U[:, :c].T
+        assert np.linalg.norm(Pg - Po, 2) <= 1e-6
