@@ -128,15 +128,15 @@ __global__ void __launch_bounds__(256) trsolve_right_upper_kernel(int64_t rows, 
 //                     panel-solve launch), updates G[I,J] -= L_I L_J^T, and the J = 0 column of CTAs stores L_I into R.
 //                     The unsolved panel blocks P stay untouched in G (nobody reads them after this launch), so there
 //                     is no read/write race between CTAs.
-__global__ void __launch_bounds__(32) chol_diag_kernel(int k, int j0, const double* __restrict__ G, int64_t ldg,
-                                                       double* __restrict__ R, int64_t ldr, double* __restrict__ Dinv,
-                                                       int* info) {
-  const int lane = threadIdx.x;
+// (one warp; G and Dinv are read / written by different CTAs across the panels of the fused kernel: L2 loads)
+__device__ __forceinline__ void chol_diag_body(int k, int j0, const double* G, int64_t ldg, double* R, int64_t ldr,
+                                               double* Dinv, int* info) {
+  const int lane = threadIdx.x & 31;
   const int jbsz = min(TB, k - j0);
   double a[TB];      // row `lane` of the diagonal block (lower triangle meaningful)
 #pragma unroll
   for (int c = 0; c < TB; ++c)
-    a[c] = (lane < jbsz && c < jbsz) ? G[(j0 + lane) + (int64_t)(j0 + c) * ldg] : (lane == c ? 1.0 : 0.0);
+    a[c] = (lane < jbsz && c < jbsz) ? __ldcg(G + (j0 + lane) + (int64_t)(j0 + c) * ldg) : (lane == c ? 1.0 : 0.0);
   // Factorization and inversion run in ONE loop over the columns: as soon as column c of L exists, unknown c of the
   // substitution L v = e_j (lane j = column j of L^{-1}) is resolved and eliminated from the rows below.  The two
   // instruction streams are independent within a step, which is what hides the shuffle / FP64 latencies of a lone warp.
@@ -170,17 +170,23 @@ __global__ void __launch_bounds__(32) chol_diag_kernel(int k, int j0, const doub
   for (int r = 0; r < TB; ++r) Dinv[r + lane * TB] = v[r];        // Dinv[r][j] = (L^{-1})[r][j], column-major 32 x 32
 }
 
-__global__ void __launch_bounds__(256) chol_trail_kernel(int k, int j0, double* __restrict__ G, int64_t ldg,
-                                                         double* __restrict__ R, int64_t ldr,
-                                                         const double* __restrict__ Dinv) {
-  __shared__ double Pi[TB][TB + 1];   // P_I, then reused
-  __shared__ double Pj[TB][TB + 1];
-  __shared__ double Di[TB][TB + 1];   // L_jj^{-1}
-  __shared__ double Li[TB][TB + 1];
-  __shared__ double Lj[TB][TB + 1];
+struct CholSmem {
+  double Pi[TB][TB + 1];   // P_I, then reused
+  double Pj[TB][TB + 1];
+  double Di[TB][TB + 1];   // L_jj^{-1}
+  double Li[TB][TB + 1];
+  double Lj[TB][TB + 1];
+};
+__device__ __forceinline__ void chol_trail_body(CholSmem& sm, int tile, int k, int j0, double* G, int64_t ldg, double* R,
+                                                int64_t ldr, const double* Dinv) {
+  auto& Pi = sm.Pi;
+  auto& Pj = sm.Pj;
+  auto& Di = sm.Di;
+  auto& Li = sm.Li;
+  auto& Lj = sm.Lj;
   const int tid = threadIdx.x;
   // linear index -> (I, J), I >= J
-  int t = blockIdx.x, I = 0;
+  int t = tile, I = 0;
   while (t > I) {
     t -= I + 1;
     ++I;
@@ -189,9 +195,9 @@ __global__ void __launch_bounds__(256) chol_trail_kernel(int k, int j0, double* 
   const int ri = j0 + (I + 1) * TB, rj = j0 + (J + 1) * TB;
   for (int e = tid; e < TB * TB; e += 256) {
     const int rr = e & 31, cc = e >> 5;
-    Pi[rr][cc] = (ri + rr < k && j0 + cc < k) ? G[(ri + rr) + (int64_t)(j0 + cc) * ldg] : 0.0;
-    Pj[rr][cc] = (rj + rr < k && j0 + cc < k) ? G[(rj + rr) + (int64_t)(j0 + cc) * ldg] : 0.0;
-    Di[rr][cc] = Dinv[rr + cc * TB];
+    Pi[rr][cc] = (ri + rr < k && j0 + cc < k) ? __ldcg(G + (ri + rr) + (int64_t)(j0 + cc) * ldg) : 0.0;
+    Pj[rr][cc] = (rj + rr < k && j0 + cc < k) ? __ldcg(G + (rj + rr) + (int64_t)(j0 + cc) * ldg) : 0.0;
+    Di[rr][cc] = __ldcg(Dinv + rr + cc * TB);
   }
   __syncthreads();
   const int tx = tid & 31, ty = tid >> 5;
@@ -227,9 +233,54 @@ __global__ void __launch_bounds__(256) chol_trail_kernel(int k, int j0, double* 
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int c = ty * 4 + u;
-      if (ri + tx < k && rj + c < k) G[(ri + tx) + (int64_t)(rj + c) * ldg] -= acc[u];
+      if (ri + tx < k && rj + c < k) {
+        double* gp = G + (ri + tx) + (int64_t)(rj + c) * ldg;
+        *gp = __ldcg(gp) - acc[u];
+      }
     }
   }
+}
+
+// The whole blocked Cholesky in ONE cooperative launch (round 1: two launches per 32-column panel, 31 at k = 497):
+// per panel CTA 0 factors and inverts the diagonal block, a grid barrier, every CTA updates its share of the trailing
+// tiles, a grid barrier.  `bar` is zeroed before the launch; a lost CTA makes the others time out and flag `info`.
+__device__ __forceinline__ bool chol_grid_barrier(unsigned* bar, unsigned target, int* s_fail) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned v, spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    } while (v < target && ++spins < (1u << 22));
+    if (v < target) *s_fail = 1;
+    __threadfence();
+  }
+  __syncthreads();
+  return *s_fail == 0;
+}
+
+__global__ void __launch_bounds__(256, 1) chol_fused_kernel(int k, double* G, int64_t ldg, double* R, int64_t ldr, double* Dinv,
+                                                            int* info, unsigned* bar) {
+  __shared__ CholSmem sm;
+  __shared__ int s_fail;
+  if (threadIdx.x == 0) s_fail = 0;
+  const int nblk = (k + TB - 1) / TB, Gn = gridDim.x;
+  unsigned epoch = 0;
+  for (int jb = 0; jb < nblk; ++jb) {
+    const int j0 = jb * TB;
+    if (blockIdx.x == 0 && threadIdx.x < 32) chol_diag_body(k, j0, G, ldg, R, ldr, Dinv, info);
+    const int nb = nblk - jb - 1;
+    if (nb == 0) break;
+    if (!chol_grid_barrier(bar, ++epoch * Gn, &s_fail)) break;
+    const int nt = nb * (nb + 1) / 2;
+    for (int t = blockIdx.x; t < nt; t += Gn) {
+      __syncthreads();
+      chol_trail_body(sm, t, k, j0, G, ldg, R, ldr, Dinv);
+    }
+    if (!chol_grid_barrier(bar, ++epoch * Gn, &s_fail)) break;
+  }
+  if (s_fail && threadIdx.x == 0) atomicExch(info, -1);
 }
 
 // ---- one-sided Jacobi (Hestenes) on the columns of X (k x k), rotations accumulated into J ----
@@ -824,20 +875,20 @@ int bra_cholesky_upper(bra_ctx* ctx, int k, double* G, int64_t ldg, double* Rout
   ProfScope ps(ctx, BRA_PROF_QR);
   // sticky status: reset by bra_chol_status_reset, read by bra_chol_status; the side lane reports in the next word
   int* info = ctx->info.as<int>() + 12 + (ctx->lane ? 1 : 0);
-  BRA_CUDA(ctx->ws_cholscr().reserve((size_t)TB * TB * 8));
+  BRA_CUDA(ctx->ws_cholscr().reserve((size_t)TB * TB * 8 + 256));
   double* Dinv = ctx->ws_cholscr().as<double>();
+  unsigned* bar = reinterpret_cast<unsigned*>(Dinv + TB * TB);
   BRA_CUDA(cudaMemset2DAsync(Rout, (size_t)ldr * 8, 0, (size_t)k * 8, (size_t)k, ctx->stream));    // zeros below the diagonal
+  BRA_CUDA(cudaMemsetAsync(bar, 0, 4, ctx->stream));
   const int nblk = (k + TB - 1) / TB;
-  for (int jb = 0; jb < nblk; ++jb) {
-    const int j0 = jb * TB;
-    chol_diag_kernel<<<1, 32, 0, ctx->stream>>>(k, j0, G, ldg, Rout, ldr, Dinv, info);
-    ctx->launches++;
-    const int nb = nblk - jb - 1;
-    if (nb > 0) {
-      chol_trail_kernel<<<nb * (nb + 1) / 2, 256, 0, ctx->stream>>>(k, j0, G, ldg, Rout, ldr, Dinv);
-      ctx->launches++;
-    }
-  }
+  const int nt0 = (nblk - 1) * nblk / 2;
+  int grid = nt0 < 1 ? 1 : nt0;
+  // the side lane shares the machine with the main chain: half the SMs each keeps both cooperative grids co-resident
+  const int cap = ctx->num_sms / 2 > 0 ? ctx->num_sms / 2 : 1;
+  if (grid > cap) grid = cap;
+  void* args[] = {(void*)&k, (void*)&G, (void*)&ldg, (void*)&Rout, (void*)&ldr, (void*)&Dinv, (void*)&info, (void*)&bar};
+  BRA_CUDA(cudaLaunchCooperativeKernel((void*)chol_fused_kernel, dim3(grid), dim3(256), args, 0, ctx->stream));
+  ctx->launches++;
   BRA_CUDA(cudaGetLastError());
   return BRA_OK;
 }

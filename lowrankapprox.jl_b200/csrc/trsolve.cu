@@ -228,10 +228,14 @@ int bra_trsolve_upper(bra_ctx* ctx, int k, int64_t nrhs, const double* R11, int6
 // parallel work instead of every column panel walking all block rows one after another (250 us -> ~60 us at k = 500).
 namespace {
 
-__global__ void __launch_bounds__(32) triinv_diag_kernel(int k, const double* __restrict__ R, int64_t ldr,
-                                                         double* __restrict__ V, int64_t ldv) {
-  __shared__ double U[TB][TB + 1];
-  const int lane = threadIdx.x, b0 = blockIdx.x * TB;
+struct TriinvSmem {
+  double Xs[TB][TB + 1];
+  double Ys[TB][TB + 1];
+};
+// one warp; `U` aliases the CTA's tile buffer
+__device__ __forceinline__ void triinv_diag_body(double (*U)[TB + 1], int vb, int k, const double* __restrict__ R, int64_t ldr,
+                                                 double* V, int64_t ldv) {
+  const int lane = threadIdx.x & 31, b0 = vb * TB;
   const int bs = min(TB, k - b0);
   for (int c = 0; c < TB; ++c)
     U[lane][c] = (lane < bs && c < bs) ? R[(b0 + lane) + (int64_t)(b0 + c) * ldr] : (lane == c ? 1.0 : 0.0);
@@ -256,13 +260,13 @@ __global__ void __launch_bounds__(32) triinv_diag_kernel(int k, const double* __
 
 // phase 0: tmp[a0+i, a0+s+j] = sum_t R[a0+i, a0+s+t] * V[a0+s+t, a0+s+j]      (t <= j: V upper triangular)
 // phase 1: V[a0+i, a0+s+j]   = - sum_t V[a0+i, a0+t] * tmp[a0+t, a0+s+j]      (t >= i)
-__global__ void __launch_bounds__(256) triinv_join_kernel(int k, int s, int phase, const double* __restrict__ R,
-                                                          int64_t ldr, double* __restrict__ V, int64_t ldv,
-                                                          double* __restrict__ tmp, int64_t ldt) {
-  __shared__ double Xs[TB][TB + 1];
-  __shared__ double Ys[TB][TB + 1];
+// (V and tmp are written by other CTAs in earlier phases of the fused kernel: L2 loads)
+__device__ __forceinline__ void triinv_join_body(TriinvSmem& sm, int tile, int k, int s, int phase, const double* __restrict__ R,
+                                                 int64_t ldr, double* V, int64_t ldv, double* tmp, int64_t ldt) {
+  auto& Xs = sm.Xs;
+  auto& Ys = sm.Ys;
   const int nt = s / TB;                               // tiles per side of an s-block
-  const int pair = blockIdx.x / (nt * nt), tt = blockIdx.x % (nt * nt);
+  const int pair = tile / (nt * nt), tt = tile % (nt * nt);
   const int ti = tt % nt, tj = tt / nt;
   const int a0 = pair * 2 * s;
   const int r0 = a0 + ti * TB, c0 = a0 + s + tj * TB;  // top-left of the output tile
@@ -281,8 +285,8 @@ __global__ void __launch_bounds__(256) triinv_join_kernel(int k, int s, int phas
     __syncthreads();
     for (int e = tid; e < TB * TB; e += 256) {
       const int rr = e & 31, cc = e >> 5;
-      Xs[rr][cc] = (r0 + rr < k && xk0 + cc < k) ? Xm[(r0 + rr) + (int64_t)(xk0 + cc) * ldxm] : 0.0;
-      Ys[rr][cc] = (yk0 + rr < k && c0 + cc < k) ? Ym[(yk0 + rr) + (int64_t)(c0 + cc) * ldym] : 0.0;
+      Xs[rr][cc] = (r0 + rr < k && xk0 + cc < k) ? __ldcg(Xm + (r0 + rr) + (int64_t)(xk0 + cc) * ldxm) : 0.0;
+      Ys[rr][cc] = (yk0 + rr < k && c0 + cc < k) ? __ldcg(Ym + (yk0 + rr) + (int64_t)(c0 + cc) * ldym) : 0.0;
     }
     __syncthreads();
 #pragma unroll 8
@@ -301,24 +305,70 @@ __global__ void __launch_bounds__(256) triinv_join_kernel(int k, int s, int phas
   }
 }
 
+// the whole blocked inverse in ONE cooperative launch (round 1: one launch for the diagonal blocks + two per level, 9 at
+// k = 497): grid barriers between the levels; `bar` is zeroed before the launch
+__device__ __forceinline__ bool tri_grid_barrier(unsigned* bar, unsigned target, int* s_fail) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned v, spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    } while (v < target && ++spins < (1u << 22));
+    if (v < target) *s_fail = 1;
+    __threadfence();
+  }
+  __syncthreads();
+  return *s_fail == 0;
+}
+
+__global__ void __launch_bounds__(256, 1) triinv_fused_kernel(int k, const double* __restrict__ R, int64_t ldr, double* V,
+                                                              int64_t ldv, double* tmp, int64_t ldt, unsigned* bar) {
+  __shared__ TriinvSmem sm;
+  __shared__ int s_fail;
+  if (threadIdx.x == 0) s_fail = 0;
+  const int nblk = (k + TB - 1) / TB, Gn = gridDim.x;
+  unsigned epoch = 0;
+  if (threadIdx.x < 32)
+    for (int vb = blockIdx.x; vb < nblk; vb += Gn) {
+      triinv_diag_body(sm.Xs, vb, k, R, ldr, V, ldv);
+      __syncwarp();
+    }
+  for (int s = TB; s < k; s *= 2) {
+    const int nt = s / TB, pairs = (k + 2 * s - 1) / (2 * s);
+    for (int phase = 0; phase < 2; ++phase) {
+      if (!tri_grid_barrier(bar, ++epoch * Gn, &s_fail)) return;
+      for (int t = blockIdx.x; t < pairs * nt * nt; t += Gn) {
+        __syncthreads();
+        triinv_join_body(sm, t, k, s, phase, R, ldr, V, ldv, tmp, ldt);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 // Rinv (k x k, ld ldx) <- R^{-1}.  Rinv's strictly lower triangle is left as the caller set it (zeros).
 int bra_tri_inverse_upper(bra_ctx* ctx, int k, const double* R, int64_t ldr, double* Rinv, int64_t ldx) {
   if (k <= 0) return BRA_OK;
   const int nblk = (k + TB - 1) / TB;
-  BRA_CUDA(ctx->ws_tritmp().reserve((size_t)k * k * 8));
+  BRA_CUDA(ctx->ws_tritmp().reserve((size_t)k * k * 8 + 256));
   double* tmp = ctx->ws_tritmp().as<double>();
-  triinv_diag_kernel<<<nblk, 32, 0, ctx->stream>>>(k, R, ldr, Rinv, ldx);
-  ctx->launches++;
+  unsigned* bar = reinterpret_cast<unsigned*>(tmp + (size_t)k * k);
+  BRA_CUDA(cudaMemsetAsync(bar, 0, 4, ctx->stream));
+  // widest level: ceil(k / 2s) pairs of (s/32)^2 tiles; half the SMs at most (the other lane may run its own cooperative grid)
+  int grid = nblk;
   for (int s = TB; s < k; s *= 2) {
-    const int nt = s / TB;
-    const int pairs = (k + 2 * s - 1) / (2 * s);
-    for (int phase = 0; phase < 2; ++phase) {
-      triinv_join_kernel<<<pairs * nt * nt, 256, 0, ctx->stream>>>(k, s, phase, R, ldr, Rinv, ldx, tmp, k);
-      ctx->launches++;
-    }
+    const int nt = s / TB, pairs = (k + 2 * s - 1) / (2 * s);
+    if (pairs * nt * nt > grid) grid = pairs * nt * nt;
   }
+  const int cap = ctx->num_sms / 2 > 0 ? ctx->num_sms / 2 : 1;
+  if (grid > cap) grid = cap;
+  int64_t ldt = k;
+  void* args[] = {(void*)&k, (void*)&R, (void*)&ldr, (void*)&Rinv, (void*)&ldx, (void*)&tmp, (void*)&ldt, (void*)&bar};
+  BRA_CUDA(cudaLaunchCooperativeKernel((void*)triinv_fused_kernel, dim3(grid), dim3(256), args, 0, ctx->stream));
+  ctx->launches++;
   BRA_CUDA(cudaGetLastError());
   return BRA_OK;
 }
