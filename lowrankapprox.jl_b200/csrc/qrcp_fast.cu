@@ -22,6 +22,7 @@
 //     (double buffered: it runs ahead of pass 2) and stores the winner column in LAPACK layout.
 //   Two named barriers per step; shared arrays are addressed by 32-bit offsets (no generic pointers in registers).
 #include "common.cuh"
+#include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 #include "qrcp_common.cuh"
@@ -90,9 +91,18 @@ __device__ __forceinline__ void tm_st2(uint32_t taddr, const double2 x) {
 }
 __device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// TMEM columns of a compute warp: quadrants 0-2 are shared by four compute warps (128 columns each), quadrant 3 by three
-// (the comm warp keeps no columns): 168 each
-__host__ __device__ __forceinline__ int qf_twin(int warp) { return (warp & 3) < 3 ? 128 : 168; }
+// Tensor-memory budget of a compute warp.  A warp reaches the 32 lanes of quadrant warp % 4 over all 512 columns; the
+// quadrant is shared by the compute warps w, w + 4, w + 8, (w + 12) -- four in quadrants 0-2, three in quadrant 3 (the comm
+// warp keeps no columns).  The quadrant's floor(512 / tchunk) slab columns are dealt out as evenly as possible (round 2a:
+// fixed 128- / 168-column windows wasted up to 20 TMEM columns per warp: 48 instead of 56 slab columns at l = 520).
+__host__ __device__ __forceinline__ int qf_tcap(int warp, int tchunk) {        // slab columns of this warp in TMEM
+  const int nw = (warp & 3) < 3 ? 4 : 3, r = warp >> 2, cq = 512 / tchunk;
+  return cq / nw + (r < cq % nw ? 1 : 0);
+}
+__host__ __device__ __forceinline__ int qf_toff(int warp, int tchunk) {        // first TMEM column of this warp's share
+  const int nw = (warp & 3) < 3 ? 4 : 3, r = warp >> 2, cq = 512 / tchunk;
+  return tchunk * (r * (cq / nw) + (r < cq % nw ? r : cq % nw));
+}
 
 #ifdef BRA_QRCP_TRACE
 __device__ __forceinline__ long long qf_gtime() {
@@ -199,9 +209,9 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qrcp_fast_kernel(QrcpParams p) 
   // ---- where column j of compute warp w lives: class 0 = tensor memory (the first tcap columns of every warp),
   //      class 1 = shared memory slot (j - tcap) * 15 + w while slots last, class 2 = global memory (L2) ----
   const int tchunk = 4 * nchtot;                       // TMEM columns per slab column
-  auto tcap_of = [&](int w) { return p.fast >= 2 ? qf_twin(w) / tchunk : 0; };
+  auto tcap_of = [&](int w) { return p.fast >= 2 ? qf_tcap(w, tchunk) : 0; };
   auto tm_col = [&](int w, int j) -> uint32_t {        // TMEM address of chunk 0 of column j of warp w
-    return tbase + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(qf_twin(w) * (w >> 2) + j * tchunk);
+    return tbase + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(qf_toff(w, tchunk) + j * tchunk);
   };
   auto class_of = [&](int w, int j, int& slot) -> int {
     const int tc = tcap_of(w);
@@ -1008,7 +1018,9 @@ bool bra_qrcp_fast_plan(int l, int cpc, int nbe, size_t budget, bool aligned, in
   // ((j - tcap) * 15 + warp), what does not fit there stays in global memory (L2)
   static const bool no_tmem = getenv("BRA_QRCP_NOTMEM") != nullptr;
   const int cpw = (cpc + QF_CW - 1) / QF_CW;
-  const int tcap_min = no_tmem ? 0 : 128 / (4 * nch);
+  int tcap_min = 1 << 30;
+  for (int w = 0; w < QF_CW; ++w) tcap_min = std::min(tcap_min, qf_tcap(w, 4 * nch));
+  if (no_tmem) tcap_min = 0;
   int want = cpw > tcap_min ? (cpw - tcap_min) * QF_CW : 0;
   int c = (int)((budget - fixed) / ((size_t)ld * 8));
   if (c > want) c = want;
