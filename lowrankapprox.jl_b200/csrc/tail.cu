@@ -262,28 +262,23 @@ __device__ __forceinline__ bool chol_grid_barrier(unsigned* bar, unsigned target
 
 __global__ void __launch_bounds__(256, 1) chol_fused_kernel(int k, double* G, int64_t ldg, double* R, int64_t ldr, double* Dinv,
                                                             int* info, unsigned* bar) {
-  // ONE grid barrier per panel: the CTA that updates trailing tile (0, 0) -- the NEXT diagonal block -- factors and
-  // inverts it right away (look-ahead) into the other half of the double-buffered Dinv, while the other CTAs finish
-  // their tiles with the current one.
   __shared__ CholSmem sm;
   __shared__ int s_fail;
   if (threadIdx.x == 0) s_fail = 0;
   const int nblk = (k + TB - 1) / TB, Gn = gridDim.x;
   unsigned epoch = 0;
-  if (blockIdx.x == 0 && threadIdx.x < 32) chol_diag_body(k, 0, G, ldg, R, ldr, Dinv, info);
-  for (int jb = 0; jb + 1 < nblk; ++jb) {
+  for (int jb = 0; jb < nblk; ++jb) {
     const int j0 = jb * TB;
+    if (blockIdx.x == 0 && threadIdx.x < 32) chol_diag_body(k, j0, G, ldg, R, ldr, Dinv, info);
+    const int nb = nblk - jb - 1;
+    if (nb == 0) break;
     if (!chol_grid_barrier(bar, ++epoch * Gn, &s_fail)) break;
-    const double* Dcur = Dinv + (jb & 1) * TB * TB;
-    const int nb = nblk - jb - 1, nt = nb * (nb + 1) / 2;
+    const int nt = nb * (nb + 1) / 2;
     for (int t = blockIdx.x; t < nt; t += Gn) {
       __syncthreads();
-      chol_trail_body(sm, t, k, j0, G, ldg, R, ldr, Dcur);
-      if (t == 0) {
-        __syncthreads();
-        if (threadIdx.x < 32) chol_diag_body(k, j0 + TB, G, ldg, R, ldr, Dinv + ((jb + 1) & 1) * TB * TB, info);
-      }
+      chol_trail_body(sm, t, k, j0, G, ldg, R, ldr, Dinv);
     }
+    if (!chol_grid_barrier(bar, ++epoch * Gn, &s_fail)) break;
   }
   if (s_fail && threadIdx.x == 0) atomicExch(info, -1);
 }
@@ -880,9 +875,9 @@ int bra_cholesky_upper(bra_ctx* ctx, int k, double* G, int64_t ldg, double* Rout
   ProfScope ps(ctx, BRA_PROF_QR);
   // sticky status: reset by bra_chol_status_reset, read by bra_chol_status; the side lane reports in the next word
   int* info = ctx->info.as<int>() + 12 + (ctx->lane ? 1 : 0);
-  BRA_CUDA(ctx->ws_cholscr().reserve((size_t)2 * TB * TB * 8 + 256));
-  double* Dinv = ctx->ws_cholscr().as<double>();              // double buffered: [2][32 x 32]
-  unsigned* bar = reinterpret_cast<unsigned*>(Dinv + 2 * TB * TB);
+  BRA_CUDA(ctx->ws_cholscr().reserve((size_t)TB * TB * 8 + 256));
+  double* Dinv = ctx->ws_cholscr().as<double>();
+  unsigned* bar = reinterpret_cast<unsigned*>(Dinv + TB * TB);
   BRA_CUDA(cudaMemset2DAsync(Rout, (size_t)ldr * 8, 0, (size_t)k * 8, (size_t)k, ctx->stream));    // zeros below the diagonal
   BRA_CUDA(cudaMemsetAsync(bar, 0, 4, ctx->stream));
   const int nblk = (k + TB - 1) / TB;
