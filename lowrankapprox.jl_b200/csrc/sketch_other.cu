@@ -366,9 +366,14 @@ __global__ void __launch_bounds__(256, 3) srft_kernel(const __grid_constant__ CU
         const int64_t f = sf[sp];
         const int pc = spc[sp], pn = spn[sp];
         const double2 w1 = twiddle(f);                           // w = exp(-2 pi i f / m)
+        // w^kk, kk = kk0 + 2q: one table lookup for this lane's first q, then -- when a lane handles several q (short FFTs:
+        // Qc > GS) -- a recurrence with w^(2 GS) instead of two table reads + a 64-bit modulo per term (measured at
+        // 16384 rows: order 40 0.845 -> 0.744 ms; the same trick on the FFT-pass twiddles made the FP64-bound long passes
+        // slower and was dropped)
+        const int64_t t0 = (int64_t)(kk0 + 2 * ql) * f, ts = (int64_t)(2 * GS) * f;
+        double2 w = twiddle(mpow2 ? (t0 & (P.m - 1)) : (t0 % P.m));
+        const double2 wst = (Qc > GS) ? twiddle(mpow2 ? (ts & (P.m - 1)) : (ts % P.m)) : make_double2(1.0, 0.0);
         for (int q = ql; q < Qc; q += GS) {
-          const int64_t tq = (int64_t)(kk0 + 2 * q) * f;
-          const double2 w = twiddle(mpow2 ? (tq & (P.m - 1)) : (tq % P.m));      // w^kk, kk = kk0 + 2q
           const double2 E = Z[(size_t)pc * Qc + q];
           const double2 On = Z[(size_t)pn * Qc + q];             // O = conj(On)
           // even inner column: (E + O)/2 ; odd: -i (E - O)/2
@@ -379,6 +384,7 @@ __global__ void __launch_bounds__(256, 3) srft_kernel(const __grid_constant__ CU
                                                     xe.y + fma(w1.x, xo.y, w1.y * xo.x)));
           zr += term.x;
           zi += term.y;
+          w = cmul(w, wst);
         }
       }
       for (int sh = GS >> 1; sh > 0; sh >>= 1) {
