@@ -996,56 +996,77 @@ int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64
   if (k > 1) {
     // team size: k <= TS * R rows in registers (R = 4, or 8 on request); panel = 2*BC columns of X and of J in
     // shared memory
-    int ts = 32, rr = 4;
-    while (ts < 1024 && ts * 4 < k) ts <<= 1;
-    if (ts * 4 < k) {
-      ctx->set_error("Jacobi SVD: k too large for the register-resident team kernel (k <= 4096)");
-      return BRA_ERR_UNSUPPORTED;
-    }
-    // measured on B200 (k = 500): 8 rows per thread and blocks of 4 columns (63 CTAs) balance the per-round
-    // latency chain against the per-step exchange
-    bool r8 = ts >= 64 && ts <= 256;
-    if (const char* ev = getenv("BRA_JACOBI_R8")) r8 = r8 && atoi(ev) > 0;
-    if (r8) {
-      ts >>= 1;
-      rr = 8;
-    }
-    bool noj = may_skip && rr == 8;
-    // without the J panel a pair fits one warp (16 rows per lane): no cross-warp reduction, no team barrier --
-    // measured at k = 498: 4.37 ms against 4.56 ms with two warps per pair
-    const char* r16 = getenv("BRA_JACOBI_R16");
-    if (noj && k <= 512 && !(r16 && atoi(r16) == 0)) {
-      ts = 32;
-      rr = 16;
-    }
-    if (skip_J) *skip_J = noj;
-    if (!noj) {
-      set_identity_kernel<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(k, J, ldj);
-      ctx->launches++;
-    }
-    int bc = 1024 / ts;
-    if (bc > 4) bc = 4;
-    if (const char* ev = getenv("BRA_JACOBI_BC")) {
-      const int v = atoi(ev);
-      if (v > 0 && v <= 8 && v * ts <= 1024 && (v & (v - 1)) == 0) bc = v;
-    }
+    int ts = 32, rr = 4, bc = 4;
+    bool noj = false;
     const size_t kp = (size_t)((k + 1) & ~1);
     const size_t budget = (size_t)ctx->smem_optin - 2048;
     auto need = [&](int b) { return (size_t)(noj ? 16 : 32) * b * kp + (size_t)2 * b * ((ts / 32) * 4 + 2) * 8 + (size_t)4 * (2 * ((k + 2 * b - 1) / (2 * b))) + 64; };
-    while (bc > 1 && (need(bc) > budget || k <= bc)) bc >>= 1;   // tiny cores: keep at least two blocks of real columns
-    if (need(bc) > budget) {
-      ctx->set_error("Jacobi SVD: k too large for the shared-memory panel");
-      return BRA_ERR_UNSUPPORTED;
-    }
-    int nblk = 2 * ((k + 2 * bc - 1) / (2 * bc));
-    while (nblk / 2 > ctx->num_sms && bc < 8) {      // one CTA per block pair must be co-resident
-      bc <<= 1;
+    int nblk;
+    if (k > 1024) {
+      // large cores: one CTA per block pair must be co-resident (k <= 2 bc #SMs) and the panel must fit shared memory
+      // (2 bc columns of X, and of J unless the caller recovers the rotations itself).  Without J: blocks of 6 columns,
+      // 4 warps x 16 rows per pair (k <= 12 #SMs = 1776 on B200); with J: blocks of 4, 5 warps x 8 rows
+      // (k <= 8 #SMs = 1184, 1280 rows).
+      noj = may_skip;
+      if (noj) {
+        bc = 6; ts = 128; rr = 16;
+      } else {
+        bc = 4; ts = 160; rr = 8;
+      }
       nblk = 2 * ((k + 2 * bc - 1) / (2 * bc));
-    }
-    if (nblk / 2 > ctx->num_sms || need(bc) > budget || bc * ts > 1024) {
-      ctx->set_error("Jacobi SVD: core too large -- one CTA per pair of 4-column blocks must be co-resident (k <= 8 * #SMs = "
-                     "1184 on B200)");
-      return BRA_ERR_UNSUPPORTED;
+      if (nblk / 2 > ctx->num_sms || need(bc) > budget || ts * rr < k) {
+        ctx->set_error("Jacobi SVD: core too large -- one CTA per pair of column blocks must be co-resident: k <= 12 * #SMs "
+                       "(1776 on B200) for psvdfact, k <= 8 * #SMs (1184) where the rotations are accumulated (pheigfact, CUR)");
+        return BRA_ERR_UNSUPPORTED;
+      }
+      if (skip_J) *skip_J = noj;
+      if (!noj) {
+        set_identity_kernel<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(k, J, ldj);
+        ctx->launches++;
+      }
+    } else {
+      while (ts < 1024 && ts * 4 < k) ts <<= 1;
+      // measured on B200 (k = 500): 8 rows per thread and blocks of 4 columns (63 CTAs) balance the per-round
+      // latency chain against the per-step exchange
+      bool r8 = ts >= 64 && ts <= 256;
+      if (const char* ev = getenv("BRA_JACOBI_R8")) r8 = r8 && atoi(ev) > 0;
+      if (r8) {
+        ts >>= 1;
+        rr = 8;
+      }
+      noj = may_skip && rr == 8;
+      // without the J panel a pair fits one warp (16 rows per lane): no cross-warp reduction, no team barrier --
+      // measured at k = 498: 4.37 ms against 4.56 ms with two warps per pair
+      const char* r16 = getenv("BRA_JACOBI_R16");
+      if (noj && k <= 512 && !(r16 && atoi(r16) == 0)) {
+        ts = 32;
+        rr = 16;
+      }
+      if (skip_J) *skip_J = noj;
+      if (!noj) {
+        set_identity_kernel<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(k, J, ldj);
+        ctx->launches++;
+      }
+      bc = 1024 / ts;
+      if (bc > 4) bc = 4;
+      if (const char* ev = getenv("BRA_JACOBI_BC")) {
+        const int v = atoi(ev);
+        if (v > 0 && v <= 8 && v * ts <= 1024 && (v & (v - 1)) == 0) bc = v;
+      }
+      while (bc > 1 && (need(bc) > budget || k <= bc)) bc >>= 1;   // tiny cores: keep at least two blocks of real columns
+      if (need(bc) > budget) {
+        ctx->set_error("Jacobi SVD: k too large for the shared-memory panel");
+        return BRA_ERR_UNSUPPORTED;
+      }
+      nblk = 2 * ((k + 2 * bc - 1) / (2 * bc));
+      while (nblk / 2 > ctx->num_sms && bc < 8) {      // one CTA per block pair must be co-resident
+        bc <<= 1;
+        nblk = 2 * ((k + 2 * bc - 1) / (2 * bc));
+      }
+      if (nblk / 2 > ctx->num_sms || need(bc) > budget || bc * ts > 1024) {
+        ctx->set_error("Jacobi SVD: core does not fit the co-resident grid");
+        return BRA_ERR_UNSUPPORTED;
+      }
     }
     const int grid = nblk / 2;
     const size_t smem = need(bc);
@@ -1082,6 +1103,8 @@ int bra_jacobi_svd(bra_ctx* ctx, int k, double* X, int64_t ldx, double* J, int64
     JN(8, 32) JN(4, 32) JN(8, 64) JN(4, 64) JN(8, 128) JN(4, 128)
     if (noj && rr == 16 && bc == 4) e = launch_jacobi<4, 32, 16, false>(P, grid, smem, ctx->stream);
     if (noj && rr == 16 && bc == 8) e = launch_jacobi<8, 32, 16, false>(P, grid, smem, ctx->stream);
+    if (noj && rr == 16 && bc == 6 && ts == 128) e = launch_jacobi<6, 128, 16, false>(P, grid, smem, ctx->stream);
+    if (!noj && rr == 8 && bc == 4 && ts == 160) e = launch_jacobi<4, 160, 8, true>(P, grid, smem, ctx->stream);
 #undef JL
 #undef JN
     BRA_CUDA(e);

@@ -322,3 +322,43 @@ def test_psvdfact_core_on_non_geometric_spectra(ctx, monkeypatch, name, noprecon
     for c in cut[:3]:
         Pg, Po = Sg.U[:, :c] @ Sg.U[:, :c].T, So.U[:, :c] @ So.U[:, :c].T
         assert np.linalg.norm(Pg - Po, 2) <= 1e-6
+
+
+def _graded(m, n, r, dec, seed):
+    rng = np.random.default_rng(seed)
+    U, _ = np.linalg.qr(rng.standard_normal((m, r)))
+    V, _ = np.linalg.qr(rng.standard_normal((n, r)))
+    s = 10.0 ** (-dec * np.arange(r) / r)
+    return np.asfortranarray((U * s) @ V.T), s
+
+
+def test_psvdfact_core_beyond_1024(ctx):
+    """Cores of more than 1024 columns take the 6-column-block configuration of the Jacobi kernel (k <= 12 #SMs); the
+    reference has no size limit (LAPACK gesdd).  Property test: rank, singular values against the construction,
+    orthogonality, reconstruction."""
+    import brapprox
+    A, s = _graded(2300, 2100, 1500, 11.0, 3)
+    F = brapprox.psvdfact(A, rtol=1e-10, seed=1, ctx=ctx)
+    kk = len(F.S)
+    assert F.k_id > 1024 and kk > 1024
+    assert np.max(np.abs(F.S - s[:kk])) <= 1e-9
+    assert np.linalg.norm(F.U.T @ F.U - np.eye(kk)) <= 1e-11
+    assert np.linalg.norm(F.Vt @ F.Vt.T - np.eye(kk)) <= 1e-10
+    assert np.linalg.norm(A - F.matrix(), 2) <= 5e-9
+
+
+def test_pheigfact_core_beyond_1024(ctx):
+    """The same for a core whose rotations are accumulated (pheigfact; blocks of 4 columns, 5 warps per pair,
+    k <= 8 #SMs = 1184)."""
+    import brapprox
+    n, r = 2400, 1170
+    rng = np.random.default_rng(5)
+    V, _ = np.linalg.qr(rng.standard_normal((n, r)))
+    lam = 10.0 ** (-10.0 * np.arange(r) / r) * np.where(np.arange(r) % 3 == 1, -1.0, 1.0)
+    A = (V * lam) @ V.T
+    A = np.asfortranarray(0.5 * (A + A.T))
+    F = brapprox.pheigfact(A, rtol=1e-9, seed=2, ctx=ctx)
+    kk = len(F.values)
+    assert F.k_id > 1024 and kk > 1024
+    assert np.linalg.norm(F.vectors.T @ F.vectors - np.eye(kk)) <= 1e-9
+    assert np.linalg.norm(A - (F.vectors * F.values) @ F.vectors.T, 2) <= 1e-7

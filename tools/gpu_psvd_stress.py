@@ -9,7 +9,7 @@ ctx = brapprox.Context(0)
 dev = torch.device("cuda", 0)
 bad = 0
 for (m, n, r, dec) in [(700, 600, 40, 9.0), (1500, 1300, 160, 10.0), (2500, 2200, 360, 11.0), (4096, 3500, 800, 11.0),
-                       (5000, 4000, 1300, 11.0)]:
+                       (5000, 4000, 1300, 11.0), (5000, 4500, 1800, 11.0)]:
     g = torch.Generator(device=dev); g.manual_seed(m)
     U, _ = torch.linalg.qr(torch.randn(m, r, dtype=torch.float64, device=dev, generator=g))
     V, _ = torch.linalg.qr(torch.randn(n, r, dtype=torch.float64, device=dev, generator=g))
