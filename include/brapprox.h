@@ -212,6 +212,15 @@ int bra_sketchfact_f64(bra_ctx* ctx, char side, char trans, int64_t m, int64_t n
 int bra_cur_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, int64_t k, const int64_t* rows1,
                 const int64_t* cols1, int hermitian);
 
+/* Float32 matrices.  The reference is generic in the element type T (LRAOptions(T), src/LowRankApprox.jl:96-118;
+ * pqrfact / idfact / psvdfact / ... take AbstractMatOrLinOp{T}); the kernels here are FP64.  bra_widen_f32 uploads a
+ * Float32 A (host or device, column-major, lda in elements) and widens it on the device into a context-owned FP64 copy;
+ * *dA / *ldd are then passed as the device-resident `A` / `lda` of any *_f64 entry point, and the caller rounds the
+ * fetched factors to Float32.  The copy stays valid until the next bra_widen_f32 on the same context.  The
+ * factorization itself runs in FP64, so with T = Float32 defaults (rtol = 5 eps(Float32)) the results agree with the
+ * reference's Float32 path to Float32 accuracy, not bit for bit.  ComplexF32 / ComplexF64 are not built. */
+int bra_widen_f32(bra_ctx* ctx, int64_t m, int64_t n, const float* A, int64_t lda, const double** dA, int64_t* ldd);
+
 /* prange(trans, A, opts) (src/prange.jl:14-62): an orthonormal basis of the range of A (trans 'n'), of A' ('c') or of
  * both ('b', square A; a Hermitian A falls back to 'n', :26).  sketch = :none -> pqrfact(op(A))[:Q] (:50-52); :sub ->
  * prange_sub (:64-77); otherwise the pivoted QR of the right-hand sketch B = op(A) S, sketchfact(:right, trans, A, opts)

@@ -99,6 +99,8 @@ lib.bra_pheigfact_f64.argtypes = [_vp, _i64, _vp, _i64, C.POINTER(bra_opts), C.P
 lib.bra_sketchfact_f64.argtypes = [_vp, C.c_char, C.c_char, _i64, _i64, _vp, _i64, C.POINTER(bra_opts),
                                    C.POINTER(bra_rand)]
 lib.bra_cur_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, C.c_int]
+lib.bra_widen_f32.argtypes = [_vp, _i64, _i64, _vp, _i64, _vp, _vp]
+lib.bra_widen_f32.restype = C.c_int
 lib.bra_prange_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand),
                                C.POINTER(bra_rand)]
 lib.bra_snorm_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _i64, C.POINTER(bra_opts), _i64, _vp,
@@ -136,6 +138,12 @@ class LRAOptions:
     snorm_niter: int = 32
     verb: bool = True
     seed: int = 0            # fast-mode device RNG key (no reference counterpart: Julia's global RNG)
+
+    @classmethod
+    def for_eltype(cls, dtype, **kw) -> "LRAOptions":
+        """LRAOptions(T; args...) (src/LowRankApprox.jl:96-118): pheig_orthtol = sqrt(eps(T)), rtol = 5 eps(T)."""
+        e = float(np.finfo(np.dtype(dtype)).eps)
+        return cls(pheig_orthtol=float(np.sqrt(e)), rtol=5 * e).copy(**kw)
 
     def copy(self, **kw) -> "LRAOptions":
         """copy(opts; args...) (src/LowRankApprox.jl:122-131): never mutates the caller's object."""
@@ -220,7 +228,7 @@ def mat_arg(A):
         return mat_arg(DeviceMatrix.from_torch(A))
     a = np.asarray(A)
     if a.dtype != np.float64:
-        raise TypeError("only Float64 is built (SURVEY 8f-3); got " + str(a.dtype))
+        raise TypeError("Float64 (and, through Context.widen_f32, Float32) matrices only; got " + str(a.dtype))
     if a.ndim != 2:
         raise ValueError("matrix expected")
     if not a.flags.f_contiguous:
@@ -298,6 +306,19 @@ class Context:
         inf = bra_info()
         self.check(lib.bra_get_info(self._h, C.byref(inf)))
         return inf
+
+    def widen_f32(self, A: np.ndarray) -> "DeviceMatrix":
+        """bra_widen_f32: uploads a Float32 matrix and widens it on the device; the returned DeviceMatrix (context-owned
+        memory, valid until the next widen_f32 on this context) is accepted wherever an FP64 matrix is."""
+        a = np.asarray(A)
+        if a.dtype != np.float32 or a.ndim != 2:
+            raise TypeError("widen_f32: 2-D float32 array expected")
+        if not a.flags.f_contiguous:
+            a = np.asfortranarray(a)
+        dA, ld = C.c_void_p(), C.c_int64()
+        self.check(lib.bra_widen_f32(self._h, a.shape[0], a.shape[1], C.c_void_p(a.ctypes.data), max(a.shape[0], 1),
+                                     C.byref(dA), C.byref(ld)))
+        return DeviceMatrix(dA.value or 0, a.shape[0], a.shape[1], ld.value, keep=self)
 
     def fetch(self, which: int, shape, dtype=np.float64, out: Optional[np.ndarray] = None) -> np.ndarray:
         """Copies one factor of the last call into host memory.  `out` (optional) is a caller-owned column-major

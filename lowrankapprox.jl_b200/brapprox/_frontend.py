@@ -2,6 +2,9 @@
 from __future__ import annotations
 
 import ctypes as C
+import dataclasses
+import functools
+import inspect
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -23,6 +26,50 @@ def _trans(trans: str) -> bytes:
     if t not in ("n", "c"):
         raise ValueError("trans")                      # chktrans (src/LowRankApprox.jl:150)
     return t.encode()
+
+
+def _is_f32(A) -> bool:
+    return isinstance(A, np.ndarray) and A.dtype == np.float32
+
+
+def _narrow(x):
+    """Rounds the FP64 arrays of a result (dataclass, tuple, list) to Float32; index sets and bookkeeping stay."""
+    if isinstance(x, np.ndarray):
+        return x.astype(np.float32) if x.dtype == np.float64 else x
+    if dataclasses.is_dataclass(x) and not isinstance(x, type):
+        for f in dataclasses.fields(x):
+            if f.name not in ("rounds", "steps"):
+                setattr(x, f.name, _narrow(getattr(x, f.name)))
+        return x
+    if isinstance(x, tuple):
+        return tuple(_narrow(v) for v in x)
+    return x
+
+
+def _eltype(fn):
+    """Element-type dispatch of the reference's front-ends (f(A::AbstractMatOrLinOp{T}, opts = LRAOptions(T); ...)):
+    a Float32 A gets the T = Float32 default options when none are passed, is widened on the device (bra_widen_f32),
+    factored by the FP64 kernels, and the factors are rounded to Float32."""
+    takes_opts = "opts" in inspect.signature(fn).parameters
+
+    @functools.wraps(fn)
+    def wrapper(A, *args, **kw):
+        if not _is_f32(A):
+            return fn(A, *args, **kw)
+        if kw.get("out") is not None:
+            raise TypeError("out= buffers are FP64; not available for a Float32 A")
+        args = list(args)
+        if not takes_opts:
+            pass
+        elif args and (args[0] is None or isinstance(args[0], LRAOptions)):
+            if args[0] is None:
+                args[0] = LRAOptions.for_eltype(np.float32)
+        elif kw.get("opts") is None:
+            kw["opts"] = LRAOptions.for_eltype(np.float32)
+        ctx = kw.get("ctx") or default_context()
+        kw["ctx"] = ctx
+        return _narrow(fn(ctx.widen_f32(A), *args, **kw))
+    return wrapper
 
 
 def _opts(opts: Optional[LRAOptions], kw) -> LRAOptions:
@@ -210,6 +257,7 @@ def idfact_device(A, opts: Optional[LRAOptions] = None, trans: str = "n", rand=N
     return ctx.info()
 
 
+@_eltype
 def idfact(A, opts: Optional[LRAOptions] = None, trans: str = "n", rand=None,
            ctx: Optional[Context] = None, **kw) -> IDPackedV:
     """idfact(trans, A, opts; kw...) -> IDPackedV(sk, rd, T) (src/id.jl:434-447)."""
@@ -225,6 +273,8 @@ def idfact(A, opts: Optional[LRAOptions] = None, trans: str = "n", rand=None,
 
 def _skeleton(A, opts, trans, rand, ctx, kw):
     """sketchfact(:left, trans, A, opts)[:p][1:k] (the index set only; src/cur.jl:538-556 asks for retval "")."""
+    if _is_f32(A):
+        A = ctx.widen_f32(A)
     idfact_device(A, opts, trans, rand, ctx, **kw)
     inf, _, _ = _rounds(ctx)
     k, n = int(inf.k), int(inf.n)
@@ -242,6 +292,8 @@ def curfact(A, opts: Optional[LRAOptions] = None, rand=None, ctx: Optional[Conte
     A = np.asarray(A)
     if A.ndim != 2:
         raise ValueError("A")
+    if _is_f32(A) and opts is None:
+        opts = LRAOptions.for_eltype(np.float32)
     r1, r2 = (rand if rand is not None else (None, None))
     m, n = A.shape
     if m == n and np.array_equal(A, A.T):
@@ -257,6 +309,7 @@ def curfact(A, opts: Optional[LRAOptions] = None, rand=None, ctx: Optional[Conte
     return B.CURPackedU(rows[:k], cols[:k])
 
 
+@_eltype
 def CUR(A, rows, cols=None, ctx: Optional[Context] = None):
     """CUR(A, U::CURPackedU) / CUR(A, rows, cols) / HermCUR(A, cols) (src/cur.jl:85-109): the factors of the CUR
     decomposition named by the index sets curfact returned -- C, R and the pseudo-inverse of the k x k core
@@ -367,6 +420,7 @@ def pqrfact_device(A, opts: Optional[LRAOptions] = None, trans: str = "n", rand=
     return ctx.info()
 
 
+@_eltype
 def pqrfact(A, opts: Optional[LRAOptions] = None, trans: str = "n", rand=None,
             ctx: Optional[Context] = None, **kw):
     """pqrfact(trans, A, opts; kw...) (src/pqr.jl:290-307), sketched path.  Returns PartialQR(Q, R, p) when
@@ -399,6 +453,7 @@ def _orgqr(Bl: np.ndarray, tau: np.ndarray, k: int) -> np.ndarray:
     return Q
 
 
+@_eltype
 def sketchfact(A, opts: Optional[LRAOptions] = None, side: str = "left", trans: str = "n", rand=None,
                ctx: Optional[Context] = None, **kw):
     """sketchfact(side, trans, A, opts; kw...) (src/sketch.jl:52-66): the early-terminating pivoted QR of the SKETCH of
@@ -450,6 +505,7 @@ def sketchfact(A, opts: Optional[LRAOptions] = None, side: str = "left", trans: 
     return B.PQRFactors(Q, R, p, k, T if want_t else None, rounds)
 
 
+@_eltype
 def prange(A, opts: Optional[LRAOptions] = None, trans: str = "n", rand=None, rand2=None,
            ctx: Optional[Context] = None, **kw):
     """prange(trans, A, opts; kw...) -> Q (src/prange.jl:14-62): an orthonormal basis of the range of A (trans "n"), of
@@ -487,6 +543,7 @@ def psvdfact_device(A, opts: Optional[LRAOptions] = None, rand=None, ctx: Option
     return ctx.info()
 
 
+@_eltype
 def psvdfact(A, opts: Optional[LRAOptions] = None, rand=None, ctx: Optional[Context] = None, out=None, **kw):
     """psvdfact(A, opts; kw...) -> PartialSVD(U, S, Vt) (src/psvd.jl:238-272).
 
@@ -507,6 +564,7 @@ def psvdfact(A, opts: Optional[LRAOptions] = None, rand=None, ctx: Optional[Cont
     return B.PartialSVD(U, S, Vt, int(inf.k), rounds)
 
 
+@_eltype
 def pheigfact(A, opts: Optional[LRAOptions] = None, rand=None, ctx: Optional[Context] = None, **kw):
     """pheigfact(A, opts; kw...) -> PartialHermEigen(values, vectors) (src/pheig.jl:276-296); A real symmetric,
     otherwise ValueError("matrix must be Hermitian") (:279)."""

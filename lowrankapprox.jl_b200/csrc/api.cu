@@ -407,7 +407,7 @@ int bra_destroy(bra_ctx* ctx) {
   if (!ctx) return BRA_OK;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->A_stage, &ctx->omega_t, &ctx->omega_in, &ctx->B, &ctx->B2, &ctx->partial, &ctx->vn1,
+  DevBuf* bufs[] = {&ctx->A_stage, &ctx->A_wide, &ctx->omega_t, &ctx->omega_in, &ctx->B, &ctx->B2, &ctx->partial, &ctx->vn1,
                     &ctx->vn2, &ctx->lpos, &ctx->fpend, &ctx->rec, &ctx->jpvt, &ctx->tau, &ctx->rdiag, &ctx->info,
                     &ctx->kbtrace, &ctx->R11, &ctx->T, &ctx->C, &ctx->Q, &ctx->R1, &ctx->Rfull, &ctx->W, &ctx->G,
                     &ctx->U, &ctx->S, &ctx->Vt, &ctx->Z, &ctx->scratch, &ctx->scratch2, &ctx->scratch3,
@@ -1031,6 +1031,49 @@ int bra_idfact_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double*
   if (rc) return rc;
   rc = bra_sketchfact_core(ctx, trans, m, n, dA, dlda, opts, rnd);
   if (rc) return rc;
+  BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BRA_OK;
+}
+
+namespace {
+// out[r + c * ldo] = (double)in[r + c * ldi]: one CTA per group of columns, rows coalesced
+__global__ void widen_f32_kernel(int64_t m, int64_t n, const float* __restrict__ in, int64_t ldi, double* __restrict__ out,
+                                 int64_t ldo) {
+  for (int64_t c = blockIdx.y; c < n; c += gridDim.y)
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < ldo; r += (int64_t)gridDim.x * blockDim.x)
+      out[r + c * ldo] = (r < m) ? (double)in[r + c * ldi] : 0.0;
+}
+}  // namespace
+
+// Float32 matrices (the reference's element-type parameter T, src/LowRankApprox.jl:96-118): the kernels of this
+// library are FP64 (DMMA), so a Float32 A is widened ONCE on the device -- half the PCIe bytes of a host-side
+// conversion -- into a context-owned buffer; the caller hands the returned device pointer to any *_f64 entry point
+// and rounds what it fetches.
+int bra_widen_f32(bra_ctx* ctx, int64_t m, int64_t n, const float* A, int64_t lda, const double** dA, int64_t* ldd) {
+  if (!ctx) return -1;
+  BRA_CHECK_ARG(m >= 0, 2, "m");
+  BRA_CHECK_ARG(n >= 0, 3, "n");
+  BRA_CHECK_ARG(A != nullptr || m == 0 || n == 0, 4, "A");
+  BRA_CHECK_ARG(lda >= (m > 1 ? m : 1), 5, "lda");
+  BRA_CHECK_ARG(dA != nullptr && ldd != nullptr, 6, "dA / ldd");
+  BRA_CUDA(cudaSetDevice(ctx->device));
+  const int64_t ld = ((m > 0 ? m : 1) + 1) & ~int64_t(1);
+  BRA_CUDA(ctx->A_wide.reserve((size_t)ld * (n > 0 ? n : 1) * 8));
+  *dA = ctx->A_wide.as<double>();
+  *ldd = ld;
+  if (m == 0 || n == 0) return BRA_OK;
+  const float* src = A;
+  int64_t lds = lda;
+  if (!is_device_ptr(A)) {
+    BRA_CUDA(ctx->A_stage.reserve((size_t)m * n * 4));
+    BRA_CUDA(copy2d(ctx, ctx->A_stage.p, m, A, lda, m, n, 4));
+    src = ctx->A_stage.as<float>();
+    lds = m;
+  }
+  dim3 grid((unsigned)std::min<int64_t>((ld + 255) / 256, 64), (unsigned)std::min<int64_t>(n, 148 * 16));
+  widen_f32_kernel<<<grid, 256, 0, ctx->stream>>>(m, n, src, lds, ctx->A_wide.as<double>(), ld);
+  ctx->launches++;
+  BRA_CUDA(cudaGetLastError());
   BRA_CUDA(cudaStreamSynchronize(ctx->stream));
   return BRA_OK;
 }

@@ -75,6 +75,7 @@ struct bra_ctx {
 
   // workspaces
   DevBuf A_stage;              // staging for host-resident A
+  DevBuf A_wide;               // a Float32 A widened to FP64 (bra_widen_f32)
   DevBuf omega_t;              // Omega^T, K-major  [order][m]
   DevBuf omega_in;             // staging for a host-resident Omega
   DevBuf B;                    // sketch, l x n (col-major, ld = l)

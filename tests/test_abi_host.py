@@ -184,3 +184,21 @@ def test_sketchfact_argument_checks_without_gpu():
         brapprox.sketchfact(A, trans="x")
     with pytest.raises(ValueError):
         brapprox.sketchfact(A, sketch="none")
+
+
+def test_float32_default_options_and_rounding():
+    """LRAOptions(Float32) (src/LowRankApprox.jl:96-118): rtol = 5 eps(Float32), pheig_orthtol = sqrt(eps(Float32));
+    the mirror rounds FP64 factors to Float32 and leaves index sets and bookkeeping alone."""
+    import brapprox
+    from brapprox import _frontend as fe
+    e = float(np.finfo(np.float32).eps)
+    o32 = brapprox.LRAOptions.for_eltype(np.float32, sketch="srft")
+    assert o32.rtol == 5 * e and o32.pheig_orthtol == float(np.sqrt(e)) and o32.sketch == "srft"
+    o64 = brapprox.LRAOptions.for_eltype(np.float64)
+    assert o64.rtol == brapprox.LRAOptions().rtol
+    V = brapprox.IDPackedV(np.array([2, 1]), np.array([3]), np.ones((2, 1)), [(40, 2)], [2])
+    W = fe._narrow(V)
+    assert W.T.dtype == np.float32 and W.sk.dtype == V.sk.dtype and W.rounds == [(40, 2)]
+    F = fe._narrow(brapprox.PQRFactors(None, np.eye(2), np.array([1, 2]), 2, None))
+    assert F.Q is None and F.R.dtype == np.float32 and F.k == 2
+    assert fe._is_f32(np.zeros((2, 2), np.float32)) and not fe._is_f32(np.zeros((2, 2)))
