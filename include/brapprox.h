@@ -252,8 +252,9 @@ int bra_idfact_batched_f64(bra_ctx* ctx, int64_t nblocks, int64_t m, int64_t n, 
                            const double* s, int64_t s_stride, int64_t* k_out, int64_t* p_out, double* T_out,
                            int64_t ldT, int64_t strideT);
 int64_t bra_batched_unfinished(bra_ctx* ctx);
-/* Cycles CTA 0 spent in the last batched launch: sketch, register load + norms, QRCP, outputs + T (diagnostic). */
-int bra_debug_batched_phases(bra_ctx* ctx, int64_t* out4);
+/* Cycles CTA 0 spent in the last batched launch (diagnostic), 8 entries: random tables, waiting for tiles, QRCP,
+ * outputs + T, tile issue, sketch gather, hand-over to registers, unused. */
+int bra_debug_batched_phases(bra_ctx* ctx, int64_t* out8);
 
 /* ---- multi-GPU: row-sharded tall matrices (BASELINE config 4) ----------------------
  * One process per GPU, one ctx per process.  Rank 0 calls bra_comm_unique_id and ships the 128 bytes to the other

@@ -29,7 +29,7 @@ struct BatchParams {
   const double* A;
   int64_t lda, strideA;
   int m, n, l, kcap, nb;
-  int nstages;             // tile stages in shared memory (2 unless the block is too tall)
+  int nstages;             // tile stages in shared memory (3, fewer when the block is too tall)
   double atol, rtol;
   const int64_t* perm;     // 1-based randperm(m); block b at perm + b*perm_stride (0 = shared by all blocks);
                            // nullptr: fast mode -- every block draws its OWN permutation and weights in the kernel
@@ -45,7 +45,7 @@ struct BatchParams {
   double* Tout;            // block b: k_b x (n - k_b) at Tout + b*strideT, leading dimension ldT
   int64_t ldT, strideT;
   int32_t* status;         // [block id]: 0 ok, 1 T slot too small (k_b > ldT)
-  long long* dbg;          // [CTA][4] cycles: tables+sketch, registers+norms, QRCP, outputs+T (diagnostic)
+  long long* dbg;          // [CTA][8] cycles: tables, waiting for tiles, QRCP, outputs+T, tile issue, gather, hand-over to registers
 };
 
 __device__ __forceinline__ uint64_t bsplitmix(uint64_t s0, uint64_t i) {      // (i+1)-th output of SplitMix64 seeded s0
@@ -55,13 +55,49 @@ __device__ __forceinline__ uint64_t bsplitmix(uint64_t s0, uint64_t i) {      //
   return z ^ (z >> 31);
 }
 
+__device__ __forceinline__ uint32_t bsmem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bmbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  const long long t0 = clock64();
+  do {
+    if (clock64() - t0 > (1ll << 31)) break;        // ~1 s: never hang the device (the results then fail their checks)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bsmem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+// BULK: the tiles arrive as one bulk copy per column (the copy engine, 4 KB each, completion on an mbarrier) into a
+// column-major stage [16][CS]; otherwise as 8-byte cp.async into a row-major stage [m][17] (any alignment).  Measured
+// on B200: a warp-wide 8-byte cp.async with 32 scattered shared-memory targets costs ~16 LSU cycles, i.e. 16 B/clk per
+// SM -- the whole sketch phase ran at that rate.
+template <bool BULK>
 __global__ void __launch_bounds__(BT, 1) idfact_batched_kernel(BatchParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t mbar[3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m = P.m, n = P.n, l = P.l;
   constexpr int TC = 16;                                         // columns of A_b per tile
   constexpr int TS = TC + 1;                                     // row stride of a tile (odd: conflict-free both ways)
-  const int nst = P.nstages;                                     // 2: double buffered; 1: tall blocks
+  // BULK: column stride = 2 (mod 4) doubles: 16-byte aligned columns, and the 16 columns of one row fall on 8 distinct
+  // 8-byte banks (a 2-way conflict in the gather instead of 16-way)
+  const int CS = (m % 4 == 2) ? m : m + 2;
+  const int rstr = BULK ? 1 : TS, cstr = BULK ? CS : 1;           // element (r, c) of a stage at r * rstr + c * cstr
+  uint32_t mphase = 0;                                           // BULK: phase bit of each stage's barrier
+  if (BULK) {
+    if (tid == 0) {
+      for (int i = 0; i < 3; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bsmem_u32(&mbar[i])));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  const int nst = P.nstages;                                     // 3 / 2: tiles in flight behind the current one; 1: tall blocks
   const size_t tile_elems = (size_t)max(m, 2 * BL) * TS;
   double* tiles = reinterpret_cast<double*>(smem_raw);          // [nst][m][TS]   (later: R11, [BL][BL+1])
   double* Xb = tiles + (size_t)nst * tile_elems;                 // [BL][TS] sketch of the current tile
@@ -78,16 +114,32 @@ __global__ void __launch_bounds__(BT, 1) idfact_batched_kernel(BatchParams P) {
   const int lmin = min(l, n);
   const int64_t q = m / l, rem = m % l;                          // p_i = q + (i < rem), off_i = i*q + min(i, rem)
   bool tables_loaded = false;
-  long long tph[4] = {0, 0, 0, 0}, tlast = clock64();
+  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
 #define BTICK(i) { long long _t = clock64(); tph[i] += _t - tlast; tlast = _t; }
 
   for (int it = blockIdx.x; it < P.nblocks; it += gridDim.x) {
     const int b = P.blocks ? P.blocks[it] : it;
     const double* Ab = P.A + (int64_t)b * P.strideA;
+    if (BULK) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // R11 / tables were written by threads
     __syncthreads();
     // tile T = columns 16T..16T+15 of A_b, all m rows, staged as tile[r][c] (row stride 17) by 8-byte cp.async: warp w
     // copies column w (lanes = consecutive rows: coalesced global reads, conflict-free shared stores)
     auto issue = [&](int T) {
+      if (BULK) {
+        // one bulk copy per column, issued by lane 0 of warp c (a single thread issues them ~100 cycles apart); thread 0
+        // posts the byte count -- a copy that completes first just drives the pending-byte count negative for a while
+        const int nc = min(TC, n - T * TC);
+        uint64_t* bar = &mbar[T % nst];
+        if (tid == 0)
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bsmem_u32(bar)), "r"((uint32_t)(nc * m * 8))
+                       : "memory");
+        if (lane == 0 && warp < nc)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           bsmem_u32(tiles + (size_t)(T % nst) * tile_elems + (size_t)warp * CS)),
+                       "l"(Ab + (int64_t)(T * TC + warp) * P.lda), "r"((uint32_t)(m * 8)), "r"(bsmem_u32(bar))
+                       : "memory");
+        return;
+      }
       const int c = T * TC + warp;                 // BW == TC: one column per warp
       if (c < n) {
         const double* g = Ab + (int64_t)c * P.lda;
@@ -183,12 +235,14 @@ __global__ void __launch_bounds__(BT, 1) idfact_batched_kernel(BatchParams P) {
           wgt = sqrt(-2.0 * log(u1)) * cs;
           prow = (long long)(skey[r] & 0x7FFull);
         }
-        tab[t * l + i] = make_double2(wgt, __longlong_as_double(prow * TS));
+        tab[t * l + i] = make_double2(wgt, __longlong_as_double(prow * rstr));
       }
       tables_loaded = true;
+      if (BULK) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the key buffers become a tile stage
       __syncthreads();
     }
 
+    BTICK(0)
     // ---- sparse-Gaussian sketch, tile by tile.  Tile T = columns 16T..16T+15 of A_b, all m rows, staged as
     // tile[r][c] (row stride 17) by 8-byte cp.async: warp w copies column w (lanes = consecutive rows: coalesced
     // global reads, conflict-free shared stores).  Thread (i = tid / 16, c = tid % 16) then forms B[i, 16T + c] in the
@@ -204,35 +258,44 @@ __global__ void __launch_bounds__(BT, 1) idfact_batched_kernel(BatchParams P) {
       if (!early) issue(0);
       const int si = tid >> 4, sc = tid & 15;        // sketch row / column within the tile
       const int pi = (si < l) ? (int)q + (si < rem ? 1 : 0) : 0;
+      if (nst > 2 && ntiles > 1) issue(1);           // three stages: two tiles in flight behind the one being read
       for (int T = 0; T < ntiles; ++T) {
-        if (nst > 1 && T + 1 < ntiles) {
-          issue(T + 1);                              // its stage was last read in iteration T-1 (barrier below)
-          asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
+        // tile T + nst - 1 goes into the stage that was last read in iteration T-1 (barrier below); then wait until at
+        // most the tiles after T are still pending
+        if (nst > 1 && T + nst - 1 < ntiles) issue(T + nst - 1);
+        const int later = min(ntiles - 1 - T, nst - 1);
+        BTICK(4)
+        if (BULK) {
+          bmbar_wait(&mbar[T % nst], (mphase >> (T % nst)) & 1u);
+          mphase ^= 1u << (T % nst);
+        } else if (later >= 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else if (later == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
+        BTICK(1)
         const double* tl = tiles + (size_t)(T % nst) * tile_elems;
         if (si < l) {
           double acc = 0.0;
 #pragma unroll 4
           for (int t = 0; t < pi; ++t) {
             const double2 e = tab[t * l + si];                   // one 16-byte read: weight and row offset
-            acc += e.x * tl[__double_as_longlong(e.y) + sc];
+            acc += e.x * tl[__double_as_longlong(e.y) + sc * cstr];
           }
           Xb[si * TS + sc] = acc;
         }
         __syncthreads();
+        BTICK(5)
         if (nst == 1 && T + 1 < ntiles) issue(T + 1);
         if ((tid >> 4) == T && live) {
 #pragma unroll
           for (int i = 0; i < BL; ++i)
             if (i < l) a[i] = Xb[i * TS + (tid & 15)];
         }
+        BTICK(6)
       }
     }
     __syncthreads();
-    BTICK(0)
+    BTICK(6)
 
     // ---- one column per thread, in registers ----
     double vn1, vn2;
@@ -257,7 +320,6 @@ __global__ void __launch_bounds__(BT, 1) idfact_batched_kernel(BatchParams P) {
     }
     int lpos = live ? tid : 0x7fffffff;
 
-    BTICK(1)
     int s = 0, jblk = 0, cnt = 0, jb = min(P.nb, P.kcap), kres = (P.kcap == 0) ? 0 : -1;
     double ptol = 0.0;
     int pend_flag = 0;          // a column was flagged in the previous step
@@ -431,7 +493,7 @@ __global__ void __launch_bounds__(BT, 1) idfact_batched_kernel(BatchParams P) {
     BTICK(3)
   }
   if (tid == 0 && P.dbg)
-    for (int i = 0; i < 4; ++i) P.dbg[blockIdx.x * 4 + i] = tph[i];
+    for (int i = 0; i < 8; ++i) P.dbg[blockIdx.x * 8 + i] = tph[i];
 #undef BTICK
 }
 
@@ -476,8 +538,9 @@ int bra_idfact_batched_f64(bra_ctx* ctx, int64_t nblocks, int64_t m, int64_t n, 
   auto smem_for = [&](int nst) {
     return ((size_t)nst * tile_elems + (size_t)BL * 17 + 2 * tpad + 2 * BL + BW + 2) * 8 + (2 * BW) * 4 + 64;
   };
-  int nstages = 2;
-  if (smem_for(2) > (size_t)ctx->smem_optin) nstages = 1;
+  int nstages = 2;                  // measured on C5: a third stage buys nothing (the tile wait is 4 % of a block); tall blocks: one
+  if (const char* ev = getenv("BRA_BATCHED_STAGES")) nstages = std::max(1, std::min(3, atoi(ev)));
+  while (nstages > 1 && smem_for(nstages) > (size_t)ctx->smem_optin) --nstages;
   const size_t smem = smem_for(nstages);
   if (order < 1 || order > BL || n > BT || order > m || smem > (size_t)ctx->smem_optin) {
     ctx->set_error("batched idfact: shape outside the fused kernel (needs order = nb <= 32, n <= 512, "
@@ -521,13 +584,20 @@ int bra_idfact_batched_f64(bra_ctx* ctx, int64_t nblocks, int64_t m, int64_t n, 
   P.strideT = strideT;
   BRA_CUDA(ctx->scratch.reserve((size_t)nblocks * 4));
   P.status = ctx->scratch.as<int32_t>();
-  BRA_CUDA(ctx->scratch3.reserve((size_t)ctx->num_sms * 4 * 8));
+  BRA_CUDA(ctx->scratch3.reserve((size_t)ctx->num_sms * 8 * 8));
   P.dbg = ctx->scratch3.as<long long>();
-  BRA_CUDA(cudaFuncSetAttribute(idfact_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // bulk copies need 16-byte aligned columns of 16-byte multiples
+  const bool bulk = (m % 2 == 0) && (lda % 2 == 0) && (strideA % 2 == 0 || nblocks <= 1) &&
+                    (reinterpret_cast<uintptr_t>(A) % 16 == 0) && getenv("BRA_BATCHED_NOBULK") == nullptr;
   const int grid = (int)std::min<int64_t>(nblocks, ctx->num_sms);
-  {
+  if (bulk) {
+    BRA_CUDA(cudaFuncSetAttribute(idfact_batched_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(ctx, BRA_PROF_BATCHED);
-    idfact_batched_kernel<<<grid, BT, smem, ctx->stream>>>(P);
+    idfact_batched_kernel<true><<<grid, BT, smem, ctx->stream>>>(P);
+  } else {
+    BRA_CUDA(cudaFuncSetAttribute(idfact_batched_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(ctx, BRA_PROF_BATCHED);
+    idfact_batched_kernel<false><<<grid, BT, smem, ctx->stream>>>(P);
   }
   ctx->launches++;
   BRA_CUDA(cudaGetLastError());
@@ -572,11 +642,11 @@ int bra_idfact_batched_f64(bra_ctx* ctx, int64_t nblocks, int64_t m, int64_t n, 
 
 int64_t bra_batched_unfinished(bra_ctx* ctx) { return ctx ? ctx->batched_unfinished : -1; }
 
-int bra_debug_batched_phases(bra_ctx* ctx, int64_t* out4) {
-  if (!ctx || !out4) return -1;
-  long long h[4];
-  BRA_CUDA(cudaMemcpy(h, ctx->scratch3.p, 32, cudaMemcpyDeviceToHost));
-  for (int i = 0; i < 4; ++i) out4[i] = h[i];
+int bra_debug_batched_phases(bra_ctx* ctx, int64_t* out8) {
+  if (!ctx || !out8) return -1;
+  long long h[8];
+  BRA_CUDA(cudaMemcpy(h, ctx->scratch3.p, 64, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 8; ++i) out8[i] = h[i];
   return BRA_OK;
 }
 

@@ -36,8 +36,8 @@ for rep in range(3):
     e1.record(ext)
     e1.synchronize()
     ms = e0.elapsed_time(e1)
-ph = (ctypes.c_int64 * 4)()
+ph = (ctypes.c_int64 * 8)()
 B.lib.bra_debug_batched_phases(ctx.handle, ph)
 per = -(-nb // 148)
 print(json.dumps({"blocks": nb, "ms": ms, "us_per_block_per_sm": ms * 1e3 / per, "GBps": nb * m * n * 8 / ms / 1e6,
-                  "cta0_cycles_per_block": {k: int(v) // per for k, v in zip(["sketch", "regs", "qrcp", "out_T"], ph)}}))
+                  "cta0_cycles_per_block": {k: int(v) // per for k, v in zip(["tables", "tile_wait", "qrcp", "out_T", "issue", "gather", "handover", "-"], ph)}}))
