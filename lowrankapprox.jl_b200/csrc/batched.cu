@@ -102,8 +102,9 @@ __global__ void __launch_bounds__(BT, 1) idfact_batched_kernel(BatchParams P) {
   double* tiles = reinterpret_cast<double*>(smem_raw);          // [nst][m][TS]   (later: R11, [BL][BL+1])
   double* Xb = tiles + (size_t)nst * tile_elems;                 // [BL][TS] sketch of the current tile
   const int tpad = (((m / l) + 1) * l + 1) & ~1;                 // table entries, [t][i] layout
-  double2* tab = reinterpret_cast<double2*>(Xb + (size_t)BL * TS);   // [tpad] {weight, permuted row offset in a tile}
-  double* vv = reinterpret_cast<double*>(tab + tpad);           // [BL] Householder vector
+  double* tabw = Xb + (size_t)BL * TS;                           // [tpad] weight of term t of sketch row i at t*l + i
+  int* tabo = reinterpret_cast<int*>(tabw + tpad);               // [tpad] offset of its (permuted) row in a stage
+  double* vv = tabw + 2 * tpad;                                  // [BL] Householder vector
   double* rdblk = vv + BL;                                      // [BL] diagonal of R within the current block
   double* cv = rdblk + BL;                                      // [BW] warp candidates: norm
   double* hh = cv + BW;                                         // tau, beta
@@ -235,7 +236,8 @@ __global__ void __launch_bounds__(BT, 1) idfact_batched_kernel(BatchParams P) {
           wgt = sqrt(-2.0 * log(u1)) * cs;
           prow = (long long)(skey[r] & 0x7FFull);
         }
-        tab[t * l + i] = make_double2(wgt, __longlong_as_double(prow * rstr));
+        tabw[t * l + i] = wgt;
+        tabo[t * l + i] = (int)prow * rstr;
       }
       tables_loaded = true;
       if (BULK) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the key buffers become a tile stage
@@ -256,7 +258,11 @@ __global__ void __launch_bounds__(BT, 1) idfact_batched_kernel(BatchParams P) {
     {
       const int ntiles = (n + TC - 1) / TC;
       if (!early) issue(0);
-      const int si = tid >> 4, sc = tid & 15;        // sketch row / column within the tile
+      // sketch row / column within the tile.  A half-warp (one wavefront of an 8-byte load) takes 8 columns of TWO
+      // sketch rows: in the column-major BULK stage the 16 columns of one row sit on only 8 distinct banks, two rows of
+      // different parity fill all 16; the weight read (8 bytes, two addresses per half-warp) is one wavefront per half,
+      // the offset read (4 bytes) one per warp -- 3 + 3 wavefronts per term instead of 4 + 4
+      const int si = 2 * (tid >> 5) + ((tid >> 3) & 1), sc = (tid & 7) | ((tid >> 1) & 8);
       const int pi = (si < l) ? (int)q + (si < rem ? 1 : 0) : 0;
       if (nst > 2 && ntiles > 1) issue(1);           // three stages: two tiles in flight behind the one being read
       for (int T = 0; T < ntiles; ++T) {
@@ -278,8 +284,7 @@ __global__ void __launch_bounds__(BT, 1) idfact_batched_kernel(BatchParams P) {
           double acc = 0.0;
 #pragma unroll 4
           for (int t = 0; t < pi; ++t) {
-            const double2 e = tab[t * l + si];                   // one 16-byte read: weight and row offset
-            acc += e.x * tl[__double_as_longlong(e.y) + sc * cstr];
+            acc += tabw[t * l + si] * tl[tabo[t * l + si] + sc * cstr];
           }
           Xb[si * TS + sc] = acc;
         }
