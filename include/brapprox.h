@@ -212,6 +212,13 @@ int bra_sketchfact_f64(bra_ctx* ctx, char side, char trans, int64_t m, int64_t n
 int bra_cur_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, int64_t k, const int64_t* rows1,
                 const int64_t* cols1, int hermitian);
 
+/* Rows of Omega that the last Gaussian-sketch factorization multiplied with op(A) (diagnostic).  With the library's own
+ * Omega the rounds of the adaptive loop are NESTED -- round t's Omega is round t-1's followed by fresh rows, so only the
+ * new rows are multiplied and the total is max(order) instead of the reference schedule's sum(order)
+ * (src/sketch.jl:223-240 draws every round afresh); caller-supplied Omegas, power iterations and BRA_SKETCH_FRESH=1
+ * keep the round-by-round products. */
+int64_t bra_debug_sketch_rows(bra_ctx* ctx);
+
 /* Float32 matrices.  The reference is generic in the element type T (LRAOptions(T), src/LowRankApprox.jl:96-118;
  * pqrfact / idfact / psvdfact / ... take AbstractMatOrLinOp{T}); the kernels here are FP64.  bra_widen_f32 uploads a
  * Float32 A (host or device, column-major, lda in elements) and widens it on the device into a context-owned FP64 copy;

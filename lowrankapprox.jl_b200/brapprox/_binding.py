@@ -101,6 +101,8 @@ lib.bra_sketchfact_f64.argtypes = [_vp, C.c_char, C.c_char, _i64, _i64, _vp, _i6
 lib.bra_cur_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, C.c_int]
 lib.bra_widen_f32.argtypes = [_vp, _i64, _i64, _vp, _i64, _vp, _vp]
 lib.bra_widen_f32.restype = C.c_int
+lib.bra_debug_sketch_rows.argtypes = [_vp]
+lib.bra_debug_sketch_rows.restype = C.c_int64
 lib.bra_prange_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand),
                                C.POINTER(bra_rand)]
 lib.bra_snorm_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _i64, C.POINTER(bra_opts), _i64, _vp,

@@ -210,14 +210,15 @@ int power_iterations(bra_ctx* ctx, char trans, int64_t m, int64_t n, const doubl
   return BRA_OK;
 }
 
-// B (order x nA) = Omega * op(A) into ctx->B (ld = order)
-int sketch_randn_round(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* dA, int64_t lda,
-                       const bra_opts* o, const bra_rand* rnd, int round, int64_t order) {
+// out (order x nA, ld = order) = Omega * op(A) for the `order` rows of Omega drawn for `round` (or supplied for it),
+// summed over the row shards
+int randn_product(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* dA, int64_t lda, const bra_opts* o,
+                  const bra_rand* rnd, int round, int64_t order, double* out) {
   const int64_t mA = (trans == 'n') ? m : n;
   const int64_t nA = (trans == 'n') ? n : m;
   int rc = prepare_omega_t(ctx, o, rnd, round, order, mA);
   if (rc) return rc;
-  BRA_CUDA(ctx->B.reserve((size_t)order * nA * 8));
+  ctx->sketch_rows_done += order;
   const int64_t ldt = (mA + 1) & ~int64_t(1);
   if (trans == 'n') {
     if (ctx->Apanels_state == 0) {
@@ -236,25 +237,62 @@ int sketch_randn_round(bra_ctx* ctx, char trans, int64_t m, int64_t n, const dou
       }
     }
     if (ctx->Apanels_state == 1)
-      rc = bra_gemm_sketch_panels(ctx, ctx->omega_t.as<double>(), order, mA, ctx->Apanels.as<double>(), nA,
-                                  ctx->B.as<double>(), order);
+      rc = bra_gemm_sketch_panels(ctx, ctx->omega_t.as<double>(), order, mA, ctx->Apanels.as<double>(), nA, out, order);
     else
-      rc = bra_gemm_sketch(ctx, ctx->omega_t.as<double>(), order, mA, dA, lda, nA, ctx->B.as<double>(), order);
+      rc = bra_gemm_sketch(ctx, ctx->omega_t.as<double>(), order, mA, dA, lda, nA, out, order);
   }
   else {
     // (:left, :c): B = Omega A' contracts along the rows of A -- on the transposed copy it is the :n product
     const double* At;
     int64_t ldat;
     if (mA >= 256 && transposed_A(ctx, m, n, dA, lda, &At, &ldat))
-      rc = bra_gemm_sketch(ctx, ctx->omega_t.as<double>(), order, mA, At, ldat, nA, ctx->B.as<double>(), order);
+      rc = bra_gemm_sketch(ctx, ctx->omega_t.as<double>(), order, mA, At, ldat, nA, out, order);
     else
-      rc = bra_gemm_generic(ctx, ctx->omega_t.as<double>(), ldt, 1, dA, lda, 1, order, nA, mA, ctx->B.as<double>(), order);
+      rc = bra_gemm_generic(ctx, ctx->omega_t.as<double>(), ldt, 1, dA, lda, 1, order, nA, mA, out, order);
   }
   if (rc) return rc;
-  // row-sharded A: B = sum over ranks of Omega_g * A_g  (one all-reduce of the l x n sketch per round)
-  rc = bra_allreduce_sum_f64(ctx, ctx->B.as<double>(), order * nA);
+  // row-sharded A: B = sum over ranks of Omega_g * A_g  (one all-reduce of the sketch rows per round)
+  return bra_allreduce_sum_f64(ctx, out, order * nA);
+}
+
+// B (order x nA) = Omega * op(A) into ctx->B (ld = order)
+int sketch_randn_round(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* dA, int64_t lda,
+                       const bra_opts* o, const bra_rand* rnd, int round, int64_t order) {
+  const int64_t nA = (trans == 'n') ? n : m;
+  BRA_CUDA(ctx->B.reserve((size_t)order * nA * 8));
+  int rc = randn_product(ctx, trans, m, n, dA, lda, o, rnd, round, order, ctx->B.as<double>());
   if (rc) return rc;
   if (o->sketch_randn_niter > 0) return power_iterations(ctx, trans, m, n, dA, lda, o, order);
+  return BRA_OK;
+}
+
+// Nested Gaussian sketches (fast mode).  The library's own Omega is a counter-based stream, and the rows of round t are
+// DEFINED as the rows of round t-1 followed by (order - have) rows of stream t -- so the first `have` rows of this
+// round's sketch are the sketch of the previous round, kept unfactored in (raw, raw_ld), and only the new rows are
+// multiplied: the adaptive loop contracts A with max(order) rows of Omega in total instead of sum(order).  Each round's
+// Omega is still an i.i.d. Gaussian matrix (what the reference draws, src/sketch.jl:223-240, src/util.jl:4); what is
+// given up is the independence BETWEEN rounds, which no result depends on.  Caller-supplied Omegas (parity mode), power
+// iterations and BRA_SKETCH_FRESH=1 take the round-by-round path.  On return ctx->B holds the round's sketch and
+// ctx->Braw a copy that survives the in-place QRCP.
+int sketch_randn_nested(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* dA, int64_t lda, const bra_opts* o,
+                        int round, const double* raw, int64_t raw_ld, int64_t have, int64_t order) {
+  const int64_t nA = (trans == 'n') ? n : m;
+  const int64_t d = order - have;
+  int rc;
+  BRA_CUDA(ctx->B.reserve((size_t)order * nA * 8));
+  if (have <= 0) {
+    if ((rc = randn_product(ctx, trans, m, n, dA, lda, o, nullptr, round, order, ctx->B.as<double>()))) return rc;
+  } else if (d <= 0) {
+    BRA_CUDA(copy2d(ctx, ctx->B.p, order, raw, raw_ld, order, nA));       // a sampler that does not grow: rows in hand
+  } else {
+    BRA_CUDA(ctx->Bnew.reserve((size_t)d * nA * 8));
+    if ((rc = randn_product(ctx, trans, m, n, dA, lda, o, nullptr, round, d, ctx->Bnew.as<double>()))) return rc;
+    BRA_CUDA(copy2d(ctx, ctx->B.p, order, raw, raw_ld, have, nA));
+    BRA_CUDA(copy2d(ctx, ctx->B.as<double>() + have, order, ctx->Bnew.p, d, d, nA));
+  }
+  // the previous raw copy may be the source above: cudaFree inside reserve() waits for the copies
+  BRA_CUDA(ctx->Braw.reserve((size_t)order * nA * 8));
+  BRA_CUDA(cudaMemcpyAsync(ctx->Braw.p, ctx->B.p, (size_t)order * nA * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   return BRA_OK;
 }
 
@@ -407,7 +445,7 @@ int bra_destroy(bra_ctx* ctx) {
   if (!ctx) return BRA_OK;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->A_stage, &ctx->A_wide, &ctx->omega_t, &ctx->omega_in, &ctx->B, &ctx->B2, &ctx->partial, &ctx->vn1,
+  DevBuf* bufs[] = {&ctx->A_stage, &ctx->A_wide, &ctx->Bnew, &ctx->Braw, &ctx->omega_t, &ctx->omega_in, &ctx->B, &ctx->B2, &ctx->partial, &ctx->vn1,
                     &ctx->vn2, &ctx->lpos, &ctx->fpend, &ctx->rec, &ctx->jpvt, &ctx->tau, &ctx->rdiag, &ctx->info,
                     &ctx->kbtrace, &ctx->R11, &ctx->T, &ctx->C, &ctx->Q, &ctx->R1, &ctx->Rfull, &ctx->W, &ctx->G,
                     &ctx->U, &ctx->S, &ctx->Vt, &ctx->Z, &ctx->scratch, &ctx->scratch2, &ctx->scratch3,
@@ -695,6 +733,12 @@ int bra_trsolve_T_f64(bra_ctx* ctx, int64_t k, int64_t n, const double* R, int64
   return BRA_OK;
 }
 
+// nested Gaussian sketches apply to the library's own Omega only (see sketch_randn_nested)
+bool bra_sketch_nested(const bra_opts* o, const bra_rand* rnd) {
+  return o->sketch == BRA_SKETCH_RANDN && !(rnd && rnd->n_rounds > 0) && o->sketch_randn_niter == 0 &&
+         getenv("BRA_SKETCH_FRESH") == nullptr;
+}
+
 // sketchfact(:left, trans, A, opts) + pqrback_postproc for retval "t"; shared by idfact/pqrfact/psvdfact.
 int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* dA, int64_t lda,
                         const bra_opts* o, const bra_rand* rnd) {
@@ -712,6 +756,7 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
   ctx->At_valid = false;
   ctx->Apanels_state = 0;
   ctx->A_sym_state = 0;
+  if (ctx->spec_rounds == 0) ctx->sketch_rows_done = 0;          // (else: the stacked rows of bra_stage_A)
   QrcpOut q = {0, 0, 0, 0};
   int64_t order = 0;
   if (o->sketch == BRA_SKETCH_NONE) {
@@ -743,6 +788,9 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
     res.rounds = 1;
   } else if (o->sketchfact_adap || o->rank < 0) {
     int64_t nn = o->nb << ctx->start_round;                          // src/sketch.jl:226 (n doubles every round)
+    const bool nested = bra_sketch_nested(o, rnd);
+    const double* raw = nullptr;                                     // nested: the unfactored sketch rows so far
+    int64_t raw_ld = 0, have = 0;
     for (int round = ctx->start_round;; ++round) {
       if (round >= BRA_MAX_ROUNDS) {
         ctx->set_error("adaptive loop exceeded BRA_MAX_ROUNDS");
@@ -750,11 +798,30 @@ int bra_sketchfact_core(bra_ctx* ctx, char trans, int64_t m, int64_t n, const do
       }
       order = default_order(o, nn);
       int rc = BRA_OK;
-      if (round < ctx->spec_rounds) {
+      if (round < ctx->spec_rounds && nested) {
+        // formed while A was still arriving from the host (bra_stage_A): the first `order` rows of the stacked sketch,
+        // copied out because the QRCP works in place and the next round needs them unfactored
+        BRA_CUDA(ctx->B.reserve((size_t)order * nA * 8));
+        BRA_CUDA(copy2d(ctx, ctx->B.p, order, ctx->Bspec.p, ctx->spec_ld, order, nA));
+        ctx->cur_B = ctx->B.as<double>();
+        ctx->cur_ldb = order;
+        ctx->cur_rows = order;
+        raw = ctx->Bspec.as<double>();
+        raw_ld = ctx->spec_ld;
+        have = order;
+      } else if (round < ctx->spec_rounds) {
         // this round's sketch was formed while A was still arriving from the host (bra_stage_A)
         ctx->cur_B = ctx->Bspec.as<double>() + ctx->spec_off[round];
         ctx->cur_ldb = ctx->spec_ld;
         ctx->cur_rows = order;
+      } else if (nested) {
+        rc = sketch_randn_nested(ctx, trans, m, n, dA, lda, o, round, raw, raw_ld, have, order);
+        ctx->cur_B = ctx->B.as<double>();
+        ctx->cur_ldb = order;
+        ctx->cur_rows = order;
+        raw = ctx->Braw.as<double>();
+        raw_ld = order;
+        have = order;
       } else {
         rc = sketch_round(ctx, trans, m, n, dA, lda, o, rnd, round, order);
         ctx->cur_B = ctx->B.as<double>();
@@ -968,13 +1035,15 @@ int bra_stage_A(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A,
   }
   // speculative rounds: orders 40, 72, 136, 264, 520 with the default sampler (stop before the order passes min(m, n))
   int T = 0;
-  int64_t lsum = 0, orders[5];
+  int64_t lsum = 0, orders[5], fresh_rows[5];
+  const bool nested = bra_sketch_nested(o, rnd);        // round t = the first orders[t] rows of ONE stacked sketch
   for (int64_t nn = o->nb; T < 5; nn *= 2, ++T) {
     const int64_t ord = default_order(o, nn);
-    if (ord > m || ord > n || ord <= 0) break;
+    if (ord > m || ord > n || ord <= 0 || (nested && ord <= lsum)) break;
     orders[T] = ord;
-    ctx->spec_off[T] = lsum;
-    lsum += ord;
+    ctx->spec_off[T] = nested ? 0 : lsum;
+    fresh_rows[T] = nested ? ord - lsum : ord;          // rows drawn from stream T, stored from row (nested ? lsum : spec_off)
+    lsum = nested ? ord : lsum + ord;
   }
   if (T == 0) {
     BRA_CUDA(copy2d(ctx, ctx->A_stage.p, ld, A, lda, m, n));
@@ -986,7 +1055,8 @@ int bra_stage_A(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A,
   {
     ProfScope ps(ctx, BRA_PROF_OMEGA);
     for (int t = 0; t < T; ++t) {
-      int rc = bra_fill_randn(ctx, ctx->omega_spec.as<double>() + ctx->spec_off[t] * ldt, orders[t] * ldt, o->seed, (uint64_t)t);
+      const int64_t row0 = nested ? orders[t] - fresh_rows[t] : ctx->spec_off[t];
+      int rc = bra_fill_randn(ctx, ctx->omega_spec.as<double>() + row0 * ldt, fresh_rows[t] * ldt, o->seed, (uint64_t)t);
       if (rc) return rc;
     }
   }
@@ -1016,6 +1086,7 @@ int bra_stage_A(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* A,
   }
   ctx->spec_rounds = T;
   ctx->spec_ld = lsum;
+  ctx->sketch_rows_done = lsum;
   return BRA_OK;
 }
 
@@ -1077,6 +1148,8 @@ int bra_widen_f32(bra_ctx* ctx, int64_t m, int64_t n, const float* A, int64_t ld
   BRA_CUDA(cudaStreamSynchronize(ctx->stream));
   return BRA_OK;
 }
+
+int64_t bra_debug_sketch_rows(bra_ctx* ctx) { return ctx ? ctx->sketch_rows_done : -1; }
 
 int bra_get_info(bra_ctx* ctx, bra_info* info) {
   if (!ctx) return -1;

@@ -80,6 +80,8 @@ struct bra_ctx {
   DevBuf omega_in;             // staging for a host-resident Omega
   DevBuf B;                    // sketch, l x n (col-major, ld = l)
   DevBuf B2;                   // permuted copy / scratch
+  DevBuf Bnew, Braw;           // nested Gaussian sketches: the new rows of a round, the raw (unfactored) rows so far
+  int64_t sketch_rows_done = 0;   // rows of Omega multiplied with op(A) by the last factorization (bra_debug_sketch_rows)
   DevBuf partial;              // split-K partial sums
   DevBuf vn1, vn2, lpos, fpend; // QRCP per-column state
   DevBuf rec;                  // LL exchange records

@@ -295,3 +295,33 @@ def test_pipelined_upload_equals_plain_upload(ctx, m, n):
     assert np.max(np.abs(C @ T1 - C @ T0)) <= 1e-10 * np.linalg.norm(A, 2)
     F = brapprox.psvdfact(A, rtol=1e-10, seed=9, ctx=ctx)
     assert np.linalg.norm(A - F.matrix(), 2) <= 1e-8 * np.linalg.norm(A, 2)
+
+
+def test_nested_sketch_rounds(ctx, monkeypatch):
+    """Fast mode: the rounds of the adaptive loop share their Omega rows (round t = round t-1's rows + fresh ones), so the
+    library multiplies max(order) rows with A where the reference schedule multiplies sum(order); BRA_SKETCH_FRESH=1
+    restores independent draws per round.  Both satisfy the reference's error inequality with the same round structure;
+    caller-supplied Omegas (parity mode) are multiplied round by round as given."""
+    import brapprox
+    A = o.decaying_matrix(1400, 1100, 200, 12.0, 200, seed=21)
+    nrm = np.linalg.norm(A, 2)
+    V = brapprox.idfact(A, rtol=1e-10, seed=3, ctx=ctx)
+    orders = [r[0] for r in V.rounds]
+    assert len(orders) >= 3
+    assert brapprox.lib.bra_debug_sketch_rows(ctx.handle) == max(orders)
+    assert np.linalg.norm(A - A[:, V.sk - 1] @ V.matrix(), 2) <= 1e3 * 1e-10 * nrm
+    monkeypatch.setenv("BRA_SKETCH_FRESH", "1")
+    W = brapprox.idfact(A, rtol=1e-10, seed=3, ctx=ctx)
+    monkeypatch.delenv("BRA_SKETCH_FRESH")
+    assert [r[0] for r in W.rounds] == orders
+    assert brapprox.lib.bra_debug_sketch_rows(ctx.handle) == sum(orders)
+    assert np.linalg.norm(A - A[:, W.sk - 1] @ W.matrix(), 2) <= 1e3 * 1e-10 * nrm
+    assert abs(len(W.sk) - len(V.sk)) <= 2
+    # the first round is the same in both (same stream, same rows): same k in round 1
+    assert V.rounds[0] == W.rounds[0]
+    # parity mode: every round's Omega is the caller's
+    rin = o.RandomInputs(6)
+    Vo = o.idfact(A, o.LRAOptions(rtol=1e-10), rin)
+    Vg = brapprox.idfact(A, brapprox.LRAOptions(rtol=1e-10), rand=rin.drawn, ctx=ctx)
+    np.testing.assert_array_equal(Vg.sk, Vo.sk)
+    assert brapprox.lib.bra_debug_sketch_rows(ctx.handle) == sum(r[0] for r in Vg.rounds)
