@@ -199,9 +199,10 @@ def hbm_peak():
 
 def ncu_traffic_per_launch():
     """dram__bytes_read.sum + dram__bytes_write.sum of the sketch GEMM from the committed `ncu --set full` capture
-    (profiles/r01e_gemm_sketch_raw.csv: one psvdfact at the C2 shape, five sketch launches), averaged per launch."""
+    (profiles/r02e_gemm_sketch_raw.csv: one psvdfact at the C2 shape, the five nested-sketch launches of 40, 32, 64, 128
+    and 256 new rows), averaged per launch."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r01e_gemm_sketch_raw.csv")
+    path = os.path.join(ROOT, "profiles", "r02e_gemm_sketch_raw.csv")
     try:
         rows = list(csv.reader(open(path)))
         H, U = rows[0], rows[1]
@@ -760,7 +761,8 @@ def main():
                           "share_of_step": gemm_ms / args.steps / (1e3 * tmax / args.steps),
                           "traffic": ncu_traffic_per_launch()[0],
                           "traffic_note": "DRAM bytes per launch, mean over the 5 sketch launches of one factorization "
-                                          "(ncu --set full); algorithmic: 537 MB of A + l x 8192 x 16 B",
+                                          "(ncu --set full, profiles/r02e_gemm_sketch_raw.csv: 0.54 GB for the launches of <= 64 new rows, "
+                                          "0.92 / 1.41 GB for 128 / 256 rows); algorithmic: 537 MB of A + rows x 8192 x 16 B",
                           "algorithmic_flops_per_step": f_sk_exec, "launches": gemm_calls, "ms_total": gemm_ms},
                          {"kernel": "qrcp_fast_kernel (persistent warp-specialised pivoted QR)", "bound": "latency",
                           "us_per_pivot_step": 1e3 * prof["qrcp"][0] / args.steps / max(1, sum(steps)),
