@@ -73,6 +73,12 @@ typedef struct bra_ctx bra_ctx;
  * three *_samp closures cannot cross a C ABI: the shim evaluates them into the
  * affine pair (samp_a, samp_b), order = samp_a*n + samp_b, or passes explicit
  * per-round orders in bra_rand.orders. */
+/* bra_opts.flags.  BRA_OPT_FRESH_SKETCH: with the library's own random numbers, draw every adaptive round's Gaussian
+ * Omega independently, like the reference (src/sketch.jl:223-240), instead of nesting the rounds (round t = round t-1's
+ * rows + fresh ones, only the new rows are multiplied with A; see bra_debug_sketch_rows).  The environment variable
+ * BRA_SKETCH_FRESH=1 sets it for every call. */
+#define BRA_OPT_FRESH_SKETCH 1
+
 typedef struct bra_opts {
   double atol;               /* >= 0 */
   double rtol;               /* >= 0; default 5*eps */
@@ -87,7 +93,7 @@ typedef struct bra_opts {
   int64_t samp_a, samp_b;    /* 0,0 = the reference default for opts.sketch */
   uint64_t seed;             /* fast mode: Philox key */
   int32_t verb;
-  int32_t reserved;
+  int32_t flags;             /* BRA_OPT_* bits; default 0 */
   double pheig_orthtol;      /* >= 0; default sqrt(eps): pheigorth! cluster tolerance (src/pheig.jl:342-364) */
 } bra_opts;
 

@@ -28,7 +28,7 @@ class bra_opts(C.Structure):
         ("sketch", C.c_int32), ("sketch_randn_niter", C.c_int32), ("sketchfact_adap", C.c_int32),
         ("retval_mask", C.c_int32), ("maxdet_tol", C.c_double), ("maxdet_niter", C.c_int64),
         ("samp_a", C.c_int64), ("samp_b", C.c_int64), ("seed", C.c_uint64), ("verb", C.c_int32),
-        ("reserved", C.c_int32), ("pheig_orthtol", C.c_double),
+        ("flags", C.c_int32), ("pheig_orthtol", C.c_double),
     ]
 
 
@@ -140,6 +140,7 @@ class LRAOptions:
     snorm_niter: int = 32
     verb: bool = True
     seed: int = 0            # fast-mode device RNG key (no reference counterpart: Julia's global RNG)
+    sketch_fresh: bool = False   # fast mode: independent Gaussian Omega per adaptive round (BRA_OPT_FRESH_SKETCH) instead of nested rounds
 
     @classmethod
     def for_eltype(cls, dtype, **kw) -> "LRAOptions":
@@ -197,6 +198,7 @@ class LRAOptions:
         o.seed = self.seed
         o.verb = int(bool(self.verb))
         o.pheig_orthtol = self.pheig_orthtol
+        o.flags = 1 if self.sketch_fresh else 0
         return o
 
 

@@ -415,6 +415,7 @@ void bra_opts_default(bra_opts* o) {
   o->samp_b = 0;
   o->seed = 0;
   o->verb = 1;
+  o->flags = 0;
   o->pheig_orthtol = 1.4901161193847656e-08;      // sqrt(eps(Float64)), src/LowRankApprox.jl:102
 }
 
@@ -736,7 +737,7 @@ int bra_trsolve_T_f64(bra_ctx* ctx, int64_t k, int64_t n, const double* R, int64
 // nested Gaussian sketches apply to the library's own Omega only (see sketch_randn_nested)
 bool bra_sketch_nested(const bra_opts* o, const bra_rand* rnd) {
   return o->sketch == BRA_SKETCH_RANDN && !(rnd && rnd->n_rounds > 0) && o->sketch_randn_niter == 0 &&
-         getenv("BRA_SKETCH_FRESH") == nullptr;
+         !(o->flags & BRA_OPT_FRESH_SKETCH) && getenv("BRA_SKETCH_FRESH") == nullptr;
 }
 
 // sketchfact(:left, trans, A, opts) + pqrback_postproc for retval "t"; shared by idfact/pqrfact/psvdfact.

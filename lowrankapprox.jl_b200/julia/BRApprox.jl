@@ -35,7 +35,7 @@ struct BraOpts                      # mirrors `bra_opts` (include/brapprox.h), f
   atol::Cdouble; rtol::Cdouble; rank::Int64; nb::Int64
   sketch::Int32; sketch_randn_niter::Int32; sketchfact_adap::Int32; retval_mask::Int32
   maxdet_tol::Cdouble; maxdet_niter::Int64; samp_a::Int64; samp_b::Int64
-  seed::UInt64; verb::Int32; reserved::Int32
+  seed::UInt64; verb::Int32; flags::Int32    # flags: BRA_OPT_FRESH_SKETCH = 1 (0: nested Gaussian sketches)
   pheig_orthtol::Cdouble
 end
 

@@ -310,9 +310,11 @@ def test_nested_sketch_rounds(ctx, monkeypatch):
     assert len(orders) >= 3
     assert brapprox.lib.bra_debug_sketch_rows(ctx.handle) == max(orders)
     assert np.linalg.norm(A - A[:, V.sk - 1] @ V.matrix(), 2) <= 1e3 * 1e-10 * nrm
+    W = brapprox.idfact(A, rtol=1e-10, seed=3, sketch_fresh=True, ctx=ctx)            # BRA_OPT_FRESH_SKETCH
     monkeypatch.setenv("BRA_SKETCH_FRESH", "1")
-    W = brapprox.idfact(A, rtol=1e-10, seed=3, ctx=ctx)
+    W2 = brapprox.idfact(A, rtol=1e-10, seed=3, ctx=ctx)                              # the same through the environment
     monkeypatch.delenv("BRA_SKETCH_FRESH")
+    np.testing.assert_array_equal(W2.sk, W.sk)
     assert [r[0] for r in W.rounds] == orders
     assert brapprox.lib.bra_debug_sketch_rows(ctx.handle) == sum(orders)
     assert np.linalg.norm(A - A[:, W.sk - 1] @ W.matrix(), 2) <= 1e3 * 1e-10 * nrm
