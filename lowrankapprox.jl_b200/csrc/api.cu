@@ -366,7 +366,7 @@ int sketch_round(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double* d
       BRA_CUDA(ctx->aux_in1.reserve((size_t)order * 8));
       BRA_CUDA(ctx->aux_in2.reserve((size_t)mA * 8));
       if ((rc = bra_fill_meta(ctx, 0, ctx->aux_in2.p, mA, 0, o->seed, (uint64_t)round))) return rc;
-      if ((rc = bra_fill_meta(ctx, 1, ctx->aux_in1.p, order, mA, o->seed, (uint64_t)round))) return rc;
+      if ((rc = bra_fill_meta(ctx, 3, ctx->aux_in1.p, order, mA, o->seed, (uint64_t)round))) return rc;
       d = ctx->aux_in2.p;
       idx = ctx->aux_in1.p;
     }

@@ -439,11 +439,67 @@ __device__ __forceinline__ uint64_t splitmix_at(uint64_t s0, uint64_t i) {      
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);
 }
+// kind 0: +-1 signs.  kind 1: `count` indices in 1..range (random subset).  kind 3: `count` SRFT index entries for an FFT of
+// length `range`.
+// The reference samples WITH replacement (rand(1:n, k), src/sketch.jl:252, 361).  For the random subset every duplicate
+// is a redundant sketch row.  For the real SRFT it is worse: srft_apply! (src/sketch.jl:396-447) turns the entries at the
+// ODD (1-based) positions of idx into TWO sketch rows each -- the real and the imaginary part of that frequency -- and
+// skips the entry behind it; frequencies f and n - f are complex conjugates, so a sample that holds both (or the same one
+// twice) gives four rows of rank two, and frequency 0 or n/2 gives a zero row.  Once k^2 approaches 4n the sketch loses
+// rank and the adaptive loop stops short of the requested accuracy (order 264 from n = 1326: rank 252 < 256 ->
+// "converged" at a tenth of the true rank's accuracy).  The library's own draws are therefore DISTINCT whenever enough
+// distinct values exist (and cover them all before repeating otherwise): kind 1 takes index i to its image under a keyed bijection of [0, range); kind 3 takes the
+// j-th USED entry to frequency 1 + (image of j under a keyed bijection of the (range - 1) / 2 conjugate classes,
+// DC and Nyquist excluded).  The bijection is a 4-round Feistel network on the smallest even number of bits that covers
+// the domain, cycle-walked back into it (< 4 steps expected).  Caller-supplied indices (parity mode) are used as given.
+__device__ __forceinline__ uint64_t keyed_bijection(uint64_t x, uint64_t domain, int h, uint64_t s0) {
+  const uint64_t mask = (uint64_t(1) << h) - 1;
+  do {
+    uint64_t L = x >> h, R = x & mask;
+#pragma unroll
+    for (int rd = 0; rd < 4; ++rd) {
+      const uint64_t f = splitmix_at(s0 + 0x632BE59BD9B4E019ull * (uint64_t)(rd + 1), R) & mask;
+      const uint64_t t = L ^ f;
+      L = R;
+      R = t;
+    }
+    x = (L << h) | R;
+  } while (x >= domain);
+  return x;
+}
+
 __global__ void meta_fill_kernel(int kind, void* __restrict__ dst, int64_t count, int64_t range, uint64_t s0) {
+  const int64_t classes = (range - 1) / 2;                       // kind 3: frequencies 1 .. classes
+  const int64_t domain = (kind == 3) ? classes : range;
+  // kind 3 with more used entries than conjugate classes (a sketch larger than the transform itself): the first
+  // `classes` entries cover every class once, then DC, then Nyquist, then the classes again
+  const bool distinct = (kind == 1 && count <= range) || (kind == 3 && classes >= 1);
+  int h = 1;
+  while (h < 31 && (int64_t(1) << (2 * h)) < domain) ++h;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
-    const uint64_t z = splitmix_at(s0, (uint64_t)i);
-    if (kind == 0) reinterpret_cast<double*>(dst)[i] = (z >> 63) ? 1.0 : -1.0;
-    else reinterpret_cast<int64_t*>(dst)[i] = (int64_t)__umul64hi(z, (uint64_t)range) + 1;
+    if (kind == 0) {
+      reinterpret_cast<double*>(dst)[i] = (splitmix_at(s0, (uint64_t)i) >> 63) ? 1.0 : -1.0;
+    } else if (!distinct || (kind == 3 && (i & 1))) {
+      // with replacement (and the entries of an SRFT index vector that srft_apply! never reads)
+      reinterpret_cast<int64_t*>(dst)[i] = (int64_t)__umul64hi(splitmix_at(s0, (uint64_t)i), (uint64_t)range) + 1;
+    } else if (kind == 1) {
+      reinterpret_cast<int64_t*>(dst)[i] = (int64_t)keyed_bijection((uint64_t)i, (uint64_t)domain, h, s0) + 1;
+    } else {
+      // 1-based index idx = frequency + 1
+      int64_t j = i >> 1, f;
+      if (j < classes) {
+        f = (int64_t)keyed_bijection((uint64_t)j, (uint64_t)domain, h, s0) + 1;
+      } else {
+        j -= classes;
+        const int64_t extra = 1 + ((range & 1) ? 0 : 1);           // DC, and Nyquist for an even length
+        const int64_t per = classes + extra;
+        const int64_t jj = j % per;
+        if (jj == 0) f = 0;
+        else if (jj == 1 && extra == 2) f = range / 2;
+        else f = (int64_t)keyed_bijection((uint64_t)(jj - extra), (uint64_t)domain, h, s0) + 1;
+      }
+      reinterpret_cast<int64_t*>(dst)[i] = f + 1;
+    }
   }
 }
 
@@ -585,7 +641,7 @@ int bra_sketch_srft(bra_ctx* ctx, const double* A, int64_t lda, int64_t mA, int6
 int bra_fill_meta(bra_ctx* ctx, int kind, void* dst_dev, int64_t count, int64_t range, uint64_t seed, uint64_t stream_id) {
   if (count <= 0) return BRA_OK;
   const uint64_t s0 = seed * 0x9E3779B97F4A7C15ull + stream_id * 0xD1B54A32D192ED03ull + (uint64_t)kind + 1;
-  if (kind == 0 || kind == 1) {
+  if (kind == 0 || kind == 1 || kind == 3) {
     const int64_t blocks = (count + 255) / 256;
     meta_fill_kernel<<<(unsigned)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, ctx->stream>>>(kind, dst_dev, count, range, s0);
     ctx->launches++;

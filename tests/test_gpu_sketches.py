@@ -115,3 +115,25 @@ def test_idfact_structured_fast_mode(ctx, kind):
     assert 20 <= V.k <= 80
     err = o.id_error(A, V)
     assert err <= 1e-5, err
+
+
+@pytest.mark.parametrize("kind", ["srft", "sub"])
+def test_fast_mode_indices_are_distinct(ctx, kind):
+    """The library's own SRFT frequencies / subset rows are drawn WITHOUT replacement (a keyed bijection of 1..n): the
+    reference's rand(1:n, k) (src/sketch.jl:252, 361) holds ~k^2/2n duplicates, each a redundant sketch row, and the
+    adaptive loop then stops short (order 264 from n = 1437: numerical rank ~240 < 256).  Here the factorization of a
+    rank-420 matrix must reach its accuracy."""
+    import brapprox
+    import lra_oracle as o
+    A = o.decaying_matrix(1437, 1230, 420, 4.6, 420, seed=77)
+    rtol = 5e-5
+    s = np.linalg.svd(A, compute_uv=False)
+    ktrue = int(np.sum(s > rtol * s[0]))
+    V = brapprox.idfact(A, rtol=rtol, sketch=kind, seed=11, ctx=ctx)
+    k = len(V.sk)
+    assert k >= ktrue - 5
+    if kind == "srft":
+        rec = np.zeros_like(A)
+        rec[:, V.sk - 1] = A[:, V.sk - 1]
+        rec[:, V.rd - 1] = A[:, V.sk - 1] @ V.T
+        assert np.linalg.norm(A - rec, 2) <= 1e3 * rtol * s[0]
