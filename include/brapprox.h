@@ -192,6 +192,12 @@ int bra_pqrfact_f64(bra_ctx* ctx, char trans, int64_t m, int64_t n, const double
 int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* opts,
                      const bra_rand* rnd);
 
+/* psvdvals(A, opts) (src/psvd.jl:274-290): the singular values of bra_psvdfact_f64 without its vectors (the explicit Q of
+ * the skeleton QR, the U and Vt products and the recovery of the rotations are skipped).  Fetch BRA_F_S
+ * (bra_get_info().ksvd values); BRA_F_U / BRA_F_VT answer BRA_ERR_NOTREADY. */
+int bra_psvdvals_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* opts,
+                     const bra_rand* rnd);
+
 /* pheigfact(A, opts) (src/pheig.jl:276-296) for a real symmetric n x n A (-3: "matrix must be Hermitian", :279):
  * idfact, QR of [I; T'] (one Cholesky pass), the k x k eigenproblem of R (A[sk,sk] R') on the device (one-sided
  * Jacobi + Rayleigh quotients), truncation with pheigrank (:322-341).  Fetch BRA_F_S (kk eigenvalues, ascending,

@@ -603,9 +603,18 @@ def psvd(A, *args, **kw):
     return F.U, F.S, F.Vt.T
 
 
-def psvdvals(A, *args, **kw):
-    """psvdvals(A, ...) (src/psvd.jl:274-290)."""
-    return psvdfact(A, *args, **kw).S
+@_eltype
+def psvdvals(A, opts: Optional[LRAOptions] = None, rand=None, ctx: Optional[Context] = None, **kw):
+    """psvdvals(A, opts; kw...) (src/psvd.jl:274-290): the singular values of psvdfact without its vectors
+    (bra_psvdvals_f64: no explicit Q, no U / Vt products)."""
+    o = _opts(opts, kw)
+    ctx = ctx or default_context()
+    pA, m, n, lda, keepA = mat_arg(A)
+    rp = _RandPack(rand, o, max(m, n))
+    co = o.to_c()
+    ctx.check(lib.bra_psvdvals_f64(ctx.handle, m, n, pA, lda, C.byref(co), C.byref(rp.c)))
+    ks = int(ctx.info().ksvd)
+    return ctx.fetch(B.F_S, (ks,)) if ks else np.zeros(0)
 
 
 def _dev(a):

@@ -1211,7 +1211,7 @@ int bra_fetch(bra_ctx* ctx, int which, void* dst, int64_t ld) {
       BRA_CUDA(copy2d(ctx, dst, ld, ctx->Rfull.p, k, k, n));
       break;
     case BRA_F_U:
-      if (!r.have_svd) return BRA_ERR_NOTREADY;
+      if (!r.have_svd || r.svd_vals_only) return BRA_ERR_NOTREADY;
       BRA_CHECK_ARG(ld >= (r.svd_m > 1 ? r.svd_m : 1), 4, "ld");
       BRA_CUDA(copy2d(ctx, dst, ld, ctx->U.p, r.svd_m, r.svd_m, r.ksvd));
       break;
@@ -1220,7 +1220,7 @@ int bra_fetch(bra_ctx* ctx, int which, void* dst, int64_t ld) {
       BRA_CUDA(cudaMemcpyAsync(dst, ctx->S.p, (size_t)r.ksvd * 8, cudaMemcpyDefault, ctx->stream));
       break;
     case BRA_F_VT:
-      if (!r.have_svd) return BRA_ERR_NOTREADY;
+      if (!r.have_svd || r.svd_vals_only) return BRA_ERR_NOTREADY;
       BRA_CHECK_ARG(ld >= (r.ksvd > 1 ? r.ksvd : 1), 4, "ld");
       BRA_CUDA(copy2d(ctx, dst, ld, ctx->Vt.p, r.ksvd, r.ksvd, r.svd_n));
       break;

@@ -284,8 +284,23 @@ int bra_sketchfact_f64(bra_ctx* ctx, char side, char trans, int64_t m, int64_t n
   }
 }
 
+static int psvd_impl(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* opts,
+                     const bra_rand* rnd, bool vals_only);
+
 int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* opts,
                      const bra_rand* rnd) {
+  return psvd_impl(ctx, m, n, A, lda, opts, rnd, false);
+}
+
+// psvdvals(A, opts) (src/psvd.jl:274-290): the same idfact, skeleton QR and core SVD, but neither Q nor the singular
+// vectors are formed -- only BRA_F_S (and bra_get_info().ksvd) are valid afterwards.
+int bra_psvdvals_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* opts,
+                     const bra_rand* rnd) {
+  return psvd_impl(ctx, m, n, A, lda, opts, rnd, true);
+}
+
+static int psvd_impl(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* opts,
+                     const bra_rand* rnd, bool vals_only) {
   if (!ctx) return -1;
   const char trans = (m >= n) ? 'n' : 'c';                              // src/psvd.jl:242,256
   int rc = bra_check_fact_args(ctx, trans, m, n, A, lda, opts);
@@ -302,6 +317,7 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
   res.ksvd = 0;
   res.svd_m = m;
   res.svd_n = n;
+  res.svd_vals_only = vals_only;
   if (k == 0) {
     res.have_svd = true;
     return BRA_OK;
@@ -386,7 +402,9 @@ skeleton_again:
   BRA_CUDA(ctx->Qt_l1.reserve((size_t)ldk * std::max(mA, nA) * 8));
   BRA_CUDA(ctx->rinv.reserve((size_t)ldk * k * 8));
   BRA_CUDA(ctx->yt.reserve((size_t)2 * ldk * mA * 8));
-  if (explicit_qz) {
+  if (vals_only) {
+    // no singular vectors: Q = Y1 R_y2^{-1} is never needed
+  } else if (explicit_qz) {
     if ((rc = finish_skeleton_q(ctx, mA, k))) return rc;       // the robust Z path below reuses ctx->scratch / rinv / yt
   } else {
     if ((rc = bra_lane_fork(ctx))) return rc;
@@ -465,6 +483,12 @@ skeleton_again:
     std::memcpy(hsrt, ssort.data(), (size_t)k * 8);
     BRA_CUDA(cudaMemcpyAsync(ctx->aux_in1.p, ho, (size_t)k * 4, cudaMemcpyHostToDevice, ctx->stream));
     BRA_CUDA(cudaMemcpyAsync(Ssorted, hsrt, (size_t)k * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (vals_only) {
+    BRA_CUDA(cudaMemcpyAsync(ctx->S.p, Ssorted, (size_t)kk * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    res.have_svd = true;
+    BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BRA_OK;
   }
 
   // Ut (kk x mA) = Jsel' Q'   and   Vp (kk x nA) = Ysel' Qz'   -- both on the TMA + DMMA kernel (TN form)

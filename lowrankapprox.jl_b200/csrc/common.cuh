@@ -60,6 +60,7 @@ struct FactResult {
   int64_t ldT = 0;             // leading dimension of ctx->T (k rounded up to even: keeps the TMA GEMM path open)
   int64_t svd_m = 0, svd_n = 0;  // dims of the ORIGINAL A for psvdfact's U (svd_m x ksvd) and Vt (ksvd x svd_n)
   bool have_T = false, have_Q = false, have_R = false, have_svd = false;
+  bool svd_vals_only = false;  // psvdvals: only BRA_F_S is valid
   bool maxdet_done = false;    // maxdet swapped columns: R11 no longer belongs to the skeleton (tails must not use it)
 };
 

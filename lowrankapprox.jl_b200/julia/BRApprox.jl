@@ -216,12 +216,18 @@ function sketchfact(side::Symbol, trans::Symbol, A::Matrix{Float64}, opts::LRAOp
 end
 
 # ---- psvdfact / psvdvals / psvd (src/psvd.jl:238-299) ---------------------------------------------------------
-function psvd_call(A::Matrix{Float64}, opts::LRAOptions)
+function psvd_call(A::Matrix{Float64}, opts::LRAOptions; vals_only::Bool=false)
   m, n = size(A)
   with_random_inputs(opts, max(m, n)) do rnd          # trans = :n if m >= n else :c (src/psvd.jl:242,256)
-    ccall((:bra_psvdfact_f64, libbra), Cint,
-          (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Ref{BraOpts}, Ref{BraRand}),
-          CTX[], m, n, A, stride(A, 2), BraOpts(opts), rnd)
+    if vals_only                                      # psvdvals: no Q, no singular vectors
+      ccall((:bra_psvdvals_f64, libbra), Cint,
+            (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Ref{BraOpts}, Ref{BraRand}),
+            CTX[], m, n, A, stride(A, 2), BraOpts(opts), rnd)
+    else
+      ccall((:bra_psvdfact_f64, libbra), Cint,
+            (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Ref{BraOpts}, Ref{BraRand}),
+            CTX[], m, n, A, stride(A, 2), BraOpts(opts), rnd)
+    end
   end
 end
 function psvdfact(A::Matrix{Float64}, opts::LRAOptions=LRAOptions(); args...)
@@ -237,7 +243,7 @@ end
 function psvdvals(A::Matrix{Float64}, opts::LRAOptions=LRAOptions(); args...)
   opts = copy(opts; args...)
   chkopts!(opts, A)
-  check(psvd_call(A, opts))
+  check(psvd_call(A, opts; vals_only=true))
   k = getinfo().ksvd
   fetch!(F_S, Vector{Float64}(undef, k), k)
 end

@@ -362,3 +362,22 @@ def test_pheigfact_core_beyond_1024(ctx):
     assert F.k_id > 1024 and kk > 1024
     assert np.linalg.norm(F.vectors.T @ F.vectors - np.eye(kk)) <= 1e-9
     assert np.linalg.norm(A - (F.vectors * F.values) @ F.vectors.T, 2) <= 1e-7
+
+
+def test_psvdvals_skips_the_vectors(ctx):
+    """psvdvals (src/psvd.jl:274-290) = the singular values of psvdfact on the same random inputs; the vectors are not
+    formed (fetching them answers BRA_ERR_NOTREADY)."""
+    import brapprox
+    from brapprox import _binding as Bd
+    for (m, n) in ((900, 700), (500, 820)):
+        A = o.decaying_matrix(m, n, 90, 12.0, 90, seed=m)
+        rin = o.RandomInputs(3)
+        Fo = o.psvdfact(A, o.LRAOptions(rtol=1e-10), rin)
+        F = brapprox.psvdfact(A, brapprox.LRAOptions(rtol=1e-10), rand=rin.drawn, ctx=ctx)
+        s = brapprox.psvdvals(A, brapprox.LRAOptions(rtol=1e-10), rand=rin.drawn, ctx=ctx)
+        assert len(s) == len(Fo.S)
+        np.testing.assert_array_equal(s, F.S)
+        assert np.max(np.abs(s - Fo.S)) <= 1e-10 * Fo.S[0]
+        with pytest.raises(Bd.BraError):
+            ctx.fetch(Bd.F_U, (m, len(s)))
+    assert brapprox.psvdvals(A.astype(np.float32), seed=1, ctx=ctx).dtype == np.float32
