@@ -198,6 +198,16 @@ int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
 int bra_psvdvals_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* opts,
                      const bra_rand* rnd);
 
+/* Host destinations for the factors of the NEXT bra_psvdfact_f64 on this context (one shot; cleared when that call
+ * returns).  U: column-major, ldu >= m, room for ucols columns; S: room for scap values; Vt: leading dimension ldvt
+ * (usable when the rank found is <= ldvt).  A factor that fits is copied to the host inside the call, on the stream
+ * that produced it -- the copy of the factor that is ready first overlaps the rest of the computation -- and
+ * bra_psvd_outputs_done() reports which ones were written (bit 0: U, bit 1: S, bit 2: Vt); the others are fetched with
+ * bra_fetch as usual.  Any pointer may be NULL.  Pinned host memory keeps the copies asynchronous. */
+int bra_psvd_set_outputs(bra_ctx* ctx, double* U, int64_t ldu, int64_t ucols, double* S, int64_t scap, double* Vt,
+                         int64_t ldvt);
+int bra_psvd_outputs_done(bra_ctx* ctx);
+
 /* pheigfact(A, opts) (src/pheig.jl:276-296) for a real symmetric n x n A (-3: "matrix must be Hermitian", :279):
  * idfact, QR of [I; T'] (one Cholesky pass), the k x k eigenproblem of R (A[sk,sk] R') on the device (one-sided
  * Jacobi + Rayleigh quotients), truncation with pheigrank (:322-341).  Fetch BRA_F_S (kk eigenvalues, ascending,

@@ -109,6 +109,8 @@ lib.bra_snorm_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, 
                               C.POINTER(C.c_double), C.POINTER(_i64)]
 lib.bra_psvdfact_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand)]
 lib.bra_psvdvals_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand)]
+lib.bra_psvd_set_outputs.argtypes = [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64]
+lib.bra_psvd_outputs_done.argtypes = [_vp]
 lib.bra_get_info.argtypes = [_vp, C.POINTER(bra_info)]
 lib.bra_fetch.argtypes = [_vp, C.c_int, _vp, _i64]
 lib.bra_profile_enable.argtypes = [_vp, C.c_int]

@@ -552,15 +552,31 @@ def psvdfact(A, opts: Optional[LRAOptions] = None, rand=None, ctx: Optional[Cont
     returned factors are views of them."""
     ctx = ctx or default_context()
     pA, m, n, lda, keepA = mat_arg(A)
+    oU, oS, oV = out if out is not None else (None, None, None)
+    if out is not None:
+        # register the caller's buffers: each factor is copied out inside the call, as soon as it exists
+        # (bra_psvd_set_outputs); what did not fit or was not registered is fetched below
+        def _ok(a, nd):
+            return (a is not None and a.dtype == np.float64 and a.ndim == nd and a.strides[0] == a.itemsize
+                    and a.flags.writeable)
+        uo = oU if _ok(oU, 2) and oU.shape[0] >= m else None
+        so = oS if _ok(oS, 1) else None
+        vo = oV if _ok(oV, 2) and oV.shape[1] >= n else None
+        lib.bra_psvd_set_outputs(
+            ctx.handle, C.c_void_p(uo.ctypes.data if uo is not None else None),
+            (uo.strides[1] // 8 if uo is not None and uo.shape[1] > 1 else max(m, 1)), (uo.shape[1] if uo is not None else 0),
+            C.c_void_p(so.ctypes.data if so is not None else None), (so.shape[0] if so is not None else 0),
+            C.c_void_p(vo.ctypes.data if vo is not None else None),
+            (vo.strides[1] // 8 if vo is not None and vo.shape[1] > 1 else (vo.shape[0] if vo is not None else 0)))
     psvdfact_device(A, opts, rand, ctx, **kw)
+    done = int(lib.bra_psvd_outputs_done(ctx.handle)) if out is not None else 0
     inf, rounds, steps = _rounds(ctx)
     ks = int(inf.ksvd)
     if ks == 0:
         return B.PartialSVD(np.zeros((m, 0)), np.zeros(0), np.zeros((0, n)), int(inf.k), rounds)
-    oU, oS, oV = out if out is not None else (None, None, None)
-    U = ctx.fetch(B.F_U, (m, ks), out=oU)
-    S = ctx.fetch(B.F_S, (ks,), out=oS)
-    Vt = ctx.fetch(B.F_VT, (ks, n), out=oV)
+    U = oU[:m, :ks] if done & 1 else ctx.fetch(B.F_U, (m, ks), out=oU)
+    S = oS[:ks] if done & 2 else ctx.fetch(B.F_S, (ks,), out=oS)
+    Vt = oV[:ks, :n] if done & 4 else ctx.fetch(B.F_VT, (ks, n), out=oV)
     return B.PartialSVD(U, S, Vt, int(inf.k), rounds)
 
 

@@ -287,6 +287,26 @@ int bra_sketchfact_f64(bra_ctx* ctx, char side, char trans, int64_t m, int64_t n
 static int psvd_impl(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* opts,
                      const bra_rand* rnd, bool vals_only);
 
+// Host destinations for the factors of the NEXT bra_psvdfact_f64 on this context (one shot).  U: column-major, leading
+// dimension ldu >= m, room for ucols columns; S: room for scap values; Vt: leading dimension ldvt (>= the rank found).
+// A factor that fits is copied to the host inside the call -- on the stream that produced it, so the copy of the
+// factor that is ready first overlaps the rest of the computation -- and bra_psvd_outputs_done reports which ones were
+// written (bit 0: U, 1: S, 2: Vt); the others are fetched with bra_fetch as usual.  Pinned memory keeps the copies
+// asynchronous.
+int bra_psvd_set_outputs(bra_ctx* ctx, double* U, int64_t ldu, int64_t ucols, double* S, int64_t scap, double* Vt,
+                         int64_t ldvt) {
+  if (!ctx) return -1;
+  ctx->out_U = U;
+  ctx->out_ldu = ldu;
+  ctx->out_ucols = ucols;
+  ctx->out_S = S;
+  ctx->out_scap = scap;
+  ctx->out_Vt = Vt;
+  ctx->out_ldvt = ldvt;
+  return BRA_OK;
+}
+int bra_psvd_outputs_done(bra_ctx* ctx) { return ctx ? ctx->out_done : -1; }
+
 int bra_psvdfact_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* opts,
                      const bra_rand* rnd) {
   return psvd_impl(ctx, m, n, A, lda, opts, rnd, false);
@@ -302,6 +322,11 @@ int bra_psvdvals_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
 static int psvd_impl(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const bra_opts* opts,
                      const bra_rand* rnd, bool vals_only) {
   if (!ctx) return -1;
+  ctx->out_done = 0;
+  struct OutGuard {                       // registered host outputs are for this call only, however it ends
+    bra_ctx* c;
+    ~OutGuard() { c->out_U = c->out_S = c->out_Vt = nullptr; }
+  } out_guard{ctx};
   const char trans = (m >= n) ? 'n' : 'c';                              // src/psvd.jl:242,256
   int rc = bra_check_fact_args(ctx, trans, m, n, A, lda, opts);
   if (rc) return rc;
@@ -318,6 +343,23 @@ static int psvd_impl(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
   res.svd_m = m;
   res.svd_n = n;
   res.svd_vals_only = vals_only;
+  // copy a finished factor to its registered host destination on the CURRENT stream (main or side lane)
+  auto emit_U = [&](int64_t kk_) -> int {
+    if (ctx->out_U && kk_ <= ctx->out_ucols && ctx->out_ldu >= m) {
+      BRA_CUDA(cudaMemcpy2DAsync(ctx->out_U, (size_t)ctx->out_ldu * 8, ctx->U.p, (size_t)m * 8, (size_t)m * 8, (size_t)kk_,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->out_done |= 1;
+    }
+    return BRA_OK;
+  };
+  auto emit_Vt = [&](int64_t kk_) -> int {
+    if (ctx->out_Vt && kk_ <= ctx->out_ldvt) {
+      BRA_CUDA(cudaMemcpy2DAsync(ctx->out_Vt, (size_t)ctx->out_ldvt * 8, ctx->Vt.p, (size_t)kk_ * 8, (size_t)kk_ * 8, (size_t)n,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->out_done |= 4;
+    }
+    return BRA_OK;
+  };
   if (k == 0) {
     res.have_svd = true;
     return BRA_OK;
@@ -518,10 +560,12 @@ skeleton_again:
     if (trans == 'n') {
       rc = bra_transpose(ctx, Uop_t, even(kk), kk, mA, ctx->U.as<double>(), mA);      // U (m x kk)
       if (rc) return rc;
+      if ((rc = emit_U(kk))) return rc;
     } else {
       // op(A) = A': A ~ Vop S Uop'  =>  Vt = Uop' (kk x n), ld = kk
       BRA_CUDA(cudaMemcpy2DAsync(ctx->Vt.p, (size_t)kk * 8, Uop_t, (size_t)even(kk) * 8, (size_t)kk * 8, (size_t)mA,
                                  cudaMemcpyDeviceToDevice, ctx->stream));
+      if ((rc = emit_Vt(kk))) return rc;
     }
   }
   // right factor of op(A):  Vop' = Ysel' Qz' P'   with Ysel = X[:, order] / sigma
@@ -570,12 +614,18 @@ skeleton_again:
   if (trans == 'n') {
     BRA_CUDA(cudaMemcpy2DAsync(ctx->Vt.p, (size_t)kk * 8, Out, (size_t)even(kk) * 8, (size_t)kk * 8, (size_t)nA,
                                cudaMemcpyDeviceToDevice, ctx->stream));
+    if ((rc = emit_Vt(kk))) return rc;
   } else {
     rc = bra_transpose(ctx, Out, even(kk), kk, nA, ctx->U.as<double>(), nA);        // U = Vop (m x kk), m == nA
     if (rc) return rc;
+    if ((rc = emit_U(kk))) return rc;
   }
   // singular values, sorted
   BRA_CUDA(cudaMemcpyAsync(ctx->S.p, Ssorted, (size_t)kk * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (ctx->out_S && kk <= ctx->out_scap) {
+    BRA_CUDA(cudaMemcpyAsync(ctx->out_S, ctx->S.p, (size_t)kk * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->out_done |= 2;
+  }
   res.have_svd = true;
   // bra_fetch reports U as m x ksvd and Vt as ksvd x n of the ORIGINAL A
   res.svd_m = m;

@@ -82,6 +82,11 @@ struct bra_ctx {
   DevBuf B;                    // sketch, l x n (col-major, ld = l)
   DevBuf B2;                   // permuted copy / scratch
   DevBuf Bnew, Braw;           // nested Gaussian sketches: the new rows of a round, the raw (unfactored) rows so far
+  // one-shot host destinations of the next psvdfact (bra_psvd_set_outputs): each factor is copied out on the stream
+  // that produced it, as soon as it exists, instead of by bra_fetch after the call
+  double* out_U = nullptr; double* out_S = nullptr; double* out_Vt = nullptr;
+  int64_t out_ldu = 0, out_ucols = 0, out_ldvt = 0, out_scap = 0;
+  int out_done = 0;               // bit 0: U, 1: S, 2: Vt written by the last psvdfact
   int64_t sketch_rows_done = 0;   // rows of Omega multiplied with op(A) by the last factorization (bra_debug_sketch_rows)
   DevBuf partial;              // split-K partial sums
   DevBuf vn1, vn2, lpos, fpend; // QRCP per-column state

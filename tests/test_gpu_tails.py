@@ -206,6 +206,19 @@ def test_psvdfact_into_caller_buffers(ctx):
     np.testing.assert_array_equal(F1.S, F0.S)
     np.testing.assert_array_equal(F1.U, F0.U)
     np.testing.assert_array_equal(F1.Vt, F0.Vt)
+    # the buffers were registered with the library (bra_psvd_set_outputs) and filled inside the call, each factor as soon
+    # as it existed; the registration is one shot
+    assert brapprox.lib.bra_psvd_outputs_done(ctx.handle) == 7
+    brapprox.psvdfact(A, rtol=1e-9, seed=4, ctx=ctx)
+    assert brapprox.lib.bra_psvd_outputs_done(ctx.handle) == 0
+    # wide matrix (factors A'): U and Vt swap lanes
+    Aw = np.asfortranarray(A.T)
+    G0 = brapprox.psvdfact(Aw, rtol=1e-9, seed=4, ctx=ctx)
+    Ub2, Vb2 = np.zeros((260, 64), order="F"), np.zeros((64, 320), order="F")
+    G1 = brapprox.psvdfact(Aw, rtol=1e-9, seed=4, ctx=ctx, out=(Ub2, Sb, Vb2))
+    assert brapprox.lib.bra_psvd_outputs_done(ctx.handle) == 7
+    np.testing.assert_array_equal(G1.U, G0.U)
+    np.testing.assert_array_equal(G1.Vt, G0.Vt)
     with pytest.raises(ValueError):
         brapprox.psvdfact(A, rtol=1e-9, seed=4, ctx=ctx, out=(np.zeros((320, 4), order="F"), Sb, Vb))
 
