@@ -1,5 +1,6 @@
+"""On-box timing of psvdvals (no Q, no singular vectors) against psvdfact on the C2 matrix.  Not a benchmark."""
 import sys, os, time
-sys.path.insert(0, "/root/repo/lowrankapprox.jl_b200")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lowrankapprox.jl_b200"))
 import numpy as np, torch, brapprox
 from brapprox._binding import DeviceMatrix
 from brapprox import _binding as B
