@@ -202,3 +202,45 @@ def test_float32_default_options_and_rounding():
     F = fe._narrow(brapprox.PQRFactors(None, np.eye(2), np.array([1, 2]), 2, None))
     assert F.Q is None and F.R.dtype == np.float32 and F.k == 2
     assert fe._is_f32(np.zeros((2, 2), np.float32)) and not fe._is_f32(np.zeros((2, 2)))
+
+
+def test_eltype_wrapper_dispatch_without_gpu():
+    """The element-type wrapper of the front-ends (f(A::AbstractMatOrLinOp{T}, opts = LRAOptions(T); ...)): a Float32 A
+    gets the LRAOptions(Float32) defaults only when no options are passed, keyword arguments still win, the matrix goes
+    through Context.widen_f32, FP64 results are rounded; a Float64 A passes through untouched."""
+    import brapprox
+    from brapprox import _frontend as fe
+    seen = {}
+
+    class FakeCtx:
+        def widen_f32(self, A):
+            seen["widened"] = A.dtype
+            return "device-matrix"
+
+    @fe._eltype
+    def f(A, opts=None, ctx=None, **kw):
+        o = fe._opts(opts, kw)
+        seen["A"], seen["rtol"], seen["orth"] = A, o.rtol, o.pheig_orthtol
+        return brapprox.IDPackedV(np.array([1]), np.array([2]), np.ones((1, 1)))
+
+    @fe._eltype
+    def g(A, rows, ctx=None):                      # no `opts` parameter (CUR)
+        seen["A"] = A
+        return np.ones(2)
+
+    e32, e64 = float(np.finfo(np.float32).eps), float(np.finfo(np.float64).eps)
+    A32, A64 = np.zeros((3, 2), np.float32), np.zeros((3, 2))
+    out = f(A32, ctx=FakeCtx())
+    assert seen["A"] == "device-matrix" and seen["widened"] == np.float32 and out.T.dtype == np.float32
+    assert seen["rtol"] == 5 * e32 and seen["orth"] == float(np.sqrt(e32))
+    f(A32, ctx=FakeCtx(), rtol=1e-3)
+    assert seen["rtol"] == 1e-3 and seen["orth"] == float(np.sqrt(e32))
+    f(A32, brapprox.LRAOptions(rtol=1e-9), ctx=FakeCtx())
+    assert seen["rtol"] == 1e-9 and seen["orth"] == float(np.sqrt(e64))            # explicit options are taken as given
+    f(A32, None, ctx=FakeCtx())
+    assert seen["rtol"] == 5 * e32
+    out = f(A64, ctx=FakeCtx())
+    assert seen["A"] is A64 and seen["rtol"] == 5 * e64 and out.T.dtype == np.float64
+    assert g(A32, [1], ctx=FakeCtx()).dtype == np.float32 and seen["A"] == "device-matrix"
+    with pytest.raises(TypeError):
+        f(A32, ctx=FakeCtx(), out=(None, None, None))
