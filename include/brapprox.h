@@ -240,6 +240,13 @@ int bra_cur_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda
  * (src/sketch.jl:223-240 draws every round afresh); caller-supplied Omegas, power iterations and BRA_SKETCH_FRESH=1
  * keep the round-by-round products. */
 int64_t bra_debug_sketch_rows(bra_ctx* ctx);
+/* The library's own random numbers (test hooks: a fast-mode factorization can be replayed through a CPU oracle on the
+ * very same inputs).  bra_debug_randn: `count` values of the Gaussian stream (seed, stream_id); row i of the fresh Omega
+ * rows of adaptive round t is values [i*ldt, i*ldt + m) of stream t, ldt = m rounded up to even.  bra_debug_meta: the
+ * 8-byte entries of kind 0 (+-1.0 SRFT signs), 1 (distinct subset rows, int64), 2 (permutation, int64), 3 (SRFT index
+ * vector, int64) for (seed, stream_id = round). */
+int bra_debug_randn(bra_ctx* ctx, double* host_out, int64_t count, uint64_t seed, uint64_t stream_id);
+int bra_debug_meta(bra_ctx* ctx, int kind, void* host_out, int64_t count, int64_t range, uint64_t seed, uint64_t stream_id);
 
 /* Float32 matrices.  The reference is generic in the element type T (LRAOptions(T), src/LowRankApprox.jl:96-118;
  * pqrfact / idfact / psvdfact / ... take AbstractMatOrLinOp{T}); the kernels here are FP64.  bra_widen_f32 uploads a

@@ -103,6 +103,8 @@ lib.bra_widen_f32.argtypes = [_vp, _i64, _i64, _vp, _i64, _vp, _vp]
 lib.bra_widen_f32.restype = C.c_int
 lib.bra_debug_sketch_rows.argtypes = [_vp]
 lib.bra_debug_sketch_rows.restype = C.c_int64
+lib.bra_debug_randn.argtypes = [_vp, _vp, _i64, C.c_uint64, C.c_uint64]
+lib.bra_debug_meta.argtypes = [_vp, C.c_int, _vp, _i64, _i64, C.c_uint64, C.c_uint64]
 lib.bra_prange_f64.argtypes = [_vp, C.c_char, _i64, _i64, _vp, _i64, C.POINTER(bra_opts), C.POINTER(bra_rand),
                                C.POINTER(bra_rand)]
 lib.bra_snorm_f64.argtypes = [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _i64, C.POINTER(bra_opts), _i64, _vp,

@@ -1152,6 +1152,31 @@ int bra_widen_f32(bra_ctx* ctx, int64_t m, int64_t n, const float* A, int64_t ld
 
 int64_t bra_debug_sketch_rows(bra_ctx* ctx) { return ctx ? ctx->sketch_rows_done : -1; }
 
+// The library's own random numbers, for tests that replay a fast-mode factorization through the oracle:
+// bra_debug_randn = `count` values of the Gaussian stream (seed, stream_id) -- row i of a round's fresh Omega rows is
+// values [i * ldt, i * ldt + m) with ldt = m rounded up to even; bra_debug_meta = the 8-byte entries bra_fill_meta
+// generates (kind 0: +-1.0 signs; 1: distinct subset rows; 2: permutation; 3: SRFT index vector), see sketch_round.
+int bra_debug_randn(bra_ctx* ctx, double* host_out, int64_t count, uint64_t seed, uint64_t stream_id) {
+  if (!ctx || !host_out || count < 0) return -1;
+  BRA_CUDA(cudaSetDevice(ctx->device));
+  BRA_CUDA(ctx->scratch2.reserve((size_t)(count > 0 ? count : 1) * 8));
+  int rc = bra_fill_randn(ctx, ctx->scratch2.as<double>(), count, seed, stream_id);
+  if (rc) return rc;
+  BRA_CUDA(cudaMemcpyAsync(host_out, ctx->scratch2.p, (size_t)count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BRA_OK;
+}
+int bra_debug_meta(bra_ctx* ctx, int kind, void* host_out, int64_t count, int64_t range, uint64_t seed, uint64_t stream_id) {
+  if (!ctx || !host_out || count < 0 || kind < 0 || kind > 3) return -1;
+  BRA_CUDA(cudaSetDevice(ctx->device));
+  BRA_CUDA(ctx->scratch2.reserve((size_t)(count > 0 ? count : 1) * 8));
+  int rc = bra_fill_meta(ctx, kind, ctx->scratch2.p, count, range, seed, stream_id);
+  if (rc) return rc;
+  BRA_CUDA(cudaMemcpyAsync(host_out, ctx->scratch2.p, (size_t)count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  BRA_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BRA_OK;
+}
+
 int bra_get_info(bra_ctx* ctx, bra_info* info) {
   if (!ctx) return -1;
   BRA_CHECK_ARG(info != nullptr, 2, "info");
