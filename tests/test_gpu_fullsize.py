@@ -62,6 +62,28 @@ def test_c2_psvdfact_full_size(ctx):
     assert eg <= 2 * eo + 1e-15, (eg, eo)
 
 
+def test_c2_fast_mode_full_size_replayed_through_the_oracle(ctx):
+    """The benchmark's own configuration -- fast mode, the library's nested device Omega, A host-resident (pipelined
+    upload with the stacked speculative sketch) -- replayed through the oracle on the random numbers read back from the
+    library (tests/test_gpu_fastmode_replay.py): rounds, k, p exact, C T within 1e-10, psvd values within 1e-10."""
+    import brapprox
+    from test_gpu_fastmode_replay import DeviceDraws
+    A = o.decaying_matrix(8192, 8192, RANK_GEN, DECADES, JDIV, seed=1)
+    seed = 2024
+    Vg = brapprox.idfact(A, rtol=RTOL, seed=seed, ctx=ctx)
+    assert brapprox.lib.bra_debug_sketch_rows(ctx.handle) == 520          # nested: max, not sum, of the orders
+    Vo = o.idfact(A, o.LRAOptions(rtol=RTOL), DeviceDraws(ctx, seed))
+    assert [l for l, _ in Vo.rounds] == [40, 72, 136, 264, 520]
+    _check_id(A, Vo, Vg)
+    Fg = brapprox.psvdfact(A, rtol=RTOL, seed=seed, ctx=ctx)
+    Fo = o.psvdfact(A, o.LRAOptions(rtol=RTOL), DeviceDraws(ctx, seed))
+    assert len(Fg.S) == len(Fo.S)
+    assert np.max(np.abs(Fg.S - Fo.S)) <= 1e-10 * Fo.S[0]
+    eo = o.snormdiff_lowrank(A, Fo.U * Fo.S, Fo.Vt)
+    eg = o.snormdiff_lowrank(A, Fg.U * Fg.S, Fg.Vt)
+    assert eg <= 2 * eo + 1e-15, (eg, eo)
+
+
 def test_c3_idfact_srft_full_size(ctx):
     import brapprox
     A = o.decaying_matrix(16384, 16384, RANK_GEN, DECADES, JDIV, seed=3)
