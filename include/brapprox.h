@@ -203,7 +203,9 @@ int bra_psvdvals_f64(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
  * (usable when the rank found is <= ldvt).  A factor that fits is copied to the host inside the call, on the stream
  * that produced it -- the copy of the factor that is ready first overlaps the rest of the computation -- and
  * bra_psvd_outputs_done() reports which ones were written (bit 0: U, bit 1: S, bit 2: Vt); the others are fetched with
- * bra_fetch as usual.  Any pointer may be NULL.  Pinned host memory keeps the copies asynchronous. */
+ * bra_fetch as usual.  Any pointer may be NULL.  Only page-locked (pinned) host memory is written inside the call (a copy
+ * into pageable memory would block the calling thread in the middle of the factorization); pageable destinations are
+ * ignored here and filled by bra_fetch. */
 int bra_psvd_set_outputs(bra_ctx* ctx, double* U, int64_t ldu, int64_t ucols, double* S, int64_t scap, double* Vt,
                          int64_t ldvt);
 int bra_psvd_outputs_done(bra_ctx* ctx);

@@ -291,17 +291,28 @@ static int psvd_impl(bra_ctx* ctx, int64_t m, int64_t n, const double* A, int64_
 // dimension ldu >= m, room for ucols columns; S: room for scap values; Vt: leading dimension ldvt (>= the rank found).
 // A factor that fits is copied to the host inside the call -- on the stream that produced it, so the copy of the
 // factor that is ready first overlaps the rest of the computation -- and bra_psvd_outputs_done reports which ones were
-// written (bit 0: U, 1: S, 2: Vt); the others are fetched with bra_fetch as usual.  Pinned memory keeps the copies
-// asynchronous.
+// written (bit 0: U, 1: S, 2: Vt); the others are fetched with bra_fetch as usual.  Only page-locked (pinned)
+// destinations are used.
 int bra_psvd_set_outputs(bra_ctx* ctx, double* U, int64_t ldu, int64_t ucols, double* S, int64_t scap, double* Vt,
                          int64_t ldvt) {
   if (!ctx) return -1;
-  ctx->out_U = U;
+  // only page-locked destinations: a copy into pageable memory blocks the calling thread until it is done, which would
+  // stall the enqueueing of the rest of the factorization -- such buffers are left to bra_fetch
+  auto pinned = [](const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+  };
+  ctx->out_U = pinned(U) ? U : nullptr;
   ctx->out_ldu = ldu;
   ctx->out_ucols = ucols;
-  ctx->out_S = S;
+  ctx->out_S = pinned(S) ? S : nullptr;
   ctx->out_scap = scap;
-  ctx->out_Vt = Vt;
+  ctx->out_Vt = pinned(Vt) ? Vt : nullptr;
   ctx->out_ldvt = ldvt;
   return BRA_OK;
 }

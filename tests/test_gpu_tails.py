@@ -206,16 +206,27 @@ def test_psvdfact_into_caller_buffers(ctx):
     np.testing.assert_array_equal(F1.S, F0.S)
     np.testing.assert_array_equal(F1.U, F0.U)
     np.testing.assert_array_equal(F1.Vt, F0.Vt)
-    # the buffers were registered with the library (bra_psvd_set_outputs) and filled inside the call, each factor as soon
-    # as it existed; the registration is one shot
+    # pageable buffers are filled by bra_fetch after the call; PINNED buffers are registered with the library
+    # (bra_psvd_set_outputs) and filled inside the call, each factor as soon as it exists; the registration is one shot
+    assert brapprox.lib.bra_psvd_outputs_done(ctx.handle) == 0
+    import torch
+    Up = torch.zeros((64, 320), dtype=torch.float64, pin_memory=True).numpy().T          # 320 x 64, column-major
+    Sp = torch.zeros((64,), dtype=torch.float64, pin_memory=True).numpy()
+    Vp = torch.zeros((260, 64), dtype=torch.float64, pin_memory=True).numpy().T          # 64 x 260, column-major
+    F2 = brapprox.psvdfact(A, rtol=1e-9, seed=4, ctx=ctx, out=(Up, Sp, Vp))
     assert brapprox.lib.bra_psvd_outputs_done(ctx.handle) == 7
+    assert np.shares_memory(F2.U, Up) and np.shares_memory(F2.Vt, Vp)
+    np.testing.assert_array_equal(F2.S, F0.S)
+    np.testing.assert_array_equal(F2.U, F0.U)
+    np.testing.assert_array_equal(F2.Vt, F0.Vt)
     brapprox.psvdfact(A, rtol=1e-9, seed=4, ctx=ctx)
     assert brapprox.lib.bra_psvd_outputs_done(ctx.handle) == 0
     # wide matrix (factors A'): U and Vt swap lanes
     Aw = np.asfortranarray(A.T)
     G0 = brapprox.psvdfact(Aw, rtol=1e-9, seed=4, ctx=ctx)
-    Ub2, Vb2 = np.zeros((260, 64), order="F"), np.zeros((64, 320), order="F")
-    G1 = brapprox.psvdfact(Aw, rtol=1e-9, seed=4, ctx=ctx, out=(Ub2, Sb, Vb2))
+    Up2 = torch.zeros((64, 260), dtype=torch.float64, pin_memory=True).numpy().T
+    Vp2 = torch.zeros((320, 64), dtype=torch.float64, pin_memory=True).numpy().T
+    G1 = brapprox.psvdfact(Aw, rtol=1e-9, seed=4, ctx=ctx, out=(Up2, Sp, Vp2))
     assert brapprox.lib.bra_psvd_outputs_done(ctx.handle) == 7
     np.testing.assert_array_equal(G1.U, G0.U)
     np.testing.assert_array_equal(G1.Vt, G0.Vt)
